@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt by running the UNMODIFIED reference
+(imported from /root/reference through oracle/ref_import.py) on seeded synthetic checkpoints,
+inputs and explicit noise.  Run in the build container:  python -m oracle.make_golden
+
+The reference ships no golden vectors, so these fixtures -- outputs of the
+reference's own `NVAEDefenseModel.__call__` (src/defenses/ours/abstract_models.py:161-193,
+models.py:160-274) and `CelebaIdentityClassifier` (models.py:40-58) -- are what pins the oracle
+and the CUDA path on the GPU box, where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+import os
+import shutil
+import sys
+import tempfile
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import                                    # noqa: E402
+from gen_adversarial_b200 import synth                           # noqa: E402
+from gen_adversarial_b200.nvae_spec import (NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION, tiny_config)  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SCRATCH = os.path.join(HERE, "_ref", "scratch")
+
+
+def cosine_alphas(n):   # src/experiments/alpha_learning/common_utils.py:20-22
+    return [0.5 * (1 - math.cos(math.pi * (i / n))) for i in range(1, n + 1)]
+
+
+def linear_alphas(n):   # common_utils.py:15-17
+    return [i / n for i in range(1, n + 1)]
+
+
+def sd_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+class _MeanClassifier:
+    """stand-in classifier for the purifier-only fixtures (the reference only needs set_device/__call__)."""
+
+    def set_device(self, d):
+        pass
+
+    def __call__(self, x):
+        return x.mean(dim=(2, 3))
+
+
+def run_reference_nvae(ckpt, alphas, attenuation, eps, blur, x, noises, classifier=None):
+    mm = ref_import.ref_models()
+    os.makedirs(SCRATCH, exist_ok=True)
+    path = os.path.join(SCRATCH, "nvae_ckpt.pt")
+    torch.save(ckpt, path)
+    dm = mm.NVAEDefenseModel(classifier or _MeanClassifier(), path, alphas, attenuation, eps, blur, "cpu")
+    with torch.no_grad(), ref_import.ExplicitNoise(noises):
+        logits, purified = dm(x, preds_only=False)
+    return logits, purified
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    # ---------------------------------------------------------------- tiny architecture, weights stored
+    cfg, res = tiny_config(), (3, 32, 32)
+    spec = NvaeSpec(cfg, res)
+    ckpt = synth.make_nvae_checkpoint(cfg, res, seed=3)
+    x, _ = synth.synthetic_batch(3, res, seed=11)
+    noises = synth.synthetic_noise(spec, 3, seed=12)
+    cases = []
+    for name, alphas, att, eps, blur in [("cosine_noise", cosine_alphas(spec.n_latents), 0.7, 2.0, False),
+                                         ("linear_blur", linear_alphas(spec.n_latents), 1.0, 0.0, True),
+                                         ("alpha0_blur_noise", [0.0] * spec.n_latents, 1.0, 1.0, True)]:
+        _, pur = run_reference_nvae(ckpt, alphas, att, eps, blur, x, noises)
+        cases.append({"name": name, "alphas": alphas, "attenuation": att, "eps": eps, "blur": blur, "purified": pur})
+        print("tiny", name, pur.mean().item(), pur.std().item())
+    torch.save({"cfg": cfg, "resolution": res, "state_dict": ckpt["state_dict_temp=0.6"], "x": x,
+                "noises": noises, "cases": cases}, os.path.join(GOLDEN, "nvae_tiny.pt"))
+
+    # ---------------------------------------------------------------- C32 + VGG11 (weights regenerated from seeds)
+    cfg, res = NVAE_C32_CONFIG, NVAE_C32_RESOLUTION
+    spec = NvaeSpec(cfg, res)
+    ckpt = synth.make_nvae_checkpoint(cfg, res, seed=0)
+    vgg_ckpt = synth.make_vgg11_checkpoint(100, seed=1)
+    vpath = os.path.join(SCRATCH, "vgg_ckpt.pt")
+    os.makedirs(SCRATCH, exist_ok=True)
+    torch.save(vgg_ckpt, vpath)
+    mm = ref_import.ref_models()
+    clf = mm.CelebaIdentityClassifier(vpath, "cpu")
+    import yaml
+    out = {"nvae_seed": 0, "vgg_seed": 1, "x_seed": 42, "noise_seed": 7, "batch": 4,
+           "nvae_digest": sd_digest(ckpt["state_dict_temp=0.6"]),
+           "vgg_small_digest": sd_digest({k: v for k, v in vgg_ckpt["state_dict"].items() if "classifier.0" not in k}),
+           "cases": []}
+    x, y = synth.synthetic_batch(4, res, seed=42)
+    noises = synth.synthetic_noise(spec, 4, seed=7)
+    for yml in ("ours_cosine_noise_ids.yaml", "ours_learned_blur_ids.yaml"):
+        with open(os.path.join(ref_import.REFERENCE_ROOT, "configs", yml)) as f:
+            p = yaml.safe_load(f)
+        logits, pur = run_reference_nvae(ckpt, p["interpolation_alphas"], p["alpha_attenuation"],
+                                         p["initial_noise_eps"], p["gaussian_blur_input"], x, noises, clf)
+        out["cases"].append({"yaml": yml, "alphas": p["interpolation_alphas"], "attenuation": p["alpha_attenuation"],
+                             "eps": p["initial_noise_eps"], "blur": p["gaussian_blur_input"],
+                             "purified": pur, "logits": logits})
+        print("c32", yml, pur.mean().item(), pur.std().item(), logits.abs().mean().item(), logits.argmax(1).tolist())
+    torch.save(out, os.path.join(GOLDEN, "nvae_c32_vgg11.pt"))
+    shutil.rmtree(SCRATCH, ignore_errors=True)
+    for f in sorted(os.listdir(GOLDEN)):
+        print(f, os.path.getsize(os.path.join(GOLDEN, f)))
+
+
+if __name__ == "__main__":
+    main()
