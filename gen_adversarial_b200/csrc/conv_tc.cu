@@ -1,0 +1,454 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Replaces the cuDNN convolutions behind the NVAE residual cells, samplers and combiners
+// (/root/reference/src/mlvgms_autoencoders/NVAE/modules/architecture.py:96-218, NVAE/model.py:184-231,310-313)
+// and the VGG11 body / head GEMMs (src/classifier/model.py:31-50) on the bf16 product path.
+//
+// GEMM view   D[M = pixels, N = Cout] = A[M, K] * B[N, K]^T,   K = taps * Cin (+ Cin2 of a second 1x1 source)
+//   * A is never materialised: one CTA owns 128 output pixels laid out as a (bn x bh x bw) box of the NHWC
+//     activation tensor; for every filter tap the TMA engine fetches the box shifted by (ky-pad, kx-pad) with
+//     hardware zero fill outside the image -- that IS the zero padding of the convolution (im2col by TMA).
+//   * B (weights, [Cout][K] K-major bf16) streams through the same mbarrier ring.
+//   * 64-channel K blocks land in shared memory in the 128-byte-swizzled K-major layout that tcgen05.mma
+//     consumes directly (UMMA descriptors, SBO = 1024 B); 4 MMAs (K=16 each) per block, issued by ONE thread.
+//   * The fp32 accumulator tile (128 lanes x BLOCK_N columns) lives in tensor memory; 4 epilogue warps read it
+//     back with tcgen05.ld (one pixel row per thread), fuse bias + activation + residual add and store bf16/fp32.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// One output tile per CTA; 2 CTAs are co-resident per SM (<= 97 KB smem, <= 256 TMEM columns each) so one CTA's
+// epilogue overlaps the other's main loop.
+#include <cuda.h>
+#include <stdlib.h>
+#include "ga_common.cuh"
+
+namespace ga {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int taps, kw, pad;          // filter taps of source 1
+  int cin, kc1, kc2;          // channels of source 1, its 64-blocks per tap, 64-blocks of source 2
+  int bw, bh, bn;             // pixel box of one M tile (bw*bh*bn == 128)
+  int tiles_x, tiles_y;       // tiles per image row / column (bn == 1) -- else whole images per tile
+  int H, W;
+  int64_t M;                  // total output pixels
+  int cout;
+  const float* bias;
+  int post_act;
+  const void* add; int add_dtype;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread for the whole CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 = 1024 B
+//   (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1, a/b K-major (bits 15,16 = 0),
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmA2,
+                                                             const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  constexpr int B_STAGE_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  constexpr int STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on a 1024 B boundary
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * TC_A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.y;
+
+  // ---- tile -> pixel box
+  int n0, y0, x0;
+  {
+    const int t = blockIdx.x;
+    if (p.bn > 1) { n0 = t * p.bn; y0 = 0; x0 = 0; }
+    else {
+      const int per_img = p.tiles_x * p.tiles_y;
+      n0 = t / per_img;
+      const int rem = t - n0 * per_img;
+      y0 = (rem / p.tiles_x) * p.bh;
+      x0 = (rem % p.tiles_x) * p.bw;
+    }
+  }
+  const int64_t pix0 = ((int64_t)n0 * p.H + y0) * p.W + x0;
+  const int num_kb = p.taps * p.kc1 + p.kc2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.kc2 > 0) tma_prefetch_desc(&tmA2);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // whole warp allocates tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (lane == 0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        uint8_t* a_dst = smem_a + stage * TC_A_STAGE_BYTES;
+        uint8_t* b_dst = smem_b + stage * B_STAGE_BYTES;
+        int kcoord;
+        if (kb < p.taps * p.kc1) {
+          const int tap = kb / p.kc1, cc = kb - tap * p.kc1;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          tma_load_4d(&tmA, &full_bar[stage], a_dst, cc * TC_BLOCK_K, x0 + kx - p.pad, y0 + ky - p.pad, n0);
+          kcoord = tap * p.cin + cc * TC_BLOCK_K;
+        } else {
+          const int cc = kb - p.taps * p.kc1;
+          tma_load_4d(&tmA2, &full_bar[stage], a_dst, cc * TC_BLOCK_K, x0, y0, n0);
+          kcoord = p.taps * p.cin + cc * TC_BLOCK_K;
+        }
+        tma_load_2d(&tmB, &full_bar[stage], b_dst, kcoord, n_blk * BLOCK_N);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc(TC_BLOCK_M, BLOCK_N);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (lane == 0) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * TC_A_STAGE_BYTES);
+        const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * 32);
+          const uint64_t db = make_smem_desc(b_addr + k * 32);
+          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);                     // smem slot free once these MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int et = threadIdx.x - 64;                 // 0..127
+    for (int i = et; i < BLOCK_N; i += 128) {
+      const int n = n_blk * BLOCK_N + i;
+      s_bias[i] = (p.bias != nullptr && n < p.cout) ? p.bias[n] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int64_t pix = pix0 + row;
+    const bool row_ok = pix < p.M;
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    const bool vec_ok = (p.cout & 7) == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const int nb = n_blk * BLOCK_N + c0;
+      if (!row_ok || nb >= p.cout) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
+      const int64_t off = pix * p.cout + nb;
+      if (vec_ok && nb + 16 <= p.cout) {
+        if (p.add != nullptr) {
+          if (p.add_dtype == GA_F32) {
+            const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add) + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float4 t = __ldg(a4 + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+          } else {
+            const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add) + off);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4 t = __ldg(a4 + j);
+              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                v[8 * j + 2 * k] += __low2float(h); v[8 * j + 2 * k + 1] += __high2float(h);
+              }
+            }
+          }
+        }
+        if (p.out_bf16 != nullptr) {
+          uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + off);
+          o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        }
+        if (p.out_f32 != nullptr) {
+          float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (nb + j >= p.cout) continue;
+          float o = v[j];
+          if (p.add != nullptr)
+            o += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
+                                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
+          if (p.out_bf16 != nullptr) p.out_bf16[off + j] = __float2bfloat16_rn(o);
+          if (p.out_f32 != nullptr) p.out_f32[off + j] = o;
+        }
+      }
+    }
+  }
+  // ---- teardown: every tcgen05 op of this CTA is complete (the epilogue waited for the last commit)
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+struct TileGeom { int bw, bh, bn, tiles_x, tiles_y; int64_t m_tiles; };
+
+static bool tile_geometry(int N, int H, int W, TileGeom* g) {
+  if (W >= 128) {
+    if (W % 128) return false;
+    g->bw = 128; g->bh = 1; g->bn = 1;
+  } else {
+    if (128 % W) return false;
+    g->bw = W;
+    const int rows = 128 / W;
+    if (H >= rows) { if (H % rows) return false; g->bh = rows; g->bn = 1; }
+    else { if (rows % H) return false; g->bh = H; g->bn = rows / H; }
+  }
+  g->tiles_x = W / g->bw; g->tiles_y = H / g->bh;
+  g->m_tiles = g->bn > 1 ? (N + g->bn - 1) / g->bn : (int64_t)N * g->tiles_x * g->tiles_y;
+  return true;
+}
+
+static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->c * 2, (cuuint64_t)t->w * t->c * 2, (cuuint64_t)t->h * t->w * t->c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d box=%d,%d,%d) failed: %d", t->n, t->h, t->w, t->c,
+           g.bw, g.bh, g.bn, (int)r);
+  return 0;
+}
+
+static int encode_weight_map(CUtensorMap* tm, const void* w, int cout, int ktot, int block_n) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight cout=%d k=%d box_n=%d) failed: %d", cout, ktot, block_n, (int)r);
+  return 0;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int smem = STAGES * (TC_A_STAGE_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024 /*align*/ + (2 * STAGES + 1) * 8 + 8 + BLOCK_N * 4;
+  static bool configured = false;
+  if (!configured) {
+    GA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, p);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+static int pick_block_n(int cout) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("GA_TC_BLOCK_N");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
+  if (cout <= 32) return 32;
+  if (cout <= 64) return 64;
+  return 128;
+}
+
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" int ga_conv2d_tc_supported(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, int cout) {
+  if (!in || !d) return 0;
+  if (in->dtype != GA_BF16) return 0;
+  if (d->stride != 1 || d->up != 1 || d->pre_op != GA_PRE_NONE) return 0;
+  if (!((d->kh == 1 && d->kw == 1 && d->pad == 0) || (d->kh == 3 && d->kw == 3 && d->pad == 1))) return 0;
+  if (in->c % 8 != 0 || cout < 1) return 0;
+  if (in2 && (in2->dtype != GA_BF16 || in2->c % 8 != 0 || in2->n != in->n || in2->h != in->h || in2->w != in->w)) return 0;
+  TileGeom g;
+  if (!tile_geometry(in->n, in->h, in->w, &g)) return 0;
+  if ((((uintptr_t)in->data) & 15) != 0) return 0;
+  return 1;
+}
+
+extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, const ga_tensor* add,
+                            const ga_tensor* out_bf16, const ga_tensor* out_f32, void* stream) {
+  GA_CHECK(in && d && (out_bf16 || out_f32), "ga_conv2d_tc: null argument");
+  const ga_tensor* out = out_bf16 ? out_bf16 : out_f32;
+  GA_CHECK(ga_conv2d_tc_supported(in, in2, d, out->c), "ga_conv2d_tc: unsupported problem (n=%d h=%d w=%d cin=%d k=%d stride=%d pre=%d)",
+           in->n, in->h, in->w, in->c, d->kh, d->stride, d->pre_op);
+  GA_CHECK(out->n == in->n && out->h == in->h && out->w == in->w, "ga_conv2d_tc: output spatial shape mismatch");
+  GA_CHECK(!out_bf16 || out_bf16->dtype == GA_BF16, "ga_conv2d_tc: out_bf16 must be bf16");
+  GA_CHECK(!out_f32 || out_f32->dtype == GA_F32, "ga_conv2d_tc: out_f32 must be fp32");
+  GA_CHECK(!(out_bf16 && out_f32) || same_shape(out_bf16, out_f32), "ga_conv2d_tc: the two outputs differ in shape");
+  if (add) GA_CHECK(same_shape(add, out), "ga_conv2d_tc: add shape mismatch");
+  const int taps = d->kh * d->kw;
+  const int ktot = taps * in->c + (in2 ? in2->c : 0);
+  GA_CHECK(d->ktot == ktot, "ga_conv2d_tc: weight row length %d != kh*kw*cin(+cin2) = %d", d->ktot, ktot);
+  GA_CHECK((((uintptr_t)d->weight) & 15) == 0, "ga_conv2d_tc: weight pointer must be 16-byte aligned");
+  if (numel(out) == 0) return 0;
+
+  TileGeom g;
+  tile_geometry(in->n, in->h, in->w, &g);
+  const int block_n = pick_block_n(out->c);
+  CUtensorMap tmA, tmA2, tmB;
+  if (encode_act_map(&tmA, in, g)) return 1;
+  if (in2) { if (encode_act_map(&tmA2, in2, g)) return 1; }
+  else tmA2 = tmA;
+  if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n)) return 1;
+
+  TcParams p;
+  p.taps = taps; p.kw = d->kw; p.pad = d->pad;
+  p.cin = in->c; p.kc1 = (in->c + TC_BLOCK_K - 1) / TC_BLOCK_K; p.kc2 = in2 ? (in2->c + TC_BLOCK_K - 1) / TC_BLOCK_K : 0;
+  p.bw = g.bw; p.bh = g.bh; p.bn = g.bn; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
+  p.H = in->h; p.W = in->w; p.M = (int64_t)in->n * in->h * in->w;
+  p.cout = out->c; p.bias = d->bias; p.post_act = d->post_act;
+  p.add = add ? add->data : nullptr; p.add_dtype = add ? add->dtype : GA_F32;
+  p.out_bf16 = out_bf16 ? (__nv_bfloat16*)out_bf16->data : nullptr;
+  p.out_f32 = out_f32 ? (float*)out_f32->data : nullptr;
+  dim3 grid((unsigned)g.m_tiles, (unsigned)((out->c + block_n - 1) / block_n));
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (block_n) {
+    case 32: return launch_tc<32, 4>(tmA, tmA2, tmB, p, grid, s);
+    case 64: return launch_tc<64, 4>(tmA, tmA2, tmB, p, grid, s);
+    case 128: return launch_tc<128, 3>(tmA, tmA2, tmB, p, grid, s);
+    default: return launch_tc<256, 3>(tmA, tmA2, tmB, p, grid, s);
+  }
+}

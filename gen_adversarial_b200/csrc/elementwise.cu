@@ -1,0 +1,806 @@
+// Bandwidth-bound fused kernels of the purification path (forward): pre-processing, depthwise 5x5,
+// squeeze-excite + residual, latent mix, DiscMixLogistic mean, resampling, PGD step, cross-entropy.
+// All are HBM-bound: coalesced / vectorised accesses, one pass over each tensor, fp32 math.
+#include "ga_common.cuh"
+
+namespace ga {
+
+// runtime-dtype 4-wide access (branch is grid-uniform)
+__device__ __forceinline__ void ld4d(const void* base, int dtype, int64_t off, float (&v)[4]) {
+  if (dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(base) + off, v);
+  else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(base) + off, v);
+}
+__device__ __forceinline__ void st4d(void* base, int dtype, int64_t off, const float (&v)[4]) {
+  if (dtype == GA_F32) st4<float>(reinterpret_cast<float*>(base) + off, v);
+  else st4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(base) + off, v);
+}
+__device__ __forceinline__ float ld1d(const void* base, int dtype, int64_t off) {
+  return dtype == GA_F32 ? reinterpret_cast<const float*>(base)[off]
+                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]);
+}
+__device__ __forceinline__ void st1d(void* base, int dtype, int64_t off, float v) {
+  if (dtype == GA_F32) reinterpret_cast<float*>(base)[off] = v;
+  else reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
+}
+
+__host__ __device__ __forceinline__ uint64_t noise_stream(int64_t sample, int level) {
+  return (uint64_t)sample * 64ull + (uint64_t)level;
+}
+
+// ============================================================================ noise L2 norm pre-pass
+__global__ void noise_sumsq_kernel(const float* __restrict__ noise, int chw, float* __restrict__ sumsq) {
+  const int b = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(noise + (int64_t)b * chw);
+  const int n4 = chw >> 2;
+  float acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 v = __ldg(src + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0)   // tail (chw not multiple of 4)
+    for (int i = (n4 << 2) + threadIdx.x; i < chw; i += blockDim.x) {
+      float v = noise[(int64_t)b * chw + i];
+      acc += v * v;
+    }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sumsq + b, acc);
+}
+
+__global__ void noise_sumsq_philox_kernel(uint64_t seed, int64_t sample0, int chw, float* __restrict__ sumsq) {
+  const int b = blockIdx.y;
+  const uint64_t stream = noise_stream(sample0 + b, 0);
+  const int n4 = (chw + 3) >> 2;
+  float acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float z[4];
+    philox_normal4(seed, stream, (uint64_t)i, z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i * 4 + j < chw) acc += z[j] * z[j];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sumsq + b, acc);
+}
+
+// ============================================================================ fused pre-processing
+// tile 32 rows x 32 cols, 256 threads, each thread 4 consecutive x of one row, all channels.
+constexpr int PT = 32;
+constexpr int MAXR = 15;
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+template <bool BLUR>
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ noise, const float* __restrict__ sumsq, uint64_t seed,
+    int64_t sample0, float eps, const float* __restrict__ taps, int R, int normalize, int C, int H, int W, void* out,
+    int out_dtype, float* __restrict__ pre) {
+  __shared__ float s_in[BLUR ? (PT + 2 * MAXR) : 1][BLUR ? (PT + 2 * MAXR + 1) : 1];
+  __shared__ float s_h[BLUR ? (PT + 2 * MAXR) : 1][BLUR ? (PT + 1) : 1];
+  __shared__ float s_taps[2 * MAXR + 1];
+
+  const int b = blockIdx.z;
+  const int tiles_x = (W + PT - 1) / PT;
+  const int ty0 = (blockIdx.x / tiles_x) * PT, tx0 = (blockIdx.x % tiles_x) * PT;
+  const int tid = threadIdx.x;
+  const int ly = tid >> 3, lx = (tid & 7) * 4;
+  const int oy = ty0 + ly, ox = tx0 + lx;
+  if (BLUR) {
+    if (tid < 2 * R + 1) s_taps[tid] = taps[tid];
+  }
+  float scale = 0.f;
+  if (eps != 0.f) scale = eps / sqrtf(sumsq[b]);
+
+  float res[4][4];   // [channel][pixel]
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= C) break;
+    const float* xp = x + ((int64_t)b * C + c) * H * W;
+    float v[4];
+    if (BLUR) {
+      const int ext = PT + 2 * R;
+      __syncthreads();
+      for (int i = tid; i < ext * ext; i += 256) {
+        int yy = i / ext, xx = i % ext;
+        int gy = reflect_idx(ty0 + yy - R, H), gx = reflect_idx(tx0 + xx - R, W);
+        // tiles hanging over the image edge (H, W not multiples of 32): clamp, results are masked later
+        gy = min(max(gy, 0), H - 1); gx = min(max(gx, 0), W - 1);
+        s_in[yy][xx] = __ldg(xp + (int64_t)gy * W + gx);
+      }
+      __syncthreads();
+      for (int i = tid; i < ext * PT; i += 256) {
+        int yy = i / PT, xx = i % PT;
+        float a = 0.f;
+        for (int t = 0; t < 2 * R + 1; ++t) a = fmaf(s_taps[t], s_in[yy][xx + t], a);
+        s_h[yy][xx] = a;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = 0.f;
+        for (int t = 0; t < 2 * R + 1; ++t) a = fmaf(s_taps[t], s_h[ly + t][lx + j], a);
+        v[j] = a;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (oy < H && ox + j < W) ? __ldg(xp + (int64_t)oy * W + ox + j) : 0.f;
+    }
+    if (eps != 0.f && oy < H) {
+      const int64_t e0 = ((int64_t)c * H + oy) * W + ox;   // element index inside the sample
+      float z[4];
+      if (noise != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = (ox + j < W) ? __ldg(noise + (int64_t)b * C * H * W + e0 + j) : 0.f;
+      } else {
+        if ((e0 & 3) == 0) {
+          philox_normal4(seed, noise_stream(sample0 + b, 0), (uint64_t)(e0 >> 2), z);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[j] = philox_normal(seed, noise_stream(sample0 + b, 0), (uint64_t)(e0 + j));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaf(z[j], scale, v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r = fminf(fmaxf(v[j], 0.f), 1.f);
+      // saved UNCLAMPED: torch's clamp backward passes the gradient where 0 <= v <= 1 (inclusive)
+      if (pre != nullptr && oy < H && ox + j < W) pre[(((int64_t)b * C + c) * H + oy) * W + ox + j] = v[j];
+      res[c][j] = normalize ? (r - 0.5f) * 2.0f : r;
+    }
+  }
+  if (oy < H) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (ox + j >= W) continue;
+      const int64_t o = (((int64_t)b * H + oy) * W + ox + j) * C;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) st1d(out, out_dtype, o + c, res[c][j]);
+    }
+  }
+}
+
+// backward helpers: g (NHWC) -> masked/scaled NCHW;  1-D transposed reflect-border blur along one axis
+__global__ void preprocess_bwd_mask_kernel(const void* __restrict__ g, int g_dtype, const float* __restrict__ pre,
+                                           float gscale, int C, int H, int W, int64_t total, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int x = (int)(i % W); int64_t t = i / W;
+  int y = (int)(t % H); t /= H;
+  int c = (int)(t % C); int64_t b = t / C;
+  float p = pre[i];
+  float gv = ld1d(g, g_dtype, ((b * H + y) * W + x) * C + c);
+  out[i] = (p >= 0.f && p <= 1.f) ? gv * gscale : 0.f;
+}
+
+__global__ void blur_transpose_1d_kernel(const float* __restrict__ in, const float* __restrict__ taps, int R, int H, int W,
+                                         int axis /*0 = y, 1 = x*/, int64_t total, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int64_t plane = i / ((int64_t)H * W) * H * W;
+  const int n = axis == 0 ? H : W;
+  const int pos = axis == 0 ? y : x;
+  const int64_t stride = axis == 0 ? W : 1;
+  const float* base = in + plane + (axis == 0 ? x : (int64_t)y * W);
+  float acc = 0.f;
+  for (int d = -R; d <= R; ++d) {
+    const float w = taps[d + R];
+    int j = pos - d;                         // direct: j + d = pos
+    if (j >= 0 && j < n) acc = fmaf(w, base[j * stride], acc);
+    if (pos > 0) {                           // left reflection: j + d = -pos
+      j = -pos - d;
+      if (j >= 0 && j < n) acc = fmaf(w, base[j * stride], acc);
+    }
+    if (pos < n - 1) {                       // right reflection: j + d = 2n-2-pos
+      j = 2 * n - 2 - pos - d;
+      if (j >= 0 && j < n) acc = fmaf(w, base[j * stride], acc);
+    }
+  }
+  out[i] = acc;
+}
+
+// ============================================================================ depthwise 5x5 (+bias, act)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) dwconv5x5_kernel(const TIn* __restrict__ in, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int act, int up, int N, int H, int W,
+                                                        int C, TOut* __restrict__ out) {
+  const int c4n = C >> 2;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)N * H * W * c4n;
+  if (idx >= total) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H);
+  const int n = (int)(t / H);
+  const int Hi = up ? H >> 1 : H, Wi = up ? W >> 1 : W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias) { float4 b = *reinterpret_cast<const float4*>(bias + c); acc[0] = b.x; acc[1] = b.y; acc[2] = b.z; acc[3] = b.w; }
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy) {
+    const int iy = y + dy - 2;
+    if (iy < 0 || iy >= H) continue;
+    const int sy = up ? iy >> 1 : iy;
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+      const int ix = x + dx - 2;
+      if (ix < 0 || ix >= W) continue;
+      const int sx = up ? ix >> 1 : ix;
+      float v[4];
+      ld4<TIn>(in + (((int64_t)n * Hi + sy) * Wi + sx) * C + c, v);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (dy * 5 + dx) * C + c));
+      acc[0] = fmaf(v[0], wv.x, acc[0]); acc[1] = fmaf(v[1], wv.y, acc[1]);
+      acc[2] = fmaf(v[2], wv.z, acc[2]); acc[3] = fmaf(v[3], wv.w, acc[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = apply_act(acc[j], act);
+  st4<TOut>(out + (((int64_t)n * H + y) * W + x) * C + c, acc);
+}
+
+// ============================================================================ SE: channel sums + gate + residual
+__global__ void __launch_bounds__(256) channel_sum_kernel(const void* __restrict__ r, int dtype, int HW, int C,
+                                                          int pix_per_block, float* __restrict__ sums) {
+  extern __shared__ float s_sum[];   // [C]
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+  __syncthreads();
+  const int64_t base = ((int64_t)n * HW + p0) * C;
+  const int cnt = (p1 - p0) * C;
+  if (256 % C == 0) {          // each thread always sees the same channel
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += 256) acc += ld1d(r, dtype, base + i);
+    atomicAdd(&s_sum[threadIdx.x % C], acc);
+  } else if (C % 256 == 0) {   // thread sees channels t, t+256, ... cyclically
+    const int per = C / 256;
+    for (int k = 0; k < per; ++k) {
+      float acc = 0.f;
+      for (int i = threadIdx.x + k * 256; i < cnt; i += C) acc += ld1d(r, dtype, base + i);
+      s_sum[threadIdx.x + k * 256] = acc;
+    }
+  } else {
+    for (int i = threadIdx.x; i < cnt; i += 256) atomicAdd(&s_sum[i % C], ld1d(r, dtype, base + i));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(sums + (int64_t)n * C + c, s_sum[c]);
+}
+
+struct SeParams {
+  const void* r; int r_dtype;
+  const float* sums; const float* w1; const float* b1; const float* w2; const float* b2;
+  int hidden; float res_scale;
+  const void* skip; int skip_dtype;
+  void* out; int out_dtype;
+  void* out2; int out2_dtype;
+  void* act; int act_dtype; const float* act_scale; const float* act_shift;
+  float* gate_out;
+  int HW, C, pix_per_block;
+};
+
+__global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
+  extern __shared__ float sm[];      // mean[C] | gate[C] | hid[hidden]
+  float* s_mean = sm;
+  float* s_gate = sm + p.C;
+  float* s_hid = sm + 2 * p.C;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float inv = 1.0f / (float)p.HW;
+  for (int c = tid; c < p.C; c += 256) s_mean[c] = p.sums[(int64_t)n * p.C + c] * inv;
+  __syncthreads();
+  for (int j = warp; j < p.hidden; j += 8) {
+    float a = 0.f;
+    for (int c = lane; c < p.C; c += 32) a = fmaf(p.w1[(int64_t)j * p.C + c], s_mean[c], a);
+    a = warp_sum(a);
+    if (lane == 0) s_hid[j] = fmaxf(a + p.b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = tid; c < p.C; c += 256) {
+    float a = p.b2[c];
+    for (int j = 0; j < p.hidden; ++j) a = fmaf(p.w2[(int64_t)c * p.hidden + j], s_hid[j], a);
+    float g = sigmoidf_(a);
+    s_gate[c] = g;
+    if (p.gate_out != nullptr && blockIdx.x == 0) p.gate_out[(int64_t)n * p.C + c] = g;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * p.pix_per_block;
+  const int p1 = min(p0 + p.pix_per_block, p.HW);
+  const int c4n = p.C >> 2;
+  const int64_t base = ((int64_t)n * p.HW + p0) * p.C;
+  const int cnt4 = (p1 - p0) * c4n;
+  for (int i = tid; i < cnt4; i += 256) {
+    const int c = (i % c4n) * 4;
+    const int64_t off = base + (int64_t)i * 4;
+    float rv[4], sv[4], o[4];
+    ld4d(p.r, p.r_dtype, off, rv);
+    ld4d(p.skip, p.skip_dtype, off, sv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaf(p.res_scale * s_gate[c + j], rv[j], sv[j]);
+    st4d(p.out, p.out_dtype, off, o);
+    if (p.out2 != nullptr) st4d(p.out2, p.out2_dtype, off, o);
+    if (p.act != nullptr) {
+      float a[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] = siluf_(fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]));
+      st4d(p.act, p.act_dtype, off, a);
+    }
+  }
+}
+
+// ============================================================================ latent mix
+__global__ void __launch_bounds__(256) latent_mix_kernel(const void* __restrict__ q, int q_dtype, int Cq,
+                                                         const void* __restrict__ pp, int p_dtype, const float* __restrict__ eps,
+                                                         uint64_t seed, int level, int64_t sample0,
+                                                         const float* __restrict__ alpha_dev, float temp, int Z, int N, int H,
+                                                         int W, void* __restrict__ zout, int z_dtype, int Cz) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)N * H * W * Cz;
+  if (idx >= total) return;
+  const int zc = (int)(idx % Cz);
+  const int64_t pix = idx / Cz;
+  if (zc >= Z) { st1d(zout, z_dtype, idx, 0.f); return; }   // zero padding channels (tensor-core K padding)
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int64_t n = pix / ((int64_t)W * H);
+  const float a = *alpha_dev;
+  const float mu_q = ld1d(q, q_dtype, pix * Cq + zc);
+  const int64_t e_idx = (((int64_t)zc) * H + y) * W + x;      // element index inside the sample (NCHW order)
+  float e;
+  if (eps != nullptr) e = eps[n * Z * H * W + e_idx];
+  else e = philox_normal(seed, noise_stream(sample0 + n, level + 1), (uint64_t)e_idx);
+  float out;
+  if (pp == nullptr) {
+    out = (1.f - a) * softclamp5_(mu_q) + a * (e * temp);
+  } else {
+    const float mu_p = ld1d(pp, p_dtype, pix * (2 * Z) + zc);
+    const float ls_p = ld1d(pp, p_dtype, pix * (2 * Z) + Z + zc);
+    const float enc = softclamp5_(mu_p + mu_q);
+    const float dec = softclamp5_(mu_p) + e * (temp * expf(softclamp5_(ls_p)));
+    out = (1.f - a) * enc + a * dec;
+  }
+  st1d(zout, z_dtype, idx, out);
+}
+
+// ============================================================================ DiscMixLogistic mean
+constexpr int DM_PIX = 64;
+__global__ void __launch_bounds__(128) discmix_mean_kernel(const void* __restrict__ logits, int dtype, int n_mix, int HW,
+                                                           int64_t total_pix, float* __restrict__ purified, void* cls,
+                                                           int cls_dtype) {
+  extern __shared__ float s_l[];   // [DM_PIX][CL + 1]
+  const int CL = 10 * n_mix;
+  const int pitch = CL + 1;
+  const int64_t pix0 = (int64_t)blockIdx.x * DM_PIX;
+  const int npx = (int)min((int64_t)DM_PIX, total_pix - pix0);
+  const int cnt = npx * CL;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+    s_l[(i / CL) * pitch + (i % CL)] = ld1d(logits, dtype, pix0 * CL + i);
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= npx) return;
+  const float* l = s_l + t * pitch;
+  float mx = l[0];
+  for (int m = 1; m < n_mix; ++m) mx = fmaxf(mx, l[m]);
+  float den = 0.f, mu0 = 0.f, mu1 = 0.f, mu2 = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f;
+  for (int m = 0; m < n_mix; ++m) {
+    const float e = expf(l[m] - mx);
+    const float* q = l + n_mix + 9 * m;   // [m0 m1 m2 | s0 s1 s2 | k0 k1 k2]
+    den += e;
+    mu0 = fmaf(e, q[0], mu0); mu1 = fmaf(e, q[1], mu1); mu2 = fmaf(e, q[2], mu2);
+    k0 = fmaf(e, tanhf(q[6]), k0); k1 = fmaf(e, tanhf(q[7]), k1); k2 = fmaf(e, tanhf(q[8]), k2);
+  }
+  const float inv = 1.f / den;
+  mu0 *= inv; mu1 *= inv; mu2 *= inv; k0 *= inv; k1 *= inv; k2 *= inv;
+  const float r = fminf(fmaxf(mu0, -1.f), 1.f);
+  const float g = fminf(fmaxf(fmaf(k0, r, mu1), -1.f), 1.f);
+  const float b = fminf(fmaxf(mu2 + k1 * r + k2 * g, -1.f), 1.f);
+  const int64_t pix = pix0 + t;
+  const int64_t n = pix / HW, hw = pix % HW;
+  float* dst = purified + n * 3 * HW + hw;
+  dst[0] = r * 0.5f + 0.5f; dst[HW] = g * 0.5f + 0.5f; dst[2 * (int64_t)HW] = b * 0.5f + 0.5f;
+  if (cls != nullptr) {
+    // classifier input normalize(purified, 0.5, 0.5) (abstract_models.py:60)
+    st1d(cls, cls_dtype, pix * 3 + 0, ((r * 0.5f + 0.5f) - 0.5f) * 2.0f);
+    st1d(cls, cls_dtype, pix * 3 + 1, ((g * 0.5f + 0.5f) - 0.5f) * 2.0f);
+    st1d(cls, cls_dtype, pix * 3 + 2, ((b * 0.5f + 0.5f) - 0.5f) * 2.0f);
+  }
+}
+
+// ============================================================================ resampling / layout
+__global__ void upsample_nearest2x_kernel(const void* in, int in_dtype, void* out, int out_dtype, int N, int H, int W, int C) {
+  const int c4n = C >> 2;
+  const int Ho = 2 * H, Wo = 2 * W;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * Ho * Wo * c4n) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int x = (int)(t % Wo); t /= Wo;
+  const int y = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  float v[4];
+  ld4d(in, in_dtype, ((n * H + (y >> 1)) * W + (x >> 1)) * C + c, v);
+  st4d(out, out_dtype, ((n * Ho + y) * Wo + x) * C + c, v);
+}
+
+__global__ void upsample_bilinear2x_kernel(const void* in, int in_dtype, void* out, int out_dtype, int N, int H, int W, int C) {
+  const int c4n = C >> 2;
+  const int Ho = 2 * H, Wo = 2 * W;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * Ho * Wo * c4n) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int x = (int)(t % Wo); t /= Wo;
+  const int y = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  // align_corners=True: src = dst * (in-1)/(out-1)
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const float fy = sy * y, fx = sx * x;
+  int y0 = (int)fy, x0 = (int)fx;
+  y0 = min(y0, H - 1); x0 = min(x0, W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float wy = fy - y0, wx = fx - x0;
+  float a[4], b[4], cc[4], d[4], o[4];
+  ld4d(in, in_dtype, ((n * H + y0) * W + x0) * C + c, a);
+  ld4d(in, in_dtype, ((n * H + y0) * W + x1) * C + c, b);
+  ld4d(in, in_dtype, ((n * H + y1) * W + x0) * C + c, cc);
+  ld4d(in, in_dtype, ((n * H + y1) * W + x1) * C + c, d);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float top = a[j] + wx * (b[j] - a[j]);
+    const float bot = cc[j] + wx * (d[j] - cc[j]);
+    o[j] = top + wy * (bot - top);
+  }
+  st4d(out, out_dtype, ((n * Ho + y) * Wo + x) * C + c, o);
+}
+
+__global__ void maxpool2x2_kernel(const void* in, int in_dtype, void* out, int out_dtype, int N, int H, int W, int C) {
+  const int c4n = C >> 2;
+  const int Ho = H >> 1, Wo = W >> 1;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * Ho * Wo * c4n) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int x = (int)(t % Wo); t /= Wo;
+  const int y = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  float a[4], b[4], cc[4], d[4], o[4];
+  const int64_t base = ((n * H + 2 * y) * W + 2 * x) * C + c;
+  ld4d(in, in_dtype, base, a);
+  ld4d(in, in_dtype, base + C, b);
+  ld4d(in, in_dtype, base + (int64_t)W * C, cc);
+  ld4d(in, in_dtype, base + (int64_t)W * C + C, d);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(cc[j], d[j]));
+  st4d(out, out_dtype, ((n * Ho + y) * Wo + x) * C + c, o);
+}
+
+__global__ void affine_act_kernel(const void* in, int in_dtype, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  int act, void* out, int out_dtype, int C, int64_t total) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float v = ld1d(in, in_dtype, idx);
+  const int c = (int)(idx % C);
+  if (scale != nullptr) v = fmaf(v, scale[c], shift[c]);
+  st1d(out, out_dtype, idx, apply_act(v, act));
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, void* out, int out_dtype, float scale, float shift, int N,
+                                    int C, int H, int W) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over NHWC output
+  if (idx >= (int64_t)N * C * H * W) return;
+  const int c = (int)(idx % C);
+  int64_t t = idx / C;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H);
+  const int64_t n = t / H;
+  st1d(out, out_dtype, idx, fmaf(in[((n * C + c) * H + y) * W + x], scale, shift));
+}
+
+// ============================================================================ attack inner loop
+__global__ void pgd_linf_step_kernel(float* __restrict__ x_adv, const float* __restrict__ grad, const float* __restrict__ x_nat,
+                                     float step, float eps, int64_t n4, int64_t numel) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 a = reinterpret_cast<float4*>(x_adv)[i];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(x_nat) + i);
+    auto upd = [&](float av, float gv, float xv) {
+      const float sg = (gv > 0.f) ? 1.f : ((gv < 0.f) ? -1.f : 0.f);
+      float v = fmaf(step, sg, av);
+      v = fminf(fmaxf(v, xv - eps), xv + eps);
+      return fminf(fmaxf(v, 0.f), 1.f);
+    };
+    a.x = upd(a.x, g.x, x.x); a.y = upd(a.y, g.y, x.y); a.z = upd(a.z, g.z, x.z); a.w = upd(a.w, g.w, x.w);
+    reinterpret_cast<float4*>(x_adv)[i] = a;
+  }
+  if (i == 0) {
+    for (int64_t k = n4 * 4; k < numel; ++k) {
+      const float gv = grad[k];
+      const float sg = (gv > 0.f) ? 1.f : ((gv < 0.f) ? -1.f : 0.f);
+      float v = fmaf(step, sg, x_adv[k]);
+      v = fminf(fmaxf(v, x_nat[k] - eps), x_nat[k] + eps);
+      x_adv[k] = fminf(fmaxf(v, 0.f), 1.f);
+    }
+  }
+}
+
+// one warp per sample
+__global__ void softmax_xent_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int n, int classes,
+                                    float* __restrict__ loss, float* __restrict__ dlogits, int32_t* __restrict__ pred,
+                                    unsigned long long* __restrict__ n_correct) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* l = logits + (int64_t)warp * classes;
+  float mx = -INFINITY; int arg = 0;
+  for (int c = lane; c < classes; c += 32) {
+    float v = l[c];
+    if (v > mx) { mx = v; arg = c; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }   // first max wins, like torch.argmax
+  }
+  float den = 0.f;
+  for (int c = lane; c < classes; c += 32) den += expf(l[c] - mx);
+  den = warp_sum(den);
+  const int64_t y = labels ? labels[warp] : -1;
+  if (dlogits != nullptr) {
+    const float invn = 1.f / (float)n;
+    for (int c = lane; c < classes; c += 32) {
+      float pr = expf(l[c] - mx) / den;
+      dlogits[(int64_t)warp * classes + c] = (pr - (c == y ? 1.f : 0.f)) * invn;
+    }
+  }
+  if (lane == 0) {
+    if (loss != nullptr && y >= 0) loss[warp] = logf(den) + mx - l[y];
+    if (pred != nullptr) pred[warp] = arg;
+    if (n_correct != nullptr && y >= 0 && arg == (int)y) atomicAdd(n_correct, 1ull);
+  }
+}
+
+}  // namespace ga
+
+// ================================================================================================ C ABI
+using namespace ga;
+
+extern "C" int ga_noise_sumsq(const float* noise, int n, int chw, float* sumsq, void* stream) {
+  GA_CHECK(noise && sumsq && n >= 0 && chw > 0, "ga_noise_sumsq: bad arguments");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  GA_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * n, s));
+  GA_CHECK((((uintptr_t)noise) & 15) == 0 && (chw % 4 == 0), "ga_noise_sumsq: noise must be 16-byte aligned with chw %% 4 == 0");
+  int bx = max(1, min(64, cdiv(chw / 4, 256)));
+  noise_sumsq_kernel<<<dim3(bx, n), 256, 0, s>>>(noise, chw, sumsq);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_noise_sumsq_philox(uint64_t seed, int64_t sample0, int n, int chw, float* sumsq, void* stream) {
+  GA_CHECK(sumsq && n >= 0 && chw > 0, "ga_noise_sumsq_philox: bad arguments");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  GA_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * n, s));
+  int bx = max(1, min(64, cdiv((chw + 3) / 4, 256)));
+  noise_sumsq_philox_kernel<<<dim3(bx, n), 256, 0, s>>>(seed, sample0, chw, sumsq);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_preprocess_fwd(const float* x, const float* noise, const float* sumsq, uint64_t seed, int64_t sample0,
+                                 float eps, const float* taps, int radius, int normalize, const ga_tensor* out, float* pre,
+                                 void* stream) {
+  GA_CHECK(x && out && out->data, "ga_preprocess_fwd: null argument");
+  GA_CHECK(out->c >= 1 && out->c <= 4, "ga_preprocess_fwd: image channels must be <= 4 (got %d)", out->c);
+  GA_CHECK(radius >= 0 && radius <= MAXR, "ga_preprocess_fwd: blur radius %d > %d", radius, MAXR);
+  GA_CHECK(eps == 0.f || sumsq, "ga_preprocess_fwd: eps != 0 needs the noise sum of squares");
+  GA_CHECK(taps == nullptr || (radius < out->h && radius < out->w), "ga_preprocess_fwd: reflect border needs radius < image size");
+  if (out->n == 0) return 0;
+  const int tiles = cdiv(out->h, PT) * cdiv(out->w, PT);
+  dim3 grid(tiles, 1, out->n);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (taps != nullptr)
+    preprocess_fwd_kernel<true><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, sample0, eps, taps, radius, normalize, out->c,
+                                                    out->h, out->w, out->data, out->dtype, pre);
+  else
+    preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, sample0, eps, nullptr, 0, normalize, out->c,
+                                                     out->h, out->w, out->data, out->dtype, pre);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_preprocess_bwd(const ga_tensor* g, const float* pre, const float* taps, int radius, int normalize,
+                                 float* tmp, float* gx, void* stream) {
+  GA_CHECK(g && pre && gx, "ga_preprocess_bwd: null argument");
+  GA_CHECK(taps == nullptr || tmp != nullptr, "ga_preprocess_bwd: blur backward needs a workspace");
+  const int64_t total = numel(g);
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = cdiv(total, 256);
+  preprocess_bwd_mask_kernel<<<blocks, 256, 0, s>>>(g->data, g->dtype, pre, normalize ? 2.0f : 1.0f, g->c, g->h, g->w, total, gx);
+  GA_LAUNCH_OK();
+  if (taps != nullptr) {
+    blur_transpose_1d_kernel<<<blocks, 256, 0, s>>>(gx, taps, radius, g->h, g->w, 0, total, tmp);
+    GA_LAUNCH_OK();
+    blur_transpose_1d_kernel<<<blocks, 256, 0, s>>>(tmp, taps, radius, g->h, g->w, 1, total, gx);
+    GA_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,
+                                const ga_tensor* out, void* stream) {
+  GA_CHECK(in && weight && out, "ga_dwconv5x5_fwd: null argument");
+  GA_CHECK(in->c == out->c && in->n == out->n && (in->c % 4) == 0, "ga_dwconv5x5_fwd: channels must match and be a multiple of 4");
+  GA_CHECK(up ? (out->h == 2 * in->h && out->w == 2 * in->w) : (out->h == in->h && out->w == in->w), "ga_dwconv5x5_fwd: shape mismatch");
+  const int64_t total = numel(out) / 4;
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = cdiv(total, 256);
+#define DW(TI, TO) dwconv5x5_kernel<TI, TO><<<blocks, 256, 0, s>>>((const TI*)in->data, weight, bias, act, up, out->n, out->h, out->w, out->c, (TO*)out->data)
+  if (in->dtype == GA_F32 && out->dtype == GA_F32) DW(float, float);
+  else if (in->dtype == GA_BF16 && out->dtype == GA_BF16) DW(__nv_bfloat16, __nv_bfloat16);
+  else if (in->dtype == GA_BF16 && out->dtype == GA_F32) DW(__nv_bfloat16, float);
+  else DW(float, __nv_bfloat16);
+#undef DW
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+static int se_pix_per_block(int HW, int n) {
+  // enough blocks to fill 148 SMs a few times, at least 64 pixels each
+  int want_blocks = max(1, (148 * 4 + n - 1) / max(n, 1));
+  int ppb = max(64, (HW + want_blocks - 1) / want_blocks);
+  return min(ppb, HW);
+}
+
+extern "C" int ga_channel_sum(const ga_tensor* r, float* sums, void* stream) {
+  GA_CHECK(r && sums, "ga_channel_sum: null argument");
+  if (numel(r) == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  GA_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)r->n * r->c, s));
+  const int HW = r->h * r->w;
+  const int ppb = se_pix_per_block(HW, r->n);
+  GA_CHECK(r->c * sizeof(float) <= 48 * 1024, "ga_channel_sum: too many channels");
+  channel_sum_kernel<<<dim3(cdiv(HW, ppb), r->n), 256, r->c * sizeof(float), s>>>(r->data, r->dtype, HW, r->c, ppb, sums);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const float* w1, const float* b1, const float* w2,
+                                  const float* b2, int hidden, float res_scale, const ga_tensor* skip, const ga_tensor* out,
+                                  const ga_tensor* out2, const ga_tensor* act, const float* act_scale, const float* act_shift,
+                                  float* gate_out, void* stream) {
+  GA_CHECK(r && sums && w1 && b1 && w2 && b2 && skip && out, "ga_se_residual_fwd: null argument");
+  GA_CHECK(same_shape(r, skip) && same_shape(r, out), "ga_se_residual_fwd: shape mismatch");
+  GA_CHECK((r->c % 4) == 0, "ga_se_residual_fwd: channels must be a multiple of 4");
+  GA_CHECK(!act || (act_scale && act_shift && same_shape(r, act)), "ga_se_residual_fwd: act output needs scale/shift");
+  GA_CHECK(!out2 || same_shape(r, out2), "ga_se_residual_fwd: out2 shape mismatch");
+  if (numel(r) == 0) return 0;
+  SeParams p;
+  p.r = r->data; p.r_dtype = r->dtype; p.sums = sums; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
+  p.hidden = hidden; p.res_scale = res_scale;
+  p.skip = skip->data; p.skip_dtype = skip->dtype;
+  p.out = out->data; p.out_dtype = out->dtype;
+  p.out2 = out2 ? out2->data : nullptr; p.out2_dtype = out2 ? out2->dtype : GA_F32;
+  p.act = act ? act->data : nullptr; p.act_dtype = act ? act->dtype : GA_F32;
+  p.act_scale = act_scale; p.act_shift = act_shift; p.gate_out = gate_out;
+  p.HW = r->h * r->w; p.C = r->c; p.pix_per_block = se_pix_per_block(p.HW, r->n);
+  const size_t smem = (2 * (size_t)p.C + hidden) * sizeof(float);
+  GA_CHECK(smem <= 48 * 1024, "ga_se_residual_fwd: too many channels");
+  se_residual_kernel<<<dim3(cdiv(p.HW, p.pix_per_block), r->n), 256, smem, (cudaStream_t)stream>>>(p);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_latent_mix_fwd(const ga_tensor* q, const ga_tensor* p, const float* eps, uint64_t seed, int level,
+                                 int64_t sample0, const float* alpha_dev, float temperature, int zdim, const ga_tensor* z,
+                                 void* stream) {
+  GA_CHECK(q && z && alpha_dev, "ga_latent_mix_fwd: null argument");
+  GA_CHECK(q->c >= zdim && z->c >= zdim, "ga_latent_mix_fwd: channel counts smaller than zdim");
+  GA_CHECK(q->n == z->n && q->h == z->h && q->w == z->w, "ga_latent_mix_fwd: shape mismatch");
+  GA_CHECK(!p || (p->c == 2 * zdim && p->n == q->n && p->h == q->h && p->w == q->w), "ga_latent_mix_fwd: prior tensor must have 2*zdim channels");
+  const int64_t total = numel(z);
+  if (total == 0) return 0;
+  latent_mix_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, seed, level, sample0, alpha_dev,
+      temperature, zdim, z->n, z->h, z->w, z->data, z->dtype, z->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_discmix_mean_fwd(const ga_tensor* logits, int n_mix, float* purified, const ga_tensor* cls, void* stream) {
+  GA_CHECK(logits && purified && n_mix > 0, "ga_discmix_mean_fwd: null argument");
+  GA_CHECK(logits->c == 10 * n_mix, "ga_discmix_mean_fwd: logits must have 10*n_mix channels (3-channel images)");
+  GA_CHECK(!cls || (cls->c == 3 && cls->n == logits->n && cls->h == logits->h && cls->w == logits->w), "ga_discmix_mean_fwd: classifier input must be NHWC with 3 channels");
+  const int64_t total_pix = (int64_t)logits->n * logits->h * logits->w;
+  if (total_pix == 0) return 0;
+  const size_t smem = (size_t)DM_PIX * (10 * n_mix + 1) * sizeof(float);
+  GA_CHECK(smem <= 48 * 1024, "ga_discmix_mean_fwd: too many mixtures");
+  discmix_mean_kernel<<<cdiv(total_pix, DM_PIX), 128, smem, (cudaStream_t)stream>>>(
+      logits->data, logits->dtype, n_mix, logits->h * logits->w, total_pix, purified, cls ? cls->data : nullptr,
+      cls ? cls->dtype : GA_F32);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_upsample_nearest2x(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && out->h == 2 * in->h && out->w == 2 * in->w && out->c == in->c && out->n == in->n && (in->c % 4) == 0,
+           "ga_upsample_nearest2x: shape mismatch");
+  const int64_t total = numel(out) / 4;
+  if (total == 0) return 0;
+  upsample_nearest2x_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, out->data, out->dtype, in->n, in->h, in->w, in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_upsample_bilinear2x(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && out->h == 2 * in->h && out->w == 2 * in->w && out->c == in->c && out->n == in->n && (in->c % 4) == 0,
+           "ga_upsample_bilinear2x: shape mismatch");
+  const int64_t total = numel(out) / 4;
+  if (total == 0) return 0;
+  upsample_bilinear2x_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, out->data, out->dtype, in->n, in->h, in->w, in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_maxpool2x2(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && out->h == in->h / 2 && out->w == in->w / 2 && out->c == in->c && out->n == in->n && (in->c % 4) == 0,
+           "ga_maxpool2x2: shape mismatch");
+  const int64_t total = numel(out) / 4;
+  if (total == 0) return 0;
+  maxpool2x2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, out->data, out->dtype, in->n, in->h, in->w, in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_affine_act(const ga_tensor* in, const float* scale, const float* shift, int act, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && same_shape(in, out), "ga_affine_act: shape mismatch");
+  GA_CHECK((scale == nullptr) == (shift == nullptr), "ga_affine_act: scale and shift go together");
+  const int64_t total = numel(in);
+  if (total == 0) return 0;
+  affine_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_cast(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  return ga_affine_act(in, nullptr, nullptr, GA_ACT_NONE, out, stream);
+}
+
+extern "C" int ga_nchw_to_nhwc(const float* in, const ga_tensor* out, float scale, float shift, void* stream) {
+  GA_CHECK(in && out, "ga_nchw_to_nhwc: null argument");
+  const int64_t total = numel(out);
+  if (total == 0) return 0;
+  nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out->data, out->dtype, scale, shift, out->n, out->c, out->h, out->w);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_pgd_linf_step(float* x_adv, const float* grad, const float* x_nat, float step, float eps, int64_t numel_, void* stream) {
+  GA_CHECK(x_adv && grad && x_nat && numel_ >= 0, "ga_pgd_linf_step: null argument");
+  if (numel_ == 0) return 0;
+  GA_CHECK(((((uintptr_t)x_adv) | ((uintptr_t)grad) | ((uintptr_t)x_nat)) & 15) == 0, "ga_pgd_linf_step: buffers must be 16-byte aligned");
+  const int64_t n4 = numel_ / 4;
+  pgd_linf_step_kernel<<<max(1, cdiv(n4, 256)), 256, 0, (cudaStream_t)stream>>>(x_adv, grad, x_nat, step, eps, n4, numel_);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_softmax_xent(const float* logits, const int64_t* labels, int n, int classes, float* loss, float* dlogits,
+                               int32_t* pred, unsigned long long* n_correct, void* stream) {
+  GA_CHECK(logits && n >= 0 && classes > 0, "ga_softmax_xent: bad arguments");
+  if (n == 0) return 0;
+  softmax_xent_kernel<<<cdiv((int64_t)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(logits, labels, n, classes, loss, dlogits, pred, n_correct);
+  GA_LAUNCH_OK();
+  return 0;
+}

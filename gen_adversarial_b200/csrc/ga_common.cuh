@@ -1,0 +1,155 @@
+// Shared device/host helpers for libga_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/ga_b200.h"
+
+namespace ga {
+
+// ----------------------------------------------------------------------------- host-side error plumbing
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define GA_CHECK(cond, ...)                         \
+  do {                                              \
+    if (!(cond)) {                                  \
+      ::ga::set_error(__VA_ARGS__);                 \
+      return 1;                                     \
+    }                                               \
+  } while (0)
+
+#define GA_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::ga::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e), \
+                      cudaGetErrorString(_e));                                          \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+// call after every kernel launch
+#define GA_LAUNCH_OK()                 \
+  do {                                 \
+    ::ga::count_launch();              \
+    GA_CUDA(cudaPeekAtLastError());    \
+  } while (0)
+
+static inline int64_t numel(const ga_tensor* t) { return (int64_t)t->n * t->h * t->w * t->c; }
+static inline bool same_shape(const ga_tensor* a, const ga_tensor* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ----------------------------------------------------------------------------- device math
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float eluf_(float x) { return x > 0.0f ? x : expm1f(x); }
+__device__ __forceinline__ float softclamp5_(float x) { return 5.0f * tanhf(x * 0.2f); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case GA_ACT_SILU: return siluf_(v);
+    case GA_ACT_ELU: return eluf_(v);
+    case GA_ACT_RELU: return fmaxf(v, 0.0f);
+    default: return v;
+  }
+}
+// derivative of act w.r.t. its pre-activation input v
+__device__ __forceinline__ float act_grad(float v, int act) {
+  switch (act) {
+    case GA_ACT_SILU: {
+      float s = sigmoidf_(v);
+      return s * (1.0f + v * (1.0f - s));
+    }
+    case GA_ACT_ELU: return v > 0.0f ? 1.0f : expf(v);
+    case GA_ACT_RELU: return v > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+
+// ----------------------------------------------------------------------------- typed loads / stores
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 4 consecutive elements (16-byte fp32 / 8-byte bf16); caller guarantees alignment
+template <typename T> __device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&a);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ----------------------------------------------------------------------------- counter-based RNG (Philox4x32-10)
+// Stream is keyed by (seed, stream id, element counter) so results do not depend on launch geometry or on
+// how a batch is sharded over GPUs ("per-GPU seeded eps streams keyed by global sample index").
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, uint32_t (&out)[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// four N(0,1) draws for counter block `blk` of stream (seed, stream)
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t blk, float (&z)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  float u0 = ((float)r[0] + 0.5f) * k, u1 = ((float)r[1] + 0.5f) * k;
+  float u2 = ((float)r[2] + 0.5f) * k, u3 = ((float)r[3] + 0.5f) * k;
+  float m0 = sqrtf(-2.0f * __logf(u0)), m1 = sqrtf(-2.0f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  z[0] = m0 * c0; z[1] = m0 * s0; z[2] = m1 * c1; z[3] = m1 * s1;
+}
+// scalar convenience: element `idx` of the stream
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t stream, uint64_t idx) {
+  float z[4];
+  philox_normal4(seed, stream, idx >> 2, z);
+  return z[idx & 3];
+}
+
+}  // namespace ga

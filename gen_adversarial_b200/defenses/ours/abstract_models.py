@@ -1,0 +1,184 @@
+"""Abstract defense-module API -- same names, constructor arguments, attributes and error behaviour as
+/root/reference/src/defenses/ours/abstract_models.py (BaseClassificationModel :13-62, MLVGMDefenseModel :65-193),
+with the compute routed through libga_b200.so (no torch/kornia arithmetic on the hot path, no CPU fallback).
+"""
+from __future__ import annotations
+
+import os
+from abc import ABC, abstractmethod
+from typing import Union
+
+import torch
+from torch import nn
+
+from ... import ops
+
+
+def default_mode() -> str:
+    """compute mode of the CUDA path: "bf16" (tcgen05 tensor cores, 1e-2 tolerance) or "fp32" (exact SIMT path)."""
+    m = os.environ.get("GA_B200_MODE", "bf16")
+    if m not in ("bf16", "fp32"):
+        raise ValueError(f"GA_B200_MODE must be bf16 or fp32, got {m}")
+    return m
+
+
+class BaseClassificationModel(ABC):
+
+    def __init__(self, model_path: str, device: str, mean: tuple = None, std: tuple = None):
+        """
+        Model containing only a base (pre-trained) classifier, with no additional defenses.
+
+        :param model_path: absolute path to the pretrained model (or an already loaded checkpoint dict).
+        :param device: cuda device to load the model on
+        :param mean: optional param for Normalization.
+        :param std: optional param for Normalization.
+        """
+        super().__init__()
+
+        if (mean is not None and std is None) or (mean is None and std is not None):
+            raise ValueError("to apply Normalization, please specify both mean and std.")
+
+        self.mean = torch.tensor(mean, device=device) if mean is not None else None
+        self.std = torch.tensor(std, device=device) if std is not None else None
+        self.preprocess = self.mean is not None
+        if self.preprocess and not (all(m == mean[0] for m in mean) and all(s == std[0] for s in std)):
+            raise NotImplementedError("the CUDA path supports a scalar mean/std (the reference only uses 0.5/0.5)")
+        self._norm_scale = 1.0 / float(std[0]) if self.preprocess else 1.0
+        self._norm_shift = -float(mean[0]) / float(std[0]) if self.preprocess else 0.0
+
+        self.classifier = self.load_classifier(model_path, device)
+
+    @abstractmethod
+    def load_classifier(self, model_path: str, device: str):
+        """custom method to load the pretrained classifier -> engine object with `.forward(x_nhwc)`."""
+        pass
+
+    def set_device(self, device: str):
+        """the engines are bound to their device at load time; moving is only allowed to the same device."""
+        if torch.device(device) != self.classifier.device:
+            if torch.device(device).type == "cuda" and torch.device(device).index in (None, self.classifier.device.index):
+                return
+            raise RuntimeError(f"classifier was loaded on {self.classifier.device}; reload it to use {device}")
+
+    def classify_nhwc(self, x_nhwc: torch.Tensor) -> torch.Tensor:
+        """normalised NHWC activations -> logits (used by the fused defense path)."""
+        return self.classifier.forward(x_nhwc)
+
+    def __call__(self, batch: torch.Tensor) -> torch.Tensor:
+        """
+        :param batch: image tensor of shape (B C H W)
+        :return un-normalized predictions of shape (B N_CLASSES)
+        """
+        if batch.requires_grad and torch.is_grad_enabled():
+            from ...autograd import classifier_apply
+            return classifier_apply(self, batch)
+        x = ops.nchw_to_nhwc(batch.detach().to(torch.float32), self.classifier.adt, self._norm_scale, self._norm_shift)
+        return self.classifier.forward(x)
+
+
+class MLVGMDefenseModel(ABC):
+
+    def __init__(self, classifier: BaseClassificationModel, autoencoder_path: str,
+                 interpolation_alphas: tuple, alpha_attenuation: float = 1.0,
+                 initial_noise_eps: float = 0.0, apply_gaussian_blur: bool = False, device: str = 'cpu',
+                 mean: tuple = None, std: tuple = None):
+        """
+        Model composed of HL-Autoencoder + CNN (see the reference docstring, abstract_models.py:71-87).
+        """
+        super().__init__()
+
+        self.eps = initial_noise_eps
+        self.blur_input = apply_gaussian_blur
+
+        self.device = device
+
+        self.classifier = classifier
+        self.classifier.set_device(device)
+
+        if (mean is not None and std is None) or (mean is None and std is not None):
+            raise ValueError("to apply Normalization/Denormalization, please specify both mean and std.")
+
+        self.mean = torch.tensor(mean, device=device) if mean is not None else None
+        self.std = torch.tensor(std, device=device) if std is not None else None
+        self.preprocess = self.mean is not None
+        self.postprocess = self.mean is not None
+
+        self.interpolation_alphas = [a * alpha_attenuation for a in interpolation_alphas]
+        self.autoencoder = self.load_autoencoder(autoencoder_path, device)
+
+        # ---- CUDA-path state (not part of the reference API)
+        self._alpha_key = None
+        self._alpha_dev = None
+        self._alpha_pinned = None
+        self._explicit_noise = None
+        self._taps_cache = {}
+        self.noise_seed = None          # None: a fresh seed is drawn from torch's CPU generator on every call
+        self.sample_offset = 0          # global index of sample 0 (data-parallel shards keep results G-independent)
+
+    @abstractmethod
+    def load_autoencoder(self, model_path: str, device: str):
+        pass
+
+    @abstractmethod
+    def purify(self, batch: torch.Tensor) -> torch.Tensor:
+        pass
+
+    # ------------------------------------------------------------------ CUDA-path helpers
+    def set_explicit_noise(self, noises):
+        """Parity/test hook: the next call consumes these N(0,1) tensors (reference draw order)
+        instead of the in-kernel Philox stream.  Pass None to go back to Philox."""
+        self._explicit_noise = None if noises is None else [t.to(self.device, torch.float32).contiguous() for t in noises]
+
+    def _alphas_device(self) -> torch.Tensor:
+        """`interpolation_alphas` is a plain list that callers reassign between calls (common_utils.py:88); the
+        kernels read alphas from device memory, refreshed here only when the list changed."""
+        key = tuple(float(a) for a in self.interpolation_alphas)
+        if key != self._alpha_key:
+            if self._alpha_pinned is None or self._alpha_pinned.numel() != len(key):
+                self._alpha_pinned = torch.empty(len(key), dtype=torch.float32).pin_memory()
+                self._alpha_dev = torch.empty(len(key), dtype=torch.float32, device=self.device)
+            self._alpha_pinned.copy_(torch.tensor(key, dtype=torch.float32))
+            self._alpha_dev.copy_(self._alpha_pinned, non_blocking=True)
+            self._alpha_key = key
+        return self._alpha_dev
+
+    def _next_seed(self) -> int:
+        if self.noise_seed is not None:
+            return int(self.noise_seed)
+        return int(torch.empty((), dtype=torch.int64).random_().item())
+
+    # ------------------------------------------------------------------ reference API
+    def add_gaussian_noise(self, x: torch.Tensor) -> torch.Tensor:
+        """abstract_models.py:129-143 (N(0,1) noise scaled to L2 norm eps per sample, clamp to [0,1])."""
+        noise = self._explicit_noise[0] if self._explicit_noise is not None else None
+        out, _ = ops.preprocess(x.to(torch.float32), noise, float(self.eps), False, torch.float32, seed=self._next_seed(),
+                                sample0=self.sample_offset, normalize=False)
+        return out.permute(0, 3, 1, 2).contiguous()
+
+    def apply_gaussian_blur(self, x: torch.Tensor) -> torch.Tensor:
+        """abstract_models.py:145-159."""
+        if not self.blur_input:
+            return x
+        out, _ = ops.preprocess(x.to(torch.float32), None, 0.0, True, torch.float32, normalize=False, taps_cache=self._taps_cache)
+        # NOTE: the fused kernel also clamps to [0,1]; a blur of values in [0,1] stays in [0,1]
+        return out.permute(0, 3, 1, 2).contiguous()
+
+    def __call__(self, batch: torch.Tensor, preds_only: bool = True) \
+            -> Union[torch.Tensor, [torch.Tensor, torch.Tensor]]:
+        """
+        :param batch: image tensor of shape (B C H W)
+        :return if preds only: un-normalized predictions (B, N_CLASSES) computed on the purified images,
+                else: (predictions, purified images (B, C, H, W))
+        """
+        if batch.requires_grad and torch.is_grad_enabled():
+            from ...autograd import defense_apply
+            preds, purified = defense_apply(self, batch)
+        else:
+            preds, purified = self._forward_cuda(batch.detach())
+        if preds_only:
+            return preds
+        return preds, purified
+
+    @abstractmethod
+    def _forward_cuda(self, batch: torch.Tensor, tape=None):
+        pass

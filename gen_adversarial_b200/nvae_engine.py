@@ -1,0 +1,277 @@
+"""Host-side driver of the NVAE purification path on the hand-written CUDA kernels.
+
+Mirrors `NVAEDefenseModel.purify` (/root/reference/src/defenses/ours/models.py:160-274) op for op, but on
+folded weights (fold.py) and NHWC tensors, calling only entry points of libga_b200.so.
+
+Two product modes:
+  * "fp32": every tensor fp32, every convolution through the SIMT implicit-GEMM kernel (exact-arithmetic path,
+            tolerance 1e-4 on purified images, identical accuracy counts);
+  * "bf16": GEMM operands bf16, accumulation fp32, residual stream kept in fp32; convolutions through the
+            tcgen05/TMEM/TMA kernel wherever the problem fits it (everything except the 3-channel stem and the
+            stride-2 cells), tolerance 1e-2 on purified images.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from ._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
+from .fold import Folder, round_up
+from .nvae_spec import NvaeSpec, EncCell, DecCell
+
+_PRE_TO_ACT = {PRE_ELU: ACT_ELU, PRE_SILU: ACT_SILU, PRE_AFFINE_SILU: ACT_SILU}
+
+
+class _Enc:
+    __slots__ = ("c1", "c2", "se", "skip", "down", "pre_affine")
+
+
+class _Dec:
+    __slots__ = ("e", "dw_w", "dw_b", "p", "se", "skip", "up")
+
+
+class NvaeEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], spec: NvaeSpec, device, mode: str = "fp32",
+                 temperature: float = 0.6, _host_logic_test: bool = False):
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(f"unknown mode {mode}")
+        if spec.use_nf:
+            raise NotImplementedError("normalizing-flow cells are not supported")
+        self.spec = spec
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and not _host_logic_test:   # (tests/emu_ops.py drives the host logic on CPU)
+            raise RuntimeError("NvaeEngine runs only on CUDA devices: there is no CPU fallback")
+        self.mode = mode
+        self.bf16 = mode == "bf16"
+        self.adt = torch.bfloat16 if self.bf16 else torch.float32      # activation dtype
+        self.temperature = float(temperature)
+        self.zc = round_up(spec.z, 8)
+        self.taps: Optional[dict] = None
+        f = Folder(state_dict, self.device, want_tc=self.bf16)
+        self._fold(f)
+        self._prior_cache = {}
+
+    # ------------------------------------------------------------------ weight preparation
+    def _fold_enc(self, f: Folder, cell: EncCell) -> _Enc:
+        p = cell.prefix
+        e = _Enc()
+        e.down = cell.down
+        a1, b1 = f.bn(f"{p}.residual.0")
+        w1, bias1 = f.wn(f"{p}.residual.2")
+        a2, b2 = f.bn(f"{p}.residual.3")
+        w1 = w1 * a2.view(-1, 1, 1, 1)
+        bias1 = bias1 * a2 + b2
+        e.pre_affine = (f.dev32(a1), f.dev32(b1))
+        e.c1 = f.conv(w1, bias1, stride=2 if cell.down else 1, pad=1, pre_op=PRE_AFFINE_SILU, pre_affine=(a1, b1),
+                      post_act=ACT_SILU, name=p + ".conv1")
+        w2, bias2 = f.wn(f"{p}.residual.5")
+        e.c2 = f.conv(w2, bias2, stride=1, pad=1, name=p + ".conv2")
+        e.se = f.se(f"{p}.residual.6")
+        e.skip = None
+        if cell.down:
+            ws, bs = f.wn(f"{p}.skip_connection.conv")
+            e.skip = f.conv(ws, bs, stride=2, pad=0, pre_op=PRE_SILU, name=p + ".skip")
+        return e
+
+    def _fold_dec(self, f: Folder, cell: DecCell) -> _Dec:
+        p, o = cell.prefix, cell.off
+        d = _Dec()
+        d.up = cell.up
+        a0, b0 = f.bn(f"{p}.residual.{0 + o}")
+        we = f.f64(f"{p}.residual.{1 + o}.weight")                   # [H, C, 1, 1]
+        a1, b1 = f.bn(f"{p}.residual.{2 + o}")
+        be = a1 * (we[:, :, 0, 0] @ b0) + b1
+        we = we * a1.view(-1, 1, 1, 1) * a0.view(1, -1, 1, 1)
+        d.e = f.conv(we, be, post_act=ACT_SILU, name=p + ".expand")
+        wd = f.f64(f"{p}.residual.{4 + o}.weight")                   # [H, 1, 5, 5]
+        a2, b2 = f.bn(f"{p}.residual.{5 + o}")
+        wd = wd[:, 0] * a2.view(-1, 1, 1)
+        d.dw_w = f.dev32(wd.permute(1, 2, 0).reshape(25, -1))        # [25][H]
+        d.dw_b = f.dev32(b2)
+        wp = f.f64(f"{p}.residual.{7 + o}.weight")                   # [Cout, H, 1, 1]
+        a3, b3 = f.bn(f"{p}.residual.{8 + o}")
+        d.p = f.conv(wp * a3.view(-1, 1, 1, 1), b3, name=p + ".project")
+        d.se = f.se(f"{p}.residual.{9 + o}")
+        d.skip = None
+        if cell.up:
+            ws, bs = f.wn(f"{p}.skip_connection.conv")
+            d.skip = f.conv(ws, bs, name=p + ".skip")
+        return d
+
+    def _fold(self, f: Folder):
+        spec = self.spec
+        w, b = f.wn("preprocessing_block.init_conv")
+        self.init_conv = f.conv(w, b, pad=1, name="init_conv")
+        self.pre_cells = [self._fold_enc(f, c) for c in spec.pre_cells]
+        self.enc_scales = []
+        for sc in spec.enc_scales:
+            groups = [[self._fold_enc(f, c) for c in grp] for grp in sc["groups"]]
+            down = self._fold_enc(f, sc["down"]) if sc["down"] is not None else None
+            self.enc_scales.append({"s": sc["s"], "groups": groups, "down": down})
+        w, b = f.wn("encoder_0.1")
+        self.enc0 = f.conv(w, b, pre_op=PRE_ELU, post_act=ACT_ELU, name="encoder_0")
+        self.levels = []
+        z = spec.z
+        for lvl in spec.levels:
+            L = {"s": lvl.s, "g": lvl.g, "res": lvl.res, "channels": lvl.channels}
+            w, b = f.wn(f"enc_sampler.sampler_{lvl.s}:{lvl.g}")
+            L["enc_sampler"] = f.conv(w[:z], b[:z], pad=1, name=f"enc_sampler_{lvl.s}:{lvl.g}")     # mu half only
+            w, b = f.wn(f"decoder_combiners.combiner_{lvl.s}:{lvl.g}.conv")
+            c = lvl.channels
+            wx = w[:, :c]
+            wz = torch.zeros((c, self.zc), dtype=torch.float64)
+            wz[:, :z] = w[:, c:, 0, 0]
+            L["dec_comb"] = f.conv(wx, b, name=f"dec_comb_{lvl.s}:{lvl.g}", w2=wz)
+            L["dec_comb_z"] = f.conv(wz.view(c, self.zc, 1, 1), None, name=f"dec_comb_z_{lvl.s}:{lvl.g}")
+            if not (lvl.s == 0 and lvl.g == 0):
+                w, b = f.wn(f"encoder_combiners.combiner_{lvl.s}:{lvl.g}.conv")
+                L["enc_comb"] = f.conv(w, b, name=f"enc_comb_{lvl.s}:{lvl.g}")
+                w, b = f.wn(f"dec_sampler.sampler_{lvl.s}:{lvl.g}.1")
+                L["dec_sampler"] = f.conv(w, b, pre_op=PRE_ELU, name=f"dec_sampler_{lvl.s}:{lvl.g}")
+                L["cells"] = [self._fold_dec(f, c) for c in lvl.cells]
+            else:
+                # the constant prior goes through the x-half of combiner_0:0 once, at load (models.py:215-218)
+                prior = f.f64("const_prior")                                        # [1, C, r, r]
+                px = torch.einsum("oc,chw->hwo", wx[:, :, 0, 0], prior[0]) + b      # [r, r, C]
+                L["prior_x"] = f.dev32(px.unsqueeze(0))
+            self.levels.append(L)
+        self.up_cells = {s: self._fold_dec(f, c) for s, c in spec.up_cells.items()}
+        self.post_cells = [self._fold_dec(f, c) for c in spec.post_cells]
+        w, b = f.wn("to_logits.1")
+        self.to_logits = f.conv(w, b, pad=1, pre_op=PRE_ELU, name="to_logits")
+
+    # ------------------------------------------------------------------ op dispatch
+    def _tap(self, name, t):
+        if self.taps is not None:
+            self.taps[name] = t.detach().float().permute(0, 3, 1, 2).contiguous()
+
+    def _conv(self, x, L: ops.ConvLayer, add=None, want_act=True, want_f32=False, x2=None, aux: ops.ConvLayer = None):
+        """-> (out in activation dtype | None, out fp32 | None).  fp32 mode: both are the same tensor."""
+        if not self.bf16:
+            if x2 is not None:
+                add = ops.conv2d_simt(x2, aux, torch.float32, add=add)
+            o = ops.conv2d_simt(x, L, torch.float32, add=add)
+            return o, o
+        xin = x
+        tc_possible = L.w_tc is not None
+        if tc_possible:
+            if L.pre_op != PRE_NONE:
+                xin = ops.affine_act(x, L.pre_scale, L.pre_shift, _PRE_TO_ACT[L.pre_op], torch.bfloat16)
+            elif x.dtype != torch.bfloat16:
+                xin = ops.cast(x, torch.bfloat16)
+            if ops.conv2d_tc_supported(xin, L, x2):
+                return ops.conv2d_tc(xin, L, want_bf16=want_act, want_f32=want_f32, add=add, x2=x2)
+        # SIMT (3-channel stem, stride-2 cells, odd shapes): applies the pre-op itself
+        if x2 is not None:
+            add = ops.conv2d_simt(x2, aux, torch.float32, add=add)
+        ob = ops.conv2d_simt(x, L, torch.bfloat16, add=add) if want_act else None
+        of = ops.conv2d_simt(x, L, torch.float32, add=add) if want_f32 else None
+        return ob, of
+
+    def _enc_cell(self, x32, act, e: _Enc, next_affine):
+        """x32: fp32 residual stream.  act: SiLU(BN1(x)) already materialised (bf16 mode) or None."""
+        if self.bf16 and e.c1.w_tc is not None and act is not None and ops.conv2d_tc_supported(act, e.c1):
+            h, _ = ops.conv2d_tc(act, e.c1)
+        else:
+            h, _ = self._conv(x32, e.c1)
+        r, _ = self._conv(h, e.c2)
+        if e.down:
+            _, skip = self._conv(x32, e.skip, want_act=False, want_f32=True)
+        else:
+            skip = x32
+        sums = ops.channel_sum(r)
+        out, _, act_next, _ = ops.se_residual(r, sums, e.se, 0.1, skip, torch.float32,
+                                              act_affine=next_affine if self.bf16 else None)
+        return out, act_next
+
+    def _dec_cell(self, x32, xa, d: _Dec):
+        """x32: fp32 residual stream; xa: same values in the activation dtype (GEMM operand)."""
+        h1, _ = self._conv(xa, d.e)                                   # low resolution for up cells (exact commute)
+        h2 = ops.dwconv5x5(h1, d.dw_w, d.dw_b, ACT_SILU, d.up, self.adt)
+        r, _ = self._conv(h2, d.p)
+        if d.up:
+            _, s = self._conv(xa, d.skip, want_act=False, want_f32=True)
+            skip = ops.upsample_bilinear2x(s)
+        else:
+            skip = x32
+        sums = ops.channel_sum(r)
+        out, out2, _, _ = ops.se_residual(r, sums, d.se, 0.1, skip, torch.float32, want_out2=self.bf16)
+        return out, (out2 if self.bf16 else out)
+
+    def _enc_sequence(self):
+        """encoder cells in execution order with the stash / scale boundaries (models.py:176-192)."""
+        seq = [("cell", e, None) for e in self.pre_cells]
+        for sc in self.enc_scales:
+            for g, grp in enumerate(sc["groups"]):
+                for i, e in enumerate(grp):
+                    stash = (sc["s"], g) if (i == len(grp) - 1 and not (sc["s"] == 0 and g == 0)) else None
+                    seq.append(("cell", e, stash))
+            if sc["down"] is not None:
+                seq.append(("cell", sc["down"], None))
+        return seq
+
+    # ------------------------------------------------------------------ forward
+    def purify(self, x_nhwc: torch.Tensor, alphas_dev: torch.Tensor, eps_levels: Optional[Sequence[torch.Tensor]] = None,
+               seed: int = 0, sample0: int = 0, cls_dtype=None, tape=None):
+        """x_nhwc: pre-processed, normalised input (N,H,W,3) in the activation dtype.
+        alphas_dev: fp32 device tensor [n_latents] (already attenuated) -- read by the kernels at run time, so it
+        can be changed between calls without re-capturing anything (alpha_learning/common_utils.py:88).
+        eps_levels: explicit N(0,1) draws per level in NCHW (parity mode) or None (Philox in-kernel).
+        -> (purified NCHW fp32 in [0,1], classifier input NHWC or None)"""
+        spec = self.spec
+        n = x_nhwc.shape[0]
+        x32 = ops.conv2d_simt(x_nhwc, self.init_conv, torch.float32)
+        self._tap("init_conv", x32)
+        seq = self._enc_sequence()
+        stash = {}
+        act = None
+        for i, (_, e, st) in enumerate(seq):
+            nxt = seq[i + 1][1].pre_affine if (i + 1 < len(seq) and not seq[i + 1][1].down) else None
+            x32, act = self._enc_cell(x32, act, e, nxt)
+            if st is not None:
+                stash[st] = x32
+            if i == len(self.pre_cells) - 1:
+                self._tap("pre", x32)
+        # encoder_0 (models.py:195)
+        xa, _ = self._conv(x32, self.enc0)
+        self._tap("enc0", xa)
+        lv0 = self.levels[0]
+        _, muq = self._conv(xa, lv0["enc_sampler"], want_act=False, want_f32=True)
+        z = ops.latent_mix(muq, None, eps_levels[0] if eps_levels is not None else None, seed, 0, sample0,
+                           alphas_dev[0:1], self.temperature, spec.z, self.zc, self.adt)
+        self._tap("z0", z[..., :spec.z])
+        key = (n,)
+        if key not in self._prior_cache:
+            self._prior_cache = {key: lv0["prior_x"].expand(n, -1, -1, -1).contiguous()}
+        prior_x = self._prior_cache[key]
+        if self.bf16:
+            xa, x32 = self._conv(z, lv0["dec_comb_z"], add=prior_x, want_act=True, want_f32=True)
+        else:
+            x32 = ops.conv2d_simt(z, lv0["dec_comb_z"], torch.float32, add=prior_x)
+            xa = x32
+        idx = 1
+        for s in range(spec.num_scales):
+            for L in self.levels:
+                if L["s"] != s or (L["s"] == 0 and L["g"] == 0):
+                    continue
+                for d in L["cells"]:
+                    x32, xa = self._dec_cell(x32, xa, d)
+                comb, _ = self._conv(xa, L["enc_comb"], add=stash[(L["s"], L["g"])])
+                _, muq = self._conv(comb, L["enc_sampler"], want_act=False, want_f32=True)
+                _, pp = self._conv(x32, L["dec_sampler"], want_act=False, want_f32=True)
+                z = ops.latent_mix(muq, pp, eps_levels[idx] if eps_levels is not None else None, seed, idx, sample0,
+                                   alphas_dev[idx:idx + 1], self.temperature, spec.z, self.zc, self.adt)
+                self._tap(f"z{idx}", z[..., :spec.z])
+                xa, x32 = self._conv(xa, L["dec_comb"], want_act=True, want_f32=True, x2=z, aux=L["dec_comb_z"])
+                idx += 1
+            if s in self.up_cells:
+                x32, xa = self._dec_cell(x32, xa, self.up_cells[s])
+        self._tap("dec_out", x32)
+        for d in self.post_cells:
+            x32, xa = self._dec_cell(x32, xa, d)
+        self._tap("post", x32)
+        _, logits = self._conv(x32, self.to_logits, want_act=False, want_f32=True)
+        self._tap("logits", logits)
+        return ops.discmix_mean(logits, spec.num_mixtures, cls_dtype)

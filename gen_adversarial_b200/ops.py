@@ -1,0 +1,270 @@
+"""Thin Python wrappers over the C-ABI (include/ga_b200.h): torch owns memory and streams, the kernels are ours.
+
+Tensors handled here are dense NHWC `torch.Tensor`s of shape (N, H, W, C), dtype float32 or bfloat16, on a
+CUDA device.  Every wrapper launches on `torch.cuda.current_stream()` and raises RuntimeError on failure;
+nothing here ever falls back to a torch/CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GaTensor, GaConvDesc, GA_F32, GA_BF16, PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, \
+    ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return GA_F32
+    if t.dtype == torch.bfloat16:
+        return GA_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def gt(t: Optional[torch.Tensor]):
+    """torch NHWC tensor -> POINTER(GaTensor) (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libga_b200 ops need CUDA tensors (no CPU fallback exists)")
+    if t.dim() != 4 or not t.is_contiguous():
+        raise RuntimeError(f"expected a contiguous NHWC tensor, got shape {tuple(t.shape)} strides {t.stride()}")
+    n, h, w, c = t.shape
+    return ctypes.pointer(GaTensor(t.data_ptr(), _dt(t), n, h, w, c))
+
+
+def ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libga_b200 ops need CUDA tensors (no CPU fallback exists)")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def torch_dtype(name: str):
+    return {"fp32": torch.float32, "bf16": torch.bfloat16}[name]
+
+
+@dataclass
+class ConvLayer:
+    """A folded convolution living on the device."""
+    kh: int
+    kw: int
+    stride: int
+    pad: int
+    cin: int
+    cout: int
+    w_simt: Optional[torch.Tensor] = None      # fp32 [kh*kw*cin, cout]
+    w_tc: Optional[torch.Tensor] = None        # bf16 [cout, ktot]  (ktot = kh*kw*cin + cin2)
+    bias: Optional[torch.Tensor] = None        # fp32 [cout]
+    pre_op: int = PRE_NONE
+    pre_scale: Optional[torch.Tensor] = None   # fp32 [cin]
+    pre_shift: Optional[torch.Tensor] = None
+    post_act: int = ACT_NONE
+    up: int = 1
+    cin2: int = 0                              # channels of the second (1x1) K source folded into w_tc
+    name: str = ""
+
+    def desc(self, tc: bool) -> GaConvDesc:
+        w = self.w_tc if tc else self.w_simt
+        if w is None:
+            raise RuntimeError(f"conv layer {self.name}: no {'tensor-core' if tc else 'SIMT'} weights prepared")
+        return GaConvDesc(self.kh, self.kw, self.stride, self.pad, self.up, PRE_NONE if tc else self.pre_op, self.post_act,
+                          ptr(self.pre_scale), ptr(self.pre_shift), w.data_ptr(), ptr(self.bias), 0,
+                          w.shape[1] if tc else 0)
+
+
+def conv_out_hw(L: ConvLayer, h: int, w: int):
+    hu, wu = (h - 1) * L.up + 1, (w - 1) * L.up + 1
+    return (hu + 2 * L.pad - L.kh) // L.stride + 1, (wu + 2 * L.pad - L.kw) // L.stride + 1
+
+
+def conv2d_simt(x: torch.Tensor, L: ConvLayer, out_dtype: torch.dtype, add: Optional[torch.Tensor] = None,
+                out_hw=None) -> torch.Tensor:
+    n, h, w, c = x.shape
+    assert c == L.cin, (L.name, c, L.cin)
+    ho, wo = out_hw if out_hw is not None else conv_out_hw(L, h, w)
+    out = torch.empty((n, ho, wo, L.cout), device=x.device, dtype=out_dtype)
+    d = L.desc(False)
+    _lib.check(_lib.lib().ga_conv2d_simt(gt(x), ctypes.byref(d), gt(add), gt(out), stream()), f"conv2d_simt[{L.name}]")
+    return out
+
+
+def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor] = None) -> bool:
+    if L.w_tc is None or x.dtype != torch.bfloat16:
+        return False
+    d = L.desc(True)
+    return bool(_lib.lib().ga_conv2d_tc_supported(gt(x), gt(x2), ctypes.byref(d), L.cout))
+
+
+def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
+              add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None):
+    """-> (out_bf16 or None, out_f32 or None)"""
+    n, h, w, c = x.shape
+    assert c == L.cin, (L.name, c, L.cin)
+    ob = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    of = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.float32) if want_f32 else None
+    d = L.desc(True)
+    _lib.check(_lib.lib().ga_conv2d_tc(gt(x), gt(x2), ctypes.byref(d), gt(add), gt(ob), gt(of), stream()),
+               f"conv2d_tc[{L.name}]")
+    return ob, of
+
+
+def dwconv5x5(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int, up: bool,
+              out_dtype: torch.dtype) -> torch.Tensor:
+    n, h, w, c = x.shape
+    s = 2 if up else 1
+    out = torch.empty((n, h * s, w * s, c), device=x.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_dwconv5x5_fwd(gt(x), ptr(weight), ptr(bias), act, int(up), gt(out), stream()), "dwconv5x5")
+    return out
+
+
+def channel_sum(r: torch.Tensor) -> torch.Tensor:
+    sums = torch.empty((r.shape[0], r.shape[3]), device=r.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ga_channel_sum(gt(r), ptr(sums), stream()), "channel_sum")
+    return sums
+
+
+def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
+                act_affine=None, act_dtype=torch.bfloat16, want_gate=False):
+    """se = (w1, b1, w2, b2) fp32 device tensors.  -> (out, out2|None, act|None, gate|None)"""
+    w1, b1, w2, b2 = se
+    out = torch.empty(r.shape, device=r.device, dtype=out_dtype)
+    out2 = torch.empty(r.shape, device=r.device, dtype=out2_dtype) if want_out2 else None
+    act = torch.empty(r.shape, device=r.device, dtype=act_dtype) if act_affine is not None else None
+    gate = torch.empty((r.shape[0], r.shape[3]), device=r.device, dtype=torch.float32) if want_gate else None
+    a_s, a_b = act_affine if act_affine is not None else (None, None)
+    _lib.check(_lib.lib().ga_se_residual_fwd(gt(r), ptr(sums), ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[0], res_scale,
+                                             gt(skip), gt(out), gt(out2), gt(act), ptr(a_s), ptr(a_b), ptr(gate), stream()),
+               "se_residual")
+    return out, out2, act, gate
+
+
+def latent_mix(q, p, eps_nchw, seed: int, level: int, sample0: int, alpha_dev, temperature: float, zdim: int,
+               zc: int, out_dtype) -> torch.Tensor:
+    n, h, w, _ = q.shape
+    z = torch.empty((n, h, w, zc), device=q.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_latent_mix_fwd(gt(q), gt(p), ptr(eps_nchw), seed, level, sample0, ptr(alpha_dev), temperature,
+                                            zdim, gt(z), stream()), "latent_mix")
+    return z
+
+
+def discmix_mean(logits, n_mix: int, cls_dtype=None):
+    n, h, w, _ = logits.shape
+    purified = torch.empty((n, 3, h, w), device=logits.device, dtype=torch.float32)
+    cls = torch.empty((n, h, w, 3), device=logits.device, dtype=cls_dtype) if cls_dtype is not None else None
+    _lib.check(_lib.lib().ga_discmix_mean_fwd(gt(logits), n_mix, ptr(purified), gt(cls), stream()), "discmix_mean")
+    return purified, cls
+
+
+def upsample_nearest2x(x, out_dtype=None):
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().ga_upsample_nearest2x(gt(x), gt(out), stream()), "upsample_nearest2x")
+    return out
+
+
+def upsample_bilinear2x(x, out_dtype=None):
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().ga_upsample_bilinear2x(gt(x), gt(out), stream()), "upsample_bilinear2x")
+    return out
+
+
+def maxpool2x2(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=x.dtype)
+    _lib.check(_lib.lib().ga_maxpool2x2(gt(x), gt(out), stream()), "maxpool2x2")
+    return out
+
+
+def affine_act(x, scale, shift, act: int, out_dtype):
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_affine_act(gt(x), ptr(scale), ptr(shift), act, gt(out), stream()), "affine_act")
+    return out
+
+
+def cast(x, out_dtype):
+    return affine_act(x, None, None, ACT_NONE, out_dtype)
+
+
+def nchw_to_nhwc(x_nchw, out_dtype, scale=1.0, shift=0.0):
+    n, c, h, w = x_nchw.shape
+    out = torch.empty((n, h, w, c), device=x_nchw.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_nchw_to_nhwc(ptr(x_nchw.contiguous()), gt(out), scale, shift, stream()), "nchw_to_nhwc")
+    return out
+
+
+def gaussian_taps(h: int, max_radius: int = 12):
+    """Blur taps of abstract_models.py:145-159 (k = int(2**(sqrt(h)//2)-1), sigma=1, kornia kernel
+    exp(-t^2/2)/sum).  k = 255 at 256x256: taps beyond |t| = 12 are < 6e-32 of the peak and are dropped."""
+    import math
+    k = int(2 ** (math.sqrt(h) // 2) - 1)
+    t = torch.arange(k, dtype=torch.float64) - k // 2
+    g = torch.exp(-(t ** 2) / 2.0)
+    g = g / g.sum()
+    r = k // 2
+    if r > max_radius:
+        g = g[r - max_radius: r + max_radius + 1]
+        r = max_radius
+    return g.to(torch.float32), r
+
+
+def preprocess(x_nchw, noise_nchw, eps: float, blur: bool, out_dtype, seed: int = 0, sample0: int = 0,
+               normalize: bool = True, save_pre: bool = False, taps_cache=None):
+    """blur -> noise -> clamp -> (x-.5)/.5 in one kernel (+ the L2-norm pre-pass).  -> (out NHWC, pre NCHW|None)"""
+    L = _lib.lib()
+    n, c, h, w = x_nchw.shape
+    x_nchw = x_nchw.contiguous()
+    out = torch.empty((n, h, w, c), device=x_nchw.device, dtype=out_dtype)
+    pre = torch.empty_like(x_nchw) if save_pre else None
+    sumsq = None
+    if eps != 0.0:
+        sumsq = torch.empty((n,), device=x_nchw.device, dtype=torch.float32)
+        if noise_nchw is not None:
+            noise_nchw = noise_nchw.contiguous()
+            _lib.check(L.ga_noise_sumsq(ptr(noise_nchw), n, c * h * w, ptr(sumsq), stream()), "noise_sumsq")
+        else:
+            _lib.check(L.ga_noise_sumsq_philox(seed, sample0, n, c * h * w, ptr(sumsq), stream()), "noise_sumsq_philox")
+    taps, radius = None, 0
+    if blur:
+        if taps_cache is not None and taps_cache.get("h") == h and taps_cache["taps"].device == x_nchw.device:
+            taps, radius = taps_cache["taps"], taps_cache["radius"]
+        else:
+            t, radius = gaussian_taps(h)
+            taps = t.to(x_nchw.device)
+            if taps_cache is not None:
+                taps_cache.update({"h": h, "taps": taps, "radius": radius})
+    _lib.check(L.ga_preprocess_fwd(ptr(x_nchw), ptr(noise_nchw) if eps != 0.0 else None, ptr(sumsq), seed, sample0, eps,
+                                   ptr(taps), radius, int(normalize), gt(out), ptr(pre), stream()), "preprocess_fwd")
+    return out, pre
+
+
+def pgd_linf_step_(x_adv, grad, x_nat, step: float, eps: float):
+    assert x_adv.is_contiguous() and grad.is_contiguous() and x_nat.is_contiguous()
+    _lib.check(_lib.lib().ga_pgd_linf_step(ptr(x_adv), ptr(grad), ptr(x_nat), step, eps, x_adv.numel(), stream()), "pgd_linf_step")
+    return x_adv
+
+
+def softmax_xent(logits, labels, want_grad=True, counter=None):
+    """-> (loss[n], dlogits|None, pred[n] int32); `counter` (uint64 device scalar) accumulates argmax==label."""
+    n, k = logits.shape
+    logits = logits.contiguous()
+    loss = torch.empty((n,), device=logits.device, dtype=torch.float32)
+    dl = torch.empty_like(logits) if want_grad else None
+    pred = torch.empty((n,), device=logits.device, dtype=torch.int32)
+    _lib.check(_lib.lib().ga_softmax_xent(ptr(logits), ptr(labels), n, k, ptr(loss), ptr(dl), ptr(pred), ptr(counter), stream()),
+               "softmax_xent")
+    return loss, dl, pred
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_lib.lib().ga_launch_count(int(reset)))

@@ -1,0 +1,110 @@
+"""VGG11-bn + 4-layer head (the `ids` classifier) on the hand-written CUDA kernels.
+
+Replaces `Vgg.forward` (/root/reference/src/classifier/model.py:31-50; body = torchvision `vgg11_bn`) for the
+purification path: conv3x3+BN+ReLU (BN folded) x8, 2x2 max-pools, AdaptiveAvgPool2d(7) + flatten +
+Linear(25088,25088,bias=False) + BatchNorm1d + ReLU + Linear(25088,n_classes).
+
+Exact load-time rewrites:
+  * eval BN2d folded into the preceding conv, BN1d into the first head linear;
+  * AdaptiveAvgPool2d(7) + NCHW flatten folded into the first head linear: for a (h x w) feature map the pooled
+    vector is a fixed linear map P (7 x h) (x) P (7 x w) of the map, so W_eff[o, (p,q,c)] = sum_ij W[o, c*49+i*7+j]
+    P[i,p] P[j,q].  At 64x64 inputs (2x2 map) this turns the 25088x25088 GEMM into 25088x2048 (12x fewer FLOPs
+    and weight bytes); roofline fractions in bench.py still use the unfolded FLOP count.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import ops
+from ._lib import ACT_NONE, ACT_RELU
+from .fold import Folder, BN_EPS
+from .synth import vgg11_feature_layout
+
+
+def adaptive_pool_matrix(out: int, inp: int) -> torch.Tensor:
+    """P[i, p] of torch's AdaptiveAvgPool (window [floor(i*inp/out), ceil((i+1)*inp/out)) )."""
+    P = torch.zeros((out, inp), dtype=torch.float64)
+    for i in range(out):
+        s = (i * inp) // out
+        e = -((-(i + 1) * inp) // out)
+        P[i, s:e] = 1.0 / (e - s)
+    return P
+
+
+class Vgg11Engine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, mode: str = "fp32", in_hw: int = 64,
+                 _host_logic_test: bool = False):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and not _host_logic_test:   # (tests/emu_ops.py drives the host logic on CPU)
+            raise RuntimeError("Vgg11Engine runs only on CUDA devices: there is no CPU fallback")
+        self.mode = mode
+        self.bf16 = mode == "bf16"
+        self.adt = torch.bfloat16 if self.bf16 else torch.float32
+        sd = {(k[len("model."):] if k.startswith("model.") else k): v for k, v in state_dict.items()}
+        f = Folder(sd, self.device, want_tc=self.bf16)
+        self.layers = []
+        hw = in_hw
+        for lay in vgg11_feature_layout():
+            if lay[0] == "pool":
+                self.layers.append(("pool", None))
+                hw //= 2
+                continue
+            _, idx, cin, cout = lay
+            w = f.f64(f"features.{idx}.weight")
+            b = f.f64(f"features.{idx}.bias")
+            a, sh = f.bn(f"features.{idx + 1}")
+            self.layers.append(("conv", f.conv(w * a.view(-1, 1, 1, 1), b * a + sh, pad=1, post_act=ACT_RELU,
+                                               name=f"vgg.features.{idx}")))
+        if hw < 1:
+            raise ValueError("input too small for VGG11")
+        self.feat_hw = hw
+        self.feat_c = 512
+        # ---- head: fold avgpool(7) + flatten + BN1d into linear 0 (chunked, on the device, fp32)
+        w0 = sd["classifier.0.weight"]
+        d_out, d_in = w0.shape
+        assert d_in == 512 * 49
+        P = adaptive_pool_matrix(7, hw).to(torch.float32).to(self.device)
+        a1 = (sd["classifier.1.weight"].double() / torch.sqrt(sd["classifier.1.running_var"].double() + BN_EPS))
+        b1 = sd["classifier.1.bias"].double() - sd["classifier.1.running_mean"].double() * a1
+        a1 = a1.to(torch.float32).to(self.device)
+        k_eff = hw * hw * 512
+        w_eff = torch.empty((d_out, k_eff), dtype=torch.float32, device=self.device)
+        step = 1024
+        for r0 in range(0, d_out, step):
+            chunk = w0[r0:r0 + step].to(self.device, torch.float32).view(-1, 512, 7, 7)
+            eff = torch.einsum("ocij,ip,jq->opqc", chunk, P, P)            # NHWC flatten order (p, q, c)
+            w_eff[r0:r0 + step] = eff.reshape(eff.shape[0], -1) * a1[r0:r0 + step, None]
+        self.fc0 = ops.ConvLayer(1, 1, 1, 0, k_eff, d_out, post_act=ACT_RELU, name="vgg.classifier.0")
+        self.fc0.bias = b1.to(torch.float32).to(self.device)
+        if self.bf16:
+            self.fc0.w_tc = w_eff.to(torch.bfloat16).contiguous()
+        else:
+            self.fc0.w_simt = w_eff.t().contiguous()
+        del w_eff
+        w3 = sd["classifier.3.weight"].to(self.device, torch.float32)
+        self.n_classes = w3.shape[0]
+        self.fc1 = ops.ConvLayer(1, 1, 1, 0, d_out, self.n_classes, name="vgg.classifier.3")
+        self.fc1.bias = sd["classifier.3.bias"].to(self.device, torch.float32).contiguous()
+        self.fc1.w_simt = w3.t().contiguous()
+        if self.bf16:
+            self.fc1.w_tc = w3.to(torch.bfloat16).contiguous()
+
+    def _conv(self, x, L, out_f32=False):
+        if self.bf16 and ops.conv2d_tc_supported(x, L):
+            ob, of = ops.conv2d_tc(x, L, want_bf16=not out_f32, want_f32=out_f32)
+            return of if out_f32 else ob
+        return ops.conv2d_simt(x, L, torch.float32 if (out_f32 or not self.bf16) else torch.bfloat16)
+
+    def forward(self, x_nhwc: torch.Tensor, tape=None) -> torch.Tensor:
+        """x_nhwc: (N,H,W,3) already normalised with mean=std=0.5 (abstract_models.py:59-60). -> logits fp32 (N, classes)"""
+        x = x_nhwc
+        for kind, L in self.layers:
+            x = ops.maxpool2x2(x) if kind == "pool" else self._conv(x, L)
+        n = x.shape[0]
+        assert x.shape[1] == self.feat_hw and x.shape[2] == self.feat_hw, "input resolution differs from the one folded at load"
+        x = x.reshape(n, 1, 1, -1)
+        x = self._conv(x, self.fc0)
+        logits = self._conv(x, self.fc1, out_f32=True)
+        return logits.reshape(n, self.n_classes)

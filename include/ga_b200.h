@@ -1,0 +1,136 @@
+/*
+ * ga_b200.h -- C ABI of libga_b200.so: hand-written sm_100a CUDA kernels for the purification hot
+ * path of SerezD/gen_adversarial (preprocess -> NVAE encode -> per-level latent mix -> decode ->
+ * classify, plus the input-gradient backward and the fused PGD step).
+ *
+ * Conventions (last row):
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - The CALLER owns every buffer (PyTorch allocates, passes data_ptr()).  The library owns nothing
+ *     between calls: every entry point is stateless, launches on the caller-supplied stream, never
+ *     synchronises, and is CUDA-graph capturable.
+ *   - Activations are dense NHWC (channels innermost).  The reference-facing boundary tensors
+ *     (input batch, noise draws, purified images, gradients w.r.t. the batch) are NCHW fp32 exactly as
+ *     the reference passes them (src/defenses/ours/abstract_models.py:161-193).
+ *   - Return value 0 = ok; non-zero = error, message via ga_last_error() (thread-local).  The Python
+ *     host raises RuntimeError -- mirrors TORCH_CHECK in the reference's
+ *     src/mlvgms_autoencoders/StyleGan_E4E/stylegan2/op/fused_bias_act.cpp:7-9.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to /root/reference).
+ */
+#ifndef GA_B200_H
+#define GA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GA_ABI_VERSION 1
+
+enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
+enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3 };
+enum ga_act { GA_ACT_NONE = 0, GA_ACT_SILU = 1, GA_ACT_ELU = 2, GA_ACT_RELU = 3 };
+
+/* dense NHWC tensor view */
+typedef struct ga_tensor {
+  void* data;
+  int32_t dtype;          /* ga_dtype */
+  int32_t n, h, w, c;
+} ga_tensor;
+
+/* convolution as implicit GEMM; weights already folded (weight-norm, eval-BN) by the host */
+typedef struct ga_conv_desc {
+  int32_t kh, kw;         /* kernel size */
+  int32_t stride;         /* 1 or 2 */
+  int32_t pad;            /* zero padding (applied AFTER pre_op, as the reference pads the activated tensor) */
+  int32_t up;             /* input dilation (zero insertion) -- 2 for the dgrad of a stride-2 conv, else 1 */
+  int32_t pre_op;         /* ga_pre_op applied to the input on load */
+  int32_t post_act;       /* ga_act applied after bias (and before `add`) */
+  const float* pre_scale; /* [cin] for GA_PRE_AFFINE_SILU (folded BN a, b) */
+  const float* pre_shift;
+  const void* weight;     /* SIMT: fp32 [kh*kw*cin][cout];  tensor-core: bf16 [cout][ktot] K-major */
+  const float* bias;      /* [cout] or NULL */
+  int32_t reserved0;
+  int32_t ktot;           /* tensor-core only: row length of `weight` = kh*kw*cin (+ cin2) */
+} ga_conv_desc;
+
+const char* ga_last_error(void);
+int ga_abi_version(void);
+/* number of kernels launched by this library on the calling thread since the last reset (bench.py "gpu_launches") */
+int64_t ga_launch_count(int reset);
+
+/* ---- pre-processing: abstract_models.py:129-159,173-178 (apply_gaussian_blur, add_gaussian_noise) and the
+ *      NVAE input normalisation NVAE/model.py:32 -- ONE pass: blur -> + eps*noise/||noise||_2 -> clamp[0,1]
+ *      -> (x-0.5)/0.5, NCHW fp32 in, NHWC out.  noise_sumsq is the per-sample reduction pre-pass. */
+int ga_noise_sumsq(const float* noise_nchw, int n, int chw, float* sumsq /*[n], zeroed by callee*/, void* stream);
+int ga_noise_sumsq_philox(uint64_t seed, int64_t sample0, int n, int chw, float* sumsq, void* stream);
+int ga_preprocess_fwd(const float* x_nchw, const float* noise_nchw /*NULL => philox*/, const float* sumsq,
+                      uint64_t seed, int64_t sample0, float eps, const float* taps /*[2r+1] or NULL*/, int radius,
+                      int normalize, const ga_tensor* out_nhwc, float* pre_nchw /*optional: value before clamp, saved for bwd*/,
+                      void* stream);
+/* backward of the above w.r.t. x: clamp mask, symmetric reflect-border blur transposed. g_nhwc is d/d(out). */
+int ga_preprocess_bwd(const ga_tensor* g_nhwc, const float* pre_nchw /*saved pre-clamp value (clamp mask)*/,
+                      const float* taps, int radius, int normalize, float* tmp_nchw /*workspace, same size as gx (blur only)*/,
+                      float* gx_nchw, void* stream);
+
+/* ---- convolutions (NVAE cells: architecture.py:64-218; VGG body; linears with h=w=1) */
+int ga_conv2d_simt(const ga_tensor* in, const ga_conv_desc* d, const ga_tensor* add /*nullable*/,
+                   const ga_tensor* out, void* stream);
+/* tcgen05/TMEM/TMA implicit GEMM, bf16 operands, fp32 accumulate.  in2: optional second K source (1x1),
+ * used for the decoder combiner conv1x1(cat[x,z]) (architecture.py:205-218). out_bf16/out_f32: either or both. */
+int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, const ga_tensor* add,
+                 const ga_tensor* out_bf16, const ga_tensor* out_f32, void* stream);
+int ga_conv2d_tc_supported(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, int cout);
+
+/* depthwise 5x5, pad 2, + bias + SiLU (decoder cell, architecture.py:168-170 with BN folded).  up=1: the
+ * input is read through a nearest x2 up-sampling (architecture.py:162). weight fp32 [25][c]. */
+int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,
+                     const ga_tensor* out, void* stream);
+
+/* ---- squeeze-excite + residual (architecture.py:37-61,128-136,178-186) */
+int ga_channel_sum(const ga_tensor* r, float* sums /*[n][c], zeroed by callee*/, void* stream);
+/* gate = sigmoid(W2 relu(W1 mean + b1) + b2);  out = skip + res_scale * gate * r;
+ * optional extra outputs: out_bf16 copy, act = SiLU(act_scale*out + act_shift) (next cell's BN+SiLU). */
+int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const float* w1, const float* b1, const float* w2,
+                       const float* b2, int hidden, float res_scale, const ga_tensor* skip,
+                       const ga_tensor* out, const ga_tensor* out2 /*nullable*/, const ga_tensor* act /*nullable*/,
+                       const float* act_scale, const float* act_shift, float* gate_out /*[n][c] nullable*/,
+                       void* stream);
+
+/* ---- per-level latent interpolation + reparameterised sampling
+ *      (models.py:198-206,243-250; distributions.py:20-45).  z = (1-a)*sc(mu_p+mu_q) + a*(sc(mu_p)+eps*T*exp(sc(ls_p)))
+ *      mu_q: first z channels of `q`; p: [mu_p | logsig_p] (NULL for level 0 => prior N(0,1)).
+ *      eps: NCHW fp32 [n][z][h][w] or NULL => Philox stream keyed by (seed, level, global sample index). */
+int ga_latent_mix_fwd(const ga_tensor* q, const ga_tensor* p /*nullable*/, const float* eps_nchw, uint64_t seed,
+                      int level, int64_t sample0, const float* alpha_dev /*device scalar*/, float temperature,
+                      int zdim, const ga_tensor* z_out, void* stream);
+
+/* ---- DiscMixLogistic(...).mean() + de-normalisation (distributions.py:103-129,231-254; models.py:269-274)
+ *      logits NHWC [n][h][w][10*n_mix] -> purified NCHW fp32 in [0,1] (+ optional NHWC classifier input
+ *      (p-0.5)/0.5, abstract_models.py:59-60). */
+int ga_discmix_mean_fwd(const ga_tensor* logits, int n_mix, float* purified_nchw, const ga_tensor* cls_in /*nullable*/,
+                        void* stream);
+
+/* ---- small layout / resampling ops */
+int ga_upsample_nearest2x(const ga_tensor* in, const ga_tensor* out, void* stream);           /* architecture.py:162 */
+int ga_upsample_bilinear2x(const ga_tensor* in, const ga_tensor* out, void* stream);          /* architecture.py:91 (align_corners=True) */
+int ga_maxpool2x2(const ga_tensor* in, const ga_tensor* out, void* stream);                   /* torchvision vgg11_bn 'M' */
+int ga_cast(const ga_tensor* in, const ga_tensor* out, void* stream);                         /* dtype cast / copy */
+int ga_affine_act(const ga_tensor* in, const float* scale, const float* shift, int act, const ga_tensor* out,
+                  void* stream);                                                               /* folded BN + act */
+int ga_nchw_to_nhwc(const float* in_nchw, const ga_tensor* out, float scale, float shift, void* stream);
+
+/* ---- attack inner loop: PGD-Linf step (update rule of competitors/trades/modules.py:43-45), fused
+ *      x_adv <- clamp(min(max(x_adv + a*sign(g), x-eps), x+eps), 0, 1), in place, NCHW fp32 */
+int ga_pgd_linf_step(float* x_adv, const float* grad, const float* x_nat, float step, float eps, int64_t numel,
+                     void* stream);
+/* softmax cross-entropy: dlogits = (softmax - onehot)/n (mean reduction), loss[n], argmax==label counter */
+int ga_softmax_xent(const float* logits, const int64_t* labels, int n, int classes, float* loss, float* dlogits,
+                    int32_t* pred, unsigned long long* n_correct /*device, accumulated*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GA_B200_H */

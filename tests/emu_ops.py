@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE ONLY: a torch-CPU emulation of the C-ABI op wrappers in gen_adversarial_b200/ops.py.
+
+It lets the `-m "not gpu"` suite exercise the HOST logic (weight folding, op ordering, tensor plumbing of
+nvae_engine.py / vgg_engine.py) against the oracle without a GPU, by monkeypatching the `ops` module inside a
+test.  It is never imported by the product; on a GPU the same host code drives the real kernels and is checked
+against the same oracle by the `-m gpu` tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from gen_adversarial_b200 import ops as real_ops
+from gen_adversarial_b200._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
+
+ConvLayer = real_ops.ConvLayer
+gaussian_taps = real_ops.gaussian_taps
+conv_out_hw = real_ops.conv_out_hw
+_launches = [0]
+
+
+def _act(v, act):
+    if act == ACT_SILU:
+        return F.silu(v)
+    if act == ACT_ELU:
+        return F.elu(v)
+    if act == ACT_RELU:
+        return F.relu(v)
+    return v
+
+
+def _pre(x, L):
+    if L.pre_op == PRE_ELU:
+        return F.elu(x)
+    if L.pre_op == PRE_SILU:
+        return F.silu(x)
+    if L.pre_op == PRE_AFFINE_SILU:
+        return F.silu(x * L.pre_scale + L.pre_shift)
+    return x
+
+
+def _nchw(x):
+    return x.float().permute(0, 3, 1, 2)
+
+
+def _nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def conv2d_simt(x, L, out_dtype, add=None, out_hw=None):
+    _launches[0] += 1
+    xin = _pre(x.float(), L)
+    w = L.w_simt.float().view(L.kh, L.kw, L.cin, L.cout).permute(3, 2, 0, 1)
+    xn = xin.permute(0, 3, 1, 2)
+    if L.up > 1:
+        n, c, h, wd = xn.shape
+        z = torch.zeros((n, c, (h - 1) * L.up + 1, (wd - 1) * L.up + 1), dtype=xn.dtype)
+        z[:, :, ::L.up, ::L.up] = xn
+        xn = z
+        if out_hw is not None:     # output_padding of a transposed conv: pad bottom/right with zeros
+            ho, wo = conv_out_hw(L, h, wd)
+            xn = F.pad(xn, (0, out_hw[1] - wo, 0, out_hw[0] - ho))
+    y = F.conv2d(xn, w, L.bias.float() if L.bias is not None else None, stride=L.stride, padding=L.pad)
+    y = _act(y, L.post_act)
+    y = y.permute(0, 2, 3, 1)
+    if add is not None:
+        y = y + add.float()
+    return y.contiguous().to(out_dtype)
+
+
+def conv2d_tc_supported(x, L, x2=None):
+    if L.w_tc is None or x.dtype != torch.bfloat16:
+        return False
+    if L.stride != 1 or L.up != 1:
+        return False
+    n, h, w, c = x.shape
+    if c % 8:
+        return False
+    if w >= 128:
+        return w % 128 == 0
+    if 128 % w:
+        return False
+    rows = 128 // w
+    return (h % rows == 0) if h >= rows else (rows % h == 0)
+
+
+def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None):
+    _launches[0] += 1
+    assert x.dtype == torch.bfloat16
+    k1 = L.kh * L.kw * L.cin
+    w = L.w_tc.float()
+    w1 = w[:, :k1].view(L.cout, L.kh, L.kw, L.cin).permute(0, 3, 1, 2)
+    y = F.conv2d(_nchw(x), w1, None, padding=L.pad)
+    if x2 is not None:
+        assert x2.dtype == torch.bfloat16 and w.shape[1] == k1 + x2.shape[3]
+        y = y + F.conv2d(_nchw(x2), w[:, k1:].view(L.cout, -1, 1, 1))
+    else:
+        assert w.shape[1] == k1
+    if L.bias is not None:
+        y = y + L.bias.float().view(1, -1, 1, 1)
+    y = _act(y, L.post_act).permute(0, 2, 3, 1)
+    if add is not None:
+        y = y + add.float()
+    y = y.contiguous()
+    return (y.to(torch.bfloat16) if want_bf16 else None), (y if want_f32 else None)
+
+
+def dwconv5x5(x, weight, bias, act, up, out_dtype):
+    _launches[0] += 1
+    xn = _nchw(x)
+    if up:
+        xn = F.interpolate(xn, scale_factor=2, mode="nearest")
+    c = xn.shape[1]
+    w = weight.float().view(5, 5, c).permute(2, 0, 1).unsqueeze(1)
+    y = F.conv2d(xn, w, bias.float() if bias is not None else None, padding=2, groups=c)
+    return _nhwc(_act(y, act), out_dtype)
+
+
+def channel_sum(r):
+    _launches[0] += 1
+    return r.float().sum(dim=(1, 2))
+
+
+def se_residual(r, sums, se, res_scale, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
+                act_affine=None, act_dtype=torch.bfloat16, want_gate=False):
+    _launches[0] += 1
+    w1, b1, w2, b2 = se
+    mean = sums / (r.shape[1] * r.shape[2])
+    gate = torch.sigmoid(F.linear(F.relu(F.linear(mean, w1, b1)), w2, b2))
+    out = skip.float() + res_scale * gate[:, None, None, :] * r.float()
+    out2 = out.to(out2_dtype) if want_out2 else None
+    act = F.silu(out * act_affine[0] + act_affine[1]).to(act_dtype) if act_affine is not None else None
+    return out.to(out_dtype), out2, act, (gate if want_gate else None)
+
+
+def latent_mix(q, p, eps_nchw, seed, level, sample0, alpha_dev, temperature, zdim, zc, out_dtype):
+    _launches[0] += 1
+    assert eps_nchw is not None, "the emulation only supports explicit noise"
+    a = float(alpha_dev[0])
+    sc = lambda t: 5.0 * torch.tanh(t / 5.0)
+    mu_q = q.float()[..., :zdim]
+    e = eps_nchw.float().permute(0, 2, 3, 1)
+    if p is None:
+        z = (1 - a) * sc(mu_q) + a * (e * temperature)
+    else:
+        mu_p, ls_p = p.float()[..., :zdim], p.float()[..., zdim:]
+        z = (1 - a) * sc(mu_p + mu_q) + a * (sc(mu_p) + e * (temperature * torch.exp(sc(ls_p))))
+    out = torch.zeros(q.shape[:3] + (zc,), dtype=torch.float32)
+    out[..., :zdim] = z
+    return out.to(out_dtype)
+
+
+def discmix_mean(logits, n_mix, cls_dtype=None):
+    _launches[0] += 1
+    from oracle.nvae_ref import disc_mix_logistic_mean
+    rec = disc_mix_logistic_mean(_nchw(logits), n_mix)
+    purified = rec * 0.5 + 0.5
+    cls = _nhwc((purified - 0.5) / 0.5, cls_dtype) if cls_dtype is not None else None
+    return purified.contiguous(), cls
+
+
+def upsample_nearest2x(x, out_dtype=None):
+    _launches[0] += 1
+    return _nhwc(F.interpolate(_nchw(x), scale_factor=2, mode="nearest"), out_dtype or x.dtype)
+
+
+def upsample_bilinear2x(x, out_dtype=None):
+    _launches[0] += 1
+    return _nhwc(F.interpolate(_nchw(x), scale_factor=2, mode="bilinear", align_corners=True), out_dtype or x.dtype)
+
+
+def maxpool2x2(x):
+    _launches[0] += 1
+    return _nhwc(F.max_pool2d(_nchw(x), 2), x.dtype)
+
+
+def affine_act(x, scale, shift, act, out_dtype):
+    _launches[0] += 1
+    v = x.float()
+    if scale is not None:
+        v = v * scale + shift
+    return _act(v, act).to(out_dtype)
+
+
+def cast(x, out_dtype):
+    return affine_act(x, None, None, ACT_NONE, out_dtype)
+
+
+def nchw_to_nhwc(x_nchw, out_dtype, scale=1.0, shift=0.0):
+    _launches[0] += 1
+    return _nhwc(x_nchw.float() * scale + shift, out_dtype)
+
+
+def preprocess(x_nchw, noise_nchw, eps, blur, out_dtype, seed=0, sample0=0, normalize=True, save_pre=False, taps_cache=None):
+    _launches[0] += 1
+    from oracle import nvae_ref
+    x = x_nchw.float()
+    if blur:
+        x = nvae_ref.gaussian_blur(x)
+    if eps != 0.0:
+        assert noise_nchw is not None, "the emulation only supports explicit noise"
+        nrm = noise_nchw.reshape(noise_nchw.shape[0], -1).norm(dim=1).view(-1, 1, 1, 1)
+        x = x + noise_nchw * (eps / nrm)
+    pre = x.clone() if save_pre else None
+    x = x.clamp(0, 1)
+    if normalize:
+        x = (x - 0.5) * 2.0
+    return _nhwc(x, out_dtype), pre
+
+
+def launch_count(reset=False):
+    v = _launches[0]
+    if reset:
+        _launches[0] = 0
+    return v

@@ -1,0 +1,64 @@
+"""CPU: host-side logic (folds, op order, plumbing) of the engines, driven through a torch emulation of the
+kernels (tests/emu_ops.py) and compared with the oracle.  The kernels themselves are checked on the GPU."""
+import pytest
+import torch
+
+from oracle import nvae_ref
+from gen_adversarial_b200 import synth, nvae_engine, vgg_engine
+from gen_adversarial_b200.nvae_spec import NvaeSpec, tiny_config
+from tests import emu_ops
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    monkeypatch.setattr(nvae_engine, "ops", emu_ops)
+    monkeypatch.setattr(vgg_engine, "ops", emu_ops)
+    return emu_ops
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_nvae_engine_host_logic_matches_oracle(emu, golden_tiny, mode, tol):
+    g = golden_tiny
+    spec = NvaeSpec(g["cfg"], g["resolution"])
+    eng = nvae_engine.NvaeEngine(g["state_dict"], spec, "cpu", mode, _host_logic_test=True)
+    for case in g["cases"]:
+        alphas = torch.tensor([a * case["attenuation"] for a in case["alphas"]], dtype=torch.float32)
+        xin, _ = emu.preprocess(g["x"], g["noises"][0], case["eps"], case["blur"], eng.adt)
+        taps = {}
+        eng.taps = taps
+        pur, cls = eng.purify(xin, alphas, g["noises"][1:], cls_dtype=eng.adt)
+        err = (pur - case["purified"]).abs().max().item()
+        assert err <= tol, (mode, case["name"], err)
+        assert cls.shape == (3, 32, 32, 3)
+
+
+def test_nvae_engine_host_logic_3scale(emu):
+    """a 3-scale / 3-group architecture with 16 base channels (exercises the tensor-core eligibility rules)."""
+    cfg, res = tiny_config(initial_channels=16, groups=3, scales=3, latent=6), (3, 64, 64)
+    spec = NvaeSpec(cfg, res)
+    sd = synth.make_nvae_state_dict(cfg, res, seed=9)
+    x, _ = synth.synthetic_batch(2, res, seed=1)
+    noises = synth.synthetic_noise(spec, 2, seed=2)
+    alphas = [0.7 * (i + 1) / spec.n_latents for i in range(spec.n_latents)]
+    with torch.no_grad():
+        _, ref = nvae_ref.defense_call(sd, spec, None, x, alphas, noises, 2.0, True)
+    for mode, tol in (("fp32", 2e-5), ("bf16", 2e-2)):
+        eng = nvae_engine.NvaeEngine(sd, spec, "cpu", mode, _host_logic_test=True)
+        xin, _ = emu.preprocess(x, noises[0], 2.0, True, eng.adt)
+        pur, _ = eng.purify(xin, torch.tensor(alphas), noises[1:])
+        assert (pur - ref).abs().max().item() <= tol, mode
+
+
+def test_vgg_engine_host_logic_matches_torchvision(emu):
+    """pool-fold + BN-fold of the VGG11 head against torchvision's vgg11_bn (small head to keep the test light)."""
+    torch.manual_seed(0)
+    sd = synth.make_vgg11_state_dict(n_classes=10, seed=3, calibrate=True)
+    model = nvae_ref.build_vgg11(sd, n_classes=10)
+    x = torch.rand(3, 3, 64, 64)
+    with torch.no_grad():
+        ref = nvae_ref.classify(model, x)
+    eng = vgg_engine.Vgg11Engine(sd, "cpu", "fp32", in_hw=64, _host_logic_test=True)
+    xin = emu.nchw_to_nhwc(x, torch.float32, 2.0, -1.0)
+    out = eng.forward(xin)
+    rel = ((out - ref).abs().max() / ref.abs().max()).item()
+    assert rel <= 1e-4, rel
