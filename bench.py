@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the purification hot path (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload purify|pgd]
+
+"step" = one pass of the hot path over one batch of synthetic input:
+  workload purify (default, BASELINE configs[1]): NVAE CelebA-64 "ids" + configs/ours_learned_blur_ids.yaml
+      (blur on, eps 0) + VGG11 classifier, batch 512 per GPU, bf16 tensor-core path, random-init weights of the
+      C32 architecture, synthetic images.  metric = purified img/s.
+  workload pgd (BASELINE configs[4]): PGD-Linf (eps 8/255, step 2/255, 50 steps) through purifier + classifier.
+
+value  : whole-job img/s with inputs resident in HBM, device-timed (CUDA events), max over ranks.
+e2e    : the same through the reference-facing API (`NVAEDefenseModel.__call__`) from pinned HOST buffers, with the
+         H2D copy of the batch and the D2H read of the logits inside the timed region.
+roofline: the tcgen05 implicit-GEMM conv kernel (dominant), FLOP-weighted over all its launches in the timed
+         region, timed per launch with CUDA events on the launching stream, against MEASURED_PEAKS.json.
+cpu_baseline: the oracle (CPU restatement of the reference, kind "port") on the host cores, bounded sample.
+--impl reference: the oracle port on the host cores for the same config, bounded sample per step.
+Multi-GPU (torchrun): batch sharded data-parallel, no data-path collective; the only collective is one
+all-reduce of the int64[3] accuracy counters.  scaling = weak (fixed 512 images per GPU).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+LEARNED_BLUR_IDS = {   # /root/reference/configs/ours_learned_blur_ids.yaml, verbatim
+    "interpolation_alphas": [0.000, 0.000, 0.001, 0.136, 0.131, 0.206, 0.179, 0.305, 0.347, 0.349, 0.465, 0.528, 0.551,
+                             0.606, 0.681, 0.676, 0.834, 0.800, 0.938, 0.911, 1.000, 1.000, 1.000, 1.000],
+    "alpha_attenuation": 0.7, "initial_noise_eps": 0.0, "gaussian_blur_input": True}
+COSINE_NOISE_IDS = {   # /root/reference/configs/ours_cosine_noise_ids.yaml, verbatim
+    "interpolation_alphas": [0.00, 0.02, 0.04, 0.07, 0.10, 0.15, 0.20, 0.25, 0.31, 0.37, 0.43, 0.50, 0.57, 0.63, 0.69,
+                             0.75, 0.80, 0.85, 0.90, 0.93, 0.96, 0.98, 1.00, 1.00],
+    "alpha_attenuation": 0.7, "initial_noise_eps": 2.0, "gaussian_blur_input": False}
+
+# algorithmic work (unpruned, conv/linear MACs x2): purifier 15.31 + VGG11 2.49 GFLOP per image
+GFLOP_PER_IMAGE_FWD = 17.8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import nvae_ref
+    from gen_adversarial_b200 import synth
+    from gen_adversarial_b200.nvae_spec import NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = LEARNED_BLUR_IDS
+    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+    sd = synth.make_nvae_state_dict(seed=0)
+    vgg = nvae_ref.build_vgg11(synth.make_vgg11_state_dict(100, seed=1), 100)
+    sample = args.ref_batch
+    x, y = synth.synthetic_batch(sample, seed=42)
+    alphas = [a * cfg["alpha_attenuation"] for a in cfg["interpolation_alphas"]]
+
+    def step():
+        g = torch.Generator().manual_seed(int(time.time() * 1e3) % (2 ** 31))
+        noises = [torch.randn(s, generator=g) for s in spec.noise_shapes(sample)]   # the reference draws fresh noise per call
+        with torch.no_grad():
+            logits, _ = nvae_ref.defense_call(sd, spec, vgg, x, alphas, noises, cfg["initial_noise_eps"], cfg["gaussian_blur_input"])
+        return logits
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "purified_img_per_s", "value": val, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "NVAE-C32 CelebA-64 ids, ours_learned_blur_ids.yaml + VGG11, CPU oracle port of the reference path",
+                       "sample_batch": sample},
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x batch {sample} of the same workload (oracle/nvae_ref.py, torch CPU fp32, {cores} threads)"},
+            "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm (GPU)
+def cpu_baseline(sample_batch=16, runs=2):
+    from oracle import nvae_ref
+    from gen_adversarial_b200 import synth
+    from gen_adversarial_b200.nvae_spec import NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = LEARNED_BLUR_IDS
+    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+    sd = synth.make_nvae_state_dict(seed=0)
+    vgg = nvae_ref.build_vgg11(synth.make_vgg11_state_dict(100, seed=1), 100)
+    x, _ = synth.synthetic_batch(sample_batch, seed=42)
+    noises = synth.synthetic_noise(spec, sample_batch, seed=7)
+    alphas = [a * cfg["alpha_attenuation"] for a in cfg["interpolation_alphas"]]
+    times = []
+    for i in range(runs + 1):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            nvae_ref.defense_call(sd, spec, vgg, x, alphas, noises, cfg["initial_noise_eps"], cfg["gaussian_blur_input"])
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times[1:])
+    return {"value": sample_batch / t, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"batch {sample_batch}, 1 warm-up + median of {runs} calls of the same workload (oracle/nvae_ref.py, torch CPU fp32)"}
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a GPU: the product has no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from gen_adversarial_b200 import ops, synth
+    from gen_adversarial_b200.nvae_spec import NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION
+    from gen_adversarial_b200.defenses.ours.models import NVAEDefenseModel, CelebaIdentityClassifier
+
+    mode = args.mode
+    B = args.batch
+    cfg = LEARNED_BLUR_IDS
+    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+    nv = synth.make_nvae_checkpoint(seed=0)
+    vg = {"state_dict": synth.make_vgg11_state_dict(100, seed=1, device=str(dev))}
+    clf = CelebaIdentityClassifier(vg, dev, mode=mode)
+    del vg
+    dm = NVAEDefenseModel(clf, nv, cfg["interpolation_alphas"], cfg["alpha_attenuation"], cfg["initial_noise_eps"],
+                          cfg["gaussian_blur_input"], dev, mode=mode).eval()
+    dm.sample_offset = rank * B                      # Philox streams keyed by the GLOBAL sample index
+    x_cpu, y_cpu = synth.synthetic_batch(B, seed=42 + rank)
+    x_host = x_cpu.pin_memory()
+    x_dev = x_host.to(dev)
+    y_dev = y_cpu.to(dev)
+    counters = torch.zeros(3, dtype=torch.int64, device=dev)       # n_total, n_clean_correct, n_robust_correct
+    logits_host = torch.empty((B, 100), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            logits = dm(x_dev)
+        _, _, pred = ops.softmax_xent(logits, y_dev, want_grad=False, counter=counters[1:2].view(torch.int64))
+        return logits
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            logits = dm(xd)
+        logits_host.copy_(logits, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return logits
+
+    # ---------------- resident timing
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    ops.launch_count(reset=True)
+    timer = ops.KernelTimer() if rank == 0 else None
+    ops.TIMER = timer
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.launch_count(reset=True)
+    ops.TIMER = None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    counters[0] = B * args.steps
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)       # the path's only collective (24 bytes)
+    ms = float(t_ms.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---------------- end-to-end timing (host buffers, copies inside the timed region)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * args.steps / (float(ms_e2e.item()) / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        agg = timer.summary()
+        tot_ms = sum(a["ms"] for a in agg.values())
+        tot_fl = sum(a["flops"] for a in agg.values())
+        n_l = sum(a["launches"] for a in agg.values())
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes, FLOP-weighted)",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})", "traffic": None,
+                "launches": n_l, "share_of_step": tot_ms / ms if ms > 0 else None,
+                "by_shape": [{"shape": k, "launches": a["launches"], "ms": round(a["ms"], 3),
+                              "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 1) if a["ms"] > 0 else None,
+                              "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] > 0 else None} for k, a in top]}
+        cpu = cpu_baseline() if not args.no_cpu_baseline else None
+        line = {"metric": "purified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": mode, "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: NVAE-C32 CelebA-64 ids purification (ours_learned_blur_ids.yaml: blur, eps 0, "
+                                       "learned alphas x0.7) + VGG11 classifier, random-init weights",
+                           "nvae": NVAE_C32_CONFIG, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": "no explicit flush: each step streams > 10 GB of activations through the 126 MB L2",
+                           "gflop_per_image_algorithmic": GFLOP_PER_IMAGE_FWD},
+                "tflops_algorithmic": value * GFLOP_PER_IMAGE_FWD / 1e3,
+                "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
+                        "d2h_bytes_per_step": logits_host.numel() * 4 * world},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "counters": {"n_total": int(counters[0].item()), "n_clean_correct": int(counters[1].item())}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=8, help="bounded sample per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 4
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 10
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

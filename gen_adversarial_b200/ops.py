@@ -105,6 +105,39 @@ def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor
     return bool(_lib.lib().ga_conv2d_tc_supported(gt(x), gt(x2), ctypes.byref(d), L.cout))
 
 
+class KernelTimer:
+    """CUDA-event timing of individual launches on the launching stream (bench.py roofline): when installed as
+    `ops.TIMER`, every tensor-core conv launch is bracketed by two events and its algorithmic FLOPs / bytes are
+    recorded; `summary()` synchronises once and aggregates per problem shape."""
+
+    def __init__(self):
+        self.records = []
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def stop(self, e0, key, flops, bytes_):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream())
+        self.records.append((key, flops, bytes_, e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for key, flops, bytes_, e0, e1 in self.records:
+            a = agg.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["launches"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+            a["bytes"] += bytes_
+        return agg
+
+
+TIMER: Optional[KernelTimer] = None
+
+
 def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
               add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None):
     """-> (out_bf16 or None, out_f32 or None)"""
@@ -113,8 +146,17 @@ def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: b
     ob = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     of = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.float32) if want_f32 else None
     d = L.desc(True)
+    e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_conv2d_tc(gt(x), gt(x2), ctypes.byref(d), gt(add), gt(ob), gt(of), stream()),
                f"conv2d_tc[{L.name}]")
+    if e0 is not None:
+        m = n * h * w
+        ktot = L.w_tc.shape[1]
+        flops = 2.0 * m * L.cout * ktot
+        # compulsory traffic: A once (not per tap), weights once, outputs (+ add) once
+        bytes_ = 2.0 * m * (c + (x2.shape[3] if x2 is not None else 0)) + 2.0 * L.cout * ktot \
+            + m * L.cout * ((2 if want_bf16 else 0) + (4 if want_f32 else 0) + (add.element_size() if add is not None else 0))
+        TIMER.stop(e0, f"k{L.kh} hw{h} cin{c} cout{L.cout}", flops, bytes_)
     return ob, of
 
 

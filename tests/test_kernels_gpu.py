@@ -1,0 +1,260 @@
+"""GPU: every kernel of libga_b200 against a torch restatement of the same op (tests/emu_ops.py, CPU fp32),
+through the C-ABI.  fp32 kernels: tight tolerances; bf16 tensor-core kernels: bf16-rounding tolerances."""
+import math
+
+import pytest
+import torch
+
+from gen_adversarial_b200 import ops
+from gen_adversarial_b200._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
+from oracle import nvae_ref
+from tests import emu_ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _layer(cin, cout, k, stride=1, pad=0, pre_op=PRE_NONE, post_act=ACT_NONE, bias=True, up=1, tc=False, cin2=0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    L = ops.ConvLayer(k, k, stride, pad, cin, cout, pre_op=pre_op, post_act=post_act, up=up, name=f"t{cin}x{cout}k{k}")
+    L.w_simt = w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous()
+    if tc:
+        wk = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+        if cin2:
+            wk = torch.cat([wk, torch.randn(cout, cin2, generator=g) / math.sqrt(cin2)], dim=1)
+            L.cin2 = cin2
+        L.w_tc = wk.to(torch.bfloat16).contiguous()
+    if bias:
+        L.bias = torch.randn(cout, generator=g) * 0.1
+    if pre_op == PRE_AFFINE_SILU:
+        L.pre_scale = torch.rand(cin, generator=g) + 0.5
+        L.pre_shift = torch.randn(cin, generator=g) * 0.2
+    return L
+
+
+def _to_dev(L):
+    import copy
+    D = copy.copy(L)
+    for f in ("w_simt", "w_tc", "bias", "pre_scale", "pre_shift"):
+        v = getattr(L, f)
+        setattr(D, f, None if v is None else v.to(DEV))
+    return D
+
+
+SIMT_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, pre, post, add, up
+    (2, 16, 16, 3, 32, 3, 1, 1, PRE_NONE, ACT_NONE, False, 1),
+    (3, 16, 16, 32, 32, 3, 1, 1, PRE_AFFINE_SILU, ACT_SILU, False, 1),
+    (2, 16, 16, 32, 64, 3, 2, 1, PRE_AFFINE_SILU, ACT_SILU, False, 1),
+    (2, 16, 16, 32, 64, 1, 2, 0, PRE_SILU, ACT_NONE, False, 1),
+    (2, 8, 8, 64, 40, 1, 1, 0, PRE_ELU, ACT_NONE, False, 1),
+    (2, 8, 8, 24, 64, 1, 1, 0, PRE_NONE, ACT_NONE, True, 1),
+    (5, 4, 4, 20, 13, 3, 1, 1, PRE_NONE, ACT_ELU, True, 1),
+    (2, 8, 8, 64, 32, 3, 1, 1, PRE_NONE, ACT_NONE, False, 2),      # transposed (dgrad of stride 2)
+    (130, 1, 1, 200, 100, 1, 1, 0, PRE_NONE, ACT_RELU, False, 1),  # linear
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES)
+def test_conv_simt_fp32(case):
+    n, h, w, cin, cout, k, stride, pad, pre, post, use_add, up = case
+    L = _layer(cin, cout, k, stride, pad, pre, post, up=up, seed=cin + cout)
+    if up > 1:
+        L.pad = k - 1 - pad
+    x = torch.randn(n, h, w, cin)
+    out_hw = (2 * h, 2 * w) if up > 1 else None
+    ho, wo = out_hw if out_hw else ops.conv_out_hw(L, h, w)
+    add = torch.randn(n, ho, wo, cout) if use_add else None
+    ref = emu_ops.conv2d_simt(x, L, torch.float32, add=add, out_hw=out_hw)
+    got = ops.conv2d_simt(x.to(DEV), _to_dev(L), torch.float32, add=add.to(DEV) if use_add else None, out_hw=out_hw)
+    assert got.shape == ref.shape
+    err = (got.cpu() - ref).abs().max().item()
+    assert err <= 2e-5, err
+
+
+def test_conv_simt_bf16_io():
+    L = _layer(32, 64, 3, 2, 1, PRE_AFFINE_SILU, ACT_SILU)
+    x = torch.randn(2, 16, 16, 32).to(torch.bfloat16)
+    ref = emu_ops.conv2d_simt(x, L, torch.float32)
+    got = ops.conv2d_simt(x.to(DEV), _to_dev(L), torch.bfloat16)
+    assert (got.float().cpu() - ref).abs().max().item() <= 2e-2
+
+
+TC_CASES = [
+    # n, h, w, cin, cout, k, post, add('f32'|'bf16'|None), cin2
+    (4, 8, 8, 64, 64, 1, ACT_NONE, None, 0),
+    (2, 32, 32, 64, 64, 3, ACT_SILU, None, 0),
+    (2, 16, 16, 128, 128, 3, ACT_NONE, None, 0),
+    (4, 8, 8, 256, 256, 3, ACT_SILU, None, 0),
+    (3, 8, 8, 256, 1536, 1, ACT_SILU, None, 0),
+    (3, 8, 8, 1536, 256, 1, ACT_NONE, None, 0),
+    (2, 16, 16, 128, 20, 3, ACT_NONE, None, 0),          # sampler: N = 20 (padded tile, scalar stores)
+    (2, 16, 16, 128, 40, 1, ACT_NONE, None, 0),
+    (2, 8, 8, 256, 256, 1, ACT_NONE, "f32", 0),           # encoder combiner: + stash
+    (2, 8, 8, 256, 256, 1, ACT_NONE, "bf16", 24),         # decoder combiner: second K source (z, 24 ch)
+    (2, 64, 64, 32, 32, 3, ACT_SILU, None, 0),            # Cin = 32 < 64: TMA zero fill in K
+    (2, 64, 64, 96, 32, 1, ACT_NONE, None, 0),            # K = 96 (not a multiple of 64)
+    (2, 64, 64, 32, 100, 3, ACT_NONE, None, 0),           # to_logits
+    (3, 8, 8, 24, 256, 1, ACT_NONE, "f32", 0),            # level 0: z only + prior
+    (5, 4, 4, 512, 512, 3, ACT_RELU, None, 0),            # VGG 4x4 (8 images per tile, ragged batch)
+    (5, 2, 2, 512, 512, 3, ACT_RELU, None, 0),
+    (130, 1, 1, 2048, 384, 1, ACT_RELU, None, 0),         # linear, ragged M
+    (3, 1, 1, 25088, 100, 1, ACT_NONE, None, 0),          # long-K linear (392 K blocks)
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_bf16(case):
+    n, h, w, cin, cout, k, post, addk, cin2 = case
+    L = _layer(cin, cout, k, 1, 1 if k == 3 else 0, PRE_NONE, post, tc=True, cin2=cin2, seed=cin + cout + k)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16)
+    x2 = torch.randn(n, h, w, cin2, generator=g).to(torch.bfloat16) if cin2 else None
+    add = None
+    if addk == "f32":
+        add = torch.randn(n, h, w, cout, generator=g)
+    elif addk == "bf16":
+        add = torch.randn(n, h, w, cout, generator=g).to(torch.bfloat16)
+    LD = _to_dev(L)
+    assert ops.conv2d_tc_supported(x.to(DEV), LD, x2.to(DEV) if cin2 else None)
+    _, ref = emu_ops.conv2d_tc(x, L, want_bf16=False, want_f32=True, add=add, x2=x2)
+    ob, of = ops.conv2d_tc(x.to(DEV), LD, want_bf16=True, want_f32=True, add=add.to(DEV) if add is not None else None,
+                           x2=x2.to(DEV) if cin2 else None)
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    e32 = (of.cpu() - ref).abs().max().item()
+    e16 = (ob.float().cpu() - ref).abs().max().item()
+    assert e32 <= 2e-3 * scale, ("fp32 out", e32, scale)       # fp32 accumulation-order differences only
+    assert e16 <= 1e-2 * scale, ("bf16 out", e16, scale)
+
+
+def test_dwconv5x5():
+    g = torch.Generator().manual_seed(0)
+    for up in (False, True):
+        x = torch.randn(2, 8, 8, 48, generator=g)
+        w = torch.randn(25, 48, generator=g) * 0.2
+        b = torch.randn(48, generator=g) * 0.1
+        ref = emu_ops.dwconv5x5(x, w, b, ACT_SILU, up, torch.float32)
+        got = ops.dwconv5x5(x.to(DEV), w.to(DEV), b.to(DEV), ACT_SILU, up, torch.float32)
+        assert (got.cpu() - ref).abs().max().item() <= 1e-5
+        gotb = ops.dwconv5x5(x.to(DEV).bfloat16(), w.to(DEV), b.to(DEV), ACT_SILU, up, torch.bfloat16)
+        assert (gotb.float().cpu() - ref).abs().max().item() <= 3e-2
+
+
+@pytest.mark.parametrize("c,hw", [(32, 64), (64, 32), (256, 8), (512, 4), (24, 8), (8, 16)])
+def test_channel_sum_and_se_residual(c, hw):
+    g = torch.Generator().manual_seed(c)
+    n = 3
+    r = torch.randn(n, hw, hw, c, generator=g)
+    skip = torch.randn(n, hw, hw, c, generator=g)
+    hid = max(c // 16, 4)
+    se = (torch.randn(hid, c, generator=g) * 0.3, torch.randn(hid, generator=g) * 0.1,
+          torch.randn(c, hid, generator=g) * 0.3, torch.randn(c, generator=g) * 0.1)
+    aff = (torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1)
+    sums_ref = emu_ops.channel_sum(r)
+    sums = ops.channel_sum(r.to(DEV))
+    assert (sums.cpu() - sums_ref).abs().max().item() <= 1e-3 * max(1.0, sums_ref.abs().max().item())
+    ref = emu_ops.se_residual(r, sums_ref, se, 0.1, skip, torch.float32, want_out2=True, act_affine=aff, want_gate=True)
+    got = ops.se_residual(r.to(DEV), sums, tuple(t.to(DEV) for t in se), 0.1, skip.to(DEV), torch.float32, want_out2=True,
+                          act_affine=tuple(t.to(DEV) for t in aff), want_gate=True)
+    assert (got[0].cpu() - ref[0]).abs().max().item() <= 1e-5
+    assert (got[1].float().cpu() - ref[0]).abs().max().item() <= 3e-2
+    assert (got[2].float().cpu() - ref[2].float()).abs().max().item() <= 3e-2
+    assert (got[3].cpu() - ref[3]).abs().max().item() <= 1e-5
+
+
+def test_latent_mix_explicit_noise():
+    g = torch.Generator().manual_seed(0)
+    n, h, z, zc = 3, 8, 20, 24
+    q = torch.randn(n, h, h, z, generator=g) * 2
+    p = torch.randn(n, h, h, 2 * z, generator=g) * 2
+    eps = torch.randn(n, z, h, h, generator=g)
+    alpha = torch.tensor([0.37])
+    for pp in (None, p):
+        ref = emu_ops.latent_mix(q, pp, eps, 0, 0, 0, alpha, 0.6, z, zc, torch.float32)
+        got = ops.latent_mix(q.to(DEV), pp.to(DEV) if pp is not None else None, eps.to(DEV), 0, 0, 0, alpha.to(DEV), 0.6, z, zc,
+                             torch.float32)
+        assert (got.cpu() - ref).abs().max().item() <= 1e-5
+        assert got[..., z:].abs().max().item() == 0.0
+
+
+def test_latent_mix_philox_statistics_and_shard_independence():
+    n, h, z, zc = 64, 16, 20, 24
+    q = torch.zeros(n, h, h, z, device=DEV)
+    alpha = torch.ones(1, device=DEV)
+    full = ops.latent_mix(q, None, None, 1234, 3, 0, alpha, 1.0, z, zc, torch.float32)[..., :z]
+    assert abs(full.mean().item()) < 0.02 and abs(full.std().item() - 1.0) < 0.02
+    half = ops.latent_mix(q[32:], None, None, 1234, 3, 32, alpha, 1.0, z, zc, torch.float32)[..., :z]
+    assert torch.equal(half, full[32:])       # keyed by the GLOBAL sample index
+
+
+def test_discmix_mean():
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(3, 16, 16, 100, generator=g) * 1.5
+    ref_p, ref_c = emu_ops.discmix_mean(logits, 10, torch.float32)
+    got_p, got_c = ops.discmix_mean(logits.to(DEV), 10, torch.float32)
+    assert (got_p.cpu() - ref_p).abs().max().item() <= 1e-5
+    assert (got_c.cpu() - ref_c).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("hw,eps,blur", [(64, 2.0, False), (64, 0.0, True), (32, 1.0, True), (128, 4.0, True), (40, 1.0, True)])
+def test_preprocess_matches_reference_semantics(hw, eps, blur):
+    g = torch.Generator().manual_seed(hw)
+    x = torch.rand(3, 3, hw, hw, generator=g)
+    noise = torch.randn(3, 3, hw, hw, generator=g)
+    ref = nvae_ref.preprocess(x, noise, eps, blur) if hw != 40 else None
+    if ref is None:                                        # k = int(2**(sqrt(40)//2)-1) = 7
+        ref = nvae_ref.preprocess(x, noise, eps, blur)
+    got, pre = ops.preprocess(x.to(DEV), noise.to(DEV), eps, blur, torch.float32, normalize=True, save_pre=True)
+    got = got.permute(0, 3, 1, 2).cpu()
+    assert (got - (ref - 0.5) / 0.5).abs().max().item() <= 2e-5
+    assert (pre.cpu().clamp(0, 1) - ref).abs().max().item() <= 1e-5
+
+
+def test_preprocess_philox_noise_has_requested_l2_norm():
+    x = torch.full((4, 3, 64, 64), 0.5, device=DEV)
+    out, _ = ops.preprocess(x, None, 2.0, False, torch.float32, seed=99, sample0=0, normalize=False)
+    d = (out.permute(0, 3, 1, 2) - x).flatten(1).norm(dim=1)
+    assert (d - 2.0).abs().max().item() <= 1e-3
+    out2, _ = ops.preprocess(x[2:], None, 2.0, False, torch.float32, seed=99, sample0=2, normalize=False)
+    assert torch.equal(out2, out[2:])
+
+
+def test_resampling_and_pool_and_cast():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 8, 16, generator=g)
+    assert (ops.upsample_nearest2x(x.to(DEV)).cpu() - emu_ops.upsample_nearest2x(x)).abs().max().item() == 0
+    assert (ops.upsample_bilinear2x(x.to(DEV)).cpu() - emu_ops.upsample_bilinear2x(x)).abs().max().item() <= 1e-5
+    assert (ops.maxpool2x2(x.to(DEV)).cpu() - emu_ops.maxpool2x2(x)).abs().max().item() == 0
+    sc, sh = torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g)
+    got = ops.affine_act(x.to(DEV), sc.to(DEV), sh.to(DEV), ACT_SILU, torch.float32)
+    assert (got.cpu() - emu_ops.affine_act(x, sc, sh, ACT_SILU, torch.float32)).abs().max().item() <= 1e-5
+    xn = torch.randn(2, 3, 8, 8, generator=g)
+    assert (ops.nchw_to_nhwc(xn.to(DEV), torch.float32, 2.0, -1.0).cpu() - emu_ops.nchw_to_nhwc(xn, torch.float32, 2.0, -1.0)).abs().max().item() <= 1e-6
+
+
+def test_pgd_step_bit_exact():
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(5, 3, 64, 64, generator=g)
+    xa = (x + (torch.rand(x.shape, generator=g) - 0.5) * 0.05).clamp(0, 1)
+    gr = torch.randn(x.shape, generator=g)
+    gr[0, 0, 0, :8] = 0.0
+    ref = nvae_ref.pgd_linf_step(xa, gr, x, 2 / 255, 8 / 255)
+    got = ops.pgd_linf_step_(xa.clone().to(DEV), gr.to(DEV), x.to(DEV), 2 / 255, 8 / 255)
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_softmax_xent():
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(37, 100, generator=g) * 3
+    y = torch.randint(0, 100, (37,), generator=g)
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    loss, dl, pred = ops.softmax_xent(logits.to(DEV), y.to(DEV), True, counter)
+    lr = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, y, reduction="none")
+    ref.mean().backward()
+    assert (loss.cpu() - ref.detach()).abs().max().item() <= 1e-5
+    assert (dl.cpu() - lr.grad).abs().max().item() <= 1e-6
+    assert torch.equal(pred.cpu().long(), logits.argmax(1))
+    assert counter.item() == (logits.argmax(1) == y).sum().item()
