@@ -81,6 +81,8 @@ _PROTOS = {
     "ga_last_error": (c_char_p, []),
     "ga_abi_version": (c_int, []),
     "ga_launch_count": (c_int64, [c_int]),
+    "ga_noise_sumsq_parts": (c_int, [c_int]),
+    "ga_channel_sum_parts": (c_int, [c_int, c_int]),
     "ga_noise_sumsq": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ga_noise_sumsq_philox": (c_int, [c_uint64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "ga_preprocess_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_int64, c_float, c_void_p, c_int, c_int, T,

@@ -28,6 +28,19 @@ __host__ __device__ __forceinline__ uint64_t noise_stream(int64_t sample, int le
 }
 
 // ============================================================================ noise L2 norm pre-pass
+// block-level deterministic sum: warp shuffle tree, then warp 0 adds the per-warp values in fixed order
+__device__ __forceinline__ float block_sum_256(float v) {
+  __shared__ float s_w[8];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += s_w[i];
+  return t;
+}
+
+// partial[b][blockIdx.x] = sum of squares of this block's slice (no atomics: bit-reproducible)
 __global__ void noise_sumsq_kernel(const float* __restrict__ noise, int chw, float* __restrict__ sumsq) {
   const int b = blockIdx.y;
   const float4* src = reinterpret_cast<const float4*>(noise + (int64_t)b * chw);
@@ -42,8 +55,8 @@ __global__ void noise_sumsq_kernel(const float* __restrict__ noise, int chw, flo
       float v = noise[(int64_t)b * chw + i];
       acc += v * v;
     }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) atomicAdd(sumsq + b, acc);
+  acc = block_sum_256(acc);
+  if (threadIdx.x == 0) sumsq[(int64_t)b * gridDim.x + blockIdx.x] = acc;
 }
 
 __global__ void noise_sumsq_philox_kernel(uint64_t seed, int64_t sample0, int chw, float* __restrict__ sumsq) {
@@ -58,14 +71,15 @@ __global__ void noise_sumsq_philox_kernel(uint64_t seed, int64_t sample0, int ch
     for (int j = 0; j < 4; ++j)
       if (i * 4 + j < chw) acc += z[j] * z[j];
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) atomicAdd(sumsq + b, acc);
+  acc = block_sum_256(acc);
+  if (threadIdx.x == 0) sumsq[(int64_t)b * gridDim.x + blockIdx.x] = acc;
 }
 
 // ============================================================================ fused pre-processing
 // tile 32 rows x 32 cols, 256 threads, each thread 4 consecutive x of one row, all channels.
 constexpr int PT = 32;
 constexpr int MAXR = 15;
+constexpr int GA_NOISE_PARTS = 16;
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
@@ -76,8 +90,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 template <bool BLUR>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ noise, const float* __restrict__ sumsq, uint64_t seed,
-    int64_t sample0, float eps, const float* __restrict__ taps, int R, int normalize, int C, int H, int W, void* out,
-    int out_dtype, float* __restrict__ pre) {
+    int nparts, int64_t sample0, float eps, const float* __restrict__ taps, int R, int normalize, int C, int H, int W,
+    void* out, int out_dtype, float* __restrict__ pre) {
   __shared__ float s_in[BLUR ? (PT + 2 * MAXR) : 1][BLUR ? (PT + 2 * MAXR + 1) : 1];
   __shared__ float s_h[BLUR ? (PT + 2 * MAXR) : 1][BLUR ? (PT + 1) : 1];
   __shared__ float s_taps[2 * MAXR + 1];
@@ -92,7 +106,11 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     if (tid < 2 * R + 1) s_taps[tid] = taps[tid];
   }
   float scale = 0.f;
-  if (eps != 0.f) scale = eps / sqrtf(sumsq[b]);
+  if (eps != 0.f) {
+    float ss = 0.f;
+    for (int i = 0; i < nparts; ++i) ss += sumsq[(int64_t)b * nparts + i];   // fixed order
+    scale = eps / sqrtf(ss);
+  }
 
   float res[4][4];   // [channel][pixel]
 #pragma unroll
@@ -246,32 +264,40 @@ __global__ void __launch_bounds__(256) dwconv5x5_kernel(const TIn* __restrict__ 
 }
 
 // ============================================================================ SE: channel sums + gate + residual
+// partial[n][blk][c] = sum over the block's pixel slice (no atomics: bit-reproducible)
 __global__ void __launch_bounds__(256) channel_sum_kernel(const void* __restrict__ r, int dtype, int HW, int C,
-                                                          int pix_per_block, float* __restrict__ sums) {
-  extern __shared__ float s_sum[];   // [C]
+                                                          int pix_per_block, float* __restrict__ partial) {
+  __shared__ float s_part[256];
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, HW);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
-  __syncthreads();
   const int64_t base = ((int64_t)n * HW + p0) * C;
   const int cnt = (p1 - p0) * C;
-  if (256 % C == 0) {          // each thread always sees the same channel
+  float* dst = partial + ((int64_t)n * gridDim.x + blockIdx.x) * C;
+  if (256 % C == 0) {          // each thread always sees the same channel (coalesced)
     float acc = 0.f;
     for (int i = threadIdx.x; i < cnt; i += 256) acc += ld1d(r, dtype, base + i);
-    atomicAdd(&s_sum[threadIdx.x % C], acc);
-  } else if (C % 256 == 0) {   // thread sees channels t, t+256, ... cyclically
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float t = 0.f;
+      for (int k = threadIdx.x; k < 256; k += C) t += s_part[k];
+      dst[threadIdx.x] = t;
+    }
+  } else if (C % 256 == 0) {   // thread sees channels t, t+256, ... (coalesced)
     const int per = C / 256;
     for (int k = 0; k < per; ++k) {
       float acc = 0.f;
       for (int i = threadIdx.x + k * 256; i < cnt; i += C) acc += ld1d(r, dtype, base + i);
-      s_sum[threadIdx.x + k * 256] = acc;
+      dst[threadIdx.x + k * 256] = acc;
     }
-  } else {
-    for (int i = threadIdx.x; i < cnt; i += 256) atomicAdd(&s_sum[i % C], ld1d(r, dtype, base + i));
+  } else {                     // odd channel counts (tiny test architectures): one thread per channel
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float acc = 0.f;
+      for (int i = c; i < cnt; i += C) acc += ld1d(r, dtype, base + i);
+      dst[c] = acc;
+    }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(sums + (int64_t)n * C + c, s_sum[c]);
 }
 
 struct SeParams {
@@ -283,7 +309,7 @@ struct SeParams {
   void* out2; int out2_dtype;
   void* act; int act_dtype; const float* act_scale; const float* act_shift;
   float* gate_out;
-  int HW, C, pix_per_block;
+  int HW, C, pix_per_block, nparts;
 };
 
 __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
@@ -294,7 +320,11 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
   const int n = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float inv = 1.0f / (float)p.HW;
-  for (int c = tid; c < p.C; c += 256) s_mean[c] = p.sums[(int64_t)n * p.C + c] * inv;
+  for (int c = tid; c < p.C; c += 256) {
+    float t = 0.f;
+    for (int k = 0; k < p.nparts; ++k) t += p.sums[((int64_t)n * p.nparts + k) * p.C + c];   // fixed order
+    s_mean[c] = t * inv;
+  }
   __syncthreads();
   for (int j = warp; j < p.hidden; j += 8) {
     float a = 0.f;
@@ -573,14 +603,13 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits, const int6
 // ================================================================================================ C ABI
 using namespace ga;
 
+extern "C" int ga_noise_sumsq_parts(int chw) { return max(1, min(GA_NOISE_PARTS, cdiv((chw + 3) / 4, 256))); }
+
 extern "C" int ga_noise_sumsq(const float* noise, int n, int chw, float* sumsq, void* stream) {
   GA_CHECK(noise && sumsq && n >= 0 && chw > 0, "ga_noise_sumsq: bad arguments");
   if (n == 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  GA_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * n, s));
   GA_CHECK((((uintptr_t)noise) & 15) == 0 && (chw % 4 == 0), "ga_noise_sumsq: noise must be 16-byte aligned with chw %% 4 == 0");
-  int bx = max(1, min(64, cdiv(chw / 4, 256)));
-  noise_sumsq_kernel<<<dim3(bx, n), 256, 0, s>>>(noise, chw, sumsq);
+  noise_sumsq_kernel<<<dim3(ga_noise_sumsq_parts(chw), n), 256, 0, (cudaStream_t)stream>>>(noise, chw, sumsq);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -588,10 +617,7 @@ extern "C" int ga_noise_sumsq(const float* noise, int n, int chw, float* sumsq, 
 extern "C" int ga_noise_sumsq_philox(uint64_t seed, int64_t sample0, int n, int chw, float* sumsq, void* stream) {
   GA_CHECK(sumsq && n >= 0 && chw > 0, "ga_noise_sumsq_philox: bad arguments");
   if (n == 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  GA_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * n, s));
-  int bx = max(1, min(64, cdiv((chw + 3) / 4, 256)));
-  noise_sumsq_philox_kernel<<<dim3(bx, n), 256, 0, s>>>(seed, sample0, chw, sumsq);
+  noise_sumsq_philox_kernel<<<dim3(ga_noise_sumsq_parts(chw), n), 256, 0, (cudaStream_t)stream>>>(seed, sample0, chw, sumsq);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -606,13 +632,14 @@ extern "C" int ga_preprocess_fwd(const float* x, const float* noise, const float
   GA_CHECK(taps == nullptr || (radius < out->h && radius < out->w), "ga_preprocess_fwd: reflect border needs radius < image size");
   if (out->n == 0) return 0;
   const int tiles = cdiv(out->h, PT) * cdiv(out->w, PT);
+  const int nparts = ga_noise_sumsq_parts(out->c * out->h * out->w);
   dim3 grid(tiles, 1, out->n);
   cudaStream_t s = (cudaStream_t)stream;
   if (taps != nullptr)
-    preprocess_fwd_kernel<true><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, sample0, eps, taps, radius, normalize, out->c,
+    preprocess_fwd_kernel<true><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, nparts, sample0, eps, taps, radius, normalize, out->c,
                                                     out->h, out->w, out->data, out->dtype, pre);
   else
-    preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, sample0, eps, nullptr, 0, normalize, out->c,
+    preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, nparts, sample0, eps, nullptr, 0, normalize, out->c,
                                                      out->h, out->w, out->data, out->dtype, pre);
   GA_LAUNCH_OK();
   return 0;
@@ -657,21 +684,20 @@ extern "C" int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const 
 }
 
 static int se_pix_per_block(int HW, int n) {
-  // enough blocks to fill 148 SMs a few times, at least 64 pixels each
-  int want_blocks = max(1, (148 * 4 + n - 1) / max(n, 1));
-  int ppb = max(64, (HW + want_blocks - 1) / want_blocks);
-  return min(ppb, HW);
+  // fixed slice of 128 pixels, independent of the batch size: a sample's reduction order (hence its bits) does
+  // not depend on how the batch is sharded over GPUs
+  (void)n;
+  return HW < 128 ? HW : 128;
 }
+
+extern "C" int ga_channel_sum_parts(int n, int hw) { return cdiv(hw, se_pix_per_block(hw, n)); }
 
 extern "C" int ga_channel_sum(const ga_tensor* r, float* sums, void* stream) {
   GA_CHECK(r && sums, "ga_channel_sum: null argument");
   if (numel(r) == 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  GA_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)r->n * r->c, s));
   const int HW = r->h * r->w;
   const int ppb = se_pix_per_block(HW, r->n);
-  GA_CHECK(r->c * sizeof(float) <= 48 * 1024, "ga_channel_sum: too many channels");
-  channel_sum_kernel<<<dim3(cdiv(HW, ppb), r->n), 256, r->c * sizeof(float), s>>>(r->data, r->dtype, HW, r->c, ppb, sums);
+  channel_sum_kernel<<<dim3(cdiv(HW, ppb), r->n), 256, 0, (cudaStream_t)stream>>>(r->data, r->dtype, HW, r->c, ppb, sums);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -695,6 +721,7 @@ extern "C" int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const f
   p.act = act ? act->data : nullptr; p.act_dtype = act ? act->dtype : GA_F32;
   p.act_scale = act_scale; p.act_shift = act_shift; p.gate_out = gate_out;
   p.HW = r->h * r->w; p.C = r->c; p.pix_per_block = se_pix_per_block(p.HW, r->n);
+  p.nparts = cdiv(p.HW, p.pix_per_block);
   const size_t smem = (2 * (size_t)p.C + hidden) * sizeof(float);
   GA_CHECK(smem <= 48 * 1024, "ga_se_residual_fwd: too many channels");
   se_residual_kernel<<<dim3(cdiv(p.HW, p.pix_per_block), r->n), 256, smem, (cudaStream_t)stream>>>(p);

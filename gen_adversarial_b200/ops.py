@@ -170,7 +170,8 @@ def dwconv5x5(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
 
 
 def channel_sum(r: torch.Tensor) -> torch.Tensor:
-    sums = torch.empty((r.shape[0], r.shape[3]), device=r.device, dtype=torch.float32)
+    parts = _lib.lib().ga_channel_sum_parts(r.shape[0], r.shape[1] * r.shape[2])
+    sums = torch.empty((r.shape[0], parts, r.shape[3]), device=r.device, dtype=torch.float32)
     _lib.check(_lib.lib().ga_channel_sum(gt(r), ptr(sums), stream()), "channel_sum")
     return sums
 
@@ -270,7 +271,7 @@ def preprocess(x_nchw, noise_nchw, eps: float, blur: bool, out_dtype, seed: int 
     pre = torch.empty_like(x_nchw) if save_pre else None
     sumsq = None
     if eps != 0.0:
-        sumsq = torch.empty((n,), device=x_nchw.device, dtype=torch.float32)
+        sumsq = torch.empty((n, L.ga_noise_sumsq_parts(c * h * w)), device=x_nchw.device, dtype=torch.float32)
         if noise_nchw is not None:
             noise_nchw = noise_nchw.contiguous()
             _lib.check(L.ga_noise_sumsq(ptr(noise_nchw), n, c * h * w, ptr(sumsq), stream()), "noise_sumsq")

@@ -64,7 +64,9 @@ int64_t ga_launch_count(int reset);
 /* ---- pre-processing: abstract_models.py:129-159,173-178 (apply_gaussian_blur, add_gaussian_noise) and the
  *      NVAE input normalisation NVAE/model.py:32 -- ONE pass: blur -> + eps*noise/||noise||_2 -> clamp[0,1]
  *      -> (x-0.5)/0.5, NCHW fp32 in, NHWC out.  noise_sumsq is the per-sample reduction pre-pass. */
-int ga_noise_sumsq(const float* noise_nchw, int n, int chw, float* sumsq /*[n], zeroed by callee*/, void* stream);
+/* reductions are two-stage without atomics (bit-reproducible): sumsq is [n][ga_noise_sumsq_parts(chw)] partial sums */
+int ga_noise_sumsq_parts(int chw);
+int ga_noise_sumsq(const float* noise_nchw, int n, int chw, float* sumsq, void* stream);
 int ga_noise_sumsq_philox(uint64_t seed, int64_t sample0, int n, int chw, float* sumsq, void* stream);
 int ga_preprocess_fwd(const float* x_nchw, const float* noise_nchw /*NULL => philox*/, const float* sumsq,
                       uint64_t seed, int64_t sample0, float eps, const float* taps /*[2r+1] or NULL*/, int radius,
@@ -90,7 +92,9 @@ int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias
                      const ga_tensor* out, void* stream);
 
 /* ---- squeeze-excite + residual (architecture.py:37-61,128-136,178-186) */
-int ga_channel_sum(const ga_tensor* r, float* sums /*[n][c], zeroed by callee*/, void* stream);
+/* sums is [n][ga_channel_sum_parts(n, h*w)][c] partial sums (two-stage, no atomics: bit-reproducible) */
+int ga_channel_sum_parts(int n, int hw);
+int ga_channel_sum(const ga_tensor* r, float* sums, void* stream);
 /* gate = sigmoid(W2 relu(W1 mean + b1) + b2);  out = skip + res_scale * gate * r;
  * optional extra outputs: out_bf16 copy, act = SiLU(act_scale*out + act_shift) (next cell's BN+SiLU). */
 int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const float* w1, const float* b1, const float* w2,

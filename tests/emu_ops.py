@@ -118,14 +118,14 @@ def dwconv5x5(x, weight, bias, act, up, out_dtype):
 
 def channel_sum(r):
     _launches[0] += 1
-    return r.float().sum(dim=(1, 2))
+    return r.float().sum(dim=(1, 2)).unsqueeze(1)      # [n, parts=1, c]
 
 
 def se_residual(r, sums, se, res_scale, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
                 act_affine=None, act_dtype=torch.bfloat16, want_gate=False):
     _launches[0] += 1
     w1, b1, w2, b2 = se
-    mean = sums / (r.shape[1] * r.shape[2])
+    mean = sums.sum(dim=1) / (r.shape[1] * r.shape[2])
     gate = torch.sigmoid(F.linear(F.relu(F.linear(mean, w1, b1)), w2, b2))
     out = skip.float() + res_scale * gate[:, None, None, :] * r.float()
     out2 = out.to(out2_dtype) if want_out2 else None

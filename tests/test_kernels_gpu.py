@@ -154,7 +154,8 @@ def test_channel_sum_and_se_residual(c, hw):
     aff = (torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1)
     sums_ref = emu_ops.channel_sum(r)
     sums = ops.channel_sum(r.to(DEV))
-    assert (sums.cpu() - sums_ref).abs().max().item() <= 1e-3 * max(1.0, sums_ref.abs().max().item())
+    assert (sums.sum(dim=1).cpu() - sums_ref[:, 0]).abs().max().item() <= 1e-3 * max(1.0, sums_ref.abs().max().item())
+    assert torch.equal(sums, ops.channel_sum(r.to(DEV)))            # two-stage reduction: bit-reproducible
     ref = emu_ops.se_residual(r, sums_ref, se, 0.1, skip, torch.float32, want_out2=True, act_affine=aff, want_gate=True)
     got = ops.se_residual(r.to(DEV), sums, tuple(t.to(DEV) for t in se), 0.1, skip.to(DEV), torch.float32, want_out2=True,
                           act_affine=tuple(t.to(DEV) for t in aff), want_gate=True)
@@ -218,7 +219,7 @@ def test_preprocess_philox_noise_has_requested_l2_norm():
     d = (out.permute(0, 3, 1, 2) - x).flatten(1).norm(dim=1)
     assert (d - 2.0).abs().max().item() <= 1e-3
     out2, _ = ops.preprocess(x[2:], None, 2.0, False, torch.float32, seed=99, sample0=2, normalize=False)
-    assert torch.equal(out2, out[2:])
+    assert torch.equal(out2, out[2:])                      # Philox keyed by the global sample index; no atomics
 
 
 def test_resampling_and_pool_and_cast():
