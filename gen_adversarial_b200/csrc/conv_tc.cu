@@ -41,6 +41,7 @@ struct TcParams {
   const void* add; int add_dtype;
   __nv_bfloat16* out_bf16;
   float* out_f32;
+  int tma_store;              // 1: epilogue stages the tile in (swizzled) shared memory and TMA-stores it
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -76,6 +77,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)tm), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
 }
@@ -126,20 +135,23 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmA2,
-                                                             const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ CUtensorMap tmOutB,
+                                                             const __grid_constant__ CUtensorMap tmOutF, const TcParams p) {
   constexpr int B_STAGE_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   constexpr int STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on a 1024 B boundary
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_hdr + 2048;                   // operand ring / epilogue staging (1024-aligned)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * TC_A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_hdr);   // header: barriers, TMEM address; bias tile after the ring
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);
+  float* s_bias = reinterpret_cast<float*>(smem_hdr + 128);      // header (2 KB): 128 B of barriers + up to 1 KB of bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,19 +253,26 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     __syncwarp();
     tc_fence_after();
     const bool vec_ok = (p.cout & 7) == 0;
+    // staging tiles for the TMA store re-use the (now idle) operand ring: every MMA has retired, so every TMA load
+    // has landed and every operand read is done.  Layout = the SWIZZLE_128B box layout of the output tensor maps:
+    // 128-byte row panels (64 bf16 / 32 fp32 columns), 16-byte chunk index XOR (row & 7).
+    uint8_t* stage_b = smem;                                   // bf16: BLOCK_N/64 panels x 128 rows x 128 B
+    uint8_t* stage_f = smem + (p.out_bf16 != nullptr ? BLOCK_N * 128 * 2 : 0);   // fp32: BLOCK_N/32 panels
+    const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
       const int nb = n_blk * BLOCK_N + c0;
-      if (!row_ok || nb >= p.cout) continue;
+      if (nb >= p.cout) continue;                              // whole chunk beyond Cout (warp-uniform)
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
       const int64_t off = pix * p.cout + nb;
-      if (vec_ok && nb + 16 <= p.cout) {
-        if (p.add != nullptr) {
+      const bool full = vec_ok && nb + 16 <= p.cout;
+      if (p.add != nullptr && row_ok) {
+        if (full) {
           if (p.add_dtype == GA_F32) {
             const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add) + off);
 #pragma unroll
@@ -271,29 +290,68 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
               }
             }
           }
-        }
-        if (p.out_bf16 != nullptr) {
-          uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + off);
-          o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-        }
-        if (p.out_f32 != nullptr) {
-          float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+        } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (nb + j >= p.cout) continue;
-          float o = v[j];
-          if (p.add != nullptr)
-            o += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
-                                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
-          if (p.out_bf16 != nullptr) p.out_bf16[off + j] = __float2bfloat16_rn(o);
-          if (p.out_f32 != nullptr) p.out_f32[off + j] = o;
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.cout)
+              v[j] += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
+                                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
         }
       }
+      if (p.tma_store) {
+        if (p.out_bf16 != nullptr) {
+          uint8_t* panel = stage_b + (c0 >> 6) * (128 * 128) + row * 128;
+          const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
+          *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        }
+        if (p.out_f32 != nullptr) {
+          uint8_t* panel = stage_f + (c0 >> 5) * (128 * 128) + row * 128;
+          const uint32_t k0 = (uint32_t)((c0 & 31) >> 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else if (row_ok) {
+        if (full) {
+          if (p.out_bf16 != nullptr) {
+            uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + off);
+            o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+          if (p.out_f32 != nullptr) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (nb + j >= p.cout) continue;
+            if (p.out_bf16 != nullptr) p.out_bf16[off + j] = __float2bfloat16_rn(v[j]);
+            if (p.out_f32 != nullptr) p.out_f32[off + j] = v[j];
+          }
+        }
+      }
+    }
+    if (p.tma_store) {
+      // each epilogue warp stores its own 32-row slab: no cross-warp barrier; TMA clips rows >= M and cols >= Cout
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = (int)(pix0 + q * 32);
+        if (p.out_bf16 != nullptr)
+          for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
+            tma_store_2d(&tmOutB, stage_b + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
+        if (p.out_f32 != nullptr)
+          for (int pn = 0; pn * 32 < BLOCK_N && n_blk * BLOCK_N + pn * 32 < p.cout; ++pn)
+            tma_store_2d(&tmOutF, stage_f + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 32, row0);
+        tma_store_commit();
+        tma_store_wait_read();       // smem must stay valid until the bulk stores have read it
+      }
+      __syncwarp();
     }
   }
   // ---- teardown: every tcgen05 op of this CTA is complete (the epilogue waited for the last commit)
@@ -366,15 +424,37 @@ static int encode_weight_map(CUtensorMap* tm, const void* w, int cout, int ktot,
   return 0;
 }
 
+static int encode_out_map(CUtensorMap* tm, void* base, int cout, int64_t m, int esize) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)m};
+  cuuint64_t strides[1] = {(cuuint64_t)cout * esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), 32u};      // one 128-byte panel x one warp's 32 rows
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output cout=%d m=%lld esize=%d) failed: %d", cout, (long long)m, esize, (int)r);
+  return 0;
+}
+
 template <int BLOCK_N, int STAGES>
-static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
-  constexpr int smem = STAGES * (TC_A_STAGE_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024 /*align*/ + (2 * STAGES + 1) * 8 + 8 + BLOCK_N * 4;
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of,
+                     const TcParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int ring = STAGES * (TC_A_STAGE_BYTES + BLOCK_N * TC_BLOCK_K * 2);
+  constexpr int max_staging = BLOCK_N * 128 * 2 + BLOCK_N * 128 * 4;
+  constexpr int max_smem = 1024 /*align*/ + 2048 /*header*/ + (ring > max_staging ? ring : max_staging);
   static bool configured = false;
   if (!configured) {
-    GA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 max_smem > 227 * 1024 ? 227 * 1024 : max_smem));
     configured = true;
   }
-  conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, p);
+  int staging = 0;
+  if (p.tma_store) staging = (p.out_bf16 ? BLOCK_N * 128 * 2 : 0) + (p.out_f32 ? BLOCK_N * 128 * 4 : 0);
+  const int smem = 1024 + 2048 + (ring > staging ? ring : staging);
+  GA_CHECK(smem <= 227 * 1024, "conv_tc: shared memory request %d too large", smem);
+  conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, p);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -445,10 +525,24 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.out_f32 = out_f32 ? (float*)out_f32->data : nullptr;
   dim3 grid((unsigned)g.m_tiles, (unsigned)((out->c + block_n - 1) / block_n));
   cudaStream_t s = (cudaStream_t)stream;
+  // TMA-store epilogue needs 16-byte aligned row pitches and bases; tiny / odd Cout falls back to direct stores
+  static int tma_store_enabled = -1;
+  if (tma_store_enabled < 0) { const char* e = getenv("GA_TC_TMA_STORE"); tma_store_enabled = e ? atoi(e) : 1; }
+  bool tma_ok = tma_store_enabled != 0;
+  if (out_bf16 && ((out->c * 2) % 16 != 0 || (((uintptr_t)out_bf16->data) & 15))) tma_ok = false;
+  if (out_f32 && ((out->c * 4) % 16 != 0 || (((uintptr_t)out_f32->data) & 15))) tma_ok = false;
+  if (block_n == 256 && out_bf16 && out_f32) tma_ok = false;       // staging would not fit
+  if (block_n == 32 && out_bf16 && out->c > 32) tma_ok = false;     // 64-column bf16 panel would spill into the next N tile
+  CUtensorMap tmOB = tmA, tmOF = tmA;
+  if (tma_ok && out_bf16) { if (encode_out_map(&tmOB, out_bf16->data, out->c, p.M, 2)) return 1; }
+  if (tma_ok && out_f32) { if (encode_out_map(&tmOF, out_f32->data, out->c, p.M, 4)) return 1; }
+  p.tma_store = tma_ok ? 1 : 0;
+  const int num_kb = p.taps * p.kc1 + p.kc2;
+  const bool short_k = num_kb <= 2;             // 1x1 convs with K <= 128: 2-stage ring -> more CTAs per SM
   switch (block_n) {
-    case 32: return launch_tc<32, 4>(tmA, tmA2, tmB, p, grid, s);
-    case 64: return launch_tc<64, 4>(tmA, tmA2, tmB, p, grid, s);
-    case 128: return launch_tc<128, 3>(tmA, tmA2, tmB, p, grid, s);
-    default: return launch_tc<256, 3>(tmA, tmA2, tmB, p, grid, s);
+    case 32: return short_k ? launch_tc<32, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<32, 4>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+    case 64: return short_k ? launch_tc<64, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<64, 4>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+    case 128: return short_k ? launch_tc<128, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<128, 3>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+    default: return launch_tc<256, 3>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
   }
 }

@@ -1,0 +1,139 @@
+// Depthwise 5x5 convolution (+ folded-BN bias + SiLU) of the NVAE decoder cell
+// (/root/reference/src/mlvgms_autoencoders/NVAE/modules/architecture.py:168-170; hidden = 6C channels).
+//
+// HBM/FMA balanced op (25 MAC per output element): a CTA stages an (8+4) x (TW+4) pixel halo tile of CH channels
+// in shared memory once (16-byte vector loads, zero fill = the conv's zero padding), then every thread produces an
+// 8-row column strip for TWO adjacent channels (32 channels per CTA, 256 threads, 3 CTAs/SM) with a sliding window: 12 x 5 shared loads feed 8 x 25 x 2 FMAs
+// (6.7 FMA per LDS.32), weights live in registers.  Lanes run along channels, so shared reads are conflict-free
+// and global stores are fully coalesced (128 B per warp).  `up` reads the input through the nearest x2
+// up-sampling of the up cells (architecture.py:162) without materialising it.
+#include "ga_common.cuh"
+
+namespace ga {
+
+constexpr int DW_TH = 8;
+
+template <typename T> struct DwTraits;
+template <> struct DwTraits<__nv_bfloat16> { static constexpr int CH = 32; static constexpr int VEC = 8; };
+template <> struct DwTraits<float> { static constexpr int CH = 32; static constexpr int VEC = 4; };
+
+template <typename T> __device__ __forceinline__ float2 lds2(const T* p);
+template <> __device__ __forceinline__ float2 lds2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 lds2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T> __device__ __forceinline__ void stg2(T* p, float a, float b);
+template <> __device__ __forceinline__ void stg2<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void stg2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename TIn, typename TOut, int TW>
+__global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_kernel(
+    const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, int act, int up, int H, int W,
+    int C, int tiles_x, TOut* __restrict__ out) {
+  constexpr int CH = DwTraits<TIn>::CH, VEC = DwTraits<TIn>::VEC;
+  constexpr int NT = TW * CH / 2;
+  constexpr int SH = DW_TH + 4, SW = TW + 4;
+  __shared__ __align__(16) TIn s_in[SH][SW][CH];
+
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z;
+  const int c_blk = blockIdx.y * CH;
+  const int oy0 = (blockIdx.x / tiles_x) * DW_TH, ox0 = (blockIdx.x % tiles_x) * TW;
+  const int Hi = up ? H >> 1 : H, Wi = up ? W >> 1 : W;
+
+  // ---- stage the halo tile (zero outside the image / beyond C)
+  constexpr int VPP = CH / VEC;                      // vectors per pixel
+  for (int i = tid; i < SH * SW * VPP; i += NT) {
+    const int v = i % VPP;
+    const int px = (i / VPP) % SW;
+    const int py = i / (VPP * SW);
+    const int iy = oy0 + py - 2, ix = ox0 + px - 2;
+    const int c = c_blk + v * VEC;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W && c < C) {
+      const int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
+      val = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)n * Hi + sy) * Wi + sx) * C + c));
+    }
+    *reinterpret_cast<uint4*>(&s_in[py][px][v * VEC]) = val;
+  }
+  // ---- per-thread weights (2 channels x 25 taps) and bias
+  const int cp = tid % (CH / 2);
+  const int tx = tid / (CH / 2);
+  const int c0 = c_blk + 2 * cp;
+  const bool c_ok = c0 < C;
+  float2 wr[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) wr[t] = c_ok ? __ldg(reinterpret_cast<const float2*>(w + t * C + c0)) : make_float2(0.f, 0.f);
+  float2 b2 = (c_ok && bias != nullptr) ? __ldg(reinterpret_cast<const float2*>(bias + c0)) : make_float2(0.f, 0.f);
+  float2 acc[DW_TH];
+#pragma unroll
+  for (int r = 0; r < DW_TH; ++r) acc[r] = b2;
+  __syncthreads();
+
+#pragma unroll
+  for (int ir = 0; ir < SH; ++ir) {
+    float2 v[5];
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) v[dx] = lds2<TIn>(&s_in[ir][tx + dx][2 * cp]);
+#pragma unroll
+    for (int r = 0; r < DW_TH; ++r) {
+      const int dy = ir - r;
+      if (dy < 0 || dy > 4) continue;
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        acc[r].x = fmaf(v[dx].x, wr[dy * 5 + dx].x, acc[r].x);
+        acc[r].y = fmaf(v[dx].y, wr[dy * 5 + dx].y, acc[r].y);
+      }
+    }
+  }
+  const int ox = ox0 + tx;
+  if (!c_ok || ox >= W) return;
+#pragma unroll
+  for (int r = 0; r < DW_TH; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= H) break;
+    stg2<TOut>(out + (((int64_t)n * H + oy) * W + ox) * C + c0, apply_act(acc[r].x, act), apply_act(acc[r].y, act));
+  }
+}
+
+template <typename TIn, typename TOut>
+static int launch_dw(const ga_tensor* in, const float* weight, const float* bias, int act, int up, const ga_tensor* out,
+                     cudaStream_t s) {
+  constexpr int CH = DwTraits<TIn>::CH;
+  const int H = out->h, W = out->w, C = out->c;
+  const int cblocks = cdiv(C, CH);
+  if (W >= 16) {
+    const int tiles_x = cdiv(W, 16);
+    dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
+    dwconv5x5_tiled_kernel<TIn, TOut, 16><<<grid, 16 * CH / 2, 0, s>>>((const TIn*)in->data, weight, bias, act, up, H, W, C,
+                                                                        tiles_x, (TOut*)out->data);
+  } else {
+    const int tiles_x = cdiv(W, 8);
+    dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
+    dwconv5x5_tiled_kernel<TIn, TOut, 8><<<grid, 8 * CH / 2, 0, s>>>((const TIn*)in->data, weight, bias, act, up, H, W, C,
+                                                                      tiles_x, (TOut*)out->data);
+  }
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,
+                                const ga_tensor* out, void* stream) {
+  GA_CHECK(in && weight && out, "ga_dwconv5x5_fwd: null argument");
+  GA_CHECK(in->c == out->c && in->n == out->n, "ga_dwconv5x5_fwd: channels / batch must match");
+  GA_CHECK(in->c % (in->dtype == GA_BF16 ? 8 : 4) == 0, "ga_dwconv5x5_fwd: channels must be a multiple of 8 (bf16) / 4 (fp32)");
+  GA_CHECK(up ? (out->h == 2 * in->h && out->w == 2 * in->w) : (out->h == in->h && out->w == in->w), "ga_dwconv5x5_fwd: shape mismatch");
+  GA_CHECK(out->n <= 65535, "ga_dwconv5x5_fwd: batch too large for grid.z");
+  if (numel(out) == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (in->dtype == GA_F32 && out->dtype == GA_F32) return launch_dw<float, float>(in, weight, bias, act, up, out, s);
+  if (in->dtype == GA_BF16 && out->dtype == GA_BF16) return launch_dw<__nv_bfloat16, __nv_bfloat16>(in, weight, bias, act, up, out, s);
+  if (in->dtype == GA_BF16 && out->dtype == GA_F32) return launch_dw<__nv_bfloat16, float>(in, weight, bias, act, up, out, s);
+  return launch_dw<float, __nv_bfloat16>(in, weight, bias, act, up, out, s);
+}

@@ -224,45 +224,6 @@ __global__ void blur_transpose_1d_kernel(const float* __restrict__ in, const flo
   out[i] = acc;
 }
 
-// ============================================================================ depthwise 5x5 (+bias, act)
-template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) dwconv5x5_kernel(const TIn* __restrict__ in, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, int act, int up, int N, int H, int W,
-                                                        int C, TOut* __restrict__ out) {
-  const int c4n = C >> 2;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)N * H * W * c4n;
-  if (idx >= total) return;
-  const int c = (int)(idx % c4n) * 4;
-  int64_t t = idx / c4n;
-  const int x = (int)(t % W); t /= W;
-  const int y = (int)(t % H);
-  const int n = (int)(t / H);
-  const int Hi = up ? H >> 1 : H, Wi = up ? W >> 1 : W;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (bias) { float4 b = *reinterpret_cast<const float4*>(bias + c); acc[0] = b.x; acc[1] = b.y; acc[2] = b.z; acc[3] = b.w; }
-#pragma unroll
-  for (int dy = 0; dy < 5; ++dy) {
-    const int iy = y + dy - 2;
-    if (iy < 0 || iy >= H) continue;
-    const int sy = up ? iy >> 1 : iy;
-#pragma unroll
-    for (int dx = 0; dx < 5; ++dx) {
-      const int ix = x + dx - 2;
-      if (ix < 0 || ix >= W) continue;
-      const int sx = up ? ix >> 1 : ix;
-      float v[4];
-      ld4<TIn>(in + (((int64_t)n * Hi + sy) * Wi + sx) * C + c, v);
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (dy * 5 + dx) * C + c));
-      acc[0] = fmaf(v[0], wv.x, acc[0]); acc[1] = fmaf(v[1], wv.y, acc[1]);
-      acc[2] = fmaf(v[2], wv.z, acc[2]); acc[3] = fmaf(v[3], wv.w, acc[3]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = apply_act(acc[j], act);
-  st4<TOut>(out + (((int64_t)n * H + y) * W + x) * C + c, acc);
-}
-
 // ============================================================================ SE: channel sums + gate + residual
 // partial[n][blk][c] = sum over the block's pixel slice (no atomics: bit-reproducible)
 __global__ void __launch_bounds__(256) channel_sum_kernel(const void* __restrict__ r, int dtype, int HW, int C,
@@ -522,6 +483,29 @@ __global__ void affine_act_kernel(const void* in, int in_dtype, const float* __r
   st1d(out, out_dtype, idx, apply_act(v, act));
 }
 
+// 8 elements per thread (C % 8 == 0): 16/32-byte vector accesses
+__global__ void __launch_bounds__(256) affine_act_vec8_kernel(const void* in, int in_dtype, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int act, void* out, int out_dtype,
+                                                              int C, int64_t total8) {
+  int64_t i8 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i8 >= total8) return;
+  const int64_t idx = i8 * 8;
+  const int c = (int)(idx % C);
+  float a[4], b[4];
+  ld4d(in, in_dtype, idx, a);
+  ld4d(in, in_dtype, idx + 4, b);
+  if (scale != nullptr) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+    a[0] = fmaf(a[0], s0.x, h0.x); a[1] = fmaf(a[1], s0.y, h0.y); a[2] = fmaf(a[2], s0.z, h0.z); a[3] = fmaf(a[3], s0.w, h0.w);
+    b[0] = fmaf(b[0], s1.x, h1.x); b[1] = fmaf(b[1], s1.y, h1.y); b[2] = fmaf(b[2], s1.z, h1.z); b[3] = fmaf(b[3], s1.w, h1.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { a[j] = apply_act(a[j], act); b[j] = apply_act(b[j], act); }
+  st4d(out, out_dtype, idx, a);
+  st4d(out, out_dtype, idx + 4, b);
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, void* out, int out_dtype, float scale, float shift, int N,
                                     int C, int H, int W) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over NHWC output
@@ -664,25 +648,6 @@ extern "C" int ga_preprocess_bwd(const ga_tensor* g, const float* pre, const flo
   return 0;
 }
 
-extern "C" int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,
-                                const ga_tensor* out, void* stream) {
-  GA_CHECK(in && weight && out, "ga_dwconv5x5_fwd: null argument");
-  GA_CHECK(in->c == out->c && in->n == out->n && (in->c % 4) == 0, "ga_dwconv5x5_fwd: channels must match and be a multiple of 4");
-  GA_CHECK(up ? (out->h == 2 * in->h && out->w == 2 * in->w) : (out->h == in->h && out->w == in->w), "ga_dwconv5x5_fwd: shape mismatch");
-  const int64_t total = numel(out) / 4;
-  if (total == 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int blocks = cdiv(total, 256);
-#define DW(TI, TO) dwconv5x5_kernel<TI, TO><<<blocks, 256, 0, s>>>((const TI*)in->data, weight, bias, act, up, out->n, out->h, out->w, out->c, (TO*)out->data)
-  if (in->dtype == GA_F32 && out->dtype == GA_F32) DW(float, float);
-  else if (in->dtype == GA_BF16 && out->dtype == GA_BF16) DW(__nv_bfloat16, __nv_bfloat16);
-  else if (in->dtype == GA_BF16 && out->dtype == GA_F32) DW(__nv_bfloat16, float);
-  else DW(float, __nv_bfloat16);
-#undef DW
-  GA_LAUNCH_OK();
-  return 0;
-}
-
 static int se_pix_per_block(int HW, int n) {
   // fixed slice of 128 pixels, independent of the batch size: a sample's reduction order (hence its bits) does
   // not depend on how the batch is sharded over GPUs
@@ -795,7 +760,10 @@ extern "C" int ga_affine_act(const ga_tensor* in, const float* scale, const floa
   GA_CHECK((scale == nullptr) == (shift == nullptr), "ga_affine_act: scale and shift go together");
   const int64_t total = numel(in);
   if (total == 0) return 0;
-  affine_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total);
+  if ((in->c & 7) == 0)
+    affine_act_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total / 8);
+  else
+    affine_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total);
   GA_LAUNCH_OK();
   return 0;
 }
