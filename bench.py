@@ -232,6 +232,7 @@ def run_ours(args):
     ops.launch_count(reset=True)
     timer = ops.KernelTimer() if rank == 0 else None
     ops.TIMER = timer
+    ops.TIME_ALL = bool(args.breakdown)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -270,7 +271,14 @@ def run_ours(args):
 
     if rank == 0:
         pk = peaks()
-        agg = timer.summary()
+        agg_all = timer.summary()
+        if args.breakdown:
+            rows = sorted(agg_all.items(), key=lambda kv: -kv[1]["ms"])
+            print(f"{'op / shape':70s} {'n':>6s} {'ms/step':>9s} {'us/launch':>10s}", file=sys.stderr)
+            for k, a in rows[:60]:
+                print(f"{k[:70]:70s} {a['launches']:6d} {a['ms'] / args.steps:9.3f} {1e3 * a['ms'] / a['launches']:10.1f}", file=sys.stderr)
+            print(f"sum of bracketed ops: {sum(a['ms'] for a in agg_all.values()) / args.steps:.2f} ms/step; step {ms / args.steps:.2f} ms", file=sys.stderr)
+        agg = {k: a for k, a in agg_all.items() if not k.startswith("op:")}
         tot_ms = sum(a["ms"] for a in agg.values())
         tot_fl = sum(a["flops"] for a in agg.values())
         n_l = sum(a["launches"] for a in agg.values())
@@ -312,6 +320,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded sample per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="CUDA-event time of EVERY op (written to stderr as a table)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 4

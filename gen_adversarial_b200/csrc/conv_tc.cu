@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     // has landed and every operand read is done.  Layout = the SWIZZLE_128B box layout of the output tensor maps:
     // 128-byte row panels (64 bf16 / 32 fp32 columns), 16-byte chunk index XOR (row & 7).
     uint8_t* stage_b = smem;                                   // bf16: BLOCK_N/64 panels x 128 rows x 128 B
-    uint8_t* stage_f = smem + (p.out_bf16 != nullptr ? BLOCK_N * 128 * 2 : 0);   // fp32: BLOCK_N/32 panels
+    uint8_t* stage_f = smem + (p.out_bf16 != nullptr ? ((BLOCK_N + 63) / 64) * 16384 : 0);   // fp32: BLOCK_N/32 panels of 16 KB
     const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
@@ -442,7 +442,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of,
                      const TcParams& p, dim3 grid, cudaStream_t s) {
   constexpr int ring = STAGES * (TC_A_STAGE_BYTES + BLOCK_N * TC_BLOCK_K * 2);
-  constexpr int max_staging = BLOCK_N * 128 * 2 + BLOCK_N * 128 * 4;
+  constexpr int max_staging = ((BLOCK_N + 63) / 64) * 16384 + (BLOCK_N / 32) * 16384;
   constexpr int max_smem = 1024 /*align*/ + 2048 /*header*/ + (ring > max_staging ? ring : max_staging);
   static bool configured = false;
   if (!configured) {
@@ -451,7 +451,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
     configured = true;
   }
   int staging = 0;
-  if (p.tma_store) staging = (p.out_bf16 ? BLOCK_N * 128 * 2 : 0) + (p.out_f32 ? BLOCK_N * 128 * 4 : 0);
+  if (p.tma_store) staging = (p.out_bf16 ? ((BLOCK_N + 63) / 64) * 16384 : 0) + (p.out_f32 ? (BLOCK_N / 32) * 16384 : 0);
   const int smem = 1024 + 2048 + (ring > staging ? ring : staging);
   GA_CHECK(smem <= 227 * 1024, "conv_tc: shared memory request %d too large", smem);
   conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, p);

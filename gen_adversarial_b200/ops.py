@@ -87,6 +87,7 @@ def conv_out_hw(L: ConvLayer, h: int, w: int):
     return (hu + 2 * L.pad - L.kh) // L.stride + 1, (wu + 2 * L.pad - L.kw) // L.stride + 1
 
 
+@_timed("conv2d_simt")
 def conv2d_simt(x: torch.Tensor, L: ConvLayer, out_dtype: torch.dtype, add: Optional[torch.Tensor] = None,
                 out_hw=None) -> torch.Tensor:
     n, h, w, c = x.shape
@@ -136,6 +137,23 @@ class KernelTimer:
 
 
 TIMER: Optional[KernelTimer] = None
+TIME_ALL = False      # bench.py --breakdown: also bracket every non-conv_tc op (keyed "op:<name> <shape>")
+
+
+def _timed(name):
+    def deco(fn):
+        def wrapper(*a, **k):
+            if TIMER is None or not TIME_ALL:
+                return fn(*a, **k)
+            e0 = TIMER.start()
+            out = fn(*a, **k)
+            shp = tuple(a[0].shape) if len(a) and torch.is_tensor(a[0]) else ()
+            TIMER.stop(e0, f"op:{name} {shp}", 0.0, 0.0)
+            return out
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
 
 
 def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
@@ -160,6 +178,7 @@ def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: b
     return ob, of
 
 
+@_timed("dwconv5x5")
 def dwconv5x5(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int, up: bool,
               out_dtype: torch.dtype) -> torch.Tensor:
     n, h, w, c = x.shape
@@ -169,6 +188,7 @@ def dwconv5x5(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+@_timed("channel_sum")
 def channel_sum(r: torch.Tensor) -> torch.Tensor:
     parts = _lib.lib().ga_channel_sum_parts(r.shape[0], r.shape[1] * r.shape[2])
     sums = torch.empty((r.shape[0], parts, r.shape[3]), device=r.device, dtype=torch.float32)
@@ -176,6 +196,7 @@ def channel_sum(r: torch.Tensor) -> torch.Tensor:
     return sums
 
 
+@_timed("se_residual")
 def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
                 act_affine=None, act_dtype=torch.bfloat16, want_gate=False):
     """se = (w1, b1, w2, b2) fp32 device tensors.  -> (out, out2|None, act|None, gate|None)"""
@@ -191,6 +212,7 @@ def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, wa
     return out, out2, act, gate
 
 
+@_timed("latent_mix")
 def latent_mix(q, p, eps_nchw, seed: int, level: int, sample0: int, alpha_dev, temperature: float, zdim: int,
                zc: int, out_dtype) -> torch.Tensor:
     n, h, w, _ = q.shape
@@ -200,6 +222,7 @@ def latent_mix(q, p, eps_nchw, seed: int, level: int, sample0: int, alpha_dev, t
     return z
 
 
+@_timed("discmix_mean")
 def discmix_mean(logits, n_mix: int, cls_dtype=None):
     n, h, w, _ = logits.shape
     purified = torch.empty((n, 3, h, w), device=logits.device, dtype=torch.float32)
@@ -208,6 +231,7 @@ def discmix_mean(logits, n_mix: int, cls_dtype=None):
     return purified, cls
 
 
+@_timed("upsample_nearest2x")
 def upsample_nearest2x(x, out_dtype=None):
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=out_dtype or x.dtype)
@@ -215,6 +239,7 @@ def upsample_nearest2x(x, out_dtype=None):
     return out
 
 
+@_timed("upsample_bilinear2x")
 def upsample_bilinear2x(x, out_dtype=None):
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=out_dtype or x.dtype)
@@ -222,6 +247,7 @@ def upsample_bilinear2x(x, out_dtype=None):
     return out
 
 
+@_timed("maxpool2x2")
 def maxpool2x2(x):
     n, h, w, c = x.shape
     out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=x.dtype)
@@ -229,6 +255,7 @@ def maxpool2x2(x):
     return out
 
 
+@_timed("affine_act")
 def affine_act(x, scale, shift, act: int, out_dtype):
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
     _lib.check(_lib.lib().ga_affine_act(gt(x), ptr(scale), ptr(shift), act, gt(out), stream()), "affine_act")
@@ -239,6 +266,7 @@ def cast(x, out_dtype):
     return affine_act(x, None, None, ACT_NONE, out_dtype)
 
 
+@_timed("nchw_to_nhwc")
 def nchw_to_nhwc(x_nchw, out_dtype, scale=1.0, shift=0.0):
     n, c, h, w = x_nchw.shape
     out = torch.empty((n, h, w, c), device=x_nchw.device, dtype=out_dtype)
@@ -261,6 +289,7 @@ def gaussian_taps(h: int, max_radius: int = 12):
     return g.to(torch.float32), r
 
 
+@_timed("preprocess")
 def preprocess(x_nchw, noise_nchw, eps: float, blur: bool, out_dtype, seed: int = 0, sample0: int = 0,
                normalize: bool = True, save_pre: bool = False, taps_cache=None):
     """blur -> noise -> clamp -> (x-.5)/.5 in one kernel (+ the L2-norm pre-pass).  -> (out NHWC, pre NCHW|None)"""
@@ -297,6 +326,7 @@ def pgd_linf_step_(x_adv, grad, x_nat, step: float, eps: float):
     return x_adv
 
 
+@_timed("softmax_xent")
 def softmax_xent(logits, labels, want_grad=True, counter=None):
     """-> (loss[n], dlogits|None, pred[n] int32); `counter` (uint64 device scalar) accumulates argmax==label."""
     n, k = logits.shape
