@@ -53,6 +53,56 @@ def torch_dtype(name: str):
     return {"fp32": torch.float32, "bf16": torch.bfloat16}[name]
 
 
+class KernelTimer:
+    """CUDA-event timing of individual launches on the launching stream (bench.py roofline): when installed as
+    `ops.TIMER`, every tensor-core conv launch is bracketed by two events and its algorithmic FLOPs / bytes are
+    recorded; `summary()` synchronises once and aggregates per problem shape."""
+
+    def __init__(self):
+        self.records = []
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def stop(self, e0, key, flops, bytes_):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream())
+        self.records.append((key, flops, bytes_, e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for key, flops, bytes_, e0, e1 in self.records:
+            a = agg.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["launches"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+            a["bytes"] += bytes_
+        return agg
+
+
+TIMER: Optional[KernelTimer] = None
+TIME_ALL = False      # bench.py --breakdown: also bracket every non-conv_tc op (keyed "op:<name> <shape>")
+
+
+def _timed(name):
+    def deco(fn):
+        def wrapper(*a, **k):
+            if TIMER is None or not TIME_ALL:
+                return fn(*a, **k)
+            e0 = TIMER.start()
+            out = fn(*a, **k)
+            shp = tuple(a[0].shape) if len(a) and torch.is_tensor(a[0]) else ()
+            TIMER.stop(e0, f"op:{name} {shp}", 0.0, 0.0)
+            return out
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
 @dataclass
 class ConvLayer:
     """A folded convolution living on the device."""
@@ -104,56 +154,6 @@ def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor
         return False
     d = L.desc(True)
     return bool(_lib.lib().ga_conv2d_tc_supported(gt(x), gt(x2), ctypes.byref(d), L.cout))
-
-
-class KernelTimer:
-    """CUDA-event timing of individual launches on the launching stream (bench.py roofline): when installed as
-    `ops.TIMER`, every tensor-core conv launch is bracketed by two events and its algorithmic FLOPs / bytes are
-    recorded; `summary()` synchronises once and aggregates per problem shape."""
-
-    def __init__(self):
-        self.records = []
-
-    def start(self):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record(torch.cuda.current_stream())
-        return e
-
-    def stop(self, e0, key, flops, bytes_):
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record(torch.cuda.current_stream())
-        self.records.append((key, flops, bytes_, e0, e1))
-
-    def summary(self):
-        torch.cuda.synchronize()
-        agg = {}
-        for key, flops, bytes_, e0, e1 in self.records:
-            a = agg.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
-            a["launches"] += 1
-            a["ms"] += e0.elapsed_time(e1)
-            a["flops"] += flops
-            a["bytes"] += bytes_
-        return agg
-
-
-TIMER: Optional[KernelTimer] = None
-TIME_ALL = False      # bench.py --breakdown: also bracket every non-conv_tc op (keyed "op:<name> <shape>")
-
-
-def _timed(name):
-    def deco(fn):
-        def wrapper(*a, **k):
-            if TIMER is None or not TIME_ALL:
-                return fn(*a, **k)
-            e0 = TIMER.start()
-            out = fn(*a, **k)
-            shp = tuple(a[0].shape) if len(a) and torch.is_tensor(a[0]) else ()
-            TIMER.stop(e0, f"op:{name} {shp}", 0.0, 0.0)
-            return out
-        wrapper.__name__ = fn.__name__
-        wrapper.__doc__ = fn.__doc__
-        return wrapper
-    return deco
 
 
 def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
