@@ -189,8 +189,8 @@ def run_ours(args):
     from gen_adversarial_b200.defenses.ours.models import NVAEDefenseModel, CelebaIdentityClassifier
 
     mode = args.mode
-    B = args.batch
-    cfg = LEARNED_BLUR_IDS
+    B = args.batch if args.batch is not None else (128 if args.workload == "pgd" else 512)
+    cfg = COSINE_NOISE_IDS if args.workload == "pgd" else LEARNED_BLUR_IDS
     spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
     nv = synth.make_nvae_checkpoint(seed=0)
     vg = {"state_dict": synth.make_vgg11_state_dict(100, seed=1, device=str(dev))}
@@ -211,7 +211,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    pgd = args.workload == "pgd"
+    if pgd:
+        from gen_adversarial_b200.attacks import PGDLinf
+        attack = PGDLinf(8 / 255, 2 / 255, args.pgd_steps)
+        with torch.no_grad():
+            y_dev = dm(x_dev).argmax(dim=1)          # attack the model's own clean predictions (labels are synthetic)
+        succ_host = torch.empty((B,), dtype=torch.bool).pin_memory()
+
     def step_resident():
+        if pgd:
+            succ, _, _ = attack(x_dev, y_dev, dm)
+            counters[2] += (~succ).sum()
+            return succ
         with torch.no_grad():
             logits = dm(x_dev)
         _, _, pred = ops.softmax_xent(logits, y_dev, want_grad=False, counter=counters[1:2].view(torch.int64))
@@ -219,6 +231,11 @@ def run_ours(args):
 
     def step_e2e():
         xd = x_host.to(dev, non_blocking=True)
+        if pgd:
+            succ, _, _ = attack(xd, y_dev, dm)
+            succ_host.copy_(succ, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return succ
         with torch.no_grad():
             logits = dm(xd)
         logits_host.copy_(logits, non_blocking=True)
@@ -292,19 +309,24 @@ def run_ours(args):
                               "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 1) if a["ms"] > 0 else None,
                               "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] > 0 else None} for k, a in top]}
         cpu = cpu_baseline() if not args.no_cpu_baseline else None
-        line = {"metric": "purified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        gflop = GFLOP_PER_IMAGE_FWD * ((2 * args.pgd_steps + 1) if pgd else 1)
+        workload = ("BASELINE configs[4]: PGD-Linf eps 8/255, step 2/255, %d steps (fwd + input-gradient each) + 1 eval forward, through "
+                    "NVAE-C32 purifier (ours_cosine_noise_ids.yaml) + VGG11, random-init weights" % args.pgd_steps) if pgd else \
+            ("BASELINE configs[1]: NVAE-C32 CelebA-64 ids purification (ours_learned_blur_ids.yaml: blur, eps 0, "
+             "learned alphas x0.7) + VGG11 classifier, random-init weights")
+        line = {"metric": "pgd_attacked_img_per_s" if pgd else "purified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": mode, "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: NVAE-C32 CelebA-64 ids purification (ours_learned_blur_ids.yaml: blur, eps 0, "
-                                       "learned alphas x0.7) + VGG11 classifier, random-init weights",
+                "config": {"workload": workload,
                            "nvae": NVAE_C32_CONFIG, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": "no explicit flush: each step streams > 10 GB of activations through the 126 MB L2",
-                           "gflop_per_image_algorithmic": GFLOP_PER_IMAGE_FWD},
-                "tflops_algorithmic": value * GFLOP_PER_IMAGE_FWD / 1e3,
+                           "gflop_per_image_algorithmic": gflop},
+                "tflops_algorithmic": value * gflop / 1e3,
                 "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
-                        "d2h_bytes_per_step": logits_host.numel() * 4 * world},
+                        "d2h_bytes_per_step": (B if pgd else logits_host.numel() * 4) * world},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "counters": {"n_total": int(counters[0].item()), "n_clean_correct": int(counters[1].item())}}
+                "counters": {"n_total": int(counters[0].item()), "n_clean_correct": int(counters[1].item()),
+                             "n_robust_correct": int(counters[2].item())}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -317,7 +339,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 512 purify / 128 pgd)")
+    ap.add_argument("--workload", default="purify", choices=["purify", "pgd"])
+    ap.add_argument("--pgd-steps", type=int, default=50)
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded sample per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="CUDA-event time of EVERY op (written to stderr as a table)")
@@ -327,8 +351,8 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
     else:
-        args.steps = args.steps if args.steps is not None else 10
-        args.warmup = args.warmup if args.warmup is not None else 3
+        args.steps = args.steps if args.steps is not None else (2 if args.workload == "pgd" else 10)
+        args.warmup = args.warmup if args.warmup is not None else (1 if args.workload == "pgd" else 3)
         run_ours(args)
 
 

@@ -23,6 +23,7 @@ HEADER = os.path.join(ROOT_DIR, "include", "ga_b200.h")
 GA_F32, GA_BF16 = 0, 1
 PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU = 0, 1, 2, 3
 ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU = 0, 1, 2, 3
+MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y = 0, 1, 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -36,7 +37,9 @@ class GaConvDesc(ctypes.Structure):
     _fields_ = [("kh", c_int32), ("kw", c_int32), ("stride", c_int32), ("pad", c_int32), ("up", c_int32),
                 ("pre_op", c_int32), ("post_act", c_int32),
                 ("pre_scale", c_void_p), ("pre_shift", c_void_p), ("weight", c_void_p), ("bias", c_void_p),
-                ("reserved0", c_int32), ("ktot", c_int32)]
+                ("reserved0", c_int32), ("ktot", c_int32),
+                ("mul", c_void_p), ("mul_dtype", c_int32), ("mul_mode", c_int32),
+                ("dact_out", c_void_p), ("dact_dtype", c_int32), ("reserved1", c_int32)]
 
 
 def sources():
@@ -92,7 +95,16 @@ _PROTOS = {
     "ga_conv2d_tc": (c_int, [T, T, D, T, T, T, c_void_p]),
     "ga_conv2d_tc_supported": (c_int, [T, T, D, c_int]),
     "ga_dwconv5x5_fwd": (c_int, [T, c_void_p, c_void_p, c_int, c_int, T, c_void_p]),
+    "ga_dwconv5x5_ex": (c_int, [T, T, c_void_p, c_void_p, c_int, c_int, T, T, c_void_p]),
     "ga_channel_sum": (c_int, [T, c_void_p, c_void_p]),
+    "ga_affine_act_bwd": (c_int, [T, T, c_void_p, c_void_p, c_int, T, T, c_void_p]),
+    "ga_add": (c_int, [T, T, T, c_void_p]),
+    "ga_se_residual_bwd": (c_int, [T, T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, T, c_void_p]),
+    "ga_sumpool2x2": (c_int, [T, T, T, c_void_p]),
+    "ga_upsample_bilinear2x_bwd": (c_int, [T, T, c_void_p]),
+    "ga_maxpool2x2_bwd": (c_int, [T, T, c_int, T, c_void_p]),
+    "ga_latent_mix_bwd": (c_int, [T, T, T, c_void_p, c_uint64, c_int, c_int64, c_void_p, c_float, c_int, T, T, c_void_p]),
+    "ga_discmix_mean_bwd": (c_int, [T, c_int, c_void_p, T, T, c_void_p]),
     "ga_se_residual_fwd": (c_int, [T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, T, T, T, T,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "ga_latent_mix_fwd": (c_int, [T, T, c_void_p, c_uint64, c_int, c_int64, c_void_p, c_float, c_int, T, c_void_p]),
@@ -124,7 +136,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 1:
+    if L.ga_abi_version() != 2:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -29,6 +29,8 @@ struct ConvParams {
   int KH, KW, stride, pad, up;
   int pre_op, post_act;
   int add_dtype;
+  const void* mul; int mul_dtype, mul_mode;
+  void* dact; int dact_dtype;
   int64_t M;
 };
 
@@ -170,14 +172,38 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
     for (int j = 0; j < 4; ++j)
       if (nb + j < p.Cout) bias4[j] = p.bias[nb + j];
   }
+  const bool extras = (p.mul != nullptr) || (p.dact != nullptr);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t m = m0 + ty * 8 + i;
     if (m >= p.M) continue;
+    const int64_t off = m * p.Cout + nb;
+    if (extras) {                                  // backward-pass epilogues: scalar path
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (nb + j >= p.Cout) continue;
+        const float pre = acc[i][j] + bias4[j];
+        if (p.dact != nullptr) {
+          const float dv = act_grad(pre, p.post_act);
+          if (p.dact_dtype == GA_F32) reinterpret_cast<float*>(p.dact)[off + j] = dv;
+          else reinterpret_cast<__nv_bfloat16*>(p.dact)[off + j] = __float2bfloat16_rn(dv);
+        }
+        float r = apply_act(pre, p.post_act);
+        if (p.add != nullptr)
+          r += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
+                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
+        if (p.mul != nullptr) {
+          const float mv = (p.mul_dtype == GA_F32) ? reinterpret_cast<const float*>(p.mul)[off + j]
+                                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mul)[off + j]);
+          r *= mul_factor(mv, p.mul_mode);
+        }
+        stf<TOut>(out + off + j, r);
+      }
+      continue;
+    }
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = apply_act(acc[i][j] + bias4[j], p.post_act);
-    const int64_t off = m * p.Cout + nb;
     if (cout_vec && nb + 4 <= p.Cout) {
       if (p.add != nullptr) {
         float a4[4];
@@ -224,6 +250,8 @@ extern "C" int ga_conv2d_simt(const ga_tensor* in, const ga_conv_desc* d, const 
   p.in = in->data; p.w = (const float*)d->weight; p.bias = d->bias;
   p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift;
   p.add = add ? add->data : nullptr; p.add_dtype = add ? add->dtype : GA_F32;
+  p.mul = d->mul; p.mul_dtype = d->mul_dtype; p.mul_mode = d->mul_mode;
+  p.dact = d->dact_out; p.dact_dtype = d->dact_dtype;
   p.out = out->data;
   p.N = in->n; p.H = in->h; p.W = in->w; p.Cin = in->c; p.Ho = out->h; p.Wo = out->w; p.Cout = out->c;
   p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->pad; p.up = d->up;

@@ -42,6 +42,8 @@ struct TcParams {
   __nv_bfloat16* out_bf16;
   float* out_f32;
   int tma_store;              // 1: epilogue stages the tile in (swizzled) shared memory and TMA-stores it
+  const void* mul; int mul_dtype, mul_mode;   // backward: out = (act(acc+bias) + add) * f(mul)
+  __nv_bfloat16* dact;        // taping forward: derivative of post_act at the pre-activation (bf16, direct stores)
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -267,10 +269,24 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       const int nb = n_blk * BLOCK_N + c0;
       if (nb >= p.cout) continue;                              // whole chunk beyond Cout (warp-uniform)
       float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
       const int64_t off = pix * p.cout + nb;
       const bool full = vec_ok && nb + 16 <= p.cout;
+      if (p.dact != nullptr && row_ok) {          // save act'(pre-activation) for the backward pass
+        float dv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dv[j] = act_grad(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
+        if (full) {
+          uint4* o = reinterpret_cast<uint4*>(p.dact + off);
+          o[0] = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+          o[1] = make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.cout) p.dact[off + j] = __float2bfloat16_rn(dv[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = apply_act_fast(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
       if (p.add != nullptr && row_ok) {
         if (full) {
           if (p.add_dtype == GA_F32) {
@@ -296,6 +312,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             if (nb + j < p.cout)
               v[j] += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
+        }
+      }
+      if (p.mul != nullptr && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (nb + j < p.cout) {
+            const float mv = (p.mul_dtype == GA_F32) ? __ldg(reinterpret_cast<const float*>(p.mul) + off + j)
+                                                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mul)[off + j]);
+            v[j] *= mul_factor(mv, p.mul_mode);
+          }
         }
       }
       if (p.tma_store) {
@@ -523,6 +549,9 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.add = add ? add->data : nullptr; p.add_dtype = add ? add->dtype : GA_F32;
   p.out_bf16 = out_bf16 ? (__nv_bfloat16*)out_bf16->data : nullptr;
   p.out_f32 = out_f32 ? (float*)out_f32->data : nullptr;
+  p.mul = d->mul; p.mul_dtype = d->mul_dtype; p.mul_mode = d->mul_mode;
+  GA_CHECK(d->dact_out == nullptr || d->dact_dtype == GA_BF16, "ga_conv2d_tc: dact_out must be bf16");
+  p.dact = (__nv_bfloat16*)d->dact_out;
   dim3 grid((unsigned)g.m_tiles, (unsigned)((out->c + block_n - 1) / block_n));
   cudaStream_t s = (cudaStream_t)stream;
   // TMA-store epilogue needs 16-byte aligned row pitches and bases; tiny / odd Cout falls back to direct stores
@@ -539,6 +568,14 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.tma_store = tma_ok ? 1 : 0;
   const int num_kb = p.taps * p.kc1 + p.kc2;
   const bool short_k = num_kb <= 2;             // 1x1 convs with K <= 128: 2-stage ring -> more CTAs per SM
+  if (num_kb == 1) {                            // single K block: 1-stage ring, up to 4 CTAs per SM (TMEM-limited)
+    switch (block_n) {
+      case 32: return launch_tc<32, 1>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+      case 64: return launch_tc<64, 1>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+      case 128: return launch_tc<128, 1>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+      default: break;
+    }
+  }
   switch (block_n) {
     case 32: return short_k ? launch_tc<32, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<32, 4>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
     case 64: return short_k ? launch_tc<64, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<64, 4>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);

@@ -28,10 +28,28 @@ template <> __device__ __forceinline__ void stg2<__nv_bfloat16>(__nv_bfloat16* p
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
+template <typename T> __device__ __forceinline__ uint4 mul_vec(uint4 a, uint4 b);
+template <> __device__ __forceinline__ uint4 mul_vec<float>(uint4 a, uint4 b) {
+  float4 x = *reinterpret_cast<float4*>(&a), y = *reinterpret_cast<float4*>(&b);
+  float4 r = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+  return *reinterpret_cast<uint4*>(&r);
+}
+template <> __device__ __forceinline__ uint4 mul_vec<__nv_bfloat16>(uint4 a, uint4 b) {
+  uint4 r;
+  const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; uint32_t* pr = &r.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa + i));
+    float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pb + i));
+    pr[i] = pack_bf16x2(fa.x * fb.x, fa.y * fb.y);
+  }
+  return r;
+}
+
 template <typename TIn, typename TOut, int TW>
 __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_kernel(
-    const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, int act, int up, int H, int W,
-    int C, int tiles_x, TOut* __restrict__ out) {
+    const TIn* __restrict__ in, const TOut* __restrict__ mul, const float* __restrict__ w, const float* __restrict__ bias, int act,
+    int up, int H, int W, int C, int tiles_x, TOut* __restrict__ out, TOut* __restrict__ dact) {
   constexpr int CH = DwTraits<TIn>::CH, VEC = DwTraits<TIn>::VEC;
   constexpr int NT = TW * CH / 2;
   constexpr int SH = DW_TH + 4, SW = TW + 4;
@@ -54,7 +72,8 @@ __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_ke
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W && c < C) {
       const int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
-      val = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)n * Hi + sy) * Wi + sx) * C + c));
+      const int64_t off = (((int64_t)n * Hi + sy) * Wi + sx) * C + c;
+      val = __ldg(reinterpret_cast<const uint4*>(in + off));
     }
     *reinterpret_cast<uint4*>(&s_in[py][px][v * VEC]) = val;
   }
@@ -94,26 +113,36 @@ __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_ke
   for (int r = 0; r < DW_TH; ++r) {
     const int oy = oy0 + r;
     if (oy >= H) break;
-    stg2<TOut>(out + (((int64_t)n * H + oy) * W + ox) * C + c0, apply_act(acc[r].x, act), apply_act(acc[r].y, act));
+    const int64_t o = (((int64_t)n * H + oy) * W + ox) * C + c0;
+    if (dact != nullptr) stg2<TOut>(dact + o, act_grad(acc[r].x, act), act_grad(acc[r].y, act));
+    if (mul != nullptr) {                          // backward: result times the saved derivative of the producer's activation
+      const float2 m = lds2<TOut>(mul + o);
+      stg2<TOut>(out + o, apply_act(acc[r].x, act) * m.x, apply_act(acc[r].y, act) * m.y);
+      continue;
+    }
+    if (sizeof(TOut) == 2)   // bf16 output: fast-math activation (error far below bf16 rounding)
+      stg2<TOut>(out + (((int64_t)n * H + oy) * W + ox) * C + c0, apply_act_fast(acc[r].x, act), apply_act_fast(acc[r].y, act));
+    else
+      stg2<TOut>(out + (((int64_t)n * H + oy) * W + ox) * C + c0, apply_act(acc[r].x, act), apply_act(acc[r].y, act));
   }
 }
 
 template <typename TIn, typename TOut>
-static int launch_dw(const ga_tensor* in, const float* weight, const float* bias, int act, int up, const ga_tensor* out,
-                     cudaStream_t s) {
+static int launch_dw(const ga_tensor* in, const void* mul, const float* weight, const float* bias, int act, int up,
+                     const ga_tensor* out, void* dact, cudaStream_t s) {
   constexpr int CH = DwTraits<TIn>::CH;
   const int H = out->h, W = out->w, C = out->c;
   const int cblocks = cdiv(C, CH);
   if (W >= 16) {
     const int tiles_x = cdiv(W, 16);
     dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
-    dwconv5x5_tiled_kernel<TIn, TOut, 16><<<grid, 16 * CH / 2, 0, s>>>((const TIn*)in->data, weight, bias, act, up, H, W, C,
-                                                                        tiles_x, (TOut*)out->data);
+    dwconv5x5_tiled_kernel<TIn, TOut, 16><<<grid, 16 * CH / 2, 0, s>>>((const TIn*)in->data, (const TOut*)mul, weight, bias, act, up,
+                                                                        H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
   } else {
     const int tiles_x = cdiv(W, 8);
     dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
-    dwconv5x5_tiled_kernel<TIn, TOut, 8><<<grid, 8 * CH / 2, 0, s>>>((const TIn*)in->data, weight, bias, act, up, H, W, C,
-                                                                      tiles_x, (TOut*)out->data);
+    dwconv5x5_tiled_kernel<TIn, TOut, 8><<<grid, 8 * CH / 2, 0, s>>>((const TIn*)in->data, (const TOut*)mul, weight, bias, act, up,
+                                                                      H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
   }
   GA_LAUNCH_OK();
   return 0;
@@ -123,17 +152,31 @@ static int launch_dw(const ga_tensor* in, const float* weight, const float* bias
 
 using namespace ga;
 
-extern "C" int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,
-                                const ga_tensor* out, void* stream) {
-  GA_CHECK(in && weight && out, "ga_dwconv5x5_fwd: null argument");
-  GA_CHECK(in->c == out->c && in->n == out->n, "ga_dwconv5x5_fwd: channels / batch must match");
-  GA_CHECK(in->c % (in->dtype == GA_BF16 ? 8 : 4) == 0, "ga_dwconv5x5_fwd: channels must be a multiple of 8 (bf16) / 4 (fp32)");
-  GA_CHECK(up ? (out->h == 2 * in->h && out->w == 2 * in->w) : (out->h == in->h && out->w == in->w), "ga_dwconv5x5_fwd: shape mismatch");
-  GA_CHECK(out->n <= 65535, "ga_dwconv5x5_fwd: batch too large for grid.z");
+static int dw_dispatch(const ga_tensor* in, const ga_tensor* mul, const float* weight, const float* bias, int act, int up,
+                       const ga_tensor* out, const ga_tensor* dact, void* stream, const char* who) {
+  GA_CHECK(in && weight && out, "%s: null argument", who);
+  GA_CHECK(in->c == out->c && in->n == out->n, "%s: channels / batch must match", who);
+  GA_CHECK(in->c % (in->dtype == GA_BF16 ? 8 : 4) == 0, "%s: channels must be a multiple of 8 (bf16) / 4 (fp32)", who);
+  GA_CHECK(up ? (out->h == 2 * in->h && out->w == 2 * in->w) : (out->h == in->h && out->w == in->w), "%s: shape mismatch", who);
+  GA_CHECK(out->n <= 65535, "%s: batch too large for grid.z", who);
+  GA_CHECK(!mul || (same_shape(mul, out) && mul->dtype == out->dtype), "%s: mul must match the output's shape and dtype", who);
+  GA_CHECK(!dact || (same_shape(dact, out) && dact->dtype == out->dtype), "%s: dact must match the output's shape and dtype", who);
   if (numel(out) == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (in->dtype == GA_F32 && out->dtype == GA_F32) return launch_dw<float, float>(in, weight, bias, act, up, out, s);
-  if (in->dtype == GA_BF16 && out->dtype == GA_BF16) return launch_dw<__nv_bfloat16, __nv_bfloat16>(in, weight, bias, act, up, out, s);
-  if (in->dtype == GA_BF16 && out->dtype == GA_F32) return launch_dw<__nv_bfloat16, float>(in, weight, bias, act, up, out, s);
-  return launch_dw<float, __nv_bfloat16>(in, weight, bias, act, up, out, s);
+  const void* m = mul ? mul->data : nullptr;
+  void* da = dact ? dact->data : nullptr;
+  if (in->dtype == GA_F32 && out->dtype == GA_F32) return launch_dw<float, float>(in, m, weight, bias, act, up, out, da, s);
+  if (in->dtype == GA_BF16 && out->dtype == GA_BF16) return launch_dw<__nv_bfloat16, __nv_bfloat16>(in, m, weight, bias, act, up, out, da, s);
+  if (in->dtype == GA_BF16 && out->dtype == GA_F32) return launch_dw<__nv_bfloat16, float>(in, m, weight, bias, act, up, out, da, s);
+  return launch_dw<float, __nv_bfloat16>(in, m, weight, bias, act, up, out, da, s);
+}
+
+extern "C" int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,
+                                const ga_tensor* out, void* stream) {
+  return dw_dispatch(in, nullptr, weight, bias, act, up, out, nullptr, stream, "ga_dwconv5x5_fwd");
+}
+
+extern "C" int ga_dwconv5x5_ex(const ga_tensor* in, const ga_tensor* mul, const float* weight, const float* bias, int act, int up,
+                               const ga_tensor* out, const ga_tensor* dact, void* stream) {
+  return dw_dispatch(in, mul, weight, bias, act, up, out, dact, stream, "ga_dwconv5x5_ex");
 }

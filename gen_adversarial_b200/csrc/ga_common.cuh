@@ -58,6 +58,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     default: return v;
   }
 }
+// fast-math variant for bf16 outputs (ex2.approx + rcp.approx; error << bf16 rounding)
+__device__ __forceinline__ float apply_act_fast(float v, int act) {
+  switch (act) {
+    case GA_ACT_SILU: return __fdividef(v, 1.0f + __expf(-v));
+    case GA_ACT_ELU: return v > 0.0f ? v : __expf(v) - 1.0f;
+    case GA_ACT_RELU: return fmaxf(v, 0.0f);
+    default: return v;
+  }
+}
 // derivative of act w.r.t. its pre-activation input v
 __device__ __forceinline__ float act_grad(float v, int act) {
   switch (act) {
@@ -68,6 +77,14 @@ __device__ __forceinline__ float act_grad(float v, int act) {
     case GA_ACT_ELU: return v > 0.0f ? 1.0f : expf(v);
     case GA_ACT_RELU: return v > 0.0f ? 1.0f : 0.0f;
     default: return 1.0f;
+  }
+}
+
+__device__ __forceinline__ float mul_factor(float m, int mode) {
+  switch (mode) {
+    case GA_MUL_RELU_MASK: return m > 0.0f ? 1.0f : 0.0f;
+    case GA_MUL_ELU_FROM_Y: return m > 0.0f ? 1.0f : m + 1.0f;
+    default: return m;
   }
 }
 

@@ -137,6 +137,8 @@ class MLVGMDefenseModel(ABC):
             if self._alpha_pinned is None or self._alpha_pinned.numel() != len(key):
                 self._alpha_pinned = torch.empty(len(key), dtype=torch.float32).pin_memory()
                 self._alpha_dev = torch.empty(len(key), dtype=torch.float32, device=self.device)
+            elif torch.cuda.is_available():
+                torch.cuda.current_stream().synchronize()      # the previous async copy must have read the pinned buffer
             self._alpha_pinned.copy_(torch.tensor(key, dtype=torch.float32))
             self._alpha_dev.copy_(self._alpha_pinned, non_blocking=True)
             self._alpha_key = key
@@ -182,3 +184,17 @@ class MLVGMDefenseModel(ABC):
     @abstractmethod
     def _forward_cuda(self, batch: torch.Tensor, tape=None):
         pass
+
+    def loss_input_grad(self, batch: torch.Tensor, labels: torch.Tensor, counter: torch.Tensor = None):
+        """Fused attack primitive: cross-entropy loss of the defended classifier and its gradient w.r.t. `batch`
+        (what `torch.autograd.grad(F.cross_entropy(net(x), y), [x])` returns, untargeted.py:146,201) without going through
+        torch's autograd engine.  -> (loss[n], grad (n,C,H,W) fp32, pred[n] int32).  `counter`: optional uint64 device
+        scalar accumulating argmax == label."""
+        from ...autograd import Tape
+        tape = Tape()
+        preds, _ = self._forward_cuda(batch.detach(), tape=tape)
+        loss, dlogits, pred = ops.softmax_xent(preds, labels, want_grad=True, counter=counter)
+        g_cls = self.classifier.classifier.backward(tape.vgg, dlogits)
+        g_x = self.autoencoder.backward(tape.nvae, None, g_cls)
+        gx = ops.preprocess_bwd(g_x, tape.pre, bool(self.blur_input), normalize=True, taps_cache=self._taps_cache)
+        return loss, gx, pred

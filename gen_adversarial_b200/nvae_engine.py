@@ -25,11 +25,11 @@ _PRE_TO_ACT = {PRE_ELU: ACT_ELU, PRE_SILU: ACT_SILU, PRE_AFFINE_SILU: ACT_SILU}
 
 
 class _Enc:
-    __slots__ = ("c1", "c2", "se", "skip", "down", "pre_affine")
+    __slots__ = ("c1", "c2", "se", "skip", "down", "pre_affine", "c1_d", "c2_d", "skip_d")
 
 
 class _Dec:
-    __slots__ = ("e", "dw_w", "dw_b", "p", "se", "skip", "up")
+    __slots__ = ("e", "dw_w", "dw_b", "p", "se", "skip", "up", "e_d", "p_d", "skip_d", "dw_wT")
 
 
 class NvaeEngine:
@@ -52,6 +52,7 @@ class NvaeEngine:
         f = Folder(state_dict, self.device, want_tc=self.bf16)
         self._fold(f)
         self._prior_cache = {}
+        self._has_dgrad = False
 
     # ------------------------------------------------------------------ weight preparation
     def _fold_enc(self, f: Folder, cell: EncCell) -> _Enc:
@@ -147,35 +148,68 @@ class NvaeEngine:
         if self.taps is not None:
             self.taps[name] = t.detach().float().permute(0, 3, 1, 2).contiguous()
 
-    def _conv(self, x, L: ops.ConvLayer, add=None, want_act=True, want_f32=False, x2=None, aux: ops.ConvLayer = None):
-        """-> (out in activation dtype | None, out fp32 | None).  fp32 mode: both are the same tensor."""
+    def _conv(self, x, L: ops.ConvLayer, add=None, want_act=True, want_f32=False, x2=None, aux: ops.ConvLayer = None,
+              mul=None, mul_mode=0, want_dact=False):
+        """-> (out in activation dtype | None, out fp32 | None[, dact]).  fp32 mode: both outputs are the same tensor.
+        out = (act(conv(pre(x)) + bias) + add) * f(mul);  dact = act'(pre-activation) (saved for the backward pass)."""
+        dact = None
         if not self.bf16:
             if x2 is not None:
                 add = ops.conv2d_simt(x2, aux, torch.float32, add=add)
-            o = ops.conv2d_simt(x, L, torch.float32, add=add)
-            return o, o
+            o = ops.conv2d_simt(x, L, torch.float32, add=add, mul=mul, mul_mode=mul_mode, want_dact=want_dact)
+            if want_dact:
+                o, dact = o
+            return (o, o, dact) if want_dact else (o, o)
         xin = x
-        tc_possible = L.w_tc is not None
-        if tc_possible:
+        if L.w_tc is not None:
             if L.pre_op != PRE_NONE:
                 xin = ops.affine_act(x, L.pre_scale, L.pre_shift, _PRE_TO_ACT[L.pre_op], torch.bfloat16)
             elif x.dtype != torch.bfloat16:
                 xin = ops.cast(x, torch.bfloat16)
             if ops.conv2d_tc_supported(xin, L, x2):
-                return ops.conv2d_tc(xin, L, want_bf16=want_act, want_f32=want_f32, add=add, x2=x2)
-        # SIMT (3-channel stem, stride-2 cells, odd shapes): applies the pre-op itself
+                if want_dact:
+                    dact = torch.empty(xin.shape[:3] + (L.cout,), device=xin.device, dtype=torch.bfloat16)
+                ob, of = ops.conv2d_tc(xin, L, want_bf16=want_act, want_f32=want_f32, add=add, x2=x2, mul=mul, mul_mode=mul_mode,
+                                       dact_out=dact)
+                return (ob, of, dact) if want_dact else (ob, of)
+        # SIMT (3-channel stem, stride-2 cells, transposed convs, odd shapes): applies the pre-op itself
         if x2 is not None:
             add = ops.conv2d_simt(x2, aux, torch.float32, add=add)
-        ob = ops.conv2d_simt(x, L, torch.bfloat16, add=add) if want_act else None
-        of = ops.conv2d_simt(x, L, torch.float32, add=add) if want_f32 else None
-        return ob, of
+        ob = of = None
+        out_hw = None
+        if L.up > 1:
+            out_hw = (x.shape[1] * L.up, x.shape[2] * L.up)        # transposed conv: full-size output (output_padding)
+        if want_act:
+            ob = ops.conv2d_simt(x, L, torch.bfloat16, add=add, out_hw=out_hw, mul=mul, mul_mode=mul_mode, want_dact=want_dact)
+            if want_dact:
+                ob, dact = ob
+        if want_f32:
+            of = ops.conv2d_simt(x, L, torch.float32, add=add, out_hw=out_hw, mul=mul, mul_mode=mul_mode,
+                                 want_dact=want_dact and dact is None)
+            if want_dact and dact is None:
+                of, dact = of
+        return (ob, of, dact) if want_dact else (ob, of)
 
-    def _enc_cell(self, x32, act, e: _Enc, next_affine):
+    def _dgrad(self, g, L: ops.ConvLayer, add=None, mul=None, mul_mode=0, f32=True):
+        """input-gradient of the forward conv whose dgrad layer is L: -> fp32 (stream gradients) or activation dtype."""
+        if not self.bf16:
+            out_hw = (g.shape[1] * L.up, g.shape[2] * L.up) if L.up > 1 else None
+            return ops.conv2d_simt(g, L, torch.float32, add=add, out_hw=out_hw, mul=mul, mul_mode=mul_mode)
+        ob, of = self._conv(g, L, add=add, want_act=not f32, want_f32=f32, mul=mul, mul_mode=mul_mode)
+        return of if f32 else ob
+
+    # ------------------------------------------------------------------ forward pieces (each returns what backward needs)
+    def _enc_cell(self, x32, act, e: _Enc, next_affine, rec):
         """x32: fp32 residual stream.  act: SiLU(BN1(x)) already materialised (bf16 mode) or None."""
+        taping = rec is not None
         if self.bf16 and e.c1.w_tc is not None and act is not None and ops.conv2d_tc_supported(act, e.c1):
-            h, _ = ops.conv2d_tc(act, e.c1)
+            dact1 = torch.empty(act.shape[:3] + (e.c1.cout,), device=act.device, dtype=torch.bfloat16) if taping else None
+            h, _ = ops.conv2d_tc(act, e.c1, dact_out=dact1)
+        elif taping:
+            h, _, dact1 = self._conv(x32, e.c1, want_dact=True)
         else:
             h, _ = self._conv(x32, e.c1)
+            dact1 = None
         r, _ = self._conv(h, e.c2)
         if e.down:
             _, skip = self._conv(x32, e.skip, want_act=False, want_f32=True)
@@ -184,12 +218,31 @@ class NvaeEngine:
         sums = ops.channel_sum(r)
         out, _, act_next, _ = ops.se_residual(r, sums, e.se, 0.1, skip, torch.float32,
                                               act_affine=next_affine if self.bf16 else None)
+        if taping:
+            rec.append(("enc", e, x32, dact1, r, sums))
         return out, act_next
 
-    def _dec_cell(self, x32, xa, d: _Dec):
+    def _enc_cell_bwd(self, g_out, rec):
+        _, e, x32, dact1, r, sums = rec
+        g_r = ops.se_residual_bwd(g_out, r, sums, e.se, 0.1, self.adt)
+        g_v1 = self._dgrad(g_r, e.c2_d, mul=dact1, f32=False)                       # through conv2, times SiLU'(v1)
+        g_a = self._dgrad(g_v1, e.c1_d, f32=True)                                   # w.r.t. SiLU(BN1(x))
+        if e.down:
+            g_s = self._dgrad(g_out, e.skip_d, f32=True)                            # w.r.t. SiLU(x)
+            t = ops.affine_act_bwd(g_s, x32, None, None, ACT_SILU, torch.float32)
+        else:
+            t = g_out
+        return ops.affine_act_bwd(g_a, x32, e.pre_affine[0], e.pre_affine[1], ACT_SILU, torch.float32, add=t)
+
+    def _dec_cell(self, x32, xa, d: _Dec, rec):
         """x32: fp32 residual stream; xa: same values in the activation dtype (GEMM operand)."""
-        h1, _ = self._conv(xa, d.e)                                   # low resolution for up cells (exact commute)
-        h2 = ops.dwconv5x5(h1, d.dw_w, d.dw_b, ACT_SILU, d.up, self.adt)
+        taping = rec is not None
+        if taping:
+            h1, _, dact_e = self._conv(xa, d.e, want_dact=True)
+            h2, dact_dw = ops.dwconv5x5(h1, d.dw_w, d.dw_b, ACT_SILU, d.up, self.adt, want_dact=True)
+        else:
+            h1, _ = self._conv(xa, d.e)                               # low resolution for up cells (exact commute)
+            h2 = ops.dwconv5x5(h1, d.dw_w, d.dw_b, ACT_SILU, d.up, self.adt)
         r, _ = self._conv(h2, d.p)
         if d.up:
             _, s = self._conv(xa, d.skip, want_act=False, want_f32=True)
@@ -198,7 +251,23 @@ class NvaeEngine:
             skip = x32
         sums = ops.channel_sum(r)
         out, out2, _, _ = ops.se_residual(r, sums, d.se, 0.1, skip, torch.float32, want_out2=self.bf16)
+        if taping:
+            rec.append(("dec", d, dact_e, dact_dw, r, sums))
         return out, (out2 if self.bf16 else out)
+
+    def _dec_cell_bwd(self, g_out, rec):
+        _, d, dact_e, dact_dw, r, sums = rec
+        g_r = ops.se_residual_bwd(g_out, r, sums, d.se, 0.1, self.adt)
+        g_v2 = self._dgrad(g_r, d.p_d, mul=dact_dw, f32=False)                      # through project, times SiLU'(dw out)
+        if d.up:
+            g_h1 = ops.dwconv5x5(g_v2, d.dw_wT, None, ACT_NONE, False, self.adt)    # transposed depthwise (flipped taps)
+            g_v1 = ops.sumpool2x2(g_h1, self.adt, mul=dact_e)                       # nearest-x2 backward, times SiLU'(expand out)
+            g_s = ops.upsample_bilinear2x_bwd(g_out, torch.float32)
+            t = self._dgrad(g_s, d.skip_d, f32=True)
+        else:
+            g_v1 = ops.dwconv5x5(g_v2, d.dw_wT, None, ACT_NONE, False, self.adt, mul=dact_e)
+            t = g_out
+        return self._dgrad(g_v1, d.e_d, add=t, f32=True)
 
     def _enc_sequence(self):
         """encoder cells in execution order with the stash / scale boundaries (models.py:176-192)."""
@@ -219,9 +288,13 @@ class NvaeEngine:
         alphas_dev: fp32 device tensor [n_latents] (already attenuated) -- read by the kernels at run time, so it
         can be changed between calls without re-capturing anything (alpha_learning/common_utils.py:88).
         eps_levels: explicit N(0,1) draws per level in NCHW (parity mode) or None (Philox in-kernel).
+        tape: None, or a list that receives what `backward` needs (saved activations stay alive with it).
         -> (purified NCHW fp32 in [0,1], classifier input NHWC or None)"""
         spec = self.spec
         n = x_nhwc.shape[0]
+        rec = tape
+        if rec is not None and not self._has_dgrad:
+            self._build_dgrad()
         x32 = ops.conv2d_simt(x_nhwc, self.init_conv, torch.float32)
         self._tap("init_conv", x32)
         seq = self._enc_sequence()
@@ -229,49 +302,138 @@ class NvaeEngine:
         act = None
         for i, (_, e, st) in enumerate(seq):
             nxt = seq[i + 1][1].pre_affine if (i + 1 < len(seq) and not seq[i + 1][1].down) else None
-            x32, act = self._enc_cell(x32, act, e, nxt)
+            x32, act = self._enc_cell(x32, act, e, nxt, rec)
             if st is not None:
                 stash[st] = x32
+                if rec is not None:
+                    rec.append(("stash", st))
             if i == len(self.pre_cells) - 1:
                 self._tap("pre", x32)
         # encoder_0 (models.py:195)
+        x32_top = x32
         xa, _ = self._conv(x32, self.enc0)
         self._tap("enc0", xa)
         lv0 = self.levels[0]
         _, muq = self._conv(xa, lv0["enc_sampler"], want_act=False, want_f32=True)
-        z = ops.latent_mix(muq, None, eps_levels[0] if eps_levels is not None else None, seed, 0, sample0,
-                           alphas_dev[0:1], self.temperature, spec.z, self.zc, self.adt)
+        eps0 = eps_levels[0] if eps_levels is not None else None
+        z = ops.latent_mix(muq, None, eps0, seed, 0, sample0, alphas_dev[0:1], self.temperature, spec.z, self.zc, self.adt)
         self._tap("z0", z[..., :spec.z])
         key = (n,)
         if key not in self._prior_cache:
             self._prior_cache = {key: lv0["prior_x"].expand(n, -1, -1, -1).contiguous()}
         prior_x = self._prior_cache[key]
         if self.bf16:
-            xa, x32 = self._conv(z, lv0["dec_comb_z"], add=prior_x, want_act=True, want_f32=True)
+            xa2, x32 = self._conv(z, lv0["dec_comb_z"], add=prior_x, want_act=True, want_f32=True)
         else:
             x32 = ops.conv2d_simt(z, lv0["dec_comb_z"], torch.float32, add=prior_x)
-            xa = x32
+            xa2 = x32
+        if rec is not None:
+            rec.append(("level0", lv0, x32_top, xa, muq, alphas_dev[0:1]))
+        xa = xa2
         idx = 1
         for s in range(spec.num_scales):
             for L in self.levels:
                 if L["s"] != s or (L["s"] == 0 and L["g"] == 0):
                     continue
                 for d in L["cells"]:
-                    x32, xa = self._dec_cell(x32, xa, d)
+                    x32, xa = self._dec_cell(x32, xa, d, rec)
                 comb, _ = self._conv(xa, L["enc_comb"], add=stash[(L["s"], L["g"])])
                 _, muq = self._conv(comb, L["enc_sampler"], want_act=False, want_f32=True)
                 _, pp = self._conv(x32, L["dec_sampler"], want_act=False, want_f32=True)
-                z = ops.latent_mix(muq, pp, eps_levels[idx] if eps_levels is not None else None, seed, idx, sample0,
-                                   alphas_dev[idx:idx + 1], self.temperature, spec.z, self.zc, self.adt)
+                eps = eps_levels[idx] if eps_levels is not None else None
+                z = ops.latent_mix(muq, pp, eps, seed, idx, sample0, alphas_dev[idx:idx + 1], self.temperature, spec.z, self.zc,
+                                   self.adt)
                 self._tap(f"z{idx}", z[..., :spec.z])
+                if rec is not None:
+                    rec.append(("level", L, x32, muq, pp, eps, seed, idx, sample0, alphas_dev[idx:idx + 1]))
                 xa, x32 = self._conv(xa, L["dec_comb"], want_act=True, want_f32=True, x2=z, aux=L["dec_comb_z"])
                 idx += 1
             if s in self.up_cells:
-                x32, xa = self._dec_cell(x32, xa, self.up_cells[s])
+                x32, xa = self._dec_cell(x32, xa, self.up_cells[s], rec)
         self._tap("dec_out", x32)
         for d in self.post_cells:
-            x32, xa = self._dec_cell(x32, xa, d)
+            x32, xa = self._dec_cell(x32, xa, d, rec)
         self._tap("post", x32)
         _, logits = self._conv(x32, self.to_logits, want_act=False, want_f32=True)
         self._tap("logits", logits)
+        if rec is not None:
+            rec.append(("head", x32, logits))
         return ops.discmix_mean(logits, spec.num_mixtures, cls_dtype)
+
+    # ------------------------------------------------------------------ backward (input gradient only)
+    def _build_dgrad(self):
+        """flipped / transposed weights of every conv on the path (built on first use: attacks only)."""
+        from .fold import Folder
+        f = Folder({}, self.device, want_tc=self.bf16)
+
+        def dg(L: ops.ConvLayer, pad_cin_to=None):
+            w = L.w_simt.detach().to("cpu", torch.float64).view(L.kh, L.kw, L.cin, L.cout).permute(3, 2, 0, 1)   # [cout,cin,kh,kw]
+            if pad_cin_to is not None and pad_cin_to > w.shape[0]:       # dgrad input channels = forward cout, zero padded
+                w = torch.cat([w, torch.zeros((pad_cin_to - w.shape[0],) + tuple(w.shape[1:]), dtype=w.dtype)], dim=0)
+            wt = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()           # [cin, cout(_pad), kh, kw]
+            return f.conv(wt, None, stride=1, pad=L.kh - 1 - L.pad, name=L.name + ".dgrad", up=L.stride)
+
+        for _, e, _ in self._enc_sequence():
+            e.c1_d, e.c2_d = dg(e.c1), dg(e.c2)
+            e.skip_d = dg(e.skip) if e.skip is not None else None
+        decs = [d for L in self.levels for d in L.get("cells", [])] + list(self.up_cells.values()) + list(self.post_cells)
+        for d in decs:
+            d.e_d, d.p_d = dg(d.e), dg(d.p)
+            d.skip_d = dg(d.skip) if d.skip is not None else None
+            d.dw_wT = d.dw_w.flip(0).contiguous()                        # 5x5 taps reversed = spatial flip
+        self.init_conv_d = dg(self.init_conv)
+        self.enc0_d = dg(self.enc0)
+        self.to_logits_d = dg(self.to_logits)
+        for L in self.levels:
+            L["enc_sampler_d"] = dg(L["enc_sampler"], pad_cin_to=self.zc)
+            L["dec_comb_x_d"] = dg(L["dec_comb"]) if "prior_x" not in L else None
+            L["dec_comb_z_d"] = dg(L["dec_comb_z"])
+            if "enc_comb" in L:
+                L["enc_comb_d"] = dg(L["enc_comb"])
+                L["dec_sampler_d"] = dg(L["dec_sampler"])
+        self._has_dgrad = True
+
+    def backward(self, tape, g_purified_nchw=None, g_cls=None):
+        """Reverse sweep over `tape` (filled by `purify`).  g_purified_nchw: d loss / d purified (N,3,H,W) fp32 or None;
+        g_cls: d loss / d classifier-input (N,H,W,3) or None.  -> d loss / d x_nhwc (N,H,W,3) fp32 (w.r.t. the
+        normalised pre-processed input).  The tape is not consumed: backward may be called repeatedly with different
+        output gradients (DeepFool / FAB, untargeted.py:529-535,622-627)."""
+        spec = self.spec
+        g = None                   # gradient w.r.t. the current stream tensor x32
+        g_stash = {}
+        for rec in reversed(tape):
+            kind = rec[0]
+            if kind == "head":
+                _, x32, logits = rec
+                g_logits = ops.discmix_mean_bwd(logits, spec.num_mixtures, g_purified_nchw, g_cls)
+                t = self._dgrad(g_logits, self.to_logits_d, f32=True)                 # w.r.t. ELU(x)
+                g = ops.affine_act_bwd(t, x32, None, None, ACT_ELU, torch.float32)
+            elif kind == "dec":
+                g = self._dec_cell_bwd(g, rec)
+            elif kind == "level":
+                _, L, x32, muq, pp, eps, seed, idx, sample0, a_dev = rec
+                g1 = self._dgrad(g, L["dec_comb_x_d"], f32=True)
+                g_z = self._dgrad(g, L["dec_comb_z_d"], f32=True)
+                g_q, g_p = ops.latent_mix_bwd(g_z, muq, pp, eps, seed, idx, sample0, a_dev, self.temperature, spec.z, self.zc)
+                g_comb = self._dgrad(g_q, L["enc_sampler_d"], f32=True)
+                g_stash[(L["s"], L["g"])] = g_comb                                    # encoder-side stash gets it as is
+                g2 = self._dgrad(g_comb, L["enc_comb_d"], add=g1, f32=True)
+                t = self._dgrad(g_p, L["dec_sampler_d"], f32=True)                    # w.r.t. ELU(x)
+                g = ops.affine_act_bwd(t, x32, None, None, ACT_ELU, torch.float32, add=g2)
+            elif kind == "level0":
+                _, lv0, x32_top, xa, muq, a_dev = rec
+                g_z = self._dgrad(g, lv0["dec_comb_z_d"], f32=True)
+                g_q, _ = ops.latent_mix_bwd(g_z, muq, None, None, 0, 0, 0, a_dev, self.temperature, spec.z, self.zc)
+                g_v = self._dgrad(g_q, lv0["enc_sampler_d"], mul=xa, mul_mode=2, f32=True)   # times ELU'(v) from y = ELU(v)
+                t = self._dgrad(g_v, self.enc0_d, f32=True)                            # w.r.t. ELU(x_top)
+                g = ops.affine_act_bwd(t, x32_top, None, None, ACT_ELU, torch.float32)
+            elif kind == "stash":
+                gs = g_stash.pop(rec[1], None)
+                if gs is not None:
+                    g = ops.add(g, gs, torch.float32)
+            elif kind == "enc":
+                g = self._enc_cell_bwd(g, rec)
+            else:
+                raise RuntimeError(f"unknown tape record {kind}")
+        out_hw = None
+        return ops.conv2d_simt(g, self.init_conv_d, torch.float32, out_hw=out_hw)

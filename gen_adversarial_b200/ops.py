@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import GaTensor, GaConvDesc, GA_F32, GA_BF16, PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, \
-    ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
+    ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -123,13 +123,15 @@ class ConvLayer:
     cin2: int = 0                              # channels of the second (1x1) K source folded into w_tc
     name: str = ""
 
-    def desc(self, tc: bool) -> GaConvDesc:
+    def desc(self, tc: bool, mul=None, mul_mode: int = 0, dact=None) -> GaConvDesc:
         w = self.w_tc if tc else self.w_simt
         if w is None:
             raise RuntimeError(f"conv layer {self.name}: no {'tensor-core' if tc else 'SIMT'} weights prepared")
         return GaConvDesc(self.kh, self.kw, self.stride, self.pad, self.up, PRE_NONE if tc else self.pre_op, self.post_act,
                           ptr(self.pre_scale), ptr(self.pre_shift), w.data_ptr(), ptr(self.bias), 0,
-                          w.shape[1] if tc else 0)
+                          w.shape[1] if tc else 0,
+                          ptr(mul), _dt(mul) if mul is not None else 0, mul_mode,
+                          ptr(dact), _dt(dact) if dact is not None else 0, 0)
 
 
 def conv_out_hw(L: ConvLayer, h: int, w: int):
@@ -139,14 +141,16 @@ def conv_out_hw(L: ConvLayer, h: int, w: int):
 
 @_timed("conv2d_simt")
 def conv2d_simt(x: torch.Tensor, L: ConvLayer, out_dtype: torch.dtype, add: Optional[torch.Tensor] = None,
-                out_hw=None) -> torch.Tensor:
+                out_hw=None, mul: Optional[torch.Tensor] = None, mul_mode: int = 0, want_dact: bool = False):
+    """out = (act(conv(pre(x)) + bias) + add) * f(mul).  With want_dact -> (out, act'(pre-activation))."""
     n, h, w, c = x.shape
     assert c == L.cin, (L.name, c, L.cin)
     ho, wo = out_hw if out_hw is not None else conv_out_hw(L, h, w)
     out = torch.empty((n, ho, wo, L.cout), device=x.device, dtype=out_dtype)
-    d = L.desc(False)
+    dact = torch.empty_like(out) if want_dact else None
+    d = L.desc(False, mul, mul_mode, dact)
     _lib.check(_lib.lib().ga_conv2d_simt(gt(x), ctypes.byref(d), gt(add), gt(out), stream()), f"conv2d_simt[{L.name}]")
-    return out
+    return (out, dact) if want_dact else out
 
 
 def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor] = None) -> bool:
@@ -157,13 +161,14 @@ def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor
 
 
 def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
-              add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None):
-    """-> (out_bf16 or None, out_f32 or None)"""
+              add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None,
+              mul: Optional[torch.Tensor] = None, mul_mode: int = 0, dact_out: Optional[torch.Tensor] = None):
+    """-> (out_bf16 or None, out_f32 or None);  out = (act(conv + bias) + add) * f(mul); dact_out <- act'(conv + bias)"""
     n, h, w, c = x.shape
     assert c == L.cin, (L.name, c, L.cin)
     ob = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     of = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.float32) if want_f32 else None
-    d = L.desc(True)
+    d = L.desc(True, mul, mul_mode, dact_out)
     e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_conv2d_tc(gt(x), gt(x2), ctypes.byref(d), gt(add), gt(ob), gt(of), stream()),
                f"conv2d_tc[{L.name}]")
@@ -180,12 +185,18 @@ def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: b
 
 @_timed("dwconv5x5")
 def dwconv5x5(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int, up: bool,
-              out_dtype: torch.dtype) -> torch.Tensor:
+              out_dtype: torch.dtype, mul: Optional[torch.Tensor] = None, want_dact: bool = False):
+    """out = act(dwconv5x5(x) + bias) * mul.  With want_dact -> (out, act'(pre-activation))."""
     n, h, w, c = x.shape
     s = 2 if up else 1
     out = torch.empty((n, h * s, w * s, c), device=x.device, dtype=out_dtype)
-    _lib.check(_lib.lib().ga_dwconv5x5_fwd(gt(x), ptr(weight), ptr(bias), act, int(up), gt(out), stream()), "dwconv5x5")
-    return out
+    if mul is None and not want_dact:
+        _lib.check(_lib.lib().ga_dwconv5x5_fwd(gt(x), ptr(weight), ptr(bias), act, int(up), gt(out), stream()), "dwconv5x5")
+        return out
+    dact = torch.empty_like(out) if want_dact else None
+    _lib.check(_lib.lib().ga_dwconv5x5_ex(gt(x), gt(mul), ptr(weight), ptr(bias), act, int(up), gt(out), gt(dact), stream()),
+               "dwconv5x5_ex")
+    return (out, dact) if want_dact else out
 
 
 @_timed("channel_sum")
@@ -337,6 +348,90 @@ def softmax_xent(logits, labels, want_grad=True, counter=None):
     _lib.check(_lib.lib().ga_softmax_xent(ptr(logits), ptr(labels), n, k, ptr(loss), ptr(dl), ptr(pred), ptr(counter), stream()),
                "softmax_xent")
     return loss, dl, pred
+
+
+# ------------------------------------------------------------------------------------------------ backward ops
+@_timed("affine_act_bwd")
+def affine_act_bwd(g, x, scale, shift, act: int, out_dtype, add=None):
+    out = torch.empty(g.shape, device=g.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_affine_act_bwd(gt(g), gt(x), ptr(scale), ptr(shift), act, gt(add), gt(out), stream()), "affine_act_bwd")
+    return out
+
+
+@_timed("add")
+def add(a, b, out_dtype):
+    out = torch.empty(a.shape, device=a.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_add(gt(a), gt(b), gt(out), stream()), "add")
+    return out
+
+
+@_timed("se_residual_bwd")
+def se_residual_bwd(g_out, r, sums, se, res_scale: float, out_dtype):
+    w1, b1, w2, b2 = se
+    g_r = torch.empty(r.shape, device=r.device, dtype=out_dtype)
+    dots = torch.empty_like(sums)
+    _lib.check(_lib.lib().ga_se_residual_bwd(gt(g_out), gt(r), ptr(sums), ptr(dots), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                             w1.shape[0], res_scale, gt(g_r), stream()), "se_residual_bwd")
+    return g_r
+
+
+@_timed("sumpool2x2")
+def sumpool2x2(x, out_dtype, mul=None):
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_sumpool2x2(gt(x), gt(mul), gt(out), stream()), "sumpool2x2")
+    return out
+
+
+@_timed("upsample_bilinear2x_bwd")
+def upsample_bilinear2x_bwd(g_out, out_dtype):
+    n, h, w, c = g_out.shape
+    out = torch.empty((n, h // 2, w // 2, c), device=g_out.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_upsample_bilinear2x_bwd(gt(g_out), gt(out), stream()), "upsample_bilinear2x_bwd")
+    return out
+
+
+@_timed("maxpool2x2_bwd")
+def maxpool2x2_bwd(x_in, g_out, relu: bool, out_dtype):
+    out = torch.empty(x_in.shape, device=x_in.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_maxpool2x2_bwd(gt(x_in), gt(g_out), int(relu), gt(out), stream()), "maxpool2x2_bwd")
+    return out
+
+
+@_timed("latent_mix_bwd")
+def latent_mix_bwd(g_z, q, p, eps_nchw, seed: int, level: int, sample0: int, alpha_dev, temperature: float, zdim: int, zc: int):
+    """-> (g_q fp32 [n,h,w,zc] zero-padded beyond zdim, g_p fp32 [n,h,w,2*zdim] | None)"""
+    n, h, w, _ = q.shape
+    g_q = torch.empty((n, h, w, zc), device=q.device, dtype=torch.float32)
+    g_p = torch.empty((n, h, w, 2 * zdim), device=q.device, dtype=torch.float32) if p is not None else None
+    _lib.check(_lib.lib().ga_latent_mix_bwd(gt(g_z), gt(q), gt(p), ptr(eps_nchw), seed, level, sample0, ptr(alpha_dev), temperature,
+                                            zdim, gt(g_q), gt(g_p), stream()), "latent_mix_bwd")
+    return g_q, g_p
+
+
+@_timed("discmix_mean_bwd")
+def discmix_mean_bwd(logits, n_mix: int, g_purified_nchw, g_cls):
+    g_logits = torch.empty_like(logits)
+    _lib.check(_lib.lib().ga_discmix_mean_bwd(gt(logits), n_mix, ptr(g_purified_nchw), gt(g_cls), gt(g_logits), stream()),
+               "discmix_mean_bwd")
+    return g_logits
+
+
+def preprocess_bwd(g_nhwc, pre_nchw, blur: bool, normalize: bool = True, taps_cache=None):
+    """-> gradient w.r.t. the input batch (NCHW fp32)."""
+    n, h, w, c = g_nhwc.shape
+    gx = torch.empty((n, c, h, w), device=g_nhwc.device, dtype=torch.float32)
+    taps, radius, tmp = None, 0, None
+    if blur:
+        if taps_cache is not None and taps_cache.get("h") == h:
+            taps, radius = taps_cache["taps"], taps_cache["radius"]
+        else:
+            t, radius = gaussian_taps(h)
+            taps = t.to(g_nhwc.device)
+        tmp = torch.empty_like(gx)
+    _lib.check(_lib.lib().ga_preprocess_bwd(gt(g_nhwc), ptr(pre_nchw), ptr(taps), radius, int(normalize), ptr(tmp), ptr(gx), stream()),
+               "preprocess_bwd")
+    return gx
 
 
 def launch_count(reset: bool = False) -> int:

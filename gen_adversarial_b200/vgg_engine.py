@@ -42,6 +42,7 @@ class Vgg11Engine:
         self.mode = mode
         self.bf16 = mode == "bf16"
         self.adt = torch.bfloat16 if self.bf16 else torch.float32
+        self._has_dgrad = False
         sd = {(k[len("model."):] if k.startswith("model.") else k): v for k, v in state_dict.items()}
         f = Folder(sd, self.device, want_tc=self.bf16)
         self.layers = []
@@ -91,20 +92,103 @@ class Vgg11Engine:
         if self.bf16:
             self.fc1.w_tc = w3.to(torch.bfloat16).contiguous()
 
-    def _conv(self, x, L, out_f32=False):
+    def _conv(self, x, L, out_f32=False, mul=None, mul_mode=0):
         if self.bf16 and ops.conv2d_tc_supported(x, L):
-            ob, of = ops.conv2d_tc(x, L, want_bf16=not out_f32, want_f32=out_f32)
+            ob, of = ops.conv2d_tc(x, L, want_bf16=not out_f32, want_f32=out_f32, mul=mul, mul_mode=mul_mode)
             return of if out_f32 else ob
-        return ops.conv2d_simt(x, L, torch.float32 if (out_f32 or not self.bf16) else torch.bfloat16)
+        return ops.conv2d_simt(x, L, torch.float32 if (out_f32 or not self.bf16) else torch.bfloat16, mul=mul, mul_mode=mul_mode)
 
     def forward(self, x_nhwc: torch.Tensor, tape=None) -> torch.Tensor:
-        """x_nhwc: (N,H,W,3) already normalised with mean=std=0.5 (abstract_models.py:59-60). -> logits fp32 (N, classes)"""
+        """x_nhwc: (N,H,W,3) already normalised with mean=std=0.5 (abstract_models.py:59-60). -> logits fp32 (N, classes)
+        tape: None or a list receiving the activations the input-gradient needs (ReLU outputs)."""
         x = x_nhwc
+        if tape is not None and not self._has_dgrad:
+            self._build_dgrad()
         for kind, L in self.layers:
-            x = ops.maxpool2x2(x) if kind == "pool" else self._conv(x, L)
+            if kind == "pool":
+                y = ops.maxpool2x2(x)
+                if tape is not None:
+                    tape.append(("vgg_pool", x))
+                x = y
+            else:
+                x = self._conv(x, L)
+                if tape is not None:
+                    tape.append(("vgg_conv", L, x))
         n = x.shape[0]
         assert x.shape[1] == self.feat_hw and x.shape[2] == self.feat_hw, "input resolution differs from the one folded at load"
+        feat_shape = x.shape
         x = x.reshape(n, 1, 1, -1)
-        x = self._conv(x, self.fc0)
-        logits = self._conv(x, self.fc1, out_f32=True)
+        h = self._conv(x, self.fc0)
+        logits = self._conv(h, self.fc1, out_f32=True)
+        if tape is not None:
+            tape.append(("vgg_head", h, feat_shape))
         return logits.reshape(n, self.n_classes)
+
+    # ------------------------------------------------------------------ backward (input gradient only)
+    def _build_dgrad(self):
+        """transposed / flipped weights for the input-gradient pass (built on first use: attacks only)."""
+        def dg_conv(L):
+            w = L.w_simt.view(L.kh, L.kw, L.cin, L.cout)                       # fp32 [kh,kw,cin,cout]
+            wt = w.flip(0, 1).permute(0, 1, 3, 2).contiguous()                 # taps flipped, [kh,kw,cout,cin]
+            D = ops.ConvLayer(L.kh, L.kw, 1, L.kh - 1 - L.pad, L.cout, L.cin, name=L.name + ".dgrad")
+            D.w_simt = wt.reshape(L.kh * L.kw * L.cout, L.cin).contiguous()
+            if self.bf16 and L.cout % 8 == 0:
+                D.w_tc = wt.permute(3, 0, 1, 2).reshape(L.cin, L.kh * L.kw * L.cout).to(torch.bfloat16).contiguous()
+            return D
+
+        self.dgrad = {id(L): dg_conv(L) for kind, L in self.layers if kind == "conv"}
+        # head: y = x W^T  ->  g_x = g_y W
+        def dg_fc(L):
+            D = ops.ConvLayer(1, 1, 1, 0, L.cout, L.cin, name=L.name + ".dgrad")
+            if self.bf16:
+                D.w_tc = L.w_tc.t().contiguous()                                # [cin, cout]
+                if L.w_simt is not None:
+                    D.w_simt = L.w_simt.t().contiguous()
+            else:
+                D.w_simt = L.w_simt.t().contiguous()                            # [cout, cin]
+            return D
+        self.fc0_d, self.fc1_d = dg_fc(self.fc0), dg_fc(self.fc1)
+        self._has_dgrad = True
+
+    def backward(self, tape, g_logits: torch.Tensor) -> torch.Tensor:
+        """g_logits (N, classes) fp32 -> d loss / d x_nhwc (N,H,W,3) in fp32.  `tape` holds only "vgg_*" records."""
+        n = g_logits.shape[0]
+        g = g_logits.contiguous().reshape(n, 1, 1, -1)
+        pending_relu = None                      # ReLU output whose mask still has to be applied to g
+        for rec in reversed(tape):
+            kind = rec[0]
+            if kind == "vgg_head":
+                _, h, feat_shape = rec
+                if self.bf16 and g.dtype != torch.bfloat16:
+                    g = ops.cast(g, torch.bfloat16)
+                g = self._conv(g, self.fc1_d, mul=h, mul_mode=1)                # times ReLU mask of h
+                g = self._conv(g, self.fc0_d).reshape(feat_shape)
+            elif kind == "vgg_pool":
+                _, x_in = rec
+                g = ops.maxpool2x2_bwd(x_in, g, True, self.adt)                  # + ReLU mask of the conv before the pool
+                pending_relu = None
+            elif kind == "vgg_conv":
+                _, L, y = rec
+                if pending_relu is not None:                                     # conv directly followed by another conv
+                    raise RuntimeError("internal: unresolved ReLU mask")
+                D = self.dgrad[id(L)]
+                # the input of this conv is either the network input, a pool output, or the previous conv's ReLU output;
+                # in the last case that ReLU's mask is applied here as the epilogue multiplier
+                prev = self._prev_relu_output(tape, rec)
+                is_first = L.cin == 3
+                if prev is not None:
+                    g = self._conv(g, D, mul=prev, mul_mode=1)
+                else:
+                    g = self._conv(g, D, out_f32=is_first)
+            else:
+                raise RuntimeError(f"unknown tape record {kind}")
+        return g if g.dtype == torch.float32 else ops.cast(g, torch.float32)
+
+    @staticmethod
+    def _prev_relu_output(tape, rec):
+        """the ReLU output feeding `rec`'s conv directly (None if its input is a pool output or the network input)."""
+        i = next(k for k, r in enumerate(tape) if r is rec)
+        if i == 0:
+            return None
+        p = tape[i - 1]
+        return p[2] if p[0] == "vgg_conv" else None

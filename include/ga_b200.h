@@ -27,11 +27,14 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 1
+#define GA_ABI_VERSION 2
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3 };
 enum ga_act { GA_ACT_NONE = 0, GA_ACT_SILU = 1, GA_ACT_ELU = 2, GA_ACT_RELU = 3 };
+/* epilogue multiplier modes (backward): multiply by the tensor itself, or by the ReLU / ELU derivative
+ * reconstructed from the saved OUTPUT y of the forward activation (relu: y>0, elu: y>0 ? 1 : y+1) */
+enum ga_mul_mode { GA_MUL_VALUE = 0, GA_MUL_RELU_MASK = 1, GA_MUL_ELU_FROM_Y = 2 };
 
 /* dense NHWC tensor view */
 typedef struct ga_tensor {
@@ -54,6 +57,13 @@ typedef struct ga_conv_desc {
   const float* bias;      /* [cout] or NULL */
   int32_t reserved0;
   int32_t ktot;           /* tensor-core only: row length of `weight` = kh*kw*cin (+ cin2) */
+  /* per-call epilogue extras.  out = (act(acc + bias) + add) * mul;  dact_out = act'(acc + bias) */
+  const void* mul;        /* optional tensor of the output's shape (backward: derivative of the producer's activation) */
+  int32_t mul_dtype;      /* ga_dtype */
+  int32_t mul_mode;       /* ga_mul_mode */
+  void* dact_out;         /* optional: derivative of post_act at the pre-activation, saved for the backward pass */
+  int32_t dact_dtype;
+  int32_t reserved1;
 } ga_conv_desc;
 
 const char* ga_last_error(void);
@@ -90,6 +100,12 @@ int ga_conv2d_tc_supported(const ga_tensor* in, const ga_tensor* in2, const ga_c
  * input is read through a nearest x2 up-sampling (architecture.py:162). weight fp32 [25][c]. */
 int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,
                      const ga_tensor* out, void* stream);
+
+/* extended form: `mul` (output's shape/dtype) multiplies the result (backward: times the saved act' of the producer),
+ * `dact` receives act'(pre-activation) (taping forward).  The dgrad of the depthwise conv is the same kernel on
+ * flipped taps. */
+int ga_dwconv5x5_ex(const ga_tensor* in, const ga_tensor* mul, const float* weight, const float* bias, int act, int up,
+                    const ga_tensor* out, const ga_tensor* dact, void* stream);
 
 /* ---- squeeze-excite + residual (architecture.py:37-61,128-136,178-186) */
 /* sums is [n][ga_channel_sum_parts(n, h*w)][c] partial sums (two-stage, no atomics: bit-reproducible) */
@@ -133,6 +149,28 @@ int ga_pgd_linf_step(float* x_adv, const float* grad, const float* x_nat, float 
 /* softmax cross-entropy: dlogits = (softmax - onehot)/n (mean reduction), loss[n], argmax==label counter */
 int ga_softmax_xent(const float* logits, const int64_t* labels, int n, int classes, float* loss, float* dlogits,
                     int32_t* pred, unsigned long long* n_correct /*device, accumulated*/, void* stream);
+
+/* ================================================================ input-gradient (dgrad-only) backward pass
+ * The attacks differentiate the logits w.r.t. the input batch only (untargeted.py:146,201): weights are frozen, no
+ * weight gradient is ever formed.  Conv dgrads = ga_conv2d_* on flipped/transposed weights (+ `mul` epilogue). */
+/* out = g * act'(scale*x + shift) * scale (+ add): backward of the BN+SiLU / SiLU / ELU pre-activations */
+int ga_affine_act_bwd(const ga_tensor* g, const ga_tensor* x, const float* scale, const float* shift, int act,
+                      const ga_tensor* add /*nullable*/, const ga_tensor* out, void* stream);
+int ga_add(const ga_tensor* a, const ga_tensor* b, const ga_tensor* out, void* stream);
+/* backward of ga_se_residual_fwd w.r.t. r (the skip gradient is g_out itself): g_r = s*gate*g_out + d(gate MLP)/HW.
+ * sums = the forward's partial channel sums of r; dots_ws = workspace of the same size. */
+int ga_se_residual_bwd(const ga_tensor* g_out, const ga_tensor* r, const float* sums, float* dots_ws, const float* w1,
+                       const float* b1, const float* w2, const float* b2, int hidden, float res_scale,
+                       const ga_tensor* g_r, void* stream);
+int ga_sumpool2x2(const ga_tensor* in, const ga_tensor* mul /*nullable, out's shape*/, const ga_tensor* out, void* stream); /* nearest x2 backward (* mul) */
+int ga_upsample_bilinear2x_bwd(const ga_tensor* g_out, const ga_tensor* g_in, void* stream);
+/* gradient to the first maximal element of each window (torch semantics); relu=1 also applies the mask x_in > 0 */
+int ga_maxpool2x2_bwd(const ga_tensor* x_in, const ga_tensor* g_out, int relu, const ga_tensor* g_in, void* stream);
+int ga_latent_mix_bwd(const ga_tensor* g_z, const ga_tensor* q, const ga_tensor* p /*nullable*/, const float* eps_nchw,
+                      uint64_t seed, int level, int64_t sample0, const float* alpha_dev, float temperature, int zdim,
+                      const ga_tensor* g_q, const ga_tensor* g_p /*nullable*/, void* stream);
+int ga_discmix_mean_bwd(const ga_tensor* logits, int n_mix, const float* g_purified_nchw /*nullable*/,
+                        const ga_tensor* g_cls /*nullable*/, const ga_tensor* g_logits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -272,3 +272,15 @@ def pgd_linf_step(x_adv, grad, x_nat, step: float, eps: float):
     x_adv = x_adv + step * torch.sign(grad)
     x_adv = torch.min(torch.max(x_adv, x_nat - eps), x_nat + eps)
     return x_adv.clamp(0.0, 1.0)
+
+
+def pgd_linf_attack(logits_fn, x, y, eps: float, step: float, steps: int):
+    """PGD-Linf with the update of trades/modules.py:43-45, cross-entropy loss, start at x (documented choices --
+    the reference has no PGD attack; parity unpinned).  logits_fn(x_adv, step_index) -> logits (differentiable)."""
+    x_adv = x.clone()
+    for i in range(steps):
+        xa = x_adv.clone().requires_grad_(True)
+        loss = F.cross_entropy(logits_fn(xa, i), y)
+        grad, = torch.autograd.grad(loss, [xa])
+        x_adv = pgd_linf_step(x_adv, grad, x, step, eps).detach()
+    return x_adv

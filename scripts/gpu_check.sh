@@ -8,10 +8,16 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 echo "== kernels (non-TC)" ; timeout -s KILL 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "not conv_tc" -p no:cacheprovider > gpurun_out/kernels_simt.log 2>&1; tail -5 gpurun_out/kernels_simt.log
 echo "== kernels (TC)" ; timeout -s KILL 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv_tc" -p no:cacheprovider > gpurun_out/kernels_tc.log 2>&1; tail -5 gpurun_out/kernels_tc.log
 echo "== nvae parity" ; timeout -s KILL 900 python -m pytest tests/test_nvae_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/nvae.log 2>&1; grep -E "err|passed|failed|FAILED|Error" gpurun_out/nvae.log | grep -v "^tap\|fp32\] tiny" | tail -30
+echo "== backward / pgd" ; timeout -s KILL 900 python -m pytest tests/test_backward_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/backward.log 2>&1; grep -E "grad|PGD|passed|failed|FAILED|Error|error" gpurun_out/backward.log | tail -30
 echo "== smoke" ; timeout -s KILL 300 python __graft_entry__.py smoke 2>&1 | tail -4 | tee gpurun_out/smoke.log
 echo "== bench" ; timeout -s KILL 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; rc=$?; python -c "
 import json;d=json.load(open('gpurun_out/bench.json'));r=d['roofline'];print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, 'e2e',d['e2e']['value'],'tc',r['achieved'],r['frac'],r['share_of_step']);[print(x) for x in r['by_shape']];print(d['cpu_baseline'])"; tail -5 gpurun_out/bench.err
 for stage in "$@"; do
+  if [ "$stage" = "pgd" ]; then
+    echo "== pgd bench"
+    timeout -s KILL 900 python bench.py --workload pgd --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_pgd.json 2> gpurun_out/bench_pgd.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_pgd.json'));print({k:d[k] for k in ('metric','value','ms_per_step','gpu_launches')}, d['e2e'], d['counters'], d['roofline']['achieved'])"; tail -5 gpurun_out/bench_pgd.err
+  fi
   if [ $rc -ne 0 ]; then break; fi
   if [ "$stage" = "breakdown" ]; then
     echo "== per-op breakdown"

@@ -11,7 +11,8 @@ import torch
 import torch.nn.functional as F
 
 from gen_adversarial_b200 import ops as real_ops
-from gen_adversarial_b200._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
+from gen_adversarial_b200._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, \
+    MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
 
 ConvLayer = real_ops.ConvLayer
 gaussian_taps = real_ops.gaussian_taps
@@ -27,6 +28,26 @@ def _act(v, act):
     if act == ACT_RELU:
         return F.relu(v)
     return v
+
+
+def _act_grad(v, act):
+    if act == ACT_SILU:
+        sg = torch.sigmoid(v)
+        return sg * (1 + v * (1 - sg))
+    if act == ACT_ELU:
+        return torch.where(v > 0, torch.ones_like(v), torch.exp(v))
+    if act == ACT_RELU:
+        return (v > 0).to(v.dtype)
+    return torch.ones_like(v)
+
+
+def _mul_factor(m, mode):
+    m = m.float()
+    if mode == MUL_RELU_MASK:
+        return (m > 0).float()
+    if mode == MUL_ELU_FROM_Y:
+        return torch.where(m > 0, torch.ones_like(m), m + 1)
+    return m
 
 
 def _pre(x, L):
@@ -47,7 +68,7 @@ def _nhwc(x, dtype):
     return x.permute(0, 2, 3, 1).contiguous().to(dtype)
 
 
-def conv2d_simt(x, L, out_dtype, add=None, out_hw=None):
+def conv2d_simt(x, L, out_dtype, add=None, out_hw=None, mul=None, mul_mode=0, want_dact=False):
     _launches[0] += 1
     xin = _pre(x.float(), L)
     w = L.w_simt.float().view(L.kh, L.kw, L.cin, L.cout).permute(3, 2, 0, 1)
@@ -60,12 +81,16 @@ def conv2d_simt(x, L, out_dtype, add=None, out_hw=None):
         if out_hw is not None:     # output_padding of a transposed conv: pad bottom/right with zeros
             ho, wo = conv_out_hw(L, h, wd)
             xn = F.pad(xn, (0, out_hw[1] - wo, 0, out_hw[0] - ho))
-    y = F.conv2d(xn, w, L.bias.float() if L.bias is not None else None, stride=L.stride, padding=L.pad)
-    y = _act(y, L.post_act)
-    y = y.permute(0, 2, 3, 1)
+    v = F.conv2d(xn, w, L.bias.float() if L.bias is not None else None, stride=L.stride, padding=L.pad)
+    y = _act(v, L.post_act).permute(0, 2, 3, 1)
     if add is not None:
         y = y + add.float()
-    return y.contiguous().to(out_dtype)
+    if mul is not None:
+        y = y * _mul_factor(mul, mul_mode)
+    y = y.contiguous().to(out_dtype)
+    if want_dact:
+        return y, _act_grad(v, L.post_act).permute(0, 2, 3, 1).contiguous().to(out_dtype)
+    return y
 
 
 def conv2d_tc_supported(x, L, x2=None):
@@ -84,7 +109,7 @@ def conv2d_tc_supported(x, L, x2=None):
     return (h % rows == 0) if h >= rows else (rows % h == 0)
 
 
-def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None):
+def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None, mul_mode=0, dact_out=None):
     _launches[0] += 1
     assert x.dtype == torch.bfloat16
     k1 = L.kh * L.kw * L.cin
@@ -98,22 +123,31 @@ def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None):
         assert w.shape[1] == k1
     if L.bias is not None:
         y = y + L.bias.float().view(1, -1, 1, 1)
+    if dact_out is not None:
+        dact_out.copy_(_act_grad(y, L.post_act).permute(0, 2, 3, 1))
     y = _act(y, L.post_act).permute(0, 2, 3, 1)
     if add is not None:
         y = y + add.float()
+    if mul is not None:
+        y = y * _mul_factor(mul, mul_mode)
     y = y.contiguous()
     return (y.to(torch.bfloat16) if want_bf16 else None), (y if want_f32 else None)
 
 
-def dwconv5x5(x, weight, bias, act, up, out_dtype):
+def dwconv5x5(x, weight, bias, act, up, out_dtype, mul=None, want_dact=False):
     _launches[0] += 1
     xn = _nchw(x)
     if up:
         xn = F.interpolate(xn, scale_factor=2, mode="nearest")
     c = xn.shape[1]
     w = weight.float().view(5, 5, c).permute(2, 0, 1).unsqueeze(1)
-    y = F.conv2d(xn, w, bias.float() if bias is not None else None, padding=2, groups=c)
-    return _nhwc(_act(y, act), out_dtype)
+    v = F.conv2d(xn, w, bias.float() if bias is not None else None, padding=2, groups=c)
+    y = _act(v, act)
+    if mul is not None:
+        y = y * _nchw(mul)
+    if want_dact:
+        return _nhwc(y, out_dtype), _nhwc(_act_grad(v, act), out_dtype)
+    return _nhwc(y, out_dtype)
 
 
 def channel_sum(r):
@@ -206,6 +240,116 @@ def preprocess(x_nchw, noise_nchw, eps, blur, out_dtype, seed=0, sample0=0, norm
     if normalize:
         x = (x - 0.5) * 2.0
     return _nhwc(x, out_dtype), pre
+
+
+# ------------------------------------------------------------------------------------------------ backward ops
+def affine_act_bwd(g, x, scale, shift, act, out_dtype, add=None):
+    _launches[0] += 1
+    v = x.float()
+    sc = 1.0
+    if scale is not None:
+        v = v * scale + shift
+        sc = scale
+    out = g.float() * _act_grad(v, act) * sc
+    if add is not None:
+        out = out + add.float()
+    return out.to(out_dtype)
+
+
+def add(a, b, out_dtype):
+    _launches[0] += 1
+    return (a.float() + b.float()).to(out_dtype)
+
+
+def se_residual_bwd(g_out, r, sums, se, res_scale, out_dtype):
+    _launches[0] += 2
+    w1, b1, w2, b2 = se
+    rr = r.float().detach().requires_grad_(True)
+    with torch.enable_grad():
+        gate = torch.sigmoid(F.linear(F.relu(F.linear(rr.mean(dim=(1, 2)), w1, b1)), w2, b2))
+        out = res_scale * gate[:, None, None, :] * rr
+        g_r, = torch.autograd.grad(out, [rr], g_out.float())
+    return g_r.to(out_dtype)
+
+
+def sumpool2x2(x, out_dtype, mul=None):
+    _launches[0] += 1
+    y = F.avg_pool2d(_nchw(x), 2) * 4.0
+    y = y.permute(0, 2, 3, 1)
+    if mul is not None:
+        y = y * mul.float()
+    return y.contiguous().to(out_dtype)
+
+
+def upsample_bilinear2x_bwd(g_out, out_dtype):
+    _launches[0] += 1
+    n, h, w, c = g_out.shape
+    x = torch.zeros((n, c, h // 2, w // 2), requires_grad=True)
+    with torch.enable_grad():
+        y = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        g, = torch.autograd.grad(y, [x], _nchw(g_out))
+    return _nhwc(g, out_dtype)
+
+
+def maxpool2x2_bwd(x_in, g_out, relu, out_dtype):
+    _launches[0] += 1
+    x = _nchw(x_in).detach().requires_grad_(True)
+    with torch.enable_grad():
+        y = F.max_pool2d(F.relu(x) if relu else x, 2)
+        g, = torch.autograd.grad(y, [x], _nchw(g_out))
+    return _nhwc(g, out_dtype)
+
+
+def latent_mix_bwd(g_z, q, p, eps_nchw, seed, level, sample0, alpha_dev, temperature, zdim, zc):
+    _launches[0] += 1
+    a = float(alpha_dev[0])
+    sc = lambda t: 5.0 * torch.tanh(t / 5.0)
+    qq = q.float()[..., :zdim].detach().requires_grad_(True)
+    g = g_z.float()[..., :zdim]
+    with torch.enable_grad():
+        if p is None:
+            z = (1 - a) * sc(qq)
+            g_q, = torch.autograd.grad(z, [qq], g)
+            g_p = None
+        else:
+            pp = p.float().detach().requires_grad_(True)
+            e = eps_nchw.float().permute(0, 2, 3, 1)
+            mu_p, ls_p = pp[..., :zdim], pp[..., zdim:]
+            z = (1 - a) * sc(mu_p + qq) + a * (sc(mu_p) + e * (temperature * torch.exp(sc(ls_p))))
+            g_q, g_p = torch.autograd.grad(z, [qq, pp], g)
+    out = torch.zeros(q.shape[:3] + (zc,), dtype=torch.float32)
+    out[..., :zdim] = g_q
+    return out, g_p
+
+
+def discmix_mean_bwd(logits, n_mix, g_purified_nchw, g_cls):
+    _launches[0] += 1
+    from oracle.nvae_ref import disc_mix_logistic_mean
+    l = _nchw(logits).detach().requires_grad_(True)
+    with torch.enable_grad():
+        v = disc_mix_logistic_mean(l, n_mix)
+        gv = torch.zeros_like(v)
+        if g_purified_nchw is not None:
+            gv = gv + 0.5 * g_purified_nchw
+        if g_cls is not None:
+            gv = gv + _nchw(g_cls)
+        g, = torch.autograd.grad(v, [l], gv)
+    return _nhwc(g, torch.float32)
+
+
+def preprocess_bwd(g_nhwc, pre_nchw, blur, normalize=True, taps_cache=None):
+    _launches[0] += 1
+    from oracle import nvae_ref
+    n, h, w, c = g_nhwc.shape
+    x = torch.zeros((n, c, h, w), requires_grad=True)
+    mask = ((pre_nchw >= 0) & (pre_nchw <= 1)).float()
+    g = _nchw(g_nhwc) * mask * (2.0 if normalize else 1.0)
+    if not blur:
+        return g.contiguous()
+    with torch.enable_grad():
+        y = nvae_ref.gaussian_blur(x)
+        gx, = torch.autograd.grad(y, [x], g)
+    return gx
 
 
 def launch_count(reset=False):

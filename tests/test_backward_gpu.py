@@ -1,0 +1,193 @@
+"""GPU: backward (input-gradient) kernels against torch restatements, the autograd bridge against torch autograd
+through the oracle, and the PGD-Linf loop (BASELINE config 5; parity unpinned -- compared with the oracle's PGD)."""
+import pytest
+import torch
+
+from gen_adversarial_b200 import ops, synth
+from gen_adversarial_b200._lib import ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
+from gen_adversarial_b200.attacks import PGDLinf
+from gen_adversarial_b200.nvae_spec import NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION
+from gen_adversarial_b200.defenses.ours.models import NVAEDefenseModel, CelebaIdentityClassifier
+from oracle import nvae_ref
+from tests import emu_ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_affine_act_bwd_and_add():
+    g = torch.Generator().manual_seed(0)
+    x, gr = torch.randn(2, 8, 8, 16, generator=g), torch.randn(2, 8, 8, 16, generator=g)
+    sc, sh = torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g) * 0.2
+    add = torch.randn(2, 8, 8, 16, generator=g)
+    for act, s, h in ((ACT_SILU, sc, sh), (ACT_ELU, None, None), (ACT_SILU, None, None)):
+        ref = emu_ops.affine_act_bwd(gr, x, s, h, act, torch.float32, add=add)
+        got = ops.affine_act_bwd(gr.to(DEV), x.to(DEV), s.to(DEV) if s is not None else None, h.to(DEV) if h is not None else None,
+                                 act, torch.float32, add=add.to(DEV))
+        assert (got.cpu() - ref).abs().max().item() <= 1e-5
+    assert (ops.add(x.to(DEV), gr.to(DEV).bfloat16(), torch.float32).cpu() - (x + gr.bfloat16().float())).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("c,hw", [(64, 32), (256, 8), (24, 8)])
+def test_se_residual_bwd(c, hw):
+    g = torch.Generator().manual_seed(c)
+    r, go = torch.randn(2, hw, hw, c, generator=g), torch.randn(2, hw, hw, c, generator=g)
+    hid = max(c // 16, 4)
+    se = (torch.randn(hid, c, generator=g) * 0.3, torch.randn(hid, generator=g) * 0.1,
+          torch.randn(c, hid, generator=g) * 0.3, torch.randn(c, generator=g) * 0.1)
+    ref = emu_ops.se_residual_bwd(go, r, None, se, 0.1, torch.float32)
+    sums = ops.channel_sum(r.to(DEV))
+    got = ops.se_residual_bwd(go.to(DEV), r.to(DEV), sums, tuple(t.to(DEV) for t in se), 0.1, torch.float32)
+    assert (got.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_resampling_backward_kernels():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 16, 16, 8, generator=g)
+    m = torch.randn(2, 8, 8, 8, generator=g)
+    assert (ops.sumpool2x2(x.to(DEV), torch.float32, mul=m.to(DEV)).cpu() - emu_ops.sumpool2x2(x, torch.float32, mul=m)).abs().max().item() <= 1e-5
+    assert (ops.upsample_bilinear2x_bwd(x.to(DEV), torch.float32).cpu() - emu_ops.upsample_bilinear2x_bwd(x, torch.float32)).abs().max().item() <= 1e-5
+    xin = torch.randn(2, 16, 16, 8, generator=g)
+    go = torch.randn(2, 8, 8, 8, generator=g)
+    for relu in (False, True):
+        got = ops.maxpool2x2_bwd(xin.to(DEV), go.to(DEV), relu, torch.float32)
+        assert (got.cpu() - emu_ops.maxpool2x2_bwd(xin, go, relu, torch.float32)).abs().max().item() <= 1e-6
+
+
+def test_dwconv_extras_and_conv_epilogue_extras():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 8, 32, generator=g)
+    w, b = torch.randn(25, 32, generator=g) * 0.2, torch.randn(32, generator=g) * 0.1
+    m = torch.randn(2, 8, 8, 32, generator=g)
+    ry, rd = emu_ops.dwconv5x5(x, w, b, ACT_SILU, False, torch.float32, want_dact=True)
+    gy, gd = ops.dwconv5x5(x.to(DEV), w.to(DEV), b.to(DEV), ACT_SILU, False, torch.float32, want_dact=True)
+    assert (gy.cpu() - ry).abs().max().item() <= 1e-5 and (gd.cpu() - rd).abs().max().item() <= 1e-5
+    rm = emu_ops.dwconv5x5(x, w, None, ACT_NONE, False, torch.float32, mul=m)
+    gm = ops.dwconv5x5(x.to(DEV), w.to(DEV), None, ACT_NONE, False, torch.float32, mul=m.to(DEV))
+    assert (gm.cpu() - rm).abs().max().item() <= 1e-5
+    from tests.test_kernels_gpu import _layer, _to_dev
+    L = _layer(64, 64, 3, 1, 1, post_act=ACT_SILU, tc=True)
+    xs = torch.randn(2, 16, 16, 64, generator=g)
+    mm = torch.randn(2, 16, 16, 64, generator=g)
+    ry, rd = emu_ops.conv2d_simt(xs, L, torch.float32, mul=mm, mul_mode=2, want_dact=True)
+    gy, gd = ops.conv2d_simt(xs.to(DEV), _to_dev(L), torch.float32, mul=mm.to(DEV), mul_mode=2, want_dact=True)
+    assert (gy.cpu() - ry).abs().max().item() <= 2e-5 and (gd.cpu() - rd).abs().max().item() <= 2e-5
+    # tensor-core kernel: mul epilogue + dact output
+    xb = xs.bfloat16()
+    dact_ref = torch.empty(2, 16, 16, 64)
+    _, rf = emu_ops.conv2d_tc(xb, L, want_bf16=False, want_f32=True, mul=mm.bfloat16(), mul_mode=1, dact_out=dact_ref)
+    dact = torch.empty(2, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    _, gf = ops.conv2d_tc(xb.to(DEV), _to_dev(L), want_bf16=False, want_f32=True, mul=mm.bfloat16().to(DEV), mul_mode=1, dact_out=dact)
+    assert (gf.cpu() - rf).abs().max().item() <= 2e-3 * max(1.0, rf.abs().max().item())
+    assert (dact.float().cpu() - dact_ref).abs().max().item() <= 2e-2
+
+
+def test_latent_mix_and_discmix_backward():
+    g = torch.Generator().manual_seed(0)
+    n, h, z, zc = 2, 8, 20, 24
+    q, p = torch.randn(n, h, h, z, generator=g) * 2, torch.randn(n, h, h, 2 * z, generator=g) * 2
+    eps, gz = torch.randn(n, z, h, h, generator=g), torch.randn(n, h, h, zc, generator=g)
+    alpha = torch.tensor([0.37])
+    for pp in (None, p):
+        rq, rp = emu_ops.latent_mix_bwd(gz, q, pp, eps, 0, 0, 0, alpha, 0.6, z, zc)
+        gq, gp = ops.latent_mix_bwd(gz.to(DEV), q.to(DEV), pp.to(DEV) if pp is not None else None, eps.to(DEV), 0, 0, 0,
+                                    alpha.to(DEV), 0.6, z, zc)
+        assert (gq.cpu() - rq).abs().max().item() <= 1e-5
+        if pp is not None:
+            assert (gp.cpu() - rp).abs().max().item() <= 1e-5
+    logits = torch.randn(2, 8, 8, 100, generator=g) * 1.5
+    gp_, gc_ = torch.randn(2, 3, 8, 8, generator=g), torch.randn(2, 8, 8, 3, generator=g)
+    ref = emu_ops.discmix_mean_bwd(logits, 10, gp_, gc_)
+    got = ops.discmix_mean_bwd(logits.to(DEV), 10, gp_.to(DEV), gc_.to(DEV))
+    assert (got.cpu() - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("blur,eps", [(True, 1.0), (False, 2.0)])
+def test_preprocess_backward(blur, eps):
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 32, 32, generator=g)
+    noise = torch.randn(2, 3, 32, 32, generator=g)
+    gr = torch.randn(2, 32, 32, 3, generator=g)
+    xr = x.clone().requires_grad_(True)
+    y = (nvae_ref.preprocess(xr, noise, eps, blur) - 0.5) / 0.5
+    ref, = torch.autograd.grad(y, [xr], gr.permute(0, 3, 1, 2))
+    _, pre = ops.preprocess(x.to(DEV), noise.to(DEV), eps, blur, torch.float32, save_pre=True)
+    got = ops.preprocess_bwd(gr.to(DEV), pre, blur)
+    assert (got.cpu() - ref).abs().max().item() <= 1e-5
+
+
+@pytest.fixture(scope="module")
+def c32_models():
+    return synth.make_nvae_checkpoint(seed=0), synth.make_vgg11_checkpoint(100, seed=1)
+
+
+def _oracle_grad(nv, vg, x, y, alphas, noises, eps, blur):
+    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+    vgg = nvae_ref.build_vgg11(vg["state_dict"], 100)
+    xr = x.clone().requires_grad_(True)
+    logits, pur = nvae_ref.defense_call(nv["state_dict_temp=0.6"], spec, vgg, xr, alphas, noises, eps, blur)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    g, = torch.autograd.grad(loss, [xr])
+    return g, logits.detach()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_input_gradient_through_the_api_matches_oracle_autograd(c32_models, mode):
+    """`torch.autograd.grad(loss, [x])` on NVAEDefenseModel + VGG11 (the attack path, untargeted.py:146) and the fused
+    loss_input_grad primitive, against torch autograd through the oracle (C32, cosine alphas, blur + noise)."""
+    nv, vg = c32_models
+    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+    alphas = [0.7 * 0.5 * (1 - __import__("math").cos(__import__("math").pi * i / 24)) for i in range(1, 25)]
+    x, _ = synth.synthetic_batch(2, seed=5)
+    y = torch.tensor([3, 41])
+    noises = synth.synthetic_noise(spec, 2, seed=6)
+    g_ref, logits_ref = _oracle_grad(nv, vg, x, y, alphas, noises, 2.0, True)
+    clf = CelebaIdentityClassifier(vg, DEV, mode=mode)
+    dm = NVAEDefenseModel(clf, nv, [a / 0.7 for a in alphas], 0.7, 2.0, True, DEV, mode=mode).eval()
+    dm.set_explicit_noise(noises)
+    xd = x.to(DEV).requires_grad_(True)
+    logits = dm(xd)
+    loss = torch.nn.functional.cross_entropy(logits, y.to(DEV))
+    g1, = torch.autograd.grad(loss, [xd], retain_graph=True)
+    g1b, = torch.autograd.grad(2 * loss, [xd])                       # repeated backward through the same node
+    _, g2, _ = dm.loss_input_grad(x.to(DEV), y.to(DEV))
+    for name, g in (("autograd", g1), ("fused", g2)):
+        g = g.cpu()
+        rel_l2 = ((g - g_ref).norm() / g_ref.norm()).item()
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
+        sign = (torch.sign(g) == torch.sign(g_ref)).float().mean().item()
+        print(f"[{mode}] {name}: grad rel-L2 err {rel_l2:.3e}, cosine {cos:.6f}, sign agreement {sign:.4f}, |g_ref|max {g_ref.abs().max():.3e}")
+        if mode == "fp32":
+            assert rel_l2 <= 1e-2 and cos >= 0.9999
+        else:
+            assert cos >= 0.98
+    assert torch.allclose(g1b, 2 * g1, rtol=1e-3, atol=1e-9)
+    assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_pgd_linf_matches_oracle_pgd(c32_models, mode):
+    """config 5 at test size: 3 PGD steps, eps 8/255, step 2/255, fixed explicit noise per step."""
+    nv, vg = c32_models
+    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+    import math
+    alphas = [0.7 * 0.5 * (1 - math.cos(math.pi * i / 24)) for i in range(1, 25)]
+    x, _ = synth.synthetic_batch(2, seed=8)
+    vgg = nvae_ref.build_vgg11(vg["state_dict"], 100)
+    steps = 3
+    sched = [synth.synthetic_noise(spec, 2, seed=100 + i) for i in range(steps + 1)]
+    with torch.no_grad():
+        y = nvae_ref.defense_call(nv["state_dict_temp=0.6"], spec, vgg, x, alphas, sched[0], 2.0, False)[0].argmax(1)
+
+    def logits_fn(xa, i):
+        return nvae_ref.defense_call(nv["state_dict_temp=0.6"], spec, vgg, xa, alphas, sched[i], 2.0, False)[0]
+
+    adv_ref = nvae_ref.pgd_linf_attack(logits_fn, x, y, 8 / 255, 2 / 255, steps)
+    clf = CelebaIdentityClassifier(vg, DEV, mode=mode)
+    dm = NVAEDefenseModel(clf, nv, [a / 0.7 for a in alphas], 0.7, 2.0, False, DEV, mode=mode).eval()
+    succ, linf, adv = PGDLinf(8 / 255, 2 / 255, steps)(x.to(DEV), y.to(DEV), dm, noise_schedule=sched)
+    same = ((adv.cpu() - adv_ref).abs() <= 1e-6).float().mean().item()
+    print(f"[{mode}] PGD: {100 * same:.2f}% of adversarial pixels identical to the oracle's; linf {linf.tolist()}")
+    assert linf.max().item() <= 8 / 255 + 1e-6
+    assert adv.min().item() >= 0 and adv.max().item() <= 1
+    assert same >= (0.97 if mode == "fp32" else 0.80)
