@@ -259,9 +259,9 @@ def upsample_bilinear2x(x, out_dtype=None):
 
 
 @_timed("maxpool2x2")
-def maxpool2x2(x):
+def maxpool2x2(x, out_dtype=None):
     n, h, w, c = x.shape
-    out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=x.dtype)
+    out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=out_dtype or x.dtype)
     _lib.check(_lib.lib().ga_maxpool2x2(gt(x), gt(out), stream()), "maxpool2x2")
     return out
 

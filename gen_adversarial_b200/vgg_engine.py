@@ -104,14 +104,17 @@ class Vgg11Engine:
         x = x_nhwc
         if tape is not None and not self._has_dgrad:
             self._build_dgrad()
-        for kind, L in self.layers:
+        for i, (kind, L) in enumerate(self.layers):
             if kind == "pool":
-                y = ops.maxpool2x2(x)
+                y = ops.maxpool2x2(x, self.adt)
                 if tape is not None:
                     tape.append(("vgg_pool", x))
                 x = y
             else:
-                x = self._conv(x, L)
+                # convs feeding a max-pool write fp32: the arg-max (and the gradient routing of the backward pass) is then
+                # decided on fp32 values -- bf16 feature maps tie in ~10% of the 2x2 windows and misroute the gradient
+                before_pool = i + 1 < len(self.layers) and self.layers[i + 1][0] == "pool"
+                x = self._conv(x, L, out_f32=before_pool)
                 if tape is not None:
                     tape.append(("vgg_conv", L, x))
         n = x.shape[0]

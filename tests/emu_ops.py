@@ -203,9 +203,9 @@ def upsample_bilinear2x(x, out_dtype=None):
     return _nhwc(F.interpolate(_nchw(x), scale_factor=2, mode="bilinear", align_corners=True), out_dtype or x.dtype)
 
 
-def maxpool2x2(x):
+def maxpool2x2(x, out_dtype=None):
     _launches[0] += 1
-    return _nhwc(F.max_pool2d(_nchw(x), 2), x.dtype)
+    return _nhwc(F.max_pool2d(_nchw(x), 2), out_dtype or x.dtype)
 
 
 def affine_act(x, scale, shift, act, out_dtype):

@@ -162,7 +162,7 @@ def test_input_gradient_through_the_api_matches_oracle_autograd(c32_models, mode
         else:
             assert cos >= 0.98
     assert torch.allclose(g1b, 2 * g1, rtol=1e-3, atol=1e-9)
-    assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-9)
+    assert ((g1 - g2).norm() / g2.norm()).item() <= 1e-4
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
