@@ -46,10 +46,12 @@ template <> __device__ __forceinline__ uint4 mul_vec<__nv_bfloat16>(uint4 a, uin
   return r;
 }
 
-template <typename TIn, typename TOut, int TW>
+// ACT (compile time): GA_ACT_NONE or GA_ACT_SILU.  EXTRAS: the backward / taping variant (mul, dact pointers live).
+template <typename TIn, typename TOut, int TW, int ACT, bool EXTRAS>
 __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_kernel(
-    const TIn* __restrict__ in, const TOut* __restrict__ mul, const float* __restrict__ w, const float* __restrict__ bias, int act,
+    const TIn* __restrict__ in, const TOut* __restrict__ mul, const float* __restrict__ w, const float* __restrict__ bias,
     int up, int H, int W, int C, int tiles_x, TOut* __restrict__ out, TOut* __restrict__ dact) {
+  constexpr int act = ACT;
   constexpr int CH = DwTraits<TIn>::CH, VEC = DwTraits<TIn>::VEC;
   constexpr int NT = TW * CH / 2;
   constexpr int SH = DW_TH + 4, SW = TW + 4;
@@ -114,38 +116,51 @@ __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_ke
     const int oy = oy0 + r;
     if (oy >= H) break;
     const int64_t o = (((int64_t)n * H + oy) * W + ox) * C + c0;
-    if (dact != nullptr) stg2<TOut>(dact + o, act_grad(acc[r].x, act), act_grad(acc[r].y, act));
-    if (mul != nullptr) {                          // backward: result times the saved derivative of the producer's activation
-      const float2 m = lds2<TOut>(mul + o);
-      stg2<TOut>(out + o, apply_act(acc[r].x, act) * m.x, apply_act(acc[r].y, act) * m.y);
-      continue;
+    if (EXTRAS) {
+      if (dact != nullptr) stg2<TOut>(dact + o, act_grad(acc[r].x, act), act_grad(acc[r].y, act));
+      if (mul != nullptr) {                        // backward: result times the saved derivative of the producer's activation
+        const float2 m = lds2<TOut>(mul + o);
+        stg2<TOut>(out + o, apply_act(acc[r].x, act) * m.x, apply_act(acc[r].y, act) * m.y);
+        continue;
+      }
     }
     if (sizeof(TOut) == 2)   // bf16 output: fast-math activation (error far below bf16 rounding)
-      stg2<TOut>(out + (((int64_t)n * H + oy) * W + ox) * C + c0, apply_act_fast(acc[r].x, act), apply_act_fast(acc[r].y, act));
+      stg2<TOut>(out + o, apply_act_fast(acc[r].x, act), apply_act_fast(acc[r].y, act));
     else
-      stg2<TOut>(out + (((int64_t)n * H + oy) * W + ox) * C + c0, apply_act(acc[r].x, act), apply_act(acc[r].y, act));
+      stg2<TOut>(out + o, apply_act(acc[r].x, act), apply_act(acc[r].y, act));
   }
 }
 
-template <typename TIn, typename TOut>
-static int launch_dw(const ga_tensor* in, const void* mul, const float* weight, const float* bias, int act, int up,
-                     const ga_tensor* out, void* dact, cudaStream_t s) {
+template <typename TIn, typename TOut, int ACT, bool EXTRAS>
+static int launch_dw2(const ga_tensor* in, const void* mul, const float* weight, const float* bias, int up, const ga_tensor* out,
+                      void* dact, cudaStream_t s) {
   constexpr int CH = DwTraits<TIn>::CH;
   const int H = out->h, W = out->w, C = out->c;
   const int cblocks = cdiv(C, CH);
   if (W >= 16) {
     const int tiles_x = cdiv(W, 16);
     dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
-    dwconv5x5_tiled_kernel<TIn, TOut, 16><<<grid, 16 * CH / 2, 0, s>>>((const TIn*)in->data, (const TOut*)mul, weight, bias, act, up,
-                                                                        H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
+    dwconv5x5_tiled_kernel<TIn, TOut, 16, ACT, EXTRAS><<<grid, 16 * CH / 2, 0, s>>>(
+        (const TIn*)in->data, (const TOut*)mul, weight, bias, up, H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
   } else {
     const int tiles_x = cdiv(W, 8);
     dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
-    dwconv5x5_tiled_kernel<TIn, TOut, 8><<<grid, 8 * CH / 2, 0, s>>>((const TIn*)in->data, (const TOut*)mul, weight, bias, act, up,
-                                                                      H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
+    dwconv5x5_tiled_kernel<TIn, TOut, 8, ACT, EXTRAS><<<grid, 8 * CH / 2, 0, s>>>(
+        (const TIn*)in->data, (const TOut*)mul, weight, bias, up, H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
   }
   GA_LAUNCH_OK();
   return 0;
+}
+
+template <typename TIn, typename TOut>
+static int launch_dw(const ga_tensor* in, const void* mul, const float* weight, const float* bias, int act, int up,
+                     const ga_tensor* out, void* dact, cudaStream_t s) {
+  const bool extras = mul != nullptr || dact != nullptr;
+  if (act == GA_ACT_SILU)
+    return extras ? launch_dw2<TIn, TOut, GA_ACT_SILU, true>(in, mul, weight, bias, up, out, dact, s)
+                  : launch_dw2<TIn, TOut, GA_ACT_SILU, false>(in, mul, weight, bias, up, out, dact, s);
+  return extras ? launch_dw2<TIn, TOut, GA_ACT_NONE, true>(in, mul, weight, bias, up, out, dact, s)
+                : launch_dw2<TIn, TOut, GA_ACT_NONE, false>(in, mul, weight, bias, up, out, dact, s);
 }
 
 }  // namespace ga
@@ -159,16 +174,16 @@ static int dw_dispatch(const ga_tensor* in, const ga_tensor* mul, const float* w
   GA_CHECK(in->c % (in->dtype == GA_BF16 ? 8 : 4) == 0, "%s: channels must be a multiple of 8 (bf16) / 4 (fp32)", who);
   GA_CHECK(up ? (out->h == 2 * in->h && out->w == 2 * in->w) : (out->h == in->h && out->w == in->w), "%s: shape mismatch", who);
   GA_CHECK(out->n <= 65535, "%s: batch too large for grid.z", who);
+  GA_CHECK(act == GA_ACT_NONE || act == GA_ACT_SILU, "%s: activation must be none or SiLU", who);
+  GA_CHECK(in->dtype == out->dtype, "%s: input and output dtypes must match", who);
   GA_CHECK(!mul || (same_shape(mul, out) && mul->dtype == out->dtype), "%s: mul must match the output's shape and dtype", who);
   GA_CHECK(!dact || (same_shape(dact, out) && dact->dtype == out->dtype), "%s: dact must match the output's shape and dtype", who);
   if (numel(out) == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const void* m = mul ? mul->data : nullptr;
   void* da = dact ? dact->data : nullptr;
-  if (in->dtype == GA_F32 && out->dtype == GA_F32) return launch_dw<float, float>(in, m, weight, bias, act, up, out, da, s);
-  if (in->dtype == GA_BF16 && out->dtype == GA_BF16) return launch_dw<__nv_bfloat16, __nv_bfloat16>(in, m, weight, bias, act, up, out, da, s);
-  if (in->dtype == GA_BF16 && out->dtype == GA_F32) return launch_dw<__nv_bfloat16, float>(in, m, weight, bias, act, up, out, da, s);
-  return launch_dw<float, __nv_bfloat16>(in, m, weight, bias, act, up, out, da, s);
+  if (in->dtype == GA_F32) return launch_dw<float, float>(in, m, weight, bias, act, up, out, da, s);
+  return launch_dw<__nv_bfloat16, __nv_bfloat16>(in, m, weight, bias, act, up, out, da, s);
 }
 
 extern "C" int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias, int act, int up,

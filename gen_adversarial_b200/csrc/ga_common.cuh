@@ -58,10 +58,21 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     default: return v;
   }
 }
-// fast-math variant for bf16 outputs (ex2.approx + rcp.approx; error << bf16 rounding)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// SiLU with ONE transcendental (MUFU.TANH): v * sigmoid(v) = v * (0.5 * tanh(v/2) + 0.5); abs error ~5e-4 * |v|, far
+// below bf16 rounding (4e-3 * |v|) -- used only where the result is rounded to bf16
+__device__ __forceinline__ float silu_fast(float v) {
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_approx(h), h);
+}
+// fast-math variant for bf16 outputs
 __device__ __forceinline__ float apply_act_fast(float v, int act) {
   switch (act) {
-    case GA_ACT_SILU: return __fdividef(v, 1.0f + __expf(-v));
+    case GA_ACT_SILU: return silu_fast(v);
     case GA_ACT_ELU: return v > 0.0f ? v : __expf(v) - 1.0f;
     case GA_ACT_RELU: return fmaxf(v, 0.0f);
     default: return v;
