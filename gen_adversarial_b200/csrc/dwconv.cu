@@ -3,10 +3,12 @@
 //
 // HBM/FMA balanced op (25 MAC per output element): a CTA stages an (8+4) x (TW+4) pixel halo tile of CH channels
 // in shared memory once (16-byte vector loads, zero fill = the conv's zero padding), then every thread produces an
-// 8-row column strip for TWO adjacent channels (32 channels per CTA, 256 threads, 3 CTAs/SM) with a sliding window: 12 x 5 shared loads feed 8 x 25 x 2 FMAs
-// (6.7 FMA per LDS.32), weights live in registers.  Lanes run along channels, so shared reads are conflict-free
-// and global stores are fully coalesced (128 B per warp).  `up` reads the input through the nearest x2
-// up-sampling of the up cells (architecture.py:162) without materialising it.
+// 8-row x 2-column strip for TWO adjacent channels with a sliding window: 12 x 6 shared loads (bf16x2 words) feed
+// 8 x 2 x 25 x 2 FMAs (11 FMA per LDS.32 and per bf16->fp32 unpack: the half-rate ALU pipe was the limiter of the
+// 1-column version, ncu: ALU 60% / FMA 28%), weights live in registers.  Lanes run along channels (64 bf16
+// channels per CTA = one warp wide), so shared reads are conflict-free and global accesses are 128-byte segments.
+// `up` reads the input through the nearest x2 up-sampling of the up cells (architecture.py:162) without
+// materialising it.
 #include "ga_common.cuh"
 
 namespace ga {
@@ -14,7 +16,7 @@ namespace ga {
 constexpr int DW_TH = 8;
 
 template <typename T> struct DwTraits;
-template <> struct DwTraits<__nv_bfloat16> { static constexpr int CH = 32; static constexpr int VEC = 8; };
+template <> struct DwTraits<__nv_bfloat16> { static constexpr int CH = 64; static constexpr int VEC = 8; };
 template <> struct DwTraits<float> { static constexpr int CH = 32; static constexpr int VEC = 4; };
 
 template <typename T> __device__ __forceinline__ float2 lds2(const T* p);
@@ -48,12 +50,12 @@ template <> __device__ __forceinline__ uint4 mul_vec<__nv_bfloat16>(uint4 a, uin
 
 // ACT (compile time): GA_ACT_NONE or GA_ACT_SILU.  EXTRAS: the backward / taping variant (mul, dact pointers live).
 template <typename TIn, typename TOut, int TW, int ACT, bool EXTRAS>
-__global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_kernel(
+__global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 4) dwconv5x5_tiled_kernel(
     const TIn* __restrict__ in, const TOut* __restrict__ mul, const float* __restrict__ w, const float* __restrict__ bias,
     int up, int H, int W, int C, int tiles_x, TOut* __restrict__ out, TOut* __restrict__ dact) {
   constexpr int act = ACT;
   constexpr int CH = DwTraits<TIn>::CH, VEC = DwTraits<TIn>::VEC;
-  constexpr int NT = TW * CH / 2;
+  constexpr int NT = TW * CH / 4;      // (TW/2 column pairs) x (CH/2 channel pairs)
   constexpr int SH = DW_TH + 4, SW = TW + 4;
   __shared__ __align__(16) TIn s_in[SH][SW][CH];
 
@@ -81,53 +83,61 @@ __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 2) dwconv5x5_tiled_ke
   }
   // ---- per-thread weights (2 channels x 25 taps) and bias
   const int cp = tid % (CH / 2);
-  const int tx = tid / (CH / 2);
+  const int txp = tid / (CH / 2);               // column pair
   const int c0 = c_blk + 2 * cp;
   const bool c_ok = c0 < C;
   float2 wr[25];
 #pragma unroll
   for (int t = 0; t < 25; ++t) wr[t] = c_ok ? __ldg(reinterpret_cast<const float2*>(w + t * C + c0)) : make_float2(0.f, 0.f);
   float2 b2 = (c_ok && bias != nullptr) ? __ldg(reinterpret_cast<const float2*>(bias + c0)) : make_float2(0.f, 0.f);
-  float2 acc[DW_TH];
+  float2 acc[DW_TH][2];
 #pragma unroll
-  for (int r = 0; r < DW_TH; ++r) acc[r] = b2;
+  for (int r = 0; r < DW_TH; ++r) { acc[r][0] = b2; acc[r][1] = b2; }
   __syncthreads();
 
 #pragma unroll
   for (int ir = 0; ir < SH; ++ir) {
-    float2 v[5];
+    float2 v[6];
 #pragma unroll
-    for (int dx = 0; dx < 5; ++dx) v[dx] = lds2<TIn>(&s_in[ir][tx + dx][2 * cp]);
+    for (int dx = 0; dx < 6; ++dx) v[dx] = lds2<TIn>(&s_in[ir][2 * txp + dx][2 * cp]);
 #pragma unroll
     for (int r = 0; r < DW_TH; ++r) {
       const int dy = ir - r;
       if (dy < 0 || dy > 4) continue;
 #pragma unroll
       for (int dx = 0; dx < 5; ++dx) {
-        acc[r].x = fmaf(v[dx].x, wr[dy * 5 + dx].x, acc[r].x);
-        acc[r].y = fmaf(v[dx].y, wr[dy * 5 + dx].y, acc[r].y);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          acc[r][j].x = fmaf(v[dx + j].x, wr[dy * 5 + dx].x, acc[r][j].x);
+          acc[r][j].y = fmaf(v[dx + j].y, wr[dy * 5 + dx].y, acc[r][j].y);
+        }
       }
     }
   }
-  const int ox = ox0 + tx;
-  if (!c_ok || ox >= W) return;
+  if (!c_ok) return;
 #pragma unroll
-  for (int r = 0; r < DW_TH; ++r) {
-    const int oy = oy0 + r;
-    if (oy >= H) break;
-    const int64_t o = (((int64_t)n * H + oy) * W + ox) * C + c0;
-    if (EXTRAS) {
-      if (dact != nullptr) stg2<TOut>(dact + o, act_grad(acc[r].x, act), act_grad(acc[r].y, act));
-      if (mul != nullptr) {                        // backward: result times the saved derivative of the producer's activation
-        const float2 m = lds2<TOut>(mul + o);
-        stg2<TOut>(out + o, apply_act(acc[r].x, act) * m.x, apply_act(acc[r].y, act) * m.y);
-        continue;
+  for (int j = 0; j < 2; ++j) {
+    const int ox = ox0 + 2 * txp + j;
+    if (ox >= W) continue;
+#pragma unroll
+    for (int r = 0; r < DW_TH; ++r) {
+      const int oy = oy0 + r;
+      if (oy >= H) break;
+      const int64_t o = (((int64_t)n * H + oy) * W + ox) * C + c0;
+      const float ax = acc[r][j].x, ay = acc[r][j].y;
+      if (EXTRAS) {
+        if (dact != nullptr) stg2<TOut>(dact + o, act_grad(ax, act), act_grad(ay, act));
+        if (mul != nullptr) {                      // backward: result times the saved derivative of the producer's activation
+          const float2 m = lds2<TOut>(mul + o);
+          stg2<TOut>(out + o, apply_act(ax, act) * m.x, apply_act(ay, act) * m.y);
+          continue;
+        }
       }
+      if (sizeof(TOut) == 2)   // bf16 output: fast-math activation (error far below bf16 rounding)
+        stg2<TOut>(out + o, apply_act_fast(ax, act), apply_act_fast(ay, act));
+      else
+        stg2<TOut>(out + o, apply_act(ax, act), apply_act(ay, act));
     }
-    if (sizeof(TOut) == 2)   // bf16 output: fast-math activation (error far below bf16 rounding)
-      stg2<TOut>(out + o, apply_act_fast(acc[r].x, act), apply_act_fast(acc[r].y, act));
-    else
-      stg2<TOut>(out + o, apply_act(acc[r].x, act), apply_act(acc[r].y, act));
   }
 }
 
@@ -140,12 +150,12 @@ static int launch_dw2(const ga_tensor* in, const void* mul, const float* weight,
   if (W >= 16) {
     const int tiles_x = cdiv(W, 16);
     dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
-    dwconv5x5_tiled_kernel<TIn, TOut, 16, ACT, EXTRAS><<<grid, 16 * CH / 2, 0, s>>>(
+    dwconv5x5_tiled_kernel<TIn, TOut, 16, ACT, EXTRAS><<<grid, 16 * CH / 4, 0, s>>>(
         (const TIn*)in->data, (const TOut*)mul, weight, bias, up, H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
   } else {
     const int tiles_x = cdiv(W, 8);
     dim3 grid(tiles_x * cdiv(H, DW_TH), cblocks, out->n);
-    dwconv5x5_tiled_kernel<TIn, TOut, 8, ACT, EXTRAS><<<grid, 8 * CH / 2, 0, s>>>(
+    dwconv5x5_tiled_kernel<TIn, TOut, 8, ACT, EXTRAS><<<grid, 8 * CH / 4, 0, s>>>(
         (const TIn*)in->data, (const TOut*)mul, weight, bias, up, H, W, C, tiles_x, (TOut*)out->data, (TOut*)dact);
   }
   GA_LAUNCH_OK();

@@ -327,37 +327,35 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
 }
 
 // ============================================================================ latent mix
-__global__ void __launch_bounds__(256) latent_mix_kernel(const void* __restrict__ q, int q_dtype, int Cq,
+// one thread per pixel: q / p / z rows are contiguous per pixel (vector-friendly, every byte of a line is used), the
+// NCHW eps reads are coalesced across the warp (adjacent threads = adjacent pixels)
+__global__ void __launch_bounds__(128) latent_mix_kernel(const void* __restrict__ q, int q_dtype, int Cq,
                                                          const void* __restrict__ pp, int p_dtype, const float* __restrict__ eps,
                                                          uint64_t seed, int level, int64_t sample0,
-                                                         const float* __restrict__ alpha_dev, float temp, int Z, int N, int H,
-                                                         int W, void* __restrict__ zout, int z_dtype, int Cz) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)N * H * W * Cz;
-  if (idx >= total) return;
-  const int zc = (int)(idx % Cz);
-  const int64_t pix = idx / Cz;
-  if (zc >= Z) { st1d(zout, z_dtype, idx, 0.f); return; }   // zero padding channels (tensor-core K padding)
-  const int x = (int)(pix % W);
-  const int y = (int)((pix / W) % H);
-  const int64_t n = pix / ((int64_t)W * H);
+                                                         const float* __restrict__ alpha_dev, float temp, int Z, int64_t total_pix,
+                                                         int HW, void* __restrict__ zout, int z_dtype, int Cz) {
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total_pix) return;
+  const int64_t n = pix / HW;
+  const int hw = (int)(pix % HW);
   const float a = *alpha_dev;
-  const float mu_q = ld1d(q, q_dtype, pix * Cq + zc);
-  const int64_t e_idx = (((int64_t)zc) * H + y) * W + x;      // element index inside the sample (NCHW order)
-  float e;
-  if (eps != nullptr) e = eps[n * Z * H * W + e_idx];
-  else e = philox_normal(seed, noise_stream(sample0 + n, level + 1), (uint64_t)e_idx);
-  float out;
-  if (pp == nullptr) {
-    out = (1.f - a) * softclamp5_(mu_q) + a * (e * temp);
-  } else {
-    const float mu_p = ld1d(pp, p_dtype, pix * (2 * Z) + zc);
-    const float ls_p = ld1d(pp, p_dtype, pix * (2 * Z) + Z + zc);
-    const float enc = softclamp5_(mu_p + mu_q);
-    const float dec = softclamp5_(mu_p) + e * (temp * expf(softclamp5_(ls_p)));
-    out = (1.f - a) * enc + a * dec;
+  const float* e_base = eps != nullptr ? eps + n * Z * HW + hw : nullptr;
+  const uint64_t stream = noise_stream(sample0 + n, level + 1);
+  for (int zc = 0; zc < Cz; ++zc) {
+    float out = 0.f;                               // channels >= Z: zero padding (tensor-core K padding)
+    if (zc < Z) {
+      const float mu_q = ld1d(q, q_dtype, pix * Cq + zc);
+      const float e = e_base != nullptr ? __ldg(e_base + (int64_t)zc * HW) : philox_normal(seed, stream, (uint64_t)zc * HW + hw);
+      if (pp == nullptr) {
+        out = (1.f - a) * softclamp5_(mu_q) + a * (e * temp);
+      } else {
+        const float mu_p = ld1d(pp, p_dtype, pix * (2 * Z) + zc);
+        const float ls_p = ld1d(pp, p_dtype, pix * (2 * Z) + Z + zc);
+        out = (1.f - a) * softclamp5_(mu_p + mu_q) + a * (softclamp5_(mu_p) + e * (temp * expf(softclamp5_(ls_p))));
+      }
+    }
+    st1d(zout, z_dtype, pix * Cz + zc, out);
   }
-  st1d(zout, z_dtype, idx, out);
 }
 
 // ============================================================================ DiscMixLogistic mean
@@ -701,11 +699,11 @@ extern "C" int ga_latent_mix_fwd(const ga_tensor* q, const ga_tensor* p, const f
   GA_CHECK(q->c >= zdim && z->c >= zdim, "ga_latent_mix_fwd: channel counts smaller than zdim");
   GA_CHECK(q->n == z->n && q->h == z->h && q->w == z->w, "ga_latent_mix_fwd: shape mismatch");
   GA_CHECK(!p || (p->c == 2 * zdim && p->n == q->n && p->h == q->h && p->w == q->w), "ga_latent_mix_fwd: prior tensor must have 2*zdim channels");
-  const int64_t total = numel(z);
-  if (total == 0) return 0;
-  latent_mix_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  const int64_t total_pix = (int64_t)z->n * z->h * z->w;
+  if (total_pix == 0) return 0;
+  latent_mix_kernel<<<cdiv(total_pix, 128), 128, 0, (cudaStream_t)stream>>>(
       q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, seed, level, sample0, alpha_dev,
-      temperature, zdim, z->n, z->h, z->w, z->data, z->dtype, z->c);
+      temperature, zdim, total_pix, z->h * z->w, z->data, z->dtype, z->c);
   GA_LAUNCH_OK();
   return 0;
 }
