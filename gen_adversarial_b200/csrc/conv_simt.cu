@@ -84,82 +84,84 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
   const int Hup = (p.H - 1) * p.up + 1, Wup = (p.W - 1) * p.up + 1;   // zero-inserted extent
   const int cchunks = (p.Cin + BK - 1) / BK;
 
-  for (int ky = 0; ky < p.KH; ++ky) {
-    for (int kx = 0; kx < p.KW; ++kx) {
-      // input coordinate of this tap for the thread's row
-      int iy = a_oy * p.stride - p.pad + ky;
-      int ix = a_ox * p.stride - p.pad + kx;
-      bool pix_ok = a_valid_m && iy >= 0 && ix >= 0 && iy < Hup && ix < Wup;
-      if (p.up > 1) {
-        pix_ok = pix_ok && (iy % p.up == 0) && (ix % p.up == 0);
-        iy /= p.up; ix /= p.up;
-      }
-      const TIn* src = in + (((int64_t)a_n * p.H + iy) * p.W + ix) * p.Cin;
-      const int tap = ky * p.KW + kx;
-      for (int cc = 0; cc < cchunks; ++cc) {
-        const int c0 = cc * BK;
-        // ---------------- load A (8 values) into registers
-        float av[8];
-        const int ca = c0 + a_k0;
-        if (pix_ok && cin_vec && ca + 8 <= p.Cin) {
-          float t4[4];
-          ld4<TIn>(src + ca, t4);
-          av[0] = t4[0]; av[1] = t4[1]; av[2] = t4[2]; av[3] = t4[3];
-          ld4<TIn>(src + ca + 4, t4);
-          av[4] = t4[0]; av[5] = t4[1]; av[6] = t4[2]; av[7] = t4[3];
-          if (p.pre_op != GA_PRE_NONE) {
+  // K loop flattened to (tap, channel chunk) steps with a register prefetch of the next step: the global loads of step
+  // i+1 are in flight while step i is multiplied out of shared memory (the un-pipelined loop exposed one DRAM/L2 round
+  // trip per step)
+  const int steps = p.KH * p.KW * cchunks;
+  float av[8], bv[4];
+  auto load_step = [&](int step) {
+    const int tap = step / cchunks, cc = step - tap * cchunks;
+    const int ky = tap / p.KW, kx = tap - ky * p.KW;
+    int iy = a_oy * p.stride - p.pad + ky;
+    int ix = a_ox * p.stride - p.pad + kx;
+    bool pix_ok = a_valid_m && iy >= 0 && ix >= 0 && iy < Hup && ix < Wup;
+    if (p.up > 1) {
+      pix_ok = pix_ok && (iy % p.up == 0) && (ix % p.up == 0);
+      iy /= p.up; ix /= p.up;
+    }
+    const TIn* src = in + (((int64_t)a_n * p.H + iy) * p.W + ix) * p.Cin;
+    const int c0 = cc * BK;
+    const int ca = c0 + a_k0;
+    if (pix_ok && cin_vec && ca + 8 <= p.Cin) {
+      float t4[4];
+      ld4<TIn>(src + ca, t4);
+      av[0] = t4[0]; av[1] = t4[1]; av[2] = t4[2]; av[3] = t4[3];
+      ld4<TIn>(src + ca + 4, t4);
+      av[4] = t4[0]; av[5] = t4[1]; av[6] = t4[2]; av[7] = t4[3];
+      if (p.pre_op != GA_PRE_NONE) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float sc = 1.f, sh = 0.f;
-              if (p.pre_op == GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
-              av[j] = pre_apply(av[j], p.pre_op, sc, sh);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v = 0.0f;
-            if (pix_ok && ca + j < p.Cin) {
-              v = load_in<TIn>(src + ca + j);
-              float sc = 1.f, sh = 0.f;
-              if (p.pre_op == GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
-              v = pre_apply(v, p.pre_op, sc, sh);
-            }
-            av[j] = v;
-          }
-        }
-        // ---------------- load B (4 values)
-        float bv[4] = {0.f, 0.f, 0.f, 0.f};
-        const int cb = c0 + b_k;
-        if (cb < p.Cin) {
-          const float* wrow = p.w + ((int64_t)tap * p.Cin + cb) * p.Cout + n0 + b_n;
-          if (cout_vec && n0 + b_n + 4 <= p.Cout) {
-            float4 t = *reinterpret_cast<const float4*>(wrow);
-            bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n0 + b_n + j < p.Cout) bv[j] = wrow[j];
-          }
-        }
-        __syncthreads();   // previous tile fully consumed
-#pragma unroll
-        for (int j = 0; j < 8; ++j) As[a_k0 + j][a_row] = av[j];
-        *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-          float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
-          float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-          float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-          float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) {
+          float sc = 1.f, sh = 0.f;
+          if (p.pre_op == GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
+          av[j] = pre_apply(av[j], p.pre_op, sc, sh);
         }
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = 0.0f;
+        if (pix_ok && ca + j < p.Cin) {
+          v = load_in<TIn>(src + ca + j);
+          float sc = 1.f, sh = 0.f;
+          if (p.pre_op == GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
+          v = pre_apply(v, p.pre_op, sc, sh);
+        }
+        av[j] = v;
+      }
+    }
+    bv[0] = bv[1] = bv[2] = bv[3] = 0.f;
+    const int cb = c0 + b_k;
+    if (cb < p.Cin) {
+      const float* wrow = p.w + ((int64_t)tap * p.Cin + cb) * p.Cout + n0 + b_n;
+      if (cout_vec && n0 + b_n + 4 <= p.Cout) {
+        float4 t = *reinterpret_cast<const float4*>(wrow);
+        bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + b_n + j < p.Cout) bv[j] = wrow[j];
+      }
+    }
+  };
+  load_step(0);
+  for (int step = 0; step < steps; ++step) {
+    __syncthreads();   // previous tile fully consumed
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[a_k0 + j][a_row] = av[j];
+    *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    __syncthreads();
+    if (step + 1 < steps) load_step(step + 1);      // prefetch: overlaps with the FMAs below
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
   }
 

@@ -65,21 +65,36 @@ __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 4) dwconv5x5_tiled_ke
   const int oy0 = (blockIdx.x / tiles_x) * DW_TH, ox0 = (blockIdx.x % tiles_x) * TW;
   const int Hi = up ? H >> 1 : H, Wi = up ? W >> 1 : W;
 
-  // ---- stage the halo tile (zero outside the image / beyond C)
+  // ---- stage the halo tile (zero outside the image / beyond C).  All of a thread's global loads are issued before the
+  // first shared store (fixed trip count, fully unrolled): with a rolled loop each thread had ONE load in flight and the
+  // CTA spent ~8 us waiting on DRAM latency 7 times in a row.
   constexpr int VPP = CH / VEC;                      // vectors per pixel
-  for (int i = tid; i < SH * SW * VPP; i += NT) {
+  constexpr int TOTAL = SH * SW * VPP;
+  constexpr int ITER = (TOTAL + NT - 1) / NT;
+  uint4 vals[ITER];
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = tid + it * NT;
     const int v = i % VPP;
     const int px = (i / VPP) % SW;
     const int py = i / (VPP * SW);
     const int iy = oy0 + py - 2, ix = ox0 + px - 2;
     const int c = c_blk + v * VEC;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W && c < C) {
+    vals[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < TOTAL && iy >= 0 && iy < H && ix >= 0 && ix < W && c < C) {
       const int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
-      const int64_t off = (((int64_t)n * Hi + sy) * Wi + sx) * C + c;
-      val = __ldg(reinterpret_cast<const uint4*>(in + off));
+      vals[it] = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)n * Hi + sy) * Wi + sx) * C + c));
     }
-    *reinterpret_cast<uint4*>(&s_in[py][px][v * VEC]) = val;
+  }
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = tid + it * NT;
+    if (i < TOTAL) {
+      const int v = i % VPP;
+      const int px = (i / VPP) % SW;
+      const int py = i / (VPP * SW);
+      *reinterpret_cast<uint4*>(&s_in[py][px][v * VEC]) = vals[it];
+    }
   }
   // ---- per-thread weights (2 channels x 25 taps) and bias
   const int cp = tid % (CH / 2);

@@ -307,21 +307,36 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
   const int c4n = p.C >> 2;
   const int64_t base = ((int64_t)n * p.HW + p0) * p.C;
   const int cnt4 = (p1 - p0) * c4n;
-  for (int i = tid; i < cnt4; i += 256) {
-    const int c = (i % c4n) * 4;
-    const int64_t off = base + (int64_t)i * 4;
-    float rv[4], sv[4], o[4];
-    ld4d(p.r, p.r_dtype, off, rv);
-    ld4d(p.skip, p.skip_dtype, off, sv);
+  // 4 independent vector items per thread per trip: all loads are issued before the first store (the output may alias
+  // nothing, but the compiler cannot know; a rolled loop kept ONE load pair in flight per thread)
+  for (int i0 = tid; i0 < cnt4; i0 += 256 * 4) {
+    float rv[4][4], sv[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = fmaf(p.res_scale * s_gate[c + j], rv[j], sv[j]);
-    st4d(p.out, p.out_dtype, off, o);
-    if (p.out2 != nullptr) st4d(p.out2, p.out2_dtype, off, o);
-    if (p.act != nullptr) {
-      float a[4];
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i < cnt4) {
+        const int64_t off = base + (int64_t)i * 4;
+        ld4d(p.r, p.r_dtype, off, rv[u]);
+        ld4d(p.skip, p.skip_dtype, off, sv[u]);
+      }
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a[j] = siluf_(fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]));
-      st4d(p.act, p.act_dtype, off, a);
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i >= cnt4) continue;
+      const int c = (i % c4n) * 4;
+      const int64_t off = base + (int64_t)i * 4;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = fmaf(p.res_scale * s_gate[c + j], rv[u][j], sv[u][j]);
+      st4d(p.out, p.out_dtype, off, o);
+      if (p.out2 != nullptr) st4d(p.out2, p.out2_dtype, off, o);
+      if (p.act != nullptr) {
+        float a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = silu_fast(fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]));
+        st4d(p.act, p.act_dtype, off, a);
+      }
     }
   }
 }
@@ -341,20 +356,32 @@ __global__ void __launch_bounds__(128) latent_mix_kernel(const void* __restrict_
   const float a = *alpha_dev;
   const float* e_base = eps != nullptr ? eps + n * Z * HW + hw : nullptr;
   const uint64_t stream = noise_stream(sample0 + n, level + 1);
-  for (int zc = 0; zc < Cz; ++zc) {
-    float out = 0.f;                               // channels >= Z: zero padding (tensor-core K padding)
-    if (zc < Z) {
-      const float mu_q = ld1d(q, q_dtype, pix * Cq + zc);
-      const float e = e_base != nullptr ? __ldg(e_base + (int64_t)zc * HW) : philox_normal(seed, stream, (uint64_t)zc * HW + hw);
-      if (pp == nullptr) {
-        out = (1.f - a) * softclamp5_(mu_q) + a * (e * temp);
-      } else {
-        const float mu_p = ld1d(pp, p_dtype, pix * (2 * Z) + zc);
-        const float ls_p = ld1d(pp, p_dtype, pix * (2 * Z) + Z + zc);
-        out = (1.f - a) * softclamp5_(mu_p + mu_q) + a * (softclamp5_(mu_p) + e * (temp * expf(softclamp5_(ls_p))));
+  for (int z0 = 0; z0 < Cz; z0 += 4) {             // 4 channels per trip: their loads are issued together
+    float mq[4], mp[4], lp[4], ee[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int zc = z0 + u;
+      mq[u] = mp[u] = lp[u] = ee[u] = 0.f;
+      if (zc < Z) {
+        mq[u] = ld1d(q, q_dtype, pix * Cq + zc);
+        ee[u] = e_base != nullptr ? __ldg(e_base + (int64_t)zc * HW) : philox_normal(seed, stream, (uint64_t)zc * HW + hw);
+        if (pp != nullptr) {
+          mp[u] = ld1d(pp, p_dtype, pix * (2 * Z) + zc);
+          lp[u] = ld1d(pp, p_dtype, pix * (2 * Z) + Z + zc);
+        }
       }
     }
-    st1d(zout, z_dtype, pix * Cz + zc, out);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int zc = z0 + u;
+      if (zc >= Cz) continue;
+      float out = 0.f;                             // channels >= Z: zero padding (tensor-core K padding)
+      if (zc < Z) {
+        if (pp == nullptr) out = (1.f - a) * softclamp5_(mq[u]) + a * (ee[u] * temp);
+        else out = (1.f - a) * softclamp5_(mp[u] + mq[u]) + a * (softclamp5_(mp[u]) + ee[u] * (temp * expf(softclamp5_(lp[u]))));
+      }
+      st1d(zout, z_dtype, pix * Cz + zc, out);
+    }
   }
 }
 
@@ -369,8 +396,19 @@ __global__ void __launch_bounds__(128) discmix_mean_kernel(const void* __restric
   const int64_t pix0 = (int64_t)blockIdx.x * DM_PIX;
   const int npx = (int)min((int64_t)DM_PIX, total_pix - pix0);
   const int cnt = npx * CL;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x)
-    s_l[(i / CL) * pitch + (i % CL)] = ld1d(logits, dtype, pix0 * CL + i);
+  for (int i0 = threadIdx.x; i0 < cnt; i0 += 128 * 8) {          // 8 loads in flight per thread
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 128;
+      t[u] = i < cnt ? ld1d(logits, dtype, pix0 * CL + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 128;
+      if (i < cnt) s_l[(i / CL) * pitch + (i % CL)] = t[u];
+    }
+  }
   __syncthreads();
   const int t = threadIdx.x;
   if (t >= npx) return;
