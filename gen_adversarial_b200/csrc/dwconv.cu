@@ -122,10 +122,7 @@ __global__ void __launch_bounds__(TW * DwTraits<TIn>::CH / 4) dwconv5x5_tiled_ke
 #pragma unroll
       for (int dx = 0; dx < 5; ++dx) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          acc[r][j].x = fmaf(v[dx + j].x, wr[dy * 5 + dx].x, acc[r][j].x);
-          acc[r][j].y = fmaf(v[dx + j].y, wr[dy * 5 + dx].y, acc[r][j].y);
-        }
+        for (int j = 0; j < 2; ++j) acc[r][j] = ffma2(v[dx + j], wr[dy * 5 + dx], acc[r][j]);   // 2 channels per FFMA2
       }
     }
   }

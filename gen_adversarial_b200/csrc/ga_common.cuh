@@ -91,6 +91,15 @@ __device__ __forceinline__ float act_grad(float v, int act) {
   }
 }
 
+// packed fp32 FMA (Blackwell FFMA2): two independent FMAs per issue slot -- d.xy = a.xy * b.xy + c.xy
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+
 __device__ __forceinline__ float mul_factor(float m, int mode) {
   switch (mode) {
     case GA_MUL_RELU_MASK: return m > 0.0f ? 1.0f : 0.0f;
