@@ -36,6 +36,30 @@ __global__ void affine_act_bwd_kernel(const void* g, int g_dtype, const void* x,
   st1b(out, out_dtype, i, v);
 }
 
+__global__ void __launch_bounds__(256) affine_act_bwd_vec4_kernel(const void* g, int g_dtype, const void* x, int x_dtype,
+                                                                  const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                                  const void* add, int add_dtype, void* out, int out_dtype, int C,
+                                                                  int64_t total4) {
+  int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int64_t i = i4 * 4;
+  const int c = (int)(i % C);
+  float gv[4], xv[4], av[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+  if (g_dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(g) + i, gv); else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(g) + i, gv);
+  if (x_dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(x) + i, xv); else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x) + i, xv);
+  if (add != nullptr) {
+    if (add_dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(add) + i, av); else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(add) + i, av);
+  }
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (scale != nullptr) {
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c)), h4 = __ldg(reinterpret_cast<const float4*>(shift + c));
+    sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w; sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = fmaf(gv[j] * act_grad(fmaf(xv[j], sc[j], sh[j]), act), sc[j], av[j]);
+  if (out_dtype == GA_F32) st4<float>(reinterpret_cast<float*>(out) + i, o); else st4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(out) + i, o);
+}
+
 // out = a + b  (gradient accumulation)
 __global__ void add_kernel(const void* a, int a_dtype, const void* b, int b_dtype, void* out, int out_dtype, int64_t total) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,12 +291,13 @@ __global__ void __launch_bounds__(256) latent_mix_bwd_kernel(const void* gz, int
 // ---------------------------------------------------------------------------- DiscMixLogistic mean backward
 __global__ void __launch_bounds__(128) discmix_mean_bwd_kernel(const float* __restrict__ logits, int n_mix, int HW, int64_t total_pix,
                                                                const float* __restrict__ g_pur, const void* g_cls, int gc_dtype,
-                                                               float* __restrict__ g_logits) {
+                                                               float* __restrict__ g_logits, int Cg) {
   const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total_pix) return;
   const int CL = 10 * n_mix;
   const float* l = logits + pix * CL;
-  float* gl = g_logits + pix * CL;
+  float* gl = g_logits + pix * Cg;
+  for (int c = CL; c < Cg; ++c) gl[c] = 0.f;              // channel padding (tensor-core K alignment of the dgrad conv)
   const int64_t n = pix / HW, hw = pix % HW;
   // incoming gradient w.r.t. v = (r, g, b) in [-1, 1]
   float gv[3] = {0.f, 0.f, 0.f};
@@ -348,9 +373,14 @@ extern "C" int ga_affine_act_bwd(const ga_tensor* g, const ga_tensor* x, const f
   GA_CHECK(!add || same_shape(add, out), "ga_affine_act_bwd: add shape mismatch");
   const int64_t total = numel(g);
   if (total == 0) return 0;
-  affine_act_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(g->data, g->dtype, x->data, x->dtype, scale, shift, act,
-                                                                            add ? add->data : nullptr, add ? add->dtype : GA_F32,
-                                                                            out->data, out->dtype, g->c, total);
+  if ((g->c & 3) == 0)
+    affine_act_bwd_vec4_kernel<<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(g->data, g->dtype, x->data, x->dtype, scale, shift, act,
+                                                                                       add ? add->data : nullptr, add ? add->dtype : GA_F32,
+                                                                                       out->data, out->dtype, g->c, total / 4);
+  else
+    affine_act_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(g->data, g->dtype, x->data, x->dtype, scale, shift, act,
+                                                                              add ? add->data : nullptr, add ? add->dtype : GA_F32,
+                                                                              out->data, out->dtype, g->c, total);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -440,15 +470,16 @@ extern "C" int ga_latent_mix_bwd(const ga_tensor* g_z, const ga_tensor* q, const
 
 extern "C" int ga_discmix_mean_bwd(const ga_tensor* logits, int n_mix, const float* g_purified_nchw, const ga_tensor* g_cls,
                                    const ga_tensor* g_logits, void* stream) {
-  GA_CHECK(logits && g_logits && same_shape(logits, g_logits) && logits->dtype == GA_F32 && g_logits->dtype == GA_F32,
-           "ga_discmix_mean_bwd: logits / g_logits must be fp32 tensors of the same shape");
+  GA_CHECK(logits && g_logits && logits->n == g_logits->n && logits->h == g_logits->h && logits->w == g_logits->w &&
+               g_logits->c >= logits->c && logits->dtype == GA_F32 && g_logits->dtype == GA_F32,
+           "ga_discmix_mean_bwd: logits / g_logits must be fp32 tensors of the same spatial shape (g_logits may be channel-padded)");
   GA_CHECK(logits->c == 10 * n_mix, "ga_discmix_mean_bwd: logits must have 10*n_mix channels");
   GA_CHECK(g_purified_nchw || g_cls, "ga_discmix_mean_bwd: no incoming gradient");
   const int64_t total_pix = (int64_t)logits->n * logits->h * logits->w;
   if (total_pix == 0) return 0;
   discmix_mean_bwd_kernel<<<cdiv(total_pix, 128), 128, 0, (cudaStream_t)stream>>>(
       (const float*)logits->data, n_mix, logits->h * logits->w, total_pix, g_purified_nchw, g_cls ? g_cls->data : nullptr,
-      g_cls ? g_cls->dtype : GA_F32, (float*)g_logits->data);
+      g_cls ? g_cls->dtype : GA_F32, (float*)g_logits->data, g_logits->c);
   GA_LAUNCH_OK();
   return 0;
 }

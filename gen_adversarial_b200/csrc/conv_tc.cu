@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap tmA2,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmOutB,
-                                                             const __grid_constant__ CUtensorMap tmOutF, const TcParams p) {
+                                                             const __grid_constant__ CUtensorMap tmOutF,
+                                                             const __grid_constant__ CUtensorMap tmOutD, const TcParams p) {
   constexpr int B_STAGE_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   constexpr int STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     // 128-byte row panels (64 bf16 / 32 fp32 columns), 16-byte chunk index XOR (row & 7).
     uint8_t* stage_b = smem;                                   // bf16: BLOCK_N/64 panels x 128 rows x 128 B
     uint8_t* stage_f = smem + (p.out_bf16 != nullptr ? ((BLOCK_N + 63) / 64) * 16384 : 0);   // fp32: BLOCK_N/32 panels of 16 KB
+    uint8_t* stage_d = stage_f + (p.out_f32 != nullptr ? (BLOCK_N / 32) * 16384 : 0);               // bf16 dact panels
     const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
@@ -271,11 +273,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       float v[16];
       const int64_t off = pix * p.cout + nb;
       const bool full = vec_ok && nb + 16 <= p.cout;
-      if (p.dact != nullptr && row_ok) {          // save act'(pre-activation) for the backward pass
+      if (p.dact != nullptr && (row_ok || p.tma_store)) {   // save act'(pre-activation) for the backward pass
         float dv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) dv[j] = act_grad(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
-        if (full) {
+        if (p.tma_store) {
+          uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
+          const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
+          *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+          *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
+        } else if (full) {
           uint4* o = reinterpret_cast<uint4*>(p.dact + off);
           o[0] = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
           o[1] = make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
@@ -314,7 +323,28 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
         }
       }
-      if (p.mul != nullptr && row_ok) {
+      if (p.mul != nullptr && row_ok && full) {
+        float mv[16];
+        if (p.mul_dtype == GA_F32) {
+          const float4* m4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mul) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { float4 t = __ldg(m4 + j); mv[4 * j] = t.x; mv[4 * j + 1] = t.y; mv[4 * j + 2] = t.z; mv[4 * j + 3] = t.w; }
+        } else {
+          const uint4* m4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mul) + off);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 t = __ldg(m4 + j);
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+              mv[8 * j + 2 * k] = __low2float(h); mv[8 * j + 2 * k + 1] = __high2float(h);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= mul_factor(mv[j], p.mul_mode);
+      } else if (p.mul != nullptr && row_ok) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (nb + j < p.cout) {
@@ -374,6 +404,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         if (p.out_f32 != nullptr)
           for (int pn = 0; pn * 32 < BLOCK_N && n_blk * BLOCK_N + pn * 32 < p.cout; ++pn)
             tma_store_2d(&tmOutF, stage_f + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 32, row0);
+        if (p.dact != nullptr)
+          for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
+            tma_store_2d(&tmOutD, stage_d + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
         tma_store_commit();
         tma_store_wait_read();       // smem must stay valid until the bulk stores have read it
       }
@@ -466,9 +499,9 @@ static int encode_out_map(CUtensorMap* tm, void* base, int cout, int64_t m, int 
 
 template <int BLOCK_N, int STAGES>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of,
-                     const TcParams& p, dim3 grid, cudaStream_t s) {
+                     const CUtensorMap& od, const TcParams& p, dim3 grid, cudaStream_t s) {
   constexpr int ring = STAGES * (TC_A_STAGE_BYTES + BLOCK_N * TC_BLOCK_K * 2);
-  constexpr int max_staging = ((BLOCK_N + 63) / 64) * 16384 + (BLOCK_N / 32) * 16384;
+  constexpr int max_staging = 2 * ((BLOCK_N + 63) / 64) * 16384 + (BLOCK_N / 32) * 16384;
   constexpr int max_smem = 1024 /*align*/ + 2048 /*header*/ + (ring > max_staging ? ring : max_staging);
   static bool configured = false;
   if (!configured) {
@@ -477,10 +510,10 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
     configured = true;
   }
   int staging = 0;
-  if (p.tma_store) staging = (p.out_bf16 ? ((BLOCK_N + 63) / 64) * 16384 : 0) + (p.out_f32 ? (BLOCK_N / 32) * 16384 : 0);
+  if (p.tma_store) staging = ((p.out_bf16 ? 1 : 0) + (p.dact ? 1 : 0)) * ((BLOCK_N + 63) / 64) * 16384 + (p.out_f32 ? (BLOCK_N / 32) * 16384 : 0);
   const int smem = 1024 + 2048 + (ring > staging ? ring : staging);
   GA_CHECK(smem <= 227 * 1024, "conv_tc: shared memory request %d too large", smem);
-  conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, p);
+  conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, od, p);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -560,9 +593,11 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   bool tma_ok = tma_store_enabled != 0;
   if (out_bf16 && ((out->c * 2) % 16 != 0 || (((uintptr_t)out_bf16->data) & 15))) tma_ok = false;
   if (out_f32 && ((out->c * 4) % 16 != 0 || (((uintptr_t)out_f32->data) & 15))) tma_ok = false;
-  if (block_n == 256 && out_bf16 && out_f32) tma_ok = false;       // staging would not fit
+  if (block_n == 256 && ((out_bf16 ? 1 : 0) + (out_f32 ? 2 : 0) + (p.dact ? 1 : 0)) > 2) tma_ok = false;   // staging would not fit
+  if (p.dact && ((((uintptr_t)p.dact) & 15) || (out->c * 2) % 16 != 0 || (block_n == 32 && out->c > 32))) tma_ok = false;
   if (block_n == 32 && out_bf16 && out->c > 32) tma_ok = false;     // 64-column bf16 panel would spill into the next N tile
-  CUtensorMap tmOB = tmA, tmOF = tmA;
+  CUtensorMap tmOB = tmA, tmOF = tmA, tmOD = tmA;
+  if (tma_ok && p.dact) { if (encode_out_map(&tmOD, p.dact, out->c, p.M, 2)) return 1; }
   if (tma_ok && out_bf16) { if (encode_out_map(&tmOB, out_bf16->data, out->c, p.M, 2)) return 1; }
   if (tma_ok && out_f32) { if (encode_out_map(&tmOF, out_f32->data, out->c, p.M, 4)) return 1; }
   p.tma_store = tma_ok ? 1 : 0;
@@ -570,16 +605,16 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   const bool short_k = num_kb <= 2;             // 1x1 convs with K <= 128: 2-stage ring -> more CTAs per SM
   if (num_kb == 1) {                            // single K block: 1-stage ring, up to 4 CTAs per SM (TMEM-limited)
     switch (block_n) {
-      case 32: return launch_tc<32, 1>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
-      case 64: return launch_tc<64, 1>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
-      case 128: return launch_tc<128, 1>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+      case 32: return launch_tc<32, 1>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
+      case 64: return launch_tc<64, 1>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
+      case 128: return launch_tc<128, 1>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
       default: break;
     }
   }
   switch (block_n) {
-    case 32: return short_k ? launch_tc<32, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<32, 4>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
-    case 64: return short_k ? launch_tc<64, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<64, 4>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
-    case 128: return short_k ? launch_tc<128, 2>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s) : launch_tc<128, 3>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
-    default: return launch_tc<256, 3>(tmA, tmA2, tmB, tmOB, tmOF, p, grid, s);
+    case 32: return short_k ? launch_tc<32, 2>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s) : launch_tc<32, 4>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
+    case 64: return short_k ? launch_tc<64, 2>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s) : launch_tc<64, 4>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
+    case 128: return short_k ? launch_tc<128, 2>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s) : launch_tc<128, 3>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
+    default: return launch_tc<256, 3>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
   }
 }

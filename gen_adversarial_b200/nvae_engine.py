@@ -383,7 +383,7 @@ class NvaeEngine:
             d.dw_wT = d.dw_w.flip(0).contiguous()                        # 5x5 taps reversed = spatial flip
         self.init_conv_d = dg(self.init_conv)
         self.enc0_d = dg(self.enc0)
-        self.to_logits_d = dg(self.to_logits)
+        self.to_logits_d = dg(self.to_logits, pad_cin_to=round_up(self.to_logits.cout, 8))
         for L in self.levels:
             L["enc_sampler_d"] = dg(L["enc_sampler"], pad_cin_to=self.zc)
             L["dec_comb_x_d"] = dg(L["dec_comb"]) if "prior_x" not in L else None
@@ -405,7 +405,7 @@ class NvaeEngine:
             kind = rec[0]
             if kind == "head":
                 _, x32, logits = rec
-                g_logits = ops.discmix_mean_bwd(logits, spec.num_mixtures, g_purified_nchw, g_cls)
+                g_logits = ops.discmix_mean_bwd(logits, spec.num_mixtures, g_purified_nchw, g_cls, pad_to=self.to_logits_d.cin)
                 t = self._dgrad(g_logits, self.to_logits_d, f32=True)                 # w.r.t. ELU(x)
                 g = ops.affine_act_bwd(t, x32, None, None, ACT_ELU, torch.float32)
             elif kind == "dec":

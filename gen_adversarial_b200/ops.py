@@ -410,8 +410,10 @@ def latent_mix_bwd(g_z, q, p, eps_nchw, seed: int, level: int, sample0: int, alp
 
 
 @_timed("discmix_mean_bwd")
-def discmix_mean_bwd(logits, n_mix: int, g_purified_nchw, g_cls):
-    g_logits = torch.empty_like(logits)
+def discmix_mean_bwd(logits, n_mix: int, g_purified_nchw, g_cls, pad_to: int = 0):
+    """-> d loss / d logits, fp32, channel-padded with zeros to `pad_to` channels (tensor-core alignment of the dgrad conv)"""
+    n, h, w, c = logits.shape
+    g_logits = torch.empty((n, h, w, max(c, pad_to)), device=logits.device, dtype=torch.float32)
     _lib.check(_lib.lib().ga_discmix_mean_bwd(gt(logits), n_mix, ptr(g_purified_nchw), gt(g_cls), gt(g_logits), stream()),
                "discmix_mean_bwd")
     return g_logits

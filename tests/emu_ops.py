@@ -322,7 +322,7 @@ def latent_mix_bwd(g_z, q, p, eps_nchw, seed, level, sample0, alpha_dev, tempera
     return out, g_p
 
 
-def discmix_mean_bwd(logits, n_mix, g_purified_nchw, g_cls):
+def discmix_mean_bwd(logits, n_mix, g_purified_nchw, g_cls, pad_to=0):
     _launches[0] += 1
     from oracle.nvae_ref import disc_mix_logistic_mean
     l = _nchw(logits).detach().requires_grad_(True)
@@ -334,7 +334,10 @@ def discmix_mean_bwd(logits, n_mix, g_purified_nchw, g_cls):
         if g_cls is not None:
             gv = gv + _nchw(g_cls)
         g, = torch.autograd.grad(v, [l], gv)
-    return _nhwc(g, torch.float32)
+    g = _nhwc(g, torch.float32)
+    if pad_to > g.shape[3]:
+        g = torch.cat([g, torch.zeros(g.shape[:3] + (pad_to - g.shape[3],))], dim=3).contiguous()
+    return g
 
 
 def preprocess_bwd(g_nhwc, pre_nchw, blur, normalize=True, taps_cache=None):
