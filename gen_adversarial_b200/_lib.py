@@ -22,7 +22,7 @@ HEADER = os.path.join(ROOT_DIR, "include", "ga_b200.h")
 
 GA_F32, GA_BF16 = 0, 1
 PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU = 0, 1, 2, 3
-ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, ACT_LRELU_SQRT2 = 0, 1, 2, 3, 4
 MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y = 0, 1, 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -115,6 +115,13 @@ _PROTOS = {
     "ga_cast": (c_int, [T, T, c_void_p]),
     "ga_affine_act": (c_int, [T, c_void_p, c_void_p, c_int, T, c_void_p]),
     "ga_nchw_to_nhwc": (c_int, [c_void_p, T, c_float, c_float, c_void_p]),
+    "ga_pixelnorm": (c_int, [c_void_p, c_int, c_int, T, c_void_p]),
+    "ga_style_demod": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ga_channel_scale": (c_int, [T, c_void_p, T, c_void_p]),
+    "ga_styled_bias_act": (c_int, [T, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, T, T, c_void_p]),
+    "ga_upfirdn2d": (c_int, [T, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, T, c_void_p]),
+    "ga_avgpool_to_nchw": (c_int, [T, c_int, c_int, c_void_p, c_void_p]),
+    "ga_latent_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ga_pgd_linf_step": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int64, c_void_p]),
     "ga_softmax_xent": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

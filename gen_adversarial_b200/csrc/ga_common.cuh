@@ -55,6 +55,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case GA_ACT_SILU: return siluf_(v);
     case GA_ACT_ELU: return eluf_(v);
     case GA_ACT_RELU: return fmaxf(v, 0.0f);
+    case GA_ACT_LRELU_SQRT2: return (v > 0.0f ? v : 0.2f * v) * 1.4142135623730951f;
     default: return v;
   }
 }
@@ -75,6 +76,7 @@ __device__ __forceinline__ float apply_act_fast(float v, int act) {
     case GA_ACT_SILU: return silu_fast(v);
     case GA_ACT_ELU: return v > 0.0f ? v : __expf(v) - 1.0f;
     case GA_ACT_RELU: return fmaxf(v, 0.0f);
+    case GA_ACT_LRELU_SQRT2: return (v > 0.0f ? v : 0.2f * v) * 1.4142135623730951f;
     default: return v;
   }
 }
@@ -87,6 +89,7 @@ __device__ __forceinline__ float act_grad(float v, int act) {
     }
     case GA_ACT_ELU: return v > 0.0f ? 1.0f : expf(v);
     case GA_ACT_RELU: return v > 0.0f ? 1.0f : 0.0f;
+    case GA_ACT_LRELU_SQRT2: return (v > 0.0f ? 1.0f : 0.2f) * 1.4142135623730951f;
     default: return 1.0f;
   }
 }

@@ -1,0 +1,241 @@
+// StyleGAN2 generator pieces (E4E / Style-Transformer decoders): sm_100a replacements of the
+// reference's only native kernels -- `fused_bias_act` (stylegan2/op/fused_bias_act_kernel.cu:19-49) and `upfirdn2d`
+// (stylegan2/op/upfirdn2d_kernel.cu:52-137) -- plus the elementwise glue of the modulated convolution rewritten as
+// "scale input channels by the style -> ONE shared-weight dense conv (tcgen05 kernel) -> scale output channels by the
+// demodulation" (exact; the reference materialises B x weight copies and runs a grouped conv with
+// groups = B, stylegan2/generator.py:163-207).  All kernels are HBM-bound, NHWC, vectorised along channels.
+#include "ga_common.cuh"
+
+namespace ga {
+
+__device__ __forceinline__ float ld1s(const void* base, int dtype, int64_t off) {
+  return dtype == GA_F32 ? reinterpret_cast<const float*>(base)[off]
+                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]);
+}
+__device__ __forceinline__ void st1s(void* base, int dtype, int64_t off, float v) {
+  if (dtype == GA_F32) reinterpret_cast<float*>(base)[off] = v;
+  else reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ void ld4s(const void* base, int dtype, int64_t off, float (&v)[4]) {
+  if (dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(base) + off, v);
+  else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(base) + off, v);
+}
+__device__ __forceinline__ void st4s(void* base, int dtype, int64_t off, const float (&v)[4]) {
+  if (dtype == GA_F32) st4<float>(reinterpret_cast<float*>(base) + off, v);
+  else st4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(base) + off, v);
+}
+
+// ---------------------------------------------------------------------------- PixelNorm (generator.py:10-15): one warp per row
+__global__ void pixelnorm_kernel(const float* __restrict__ x, int rows, int d, void* out, int out_dtype) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * d;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) s = fmaf(xr[i], xr[i], s);
+  s = warp_sum(s);
+  const float r = rsqrtf(s / (float)d + 1e-8f);
+  for (int i = lane; i < d; i += 32) st1s(out, out_dtype, (int64_t)row * d + i, xr[i] * r);
+}
+
+// ---------------------------------------------------------------------------- demodulation factors (generator.py:169-171)
+// demod[n, co] = rsqrt( sum_ci s[n,ci]^2 * wsq[co,ci] + 1e-8 ),  wsq[co,ci] = sum_k (scale * W[co,ci,k])^2
+__global__ void style_demod_kernel(const float* __restrict__ s, const float* __restrict__ wsq, int N, int Cin, int Cout,
+                                   float* __restrict__ demod) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= N * Cout) return;
+  const int n = w / Cout, co = w % Cout;
+  float a = 0.f;
+  for (int ci = lane; ci < Cin; ci += 32) {
+    const float sv = s[(int64_t)n * Cin + ci];
+    a = fmaf(sv * sv, wsq[(int64_t)co * Cin + ci], a);
+  }
+  a = warp_sum(a);
+  if (lane == 0) demod[(int64_t)n * Cout + co] = rsqrtf(a + 1e-8f);
+}
+
+// ---------------------------------------------------------------------------- x[n,p,c] * s[n,c]  (modulation as activation scaling)
+__global__ void __launch_bounds__(256) channel_scale_kernel(const void* x, int x_dtype, const float* __restrict__ s, int HW, int C,
+                                                            int64_t total4, void* out, int out_dtype) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int64_t i = i4 * 4;
+  const int c = (int)(i % C);
+  const int64_t n = i / ((int64_t)HW * C);
+  float v[4];
+  ld4s(x, x_dtype, i, v);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(s + n * C + c));
+  v[0] *= sc.x; v[1] *= sc.y; v[2] *= sc.z; v[3] *= sc.w;
+  st4s(out, out_dtype, i, v);
+}
+
+// ---------------------------------------------------------------------------- fused demod + noise + bias + leaky-ReLU*sqrt(2)
+// out[n,y,x,c] = act( y_conv * demod[n,c] + noise_w * noise[y,x] + bias[c] ) (+ skip)    -- StyledConv.forward (generator.py:258-268)
+// and ToRGB (generator.py:283-292, act = none, demod = NULL, skip = up-sampled RGB).  This is the `fused_bias_act` equivalent.
+// phases = 1: y_conv holds the 4 sub-pixel phase planes [4][N][H/2][W/2][C] of an up-sampling conv (see stylegan_engine.py).
+__global__ void __launch_bounds__(256) styled_bias_act_kernel(const void* y, int y_dtype, int phases, const float* __restrict__ demod,
+                                                              const float* __restrict__ noise, float noise_w,
+                                                              const float* __restrict__ bias, int act, const void* skip, int skip_dtype,
+                                                              int N, int H, int W, int C, void* out, int out_dtype) {
+  const int c4n = C >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * H * W * c4n) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int x = (int)(t % W); t /= W;
+  const int yy = (int)(t % H);
+  const int64_t n = t / H;
+  int64_t src;
+  if (phases) {
+    const int ph = (yy & 1) * 2 + (x & 1);
+    const int Hh = H >> 1, Wh = W >> 1;
+    src = ((((int64_t)ph * N + n) * Hh + (yy >> 1)) * Wh + (x >> 1)) * C + c;
+  } else {
+    src = ((n * H + yy) * W + x) * C + c;
+  }
+  float v[4];
+  ld4s(y, y_dtype, src, v);
+  if (demod != nullptr) {
+    const float4 d = __ldg(reinterpret_cast<const float4*>(demod + n * C + c));
+    v[0] *= d.x; v[1] *= d.y; v[2] *= d.z; v[3] *= d.w;
+  }
+  const float nz = noise != nullptr ? noise_w * __ldg(noise + (int64_t)yy * W + x) : 0.f;
+  float b4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias != nullptr) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c)); b4[0] = b.x; b4[1] = b.y; b4[2] = b.z; b4[3] = b.w; }
+  const int64_t o = ((n * H + yy) * W + x) * C + c;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j] + nz + b4[j], act);
+  if (skip != nullptr) {
+    float s4[4];
+    ld4s(skip, skip_dtype, o, s4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += s4[j];
+  }
+  st4s(out, out_dtype, o, v);
+}
+
+// ---------------------------------------------------------------------------- upfirdn2d (general; op/upfirdn2d_kernel.cu:52-137)
+// out[o] = sum_k U[o*down + k - pad0] * kernel[K-1-k],  U = zero-insertion up-sampling of the input (per dimension)
+__global__ void upfirdn2d_kernel(const void* in, int in_dtype, const float* __restrict__ kern, int KH, int KW, int up, int down, int pad0,
+                                 int N, int H, int W, int C, int Ho, int Wo, void* out, int out_dtype) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * Ho * Wo * C) return;
+  const int c = (int)(idx % C);
+  int64_t t = idx / C;
+  const int ox = (int)(t % Wo); t /= Wo;
+  const int oy = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  float acc = 0.f;
+  for (int ky = 0; ky < KH; ++ky) {
+    const int uy = oy * down + ky - pad0;
+    if (uy < 0 || uy >= H * up || (uy % up) != 0) continue;
+    const int iy = uy / up;
+    for (int kx = 0; kx < KW; ++kx) {
+      const int ux = ox * down + kx - pad0;
+      if (ux < 0 || ux >= W * up || (ux % up) != 0) continue;
+      const int ix = ux / up;
+      acc = fmaf(ld1s(in, in_dtype, ((n * H + iy) * W + ix) * C + c), kern[(KH - 1 - ky) * KW + (KW - 1 - kx)], acc);
+    }
+  }
+  st1s(out, out_dtype, idx, acc);
+}
+
+// ---------------------------------------------------------------------------- k x k mean pooling (face_pool, psp.py:26,114), NHWC in -> NCHW fp32 out
+__global__ void avgpool_to_nchw_kernel(const void* in, int in_dtype, int N, int H, int W, int C, int Co, int k, float* __restrict__ out) {
+  const int Ho = H / k, Wo = W / k;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // over NCHW output (Co <= C channels kept)
+  if (idx >= (int64_t)N * Co * Ho * Wo) return;
+  const int ox = (int)(idx % Wo);
+  int64_t t = idx / Wo;
+  const int oy = (int)(t % Ho); t /= Ho;
+  const int c = (int)(t % Co);
+  const int64_t n = t / Co;
+  float acc = 0.f;
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx) acc += ld1s(in, in_dtype, ((n * H + oy * k + dy) * W + ox * k + dx) * C + c);
+  out[idx] = acc / (float)(k * k);
+}
+
+// ---------------------------------------------------------------------------- per-level latent interpolation of the W+ codes
+// out[b,l,:] = (1 - a_l) * codes[b,l,:] + a_l * styles[b,l,:]      (models.py:123-124, 338-339)
+__global__ void latent_lerp_kernel(const float* __restrict__ codes, const float* __restrict__ styles, const float* __restrict__ alphas,
+                                   int L, int D, int64_t total, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float a = alphas[(i / D) % L];
+  out[i] = (1.f - a) * codes[i] + a * styles[i];
+}
+
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" int ga_pixelnorm(const float* x, int rows, int d, const ga_tensor* out, void* stream) {
+  GA_CHECK(x && out && rows >= 0 && d > 0 && numel(out) == (int64_t)rows * d, "ga_pixelnorm: bad arguments");
+  if (rows == 0) return 0;
+  pixelnorm_kernel<<<cdiv((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, d, out->data, out->dtype);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_style_demod(const float* s, const float* wsq, int n, int cin, int cout, float* demod, void* stream) {
+  GA_CHECK(s && wsq && demod && n >= 0 && cin > 0 && cout > 0, "ga_style_demod: bad arguments");
+  if (n == 0) return 0;
+  style_demod_kernel<<<cdiv((int64_t)n * cout * 32, 256), 256, 0, (cudaStream_t)stream>>>(s, wsq, n, cin, cout, demod);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_channel_scale(const ga_tensor* x, const float* s, const ga_tensor* out, void* stream) {
+  GA_CHECK(x && s && out && same_shape(x, out) && (x->c % 4) == 0, "ga_channel_scale: shape mismatch (channels must be a multiple of 4)");
+  const int64_t total4 = numel(x) / 4;
+  if (total4 == 0) return 0;
+  channel_scale_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(x->data, x->dtype, s, x->h * x->w, x->c, total4, out->data, out->dtype);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_styled_bias_act(const ga_tensor* y, int phases, const float* demod, const float* noise_hw, float noise_w,
+                                  const float* bias, int act, const ga_tensor* skip, const ga_tensor* out, void* stream) {
+  GA_CHECK(y && out && (out->c % 4) == 0, "ga_styled_bias_act: null argument / channels must be a multiple of 4");
+  if (phases) GA_CHECK(y->n == 4 * out->n && y->h * 2 == out->h && y->w * 2 == out->w && y->c == out->c, "ga_styled_bias_act: phase planes must be [4*n][h/2][w/2][c]");
+  else GA_CHECK(same_shape(y, out), "ga_styled_bias_act: shape mismatch");
+  GA_CHECK(!skip || same_shape(skip, out), "ga_styled_bias_act: skip shape mismatch");
+  const int64_t total = numel(out) / 4;
+  if (total == 0) return 0;
+  styled_bias_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y->data, y->dtype, phases, demod, noise_hw, noise_w, bias, act,
+                                                                              skip ? skip->data : nullptr, skip ? skip->dtype : GA_F32, out->n,
+                                                                              out->h, out->w, out->c, out->data, out->dtype);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_upfirdn2d(const ga_tensor* in, const float* kernel, int kh, int kw, int up, int down, int pad0, int pad1,
+                            const ga_tensor* out, void* stream) {
+  GA_CHECK(in && kernel && out && up >= 1 && down >= 1 && kh >= 1 && kw >= 1, "ga_upfirdn2d: bad arguments");
+  const int Ho = (in->h * up + pad0 + pad1 - kh) / down + 1, Wo = (in->w * up + pad0 + pad1 - kw) / down + 1;
+  GA_CHECK(out->n == in->n && out->c == in->c && out->h == Ho && out->w == Wo, "ga_upfirdn2d: output must be (%d,%d,%d,%d)", in->n, Ho, Wo, in->c);
+  const int64_t total = numel(out);
+  if (total == 0) return 0;
+  upfirdn2d_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, kernel, kh, kw, up, down, pad0, in->n, in->h, in->w,
+                                                                       in->c, Ho, Wo, out->data, out->dtype);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_avgpool_to_nchw(const ga_tensor* in, int k, int out_c, float* out_nchw, void* stream) {
+  GA_CHECK(in && out_nchw && k >= 1 && in->h % k == 0 && in->w % k == 0 && out_c >= 1 && out_c <= in->c, "ga_avgpool_to_nchw: bad arguments");
+  const int64_t total = (int64_t)in->n * out_c * (in->h / k) * (in->w / k);
+  if (total == 0) return 0;
+  avgpool_to_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, in->n, in->h, in->w, in->c, out_c, k, out_nchw);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_latent_lerp(const float* codes, const float* styles, const float* alphas_dev, int b, int l, int d, float* out, void* stream) {
+  GA_CHECK(codes && styles && alphas_dev && out && b >= 0 && l > 0 && d > 0, "ga_latent_lerp: bad arguments");
+  const int64_t total = (int64_t)b * l * d;
+  if (total == 0) return 0;
+  latent_lerp_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(codes, styles, alphas_dev, l, d, total, out);
+  GA_LAUNCH_OK();
+  return 0;
+}

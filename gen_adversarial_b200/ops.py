@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import GaTensor, GaConvDesc, GA_F32, GA_BF16, PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, \
-    ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
+    ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, ACT_LRELU_SQRT2, MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -141,12 +141,14 @@ def conv_out_hw(L: ConvLayer, h: int, w: int):
 
 @_timed("conv2d_simt")
 def conv2d_simt(x: torch.Tensor, L: ConvLayer, out_dtype: torch.dtype, add: Optional[torch.Tensor] = None,
-                out_hw=None, mul: Optional[torch.Tensor] = None, mul_mode: int = 0, want_dact: bool = False):
+                out_hw=None, mul: Optional[torch.Tensor] = None, mul_mode: int = 0, want_dact: bool = False,
+                out: Optional[torch.Tensor] = None):
     """out = (act(conv(pre(x)) + bias) + add) * f(mul).  With want_dact -> (out, act'(pre-activation))."""
     n, h, w, c = x.shape
     assert c == L.cin, (L.name, c, L.cin)
     ho, wo = out_hw if out_hw is not None else conv_out_hw(L, h, w)
-    out = torch.empty((n, ho, wo, L.cout), device=x.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty((n, ho, wo, L.cout), device=x.device, dtype=out_dtype)
     dact = torch.empty_like(out) if want_dact else None
     d = L.desc(False, mul, mul_mode, dact)
     _lib.check(_lib.lib().ga_conv2d_simt(gt(x), ctypes.byref(d), gt(add), gt(out), stream()), f"conv2d_simt[{L.name}]")
@@ -162,12 +164,13 @@ def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor
 
 def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
               add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None,
-              mul: Optional[torch.Tensor] = None, mul_mode: int = 0, dact_out: Optional[torch.Tensor] = None):
+              mul: Optional[torch.Tensor] = None, mul_mode: int = 0, dact_out: Optional[torch.Tensor] = None,
+              out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
     """-> (out_bf16 or None, out_f32 or None);  out = (act(conv + bias) + add) * f(mul); dact_out <- act'(conv + bias)"""
     n, h, w, c = x.shape
     assert c == L.cin, (L.name, c, L.cin)
-    ob = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    of = torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.float32) if want_f32 else None
+    ob = (out_bf16 if out_bf16 is not None else torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.bfloat16)) if want_bf16 else None
+    of = (out_f32 if out_f32 is not None else torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.float32)) if want_f32 else None
     d = L.desc(True, mul, mul_mode, dact_out)
     e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_conv2d_tc(gt(x), gt(x2), ctypes.byref(d), gt(add), gt(ob), gt(of), stream()),
@@ -348,6 +351,71 @@ def softmax_xent(logits, labels, want_grad=True, counter=None):
     _lib.check(_lib.lib().ga_softmax_xent(ptr(logits), ptr(labels), n, k, ptr(loss), ptr(dl), ptr(pred), ptr(counter), stream()),
                "softmax_xent")
     return loss, dl, pred
+
+
+# ------------------------------------------------------------------------------------------------ StyleGAN2 generator ops
+@_timed("pixelnorm")
+def pixelnorm(x: torch.Tensor, out_dtype) -> torch.Tensor:
+    """x: (rows, d) fp32 -> (rows, 1, 1, d) NHWC view"""
+    rows, d = x.shape
+    out = torch.empty((rows, 1, 1, d), device=x.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_pixelnorm(ptr(x.contiguous()), rows, d, gt(out), stream()), "pixelnorm")
+    return out
+
+
+@_timed("style_demod")
+def style_demod(s: torch.Tensor, wsq: torch.Tensor) -> torch.Tensor:
+    n, cin = s.shape
+    cout = wsq.shape[0]
+    demod = torch.empty((n, cout), device=s.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ga_style_demod(ptr(s), ptr(wsq), n, cin, cout, ptr(demod), stream()), "style_demod")
+    return demod
+
+
+@_timed("channel_scale")
+def channel_scale(x, s, out_dtype):
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_channel_scale(gt(x), ptr(s), gt(out), stream()), "channel_scale")
+    return out
+
+
+@_timed("styled_bias_act")
+def styled_bias_act(y, phases: bool, demod, noise_hw, noise_w: float, bias, act: int, skip, out_dtype):
+    n = y.shape[0] // 4 if phases else y.shape[0]
+    h, w = (y.shape[1] * 2, y.shape[2] * 2) if phases else (y.shape[1], y.shape[2])
+    out = torch.empty((n, h, w, y.shape[3]), device=y.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_styled_bias_act(gt(y), int(phases), ptr(demod), ptr(noise_hw), float(noise_w), ptr(bias), act, gt(skip),
+                                             gt(out), stream()), "styled_bias_act")
+    return out
+
+
+@_timed("upfirdn2d")
+def upfirdn2d(x, kernel, up: int = 1, down: int = 1, pad=(0, 0), out_dtype=None):
+    """same semantics as the reference op (stylegan2/op/upfirdn2d.py:141-147) on NHWC tensors"""
+    n, h, w, c = x.shape
+    kh, kw = kernel.shape
+    ho = (h * up + pad[0] + pad[1] - kh) // down + 1
+    wo = (w * up + pad[0] + pad[1] - kw) // down + 1
+    out = torch.empty((n, ho, wo, c), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().ga_upfirdn2d(gt(x), ptr(kernel), kh, kw, up, down, pad[0], pad[1], gt(out), stream()), "upfirdn2d")
+    return out
+
+
+@_timed("avgpool_to_nchw")
+def avgpool_to_nchw(x, k: int, out_c: int):
+    n, h, w, c = x.shape
+    out = torch.empty((n, out_c, h // k, w // k), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ga_avgpool_to_nchw(gt(x), k, out_c, ptr(out), stream()), "avgpool_to_nchw")
+    return out
+
+
+@_timed("latent_lerp")
+def latent_lerp(codes, styles, alphas_dev):
+    b, l, d = codes.shape
+    out = torch.empty_like(codes)
+    _lib.check(_lib.lib().ga_latent_lerp(ptr(codes.contiguous()), ptr(styles.contiguous()), ptr(alphas_dev), b, l, d, ptr(out), stream()),
+               "latent_lerp")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ backward ops

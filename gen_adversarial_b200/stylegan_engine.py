@@ -1,0 +1,201 @@
+"""StyleGAN2 generator (decoder of the E4E / Style-Transformer purifiers) on the hand-written CUDA kernels.
+
+Replaces `Generator.forward(..., input_is_latent=True, randomize_noise=False)` and `Generator.style`
+(/root/reference/src/mlvgms_autoencoders/StyleGan_E4E/stylegan2/generator.py:294-479).
+
+Exact rewrites done at load (fp64):
+  * equalised-lr scales folded into the weights (`EqualLinear`, generator.py:69-100; conv scale :154-155);
+  * modulated conv = scale the input channels by the style s[b,ci]  ->  ONE shared-weight dense conv (tcgen05 kernel)
+    ->  scale the output channels by demod[b,co] = rsqrt(sum_ci s^2 * sum_k W^2 + 1e-8)   (SURVEY App. D, 6e-15);
+    the reference builds B x Cout x Cin x k x k weights and a grouped conv with groups = B (generator.py:163-207);
+  * up-sampling StyledConv = conv_transpose2d(stride 2) followed by the 4x4 FIR blur (generator.py:180-191): both are
+    linear with zero boundaries, so their composition is a stride-2 transposed conv with a 6x6 kernel, i.e. FOUR
+    ordinary 3x3 convolutions (one per output sub-pixel phase) at the INPUT resolution on composed weights
+    K_{py,px}[a,b] = G[py+2-2a, px+2-2b], G = W (*) blur.  They run on the tensor-core conv kernel and are interleaved by
+    the fused epilogue kernel -- no zero-insertion, no (2H+1)^2 intermediate, no separate blur pass;
+  * `noise + bias + leaky_relu * sqrt(2)` (NoiseInjection + FusedLeakyReLU, generator.py:210-268) and the demodulation
+    scale are one kernel (`ga_styled_bias_act`, the `fused_bias_act` equivalent);
+  * the mapping MLP runs ONCE on all n_codes x B rows (the reference loops over codes in Python, models.py:120,335).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from ._lib import ACT_NONE, ACT_LRELU_SQRT2
+from .fold import Folder
+from .synth import STYLEGAN_CHANNELS
+
+
+class _Styled:
+    __slots__ = ("mod", "conv", "phase_convs", "wsq", "noise", "noise_w", "bias", "up", "cin", "cout")
+
+
+class _ToRGB:
+    __slots__ = ("mod", "conv", "bias", "up_kernel")
+
+
+class StyleGan2Engine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], size: int, device, mode: str = "fp32", style_dim: int = 512,
+                 n_mlp: int = 8, channel_multiplier: int = 2, lr_mlp: float = 0.01, _host_logic_test: bool = False):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and not _host_logic_test:
+            raise RuntimeError("StyleGan2Engine runs only on CUDA devices: there is no CPU fallback")
+        self.mode, self.bf16 = mode, mode == "bf16"
+        self.adt = torch.bfloat16 if self.bf16 else torch.float32
+        self.size, self.style_dim = size, style_dim
+        self.log_size = int(math.log2(size))
+        self.n_latent = self.log_size * 2 - 2
+        ch = STYLEGAN_CHANNELS(channel_multiplier)
+        f = Folder(state_dict, self.device, want_tc=self.bf16)
+        sd = state_dict
+        # ---- mapping network (generator.py:311-320)
+        self.mapping_layers = []
+        sc = (1.0 / math.sqrt(style_dim)) * lr_mlp
+        for i in range(1, n_mlp + 1):
+            w = f.f64(f"style.{i}.weight") * sc
+            b = f.f64(f"style.{i}.bias") * lr_mlp
+            self.mapping_layers.append(f.conv(w.view(style_dim, style_dim, 1, 1), b, post_act=ACT_LRELU_SQRT2, name=f"style.{i}"))
+        # ---- synthesis
+        self.const_input = f.dev32(f.f64("input.input")[0].permute(1, 2, 0).unsqueeze(0))          # [1,4,4,C]
+        self.conv1 = self._fold_styled(f, "conv1", up=False)
+        self.to_rgb1 = self._fold_rgb(f, "to_rgb1", up=False)
+        self.blocks = []
+        for j in range(self.log_size - 2):
+            self.blocks.append((self._fold_styled(f, f"convs.{2 * j}", up=True), self._fold_styled(f, f"convs.{2 * j + 1}", up=False),
+                                self._fold_rgb(f, f"to_rgbs.{j}", up=True)))
+        num_layers = (self.log_size - 2) * 2 + 1
+        self.noises = [f.dev32(f.f64(f"noises.noise_{i}")[0, 0]) for i in range(num_layers)]
+
+    # ------------------------------------------------------------------ load-time folds
+    def _fold_mod(self, f: Folder, prefix: str):
+        w = f.f64(f"{prefix}.conv.modulation.weight") * (1.0 / math.sqrt(self.style_dim))           # lr_mul = 1
+        b = f.f64(f"{prefix}.conv.modulation.bias")
+        L = f.conv(w.view(w.shape[0], w.shape[1], 1, 1), b, name=prefix + ".modulation")
+        L.w_tc = None                      # tiny GEMM; keep the style in fp32 (SIMT kernel) in both modes
+        return L
+
+    def _fold_styled(self, f: Folder, prefix: str, up: bool) -> _Styled:
+        s = _Styled()
+        w = f.f64(f"{prefix}.conv.weight")[0]                                                       # [cout, cin, 3, 3]
+        cout, cin, k, _ = w.shape
+        w = w * (1.0 / math.sqrt(cin * k * k))
+        s.cin, s.cout, s.up = cin, cout, up
+        s.mod = self._fold_mod(f, prefix)
+        s.wsq = f.dev32((w ** 2).sum(dim=(2, 3)))                                                   # [cout, cin]
+        s.conv, s.phase_convs = None, None
+        if not up:
+            s.conv = f.conv(w, None, pad=1, name=prefix + ".conv")
+        else:
+            kb = f.f64(f"{prefix}.conv.blur.kernel")                                                # 4x4, already x4
+            G = torch.zeros((cout, cin, 6, 6), dtype=torch.float64)                                 # index d+2, d in [-2, 3]
+            for dy in range(-2, 4):
+                for dx in range(-2, 4):
+                    for ty in range(4):
+                        for tx in range(4):
+                            ky, kx = dy + ty - 1, dx + tx - 1
+                            if 0 <= ky < 3 and 0 <= kx < 3:
+                                G[:, :, dy + 2, dx + 2] += kb[ty, tx] * w[:, :, ky, kx]
+            s.phase_convs = []
+            for py in range(2):
+                for px in range(2):
+                    K = torch.zeros((cout, cin, 3, 3), dtype=torch.float64)
+                    for a in range(3):
+                        for b in range(3):
+                            K[:, :, a, b] = G[:, :, (py + 2 - 2 * a) + 2, (px + 2 - 2 * b) + 2]
+                    s.phase_convs.append(f.conv(K, None, pad=1, name=f"{prefix}.conv.phase{py}{px}"))
+        s.noise_w = float(f.f64(f"{prefix}.noise.weight")[0])
+        s.bias = f.dev32(f.f64(f"{prefix}.activate.bias"))
+        return s
+
+    def _fold_rgb(self, f: Folder, prefix: str, up: bool) -> _ToRGB:
+        r = _ToRGB()
+        w = f.f64(f"{prefix}.conv.weight")[0]                                                       # [3, cin, 1, 1]
+        cin = w.shape[1]
+        w4 = torch.zeros((4, cin, 1, 1), dtype=torch.float64)                                       # RGB padded to 4 channels
+        w4[:3] = w * (1.0 / math.sqrt(cin))
+        r.mod = self._fold_mod(f, prefix)
+        r.conv = f.conv(w4, None, name=prefix + ".conv")
+        b4 = torch.zeros(4, dtype=torch.float64)
+        b4[:3] = f.f64(f"{prefix}.bias").view(3)
+        r.bias = f.dev32(b4)
+        r.up_kernel = f.dev32(f.f64(f"{prefix}.upsample.kernel")) if up else None
+        return r
+
+    # ------------------------------------------------------------------ ops
+    def _conv(self, x, L, want_f32=False, out=None):
+        if self.bf16 and ops.conv2d_tc_supported(x, L):
+            ob, of = ops.conv2d_tc(x, L, want_bf16=not want_f32, want_f32=want_f32, out_bf16=None if want_f32 else out,
+                                   out_f32=out if want_f32 else None)
+            return of if want_f32 else ob
+        return ops.conv2d_simt(x, L, torch.float32 if (want_f32 or not self.bf16) else torch.bfloat16, out=out)
+
+    def mapping(self, z: torch.Tensor) -> torch.Tensor:
+        """z: (rows, style_dim) fp32 -> w: (rows, style_dim) fp32   [`Generator.style`, all codes in one batch]"""
+        x = ops.pixelnorm(z.to(torch.float32), self.adt)
+        for i, L in enumerate(self.mapping_layers):
+            x = self._conv(x, L, want_f32=(i == len(self.mapping_layers) - 1))
+        return x.reshape(z.shape[0], self.style_dim)
+
+    def _style(self, L, latent_i):
+        """modulation EqualLinear (generator.py:164): (B, style_dim) -> (B, Cin) fp32"""
+        b = latent_i.shape[0]
+        return ops.conv2d_simt(latent_i.reshape(b, 1, 1, -1).contiguous(), L, torch.float32).reshape(b, -1)
+
+    def _styled(self, x, s: _Styled, latent_i, noise):
+        st = self._style(s.mod, latent_i)
+        xs = ops.channel_scale(x, st, self.adt)
+        demod = ops.style_demod(st, s.wsq)
+        if not s.up:
+            y = self._conv(xs, s.conv)
+            return ops.styled_bias_act(y, False, demod, noise, s.noise_w, s.bias, ACT_LRELU_SQRT2, None, self.adt)
+        b, h, w, _ = x.shape
+        planes = torch.empty((4 * b, h, w, s.cout), device=x.device, dtype=self.adt)
+        for ph, L in enumerate(s.phase_convs):
+            self._conv(xs, L, out=planes[ph * b:(ph + 1) * b])
+        return ops.styled_bias_act(planes, True, demod, noise, s.noise_w, s.bias, ACT_LRELU_SQRT2, None, self.adt)
+
+    def _rgb(self, x, r: _ToRGB, latent_i, skip):
+        st = self._style(r.mod, latent_i)
+        xs = ops.channel_scale(x, st, self.adt)
+        y = self._conv(xs, r.conv, want_f32=True)                                                   # [B,H,W,4] fp32
+        if skip is not None:
+            skip = ops.upfirdn2d(skip, r.up_kernel, up=2, down=1, pad=(2, 1))                        # Upsample (generator.py:30-47)
+        return ops.styled_bias_act(y, False, None, None, 0.0, r.bias, ACT_NONE, skip, torch.float32)
+
+    def synthesis(self, latent: torch.Tensor) -> torch.Tensor:
+        """latent: (B, n_latent, style_dim) fp32 -> RGB image NHWC (B, size, size, 4) fp32 (4th channel is padding)"""
+        b = latent.shape[0]
+        assert latent.shape[1] == self.n_latent, (latent.shape, self.n_latent)
+        latent = latent.to(torch.float32)
+        x = ops.cast(self.const_input.expand(b, -1, -1, -1).contiguous(), self.adt)
+        x = self._styled(x, self.conv1, latent[:, 0], self.noises[0])
+        skip = self._rgb(x, self.to_rgb1, latent[:, 1], None)
+        i = 1
+        for j, (up, conv, rgb) in enumerate(self.blocks):
+            x = self._styled(x, up, latent[:, i], self.noises[2 * j + 1])
+            x = self._styled(x, conv, latent[:, i + 1], self.noises[2 * j + 2])
+            skip = self._rgb(x, rgb, latent[:, i + 2], skip)
+            i += 2
+        return skip
+
+    def decode(self, latent: torch.Tensor, pool: int = 1, chunk: Optional[int] = None) -> torch.Tensor:
+        """`pSp.decode` (psp.py:109-115): synthesis + face_pool (k x k mean) -> NCHW fp32 (B,3,size/pool,size/pool).
+        The batch is processed in chunks: at 1024^2 one (chunk,32,1024,1024) bf16 activation is already chunk x 64 MB."""
+        b = latent.shape[0]
+        chunk = chunk or max(1, min(b, (256 * 256 * 64) // (self.size * self.size) or 1))
+        outs = []
+        for lo in range(0, b, chunk):
+            img = self.synthesis(latent[lo:lo + chunk])
+            outs.append(ops.avgpool_to_nchw(img, pool, 3))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def mix_codes(self, codes: torch.Tensor, z_noise: torch.Tensor, alphas_dev: torch.Tensor) -> torch.Tensor:
+        """per-level latent interpolation (models.py:117-127): styles = mapping(noise) for all n_codes x B rows at once;
+        codes (B, n, d), z_noise (n, B, d) in the reference's draw layout (torch.normal(0,1,(n_codes,b,d)), models.py:119)"""
+        b, n, d = codes.shape
+        styles = self.mapping(z_noise.reshape(n * b, d)).reshape(n, b, d).permute(1, 0, 2).contiguous()
+        return ops.latent_lerp(codes.to(torch.float32), styles, alphas_dev)

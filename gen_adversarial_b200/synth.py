@@ -180,3 +180,57 @@ def synthetic_noise(spec: NvaeSpec, batch: int, seed: int = 7):
     """Explicit N(0,1) tensors in the reference's draw order (SURVEY 8c "RNG order")."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     return [torch.randn(s, generator=g, dtype=torch.float32) for s in spec.noise_shapes(batch)]
+
+
+# ----------------------------------------------------------------------------------------------- StyleGAN2 generator
+STYLEGAN_CHANNELS = lambda cm: {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * cm, 128: 128 * cm, 256: 64 * cm, 512: 32 * cm, 1024: 16 * cm}
+
+
+def make_stylegan2_state_dict(size: int = 32, style_dim: int = 512, n_mlp: int = 8, channel_multiplier: int = 2, seed: int = 2,
+                              lr_mlp: float = 0.01) -> "OrderedDict[str, torch.Tensor]":
+    """State dict of the reference `Generator` (/root/reference/src/mlvgms_autoencoders/StyleGan_E4E/stylegan2/
+    generator.py:294-385): mapping MLP, constant input, StyledConv / ToRGB stacks, fixed noise buffers, blur kernels."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    ch = STYLEGAN_CHANNELS(channel_multiplier)
+    log_size = int(math.log2(size))
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for i in range(1, n_mlp + 1):
+        sd[f"style.{i}.weight"] = _randn((style_dim, style_dim), g) / lr_mlp
+        sd[f"style.{i}.bias"] = _randn((style_dim,), g, 0.1 / lr_mlp)
+    sd["input.input"] = _randn((1, ch[4], 4, 4), g)
+    blur = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    blur2 = blur[None, :] * blur[:, None]
+    blur2 = blur2 / blur2.sum()
+
+    def styled(prefix, cin, cout, k, up):
+        sd[f"{prefix}.conv.weight"] = _randn((1, cout, cin, k, k), g)
+        if up:
+            sd[f"{prefix}.conv.blur.kernel"] = blur2 * 4.0
+        sd[f"{prefix}.conv.modulation.weight"] = _randn((cin, style_dim), g)
+        sd[f"{prefix}.conv.modulation.bias"] = torch.ones(cin) + _randn((cin,), g, 0.1)
+
+    def conv_block(prefix, cin, cout, up):
+        styled(prefix, cin, cout, 3, up)
+        sd[f"{prefix}.noise.weight"] = _randn((1,), g, 0.3)
+        sd[f"{prefix}.activate.bias"] = _randn((cout,), g, 0.1)
+
+    def to_rgb(prefix, cin, up):
+        sd[f"{prefix}.bias"] = _randn((1, 3, 1, 1), g, 0.1)
+        if up:
+            sd[f"{prefix}.upsample.kernel"] = blur2 * 4.0
+        styled(prefix, cin, 3, 1, False)
+
+    conv_block("conv1", ch[4], ch[4], False)
+    to_rgb("to_rgb1", ch[4], False)
+    cin = ch[4]
+    for j, i in enumerate(range(3, log_size + 1)):
+        cout = ch[2 ** i]
+        conv_block(f"convs.{2 * j}", cin, cout, True)
+        conv_block(f"convs.{2 * j + 1}", cout, cout, False)
+        to_rgb(f"to_rgbs.{j}", cout, True)
+        cin = cout
+    num_layers = (log_size - 2) * 2 + 1
+    for layer_idx in range(num_layers):
+        res = (layer_idx + 5) // 2
+        sd[f"noises.noise_{layer_idx}"] = _randn((1, 1, 2 ** res, 2 ** res), g)
+    return sd

@@ -31,7 +31,8 @@ extern "C" {
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3 };
-enum ga_act { GA_ACT_NONE = 0, GA_ACT_SILU = 1, GA_ACT_ELU = 2, GA_ACT_RELU = 3 };
+enum ga_act { GA_ACT_NONE = 0, GA_ACT_SILU = 1, GA_ACT_ELU = 2, GA_ACT_RELU = 3,
+              GA_ACT_LRELU_SQRT2 = 4 /* leaky_relu(x, 0.2) * sqrt(2): fused_bias_act_kernel.cu:28-47 */ };
 /* epilogue multiplier modes (backward): multiply by the tensor itself, or by the ReLU / ELU derivative
  * reconstructed from the saved OUTPUT y of the forward activation (relu: y>0, elu: y>0 ? 1 : y+1) */
 enum ga_mul_mode { GA_MUL_VALUE = 0, GA_MUL_RELU_MASK = 1, GA_MUL_ELU_FROM_Y = 2 };
@@ -149,6 +150,24 @@ int ga_pgd_linf_step(float* x_adv, const float* grad, const float* x_nat, float 
 /* softmax cross-entropy: dlogits = (softmax - onehot)/n (mean reduction), loss[n], argmax==label counter */
 int ga_softmax_xent(const float* logits, const int64_t* labels, int n, int classes, float* loss, float* dlogits,
                     int32_t* pred, unsigned long long* n_correct /*device, accumulated*/, void* stream);
+
+/* ================================================================ StyleGAN2 generator pieces
+ * sm_100a replacements of the reference's only native kernels (stylegan2/op/fused_bias_act_kernel.cu,
+ * stylegan2/op/upfirdn2d_kernel.cu) and the glue of the modulated conv rewritten as activation scaling. */
+int ga_pixelnorm(const float* x, int rows, int d, const ga_tensor* out, void* stream);                  /* generator.py:10-15 */
+/* demod[n][co] = rsqrt(sum_ci s[n][ci]^2 * wsq[co][ci] + 1e-8)                                          generator.py:169-171 */
+int ga_style_demod(const float* s, const float* wsq, int n, int cin, int cout, float* demod, void* stream);
+int ga_channel_scale(const ga_tensor* x, const float* s /*[n][c]*/, const ga_tensor* out, void* stream); /* generator.py:164-167 */
+/* out = act(y * demod[n][c] + noise_w * noise[h][w] + bias[c]) (+ skip): StyledConv / ToRGB epilogue = fused_bias_act
+ * (generator.py:258-268,283-292).  phases=1: y = the 4 sub-pixel planes [4*n][h/2][w/2][c] of an up-sampling conv. */
+int ga_styled_bias_act(const ga_tensor* y, int phases, const float* demod, const float* noise_hw, float noise_w,
+                       const float* bias, int act, const ga_tensor* skip, const ga_tensor* out, void* stream);
+/* zero-insert up-sample -> pad -> FIR (flipped kernel) -> decimate, NHWC                                 op/upfirdn2d_kernel.cu:52-137 */
+int ga_upfirdn2d(const ga_tensor* in, const float* kernel, int kh, int kw, int up, int down, int pad0, int pad1,
+                 const ga_tensor* out, void* stream);
+int ga_avgpool_to_nchw(const ga_tensor* in, int k, int out_c, float* out_nchw, void* stream);           /* face_pool, psp.py:26,114 */
+int ga_latent_lerp(const float* codes, const float* styles, const float* alphas_dev, int b, int l, int d, float* out,
+                   void* stream);                                                                         /* models.py:123-124,338-339 */
 
 /* ================================================================ input-gradient (dgrad-only) backward pass
  * The attacks differentiate the logits w.r.t. the input batch only (untargeted.py:146,201): weights are frozen, no

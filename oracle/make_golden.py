@@ -113,6 +113,21 @@ def main():
                              "purified": pur, "logits": logits})
         print("c32", yml, pur.mean().item(), pur.std().item(), logits.abs().mean().item(), logits.argmax(1).tolist())
     torch.save(out, os.path.join(GOLDEN, "nvae_c32_vgg11.pt"))
+    # ---------------------------------------------------------------- StyleGAN2 generator (size 32, weights regenerated from the seed)
+    import importlib
+    gen = importlib.import_module("src.mlvgms_autoencoders.StyleGan_E4E.stylegan2.generator")
+    sd = synth.make_stylegan2_state_dict(32, seed=2)
+    G = gen.Generator(32, 512, 8, channel_multiplier=2).eval()
+    G.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(0)
+    latent = torch.randn(3, G.n_latent, 512, generator=g) * 0.7
+    z = torch.randn(G.n_latent, 3, 512, generator=g)
+    with torch.no_grad():
+        img, _ = G([latent], input_is_latent=True, randomize_noise=False)           # Generator.forward, generator.py:407-479
+        w = torch.stack([G.style(n) for n in z], dim=0)                              # models.py:120
+    torch.save({"seed": 2, "size": 32, "latent": latent, "z": z, "image": img, "image_pool2": torch.nn.functional.avg_pool2d(img, 2),
+                "w": w}, os.path.join(GOLDEN, "stylegan2_gen32.pt"))
+    print("stylegan2 gen32", img.abs().max().item(), img.std().item())
     shutil.rmtree(SCRATCH, ignore_errors=True)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))

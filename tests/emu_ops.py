@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from gen_adversarial_b200 import ops as real_ops
 from gen_adversarial_b200._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, \
-    MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
+    ACT_LRELU_SQRT2, MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
 
 ConvLayer = real_ops.ConvLayer
 gaussian_taps = real_ops.gaussian_taps
@@ -27,6 +27,8 @@ def _act(v, act):
         return F.elu(v)
     if act == ACT_RELU:
         return F.relu(v)
+    if act == ACT_LRELU_SQRT2:
+        return F.leaky_relu(v, 0.2) * (2 ** 0.5)
     return v
 
 
@@ -68,7 +70,7 @@ def _nhwc(x, dtype):
     return x.permute(0, 2, 3, 1).contiguous().to(dtype)
 
 
-def conv2d_simt(x, L, out_dtype, add=None, out_hw=None, mul=None, mul_mode=0, want_dact=False):
+def conv2d_simt(x, L, out_dtype, add=None, out_hw=None, mul=None, mul_mode=0, want_dact=False, out=None):
     _launches[0] += 1
     xin = _pre(x.float(), L)
     w = L.w_simt.float().view(L.kh, L.kw, L.cin, L.cout).permute(3, 2, 0, 1)
@@ -88,6 +90,9 @@ def conv2d_simt(x, L, out_dtype, add=None, out_hw=None, mul=None, mul_mode=0, wa
     if mul is not None:
         y = y * _mul_factor(mul, mul_mode)
     y = y.contiguous().to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        y = out
     if want_dact:
         return y, _act_grad(v, L.post_act).permute(0, 2, 3, 1).contiguous().to(out_dtype)
     return y
@@ -109,7 +114,8 @@ def conv2d_tc_supported(x, L, x2=None):
     return (h % rows == 0) if h >= rows else (rows % h == 0)
 
 
-def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None, mul_mode=0, dact_out=None):
+def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None, mul_mode=0, dact_out=None, out_bf16=None,
+              out_f32=None):
     _launches[0] += 1
     assert x.dtype == torch.bfloat16
     k1 = L.kh * L.kw * L.cin
@@ -131,7 +137,13 @@ def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None,
     if mul is not None:
         y = y * _mul_factor(mul, mul_mode)
     y = y.contiguous()
-    return (y.to(torch.bfloat16) if want_bf16 else None), (y if want_f32 else None)
+    ob = y.to(torch.bfloat16) if want_bf16 else None
+    of = y if want_f32 else None
+    if ob is not None and out_bf16 is not None:
+        out_bf16.copy_(ob); ob = out_bf16
+    if of is not None and out_f32 is not None:
+        out_f32.copy_(of); of = out_f32
+    return ob, of
 
 
 def dwconv5x5(x, weight, bias, act, up, out_dtype, mul=None, want_dact=False):
@@ -240,6 +252,59 @@ def preprocess(x_nchw, noise_nchw, eps, blur, out_dtype, seed=0, sample0=0, norm
     if normalize:
         x = (x - 0.5) * 2.0
     return _nhwc(x, out_dtype), pre
+
+
+# ------------------------------------------------------------------------------------------------ StyleGAN2 generator ops
+def pixelnorm(x, out_dtype):
+    _launches[0] += 1
+    y = x * torch.rsqrt(torch.mean(x ** 2, dim=1, keepdim=True) + 1e-8)
+    return y.view(x.shape[0], 1, 1, x.shape[1]).to(out_dtype)
+
+
+def style_demod(s, wsq):
+    _launches[0] += 1
+    return torch.rsqrt((s ** 2) @ wsq.t() + 1e-8)
+
+
+def channel_scale(x, s, out_dtype):
+    _launches[0] += 1
+    return (x.float() * s[:, None, None, :]).to(out_dtype)
+
+
+def styled_bias_act(y, phases, demod, noise_hw, noise_w, bias, act, skip, out_dtype):
+    _launches[0] += 1
+    v = y.float()
+    if phases:
+        n = v.shape[0] // 4
+        ph = v.view(2, 2, n, v.shape[1], v.shape[2], v.shape[3])        # [py, px, n, h, w, c]
+        v = ph.permute(2, 3, 0, 4, 1, 5).reshape(n, v.shape[1] * 2, v.shape[2] * 2, v.shape[3])
+    if demod is not None:
+        v = v * demod[:, None, None, :]
+    if noise_hw is not None:
+        v = v + noise_w * noise_hw.view(1, v.shape[1], v.shape[2], 1)
+    if bias is not None:
+        v = v + bias
+    v = _act(v, act)
+    if skip is not None:
+        v = v + skip.float()
+    return v.contiguous().to(out_dtype)
+
+
+def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0), out_dtype=None):
+    _launches[0] += 1
+    from oracle.ref_import import upfirdn2d_cpu
+    return _nhwc(upfirdn2d_cpu(_nchw(x), kernel.float(), up, down, pad), out_dtype or x.dtype)
+
+
+def avgpool_to_nchw(x, k, out_c):
+    _launches[0] += 1
+    return F.avg_pool2d(_nchw(x)[:, :out_c], k).contiguous()
+
+
+def latent_lerp(codes, styles, alphas_dev):
+    _launches[0] += 1
+    a = alphas_dev.view(1, -1, 1)
+    return (1 - a) * codes + a * styles
 
 
 # ------------------------------------------------------------------------------------------------ backward ops

@@ -1,0 +1,72 @@
+"""GPU: StyleGAN2 generator kernels (fused_bias_act / upfirdn2d replacements, modulation glue) against their torch
+restatements, and the generator engine against the fixture produced by the reference Generator."""
+import os
+
+import pytest
+import torch
+
+from gen_adversarial_b200 import ops, synth
+from gen_adversarial_b200._lib import ACT_NONE, ACT_LRELU_SQRT2
+from gen_adversarial_b200.stylegan_engine import StyleGan2Engine
+from tests import emu_ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stylegan2_gen32.pt")
+
+
+def test_pixelnorm_demod_scale_lerp():
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(37, 512, generator=g)
+    assert (ops.pixelnorm(z.to(DEV), torch.float32).cpu() - emu_ops.pixelnorm(z, torch.float32)).abs().max().item() <= 1e-5
+    s, wsq = torch.randn(3, 96, generator=g), torch.rand(40, 96, generator=g)
+    assert (ops.style_demod(s.to(DEV), wsq.to(DEV)).cpu() - emu_ops.style_demod(s, wsq)).abs().max().item() <= 1e-5
+    x = torch.randn(3, 8, 8, 96, generator=g)
+    assert (ops.channel_scale(x.to(DEV), s.to(DEV), torch.float32).cpu() - emu_ops.channel_scale(x, s, torch.float32)).abs().max().item() <= 1e-6
+    codes, styles, a = torch.randn(3, 6, 512, generator=g), torch.randn(3, 6, 512, generator=g), torch.rand(6, generator=g)
+    assert (ops.latent_lerp(codes.to(DEV), styles.to(DEV), a.to(DEV)).cpu() - emu_ops.latent_lerp(codes, styles, a)).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("phases", [False, True])
+def test_styled_bias_act(phases):
+    """fused demod + noise + bias + leaky_relu*sqrt(2) (= fused_bias_act_kernel.cu + NoiseInjection)"""
+    g = torch.Generator().manual_seed(1)
+    n, h, w, c = 2, 16, 16, 32
+    y = torch.randn((4 * n, h // 2, w // 2, c) if phases else (n, h, w, c), generator=g)
+    demod, noise, bias = torch.rand(n, c, generator=g) + 0.5, torch.randn(h, w, generator=g), torch.randn(c, generator=g)
+    skip = torch.randn(n, h, w, c, generator=g)
+    for act, d, nz, sk in ((ACT_LRELU_SQRT2, demod, noise, None), (ACT_NONE, None, None, skip)):
+        ref = emu_ops.styled_bias_act(y, phases, d, nz, 0.37, bias, act, sk, torch.float32)
+        got = ops.styled_bias_act(y.to(DEV), phases, d.to(DEV) if d is not None else None, nz.to(DEV) if nz is not None else None,
+                                  0.37, bias.to(DEV), act, sk.to(DEV) if sk is not None else None, torch.float32)
+        assert (got.cpu() - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("up,down,pad", [(1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (2, 2)), (1, 1, (2, 1))])
+def test_upfirdn2d_matches_reference_semantics(up, down, pad):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 9, 9, 4, generator=g)
+    k = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    k = (k[None] * k[:, None]); k = k / k.sum() * (up ** 2)
+    ref = emu_ops.upfirdn2d(x, k, up, down, pad, torch.float32)
+    got = ops.upfirdn2d(x.to(DEV), k.to(DEV), up, down, pad, torch.float32)
+    assert got.shape == ref.shape and (got.cpu() - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("bf16", 6e-2)])
+def test_generator_matches_reference_fixture(mode, tol):
+    """`Generator([latent], input_is_latent=True, randomize_noise=False)` + `Generator.style` of the reference (fixture)"""
+    g = torch.load(GOLDEN, weights_only=True)
+    sd = synth.make_stylegan2_state_dict(g["size"], seed=g["seed"])
+    eng = StyleGan2Engine(sd, g["size"], DEV, mode)
+    img = eng.decode(g["latent"].to(DEV), pool=1).cpu()
+    scale = g["image"].abs().max().item()
+    err = (img - g["image"]).abs().max().item()
+    w = eng.mapping(g["z"].reshape(-1, 512).to(DEV)).reshape(g["z"].shape).cpu()
+    werr = (w - g["w"]).abs().max().item()
+    print(f"[{mode}] generator@32: image max-abs err {err:.3e} (range {scale:.2f}); mapping err {werr:.3e} (range {g['w'].abs().max():.2f}); "
+          f"kernels {ops.launch_count(True)}")
+    assert err <= tol * scale
+    assert werr <= tol * max(1.0, g["w"].abs().max().item())
+    pooled = eng.decode(g["latent"].to(DEV), pool=2).cpu()
+    assert (pooled - g["image_pool2"]).abs().max().item() <= tol * scale
