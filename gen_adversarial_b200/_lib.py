@@ -21,8 +21,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libga_b200.so")
 HEADER = os.path.join(ROOT_DIR, "include", "ga_b200.h")
 
 GA_F32, GA_BF16 = 0, 1
-PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU = 0, 1, 2, 3
-ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, ACT_LRELU_SQRT2 = 0, 1, 2, 3, 4
+PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, PRE_AFFINE = 0, 1, 2, 3, 4
+ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, ACT_LRELU_SQRT2, ACT_PRELU = 0, 1, 2, 3, 4, 5
 MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y = 0, 1, 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -39,7 +39,7 @@ class GaConvDesc(ctypes.Structure):
                 ("pre_scale", c_void_p), ("pre_shift", c_void_p), ("weight", c_void_p), ("bias", c_void_p),
                 ("reserved0", c_int32), ("ktot", c_int32),
                 ("mul", c_void_p), ("mul_dtype", c_int32), ("mul_mode", c_int32),
-                ("dact_out", c_void_p), ("dact_dtype", c_int32), ("reserved1", c_int32)]
+                ("dact_out", c_void_p), ("dact_dtype", c_int32), ("act_after_add", c_int32), ("act_slope", c_void_p)]
 
 
 def sources():
@@ -113,6 +113,9 @@ _PROTOS = {
     "ga_upsample_bilinear2x": (c_int, [T, T, c_void_p]),
     "ga_maxpool2x2": (c_int, [T, T, c_void_p]),
     "ga_cast": (c_int, [T, T, c_void_p]),
+    "ga_subsample2x": (c_int, [T, T, c_void_p]),
+    "ga_maxpool3x3s2": (c_int, [T, T, c_void_p]),
+    "ga_global_avgpool": (c_int, [T, T, c_void_p]),
     "ga_affine_act": (c_int, [T, c_void_p, c_void_p, c_int, T, c_void_p]),
     "ga_nchw_to_nhwc": (c_int, [c_void_p, T, c_float, c_float, c_void_p]),
     "ga_pixelnorm": (c_int, [c_void_p, c_int, c_int, T, c_void_p]),
@@ -143,7 +146,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 2:
+    if L.ga_abi_version() != 3:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -31,6 +31,7 @@ struct ConvParams {
   int add_dtype;
   const void* mul; int mul_dtype, mul_mode;
   void* dact; int dact_dtype;
+  const float* act_slope; int act_after_add;
   int64_t M;
 };
 
@@ -42,6 +43,7 @@ __device__ __forceinline__ float pre_apply(float v, int pre_op, float sc, float 
     case GA_PRE_ELU: return eluf_(v);
     case GA_PRE_SILU: return siluf_(v);
     case GA_PRE_AFFINE_SILU: return siluf_(fmaf(v, sc, sh));
+    case GA_PRE_AFFINE: return fmaf(v, sc, sh);
     default: return v;
   }
 }
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float sc = 1.f, sh = 0.f;
-          if (p.pre_op == GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
+          if (p.pre_op >= GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
           av[j] = pre_apply(av[j], p.pre_op, sc, sh);
         }
       }
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
         if (pix_ok && ca + j < p.Cin) {
           v = load_in<TIn>(src + ca + j);
           float sc = 1.f, sh = 0.f;
-          if (p.pre_op == GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
+          if (p.pre_op >= GA_PRE_AFFINE_SILU) { sc = p.pre_scale[ca + j]; sh = p.pre_shift[ca + j]; }
           v = pre_apply(v, p.pre_op, sc, sh);
         }
         av[j] = v;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
     for (int j = 0; j < 4; ++j)
       if (nb + j < p.Cout) bias4[j] = p.bias[nb + j];
   }
-  const bool extras = (p.mul != nullptr) || (p.dact != nullptr);
+  const bool extras = (p.mul != nullptr) || (p.dact != nullptr) || p.post_act == GA_ACT_PRELU || p.act_after_add;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t m = m0 + ty * 8 + i;
@@ -190,10 +192,12 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
           if (p.dact_dtype == GA_F32) reinterpret_cast<float*>(p.dact)[off + j] = dv;
           else reinterpret_cast<__nv_bfloat16*>(p.dact)[off + j] = __float2bfloat16_rn(dv);
         }
-        float r = apply_act(pre, p.post_act);
+        const float slope = p.act_slope != nullptr ? p.act_slope[nb + j] : 0.f;
+        float r = p.act_after_add ? pre : apply_act_s(pre, p.post_act, slope);
         if (p.add != nullptr)
           r += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
                                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
+        if (p.act_after_add) r = apply_act_s(r, p.post_act, slope);
         if (p.mul != nullptr) {
           const float mv = (p.mul_dtype == GA_F32) ? reinterpret_cast<const float*>(p.mul)[off + j]
                                                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mul)[off + j]);
@@ -310,11 +314,12 @@ extern "C" int ga_conv2d_simt(const ga_tensor* in, const ga_conv_desc* d, const 
                (out->w == Wo || (d->up > 1 && out->w == Wo + 1)),
            "ga_conv2d_simt: output shape (%d,%d,%d) does not match conv geometry (%d,%d,%d)", out->n, out->h, out->w,
            in->n, Ho, Wo);
-  GA_CHECK(d->pre_op != GA_PRE_AFFINE_SILU || (d->pre_scale && d->pre_shift), "ga_conv2d_simt: affine pre-op needs scale/shift");
+  GA_CHECK(d->pre_op < GA_PRE_AFFINE_SILU || (d->pre_scale && d->pre_shift), "ga_conv2d_simt: affine pre-op needs scale/shift");
   if (add) GA_CHECK(same_shape(add, out), "ga_conv2d_simt: add shape mismatch");
   // stem fast path: 3x3 / stride 1 / pad 1 / Cin <= 4 / no extras
   if (d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && d->up == 1 && in->c <= 4 && (out->c % 8) == 0 && out->c <= 256 &&
-      d->pre_op == GA_PRE_NONE && add == nullptr && d->mul == nullptr && d->dact_out == nullptr && numel(out) > 0) {
+      d->pre_op == GA_PRE_NONE && add == nullptr && d->mul == nullptr && d->dact_out == nullptr && d->post_act != GA_ACT_PRELU &&
+      !d->act_after_add && numel(out) > 0) {
     cudaStream_t s = (cudaStream_t)stream;
     if (in->dtype == GA_F32 && out->dtype == GA_F32) return launch_stem<float, float>(in, d, out, s);
     if (in->dtype == GA_BF16 && out->dtype == GA_BF16) return launch_stem<__nv_bfloat16, __nv_bfloat16>(in, d, out, s);
@@ -327,6 +332,8 @@ extern "C" int ga_conv2d_simt(const ga_tensor* in, const ga_conv_desc* d, const 
   p.add = add ? add->data : nullptr; p.add_dtype = add ? add->dtype : GA_F32;
   p.mul = d->mul; p.mul_dtype = d->mul_dtype; p.mul_mode = d->mul_mode;
   p.dact = d->dact_out; p.dact_dtype = d->dact_dtype;
+  p.act_slope = d->act_slope; p.act_after_add = d->act_after_add;
+  GA_CHECK(d->post_act != GA_ACT_PRELU || d->act_slope != nullptr, "ga_conv2d_simt: PReLU needs act_slope");
   p.out = out->data;
   p.N = in->n; p.H = in->h; p.W = in->w; p.Cin = in->c; p.Ho = out->h; p.Wo = out->w; p.Cout = out->c;
   p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->pad; p.up = d->up;

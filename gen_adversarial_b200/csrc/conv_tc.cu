@@ -43,7 +43,9 @@ struct TcParams {
   float* out_f32;
   int tma_store;              // 1: epilogue stages the tile in (swizzled) shared memory and TMA-stores it
   const void* mul; int mul_dtype, mul_mode;   // backward: out = (act(acc+bias) + add) * f(mul)
-  __nv_bfloat16* dact;        // taping forward: derivative of post_act at the pre-activation (bf16, direct stores)
+  __nv_bfloat16* dact;        // taping forward: derivative of post_act at the pre-activation (bf16)
+  const float* act_slope;     // PReLU slopes [cout]
+  int act_after_add;          // act(acc + bias + add)
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -147,14 +149,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on a 1024 B boundary
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem = smem_hdr + 2048;                   // operand ring / epilogue staging (1024-aligned)
+  uint8_t* smem = smem_hdr + 4096;                   // operand ring / epilogue staging (1024-aligned)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * TC_A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_hdr);   // header: barriers, TMEM address; bias tile after the ring
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(smem_hdr + 128);      // header (2 KB): 128 B of barriers + up to 1 KB of bias
+  float* s_slope = reinterpret_cast<float*>(smem_hdr + 128 + 1024);
+  float* s_bias = reinterpret_cast<float*>(smem_hdr + 128);      // header (4 KB): 128 B of barriers + up to 1 KB of bias + up to 1 KB of PReLU slopes
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     for (int i = et; i < BLOCK_N; i += 128) {
       const int n = n_blk * BLOCK_N + i;
       s_bias[i] = (p.bias != nullptr && n < p.cout) ? p.bias[n] : 0.f;
+      s_slope[i] = (p.act_slope != nullptr && n < p.cout) ? p.act_slope[n] : 0.f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
@@ -295,7 +299,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = apply_act_fast(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
+      for (int j = 0; j < 16; ++j) {
+        const float pre = __uint_as_float(r[j]) + s_bias[c0 + j];
+        v[j] = p.act_after_add ? pre : (p.post_act == GA_ACT_PRELU ? (pre > 0.f ? pre : s_slope[c0 + j] * pre) : apply_act_fast(pre, p.post_act));
+      }
       if (p.add != nullptr && row_ok) {
         if (full) {
           if (p.add_dtype == GA_F32) {
@@ -322,6 +329,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
               v[j] += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
         }
+      }
+      if (p.act_after_add) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = p.post_act == GA_ACT_PRELU ? (v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j]) : apply_act_fast(v[j], p.post_act);
       }
       if (p.mul != nullptr && row_ok && full) {
         float mv[16];
@@ -502,7 +514,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
                      const CUtensorMap& od, const TcParams& p, dim3 grid, cudaStream_t s) {
   constexpr int ring = STAGES * (TC_A_STAGE_BYTES + BLOCK_N * TC_BLOCK_K * 2);
   constexpr int max_staging = 2 * ((BLOCK_N + 63) / 64) * 16384 + (BLOCK_N / 32) * 16384;
-  constexpr int max_smem = 1024 /*align*/ + 2048 /*header*/ + (ring > max_staging ? ring : max_staging);
+  constexpr int max_smem = 1024 /*align*/ + 4096 /*header*/ + (ring > max_staging ? ring : max_staging);
   static bool configured = false;
   if (!configured) {
     GA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -511,7 +523,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
   }
   int staging = 0;
   if (p.tma_store) staging = ((p.out_bf16 ? 1 : 0) + (p.dact ? 1 : 0)) * ((BLOCK_N + 63) / 64) * 16384 + (p.out_f32 ? (BLOCK_N / 32) * 16384 : 0);
-  const int smem = 1024 + 2048 + (ring > staging ? ring : staging);
+  const int smem = 1024 + 4096 + (ring > staging ? ring : staging);
   GA_CHECK(smem <= 227 * 1024, "conv_tc: shared memory request %d too large", smem);
   conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, od, p);
   GA_LAUNCH_OK();
@@ -585,6 +597,8 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.mul = d->mul; p.mul_dtype = d->mul_dtype; p.mul_mode = d->mul_mode;
   GA_CHECK(d->dact_out == nullptr || d->dact_dtype == GA_BF16, "ga_conv2d_tc: dact_out must be bf16");
   p.dact = (__nv_bfloat16*)d->dact_out;
+  p.act_slope = d->act_slope; p.act_after_add = d->act_after_add;
+  GA_CHECK(d->post_act != GA_ACT_PRELU || d->act_slope != nullptr, "ga_conv2d_tc: PReLU needs act_slope");
   dim3 grid((unsigned)g.m_tiles, (unsigned)((out->c + block_n - 1) / block_n));
   cudaStream_t s = (cudaStream_t)stream;
   // TMA-store epilogue needs 16-byte aligned row pitches and bases; tiny / odd Cout falls back to direct stores

@@ -509,6 +509,59 @@ __global__ void maxpool2x2_kernel(const void* in, int in_dtype, void* out, int o
   st4d(out, out_dtype, ((n * Ho + y) * Wo + x) * C + c, o);
 }
 
+// x[:, ::2, ::2, :]  (nn.MaxPool2d(1, 2) shortcut of the IR-SE50 bottlenecks, encoding/helpers.py:95-96)
+__global__ void subsample2x_kernel(const void* in, int in_dtype, void* out, int out_dtype, int N, int H, int W, int C) {
+  const int c4n = C >> 2;
+  const int Ho = (H + 1) >> 1, Wo = (W + 1) >> 1;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * Ho * Wo * c4n) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int x = (int)(t % Wo); t /= Wo;
+  const int y = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  float v[4];
+  ld4d(in, in_dtype, ((n * H + 2 * y) * W + 2 * x) * C + c, v);
+  st4d(out, out_dtype, ((n * Ho + y) * Wo + x) * C + c, v);
+}
+
+// 3x3 max-pool, stride 2, pad 1 (torchvision ResNet stem)
+__global__ void maxpool3x3s2_kernel(const void* in, int in_dtype, void* out, int out_dtype, int N, int H, int W, int C) {
+  const int c4n = C >> 2;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * Ho * Wo * c4n) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int x = (int)(t % Wo); t /= Wo;
+  const int y = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = 2 * y + dy;
+    if (iy < 0 || iy >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = 2 * x + dx;
+      if (ix < 0 || ix >= W) continue;
+      float v[4];
+      ld4d(in, in_dtype, ((n * H + iy) * W + ix) * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+  }
+  st4d(out, out_dtype, ((n * Ho + y) * Wo + x) * C + c, m);
+}
+
+// global average pool: one block per image, fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) global_avgpool_kernel(const void* in, int in_dtype, int HW, int C, void* out, int out_dtype) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float acc = 0.f;
+    for (int p = 0; p < HW; ++p) acc += ld1d(in, in_dtype, ((int64_t)n * HW + p) * C + c);
+    st1d(out, out_dtype, (int64_t)n * C + c, acc / (float)HW);
+  }
+}
+
 __global__ void affine_act_kernel(const void* in, int in_dtype, const float* __restrict__ scale, const float* __restrict__ shift,
                                   int act, void* out, int out_dtype, int C, int64_t total) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -787,6 +840,34 @@ extern "C" int ga_maxpool2x2(const ga_tensor* in, const ga_tensor* out, void* st
   const int64_t total = numel(out) / 4;
   if (total == 0) return 0;
   maxpool2x2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, out->data, out->dtype, in->n, in->h, in->w, in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_subsample2x(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && out->h == (in->h + 1) / 2 && out->w == (in->w + 1) / 2 && out->c == in->c && out->n == in->n && (in->c % 4) == 0,
+           "ga_subsample2x: shape mismatch");
+  const int64_t total = numel(out) / 4;
+  if (total == 0) return 0;
+  subsample2x_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, out->data, out->dtype, in->n, in->h, in->w, in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_maxpool3x3s2(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && out->h == (in->h - 1) / 2 + 1 && out->w == (in->w - 1) / 2 + 1 && out->c == in->c && out->n == in->n && (in->c % 4) == 0,
+           "ga_maxpool3x3s2: shape mismatch");
+  const int64_t total = numel(out) / 4;
+  if (total == 0) return 0;
+  maxpool3x3s2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, out->data, out->dtype, in->n, in->h, in->w, in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_global_avgpool(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && out->n == in->n && out->h == 1 && out->w == 1 && out->c == in->c, "ga_global_avgpool: shape mismatch");
+  if (numel(in) == 0) return 0;
+  global_avgpool_kernel<<<in->n, 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, in->h * in->w, in->c, out->data, out->dtype);
   GA_LAUNCH_OK();
   return 0;
 }

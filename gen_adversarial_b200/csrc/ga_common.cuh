@@ -59,6 +59,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     default: return v;
   }
 }
+// activation with per-channel slope (PReLU); other codes ignore `slope`
+__device__ __forceinline__ float apply_act_s(float v, int act, float slope) {
+  return act == GA_ACT_PRELU ? (v > 0.0f ? v : slope * v) : apply_act(v, act);
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

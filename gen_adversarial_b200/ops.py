@@ -121,6 +121,8 @@ class ConvLayer:
     post_act: int = ACT_NONE
     up: int = 1
     cin2: int = 0                              # channels of the second (1x1) K source folded into w_tc
+    act_slope: Optional[torch.Tensor] = None   # fp32 [cout] negative slopes (ACT_PRELU)
+    act_after_add: bool = False                # out = act(conv + bias + add)
     name: str = ""
 
     def desc(self, tc: bool, mul=None, mul_mode: int = 0, dact=None) -> GaConvDesc:
@@ -131,7 +133,7 @@ class ConvLayer:
                           ptr(self.pre_scale), ptr(self.pre_shift), w.data_ptr(), ptr(self.bias), 0,
                           w.shape[1] if tc else 0,
                           ptr(mul), _dt(mul) if mul is not None else 0, mul_mode,
-                          ptr(dact), _dt(dact) if dact is not None else 0, 0)
+                          ptr(dact), _dt(dact) if dact is not None else 0, int(self.act_after_add), ptr(self.act_slope))
 
 
 def conv_out_hw(L: ConvLayer, h: int, w: int):
@@ -266,6 +268,30 @@ def maxpool2x2(x, out_dtype=None):
     n, h, w, c = x.shape
     out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=out_dtype or x.dtype)
     _lib.check(_lib.lib().ga_maxpool2x2(gt(x), gt(out), stream()), "maxpool2x2")
+    return out
+
+
+@_timed("subsample2x")
+def subsample2x(x, out_dtype=None):
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h + 1) // 2, (w + 1) // 2, c), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().ga_subsample2x(gt(x), gt(out), stream()), "subsample2x")
+    return out
+
+
+@_timed("maxpool3x3s2")
+def maxpool3x3s2(x, out_dtype=None):
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().ga_maxpool3x3s2(gt(x), gt(out), stream()), "maxpool3x3s2")
+    return out
+
+
+@_timed("global_avgpool")
+def global_avgpool(x, out_dtype=None):
+    n, h, w, c = x.shape
+    out = torch.empty((n, 1, 1, c), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().ga_global_avgpool(gt(x), gt(out), stream()), "global_avgpool")
     return out
 
 

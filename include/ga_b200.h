@@ -27,12 +27,13 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 2
+#define GA_ABI_VERSION 3
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
-enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3 };
+enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3, GA_PRE_AFFINE = 4 };
 enum ga_act { GA_ACT_NONE = 0, GA_ACT_SILU = 1, GA_ACT_ELU = 2, GA_ACT_RELU = 3,
-              GA_ACT_LRELU_SQRT2 = 4 /* leaky_relu(x, 0.2) * sqrt(2): fused_bias_act_kernel.cu:28-47 */ };
+              GA_ACT_LRELU_SQRT2 = 4 /* leaky_relu(x, 0.2) * sqrt(2): fused_bias_act_kernel.cu:28-47 */,
+              GA_ACT_PRELU = 5 /* x > 0 ? x : act_slope[c] * x (nn.PReLU / nn.LeakyReLU of the IR-SE50 encoder) */ };
 /* epilogue multiplier modes (backward): multiply by the tensor itself, or by the ReLU / ELU derivative
  * reconstructed from the saved OUTPUT y of the forward activation (relu: y>0, elu: y>0 ? 1 : y+1) */
 enum ga_mul_mode { GA_MUL_VALUE = 0, GA_MUL_RELU_MASK = 1, GA_MUL_ELU_FROM_Y = 2 };
@@ -64,7 +65,8 @@ typedef struct ga_conv_desc {
   int32_t mul_mode;       /* ga_mul_mode */
   void* dact_out;         /* optional: derivative of post_act at the pre-activation, saved for the backward pass */
   int32_t dact_dtype;
-  int32_t reserved1;
+  int32_t act_after_add;  /* 1: out = act(acc + bias + add) (ResNet bottleneck) instead of act(acc + bias) + add */
+  const float* act_slope; /* [cout] negative slopes for GA_ACT_PRELU */
 } ga_conv_desc;
 
 const char* ga_last_error(void);
@@ -138,6 +140,9 @@ int ga_discmix_mean_fwd(const ga_tensor* logits, int n_mix, float* purified_nchw
 int ga_upsample_nearest2x(const ga_tensor* in, const ga_tensor* out, void* stream);           /* architecture.py:162 */
 int ga_upsample_bilinear2x(const ga_tensor* in, const ga_tensor* out, void* stream);          /* architecture.py:91 (align_corners=True) */
 int ga_maxpool2x2(const ga_tensor* in, const ga_tensor* out, void* stream);                   /* torchvision vgg11_bn 'M' */
+int ga_subsample2x(const ga_tensor* in, const ga_tensor* out, void* stream);                  /* nn.MaxPool2d(1, 2): encoding/helpers.py:95-96 */
+int ga_maxpool3x3s2(const ga_tensor* in, const ga_tensor* out, void* stream);                 /* torchvision resnet stem pool */
+int ga_global_avgpool(const ga_tensor* in, const ga_tensor* out, void* stream);               /* AdaptiveAvgPool2d(1) */
 int ga_cast(const ga_tensor* in, const ga_tensor* out, void* stream);                         /* dtype cast / copy */
 int ga_affine_act(const ga_tensor* in, const float* scale, const float* shift, int act, const ga_tensor* out,
                   void* stream);                                                               /* folded BN + act */

@@ -11,8 +11,8 @@ import torch
 import torch.nn.functional as F
 
 from gen_adversarial_b200 import ops as real_ops
-from gen_adversarial_b200._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU, \
-    ACT_LRELU_SQRT2, MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
+from gen_adversarial_b200._lib import PRE_NONE, PRE_ELU, PRE_SILU, PRE_AFFINE_SILU, PRE_AFFINE, ACT_NONE, ACT_SILU, ACT_ELU, \
+    ACT_RELU, ACT_LRELU_SQRT2, ACT_PRELU, MUL_VALUE, MUL_RELU_MASK, MUL_ELU_FROM_Y
 
 ConvLayer = real_ops.ConvLayer
 gaussian_taps = real_ops.gaussian_taps
@@ -59,7 +59,26 @@ def _pre(x, L):
         return F.silu(x)
     if L.pre_op == PRE_AFFINE_SILU:
         return F.silu(x * L.pre_scale + L.pre_shift)
+    if L.pre_op == PRE_AFFINE:
+        return x * L.pre_scale + L.pre_shift
     return x
+
+
+def _epilogue(v_nchw, L, add, mul, mul_mode):
+    """out = (act(v) + add) * f(mul), or act(v + add) with act_after_add; PReLU uses the per-channel slopes"""
+    def act(t):
+        if L.post_act == ACT_PRELU:
+            return torch.where(t > 0, t, t * L.act_slope.float().view(1, -1, 1, 1))
+        return _act(t, L.post_act)
+    y = v_nchw if L.act_after_add else act(v_nchw)
+    y = y.permute(0, 2, 3, 1)
+    if add is not None:
+        y = y + add.float()
+    if L.act_after_add:
+        y = act(y.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    if mul is not None:
+        y = y * _mul_factor(mul, mul_mode)
+    return y.contiguous()
 
 
 def _nchw(x):
@@ -84,12 +103,7 @@ def conv2d_simt(x, L, out_dtype, add=None, out_hw=None, mul=None, mul_mode=0, wa
             ho, wo = conv_out_hw(L, h, wd)
             xn = F.pad(xn, (0, out_hw[1] - wo, 0, out_hw[0] - ho))
     v = F.conv2d(xn, w, L.bias.float() if L.bias is not None else None, stride=L.stride, padding=L.pad)
-    y = _act(v, L.post_act).permute(0, 2, 3, 1)
-    if add is not None:
-        y = y + add.float()
-    if mul is not None:
-        y = y * _mul_factor(mul, mul_mode)
-    y = y.contiguous().to(out_dtype)
+    y = _epilogue(v, L, add, mul, mul_mode).to(out_dtype)
     if out is not None:
         out.copy_(y)
         y = out
@@ -131,12 +145,7 @@ def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None,
         y = y + L.bias.float().view(1, -1, 1, 1)
     if dact_out is not None:
         dact_out.copy_(_act_grad(y, L.post_act).permute(0, 2, 3, 1))
-    y = _act(y, L.post_act).permute(0, 2, 3, 1)
-    if add is not None:
-        y = y + add.float()
-    if mul is not None:
-        y = y * _mul_factor(mul, mul_mode)
-    y = y.contiguous()
+    y = _epilogue(y, L, add, mul, mul_mode)
     ob = y.to(torch.bfloat16) if want_bf16 else None
     of = y if want_f32 else None
     if ob is not None and out_bf16 is not None:
@@ -218,6 +227,21 @@ def upsample_bilinear2x(x, out_dtype=None):
 def maxpool2x2(x, out_dtype=None):
     _launches[0] += 1
     return _nhwc(F.max_pool2d(_nchw(x), 2), out_dtype or x.dtype)
+
+
+def subsample2x(x, out_dtype=None):
+    _launches[0] += 1
+    return x[:, ::2, ::2, :].contiguous().to(out_dtype or x.dtype)
+
+
+def maxpool3x3s2(x, out_dtype=None):
+    _launches[0] += 1
+    return _nhwc(F.max_pool2d(_nchw(x), 3, 2, 1), out_dtype or x.dtype)
+
+
+def global_avgpool(x, out_dtype=None):
+    _launches[0] += 1
+    return x.float().mean(dim=(1, 2), keepdim=True).to(out_dtype or x.dtype)
 
 
 def affine_act(x, scale, shift, act, out_dtype):
