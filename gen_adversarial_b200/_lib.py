@@ -55,16 +55,34 @@ def _stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> gen_adversarial_b200/libga_b200.so (in-tree)."""
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> gen_adversarial_b200/libga_b200.so (in-tree).
+    Every .cu is compiled to its own object (in parallel, cached by mtime under csrc/_build/) and linked with nvcc -shared."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    obj_dir = os.path.join(CSRC_DIR, "_build")
+    os.makedirs(obj_dir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC_DIR, "*.cuh")) + [HEADER])
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""
+        cmd = [nvcc] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
     if verbose:
-        print(res.stderr)
+        print("".join(r[1] for r in results))
+    res = subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + [r[0] for r in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 
@@ -106,7 +124,14 @@ _PROTOS = {
     "ga_latent_mix_bwd": (c_int, [T, T, T, c_void_p, c_uint64, c_int, c_int64, c_void_p, c_float, c_int, T, T, c_void_p]),
     "ga_discmix_mean_bwd": (c_int, [T, c_int, c_void_p, T, T, c_void_p]),
     "ga_se_residual_fwd": (c_int, [T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, T, T, T, T,
-                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ga_add_layernorm": (c_int, [T, T, c_void_p, c_void_p, c_float, T, T, c_void_p]),
+    "ga_attention_ws_floats": (c_int64, [c_int, c_int, c_int, c_int]),
+    "ga_attention": (c_int, [T, c_int, T, c_int, T, c_int, c_int, c_int, c_void_p, T, c_void_p]),
+    "ga_codes_assemble": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ga_resize_bilinear": (c_int, [T, c_int, c_int, T, c_void_p]),
+    "ga_image_pool_out": (c_int, [T, c_int, c_int, c_int, c_float, c_float, c_void_p, T, c_void_p]),
+    "ga_philox_codes": (c_int, [c_uint64, c_int64, c_float, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ga_latent_mix_fwd": (c_int, [T, T, c_void_p, c_uint64, c_int, c_int64, c_void_p, c_float, c_int, T, c_void_p]),
     "ga_discmix_mean_fwd": (c_int, [T, c_int, c_void_p, T, c_void_p]),
     "ga_upsample_nearest2x": (c_int, [T, T, c_void_p]),
@@ -146,7 +171,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 3:
+    if L.ga_abi_version() != 4:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -29,7 +29,7 @@ constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 constexpr int TC_THREADS = 192;
 
 struct TcParams {
-  int taps, kw, pad;          // filter taps of source 1
+  int taps, kw, pad, stride;  // filter taps of source 1; stride 1 or 2 (TMA element strides do the decimation)
   int cin, kc1, kc2;          // channels of source 1, its 64-blocks per tap, 64-blocks of source 2
   int bw, bh, bn;             // pixel box of one M tile (bw*bh*bn == 128)
   int tiles_x, tiles_y;       // tiles per image row / column (bn == 1) -- else whole images per tile
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         if (kb < p.taps * p.kc1) {
           const int tap = kb / p.kc1, cc = kb - tap * p.kc1;
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
-          tma_load_4d(&tmA, &full_bar[stage], a_dst, cc * TC_BLOCK_K, x0 + kx - p.pad, y0 + ky - p.pad, n0);
+          tma_load_4d(&tmA, &full_bar[stage], a_dst, cc * TC_BLOCK_K, x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, n0);
           kcoord = tap * p.cin + cc * TC_BLOCK_K;
         } else {
           const int cc = kb - p.taps * p.kc1;
@@ -467,13 +467,15 @@ static bool tile_geometry(int N, int H, int W, TileGeom* g) {
   return true;
 }
 
-static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g) {
+static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g, int stride = 1) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
   cuuint64_t strides[3] = {(cuuint64_t)t->c * 2, (cuuint64_t)t->w * t->c * 2, (cuuint64_t)t->h * t->w * t->c * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // stride-2 convs: the box spans stride*bw x stride*bh input pixels and the TMA engine keeps every stride-th one
+  // (ceil(box/elementStride) elements per dimension land in shared memory)
+  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(g.bw * stride), (cuuint32_t)(g.bh * stride), (cuuint32_t)g.bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d box=%d,%d,%d) failed: %d", t->n, t->h, t->w, t->c,
@@ -549,12 +551,13 @@ using namespace ga;
 extern "C" int ga_conv2d_tc_supported(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, int cout) {
   if (!in || !d) return 0;
   if (in->dtype != GA_BF16) return 0;
-  if (d->stride != 1 || d->up != 1 || d->pre_op != GA_PRE_NONE) return 0;
+  if ((d->stride != 1 && d->stride != 2) || d->up != 1 || d->pre_op != GA_PRE_NONE) return 0;
   if (!((d->kh == 1 && d->kw == 1 && d->pad == 0) || (d->kh == 3 && d->kw == 3 && d->pad == 1))) return 0;
   if (in->c % 8 != 0 || cout < 1) return 0;
-  if (in2 && (in2->dtype != GA_BF16 || in2->c % 8 != 0 || in2->n != in->n || in2->h != in->h || in2->w != in->w)) return 0;
+  if (in2 && (d->stride != 1 || in2->dtype != GA_BF16 || in2->c % 8 != 0 || in2->n != in->n || in2->h != in->h || in2->w != in->w)) return 0;
   TileGeom g;
-  if (!tile_geometry(in->n, in->h, in->w, &g)) return 0;
+  const int Ho = (in->h + 2 * d->pad - d->kh) / d->stride + 1, Wo = (in->w + 2 * d->pad - d->kw) / d->stride + 1;
+  if (!tile_geometry(in->n, Ho, Wo, &g)) return 0;
   if ((((uintptr_t)in->data) & 15) != 0) return 0;
   return 1;
 }
@@ -565,7 +568,8 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   const ga_tensor* out = out_bf16 ? out_bf16 : out_f32;
   GA_CHECK(ga_conv2d_tc_supported(in, in2, d, out->c), "ga_conv2d_tc: unsupported problem (n=%d h=%d w=%d cin=%d k=%d stride=%d pre=%d)",
            in->n, in->h, in->w, in->c, d->kh, d->stride, d->pre_op);
-  GA_CHECK(out->n == in->n && out->h == in->h && out->w == in->w, "ga_conv2d_tc: output spatial shape mismatch");
+  const int Ho = (in->h + 2 * d->pad - d->kh) / d->stride + 1, Wo = (in->w + 2 * d->pad - d->kw) / d->stride + 1;
+  GA_CHECK(out->n == in->n && out->h == Ho && out->w == Wo, "ga_conv2d_tc: output spatial shape mismatch");
   GA_CHECK(!out_bf16 || out_bf16->dtype == GA_BF16, "ga_conv2d_tc: out_bf16 must be bf16");
   GA_CHECK(!out_f32 || out_f32->dtype == GA_F32, "ga_conv2d_tc: out_f32 must be fp32");
   GA_CHECK(!(out_bf16 && out_f32) || same_shape(out_bf16, out_f32), "ga_conv2d_tc: the two outputs differ in shape");
@@ -577,19 +581,19 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   if (numel(out) == 0) return 0;
 
   TileGeom g;
-  tile_geometry(in->n, in->h, in->w, &g);
+  tile_geometry(in->n, Ho, Wo, &g);
   const int block_n = pick_block_n(out->c);
   CUtensorMap tmA, tmA2, tmB;
-  if (encode_act_map(&tmA, in, g)) return 1;
+  if (encode_act_map(&tmA, in, g, d->stride)) return 1;
   if (in2) { if (encode_act_map(&tmA2, in2, g)) return 1; }
   else tmA2 = tmA;
   if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n)) return 1;
 
   TcParams p;
-  p.taps = taps; p.kw = d->kw; p.pad = d->pad;
+  p.taps = taps; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
   p.cin = in->c; p.kc1 = (in->c + TC_BLOCK_K - 1) / TC_BLOCK_K; p.kc2 = in2 ? (in2->c + TC_BLOCK_K - 1) / TC_BLOCK_K : 0;
   p.bw = g.bw; p.bh = g.bh; p.bn = g.bn; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
-  p.H = in->h; p.W = in->w; p.M = (int64_t)in->n * in->h * in->w;
+  p.H = Ho; p.W = Wo; p.M = (int64_t)in->n * Ho * Wo;
   p.cout = out->c; p.bias = d->bias; p.post_act = d->post_act;
   p.add = add ? add->data : nullptr; p.add_dtype = add ? add->dtype : GA_F32;
   p.out_bf16 = out_bf16 ? (__nv_bfloat16*)out_bf16->data : nullptr;

@@ -268,7 +268,7 @@ struct SeParams {
   const void* skip; int skip_dtype;
   void* out; int out_dtype;
   void* out2; int out2_dtype;
-  void* act; int act_dtype; const float* act_scale; const float* act_shift;
+  void* act; int act_dtype; const float* act_scale; const float* act_shift; int act_op;
   float* gate_out;
   int HW, C, pix_per_block, nparts;
 };
@@ -291,11 +291,11 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
     float a = 0.f;
     for (int c = lane; c < p.C; c += 32) a = fmaf(p.w1[(int64_t)j * p.C + c], s_mean[c], a);
     a = warp_sum(a);
-    if (lane == 0) s_hid[j] = fmaxf(a + p.b1[j], 0.f);
+    if (lane == 0) s_hid[j] = fmaxf(a + (p.b1 != nullptr ? p.b1[j] : 0.f), 0.f);
   }
   __syncthreads();
   for (int c = tid; c < p.C; c += 256) {
-    float a = p.b2[c];
+    float a = p.b2 != nullptr ? p.b2[c] : 0.f;
     for (int j = 0; j < p.hidden; ++j) a = fmaf(p.w2[(int64_t)c * p.hidden + j], s_hid[j], a);
     float g = sigmoidf_(a);
     s_gate[c] = g;
@@ -334,7 +334,10 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
       if (p.act != nullptr) {
         float a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = silu_fast(fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]));
+        for (int j = 0; j < 4; ++j) {
+          const float t = fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]);
+          a[j] = p.act_op == GA_ACT_SILU ? silu_fast(t) : t;
+        }
         st4d(p.act, p.act_dtype, off, a);
       }
     }
@@ -759,8 +762,9 @@ extern "C" int ga_channel_sum(const ga_tensor* r, float* sums, void* stream) {
 extern "C" int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const float* w1, const float* b1, const float* w2,
                                   const float* b2, int hidden, float res_scale, const ga_tensor* skip, const ga_tensor* out,
                                   const ga_tensor* out2, const ga_tensor* act, const float* act_scale, const float* act_shift,
-                                  float* gate_out, void* stream) {
-  GA_CHECK(r && sums && w1 && b1 && w2 && b2 && skip && out, "ga_se_residual_fwd: null argument");
+                                  int act_op, float* gate_out, void* stream) {
+  GA_CHECK(r && sums && w1 && w2 && skip && out, "ga_se_residual_fwd: null argument");
+  GA_CHECK(act_op == GA_ACT_SILU || act_op == GA_ACT_NONE, "ga_se_residual_fwd: act_op must be SILU or NONE");
   GA_CHECK(same_shape(r, skip) && same_shape(r, out), "ga_se_residual_fwd: shape mismatch");
   GA_CHECK((r->c % 4) == 0, "ga_se_residual_fwd: channels must be a multiple of 4");
   GA_CHECK(!act || (act_scale && act_shift && same_shape(r, act)), "ga_se_residual_fwd: act output needs scale/shift");
@@ -773,7 +777,7 @@ extern "C" int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const f
   p.out = out->data; p.out_dtype = out->dtype;
   p.out2 = out2 ? out2->data : nullptr; p.out2_dtype = out2 ? out2->dtype : GA_F32;
   p.act = act ? act->data : nullptr; p.act_dtype = act ? act->dtype : GA_F32;
-  p.act_scale = act_scale; p.act_shift = act_shift; p.gate_out = gate_out;
+  p.act_scale = act_scale; p.act_shift = act_shift; p.act_op = act_op; p.gate_out = gate_out;
   p.HW = r->h * r->w; p.C = r->c; p.pix_per_block = se_pix_per_block(p.HW, r->n);
   p.nparts = cdiv(p.HW, p.pix_per_block);
   const size_t smem = (2 * (size_t)p.C + hidden) * sizeof(float);

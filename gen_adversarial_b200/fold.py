@@ -66,7 +66,7 @@ class Folder:
         L = ConvLayer(kh, kw, stride, pad, cin, cout, pre_op=pre_op, post_act=post_act, name=name, up=up)
         if simt:
             L.w_simt = self.dev32(w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout))
-        if self.want_tc and stride == 1 and up == 1 and cin % 8 == 0:
+        if self.want_tc and stride in (1, 2) and up == 1 and cin % 8 == 0 and ((kh == 1 and pad == 0) or (kh == 3 and pad == 1)):
             wk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
             if w2 is not None:
                 wk = torch.cat([wk, w2], dim=1)

@@ -168,7 +168,8 @@ class NvaeEngine:
                 xin = ops.cast(x, torch.bfloat16)
             if ops.conv2d_tc_supported(xin, L, x2):
                 if want_dact:
-                    dact = torch.empty(xin.shape[:3] + (L.cout,), device=xin.device, dtype=torch.bfloat16)
+                    ho, wo = ops.conv_out_hw(L, xin.shape[1], xin.shape[2])
+                    dact = torch.empty((xin.shape[0], ho, wo, L.cout), device=xin.device, dtype=torch.bfloat16)
                 ob, of = ops.conv2d_tc(xin, L, want_bf16=want_act, want_f32=want_f32, add=add, x2=x2, mul=mul, mul_mode=mul_mode,
                                        dact_out=dact)
                 return (ob, of, dact) if want_dact else (ob, of)

@@ -171,20 +171,21 @@ def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: b
     """-> (out_bf16 or None, out_f32 or None);  out = (act(conv + bias) + add) * f(mul); dact_out <- act'(conv + bias)"""
     n, h, w, c = x.shape
     assert c == L.cin, (L.name, c, L.cin)
-    ob = (out_bf16 if out_bf16 is not None else torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.bfloat16)) if want_bf16 else None
-    of = (out_f32 if out_f32 is not None else torch.empty((n, h, w, L.cout), device=x.device, dtype=torch.float32)) if want_f32 else None
+    ho, wo = conv_out_hw(L, h, w)
+    ob = (out_bf16 if out_bf16 is not None else torch.empty((n, ho, wo, L.cout), device=x.device, dtype=torch.bfloat16)) if want_bf16 else None
+    of = (out_f32 if out_f32 is not None else torch.empty((n, ho, wo, L.cout), device=x.device, dtype=torch.float32)) if want_f32 else None
     d = L.desc(True, mul, mul_mode, dact_out)
     e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_conv2d_tc(gt(x), gt(x2), ctypes.byref(d), gt(add), gt(ob), gt(of), stream()),
                f"conv2d_tc[{L.name}]")
     if e0 is not None:
-        m = n * h * w
+        m = n * ho * wo
         ktot = L.w_tc.shape[1]
         flops = 2.0 * m * L.cout * ktot
         # compulsory traffic: A once (not per tap), weights once, outputs (+ add) once
-        bytes_ = 2.0 * m * (c + (x2.shape[3] if x2 is not None else 0)) + 2.0 * L.cout * ktot \
+        bytes_ = 2.0 * n * h * w * c + 2.0 * m * (x2.shape[3] if x2 is not None else 0) + 2.0 * L.cout * ktot \
             + m * L.cout * ((2 if want_bf16 else 0) + (4 if want_f32 else 0) + (add.element_size() if add is not None else 0))
-        TIMER.stop(e0, f"k{L.kh} hw{h} cin{c} cout{L.cout}", flops, bytes_)
+        TIMER.stop(e0, f"k{L.kh}{'s2' if L.stride == 2 else ''} hw{h} cin{c} cout{L.cout}", flops, bytes_)
     return ob, of
 
 
@@ -214,8 +215,9 @@ def channel_sum(r: torch.Tensor) -> torch.Tensor:
 
 @_timed("se_residual")
 def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
-                act_affine=None, act_dtype=torch.bfloat16, want_gate=False):
-    """se = (w1, b1, w2, b2) fp32 device tensors.  -> (out, out2|None, act|None, gate|None)"""
+                act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op: int = ACT_SILU):
+    """se = (w1, b1, w2, b2) fp32 device tensors (biases may be None).  -> (out, out2|None, act|None, gate|None);
+    act = act_op(act_scale * out + act_shift), act_op SiLU (NVAE cells) or none (IR-SE50 BatchNorm)"""
     w1, b1, w2, b2 = se
     out = torch.empty(r.shape, device=r.device, dtype=out_dtype)
     out2 = torch.empty(r.shape, device=r.device, dtype=out2_dtype) if want_out2 else None
@@ -223,7 +225,7 @@ def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, wa
     gate = torch.empty((r.shape[0], r.shape[3]), device=r.device, dtype=torch.float32) if want_gate else None
     a_s, a_b = act_affine if act_affine is not None else (None, None)
     _lib.check(_lib.lib().ga_se_residual_fwd(gt(r), ptr(sums), ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[0], res_scale,
-                                             gt(skip), gt(out), gt(out2), gt(act), ptr(a_s), ptr(a_b), ptr(gate), stream()),
+                                             gt(skip), gt(out), gt(out2), gt(act), ptr(a_s), ptr(a_b), act_op, ptr(gate), stream()),
                "se_residual")
     return out, out2, act, gate
 
@@ -441,6 +443,62 @@ def latent_lerp(codes, styles, alphas_dev):
     out = torch.empty_like(codes)
     _lib.check(_lib.lib().ga_latent_lerp(ptr(codes.contiguous()), ptr(styles.contiguous()), ptr(alphas_dev), b, l, d, ptr(out), stream()),
                "latent_lerp")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ encoder-side ops (encoders.cu)
+@_timed("add_layernorm")
+def add_layernorm(x, y, gamma, beta, out_dtype, eps: float = 1e-5, out2_dtype=None):
+    """LayerNorm(x + y) over channels -> out (and a second copy in out2_dtype)"""
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    out2 = torch.empty(x.shape, device=x.device, dtype=out2_dtype) if out2_dtype is not None else None
+    _lib.check(_lib.lib().ga_add_layernorm(gt(x), gt(y), ptr(gamma), ptr(beta), eps, gt(out), gt(out2), stream()), "add_layernorm")
+    return (out, out2) if out2_dtype is not None else out
+
+
+@_timed("attention")
+def attention(q, q_off: int, k, k_off: int, v, v_off: int, heads: int, dh: int, out_dtype):
+    """q (B,Q,1,Cq), k / v (B,*,*,C): head h = columns [off + h*dh, off + (h+1)*dh).  -> (B,Q,1,heads*dh)"""
+    b, nq = q.shape[0], q.shape[1] * q.shape[2]
+    s = k.shape[1] * k.shape[2]
+    ws = torch.empty((int(_lib.lib().ga_attention_ws_floats(b, heads, nq, s)),), device=q.device, dtype=torch.float32)
+    out = torch.empty((b, nq, 1, heads * dh), device=q.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_attention(gt(q), q_off, gt(k), k_off, gt(v), v_off, heads, dh, ptr(ws), gt(out), stream()), "attention")
+    return out
+
+
+@_timed("codes_assemble")
+def codes_assemble(heads, heads_lb: bool, use_w0: bool, latent_avg, b: int, l: int, d: int):
+    out = torch.empty((b, l, d), device=heads.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ga_codes_assemble(ptr(heads), int(heads_lb), int(use_w0), ptr(latent_avg), b, l, d, ptr(out), stream()),
+               "codes_assemble")
+    return out
+
+
+@_timed("resize_bilinear")
+def resize_bilinear(x, full_h: int, out_w: int, crop_y0: int, crop_h: int, out_dtype=None):
+    n, h, w, c = x.shape
+    out = torch.empty((n, crop_h, out_w, c), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().ga_resize_bilinear(gt(x), full_h, crop_y0, gt(out), stream()), "resize_bilinear")
+    return out
+
+
+@_timed("image_pool_out")
+def image_pool_out(img, k1: int, k2: int = 1, mask_rows: int = 0, denorm=(0.5, 0.5), cls_dtype=None, want_purified: bool = True):
+    """generator image NHWC fp32 -> (purified NCHW fp32 denormalised | None, classifier input NHWC | None)"""
+    n, s = img.shape[0], img.shape[1]
+    so = s // (k1 * k2)
+    pur = torch.empty((n, 3, so, so), device=img.device, dtype=torch.float32) if want_purified else None
+    cls = torch.empty((n, so, so, 3), device=img.device, dtype=cls_dtype) if cls_dtype is not None else None
+    _lib.check(_lib.lib().ga_image_pool_out(gt(img), k1, k2, mask_rows, float(denorm[0]), float(denorm[1]), ptr(pur), gt(cls), stream()),
+               "image_pool_out")
+    return pur, cls
+
+
+@_timed("philox_codes")
+def philox_codes(seed: int, sample0: int, std: float, l: int, b: int, d: int, device):
+    out = torch.empty((l, b, d), device=device, dtype=torch.float32)
+    _lib.check(_lib.lib().ga_philox_codes(seed, sample0, float(std), l, b, d, ptr(out), stream()), "philox_codes")
     return out
 
 

@@ -167,6 +167,16 @@ def make_vgg11_checkpoint(n_classes: int = 100, seed: int = 1, device: str = "cp
     return {"state_dict": make_vgg11_state_dict(n_classes, seed, device)}
 
 
+def synthetic_stylegan_inputs(batch: int, res: int, n_codes: int, seed: int = 42):
+    """x in [0,1] (B,3,res,res) + the two explicit N(0,1) draws of a StyleGAN defense call in the reference's order
+    (SURVEY 8c): input noise (B,3,res,res), style noise (n_codes,B,512)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.rand((batch, 3, res, res), generator=g, dtype=torch.float32)
+    noises = [torch.randn((batch, 3, res, res), generator=g, dtype=torch.float32),
+              torch.randn((n_codes, batch, 512), generator=g, dtype=torch.float32)]
+    return x, noises
+
+
 def synthetic_batch(batch: int, resolution=NVAE_C32_RESOLUTION, n_classes: int = 100, seed: int = 42):
     """x = rand(B,3,H,W) in [0,1] with seed 42, labels randint(n_classes)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -202,8 +212,8 @@ def make_stylegan2_state_dict(size: int = 32, style_dim: int = 512, n_mlp: int =
     blur2 = blur[None, :] * blur[:, None]
     blur2 = blur2 / blur2.sum()
 
-    def styled(prefix, cin, cout, k, up):
-        sd[f"{prefix}.conv.weight"] = _randn((1, cout, cin, k, k), g)
+    def styled(prefix, cin, cout, k, up, gain=1.0):
+        sd[f"{prefix}.conv.weight"] = _randn((1, cout, cin, k, k), g, gain)
         if up:
             sd[f"{prefix}.conv.blur.kernel"] = blur2 * 4.0
         sd[f"{prefix}.conv.modulation.weight"] = _randn((cin, style_dim), g)
@@ -218,7 +228,7 @@ def make_stylegan2_state_dict(size: int = 32, style_dim: int = 512, n_mlp: int =
         sd[f"{prefix}.bias"] = _randn((1, 3, 1, 1), g, 0.1)
         if up:
             sd[f"{prefix}.upsample.kernel"] = blur2 * 4.0
-        styled(prefix, cin, 3, 1, False)
+        styled(prefix, cin, 3, 1, False, gain=0.1)     # the RGB skip sums log2(size)-1 such outputs: keeps the image inside ~[-1, 1]
 
     conv_block("conv1", ch[4], ch[4], False)
     to_rgb("to_rgb1", ch[4], False)
@@ -234,3 +244,189 @@ def make_stylegan2_state_dict(size: int = 32, style_dim: int = 512, n_mlp: int =
         res = (layer_idx + 5) // 2
         sd[f"noises.noise_{layer_idx}"] = _randn((1, 1, 2 ** res, 2 ** res), g)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------- IR-SE50 encoders (E4E / Style-Transformer)
+IRSE50_BLOCKS = [(64, 64, 3), (64, 128, 4), (128, 256, 14), (256, 512, 3)]          # encoding/helpers.py:30-37
+
+
+def _bn_entries(sd, prefix, c, g):
+    sd[f"{prefix}.weight"] = _rand((c,), g, 0.7, 1.3)
+    sd[f"{prefix}.bias"] = _randn((c,), g, 0.1)
+    sd[f"{prefix}.running_mean"] = _randn((c,), g, 0.1)
+    sd[f"{prefix}.running_var"] = _rand((c,), g, 0.7, 1.3)
+    sd[f"{prefix}.num_batches_tracked"] = torch.tensor(100, dtype=torch.long)
+
+
+def _irse50_backbone_entries(sd, g, in_channels: int = 3):
+    """`input_layer` + 24 `bottleneck_IR_SE` units (encoding/encoder.py:72-83, helpers.py:98-120).  Residual branches are
+    scaled down (gain 0.5) so the un-normalised residual stream stays O(1) through 24 units, like a trained network's."""
+    sd["input_layer.0.weight"] = _randn((64, in_channels, 3, 3), g, math.sqrt(2.0 / (in_channels * 9)))
+    _bn_entries(sd, "input_layer.1", 64, g)
+    sd["input_layer.2.weight"] = _rand((64,), g, 0.1, 0.4)
+    i = 0
+    for cin0, depth, n in IRSE50_BLOCKS:
+        for j in range(n):
+            cin = cin0 if j == 0 else depth
+            p = f"body.{i}"
+            if cin != depth:
+                sd[f"{p}.shortcut_layer.0.weight"] = _randn((depth, cin, 1, 1), g, math.sqrt(1.0 / cin))
+                _bn_entries(sd, f"{p}.shortcut_layer.1", depth, g)
+            _bn_entries(sd, f"{p}.res_layer.0", cin, g)
+            sd[f"{p}.res_layer.1.weight"] = _randn((depth, cin, 3, 3), g, math.sqrt(2.0 / (cin * 9)))
+            sd[f"{p}.res_layer.2.weight"] = _rand((depth,), g, 0.1, 0.4)
+            sd[f"{p}.res_layer.3.weight"] = _randn((depth, depth, 3, 3), g, 0.5 * math.sqrt(1.0 / (depth * 9)))
+            _bn_entries(sd, f"{p}.res_layer.4", depth, g)
+            sd[f"{p}.res_layer.5.fc1.weight"] = _randn((depth // 16, depth, 1, 1), g, 1.5 / math.sqrt(depth))
+            sd[f"{p}.res_layer.5.fc2.weight"] = _randn((depth, depth // 16, 1, 1), g, 1.5 / math.sqrt(depth // 16))
+            i += 1
+    for name, cin in (("latlayer1", 256), ("latlayer2", 128)):
+        sd[f"{name}.weight"] = _randn((512, cin, 1, 1), g, math.sqrt(1.0 / cin))
+        sd[f"{name}.bias"] = _randn((512,), g, 0.1)
+
+
+def make_e4e_encoder_state_dict(stylegan_size: int = 1024, seed: int = 4) -> "OrderedDict[str, torch.Tensor]":
+    """State dict of `Encoder4Editing(50, 'ir_se', opts)` (StyleGan_E4E/encoding/encoder.py:57-108)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    _irse50_backbone_entries(sd, g)
+    n_styles = 2 * int(math.log2(stylegan_size)) - 2
+    for i in range(n_styles):
+        spatial = 16 if i < 3 else (32 if i < 7 else 64)
+        for j in range(int(math.log2(spatial))):
+            sd[f"styles.{i}.convs.{2 * j}.weight"] = _randn((512, 512, 3, 3), g, math.sqrt(2.0 / (512 * 9)))
+            sd[f"styles.{i}.convs.{2 * j}.bias"] = _randn((512,), g, 0.1)
+        sd[f"styles.{i}.linear.weight"] = _randn((512, 512), g, 0.5 if i else 1.0)
+        sd[f"styles.{i}.linear.bias"] = _randn((512,), g, 0.1)
+    return sd
+
+
+def make_trans_encoder_state_dict(seed: int = 5) -> "OrderedDict[str, torch.Tensor]":
+    """State dict of `GradualStyleEncoder(50, 'ir_se', opts)` (StyleGan_Trans/models/encoders/style_transformer_encoders.py:10-40)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    _irse50_backbone_entries(sd, g)
+    d, ff = 512, 1024
+    for n in ("coarse", "medium", "fine"):
+        p = f"transformerlayer_{n}"
+        for att in ("self_attn", "multihead_attn"):
+            sd[f"{p}.{att}.in_proj_weight"] = _randn((3 * d, d), g, math.sqrt(1.0 / d))
+            sd[f"{p}.{att}.in_proj_bias"] = _randn((3 * d,), g, 0.1)
+            sd[f"{p}.{att}.out_proj.weight"] = _randn((d, d), g, math.sqrt(1.0 / d))
+            sd[f"{p}.{att}.out_proj.bias"] = _randn((d,), g, 0.1)
+        sd[f"{p}.linear1.weight"] = _randn((ff, d), g, math.sqrt(2.0 / d))
+        sd[f"{p}.linear1.bias"] = _randn((ff,), g, 0.1)
+        sd[f"{p}.linear2.weight"] = _randn((d, ff), g, math.sqrt(1.0 / ff))
+        sd[f"{p}.linear2.bias"] = _randn((d,), g, 0.1)
+        for k in ("1", "2", "3"):
+            sd[f"{p}.norm{k}.weight"] = _rand((d,), g, 0.7, 1.3)
+            sd[f"{p}.norm{k}.bias"] = _randn((d,), g, 0.1)
+    sd["z"] = _randn((1, 16, d), g)
+    return sd
+
+
+def make_e4e_checkpoint(stylegan_size: int = 1024, seed: int = 4) -> dict:
+    """Format read by `load_E4EStyleGan` / `pSp.load_weights` (loading_utils.py:38-49, psp.py:39-45,117-127)."""
+    n_styles = 2 * int(math.log2(stylegan_size)) - 2
+    g = torch.Generator(device="cpu").manual_seed(seed + 1000)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for k, v in make_e4e_encoder_state_dict(stylegan_size, seed).items():
+        sd["encoder." + k] = v
+    for k, v in make_stylegan2_state_dict(stylegan_size, seed=seed + 1).items():
+        sd["decoder." + k] = v
+    return {"opts": {"stylegan_size": stylegan_size, "encoder_type": "Encoder4Editing", "start_from_latent_avg": True},
+            "state_dict": sd, "latent_avg": _randn((n_styles, 512), g, 0.3)}
+
+
+def make_trans_checkpoint(output_size: int = 512, seed: int = 5) -> dict:
+    """Format read by `load_TranStyleGan` / `StyleTransformer.load_weights` (loading_utils.py:69-81, style_transformer.py:30-36):
+    keys carry the `.module` prefix of the DataParallel-trained checkpoint."""
+    g = torch.Generator(device="cpu").manual_seed(seed + 1000)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for k, v in make_trans_encoder_state_dict(seed).items():
+        sd["encoder.module." + k] = v
+    for k, v in make_stylegan2_state_dict(output_size, seed=seed + 1).items():
+        sd["decoder.module." + k] = v
+    return {"opts": {"output_size": output_size, "input_nc": 3, "start_from_latent_avg": True, "learn_in_w": False, "device": "cpu"},
+            "state_dict": sd, "latent_avg": _randn((16, 512), g, 0.3)}
+
+
+# ----------------------------------------------------------------------------------------------- ResNet-50 / ResNeXt-50 classifiers
+def make_resnet_state_dict(n_classes: int, groups: int = 1, width_per_group: int = 64, seed: int = 6, calib_hw: int = 64,
+                           calibrate: bool = True) -> "OrderedDict[str, torch.Tensor]":
+    """State dict of `ResNet` / `ResNext` (/root/reference/src/classifier/model.py:10-28,53-70: torchvision resnet50 /
+    resnext50_32x4d bodies, keys prefixed `model.`, 4-layer head in `model.fc`)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def bn(prefix, c):
+        _bn_entries(sd, prefix, c, g)
+
+    sd["model.conv1.weight"] = _randn((64, 3, 7, 7), g, math.sqrt(2.0 / (3 * 49)))
+    bn("model.bn1", 64)
+    inplanes = 64
+    for li, (planes, n) in enumerate(zip((64, 128, 256, 512), (3, 4, 6, 3)), start=1):
+        width = int(planes * (width_per_group / 64.0)) * groups
+        for bi in range(n):
+            p = f"model.layer{li}.{bi}"
+            sd[f"{p}.conv1.weight"] = _randn((width, inplanes, 1, 1), g, math.sqrt(2.0 / inplanes))
+            bn(f"{p}.bn1", width)
+            sd[f"{p}.conv2.weight"] = _randn((width, width // groups, 3, 3), g, math.sqrt(2.0 / (width // groups * 9)))
+            bn(f"{p}.bn2", width)
+            sd[f"{p}.conv3.weight"] = _randn((planes * 4, width, 1, 1), g, 0.5 * math.sqrt(1.0 / width))
+            bn(f"{p}.bn3", planes * 4)
+            if bi == 0:
+                sd[f"{p}.downsample.0.weight"] = _randn((planes * 4, inplanes, 1, 1), g, math.sqrt(1.0 / inplanes))
+                bn(f"{p}.downsample.1", planes * 4)
+            inplanes = planes * 4
+    sd["model.fc.0.weight"] = _randn((2048, 2048), g, math.sqrt(2.0 / 2048))
+    bn("model.fc.1", 2048)
+    sd["model.fc.3.weight"] = _randn((n_classes, 2048), g, math.sqrt(1.0 / 2048))
+    sd["model.fc.3.bias"] = _randn((n_classes,), g, 0.05)
+    if calibrate:
+        # smooth calibration images (bilinearly up-sampled 8x8 noise): closer to purified reconstructions than white noise
+        low = torch.rand((16, 3, 8, 8), generator=g, dtype=torch.float32)
+        xc = torch.nn.functional.interpolate(low, size=(calib_hw, calib_hw), mode="bilinear", align_corners=False)
+        calibrate_resnet_bn(sd, groups, width_per_group, xc)
+    return sd
+
+
+def calibrate_resnet_bn(sd, groups: int, width_per_group: int, x_calib: torch.Tensor):
+    """Weight synthesis only (not the product path): set every BatchNorm's running statistics to the batch statistics of a
+    calibration batch, as a trained checkpoint would have them -- otherwise a random-init network predicts one class for
+    every input and equal accuracy counters would prove nothing.  Functional torch ops on the state dict."""
+    import torch.nn.functional as F
+
+    def bn_cal(x, prefix):
+        dims = (0, 2, 3) if x.dim() == 4 else (0,)
+        m, v = x.mean(dim=dims), x.var(dim=dims, unbiased=False)
+        sd[f"{prefix}.running_mean"], sd[f"{prefix}.running_var"] = m, v
+        return F.batch_norm(x, m, v, sd[f"{prefix}.weight"], sd[f"{prefix}.bias"], False, 0.0, 1e-5)
+
+    x = (x_calib - 0.5) / 0.5
+    x = F.relu(bn_cal(F.conv2d(x, sd["model.conv1.weight"], stride=2, padding=3), "model.bn1"))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, n in enumerate((3, 4, 6, 3), start=1):
+        for bi in range(n):
+            p = f"model.layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            h = F.relu(bn_cal(F.conv2d(x, sd[f"{p}.conv1.weight"]), f"{p}.bn1"))
+            h = F.relu(bn_cal(F.conv2d(h, sd[f"{p}.conv2.weight"], stride=stride, padding=1, groups=groups), f"{p}.bn2"))
+            h = bn_cal(F.conv2d(h, sd[f"{p}.conv3.weight"]), f"{p}.bn3")
+            idt = x
+            if f"{p}.downsample.0.weight" in sd:
+                idt = bn_cal(F.conv2d(x, sd[f"{p}.downsample.0.weight"], stride=stride), f"{p}.downsample.1")
+            x = F.relu(h + idt)
+    x = x.mean(dim=(2, 3))
+    bn_cal(x @ sd["model.fc.0.weight"].t(), "model.fc.1")
+    return sd
+
+
+def make_resnet50_checkpoint(n_classes: int = 2, seed: int = 6) -> dict:
+    """`load_ResNet50` format (loading_utils.py:10-17): gender classifier."""
+    return {"state_dict": make_resnet_state_dict(n_classes, 1, 64, seed)}
+
+
+def make_resnext50_checkpoint(n_classes: int = 4, seed: int = 7) -> dict:
+    """`load_ResNext50` format (loading_utils.py:29-36): cars classifier (resnext50_32x4d)."""
+    return {"state_dict": make_resnet_state_dict(n_classes, 32, 4, seed)}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 3
+#define GA_ABI_VERSION 4
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3, GA_PRE_AFFINE = 4 };
@@ -119,8 +119,8 @@ int ga_channel_sum(const ga_tensor* r, float* sums, void* stream);
 int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const float* w1, const float* b1, const float* w2,
                        const float* b2, int hidden, float res_scale, const ga_tensor* skip,
                        const ga_tensor* out, const ga_tensor* out2 /*nullable*/, const ga_tensor* act /*nullable*/,
-                       const float* act_scale, const float* act_shift, float* gate_out /*[n][c] nullable*/,
-                       void* stream);
+                       const float* act_scale, const float* act_shift, int act_op /* GA_ACT_SILU | GA_ACT_NONE */,
+                       float* gate_out /*[n][c] nullable*/, void* stream);
 
 /* ---- per-level latent interpolation + reparameterised sampling
  *      (models.py:198-206,243-250; distributions.py:20-45).  z = (1-a)*sc(mu_p+mu_q) + a*(sc(mu_p)+eps*T*exp(sc(ls_p)))
@@ -173,6 +173,31 @@ int ga_upfirdn2d(const ga_tensor* in, const float* kernel, int kh, int kw, int u
 int ga_avgpool_to_nchw(const ga_tensor* in, int k, int out_c, float* out_nchw, void* stream);           /* face_pool, psp.py:26,114 */
 int ga_latent_lerp(const float* codes, const float* styles, const float* alphas_dev, int b, int l, int d, float* out,
                    void* stream);                                                                         /* models.py:123-124,338-339 */
+
+/* ================================================================ encoder-side pieces of the StyleGAN purifiers (encoders.cu)
+ * out (and optional second copy out2) = LayerNorm(x + y) * gamma + beta over the channel dim   transformer.py:54-66 (norm1-3) */
+int ga_add_layernorm(const ga_tensor* x, const ga_tensor* y /*nullable*/, const float* gamma, const float* beta, float eps,
+                     const ga_tensor* out, const ga_tensor* out2 /*nullable*/, void* stream);
+/* multi-head attention softmax(q k^T / sqrt(dh)) v with few queries (nn.MultiheadAttention core, transformer.py:51-62):
+ * q (B, Q tokens, C), k / v (B, S tokens, C'): head h reads columns [off + h*dh, off + (h+1)*dh) of its tensor, so fused
+ * q|k|v or k|v projection outputs are consumed in place.  scores_ws: ga_attention_ws_floats(B, heads, Q, S) floats. */
+int64_t ga_attention_ws_floats(int b, int heads, int q, int s);
+int ga_attention(const ga_tensor* q, int q_off, const ga_tensor* k, int k_off, const ga_tensor* v, int v_off, int heads, int dh,
+                 float* scores_ws, const ga_tensor* out, void* stream);
+/* W+ codes: out[b][l] = (use_w0 && l > 0 ? heads[0][b] : 0) + heads[l][b] + latent_avg[l]   encoder.py:125-139, psp.py:92-99;
+ * heads_lb = 1: heads stored [l][b][d] (map2style outputs), 0: [b][l][d] (Style-Transformer codes, models.py:318-325) */
+int ga_codes_assemble(const float* heads, int heads_lb, int use_w0, const float* latent_avg /*[l][d] nullable*/, int b, int l, int d,
+                      float* out, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=False) to (full_h, out->w), keeping rows [crop_y0, crop_y0 + out->h)
+ * (kornia.geometry.resize + crop, models.py:307-308) */
+int ga_resize_bilinear(const ga_tensor* in, int full_h, int crop_y0, const ga_tensor* out, void* stream);
+/* generator image (N,S,S,C>=3 fp32) -> k1 x k1 face_pool -> [rows < mask_rows or >= S/k1 - mask_rows := -1 -> 2x2 mean when k2 = 2]
+ * -> purified NCHW fp32 (* out_scale + out_shift = kornia denormalize) and/or the classifier's normalised NHWC input
+ * (psp.py:26,114; models.py:346-351; abstract_models.py:184-185) */
+int ga_image_pool_out(const ga_tensor* in, int k1, int k2, int mask_rows, float out_scale, float out_shift, float* purified_nchw,
+                      const ga_tensor* cls_nhwc /*nullable*/, void* stream);
+/* out[l][b][d] ~ N(0, std^2), Philox stream keyed by (seed, l, global sample index): torch.normal(0, std, (n_codes, b, d)), models.py:119,334 */
+int ga_philox_codes(uint64_t seed, int64_t sample0, float std_, int l, int b, int d, float* out, void* stream);
 
 /* ================================================================ input-gradient (dgrad-only) backward pass
  * The attacks differentiate the logits w.r.t. the input batch only (untargeted.py:146,201): weights are frozen, no

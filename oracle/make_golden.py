@@ -67,6 +67,60 @@ def run_reference_nvae(ckpt, alphas, attenuation, eps, blur, x, noises, classifi
     return logits, purified
 
 
+def run_reference_stylegan(kind: str, batch: int = 2):
+    """configs 3 / 4 of BASELINE.json through the reference's own `E4EStyleGanDefenseModel` / `TransStyleGanDefenseModel`
+    + `CelebaGenderClassifier` / `CarsTypeClassifier` (src/defenses/ours/models.py:17-132,277-353), full-size architectures,
+    YAMLs verbatim, seeded synthetic checkpoints in the loaders' formats, explicit noise."""
+    import yaml
+    mm = ref_import.ref_models()
+    os.makedirs(SCRATCH, exist_ok=True)
+    if kind == "e4e":
+        ckpt, clf, yml, res, n_codes = synth.make_e4e_checkpoint(1024), synth.make_resnet50_checkpoint(), "ours_linear_noise_gender.yaml", 256, 18
+        Clf, Def = mm.CelebaGenderClassifier, mm.E4EStyleGanDefenseModel
+    else:
+        ckpt, clf, yml, res, n_codes = synth.make_trans_checkpoint(512), synth.make_resnext50_checkpoint(), "ours_cosine_blur_cars.yaml", 128, 16
+        Clf, Def = mm.CarsTypeClassifier, mm.TransStyleGanDefenseModel
+    ap, cp = os.path.join(SCRATCH, f"{kind}_ae.pt"), os.path.join(SCRATCH, f"{kind}_clf.pt")
+    torch.save(ckpt, ap)
+    torch.save(clf, cp)
+    with open(os.path.join(ref_import.REFERENCE_ROOT, "configs", yml)) as f:
+        p = yaml.safe_load(f)
+    dm = Def(Clf(cp, "cpu"), ap, p["interpolation_alphas"], p["alpha_attenuation"], p["initial_noise_eps"], p["gaussian_blur_input"], "cpu")
+    x, noises = synth.synthetic_stylegan_inputs(batch, res, n_codes, seed=42)
+    with torch.no_grad(), ref_import.ExplicitNoise(noises):
+        logits, purified = dm(x, preds_only=False)
+    out = {"yaml": yml, "alphas": p["interpolation_alphas"], "attenuation": p["alpha_attenuation"], "eps": p["initial_noise_eps"],
+           "blur": p["gaussian_blur_input"], "batch": batch, "x_seed": 42, "purified": purified, "logits": logits,
+           "ae_digest": sd_digest(ckpt["state_dict"]), "clf_digest": sd_digest(clf["state_dict"])}
+    print(kind, yml, "purified", purified.min().item(), purified.max().item(), purified.std().item(), "logits", logits.tolist())
+    return out
+
+
+def main_stylegan_paths():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.save(run_reference_stylegan("e4e"), os.path.join(GOLDEN, "e4e_gender_b2.pt"))
+    torch.save(run_reference_stylegan("trans"), os.path.join(GOLDEN, "trans_cars_b2.pt"))
+    shutil.rmtree(SCRATCH, ignore_errors=True)
+
+
+def main_generator():
+    import importlib
+    ref_import.install()
+    gen = importlib.import_module("src.mlvgms_autoencoders.StyleGan_E4E.stylegan2.generator")
+    sd = synth.make_stylegan2_state_dict(32, seed=2)
+    G = gen.Generator(32, 512, 8, channel_multiplier=2).eval()
+    G.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(0)
+    latent = torch.randn(3, G.n_latent, 512, generator=g) * 0.7
+    z = torch.randn(G.n_latent, 3, 512, generator=g)
+    with torch.no_grad():
+        img, _ = G([latent], input_is_latent=True, randomize_noise=False)           # Generator.forward, generator.py:407-479
+        w = torch.stack([G.style(n) for n in z], dim=0)                              # models.py:120
+    torch.save({"seed": 2, "size": 32, "latent": latent, "z": z, "image": img, "image_pool2": torch.nn.functional.avg_pool2d(img, 2),
+                "w": w}, os.path.join(GOLDEN, "stylegan2_gen32.pt"))
+    print("stylegan2 gen32", img.abs().max().item(), img.std().item())
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -113,25 +167,13 @@ def main():
                              "purified": pur, "logits": logits})
         print("c32", yml, pur.mean().item(), pur.std().item(), logits.abs().mean().item(), logits.argmax(1).tolist())
     torch.save(out, os.path.join(GOLDEN, "nvae_c32_vgg11.pt"))
-    # ---------------------------------------------------------------- StyleGAN2 generator (size 32, weights regenerated from the seed)
-    import importlib
-    gen = importlib.import_module("src.mlvgms_autoencoders.StyleGan_E4E.stylegan2.generator")
-    sd = synth.make_stylegan2_state_dict(32, seed=2)
-    G = gen.Generator(32, 512, 8, channel_multiplier=2).eval()
-    G.load_state_dict(sd, strict=True)
-    g = torch.Generator().manual_seed(0)
-    latent = torch.randn(3, G.n_latent, 512, generator=g) * 0.7
-    z = torch.randn(G.n_latent, 3, 512, generator=g)
-    with torch.no_grad():
-        img, _ = G([latent], input_is_latent=True, randomize_noise=False)           # Generator.forward, generator.py:407-479
-        w = torch.stack([G.style(n) for n in z], dim=0)                              # models.py:120
-    torch.save({"seed": 2, "size": 32, "latent": latent, "z": z, "image": img, "image_pool2": torch.nn.functional.avg_pool2d(img, 2),
-                "w": w}, os.path.join(GOLDEN, "stylegan2_gen32.pt"))
-    print("stylegan2 gen32", img.abs().max().item(), img.std().item())
+    main_generator()
+    main_stylegan_paths()
     shutil.rmtree(SCRATCH, ignore_errors=True)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 
 
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    {"all": main, "generator": main_generator, "stylegan_paths": main_stylegan_paths}[which]()

@@ -115,11 +115,12 @@ def conv2d_simt(x, L, out_dtype, add=None, out_hw=None, mul=None, mul_mode=0, wa
 def conv2d_tc_supported(x, L, x2=None):
     if L.w_tc is None or x.dtype != torch.bfloat16:
         return False
-    if L.stride != 1 or L.up != 1:
+    if L.stride not in (1, 2) or L.up != 1 or (x2 is not None and L.stride != 1):
         return False
     n, h, w, c = x.shape
     if c % 8:
         return False
+    h, w = conv_out_hw(L, h, w)
     if w >= 128:
         return w % 128 == 0
     if 128 % w:
@@ -135,7 +136,7 @@ def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None,
     k1 = L.kh * L.kw * L.cin
     w = L.w_tc.float()
     w1 = w[:, :k1].view(L.cout, L.kh, L.kw, L.cin).permute(0, 3, 1, 2)
-    y = F.conv2d(_nchw(x), w1, None, padding=L.pad)
+    y = F.conv2d(_nchw(x), w1, None, stride=L.stride, padding=L.pad)
     if x2 is not None:
         assert x2.dtype == torch.bfloat16 and w.shape[1] == k1 + x2.shape[3]
         y = y + F.conv2d(_nchw(x2), w[:, k1:].view(L.cout, -1, 1, 1))
@@ -177,15 +178,73 @@ def channel_sum(r):
 
 
 def se_residual(r, sums, se, res_scale, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
-                act_affine=None, act_dtype=torch.bfloat16, want_gate=False):
+                act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op=ACT_SILU):
     _launches[0] += 1
     w1, b1, w2, b2 = se
     mean = sums.sum(dim=1) / (r.shape[1] * r.shape[2])
     gate = torch.sigmoid(F.linear(F.relu(F.linear(mean, w1, b1)), w2, b2))
     out = skip.float() + res_scale * gate[:, None, None, :] * r.float()
     out2 = out.to(out2_dtype) if want_out2 else None
-    act = F.silu(out * act_affine[0] + act_affine[1]).to(act_dtype) if act_affine is not None else None
+    act = None
+    if act_affine is not None:
+        act = out * act_affine[0] + act_affine[1]
+        act = (F.silu(act) if act_op == ACT_SILU else act).to(act_dtype)
     return out.to(out_dtype), out2, act, (gate if want_gate else None)
+
+
+# ------------------------------------------------------------------------------------------------ encoder-side ops
+def add_layernorm(x, y, gamma, beta, out_dtype, eps=1e-5, out2_dtype=None):
+    _launches[0] += 1
+    t = x.float() + (y.float() if y is not None else 0.0)
+    o = F.layer_norm(t, (t.shape[-1],), gamma, beta, eps)
+    return (o.to(out_dtype), o.to(out2_dtype)) if out2_dtype is not None else o.to(out_dtype)
+
+
+def attention(q, q_off, k, k_off, v, v_off, heads, dh, out_dtype):
+    _launches[0] += 2
+    b, nq = q.shape[0], q.shape[1] * q.shape[2]
+    s = k.shape[1] * k.shape[2]
+    qf = q.float().reshape(b, nq, -1)[..., q_off:q_off + heads * dh].reshape(b, nq, heads, dh).permute(0, 2, 1, 3)
+    kf = k.float().reshape(b, s, -1)[..., k_off:k_off + heads * dh].reshape(b, s, heads, dh).permute(0, 2, 1, 3)
+    vf = v.float().reshape(b, s, -1)[..., v_off:v_off + heads * dh].reshape(b, s, heads, dh).permute(0, 2, 1, 3)
+    p = torch.softmax(qf @ kf.transpose(-1, -2) / (dh ** 0.5), dim=-1)
+    o = (p @ vf).permute(0, 2, 1, 3).reshape(b, nq, 1, heads * dh)
+    return o.contiguous().to(out_dtype)
+
+
+def codes_assemble(heads, heads_lb, use_w0, latent_avg, b, l, d):
+    _launches[0] += 1
+    h = heads.float().reshape(l, b, d).permute(1, 0, 2) if heads_lb else heads.float().reshape(b, l, d)
+    out = h.clone()
+    if use_w0:
+        out[:, 1:] += h[:, :1]
+    if latent_avg is not None:
+        out = out + latent_avg.float().reshape(1, l, d)
+    return out.contiguous()
+
+
+def resize_bilinear(x, full_h, out_w, crop_y0, crop_h, out_dtype=None):
+    _launches[0] += 1
+    y = F.interpolate(_nchw(x), size=(full_h, out_w), mode="bilinear", align_corners=False)
+    return _nhwc(y[:, :, crop_y0:crop_y0 + crop_h], out_dtype or x.dtype)
+
+
+def image_pool_out(img, k1, k2=1, mask_rows=0, denorm=(0.5, 0.5), cls_dtype=None, want_purified=True):
+    _launches[0] += 1
+    y = F.avg_pool2d(_nchw(img)[:, :3], k1)
+    if k2 == 2:
+        if mask_rows:
+            y = y.clone()
+            y[:, :, :mask_rows] = -1.0
+            y[:, :, -mask_rows:] = -1.0
+        y = F.avg_pool2d(y, 2)
+    pur = (y * denorm[0] + denorm[1]).contiguous() if want_purified else None
+    cls = _nhwc(y, cls_dtype) if cls_dtype is not None else None
+    return pur, cls
+
+
+def philox_codes(seed, sample0, std, l, b, d, device):
+    raise RuntimeError("the emulation only supports explicit noise")
 
 
 def latent_mix(q, p, eps_nchw, seed, level, sample0, alpha_dev, temperature, zdim, zc, out_dtype):

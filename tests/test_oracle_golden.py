@@ -60,3 +60,20 @@ def test_pgd_step_projection():
         xa = nvae_ref.pgd_linf_step(xa, g, x, step, eps)
     assert (xa - x).abs().max() <= eps + 1e-7
     assert xa.min() >= 0 and xa.max() <= 1
+
+
+def test_stylegan_oracle_matches_reference_fixtures():
+    """oracle/stylegan_ref.py (configs 3 and 4, full-size architectures, batch 2) against the reference's own outputs"""
+    import os
+    from oracle import stylegan_ref
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for kind, res, n_codes, mk_ae, mk_clf, fn in (
+            ("e4e_gender_b2.pt", 256, 18, lambda: synth.make_e4e_checkpoint(1024), synth.make_resnet50_checkpoint, stylegan_ref.e4e_defense_call),
+            ("trans_cars_b2.pt", 128, 16, lambda: synth.make_trans_checkpoint(512), synth.make_resnext50_checkpoint, stylegan_ref.trans_defense_call)):
+        g = torch.load(os.path.join(golden, kind), weights_only=True)
+        x, noises = synth.synthetic_stylegan_inputs(g["batch"], res, n_codes, seed=g["x_seed"])
+        alphas = [a * g["attenuation"] for a in g["alphas"]]
+        with torch.no_grad():
+            logits, pur = fn(mk_ae(), mk_clf()["state_dict"], x, alphas, noises, g["eps"], g["blur"])
+        assert (pur - g["purified"]).abs().max().item() <= 1e-5, kind
+        assert ((logits - g["logits"]).abs().max() / g["logits"].abs().max()).item() <= 1e-4, kind

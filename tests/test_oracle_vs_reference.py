@@ -74,3 +74,30 @@ def test_restatement_gradient_matches_reference(tmp_path):
     _, pur = nvae_ref.defense_call(ckpt["state_dict_temp=0.6"], spec, None, xo, alphas, noises, 1.0, True)
     g, = torch.autograd.grad((pur * w).sum(), [xo])
     assert (g - g_ref).abs().max().item() <= 1e-5 * max(1.0, g_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("kind", ["e4e", "trans"])
+def test_stylegan_restatement_matches_reference_call(tmp_path, kind):
+    """configs 3 / 4: oracle/stylegan_ref.py against the reference's own defense classes (different seeds, blur AND noise on,
+    other alpha schedule than the committed fixtures); also checks that the synthetic checkpoints load through the
+    reference loaders with strict=True (loading_utils.py:10-49,69-81)."""
+    from oracle import stylegan_ref
+    mm = ref_import.ref_models()
+    if kind == "e4e":
+        ckpt, clf = synth.make_e4e_checkpoint(1024, seed=14), synth.make_resnet50_checkpoint(seed=16)
+        Clf, Def, res, n_codes, fn = mm.CelebaGenderClassifier, mm.E4EStyleGanDefenseModel, 256, 18, stylegan_ref.e4e_defense_call
+    else:
+        ckpt, clf = synth.make_trans_checkpoint(512, seed=15), synth.make_resnext50_checkpoint(seed=17)
+        Clf, Def, res, n_codes, fn = mm.CarsTypeClassifier, mm.TransStyleGanDefenseModel, 128, 16, stylegan_ref.trans_defense_call
+    ap, cp = os.path.join(tmp_path, "ae.pt"), os.path.join(tmp_path, "clf.pt")
+    torch.save(ckpt, ap)
+    torch.save(clf, cp)
+    alphas = [0.5 * (1 - math.cos(math.pi * i / n_codes)) for i in range(1, n_codes + 1)]
+    dm = Def(Clf(cp, "cpu"), ap, alphas, 0.8, 2.0, True, "cpu")
+    x, noises = synth.synthetic_stylegan_inputs(1, res, n_codes, seed=5)
+    with torch.no_grad(), ref_import.ExplicitNoise(noises):
+        logits_ref, pur_ref = dm(x, preds_only=False)
+    with torch.no_grad():
+        logits, pur = fn(ckpt, clf["state_dict"], x, [a * 0.8 for a in alphas], noises, 2.0, True)
+    assert (pur - pur_ref).abs().max().item() <= 1e-5
+    assert ((logits - logits_ref).abs().max() / logits_ref.abs().max()).item() <= 1e-4
