@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the purification hot path (BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload purify|pgd]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload purify|pgd|gender|cars]
 
 "step" = one pass of the hot path over one batch of synthetic input:
   workload purify (default, BASELINE configs[1]): NVAE CelebA-64 "ids" + configs/ours_learned_blur_ids.yaml
       (blur on, eps 0) + VGG11 classifier, batch 512 per GPU, bf16 tensor-core path, random-init weights of the
       C32 architecture, synthetic images.  metric = purified img/s.
   workload pgd (BASELINE configs[4]): PGD-Linf (eps 8/255, step 2/255, 50 steps) through purifier + classifier.
+  workload gender / cars (BASELINE configs[2] / [3]): StyleGAN-E4E @1024 + ResNet-50, batch 128 / Style-Transformer @512 +
+      ResNeXt-50, batch 256 (extra measurements; the driver's headline line stays configs[1]).
 
 value  : whole-job img/s with inputs resident in HBM, device-timed (CUDA events), max over ranks.
 e2e    : the same through the reference-facing API (`NVAEDefenseModel.__call__`) from pinned HOST buffers, with the
@@ -189,22 +191,46 @@ def run_ours(args):
     from gen_adversarial_b200.defenses.ours.models import NVAEDefenseModel, CelebaIdentityClassifier
 
     mode = args.mode
-    B = args.batch if args.batch is not None else (128 if args.workload == "pgd" else 512)
-    cfg = COSINE_NOISE_IDS if args.workload == "pgd" else LEARNED_BLUR_IDS
-    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
-    nv = synth.make_nvae_checkpoint(seed=0)
-    vg = {"state_dict": synth.make_vgg11_state_dict(100, seed=1, device=str(dev))}
-    clf = CelebaIdentityClassifier(vg, dev, mode=mode)
-    del vg
-    dm = NVAEDefenseModel(clf, nv, cfg["interpolation_alphas"], cfg["alpha_attenuation"], cfg["initial_noise_eps"],
-                          cfg["gaussian_blur_input"], dev, mode=mode).eval()
+    sg = args.workload in ("gender", "cars")
+    B = args.batch if args.batch is not None else {"purify": 512, "pgd": 128, "gender": 128, "cars": 256}[args.workload]
+    if sg:
+        # BASELINE configs[2] / [3]: StyleGAN-E4E @1024 + ResNet-50 (ours_linear_noise_gender.yaml) and
+        # Style-Transformer @512 + ResNeXt-50 (ours_cosine_blur_cars.yaml); YAML values verbatim
+        from gen_adversarial_b200.defenses.ours.models import (E4EStyleGanDefenseModel, TransStyleGanDefenseModel,
+                                                               CelebaGenderClassifier, CarsTypeClassifier)
+        if args.workload == "gender":
+            cfg = {"interpolation_alphas": [0.05, 0.11, 0.16, 0.22, 0.27, 0.33, 0.38, 0.44, 0.50, 0.55, 0.61, 0.66, 0.72, 0.77, 0.83, 0.88, 0.94, 1.00],
+                   "alpha_attenuation": 1.0, "initial_noise_eps": 4.0, "gaussian_blur_input": False}
+            clf = CelebaGenderClassifier(synth.make_resnet50_checkpoint(), dev, mode=mode)
+            dm = E4EStyleGanDefenseModel(clf, synth.make_e4e_checkpoint(1024), cfg["interpolation_alphas"], cfg["alpha_attenuation"],
+                                         cfg["initial_noise_eps"], cfg["gaussian_blur_input"], dev, mode=mode).eval()
+            res, n_cls = (3, 256, 256), 2
+        else:
+            cfg = {"interpolation_alphas": [0.010, 0.038, 0.084, 0.146, 0.222, 0.309, 0.402, 0.500, 0.598, 0.691, 0.778, 0.854, 0.916, 0.962, 0.990, 1.000],
+                   "alpha_attenuation": 0.7, "initial_noise_eps": 0.0, "gaussian_blur_input": True}
+            clf = CarsTypeClassifier(synth.make_resnext50_checkpoint(), dev, mode=mode)
+            dm = TransStyleGanDefenseModel(clf, synth.make_trans_checkpoint(512), cfg["interpolation_alphas"], cfg["alpha_attenuation"],
+                                           cfg["initial_noise_eps"], cfg["gaussian_blur_input"], dev, mode=mode).eval()
+            res, n_cls = (3, 128, 128), 4
+        if args.chunk:
+            dm.max_chunk = args.chunk
+    else:
+        cfg = COSINE_NOISE_IDS if args.workload == "pgd" else LEARNED_BLUR_IDS
+        spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+        nv = synth.make_nvae_checkpoint(seed=0)
+        vg = {"state_dict": synth.make_vgg11_state_dict(100, seed=1, device=str(dev))}
+        clf = CelebaIdentityClassifier(vg, dev, mode=mode)
+        del vg
+        dm = NVAEDefenseModel(clf, nv, cfg["interpolation_alphas"], cfg["alpha_attenuation"], cfg["initial_noise_eps"],
+                              cfg["gaussian_blur_input"], dev, mode=mode).eval()
+        res, n_cls = NVAE_C32_RESOLUTION, 100
     dm.sample_offset = rank * B                      # Philox streams keyed by the GLOBAL sample index
-    x_cpu, y_cpu = synth.synthetic_batch(B, seed=42 + rank)
+    x_cpu, y_cpu = synth.synthetic_batch(B, res, n_cls, seed=42 + rank)
     x_host = x_cpu.pin_memory()
     x_dev = x_host.to(dev)
     y_dev = y_cpu.to(dev)
     counters = torch.zeros(3, dtype=torch.int64, device=dev)       # n_total, n_clean_correct, n_robust_correct
-    logits_host = torch.empty((B, 100), dtype=torch.float32).pin_memory()
+    logits_host = torch.empty((B, n_cls), dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
@@ -310,15 +336,23 @@ def run_ours(args):
                               "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] > 0 else None} for k, a in top]}
         cpu = cpu_baseline() if not args.no_cpu_baseline else None
         gflop = GFLOP_PER_IMAGE_FWD * ((2 * args.pgd_steps + 1) if pgd else 1)
+        if sg:
+            gflop = {"gender": 304.0, "cars": 172.0}[args.workload]      # encoder + decoder + classifier, MACs x 2
         workload = ("BASELINE configs[4]: PGD-Linf eps 8/255, step 2/255, %d steps (fwd + input-gradient each) + 1 eval forward, through "
                     "NVAE-C32 purifier (ours_cosine_noise_ids.yaml) + VGG11, random-init weights" % args.pgd_steps) if pgd else \
             ("BASELINE configs[1]: NVAE-C32 CelebA-64 ids purification (ours_learned_blur_ids.yaml: blur, eps 0, "
              "learned alphas x0.7) + VGG11 classifier, random-init weights")
+        if args.workload == "gender":
+            workload = ("BASELINE configs[2]: StyleGAN-E4E CelebA-HQ 256 gender (IR-SE50 + 18 map2style heads -> StyleGAN2 @1024 -> face_pool) "
+                        "ours_linear_noise_gender.yaml (eps 4, linear alphas) + ResNet-50, random-init weights")
+        elif args.workload == "cars":
+            workload = ("BASELINE configs[3]: Style-Transformer Stanford Cars 128 (IR-SE50 + 3 transformer decoder layers -> StyleGAN2 @512) "
+                        "ours_cosine_blur_cars.yaml (blur, cosine alphas x0.7) + ResNeXt-50, random-init weights")
         line = {"metric": "pgd_attacked_img_per_s" if pgd else "purified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": mode, "data": "synthetic",
                 "config": {"workload": workload,
-                           "nvae": NVAE_C32_CONFIG, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "nvae": None if sg else NVAE_C32_CONFIG, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": "no explicit flush: each step streams > 10 GB of activations through the 126 MB L2",
                            "gflop_per_image_algorithmic": gflop},
                 "tflops_algorithmic": value * gflop / 1e3,
@@ -340,7 +374,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 512 purify / 128 pgd)")
-    ap.add_argument("--workload", default="purify", choices=["purify", "pgd"])
+    ap.add_argument("--workload", default="purify", choices=["purify", "pgd", "gender", "cars"])
+    ap.add_argument("--chunk", type=int, default=0, help="generator batch chunk of the StyleGAN workloads (0: automatic)")
     ap.add_argument("--pgd-steps", type=int, default=50)
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded sample per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -351,8 +386,8 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
     else:
-        args.steps = args.steps if args.steps is not None else (2 if args.workload == "pgd" else 10)
-        args.warmup = args.warmup if args.warmup is not None else (1 if args.workload == "pgd" else 3)
+        args.steps = args.steps if args.steps is not None else {"purify": 10, "pgd": 2}.get(args.workload, 3)
+        args.warmup = args.warmup if args.warmup is not None else {"purify": 3, "pgd": 1}.get(args.workload, 3)
         run_ours(args)
 
 

@@ -55,8 +55,12 @@ __global__ void __launch_bounds__(256) affine_act_bwd_vec4_kernel(const void* g,
     const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c)), h4 = __ldg(reinterpret_cast<const float4*>(shift + c));
     sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w; sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
   }
+  float pre4[4], d4[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o[j] = fmaf(gv[j] * act_grad(fmaf(xv[j], sc[j], sh[j]), act), sc[j], av[j]);
+  for (int j = 0; j < 4; ++j) pre4[j] = fmaf(xv[j], sc[j], sh[j]);
+  act_grad_n<4>(pre4, d4, act);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = fmaf(gv[j] * d4[j], sc[j], av[j]);
   if (out_dtype == GA_F32) st4<float>(reinterpret_cast<float*>(out) + i, o); else st4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(out) + i, o);
 }
 

@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
     }
     float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = apply_act(acc[i][j] + bias4[j], p.post_act);
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias4[j];
+    apply_act_n<4>(v, p.post_act);
     if (cout_vec && nb + 4 <= p.Cout) {
       if (p.add != nullptr) {
         float a4[4];
@@ -280,7 +281,9 @@ __global__ void __launch_bounds__(256) conv3x3_stem_kernel(const TIn* __restrict
   }
   float o0[4], o1[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { o0[j] = apply_act(acc[j], post_act); o1[j] = apply_act(acc[4 + j], post_act); }
+  for (int j = 0; j < 4; ++j) { o0[j] = acc[j]; o1[j] = acc[4 + j]; }
+  apply_act_n<4>(o0, post_act);
+  apply_act_n<4>(o1, post_act);
   TOut* dst = out + pix * Cout + cg * 8;
   st4<TOut>(dst, o0);
   st4<TOut>(dst + 4, o1);

@@ -42,6 +42,7 @@ struct TcParams {
   __nv_bfloat16* out_bf16;
   float* out_f32;
   int tma_store;              // 1: epilogue stages the tile in (swizzled) shared memory and TMA-stores it
+  int partial;                // 1: the last tile row of an image hangs over its bottom edge (bn == 1, bw == W): mask rows, direct stores
   const void* mul; int mul_dtype, mul_mode;   // backward: out = (act(acc+bias) + add) * f(mul)
   __nv_bfloat16* dact;        // taping forward: derivative of post_act at the pre-activation (bf16)
   const float* act_slope;     // PReLU slopes [cout]
@@ -136,7 +137,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool GENERAL_ACT>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmA2,
                                                              const __grid_constant__ CUtensorMap tmB,
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on a 1024 B boundary
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem = smem_hdr + 4096;                   // operand ring / epilogue staging (1024-aligned)
+  constexpr int HDR_BYTES = GENERAL_ACT ? 4096 : 2048;
+  uint8_t* smem = smem_hdr + HDR_BYTES;              // operand ring / epilogue staging (1024-aligned)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * TC_A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_hdr);   // header: barriers, TMEM address; bias tile after the ring
@@ -249,13 +251,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     for (int i = et; i < BLOCK_N; i += 128) {
       const int n = n_blk * BLOCK_N + i;
       s_bias[i] = (p.bias != nullptr && n < p.cout) ? p.bias[n] : 0.f;
-      s_slope[i] = (p.act_slope != nullptr && n < p.cout) ? p.act_slope[n] : 0.f;
+      if (GENERAL_ACT) s_slope[i] = (p.act_slope != nullptr && n < p.cout) ? p.act_slope[n] : 0.f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier
+    // GENERAL_ACT (compile time): PReLU slopes and/or act(acc + bias + add); the hot NVAE path compiles without it
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
     const int64_t pix = pix0 + row;
-    const bool row_ok = pix < p.M;
+    // partial tiles (H not a multiple of the tile's row count): rows past the image's last row were zero-filled by TMA, never stored
+    const bool row_ok = pix < p.M && (p.partial == 0 || row < (p.H - y0) * p.W);
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
@@ -278,9 +282,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       const int64_t off = pix * p.cout + nb;
       const bool full = vec_ok && nb + 16 <= p.cout;
       if (p.dact != nullptr && (row_ok || p.tma_store)) {   // save act'(pre-activation) for the backward pass
-        float dv[16];
+        float dv[16], pre16[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dv[j] = act_grad(__uint_as_float(r[j]) + s_bias[c0 + j], p.post_act);
+        for (int j = 0; j < 16; ++j) pre16[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+        act_grad_n<16>(pre16, dv, p.post_act);
         if (p.tma_store) {
           uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
           const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
@@ -299,9 +304,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float pre = __uint_as_float(r[j]) + s_bias[c0 + j];
-        v[j] = p.act_after_add ? pre : (p.post_act == GA_ACT_PRELU ? (pre > 0.f ? pre : s_slope[c0 + j] * pre) : apply_act_fast(pre, p.post_act));
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+      if (!GENERAL_ACT) {
+        apply_act_fast_n<16>(v, p.post_act);
+      } else if (!p.act_after_add) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j];
       }
       if (p.add != nullptr && row_ok) {
         if (full) {
@@ -330,10 +338,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
         }
       }
-      if (p.act_after_add) {
+      if (GENERAL_ACT && p.act_after_add) {
+        if (p.post_act == GA_ACT_PRELU) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = p.post_act == GA_ACT_PRELU ? (v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j]) : apply_act_fast(v[j], p.post_act);
+          for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j];
+        } else {
+          apply_act_fast_n<16>(v, p.post_act);
+        }
       }
       if (p.mul != nullptr && row_ok && full) {
         float mv[16];
@@ -449,9 +460,10 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-struct TileGeom { int bw, bh, bn, tiles_x, tiles_y; int64_t m_tiles; };
+struct TileGeom { int bw, bh, bn, tiles_x, tiles_y, partial; int64_t m_tiles; };
 
 static bool tile_geometry(int N, int H, int W, TileGeom* g) {
+  g->partial = 0;
   if (W >= 128) {
     if (W % 128) return false;
     g->bw = 128; g->bh = 1; g->bn = 1;
@@ -459,10 +471,10 @@ static bool tile_geometry(int N, int H, int W, TileGeom* g) {
     if (128 % W) return false;
     g->bw = W;
     const int rows = 128 / W;
-    if (H >= rows) { if (H % rows) return false; g->bh = rows; g->bn = 1; }
+    if (H >= rows) { g->bh = rows; g->bn = 1; g->partial = (H % rows) != 0; }      // e.g. 12 x 16 maps: 8-row tiles, the 2nd half empty
     else { if (rows % H) return false; g->bh = H; g->bn = rows / H; }
   }
-  g->tiles_x = W / g->bw; g->tiles_y = H / g->bh;
+  g->tiles_x = W / g->bw; g->tiles_y = (H + g->bh - 1) / g->bh;
   g->m_tiles = g->bn > 1 ? (N + g->bn - 1) / g->bn : (int64_t)N * g->tiles_x * g->tiles_y;
   return true;
 }
@@ -511,25 +523,33 @@ static int encode_out_map(CUtensorMap* tm, void* base, int cout, int64_t m, int 
   return 0;
 }
 
-template <int BLOCK_N, int STAGES>
-static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of,
+template <int BLOCK_N, int STAGES, bool GENERAL_ACT>
+static int launch_tc_(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of,
                      const CUtensorMap& od, const TcParams& p, dim3 grid, cudaStream_t s) {
   constexpr int ring = STAGES * (TC_A_STAGE_BYTES + BLOCK_N * TC_BLOCK_K * 2);
   constexpr int max_staging = 2 * ((BLOCK_N + 63) / 64) * 16384 + (BLOCK_N / 32) * 16384;
-  constexpr int max_smem = 1024 /*align*/ + 4096 /*header*/ + (ring > max_staging ? ring : max_staging);
+  constexpr int HDR_BYTES = GENERAL_ACT ? 4096 : 2048;
+  constexpr int max_smem = 1024 /*align*/ + HDR_BYTES + (ring > max_staging ? ring : max_staging);
   static bool configured = false;
   if (!configured) {
-    GA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, GENERAL_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  max_smem > 227 * 1024 ? 227 * 1024 : max_smem));
     configured = true;
   }
   int staging = 0;
   if (p.tma_store) staging = ((p.out_bf16 ? 1 : 0) + (p.dact ? 1 : 0)) * ((BLOCK_N + 63) / 64) * 16384 + (p.out_f32 ? (BLOCK_N / 32) * 16384 : 0);
-  const int smem = 1024 + 4096 + (ring > staging ? ring : staging);
+  const int smem = 1024 + HDR_BYTES + (ring > staging ? ring : staging);
   GA_CHECK(smem <= 227 * 1024, "conv_tc: shared memory request %d too large", smem);
-  conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, od, p);
+  conv_tc_kernel<BLOCK_N, STAGES, GENERAL_ACT><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, od, p);
   GA_LAUNCH_OK();
   return 0;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of,
+                     const CUtensorMap& od, const TcParams& p, dim3 grid, cudaStream_t s) {
+  if (p.act_after_add != 0 || p.post_act == GA_ACT_PRELU) return launch_tc_<BLOCK_N, STAGES, true>(a, a2, b, ob, of, od, p, grid, s);
+  return launch_tc_<BLOCK_N, STAGES, false>(a, a2, b, ob, of, od, p, grid, s);
 }
 
 static int pick_block_n(int cout) {
@@ -618,7 +638,9 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   if (tma_ok && p.dact) { if (encode_out_map(&tmOD, p.dact, out->c, p.M, 2)) return 1; }
   if (tma_ok && out_bf16) { if (encode_out_map(&tmOB, out_bf16->data, out->c, p.M, 2)) return 1; }
   if (tma_ok && out_f32) { if (encode_out_map(&tmOF, out_f32->data, out->c, p.M, 4)) return 1; }
+  if (g.partial) tma_ok = false;          // a 32-row store box would spill into the next image
   p.tma_store = tma_ok ? 1 : 0;
+  p.partial = g.partial;
   const int num_kb = p.taps * p.kc1 + p.kc2;
   const bool short_k = num_kb <= 2;             // 1x1 convs with K <= 128: 2-stage ring -> more CTAs per SM
   if (num_kb == 1) {                            // single K block: 1-stage ring, up to 4 CTAs per SM (TMEM-limited)

@@ -592,8 +592,8 @@ __global__ void __launch_bounds__(256) affine_act_vec8_kernel(const void* in, in
     a[0] = fmaf(a[0], s0.x, h0.x); a[1] = fmaf(a[1], s0.y, h0.y); a[2] = fmaf(a[2], s0.z, h0.z); a[3] = fmaf(a[3], s0.w, h0.w);
     b[0] = fmaf(b[0], s1.x, h1.x); b[1] = fmaf(b[1], s1.y, h1.y); b[2] = fmaf(b[2], s1.z, h1.z); b[3] = fmaf(b[3], s1.w, h1.w);
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { a[j] = apply_act(a[j], act); b[j] = apply_act(b[j], act); }
+  apply_act_n<4>(a, act);
+  apply_act_n<4>(b, act);
   st4d(out, out_dtype, idx, a);
   st4d(out, out_dtype, idx + 4, b);
 }

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) channel_scale_kernel(const void* x, int x
 __global__ void __launch_bounds__(256) styled_bias_act_kernel(const void* y, int y_dtype, int phases, const float* __restrict__ demod,
                                                               const float* __restrict__ noise, float noise_w,
                                                               const float* __restrict__ bias, int act, const void* skip, int skip_dtype,
-                                                              int N, int H, int W, int C, void* out, int out_dtype) {
+                                                              int N, int H, int W, int C, const float* __restrict__ scale_a, void* out,
+                                                              int out_dtype, const float* __restrict__ scale_b, void* out_b, int out_b_dtype) {
   const int c4n = C >> 2;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * H * W * c4n) return;
@@ -103,14 +104,28 @@ __global__ void __launch_bounds__(256) styled_bias_act_kernel(const void* y, int
   if (bias != nullptr) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c)); b4[0] = b.x; b4[1] = b.y; b4[2] = b.z; b4[3] = b.w; }
   const int64_t o = ((n * H + yy) * W + x) * C + c;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j] + nz + b4[j], act);
+  for (int j = 0; j < 4; ++j) v[j] = v[j] + nz + b4[j];
+  apply_act_n<4>(v, act);
   if (skip != nullptr) {
     float s4[4];
     ld4s(skip, skip_dtype, o, s4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] += s4[j];
   }
-  st4s(out, out_dtype, o, v);
+  // the consumers are modulated convs: their per-sample input scaling (the "modulation", generator.py:164-167) is applied here on the
+  // fp32 value, so no separate scaling pass (and no second bf16 rounding) exists -- one copy per consumer (next StyledConv / ToRGB)
+  if (out_b != nullptr) {
+    const float4 sb = __ldg(reinterpret_cast<const float4*>(scale_b + n * C + c));
+    const float w[4] = {v[0] * sb.x, v[1] * sb.y, v[2] * sb.z, v[3] * sb.w};
+    st4s(out_b, out_b_dtype, o, w);
+  }
+  if (out != nullptr) {
+    if (scale_a != nullptr) {
+      const float4 sa = __ldg(reinterpret_cast<const float4*>(scale_a + n * C + c));
+      v[0] *= sa.x; v[1] *= sa.y; v[2] *= sa.z; v[3] *= sa.w;
+    }
+    st4s(out, out_dtype, o, v);
+  }
 }
 
 // ---------------------------------------------------------------------------- upfirdn2d (general; op/upfirdn2d_kernel.cu:52-137)
@@ -195,16 +210,22 @@ extern "C" int ga_channel_scale(const ga_tensor* x, const float* s, const ga_ten
 }
 
 extern "C" int ga_styled_bias_act(const ga_tensor* y, int phases, const float* demod, const float* noise_hw, float noise_w,
-                                  const float* bias, int act, const ga_tensor* skip, const ga_tensor* out, void* stream) {
-  GA_CHECK(y && out && (out->c % 4) == 0, "ga_styled_bias_act: null argument / channels must be a multiple of 4");
-  if (phases) GA_CHECK(y->n == 4 * out->n && y->h * 2 == out->h && y->w * 2 == out->w && y->c == out->c, "ga_styled_bias_act: phase planes must be [4*n][h/2][w/2][c]");
-  else GA_CHECK(same_shape(y, out), "ga_styled_bias_act: shape mismatch");
-  GA_CHECK(!skip || same_shape(skip, out), "ga_styled_bias_act: skip shape mismatch");
-  const int64_t total = numel(out) / 4;
+                                  const float* bias, int act, const ga_tensor* skip, const float* scale_a, const ga_tensor* out,
+                                  const float* scale_b, const ga_tensor* out_b, void* stream) {
+  GA_CHECK(y && (out || out_b), "ga_styled_bias_act: null argument");
+  const ga_tensor* o = out ? out : out_b;
+  GA_CHECK((o->c % 4) == 0, "ga_styled_bias_act: channels must be a multiple of 4");
+  if (phases) GA_CHECK(y->n == 4 * o->n && y->h * 2 == o->h && y->w * 2 == o->w && y->c == o->c, "ga_styled_bias_act: phase planes must be [4*n][h/2][w/2][c]");
+  else GA_CHECK(same_shape(y, o), "ga_styled_bias_act: shape mismatch");
+  GA_CHECK(!skip || same_shape(skip, o), "ga_styled_bias_act: skip shape mismatch");
+  GA_CHECK(!out_b || (scale_b && (!out || same_shape(out, out_b))), "ga_styled_bias_act: out_b needs scale_b and out's shape");
+  const int64_t total = numel(o) / 4;
   if (total == 0) return 0;
   styled_bias_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y->data, y->dtype, phases, demod, noise_hw, noise_w, bias, act,
-                                                                              skip ? skip->data : nullptr, skip ? skip->dtype : GA_F32, out->n,
-                                                                              out->h, out->w, out->c, out->data, out->dtype);
+                                                                              skip ? skip->data : nullptr, skip ? skip->dtype : GA_F32, o->n,
+                                                                              o->h, o->w, o->c, scale_a, out ? out->data : nullptr,
+                                                                              out ? out->dtype : GA_F32, scale_b, out_b ? out_b->data : nullptr,
+                                                                              out_b ? out_b->dtype : GA_F32);
   GA_LAUNCH_OK();
   return 0;
 }

@@ -173,23 +173,18 @@ class _StyleGanDefenseBase(MLVGMDefenseModel):
     def _preprocessed(self, batch, normalize=True):
         noise0 = self._explicit_noise[0] if self._explicit_noise is not None else None
         self._seed_now = self._next_seed()
-        x, _ = ops.preprocess(batch.detach().to(torch.float32), noise0, float(self.eps), bool(self.blur_input), self.autoencoder.adt,
+        # fp32 image into the encoder stem (a 3-channel SIMT conv either way): a bf16 input would perturb the image by up to 2e-3
+        x, _ = ops.preprocess(batch.detach().to(torch.float32), noise0, float(self.eps), bool(self.blur_input), torch.float32,
                               seed=self._seed_now, sample0=self.sample_offset, normalize=normalize, taps_cache=self._taps_cache)
         return x
 
     def _decode(self, codes, cls_dtype, want_purified=True, denorm=(0.5, 0.5)):
         """synthesis in batch chunks + the fused output kernel -> (purified NCHW [0,1], classifier input NHWC)"""
         dec = self.autoencoder.decoder
-        b = codes.shape[0]
-        chunk = self.max_chunk or max(1, min(b, (256 * 256 * 64) // (dec.size * dec.size) or 1))
-        purs, clss = [], []
-        for lo in range(0, b, chunk):
-            img = dec.synthesis(codes[lo:lo + chunk])
-            pur, cls = self._pool_out(img, cls_dtype, want_purified, denorm)
-            purs.append(pur)
-            clss.append(cls)
+        dec.max_chunk = self.max_chunk
+        outs = dec.synthesis(codes, sink=lambda img: self._pool_out(img, cls_dtype, want_purified, denorm))
         cat = lambda ts: None if ts[0] is None else (ts[0] if len(ts) == 1 else torch.cat(ts, dim=0))
-        return cat(purs), cat(clss)
+        return cat([o[0] for o in outs]), cat([o[1] for o in outs])
 
     def purify(self, batch: torch.Tensor) -> torch.Tensor:
         """
@@ -198,7 +193,7 @@ class _StyleGanDefenseBase(MLVGMDefenseModel):
         :return: purified reconstructions (B, C, H, W), still normalised (the caller de-normalises, abstract_models.py:184-185)
         """
         self._seed_now = self._next_seed()
-        x = ops.nchw_to_nhwc(batch.detach().to(torch.float32), self.autoencoder.adt)
+        x = ops.nchw_to_nhwc(batch.detach().to(torch.float32), torch.float32)
         pur, _ = self._decode(self._mix(self._encode(x)), None, denorm=(1.0, 0.0))
         return pur
 

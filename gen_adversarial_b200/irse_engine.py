@@ -106,7 +106,7 @@ class IrSe50Backbone:
                     h = ops.conv2d_simt(x32, u.c1, torch.bfloat16)            # SIMT applies the BN pre-op itself
             else:
                 h = ops.conv2d_simt(x32, u.c1, torch.float32)
-            r = self._conv(h, u.c2)
+            r = self._conv(h, u.c2, want_f32=True)     # fp32: r only feeds the SE mean and the fp32 residual stream (one bf16 rounding less per unit)
             if u.sc is not None:
                 skip = self._conv(xb if self.bf16 else x32, u.sc, want_f32=True)
             else:
@@ -119,6 +119,7 @@ class IrSe50Backbone:
                                              act_affine=nxt.pre if (self.bf16 and nxt is not None) else None, act_op=ACT_NONE)
             if is_tap:
                 taps[i] = xb if self.bf16 else x32
+        self.c3_f32 = x32                                  # fp32 copy of the last tap (E4E head 0 reads it)
         return taps[6], taps[20], taps[23]
 
 
@@ -161,10 +162,15 @@ class E4EEncoderEngine:
     _conv = IrSe50Backbone._conv
 
     def _head(self, feat, hd: _Head, out):
+        """map2style head.  bf16 mode: the convs on maps of 4x4 and smaller (the last two) and the EqualLinear run in fp32 -- 0.3% of the
+        head's FLOPs, and the W+ codes they produce steer every modulated conv of the generator"""
         x = feat
         for L in hd.convs:
-            x = self._conv(x, L)
-        self._conv(x.reshape(x.shape[0], 1, 1, -1), hd.linear, want_f32=True, out=out)
+            if self.bf16 and (x.shape[1] <= 4 or x.dtype == torch.float32):
+                x = ops.conv2d_simt(x, L, torch.float32)
+            else:
+                x = self._conv(x, L)
+        ops.conv2d_simt(x.reshape(x.shape[0], 1, 1, -1), hd.linear, torch.float32, out=out)
 
     def encode(self, x_nhwc: torch.Tensor) -> torch.Tensor:
         """x_nhwc (B,256,256,3) normalised -> codes (B, n_styles, 512) fp32 (latent_avg already added, psp.py:92-99)"""
@@ -179,7 +185,8 @@ class E4EEncoderEngine:
                 feat = p2
             elif i == self.middle_ind:
                 feat = conv1x1_any(self, c1, self.lat2, add=ops.upsample_bilinear2x(p2))
-            self._head(feat, hd, heads[i])
+            # head 0 (w0, added to all 18 codes) runs in fp32 from the fp32 residual stream in both modes: 1% of the encoder's FLOPs
+            self._head(self.backbone.c3_f32 if (i == 0 and self.bf16) else feat, hd, heads[i])
         return ops.codes_assemble(heads, True, True, self.latent_avg, b, self.style_count, 512)
 
 

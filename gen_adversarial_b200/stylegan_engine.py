@@ -58,7 +58,9 @@ class StyleGan2Engine:
         for i in range(1, n_mlp + 1):
             w = f.f64(f"style.{i}.weight") * sc
             b = f.f64(f"style.{i}.bias") * lr_mlp
-            self.mapping_layers.append(f.conv(w.view(style_dim, style_dim, 1, 1), b, post_act=ACT_LRELU_SQRT2, name=f"style.{i}"))
+            L = f.conv(w.view(style_dim, style_dim, 1, 1), b, post_act=ACT_LRELU_SQRT2, name=f"style.{i}")
+            L.w_tc = None          # the W+ codes steer every modulated conv: the 8-layer MLP stays fp32 in both modes (0.1% of the FLOPs)
+            self.mapping_layers.append(L)
         # ---- synthesis
         self.const_input = f.dev32(f.f64("input.input")[0].permute(1, 2, 0).unsqueeze(0))          # [1,4,4,C]
         self.conv1 = self._fold_styled(f, "conv1", up=False)
@@ -135,9 +137,9 @@ class StyleGan2Engine:
 
     def mapping(self, z: torch.Tensor) -> torch.Tensor:
         """z: (rows, style_dim) fp32 -> w: (rows, style_dim) fp32   [`Generator.style`, all codes in one batch]"""
-        x = ops.pixelnorm(z.to(torch.float32), self.adt)
-        for i, L in enumerate(self.mapping_layers):
-            x = self._conv(x, L, want_f32=(i == len(self.mapping_layers) - 1))
+        x = ops.pixelnorm(z.to(torch.float32), torch.float32)
+        for L in self.mapping_layers:
+            x = ops.conv2d_simt(x, L, torch.float32)
         return x.reshape(z.shape[0], self.style_dim)
 
     def _style(self, L, latent_i):
@@ -145,52 +147,99 @@ class StyleGan2Engine:
         b = latent_i.shape[0]
         return ops.conv2d_simt(latent_i.reshape(b, 1, 1, -1).contiguous(), L, torch.float32).reshape(b, -1)
 
-    def _styled(self, x, s: _Styled, latent_i, noise):
-        st = self._style(s.mod, latent_i)
-        xs = ops.channel_scale(x, st, self.adt)
-        demod = ops.style_demod(st, s.wsq)
-        if not s.up:
-            y = self._conv(xs, s.conv)
-            return ops.styled_bias_act(y, False, demod, noise, s.noise_w, s.bias, ACT_LRELU_SQRT2, None, self.adt)
-        b, h, w, _ = x.shape
-        planes = torch.empty((4 * b, h, w, s.cout), device=x.device, dtype=self.adt)
-        for ph, L in enumerate(s.phase_convs):
-            self._conv(xs, L, out=planes[ph * b:(ph + 1) * b])
-        return ops.styled_bias_act(planes, True, demod, noise, s.noise_w, s.bias, ACT_LRELU_SQRT2, None, self.adt)
+    def _plan(self):
+        """execution order: [(kind, layer, latent index)] -- conv1, to_rgb1, then (up conv, conv, to_rgb) per resolution"""
+        plan = [("styled", self.conv1, 0), ("rgb", self.to_rgb1, 1)]
+        i = 1
+        for up, conv, rgb in self.blocks:
+            plan += [("styled", up, i), ("styled", conv, i + 1), ("rgb", rgb, i + 2)]
+            i += 2
+        return plan
 
-    def _rgb(self, x, r: _ToRGB, latent_i, skip):
-        st = self._style(r.mod, latent_i)
-        xs = ops.channel_scale(x, st, self.adt)
+    def _styles(self, latent):
+        """all modulation vectors s[b, cin] and demodulation factors of one call, for the WHOLE batch (one small GEMM per layer
+        instead of one per layer per generator chunk)"""
+        out = {}
+        for kind, layer, idx in self._plan():
+            st = self._style(layer.mod, latent[:, idx])
+            out[id(layer)] = (st, ops.style_demod(st, layer.wsq) if kind == "styled" else None)
+        return out
+
+    def _styled(self, xs, s: _Styled, demod, noise, scale_next, scale_rgb):
+        """xs: input already scaled by this layer's style.  -> (act * scale_next | None, act * scale_rgb | None): the output is
+        handed to its consumers pre-modulated (the fused epilogue kernel applies their style vectors on the fp32 value)"""
+        # conv outputs at <= 128^2 stay fp32 until the fused epilogue (one bf16 rounding less per layer where it is almost free:
+        # errors made in the early layers pass through every later one)
+        b, h, w, _ = xs.shape
+        f32 = self.bf16 and h * (2 if s.up else 1) <= 128
+        if not s.up:
+            y = self._conv(xs, s.conv, want_f32=f32)
+            phases = False
+        else:
+            y = torch.empty((4 * b, h, w, s.cout), device=xs.device, dtype=torch.float32 if f32 else self.adt)
+            for ph, L in enumerate(s.phase_convs):
+                self._conv(xs, L, want_f32=f32, out=y[ph * b:(ph + 1) * b])
+            phases = True
+        r = ops.styled_bias_act(y, phases, demod, noise, s.noise_w, s.bias, ACT_LRELU_SQRT2, None, self.adt, scale_a=scale_next,
+                                scale_b=scale_rgb, want_out=scale_next is not None)
+        return r if scale_rgb is not None else (r, None)
+
+    def _rgb(self, xs, r: _ToRGB, skip):
         y = self._conv(xs, r.conv, want_f32=True)                                                   # [B,H,W,4] fp32
         if skip is not None:
             skip = ops.upfirdn2d(skip, r.up_kernel, up=2, down=1, pad=(2, 1))                        # Upsample (generator.py:30-47)
         return ops.styled_bias_act(y, False, None, None, 0.0, r.bias, ACT_NONE, skip, torch.float32)
 
-    def synthesis(self, latent: torch.Tensor) -> torch.Tensor:
-        """latent: (B, n_latent, style_dim) fp32 -> RGB image NHWC (B, size, size, 4) fp32 (4th channel is padding)"""
+    def _cap(self, j: int) -> int:
+        """largest batch slice block j (output resolution 8 * 2^j) runs on: keeps one activation tensor <= 2^29 elements (1 GB bf16)"""
+        res = 8 << j
+        cout = self.blocks[j][0].cout
+        return max(1, (1 << 29) // (res * res * cout))
+
+    def _run_blocks(self, j, x, skip, st, lo, sink, outs):
+        """blocks j.. on samples [lo, lo + n): low resolutions run on the whole batch, high resolutions on slices (recursive split)"""
+        n = skip.shape[0]
+        if j == len(self.blocks):
+            outs.append(sink(skip) if sink is not None else skip)
+            return
+        cap = self.max_chunk or self._cap(j)
+        if n > cap:
+            for o in range(0, n, cap):
+                self._run_blocks(j, x[o:o + cap], skip[o:o + cap], st, lo + o, sink, outs)
+            return
+        up, conv, rgb = self.blocks[j]
+        sl = slice(lo, lo + n)
+        s_conv, d_conv = st[id(conv)]
+        s_rgb, _ = st[id(rgb)]
+        s_next = st[id(self.blocks[j + 1][0])][0][sl] if j + 1 < len(self.blocks) else None
+        x, _ = self._styled(x, up, st[id(up)][1][sl], self.noises[2 * j + 1], s_conv[sl], None)
+        x, xr = self._styled(x, conv, d_conv[sl], self.noises[2 * j + 2], s_next, s_rgb[sl])
+        skip = self._rgb(xr, rgb, skip)
+        self._run_blocks(j + 1, x, skip, st, lo, sink, outs)
+
+    max_chunk = None
+
+    def synthesis(self, latent: torch.Tensor, sink=None):
+        """latent: (B, >= n_latent, style_dim) fp32 -> list of RGB image slices NHWC (n_i, size, size, 4) fp32 in batch order (4th
+        channel is padding), or of `sink(slice)` results when a sink is given (the caller pools each slice as soon as it exists)"""
         b = latent.shape[0]
-        assert latent.shape[1] == self.n_latent, (latent.shape, self.n_latent)
+        assert latent.shape[1] >= self.n_latent, (latent.shape, self.n_latent)
         latent = latent.to(torch.float32)
-        x = ops.cast(self.const_input.expand(b, -1, -1, -1).contiguous(), self.adt)
-        x = self._styled(x, self.conv1, latent[:, 0], self.noises[0])
-        skip = self._rgb(x, self.to_rgb1, latent[:, 1], None)
-        i = 1
-        for j, (up, conv, rgb) in enumerate(self.blocks):
-            x = self._styled(x, up, latent[:, i], self.noises[2 * j + 1])
-            x = self._styled(x, conv, latent[:, i + 1], self.noises[2 * j + 2])
-            skip = self._rgb(x, rgb, latent[:, i + 2], skip)
-            i += 2
-        return skip
+        st = self._styles(latent)
+        s1, d1 = st[id(self.conv1)]
+        x0 = ops.channel_scale(self.const_input.expand(b, -1, -1, -1).contiguous(), s1, self.adt)
+        s_next = st[id(self.blocks[0][0])][0] if self.blocks else None
+        x, xr = self._styled(x0, self.conv1, d1, self.noises[0], s_next, st[id(self.to_rgb1)][0])
+        skip = self._rgb(xr, self.to_rgb1, None)
+        outs = []
+        self._run_blocks(0, x, skip, st, 0, sink, outs)
+        return outs
 
     def decode(self, latent: torch.Tensor, pool: int = 1, chunk: Optional[int] = None) -> torch.Tensor:
-        """`pSp.decode` (psp.py:109-115): synthesis + face_pool (k x k mean) -> NCHW fp32 (B,3,size/pool,size/pool).
-        The batch is processed in chunks: at 1024^2 one (chunk,32,1024,1024) bf16 activation is already chunk x 64 MB."""
-        b = latent.shape[0]
-        chunk = chunk or max(1, min(b, (256 * 256 * 64) // (self.size * self.size) or 1))
-        outs = []
-        for lo in range(0, b, chunk):
-            img = self.synthesis(latent[lo:lo + chunk])
-            outs.append(ops.avgpool_to_nchw(img, pool, 3))
+        """`pSp.decode` (psp.py:109-115): synthesis + face_pool (k x k mean) -> NCHW fp32 (B,3,size/pool,size/pool)."""
+        if chunk is not None:
+            self.max_chunk = chunk
+        outs = self.synthesis(latent, sink=lambda img: ops.avgpool_to_nchw(img, pool, 3))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def mix_codes(self, codes: torch.Tensor, z_noise: torch.Tensor, alphas_dev: torch.Tensor) -> torch.Tensor:

@@ -126,7 +126,7 @@ def conv2d_tc_supported(x, L, x2=None):
     if 128 % w:
         return False
     rows = 128 // w
-    return (h % rows == 0) if h >= rows else (rows % h == 0)
+    return True if h >= rows else (rows % h == 0)
 
 
 def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None, mul_mode=0, dact_out=None, out_bf16=None,
@@ -354,7 +354,7 @@ def channel_scale(x, s, out_dtype):
     return (x.float() * s[:, None, None, :]).to(out_dtype)
 
 
-def styled_bias_act(y, phases, demod, noise_hw, noise_w, bias, act, skip, out_dtype):
+def styled_bias_act(y, phases, demod, noise_hw, noise_w, bias, act, skip, out_dtype, scale_a=None, scale_b=None, want_out=True):
     _launches[0] += 1
     v = y.float()
     if phases:
@@ -370,7 +370,12 @@ def styled_bias_act(y, phases, demod, noise_hw, noise_w, bias, act, skip, out_dt
     v = _act(v, act)
     if skip is not None:
         v = v + skip.float()
-    return v.contiguous().to(out_dtype)
+    out = None
+    if want_out:
+        out = (v * scale_a[:, None, None, :] if scale_a is not None else v).contiguous().to(out_dtype)
+    if scale_b is not None:
+        return out, (v * scale_b[:, None, None, :]).contiguous().to(out_dtype)
+    return out
 
 
 def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0), out_dtype=None):

@@ -53,6 +53,9 @@ TC_CASES = [
     (2, 256, 256, 64, 64, 3, 2, ACT_NONE, False, False),      # W_out = 128
     (2, 16, 16, 256, 1024, 1, 1, ACT_RELU, True, True),       # bottleneck conv3: relu(conv + identity)
     (2, 8, 8, 64, 64, 3, 1, ACT_PRELU, False, True),
+    (3, 12, 16, 64, 128, 3, 1, ACT_PRELU, False, False),      # Style-Transformer 192x256 input: 12x16 maps (partial tiles)
+    (3, 24, 32, 64, 64, 3, 2, ACT_NONE, False, True),         # ... stride 2 onto a 12x16 map
+    (2, 20, 32, 32, 96, 1, 1, ACT_RELU, True, True),
 ]
 
 
