@@ -125,6 +125,8 @@ _PROTOS = {
     "ga_discmix_mean_bwd": (c_int, [T, c_int, c_void_p, T, T, c_void_p]),
     "ga_se_residual_fwd": (c_int, [T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, T, T, T, T,
                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ga_mbconv_fused_supported": (c_int, [T, c_int]),
+    "ga_mbconv_fused": (c_int, [T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, T, c_void_p]),
     "ga_add_layernorm": (c_int, [T, T, c_void_p, c_void_p, c_float, T, T, c_void_p]),
     "ga_attention_ws_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "ga_attention": (c_int, [T, c_int, T, c_int, T, c_int, c_int, c_int, c_void_p, T, c_void_p]),
@@ -171,7 +173,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 5:
+    if L.ga_abi_version() != 6:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -1,0 +1,404 @@
+// Fused NVAE decoder cell body for sm_100a:  r = conv1x1_project( SiLU( dwconv5x5( SiLU( conv1x1_expand(x) ) ) ) )
+// (/root/reference/src/mlvgms_autoencoders/NVAE/modules/architecture.py:164-173 with the four BatchNorms folded into the three
+// convolutions).  The 6C-channel hidden tensor never leaves the SM:
+//
+//   per CTA: one spatial tile of the image batch; the hidden dimension is walked in chunks of 64 channels
+//     expand   tcgen05.mma  X[tile px, C] (smem, TMA) x We[chunk, C]^T (smem, TMA)  -> TMEM (double buffered)
+//     act      TMEM -> registers, + bias, SiLU, bf16 -> shared memory H (128-byte rows, XOR-swizzled: conflict free)
+//     depthwise 5x5 on H out of shared memory: one lane = one channel pair, one warp = a column strip, sliding window in
+//              registers, packed FFMA2; + bias, SiLU -> bf16, written straight into the 128B-swizzled K-major layout that
+//     project  tcgen05.mma  A2[tile px, chunk] x Wp[Cout, chunk]^T  accumulates into TMEM over all chunks
+//   epilogue: TMEM -> + bias -> r (bf16, NHWC) to HBM
+//
+// HBM traffic per cell drops from (x + 4 x hidden + r) to (x + r): 1.6 GB -> 0.13 GB at 32x32 / batch 512.  The unfused path
+// (conv_tc + dwconv5x5_tiled + conv_tc) stays for the taping forward of the attack path and for other shapes.
+//
+// Warp roles (288 threads): warp 0 = control (TMA producer + MMA issuer, one lane), warps 1-8 = SIMT (act, depthwise, epilogue).
+// Tiles: 8x8 maps: 2 images / CTA;  16x16: 1 image;  32x32: 8 output rows (+2 halo rows each side, expand recomputed 1.5x).
+#include <cuda.h>
+#include <stdlib.h>
+#include "ga_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ga {
+
+constexpr int MB_THREADS = 288;
+
+template <int W_IMG> struct MbGeom;
+template <> struct MbGeom<8>  { static constexpr int IMGS = 2, R_OUT = 8,  HALO = 0, MT_IN = 1, MT_OUT = 1, STRIP_W = 2; };
+template <> struct MbGeom<16> { static constexpr int IMGS = 1, R_OUT = 16, HALO = 0, MT_IN = 2, MT_OUT = 2, STRIP_W = 2; };
+template <> struct MbGeom<32> { static constexpr int IMGS = 1, R_OUT = 8,  HALO = 2, MT_IN = 3, MT_OUT = 2, STRIP_W = 4; };
+
+struct MbParams {
+  int N, H;                     // images, image height (= width = W_IMG)
+  int hidden;                   // 6C (multiple of 64)
+  const float* be;              // [hidden] expand bias
+  const float* dw_w;            // [25][hidden] depthwise taps
+  const float* dw_b;            // [hidden]
+  const float* bp;              // [C] project bias
+  __nv_bfloat16* out;           // [N][H][W][C]
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int C, int W_IMG, int NBUF>
+__global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                     const __grid_constant__ CUtensorMap tmWe,
+                                                                     const __grid_constant__ CUtensorMap tmWp, const MbParams p) {
+  using G = MbGeom<W_IMG>;
+  constexpr int KB = C / 64;                           // 64-channel K blocks of the expand GEMM
+  constexpr int R_IN = G::R_OUT + 2 * G::HALO;
+  constexpr int X_BYTES = G::MT_IN * KB * 16384;
+  constexpr int WE_BYTES = KB * 8192;                  // one chunk: 64 hidden rows x C
+  constexpr int WP_BYTES = C * 128;                    // one chunk: C rows x 64 hidden
+  constexpr int H_BYTES = G::MT_IN * 16384;
+  constexpr int A2_BYTES = G::MT_OUT * 16384;
+  constexpr uint32_t EXP_COLS = G::MT_IN * 64;         // one expand accumulator buffer
+  constexpr uint32_t PROJ_OFF = 2 * EXP_COLS;
+  static_assert(PROJ_OFF + G::MT_OUT * C <= 512, "TMEM budget");
+  static_assert(G::IMGS * R_IN * W_IMG == G::MT_IN * 128 && G::IMGS * G::R_OUT * W_IMG == G::MT_OUT * 128, "tile geometry");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hdr);
+  uint64_t* x_full = bars + 0;
+  uint64_t* we_full = bars + 1;          // [2]
+  uint64_t* we_empty = bars + 3;         // [2]
+  uint64_t* wp_full = bars + 5;          // [2]
+  uint64_t* wp_empty = bars + 7;         // [2]
+  uint64_t* exp_full = bars + 9;         // [2]
+  uint64_t* exp_empty = bars + 11;       // [2]
+  uint64_t* a2_full = bars + 13;
+  uint64_t* a2_empty = bars + 14;
+  uint64_t* proj_full = bars + 15;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  uint8_t* sX = hdr + 1024;
+  uint8_t* sWe = sX + X_BYTES;
+  uint8_t* sWp = sWe + NBUF * WE_BYTES;
+  uint8_t* sH = sWp + NBUF * WP_BYTES;
+  uint8_t* sA2 = sH + H_BYTES;
+  float* s_be = reinterpret_cast<float*>(sA2 + A2_BYTES);
+  float* s_dwb = s_be + p.hidden;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = p.hidden / 64;
+
+  // ---- tile -> (first image, first output row)
+  int n0, y0;
+  if (W_IMG == 8) { n0 = blockIdx.x * 2; y0 = 0; }
+  else if (W_IMG == 16) { n0 = blockIdx.x; y0 = 0; }
+  else { n0 = blockIdx.x / (W_IMG / G::R_OUT); y0 = (blockIdx.x % (W_IMG / G::R_OUT)) * G::R_OUT; }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmWe); tma_prefetch_desc(&tmWp);
+    mbar_init(x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&we_full[i], 1); mbar_init(&we_empty[i], 1); mbar_init(&wp_full[i], 1); mbar_init(&wp_empty[i], 1);
+      mbar_init(&exp_full[i], 1); mbar_init(&exp_empty[i], 8);
+    }
+    mbar_init(a2_full, 1); mbar_init(a2_empty, 1); mbar_init(proj_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    for (int i = threadIdx.x - 32; i < p.hidden; i += 256) { s_be[i] = p.be[i]; s_dwb[i] = p.dw_b[i]; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ======================================================================= control: TMA producer + MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_e = make_idesc(128, 64);
+      constexpr uint32_t idesc_p = make_idesc(128, C);
+      auto load_we = [&](int j) {
+        const int b = j % NBUF;
+        mbar_expect_tx(&we_full[b], WE_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmWe, &we_full[b], sWe + b * WE_BYTES + kb * 8192, kb * 64, j * 64);
+      };
+      auto load_wp = [&](int j) {
+        const int b = j % NBUF;
+        mbar_expect_tx(&wp_full[b], WP_BYTES);
+        tma_load_2d(&tmWp, &wp_full[b], sWp + b * WP_BYTES, j * 64, 0);
+      };
+      auto expand = [&](int k) {
+        if (k >= 1) {                                     // lazy refill of the buffer expand(k-1) has finished with
+          const int j = k - 1 + NBUF;
+          if (j < nch) { mbar_wait(&we_empty[(k - 1) % NBUF], ((k - 1) / NBUF) & 1); load_we(j); }
+        }
+        mbar_wait(&we_full[k % NBUF], (k / NBUF) & 1);
+        if (k >= 2) mbar_wait(&exp_empty[k & 1], ((k - 2) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t we_addr = smem_u32(sWe + (k % NBUF) * WE_BYTES);
+        for (int m = 0; m < G::MT_IN; ++m) {
+          const uint32_t d = tmem_base + (k & 1) * EXP_COLS + m * 64;
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t a_addr = smem_u32(sX + (m * KB + kb) * 16384);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(d, make_smem_desc(a_addr + kk * 32), make_smem_desc(we_addr + kb * 8192 + kk * 32), idesc_e, (kb > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&exp_full[k & 1]);
+        umma_commit(&we_empty[k % NBUF]);
+      };
+      auto project = [&](int k) {
+        if (k >= 1) {
+          const int j = k - 1 + NBUF;
+          if (j < nch) { mbar_wait(&wp_empty[(k - 1) % NBUF], ((k - 1) / NBUF) & 1); load_wp(j); }
+        }
+        mbar_wait(a2_full, k & 1);
+        mbar_wait(&wp_full[k % NBUF], (k / NBUF) & 1);
+        tc_fence_after();
+        const uint32_t wp_addr = smem_u32(sWp + (k % NBUF) * WP_BYTES);
+        for (int m = 0; m < G::MT_OUT; ++m) {
+          const uint32_t a_addr = smem_u32(sA2 + m * 16384);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + PROJ_OFF + m * C, make_smem_desc(a_addr + kk * 32), make_smem_desc(wp_addr + kk * 32), idesc_p,
+                      (k > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(a2_empty);
+        umma_commit(&wp_empty[k % NBUF]);
+        if (k == nch - 1) umma_commit(proj_full);
+      };
+      // ---- prologue: the activation tile (stays resident) and the first weight chunks
+      mbar_expect_tx(x_full, X_BYTES);
+      for (int m = 0; m < G::MT_IN; ++m)
+        for (int kb = 0; kb < KB; ++kb) {
+          uint8_t* dst = sX + (m * KB + kb) * 16384;
+          if (W_IMG == 8) tma_load_4d(&tmX, x_full, dst, kb * 64, 0, 0, n0);
+          else tma_load_4d(&tmX, x_full, dst, kb * 64, 0, y0 - G::HALO + m * (128 / W_IMG), n0);
+        }
+      for (int j = 0; j < NBUF && j < nch; ++j) { load_we(j); load_wp(j); }
+      mbar_wait(x_full, 0);
+      expand(0);
+      for (int k = 0; k < nch; ++k) {
+        if (k + 1 < nch) expand(k + 1);
+        project(k);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================================================= SIMT warps
+    const int sw = warp - 1;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int half = sw >> 2;                // column half of the 64-channel chunk / of the project accumulator
+    // depthwise strip of this warp
+    const int img = (W_IMG == 8) ? (sw >> 2) : 0;
+    const int cs = (W_IMG == 8) ? (sw & 3) * G::STRIP_W : sw * G::STRIP_W;
+    for (int k = 0; k < nch; ++k) {
+      // ---- (1) expand accumulator -> + bias -> SiLU -> bf16 -> H (swizzled rows)
+      mbar_wait(&exp_full[k & 1], (k >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < G::MT_IN; ++m) {
+        const int pin = m * 128 + q * 32 + lane;
+        bool in_img = true;
+        if (G::HALO > 0) {
+          const int y = y0 - G::HALO + (pin / W_IMG) % R_IN;
+          in_img = y >= 0 && y < p.H;                     // halo rows outside the image are the conv's zero padding
+        }
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (k & 1) * EXP_COLS + m * 64 + half * 32 + c16 * 16, r);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float b0 = s_be[k * 64 + half * 32 + c16 * 16 + 2 * j], b1 = s_be[k * 64 + half * 32 + c16 * 16 + 2 * j + 1];
+            const float v0 = silu_fast(__uint_as_float(r[2 * j]) + b0), v1 = silu_fast(__uint_as_float(r[2 * j + 1]) + b1);
+            pk[j] = in_img ? pack_bf16x2(v0, v1) : 0u;
+          }
+          const uint32_t ch0 = (uint32_t)(half * 4 + c16 * 2);            // 16-byte chunk index inside the 128-byte row
+          uint8_t* row = sH + pin * 128;
+          *reinterpret_cast<uint4*>(row + (((ch0) ^ (pin & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(row + (((ch0 + 1) ^ (pin & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&exp_empty[k & 1]);
+      simt_bar();                                                          // H complete
+      // ---- (2) depthwise 5x5 + bias + SiLU: H -> A2 (project operand layout)
+      float2 wt[25];
+      {
+        const float* wsrc = p.dw_w + k * 64 + 2 * lane;
+#pragma unroll
+        for (int t = 0; t < 25; ++t) wt[t] = __ldg(reinterpret_cast<const float2*>(wsrc + (size_t)t * p.hidden));
+      }
+      float2 acc[G::R_OUT][G::STRIP_W];
+      {
+        const float2 b2 = make_float2(s_dwb[k * 64 + 2 * lane], s_dwb[k * 64 + 2 * lane + 1]);
+#pragma unroll
+        for (int oy = 0; oy < G::R_OUT; ++oy)
+#pragma unroll
+          for (int c = 0; c < G::STRIP_W; ++c) acc[oy][c] = b2;
+      }
+      const uint32_t lch = (uint32_t)(lane >> 2), lof = (uint32_t)(lane & 3) * 4;
+#pragma unroll
+      for (int iy = 0; iy < R_IN; ++iy) {
+        float2 in[G::STRIP_W + 4];
+#pragma unroll
+        for (int c = 0; c < G::STRIP_W + 4; ++c) {
+          const int x = cs - 2 + c;
+          const int pin = (img * R_IN + iy) * W_IMG + x;
+          in[c] = make_float2(0.f, 0.f);
+          if (x >= 0 && x < W_IMG)
+            in[c] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sH + pin * 128 + ((lch ^ (uint32_t)(pin & 7)) << 4) + lof));
+        }
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+          const int oy = iy - G::HALO - ky + 2;          // output row fed by input row iy through tap row ky
+          if (oy < 0 || oy >= G::R_OUT) continue;
+#pragma unroll
+          for (int c = 0; c < G::STRIP_W; ++c)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) acc[oy][c] = ffma2(wt[ky * 5 + kx], in[c + kx], acc[oy][c]);
+        }
+      }
+      if (k >= 1) mbar_wait(a2_empty, (k - 1) & 1);                        // project(k-1) has consumed A2
+#pragma unroll
+      for (int oy = 0; oy < G::R_OUT; ++oy)
+#pragma unroll
+        for (int c = 0; c < G::STRIP_W; ++c) {
+          const int pout = (img * G::R_OUT + oy) * W_IMG + cs + c;
+          *reinterpret_cast<uint32_t*>(sA2 + pout * 128 + ((lch ^ (uint32_t)(pout & 7)) << 4) + lof) =
+              pack_bf16x2(silu_fast(acc[oy][c].x), silu_fast(acc[oy][c].y));
+        }
+      fence_proxy_async_smem();                                            // generic-proxy writes -> visible to the MMA (async proxy)
+      simt_bar();                                                          // A2 complete; H free for the next chunk
+      if (threadIdx.x == 32) mbar_arrive(a2_full);
+    }
+    // ---- (3) project accumulator -> + bias -> r (bf16) -> HBM
+    mbar_wait(proj_full, 0);
+    tc_fence_after();
+    const int64_t pix0 = (W_IMG == 32) ? ((int64_t)n0 * p.H + y0) * W_IMG : (int64_t)n0 * p.H * W_IMG;
+    const int64_t total_pix = (int64_t)p.N * p.H * W_IMG;
+#pragma unroll 1
+    for (int m = 0; m < G::MT_OUT; ++m) {
+      const int64_t pix = pix0 + m * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = half * (C / 2); c0 < (half + 1) * (C / 2); c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + PROJ_OFF + m * C + c0, r);
+        tmem_ld_wait();
+        if (pix < total_pix) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + __ldg(p.bp + c0 + 2 * j), __uint_as_float(r[2 * j + 1]) + __ldg(p.bp + c0 + 2 * j + 1));
+          uint4* o = reinterpret_cast<uint4*>(p.out + pix * C + c0);
+          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_mbEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_mbEncodeTiled mb_encode_fn() {
+  static PFN_mbEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_mbEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int mb_encode_2d(CUtensorMap* tm, const void* base, int cols, int rows, int box_rows) {
+  PFN_mbEncodeTiled enc = mb_encode_fn();
+  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights %d x %d, box rows %d) failed: %d", rows, cols, box_rows, (int)r);
+  return 0;
+}
+
+static int mb_encode_x(CUtensorMap* tm, const ga_tensor* t, int bw, int bh, int bn) {
+  PFN_mbEncodeTiled enc = mb_encode_fn();
+  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->c * 2, (cuuint64_t)t->w * t->c * 2, (cuuint64_t)t->h * t->w * t->c * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d) failed: %d", t->n, t->h, t->w, t->c, (int)r);
+  return 0;
+}
+
+template <int C, int W_IMG, int NBUF>
+static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, const MbParams& p, cudaStream_t s) {
+  using G = MbGeom<W_IMG>;
+  constexpr int KB = C / 64;
+  const int smem = 1024 /*align*/ + 1024 /*header*/ + G::MT_IN * KB * 16384 + NBUF * (KB * 8192 + C * 128) + G::MT_IN * 16384 +
+                   G::MT_OUT * 16384 + 2 * p.hidden * 4;
+  GA_CHECK(smem <= 227 * 1024, "ga_mbconv_fused: shared memory request %d too large", smem);
+  static int configured = 0;
+  if (configured < smem) {
+    GA_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<C, W_IMG, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  CUtensorMap tmX, tmWe, tmWp;
+  if (W_IMG == 8) { if (mb_encode_x(&tmX, x, 8, 8, 2)) return 1; }
+  else if (mb_encode_x(&tmX, x, W_IMG, 128 / W_IMG, 1)) return 1;
+  if (mb_encode_2d(&tmWe, we, C, p.hidden, 64)) return 1;          // [hidden][C]: box = 64 hidden rows x 64 k
+  if (mb_encode_2d(&tmWp, wp, p.hidden, C, C)) return 1;           // [C][hidden]: box = C rows x 64 k
+  int tiles;
+  if (W_IMG == 8) tiles = (x->n + 1) / 2;
+  else if (W_IMG == 16) tiles = x->n;
+  else tiles = x->n * (W_IMG / G::R_OUT);
+  mbconv_fused_kernel<C, W_IMG, NBUF><<<tiles, MB_THREADS, smem, s>>>(tmX, tmWe, tmWp, p);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" int ga_mbconv_fused_supported(const ga_tensor* x, int hidden) {
+  if (!x || x->dtype != GA_BF16 || x->h != x->w || hidden % 64 != 0 || hidden < 64 || hidden > 1536) return 0;
+  if ((((uintptr_t)x->data) & 15) != 0) return 0;
+  return (x->w == 8 && x->c == 256) || (x->w == 16 && x->c == 128) || (x->w == 32 && x->c == 64);
+}
+
+extern "C" int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
+                               const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, void* stream) {
+  GA_CHECK(x && we_tc && be && dw_w && dw_b && wp_tc && bp && out, "ga_mbconv_fused: null argument");
+  GA_CHECK(ga_mbconv_fused_supported(x, hidden), "ga_mbconv_fused: unsupported problem (n=%d h=%d w=%d c=%d hidden=%d)", x->n, x->h, x->w,
+           x->c, hidden);
+  GA_CHECK(out->dtype == GA_BF16 && same_shape(x, out), "ga_mbconv_fused: output must be bf16 with the input's shape");
+  GA_CHECK(((((uintptr_t)we_tc) | ((uintptr_t)wp_tc) | ((uintptr_t)out->data)) & 15) == 0, "ga_mbconv_fused: pointers must be 16-byte aligned");
+  if (numel(x) == 0) return 0;
+  MbParams p;
+  p.N = x->n; p.H = x->h; p.hidden = hidden; p.be = be; p.dw_w = dw_w; p.dw_b = dw_b; p.bp = bp;
+  p.out = (__nv_bfloat16*)out->data;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x->w == 8) return launch_mbconv<256, 8, 1>(x, we_tc, wp_tc, p, s);
+  if (x->w == 16) return launch_mbconv<128, 16, 2>(x, we_tc, wp_tc, p, s);
+  return launch_mbconv<64, 32, 2>(x, we_tc, wp_tc, p, s);
+}

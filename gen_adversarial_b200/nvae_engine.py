@@ -49,6 +49,8 @@ class NvaeEngine:
         self.temperature = float(temperature)
         self.zc = round_up(spec.z, 8)
         self.taps: Optional[dict] = None
+        # fused decoder-cell kernel (expand -> dw5x5 -> project, hidden tensor on chip); GA_MBCONV_FUSED=0 selects the three-kernel path
+        self.fuse_cells = __import__("os").environ.get("GA_MBCONV_FUSED", "1") != "0"
         f = Folder(state_dict, self.device, want_tc=self.bf16)
         self._fold(f)
         self._prior_cache = {}
@@ -238,6 +240,11 @@ class NvaeEngine:
     def _dec_cell(self, x32, xa, d: _Dec, rec):
         """x32: fp32 residual stream; xa: same values in the activation dtype (GEMM operand)."""
         taping = rec is not None
+        if not taping and self.fuse_cells and self.bf16 and not d.up and ops.mbconv_fused_supported(xa, d.e, d.p):
+            r = ops.mbconv_fused(xa, d.e, d.dw_w, d.dw_b, d.p)     # expand -> dw5x5 -> project in one kernel, hidden tensor on chip
+            sums = ops.channel_sum(r)
+            out, out2, _, _ = ops.se_residual(r, sums, d.se, 0.1, x32, torch.float32, want_out2=True)
+            return out, out2
         if taping:
             h1, _, dact_e = self._conv(xa, d.e, want_dact=True)
             h2, dact_dw = ops.dwconv5x5(h1, d.dw_w, d.dw_b, ACT_SILU, d.up, self.adt, want_dact=True)

@@ -205,6 +205,21 @@ def dwconv5x5(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return (out, dact) if want_dact else out
 
 
+def mbconv_fused_supported(x: torch.Tensor, e: ConvLayer, p: ConvLayer) -> bool:
+    if x.dtype != torch.bfloat16 or e.w_tc is None or p.w_tc is None or e.bias is None or p.bias is None:
+        return False
+    return bool(_lib.lib().ga_mbconv_fused_supported(gt(x), e.cout))
+
+
+@_timed("mbconv_fused")
+def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer) -> torch.Tensor:
+    """decoder-cell body in ONE kernel: project(SiLU(dw5x5(SiLU(expand(x)))))  -> r (bf16)"""
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ga_mbconv_fused(gt(x), e.w_tc.data_ptr(), ptr(e.bias), ptr(dw_w), ptr(dw_b), p.w_tc.data_ptr(), ptr(p.bias),
+                                          e.cout, gt(out), stream()), "mbconv_fused")
+    return out
+
+
 @_timed("channel_sum")
 def channel_sum(r: torch.Tensor) -> torch.Tensor:
     parts = _lib.lib().ga_channel_sum_parts(r.shape[0], r.shape[1] * r.shape[2])

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 5
+#define GA_ABI_VERSION 6
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3, GA_PRE_AFFINE = 4 };
@@ -109,6 +109,14 @@ int ga_dwconv5x5_fwd(const ga_tensor* in, const float* weight, const float* bias
  * flipped taps. */
 int ga_dwconv5x5_ex(const ga_tensor* in, const ga_tensor* mul, const float* weight, const float* bias, int act, int up,
                     const ga_tensor* out, const ga_tensor* dact, void* stream);
+
+/* ---- fused decoder-cell body: r = project1x1(SiLU(dw5x5(SiLU(expand1x1(x) + be)) + dw_b)) + bp  (architecture.py:164-173, the four
+ *      BatchNorms folded into the convs).  The 6C-channel hidden tensor stays in shared / tensor memory (tcgen05 + TMA).
+ *      x, out: bf16 NHWC; we_tc [hidden][C], wp_tc [C][hidden] bf16 K-major; dw_w [25][hidden] fp32.  Supported: square maps of
+ *      8 / 16 / 32 pixels with C = 256 / 128 / 64 (the three decoder scales of the 64x64 NVAE); other shapes use the three kernels. */
+int ga_mbconv_fused_supported(const ga_tensor* x, int hidden);
+int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
+                    const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, void* stream);
 
 /* ---- squeeze-excite + residual (architecture.py:37-61,128-136,178-186) */
 /* sums is [n][ga_channel_sum_parts(n, h*w)][c] partial sums (two-stage, no atomics: bit-reproducible) */

@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== kernels (non-TC)" ; timeout -s KILL 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "not conv_tc" -p no:cacheprovider > gpurun_out/kernels_simt.log 2>&1; tail -5 gpurun_out/kernels_simt.log
 echo "== kernels (TC)" ; timeout -s KILL 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv_tc" -p no:cacheprovider > gpurun_out/kernels_tc.log 2>&1; tail -5 gpurun_out/kernels_tc.log
+echo "== fused decoder cell" ; timeout -s KILL 300 python -m pytest tests/test_mbconv_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/mbconv.log 2>&1; grep -E "mbconv n=|passed|failed|FAILED|Error|error" gpurun_out/mbconv.log | tail -12
 echo "== nvae parity" ; timeout -s KILL 900 python -m pytest tests/test_nvae_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/nvae.log 2>&1; grep -E "err|passed|failed|FAILED|Error" gpurun_out/nvae.log | grep -v "^tap\|fp32\] tiny" | tail -30
 echo "== backward / pgd" ; timeout -s KILL 900 python -m pytest tests/test_backward_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/backward.log 2>&1; grep -E "grad|PGD|passed|failed|FAILED|Error|error" gpurun_out/backward.log | tail -30
 echo "== stylegan" ; timeout -s KILL 600 python -m pytest tests/test_stylegan_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/stylegan.log 2>&1; grep -E "generator@|passed|failed|FAILED|Error|error" gpurun_out/stylegan.log | tail -12

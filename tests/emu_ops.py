@@ -177,6 +177,22 @@ def channel_sum(r):
     return r.float().sum(dim=(1, 2)).unsqueeze(1)      # [n, parts=1, c]
 
 
+def mbconv_fused_supported(x, e, p):
+    n, h, w, c = x.shape
+    return x.dtype == torch.bfloat16 and e.w_tc is not None and p.w_tc is not None and h == w and (w, c) in ((8, 256), (16, 128), (32, 64))
+
+
+def mbconv_fused(x, e, dw_w, dw_b, p):
+    _launches[0] += 1
+    h1, _ = conv2d_tc(x, e)
+    _launches[0] -= 1
+    h2 = dwconv5x5(h1, dw_w, dw_b, ACT_SILU, False, torch.bfloat16)
+    _launches[0] -= 1
+    r, _ = conv2d_tc(h2, p)
+    _launches[0] -= 1
+    return r
+
+
 def se_residual(r, sums, se, res_scale, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
                 act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op=ACT_SILU):
     _launches[0] += 1

@@ -1,0 +1,57 @@
+"""GPU: the fused decoder-cell kernel (expand 1x1 -> SiLU -> depthwise 5x5 -> SiLU -> project 1x1, hidden tensor on chip)
+against the torch restatement of the three ops (tests/emu_ops.py) and against the three separate CUDA kernels."""
+import math
+
+import pytest
+import torch
+
+from gen_adversarial_b200 import ops
+from gen_adversarial_b200._lib import ACT_NONE, ACT_SILU
+from tests import emu_ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _cell(c, hidden, seed):
+    g = torch.Generator().manual_seed(seed)
+    we = torch.randn(hidden, c, generator=g) / math.sqrt(c)
+    wp = torch.randn(c, hidden, generator=g) / math.sqrt(hidden)
+    e = ops.ConvLayer(1, 1, 1, 0, c, hidden, post_act=ACT_SILU, name="expand")
+    e.w_tc = we.to(torch.bfloat16).contiguous()
+    e.bias = torch.randn(hidden, generator=g) * 0.3
+    p = ops.ConvLayer(1, 1, 1, 0, hidden, c, post_act=ACT_NONE, name="project")
+    p.w_tc = wp.to(torch.bfloat16).contiguous()
+    p.bias = torch.randn(c, generator=g) * 0.3
+    dw_w = torch.randn(25, hidden, generator=g) / 5.0
+    dw_b = torch.randn(hidden, generator=g) * 0.3
+    return e, dw_w, dw_b, p
+
+
+def _dev(L):
+    import copy
+    D = copy.copy(L)
+    D.w_tc, D.bias = L.w_tc.to(DEV), L.bias.to(DEV)
+    return D
+
+
+@pytest.mark.parametrize("n,w,c,hidden", [(3, 8, 256, 1536), (2, 8, 256, 64), (2, 16, 128, 768), (1, 16, 128, 128),
+                                          (2, 32, 64, 384), (1, 32, 64, 192), (5, 32, 64, 64)])
+def test_mbconv_fused_matches_three_kernels(n, w, c, hidden):
+    e, dw_w, dw_b, p = _cell(c, hidden, seed=n + w + hidden)
+    x = torch.randn(n, w, w, c, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    ref = emu_ops.mbconv_fused(x, e, dw_w, dw_b, p).float()
+    ed, pd, xd, wd, bd = _dev(e), _dev(p), x.to(DEV), dw_w.to(DEV), dw_b.to(DEV)
+    assert ops.mbconv_fused_supported(xd, ed, pd)
+    got = ops.mbconv_fused(xd, ed, wd, bd, pd)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    err = (got.float().cpu() - ref).abs().max().item()
+    # the same cell through the three separate kernels (what the fused kernel replaces)
+    h1, _ = ops.conv2d_tc(xd, ed)
+    h2 = ops.dwconv5x5(h1, wd, bd, ACT_SILU, False, torch.bfloat16)
+    r3, _ = ops.conv2d_tc(h2, pd)
+    err3 = (got.float() - r3.float()).abs().max().item()
+    print(f"mbconv n={n} w={w} c={c} hidden={hidden}: vs torch {err:.3e}, vs 3 kernels {err3:.3e} (scale {scale:.2f})")
+    assert err <= 2e-2 * scale, (err, scale)
+    assert err3 <= 2e-2 * scale, (err3, scale)
