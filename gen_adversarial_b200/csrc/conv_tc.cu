@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on a 1024 B boundary
-  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (aligned up by indexing the __shared__ array, not through an integer cast: the compiler keeps the shared address space and emits
+  // LDS / STS with 32-bit addresses instead of generic LD / ST with 64-bit address arithmetic)
+  uint8_t* smem_hdr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int HDR_BYTES = GENERAL_ACT ? 4096 : 2048;
   uint8_t* smem = smem_hdr + HDR_BYTES;              // operand ring / epilogue staging (1024-aligned)
   uint8_t* smem_a = smem;

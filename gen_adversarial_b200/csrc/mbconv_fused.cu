@@ -13,7 +13,8 @@
 // HBM traffic per cell drops from (x + 4 x hidden + r) to (x + r): 1.6 GB -> 0.13 GB at 32x32 / batch 512.  The unfused path
 // (conv_tc + dwconv5x5_tiled + conv_tc) stays for the taping forward of the attack path and for other shapes.
 //
-// Warp roles (288 threads): warp 0 = control (TMA producer + MMA issuer, one lane), warps 1-8 = SIMT (act, depthwise, epilogue).
+// Warp roles (416 threads): warp 0 = control (TMA producer + MMA issuer, one lane); warps 1-4 = activation (TMEM -> SiLU -> H, and
+// the final epilogue), one chunk ahead of warps 5-12 = depthwise (H -> A2): the MUFU-bound and the FMA-bound phases overlap.
 // Tiles: 8x8 maps: 2 images / CTA;  16x16: 1 image;  32x32: 8 output rows (+2 halo rows each side, expand recomputed 1.5x).
 #include <cuda.h>
 #include <stdlib.h>
@@ -22,7 +23,7 @@
 
 namespace ga {
 
-constexpr int MB_THREADS = 288;
+constexpr int MB_THREADS = 416;      // control warp + 4 activation warps + 8 depthwise warps
 
 template <int W_IMG> struct MbGeom;
 template <> struct MbGeom<8>  { static constexpr int IMGS = 2, R_OUT = 8,  HALO = 0, MT_IN = 1, MT_OUT = 1, STRIP_W = 2; };
@@ -33,7 +34,7 @@ struct MbParams {
   int N, H;                     // images, image height (= width = W_IMG)
   int hidden;                   // 6C (multiple of 64)
   const float* be;              // [hidden] expand bias
-  const float* dw_w;            // [25][hidden] depthwise taps
+  const float* dw_w;            // [hidden/64][25][64] depthwise taps, chunk-major (one 6400-byte bulk copy per chunk)
   const float* dw_b;            // [hidden]
   const float* bp;              // [C] project bias
   __nv_bfloat16* out;           // [N][H][W][C]
@@ -42,7 +43,36 @@ struct MbParams {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// mbarrier wait for the SIMT warps: back off between polls so that a waiting warp does not take issue slots from the warps of the
+// other role that share its scheduler (activation and depthwise warps wait for each other by design)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  while (!done) {
+    __nanosleep(100);
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
 __device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// 1-D bulk copy global -> shared, completion on an mbarrier (TMA without a tensor map)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+constexpr int DWW_BYTES = 25 * 64 * 4;
+// explicit shared-space accesses on 32-bit addresses: the tile pointers are derived from an aligned-up integer, so the compiler cannot
+// prove the address space and would emit generic LD/ST with 64-bit address arithmetic (measured: 2x the integer instructions + spills)
+__device__ __forceinline__ uint32_t lds_b32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f2(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_b32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 
 template <int C, int W_IMG, int NBUF>
 __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
@@ -62,7 +92,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
   static_assert(G::IMGS * R_IN * W_IMG == G::MT_IN * 128 && G::IMGS * G::R_OUT * W_IMG == G::MT_OUT * 128, "tile geometry");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* hdr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(hdr);
   uint64_t* x_full = bars + 0;
   uint64_t* we_full = bars + 1;          // [2]
@@ -74,13 +104,17 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
   uint64_t* a2_full = bars + 13;
   uint64_t* a2_empty = bars + 14;
   uint64_t* proj_full = bars + 15;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* dww_full = bars + 16;        // [2]
+  uint64_t* h_full = bars + 18;          // [2]
+  uint64_t* h_empty = bars + 20;         // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
   uint8_t* sX = hdr + 1024;
   uint8_t* sWe = sX + X_BYTES;
   uint8_t* sWp = sWe + NBUF * WE_BYTES;
   uint8_t* sH = sWp + NBUF * WP_BYTES;
-  uint8_t* sA2 = sH + H_BYTES;
-  float* s_be = reinterpret_cast<float*>(sA2 + A2_BYTES);
+  uint8_t* sA2 = sH + 2 * H_BYTES;                                   // H is double buffered (activation warps run one chunk ahead)
+  float* s_dww = reinterpret_cast<float*>(sA2 + A2_BYTES);          // [2][25][64] depthwise taps of the current / next chunk
+  float* s_be = s_dww + 2 * 25 * 64;
   float* s_dwb = s_be + p.hidden;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,7 +131,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     mbar_init(x_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&we_full[i], 1); mbar_init(&we_empty[i], 1); mbar_init(&wp_full[i], 1); mbar_init(&wp_empty[i], 1);
-      mbar_init(&exp_full[i], 1); mbar_init(&exp_empty[i], 8);
+      mbar_init(&exp_full[i], 1); mbar_init(&exp_empty[i], 4); mbar_init(&dww_full[i], 1);
+      mbar_init(&h_full[i], 4); mbar_init(&h_empty[i], 8);
     }
     mbar_init(a2_full, 1); mbar_init(a2_empty, 1); mbar_init(proj_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -106,7 +141,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    for (int i = threadIdx.x - 32; i < p.hidden; i += 256) { s_be[i] = p.be[i]; s_dwb[i] = p.dw_b[i]; }
+    for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) { s_be[i] = p.be[i]; s_dwb[i] = p.dw_b[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -122,6 +157,10 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
         const int b = j % NBUF;
         mbar_expect_tx(&we_full[b], WE_BYTES);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmWe, &we_full[b], sWe + b * WE_BYTES + kb * 8192, kb * 64, j * 64);
+      };
+      auto load_dww = [&](int j) {
+        mbar_expect_tx(&dww_full[j & 1], DWW_BYTES);
+        bulk_load_1d(s_dww + (j & 1) * 25 * 64, p.dw_w + (size_t)j * 25 * 64, DWW_BYTES, &dww_full[j & 1]);
       };
       auto load_wp = [&](int j) {
         const int b = j % NBUF;
@@ -155,6 +194,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
           if (j < nch) { mbar_wait(&wp_empty[(k - 1) % NBUF], ((k - 1) / NBUF) & 1); load_wp(j); }
         }
         mbar_wait(a2_full, k & 1);
+        if (k + 2 < nch) load_dww(k + 2);                 // every SIMT thread has taken chunk k's taps into registers
         mbar_wait(&wp_full[k % NBUF], (k / NBUF) & 1);
         tc_fence_after();
         const uint32_t wp_addr = smem_u32(sWp + (k % NBUF) * WP_BYTES);
@@ -178,6 +218,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
           else tma_load_4d(&tmX, x_full, dst, kb * 64, 0, y0 - G::HALO + m * (128 / W_IMG), n0);
         }
       for (int j = 0; j < NBUF && j < nch; ++j) { load_we(j); load_wp(j); }
+      for (int j = 0; j < 2 && j < nch; ++j) load_dww(j);
       mbar_wait(x_full, 0);
       expand(0);
       for (int k = 0; k < nch; ++k) {
@@ -186,19 +227,17 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       }
     }
     __syncwarp();
-  } else {
-    // ======================================================================= SIMT warps
-    const int sw = warp - 1;                 // 0..7
+  } else if (warp <= 4) {
+    // ======================================================================= activation warps (1-4, one per TMEM lane quadrant):
+    // expand accumulator -> + bias -> SiLU -> bf16 -> H[k & 1] (swizzled rows), one chunk ahead of the depthwise warps
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-    const int half = sw >> 2;                // column half of the 64-channel chunk / of the project accumulator
-    // depthwise strip of this warp
-    const int img = (W_IMG == 8) ? (sw >> 2) : 0;
-    const int cs = (W_IMG == 8) ? (sw & 3) * G::STRIP_W : sw * G::STRIP_W;
     for (int k = 0; k < nch; ++k) {
-      // ---- (1) expand accumulator -> + bias -> SiLU -> bf16 -> H (swizzled rows)
-      mbar_wait(&exp_full[k & 1], (k >> 1) & 1);
+      mbar_wait_backoff(&exp_full[k & 1], (k >> 1) & 1);
+      if (k >= 2) mbar_wait_backoff(&h_empty[k & 1], ((k - 2) >> 1) & 1);          // depthwise(k-2) has read this H buffer
       tc_fence_after();
-#pragma unroll 1
+      const uint32_t hb = smem_u32(sH) + (k & 1) * H_BYTES;
+      const uint32_t be_a = smem_u32(s_be) + k * 256;
+#pragma unroll
       for (int m = 0; m < G::MT_IN; ++m) {
         const int pin = m * 128 + q * 32 + lane;
         bool in_img = true;
@@ -206,80 +245,34 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
           const int y = y0 - G::HALO + (pin / W_IMG) % R_IN;
           in_img = y >= 0 && y < p.H;                     // halo rows outside the image are the conv's zero padding
         }
+        const uint32_t row = hb + pin * 128;
+        // all 64 columns of this lane's pixel in flight before ONE wait: a tcgen05.ld round trip costs ~1k cycles, and one warp per
+        // scheduler cannot hide it behind anything else
+        uint32_t r[4][16];
 #pragma unroll
-        for (int c16 = 0; c16 < 2; ++c16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (k & 1) * EXP_COLS + m * 64 + half * 32 + c16 * 16, r);
-          tmem_ld_wait();
+        for (int c16 = 0; c16 < 4; ++c16)
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (k & 1) * EXP_COLS + m * 64 + c16 * 16, r[c16]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float b0 = s_be[k * 64 + half * 32 + c16 * 16 + 2 * j], b1 = s_be[k * 64 + half * 32 + c16 * 16 + 2 * j + 1];
-            const float v0 = silu_fast(__uint_as_float(r[2 * j]) + b0), v1 = silu_fast(__uint_as_float(r[2 * j + 1]) + b1);
+            const float2 b = lds_f2(be_a + (c16 * 16 + 2 * j) * 4);
+            const float v0 = silu_fast(__uint_as_float(r[c16][2 * j]) + b.x), v1 = silu_fast(__uint_as_float(r[c16][2 * j + 1]) + b.y);
             pk[j] = in_img ? pack_bf16x2(v0, v1) : 0u;
           }
-          const uint32_t ch0 = (uint32_t)(half * 4 + c16 * 2);            // 16-byte chunk index inside the 128-byte row
-          uint8_t* row = sH + pin * 128;
-          *reinterpret_cast<uint4*>(row + (((ch0) ^ (pin & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(row + (((ch0 + 1) ^ (pin & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          const uint32_t ch0 = (uint32_t)(c16 * 2);                       // 16-byte chunk index inside the 128-byte row
+          sts_v4(row + (((ch0) ^ (pin & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          sts_v4(row + (((ch0 + 1) ^ (pin & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&exp_empty[k & 1]);
-      simt_bar();                                                          // H complete
-      // ---- (2) depthwise 5x5 + bias + SiLU: H -> A2 (project operand layout)
-      float2 wt[25];
-      {
-        const float* wsrc = p.dw_w + k * 64 + 2 * lane;
-#pragma unroll
-        for (int t = 0; t < 25; ++t) wt[t] = __ldg(reinterpret_cast<const float2*>(wsrc + (size_t)t * p.hidden));
-      }
-      float2 acc[G::R_OUT][G::STRIP_W];
-      {
-        const float2 b2 = make_float2(s_dwb[k * 64 + 2 * lane], s_dwb[k * 64 + 2 * lane + 1]);
-#pragma unroll
-        for (int oy = 0; oy < G::R_OUT; ++oy)
-#pragma unroll
-          for (int c = 0; c < G::STRIP_W; ++c) acc[oy][c] = b2;
-      }
-      const uint32_t lch = (uint32_t)(lane >> 2), lof = (uint32_t)(lane & 3) * 4;
-#pragma unroll
-      for (int iy = 0; iy < R_IN; ++iy) {
-        float2 in[G::STRIP_W + 4];
-#pragma unroll
-        for (int c = 0; c < G::STRIP_W + 4; ++c) {
-          const int x = cs - 2 + c;
-          const int pin = (img * R_IN + iy) * W_IMG + x;
-          in[c] = make_float2(0.f, 0.f);
-          if (x >= 0 && x < W_IMG)
-            in[c] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sH + pin * 128 + ((lch ^ (uint32_t)(pin & 7)) << 4) + lof));
-        }
-#pragma unroll
-        for (int ky = 0; ky < 5; ++ky) {
-          const int oy = iy - G::HALO - ky + 2;          // output row fed by input row iy through tap row ky
-          if (oy < 0 || oy >= G::R_OUT) continue;
-#pragma unroll
-          for (int c = 0; c < G::STRIP_W; ++c)
-#pragma unroll
-            for (int kx = 0; kx < 5; ++kx) acc[oy][c] = ffma2(wt[ky * 5 + kx], in[c + kx], acc[oy][c]);
-        }
-      }
-      if (k >= 1) mbar_wait(a2_empty, (k - 1) & 1);                        // project(k-1) has consumed A2
-#pragma unroll
-      for (int oy = 0; oy < G::R_OUT; ++oy)
-#pragma unroll
-        for (int c = 0; c < G::STRIP_W; ++c) {
-          const int pout = (img * G::R_OUT + oy) * W_IMG + cs + c;
-          *reinterpret_cast<uint32_t*>(sA2 + pout * 128 + ((lch ^ (uint32_t)(pout & 7)) << 4) + lof) =
-              pack_bf16x2(silu_fast(acc[oy][c].x), silu_fast(acc[oy][c].y));
-        }
-      fence_proxy_async_smem();                                            // generic-proxy writes -> visible to the MMA (async proxy)
-      simt_bar();                                                          // A2 complete; H free for the next chunk
-      if (threadIdx.x == 32) mbar_arrive(a2_full);
+      if (lane == 0) { mbar_arrive(&exp_empty[k & 1]); mbar_arrive(&h_full[k & 1]); }
     }
-    // ---- (3) project accumulator -> + bias -> r (bf16) -> HBM
-    mbar_wait(proj_full, 0);
+    // ---- project accumulator -> + bias -> r (bf16) -> HBM
+    mbar_wait_backoff(proj_full, 0);
     tc_fence_after();
     const int64_t pix0 = (W_IMG == 32) ? ((int64_t)n0 * p.H + y0) * W_IMG : (int64_t)n0 * p.H * W_IMG;
     const int64_t total_pix = (int64_t)p.N * p.H * W_IMG;
@@ -287,20 +280,100 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     for (int m = 0; m < G::MT_OUT; ++m) {
       const int64_t pix = pix0 + m * 128 + q * 32 + lane;
 #pragma unroll 1
-      for (int c0 = half * (C / 2); c0 < (half + 1) * (C / 2); c0 += 16) {
+      for (int c0 = 0; c0 < C; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + PROJ_OFF + m * C + c0, r);
         tmem_ld_wait();
         if (pix < total_pix) {
           uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + __ldg(p.bp + c0 + 2 * j), __uint_as_float(r[2 * j + 1]) + __ldg(p.bp + c0 + 2 * j + 1));
+          for (int j = 0; j < 8; ++j) {
+            const float2 b = __ldg(reinterpret_cast<const float2*>(p.bp + c0 + 2 * j));
+            pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + b.x, __uint_as_float(r[2 * j + 1]) + b.y);
+          }
           uint4* o = reinterpret_cast<uint4*>(p.out + pix * C + c0);
           o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
+    }
+  } else {
+    // ======================================================================= depthwise warps (5-12): 5x5 + bias + SiLU: H -> A2
+    const int sw = warp - 5;                 // 0..7
+    // strip of this warp
+    const int img = (W_IMG == 8) ? (sw >> 2) : 0;
+    const int cs = (W_IMG == 8) ? (sw & 3) * G::STRIP_W : sw * G::STRIP_W;
+    // per-column shared-memory addresses of this lane's channel pair: pixel p = (row)*W + x sits in 128-byte row p, its 16-byte chunk
+    // j at (j ^ (p & 7)); W is a multiple of 8, so p & 7 == x & 7 and only the row term changes inside the loops
+    const uint32_t lch = (uint32_t)(lane >> 2), lof = (uint32_t)(lane & 3) * 4;
+    uint32_t h_col[G::STRIP_W + 4];
+    bool col_ok[G::STRIP_W + 4];
+    uint32_t a2_col[G::STRIP_W];
+#pragma unroll
+    for (int c = 0; c < G::STRIP_W + 4; ++c) {
+      const int x = cs - 2 + c;
+      col_ok[c] = x >= 0 && x < W_IMG;
+      h_col[c] = (uint32_t)((img * R_IN * W_IMG + x) * 128) + ((lch ^ (uint32_t)(x & 7)) << 4) + lof;
+    }
+#pragma unroll
+    for (int c = 0; c < G::STRIP_W; ++c)
+      a2_col[c] = smem_u32(sA2) + (img * G::R_OUT * W_IMG + cs + c) * 128 + ((lch ^ (uint32_t)((cs + c) & 7)) << 4) + lof;
+    for (int k = 0; k < nch; ++k) {
+      float2 wt[25];
+      {
+        mbar_wait_backoff(&dww_full[k & 1], (k >> 1) & 1);
+        const uint32_t wsrc = smem_u32(s_dww) + ((k & 1) * 25 * 64 + 2 * lane) * 4;
+#pragma unroll
+        for (int t = 0; t < 25; ++t) wt[t] = lds_f2(wsrc + t * 256);
+      }
+      const float2 b2 = lds_f2(smem_u32(s_dwb) + (k * 64 + 2 * lane) * 4);
+      mbar_wait_backoff(&h_full[k & 1], (k >> 1) & 1);
+      const uint32_t hb = smem_u32(sH) + (k & 1) * H_BYTES;
+      // the strip's rows are produced in passes of RP rows (RP + 4 input rows each): RP x STRIP_W accumulators + 25 taps stay in
+      // registers under the 128-register cap of a 13-warp CTA (16K registers per SM sub-partition, 4 warps on one of them)
+      constexpr int RP = (G::R_OUT * G::STRIP_W > 16) ? G::R_OUT / 2 : G::R_OUT;
+#pragma unroll
+      for (int pass = 0; pass < G::R_OUT / RP; ++pass) {
+        float2 acc[RP][G::STRIP_W];
+#pragma unroll
+        for (int oy = 0; oy < RP; ++oy)
+#pragma unroll
+          for (int c = 0; c < G::STRIP_W; ++c) acc[oy][c] = b2;
+#pragma unroll
+        for (int ir = 0; ir < RP + 4; ++ir) {
+          const int iy = pass * RP + G::HALO - 2 + ir;     // input row (H-tile coordinates) feeding this pass
+          if (iy < 0 || iy >= R_IN) continue;             // above / below the tile: zero rows (whole-image tiles only)
+          float2 in[G::STRIP_W + 4];
+#pragma unroll
+          for (int c = 0; c < G::STRIP_W + 4; ++c) {
+            in[c] = make_float2(0.f, 0.f);
+            if (col_ok[c])
+              in[c] = bf2_to_f2(lds_b32(hb + h_col[c] + iy * (W_IMG * 128)));
+          }
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) {
+            const int oy = ir - ky;                       // output row (inside the pass) fed by input row ir through tap row ky
+            if (oy < 0 || oy >= RP) continue;
+#pragma unroll
+            for (int c = 0; c < G::STRIP_W; ++c)
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) acc[oy][c] = ffma2(wt[ky * 5 + kx], in[c + kx], acc[oy][c]);
+          }
+        }
+        if (pass == G::R_OUT / RP - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&h_empty[k & 1]);                     // this warp is done reading H[k & 1]
+        }
+        if (pass == 0 && k >= 1) mbar_wait_backoff(a2_empty, (k - 1) & 1); // project(k-1) has consumed A2
+#pragma unroll
+        for (int oy = 0; oy < RP; ++oy)
+#pragma unroll
+          for (int c = 0; c < G::STRIP_W; ++c)
+            sts_b32(a2_col[c] + (pass * RP + oy) * (W_IMG * 128), pack_bf16x2(silu_fast(acc[oy][c].x), silu_fast(acc[oy][c].y)));
+      }
+      fence_proxy_async_smem();                                            // generic-proxy writes -> visible to the MMA (async proxy)
+      simt_bar();                                                          // A2 complete (all 8 depthwise warps)
+      if (threadIdx.x == 5 * 32) mbar_arrive(a2_full);
     }
   }
   tc_fence_before();
@@ -354,8 +427,8 @@ template <int C, int W_IMG, int NBUF>
 static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, const MbParams& p, cudaStream_t s) {
   using G = MbGeom<W_IMG>;
   constexpr int KB = C / 64;
-  const int smem = 1024 /*align*/ + 1024 /*header*/ + G::MT_IN * KB * 16384 + NBUF * (KB * 8192 + C * 128) + G::MT_IN * 16384 +
-                   G::MT_OUT * 16384 + 2 * p.hidden * 4;
+  const int smem = 1024 /*align*/ + 1024 /*header*/ + G::MT_IN * KB * 16384 + NBUF * (KB * 8192 + C * 128) + 2 * G::MT_IN * 16384 +
+                   G::MT_OUT * 16384 + 2 * DWW_BYTES + 2 * p.hidden * 4;
   GA_CHECK(smem <= 227 * 1024, "ga_mbconv_fused: shared memory request %d too large", smem);
   static int configured = 0;
   if (configured < smem) {
@@ -399,6 +472,6 @@ extern "C" int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const floa
   p.out = (__nv_bfloat16*)out->data;
   cudaStream_t s = (cudaStream_t)stream;
   if (x->w == 8) return launch_mbconv<256, 8, 1>(x, we_tc, wp_tc, p, s);
-  if (x->w == 16) return launch_mbconv<128, 16, 2>(x, we_tc, wp_tc, p, s);
+  if (x->w == 16) return launch_mbconv<128, 16, 1>(x, we_tc, wp_tc, p, s);
   return launch_mbconv<64, 32, 2>(x, we_tc, wp_tc, p, s);
 }

@@ -29,7 +29,7 @@ class _Enc:
 
 
 class _Dec:
-    __slots__ = ("e", "dw_w", "dw_b", "p", "se", "skip", "up", "e_d", "p_d", "skip_d", "dw_wT")
+    __slots__ = ("e", "dw_w", "dw_wc", "dw_b", "p", "se", "skip", "up", "e_d", "p_d", "skip_d", "dw_wT")
 
 
 class NvaeEngine:
@@ -92,6 +92,7 @@ class NvaeEngine:
         a2, b2 = f.bn(f"{p}.residual.{5 + o}")
         wd = wd[:, 0] * a2.view(-1, 1, 1)
         d.dw_w = f.dev32(wd.permute(1, 2, 0).reshape(25, -1))        # [25][H]
+        d.dw_wc = ops.dw_weights_chunked(d.dw_w) if d.dw_w.shape[1] % 64 == 0 else None     # chunk-major copy for the fused cell kernel
         d.dw_b = f.dev32(b2)
         wp = f.f64(f"{p}.residual.{7 + o}.weight")                   # [Cout, H, 1, 1]
         a3, b3 = f.bn(f"{p}.residual.{8 + o}")
@@ -240,8 +241,8 @@ class NvaeEngine:
     def _dec_cell(self, x32, xa, d: _Dec, rec):
         """x32: fp32 residual stream; xa: same values in the activation dtype (GEMM operand)."""
         taping = rec is not None
-        if not taping and self.fuse_cells and self.bf16 and not d.up and ops.mbconv_fused_supported(xa, d.e, d.p):
-            r = ops.mbconv_fused(xa, d.e, d.dw_w, d.dw_b, d.p)     # expand -> dw5x5 -> project in one kernel, hidden tensor on chip
+        if not taping and self.fuse_cells and self.bf16 and not d.up and d.dw_wc is not None and ops.mbconv_fused_supported(xa, d.e, d.p):
+            r = ops.mbconv_fused(xa, d.e, d.dw_wc, d.dw_b, d.p)     # expand -> dw5x5 -> project in one kernel, hidden tensor on chip
             sums = ops.channel_sum(r)
             out, out2, _, _ = ops.se_residual(r, sums, d.se, 0.1, x32, torch.float32, want_out2=True)
             return out, out2

@@ -211,11 +211,17 @@ def mbconv_fused_supported(x: torch.Tensor, e: ConvLayer, p: ConvLayer) -> bool:
     return bool(_lib.lib().ga_mbconv_fused_supported(gt(x), e.cout))
 
 
+def dw_weights_chunked(dw_w: torch.Tensor) -> torch.Tensor:
+    """[25][hidden] depthwise taps -> chunk-major [hidden/64][25][64] (one contiguous 6400-byte block per 64-channel chunk)"""
+    t, hidden = dw_w.shape
+    return dw_w.reshape(t, hidden // 64, 64).permute(1, 0, 2).contiguous()
+
+
 @_timed("mbconv_fused")
-def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer) -> torch.Tensor:
-    """decoder-cell body in ONE kernel: project(SiLU(dw5x5(SiLU(expand(x)))))  -> r (bf16)"""
+def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer) -> torch.Tensor:
+    """decoder-cell body in ONE kernel: project(SiLU(dw5x5(SiLU(expand(x)))))  -> r (bf16); dw_w_chunked = dw_weights_chunked(dw_w)"""
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    _lib.check(_lib.lib().ga_mbconv_fused(gt(x), e.w_tc.data_ptr(), ptr(e.bias), ptr(dw_w), ptr(dw_b), p.w_tc.data_ptr(), ptr(p.bias),
+    _lib.check(_lib.lib().ga_mbconv_fused(gt(x), e.w_tc.data_ptr(), ptr(e.bias), ptr(dw_w_chunked), ptr(dw_b), p.w_tc.data_ptr(), ptr(p.bias),
                                           e.cout, gt(out), stream()), "mbconv_fused")
     return out
 

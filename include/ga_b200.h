@@ -112,7 +112,7 @@ int ga_dwconv5x5_ex(const ga_tensor* in, const ga_tensor* mul, const float* weig
 
 /* ---- fused decoder-cell body: r = project1x1(SiLU(dw5x5(SiLU(expand1x1(x) + be)) + dw_b)) + bp  (architecture.py:164-173, the four
  *      BatchNorms folded into the convs).  The 6C-channel hidden tensor stays in shared / tensor memory (tcgen05 + TMA).
- *      x, out: bf16 NHWC; we_tc [hidden][C], wp_tc [C][hidden] bf16 K-major; dw_w [25][hidden] fp32.  Supported: square maps of
+ *      x, out: bf16 NHWC; we_tc [hidden][C], wp_tc [C][hidden] bf16 K-major; dw_w chunk-major [hidden/64][25][64] fp32.  Supported: square maps of
  *      8 / 16 / 32 pixels with C = 256 / 128 / 64 (the three decoder scales of the 64x64 NVAE); other shapes use the three kernels. */
 int ga_mbconv_fused_supported(const ga_tensor* x, int hidden);
 int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,

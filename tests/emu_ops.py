@@ -182,8 +182,13 @@ def mbconv_fused_supported(x, e, p):
     return x.dtype == torch.bfloat16 and e.w_tc is not None and p.w_tc is not None and h == w and (w, c) in ((8, 256), (16, 128), (32, 64))
 
 
-def mbconv_fused(x, e, dw_w, dw_b, p):
+def dw_weights_chunked(dw_w):
+    return real_ops.dw_weights_chunked(dw_w)
+
+
+def mbconv_fused(x, e, dw_w_chunked, dw_b, p):
     _launches[0] += 1
+    dw_w = dw_w_chunked.permute(1, 0, 2).reshape(25, -1)
     h1, _ = conv2d_tc(x, e)
     _launches[0] -= 1
     h2 = dwconv5x5(h1, dw_w, dw_b, ACT_SILU, False, torch.bfloat16)

@@ -40,10 +40,10 @@ def _dev(L):
 def test_mbconv_fused_matches_three_kernels(n, w, c, hidden):
     e, dw_w, dw_b, p = _cell(c, hidden, seed=n + w + hidden)
     x = torch.randn(n, w, w, c, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
-    ref = emu_ops.mbconv_fused(x, e, dw_w, dw_b, p).float()
+    ref = emu_ops.mbconv_fused(x, e, ops.dw_weights_chunked(dw_w), dw_b, p).float()
     ed, pd, xd, wd, bd = _dev(e), _dev(p), x.to(DEV), dw_w.to(DEV), dw_b.to(DEV)
     assert ops.mbconv_fused_supported(xd, ed, pd)
-    got = ops.mbconv_fused(xd, ed, wd, bd, pd)
+    got = ops.mbconv_fused(xd, ed, ops.dw_weights_chunked(wd), bd, pd)
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     err = (got.float().cpu() - ref).abs().max().item()
