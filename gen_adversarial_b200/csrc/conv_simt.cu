@@ -235,70 +235,105 @@ __global__ void __launch_bounds__(NT) conv_igemm_simt_kernel(ConvParams p) {
   }
 }
 
-// ---------------------------------------------------------------------------- stem: 3x3, stride 1, pad 1, Cin <= 4
-// (NVAE init_conv 3->32, VGG features.0 3->64).  K = 27 is far too short for the tiled GEMM above (it ran 25x over its
-// HBM floor); here a warp owns 32 consecutive pixels x 8 output channels, weights are broadcast from shared memory.
-template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) conv3x3_stem_kernel(const TIn* __restrict__ in, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, int post_act, int N, int H, int W, int Cin,
-                                                           int Cout, TOut* __restrict__ out) {
-  extern __shared__ float s_w[];                      // [9*Cin][Cout] + bias[Cout]
-  const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < K * Cout; i += 256) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += 256) s_w[K * Cout + i] = bias ? bias[i] : 0.f;
+// ---------------------------------------------------------------------------- stems: Cin <= 4, 3x3 stride 1 (NVAE init_conv 3->32,
+// VGG features.0 3->64, IR-SE50 input_layer 3->64 + PReLU) and 7x7 stride 2 (torchvision ResNet conv1 3->64 + ReLU).
+// K = 27 / 147 is far too short for the tiled GEMM above.  One thread owns one output pixel and ALL output channels (COUT fp32
+// accumulators): every input value is loaded once, weights are broadcast from shared memory as float4 (4 FMA per LDS.128), the block
+// is persistent (grid-stride over 256-pixel chunks) so the weight stage-in is paid once, and a thread's COUT outputs are one
+// contiguous run of the NHWC tensor.
+template <typename TIn, typename TOut, int KS, int STRIDE, int COUT>
+__global__ void __launch_bounds__(256) conv_stem_kernel(const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        const float* __restrict__ slope, int post_act, int N, int H, int W, int Cin, int Ho,
+                                                        int Wo, TOut* __restrict__ out) {
+  extern __shared__ float s_w[];                      // [KS*KS*Cin][COUT] | bias[COUT] | slope[COUT]
+  constexpr int PAD = KS / 2;
+  const int K = KS * KS * Cin;
+  for (int i = threadIdx.x; i < K * COUT; i += 256) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += 256) {
+    s_w[K * COUT + i] = bias ? bias[i] : 0.f;
+    s_w[(K + 1) * COUT + i] = slope ? slope[i] : 0.f;
+  }
   __syncthreads();
-  const int groups = Cout >> 3;                       // 8 output channels per thread
-  const int warps_per_block = 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t total_pix = (int64_t)N * H * W;
-  // work item = (32-pixel chunk, channel group); consecutive warps take consecutive groups of the same chunk
-  const int64_t item = (int64_t)blockIdx.x * warps_per_block + warp;
-  const int64_t chunk = item / groups;
-  const int cg = (int)(item % groups);
-  const int64_t pix = chunk * 32 + lane;
-  if (pix >= total_pix) return;
-  const int x = (int)(pix % W);
-  const int y = (int)((pix / W) % H);
-  const int64_t n = pix / ((int64_t)W * H);
-  float acc[8];
+  const int64_t total_pix = (int64_t)N * Ho * Wo;
+  for (int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x; pix < total_pix; pix += (int64_t)gridDim.x * 256) {
+    const int x = (int)(pix % Wo);
+    const int y = (int)((pix / Wo) % Ho);
+    const int64_t n = pix / ((int64_t)Wo * Ho);
+    float acc[COUT];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = s_w[K * Cout + cg * 8 + j];
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = y + ky - 1;
-    if (iy < 0 || iy >= H) continue;
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = x + kx - 1;
-      if (ix < 0 || ix >= W) continue;
-      const TIn* src = in + ((n * H + iy) * W + ix) * Cin;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float v = ldf<TIn>(src + ci);
-        const float* wk = s_w + ((ky * 3 + kx) * Cin + ci) * Cout + cg * 8;
-        const float4 w0 = *reinterpret_cast<const float4*>(wk), w1 = *reinterpret_cast<const float4*>(wk + 4);
-        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    for (int j = 0; j < COUT; ++j) acc[j] = s_w[K * COUT + j];
+#pragma unroll 1
+    for (int ky = 0; ky < KS; ++ky) {
+      const int iy = y * STRIDE + ky - PAD;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll 1
+      for (int kx = 0; kx < KS; ++kx) {
+        const int ix = x * STRIDE + kx - PAD;
+        if (ix < 0 || ix >= W) continue;
+        const TIn* src = in + ((n * H + iy) * W + ix) * Cin;
+        const float* wk = s_w + (ky * KS + kx) * Cin * COUT;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = ldf<TIn>(src + ci);
+#pragma unroll
+          for (int j = 0; j < COUT; j += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + ci * COUT + j);
+            acc[j] = fmaf(v, w4.x, acc[j]); acc[j + 1] = fmaf(v, w4.y, acc[j + 1]);
+            acc[j + 2] = fmaf(v, w4.z, acc[j + 2]); acc[j + 3] = fmaf(v, w4.w, acc[j + 3]);
+          }
+        }
       }
     }
-  }
-  float o0[4], o1[4];
+    if (post_act == GA_ACT_PRELU) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { o0[j] = acc[j]; o1[j] = acc[4 + j]; }
-  apply_act_n<4>(o0, post_act);
-  apply_act_n<4>(o1, post_act);
-  TOut* dst = out + pix * Cout + cg * 8;
-  st4<TOut>(dst, o0);
-  st4<TOut>(dst + 4, o1);
+      for (int j = 0; j < COUT; ++j) acc[j] = acc[j] > 0.f ? acc[j] : s_w[(K + 1) * COUT + j] * acc[j];
+    } else {
+      apply_act_n<COUT>(acc, post_act);
+    }
+    TOut* dst = out + pix * COUT;
+#pragma unroll
+    for (int j = 0; j < COUT; j += 4) {
+      const float o[4] = {acc[j], acc[j + 1], acc[j + 2], acc[j + 3]};
+      st4<TOut>(dst + j, o);
+    }
+  }
+}
+
+template <typename TIn, typename TOut, int KS, int STRIDE, int COUT>
+static int launch_stem_t(const ga_tensor* in, const ga_conv_desc* d, const ga_tensor* out, cudaStream_t s) {
+  const int K = KS * KS * in->c;
+  const int64_t total_pix = (int64_t)out->n * out->h * out->w;
+  const size_t smem = (size_t)(K + 2) * COUT * sizeof(float);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    GA_CUDA(cudaFuncSetAttribute(conv_stem_kernel<TIn, TOut, KS, STRIDE, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int sms = 148;
+  const int64_t want = (total_pix + 255) / 256;
+  const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);       // persistent: <= 8 blocks per SM
+  conv_stem_kernel<TIn, TOut, KS, STRIDE, COUT><<<grid, 256, smem, s>>>((const TIn*)in->data, (const float*)d->weight, d->bias, d->act_slope,
+                                                                       d->post_act, in->n, in->h, in->w, in->c, out->h, out->w,
+                                                                       (TOut*)out->data);
+  GA_LAUNCH_OK();
+  return 0;
 }
 
 template <typename TIn, typename TOut>
 static int launch_stem(const ga_tensor* in, const ga_conv_desc* d, const ga_tensor* out, cudaStream_t s) {
-  const int K = 9 * in->c, Cout = out->c;
-  const int64_t total_pix = (int64_t)out->n * out->h * out->w;
-  const int64_t items = ((total_pix + 31) / 32) * (Cout / 8);
-  const size_t smem = (size_t)(K + 1) * Cout * sizeof(float);
-  conv3x3_stem_kernel<TIn, TOut><<<cdiv(items, 8), 256, smem, s>>>((const TIn*)in->data, (const float*)d->weight, d->bias, d->post_act,
-                                                                  in->n, in->h, in->w, in->c, Cout, (TOut*)out->data);
-  GA_LAUNCH_OK();
-  return 0;
+  if (d->kh == 3 && d->stride == 1) {
+    if (out->c == 32) return launch_stem_t<TIn, TOut, 3, 1, 32>(in, d, out, s);
+    if (out->c == 64) return launch_stem_t<TIn, TOut, 3, 1, 64>(in, d, out, s);
+  }
+  if (d->kh == 7 && d->stride == 2 && out->c == 64) return launch_stem_t<TIn, TOut, 7, 2, 64>(in, d, out, s);
+  return -1;     // not a stem shape
+}
+
+static bool is_stem(const ga_tensor* in, const ga_conv_desc* d, const ga_tensor* add, const ga_tensor* out) {
+  if (in->c > 4 || d->up != 1 || d->pre_op != GA_PRE_NONE || add != nullptr || d->mul != nullptr || d->dact_out != nullptr ||
+      d->act_after_add || numel(out) == 0 || d->kh != d->kw)
+    return false;
+  if (d->kh == 3 && d->stride == 1 && d->pad == 1) return out->c == 32 || out->c == 64;
+  return d->kh == 7 && d->stride == 2 && d->pad == 3 && out->c == 64;
 }
 
 }  // namespace ga
@@ -319,11 +354,10 @@ extern "C" int ga_conv2d_simt(const ga_tensor* in, const ga_conv_desc* d, const 
            in->n, Ho, Wo);
   GA_CHECK(d->pre_op < GA_PRE_AFFINE_SILU || (d->pre_scale && d->pre_shift), "ga_conv2d_simt: affine pre-op needs scale/shift");
   if (add) GA_CHECK(same_shape(add, out), "ga_conv2d_simt: add shape mismatch");
-  // stem fast path: 3x3 / stride 1 / pad 1 / Cin <= 4 / no extras
-  if (d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && d->up == 1 && in->c <= 4 && (out->c % 8) == 0 && out->c <= 256 &&
-      d->pre_op == GA_PRE_NONE && add == nullptr && d->mul == nullptr && d->dact_out == nullptr && d->post_act != GA_ACT_PRELU &&
-      !d->act_after_add && numel(out) > 0) {
+  // stem fast path: Cin <= 4, 3x3 stride 1 or 7x7 stride 2, no extras
+  if (is_stem(in, d, add, out)) {
     cudaStream_t s = (cudaStream_t)stream;
+    GA_CHECK(d->post_act != GA_ACT_PRELU || d->act_slope != nullptr, "ga_conv2d_simt: PReLU needs act_slope");
     if (in->dtype == GA_F32 && out->dtype == GA_F32) return launch_stem<float, float>(in, d, out, s);
     if (in->dtype == GA_BF16 && out->dtype == GA_BF16) return launch_stem<__nv_bfloat16, __nv_bfloat16>(in, d, out, s);
     if (in->dtype == GA_BF16 && out->dtype == GA_F32) return launch_stem<__nv_bfloat16, float>(in, d, out, s);

@@ -142,6 +142,10 @@ class E4EEncoderEngine:
         self.style_count = 2 * int(math.log2(stylegan_size)) - 2
         self.coarse_ind, self.middle_ind = 3, 7
         self.slope = torch.full((512,), 0.01, dtype=torch.float32, device=self.device)        # nn.LeakyReLU() default
+        # (measured: fp32 tails / more fp32 heads do not move the end-to-end bf16 error, which is dominated by the 48 bf16 convs of the
+        # backbone -- DESIGN.md section 2; the knobs stay for experiments)
+        self.fp32_tail_hw = int(__import__("os").environ.get("GA_E4E_FP32_TAIL_HW", "0"))
+        self.fp32_heads = int(__import__("os").environ.get("GA_E4E_FP32_HEADS", "1"))      # heads fed by c3 that run fully in fp32
         self.heads: List[_Head] = []
         for i in range(self.style_count):
             spatial = 16 if i < self.coarse_ind else (32 if i < self.middle_ind else 64)
@@ -162,11 +166,10 @@ class E4EEncoderEngine:
     _conv = IrSe50Backbone._conv
 
     def _head(self, feat, hd: _Head, out):
-        """map2style head.  bf16 mode: the convs on maps of 4x4 and smaller (the last two) and the EqualLinear run in fp32 -- 0.3% of the
-        head's FLOPs, and the W+ codes they produce steer every modulated conv of the generator"""
+        """map2style head.  bf16 mode: the final EqualLinear (and, optionally, the convs on maps <= fp32_tail_hw) run in fp32"""
         x = feat
         for L in hd.convs:
-            if self.bf16 and (x.shape[1] <= 4 or x.dtype == torch.float32):
+            if self.bf16 and (x.shape[1] <= self.fp32_tail_hw or x.dtype == torch.float32):
                 x = ops.conv2d_simt(x, L, torch.float32)
             else:
                 x = self._conv(x, L)
@@ -186,7 +189,7 @@ class E4EEncoderEngine:
             elif i == self.middle_ind:
                 feat = conv1x1_any(self, c1, self.lat2, add=ops.upsample_bilinear2x(p2))
             # head 0 (w0, added to all 18 codes) runs in fp32 from the fp32 residual stream in both modes: 1% of the encoder's FLOPs
-            self._head(self.backbone.c3_f32 if (i == 0 and self.bf16) else feat, hd, heads[i])
+            self._head(self.backbone.c3_f32 if (i < self.fp32_heads and self.bf16) else feat, hd, heads[i])
         return ops.codes_assemble(heads, True, True, self.latent_avg, b, self.style_count, 512)
 
 

@@ -217,12 +217,17 @@ def dw_weights_chunked(dw_w: torch.Tensor) -> torch.Tensor:
     return dw_w.reshape(t, hidden // 64, 64).permute(1, 0, 2).contiguous()
 
 
-@_timed("mbconv_fused")
 def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer) -> torch.Tensor:
     """decoder-cell body in ONE kernel: project(SiLU(dw5x5(SiLU(expand(x)))))  -> r (bf16); dw_w_chunked = dw_weights_chunked(dw_w)"""
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_mbconv_fused(gt(x), e.w_tc.data_ptr(), ptr(e.bias), ptr(dw_w_chunked), ptr(dw_b), p.w_tc.data_ptr(), ptr(p.bias),
                                           e.cout, gt(out), stream()), "mbconv_fused")
+    if e0 is not None:
+        n, h, w, c = x.shape
+        m, hid = n * h * w, e.cout
+        # algorithmic work: two 1x1 GEMMs on the tensor cores + 25 MAC per hidden element on the fp32 pipe; compulsory HBM traffic: x in, r out
+        TIMER.stop(e0, f"fused:mbconv hw{h} c{c} hidden{hid}", 2.0 * m * hid * c * 2 + 2.0 * m * hid * 25, 2.0 * m * c * 2 + 2.0 * hid * c * 2)
     return out
 
 
@@ -234,7 +239,6 @@ def channel_sum(r: torch.Tensor) -> torch.Tensor:
     return sums
 
 
-@_timed("se_residual")
 def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
                 act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op: int = ACT_SILU):
     """se = (w1, b1, w2, b2) fp32 device tensors (biases may be None).  -> (out, out2|None, act|None, gate|None);
@@ -245,9 +249,13 @@ def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, wa
     act = torch.empty(r.shape, device=r.device, dtype=act_dtype) if act_affine is not None else None
     gate = torch.empty((r.shape[0], r.shape[3]), device=r.device, dtype=torch.float32) if want_gate else None
     a_s, a_b = act_affine if act_affine is not None else (None, None)
+    e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_se_residual_fwd(gt(r), ptr(sums), ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[0], res_scale,
                                              gt(skip), gt(out), gt(out2), gt(act), ptr(a_s), ptr(a_b), act_op, ptr(gate), stream()),
                "se_residual")
+    if e0 is not None:     # HBM-bound: every operand is read or written exactly once
+        by = sum(t.numel() * t.element_size() for t in (r, skip, out, out2, act) if t is not None)
+        TIMER.stop(e0, f"hbm:se_residual {tuple(r.shape)}", 0.0, float(by))
     return out, out2, act, gate
 
 

@@ -171,7 +171,7 @@ class StyleGan2Engine:
         # conv outputs at <= 128^2 stay fp32 until the fused epilogue (one bf16 rounding less per layer where it is almost free:
         # errors made in the early layers pass through every later one)
         b, h, w, _ = xs.shape
-        f32 = self.bf16 and h * (2 if s.up else 1) <= 128
+        f32 = self.bf16 and h * (2 if s.up else 1) <= self.f32_conv_out_res
         if not s.up:
             y = self._conv(xs, s.conv, want_f32=f32)
             phases = False
@@ -218,6 +218,7 @@ class StyleGan2Engine:
         self._run_blocks(j + 1, x, skip, st, lo, sink, outs)
 
     max_chunk = None
+    f32_conv_out_res = int(__import__("os").environ.get("GA_SG_F32_RES", "128"))
 
     def synthesis(self, latent: torch.Tensor, sink=None):
         """latent: (B, >= n_latent, style_dim) fp32 -> list of RGB image slices NHWC (n_i, size, size, 4) fp32 in batch order (4th
