@@ -148,7 +148,7 @@ _PROTOS = {
     "ga_pixelnorm": (c_int, [c_void_p, c_int, c_int, T, c_void_p]),
     "ga_style_demod": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ga_channel_scale": (c_int, [T, c_void_p, T, c_void_p]),
-    "ga_styled_bias_act": (c_int, [T, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, T, c_void_p, T, c_void_p, T, c_void_p]),
+    "ga_styled_bias_act": (c_int, [T, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, T, c_void_p, c_void_p, T, c_void_p, T, c_void_p]),
     "ga_upfirdn2d": (c_int, [T, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, T, c_void_p]),
     "ga_avgpool_to_nchw": (c_int, [T, c_int, c_int, c_void_p, c_void_p]),
     "ga_latent_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -173,7 +173,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 6:
+    if L.ga_abi_version() != 7:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -283,8 +283,13 @@ __global__ void __launch_bounds__(256) latent_mix_bwd_kernel(const void* gz, int
     return;
   }
   const int64_t e_idx = (((int64_t)zc) * H + y) * W + x;
-  const float e = eps != nullptr ? eps[n * Z * H * W + e_idx]
-                                 : philox_normal(seed, (uint64_t)(sample0 + n) * 64ull + (uint64_t)(level + 1), (uint64_t)e_idx);
+  float e;
+  if (eps != nullptr) e = eps[n * Z * H * W + e_idx];
+  else {                                             // same stream layout as the forward kernel (latent_eps4)
+    float z4[4];
+    latent_eps4(seed, (uint64_t)(sample0 + n) * 64ull + (uint64_t)(level + 1), zc >> 2, y * W + x, H * W, z4);
+    e = z4[zc & 3];
+  }
   const float mu_p = pp[pix * 2 * Z + zc], ls_p = pp[pix * 2 * Z + Z + zc];
   const float d_enc = (1.f - a) * sc5_grad(mu_p + mu_q);
   g_q[idx] = g * d_enc;

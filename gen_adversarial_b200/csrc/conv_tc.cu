@@ -31,6 +31,7 @@ constexpr int TC_THREADS = 192;
 
 struct TcParams {
   int taps, kw, pad, stride;  // filter taps of source 1; stride 1 or 2 (TMA element strides do the decimation)
+  int k32;                    // 1: 32-channel K blocks (64-byte swizzle) for Cin = 32, 96, ...: no half-empty 64-channel boxes
   int cin, kc1, kc2;          // channels of source 1, its 64-blocks per tap, 64-blocks of source 2
   int bw, bh, bn;             // pixel box of one M tile (bw*bh*bn == 128)
   int tiles_x, tiles_y;       // tiles per image row / column (bn == 1) -- else whole images per tile
@@ -68,7 +69,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   constexpr int HDR_BYTES = GENERAL_ACT ? 4096 : 2048;
   uint8_t* smem = smem_hdr + HDR_BYTES;              // operand ring / epilogue staging (1024-aligned)
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * TC_A_STAGE_BYTES;
+  // 32-channel K blocks use half-size stages (more co-resident CTAs for the small-channel, high-resolution layers)
+  const int a_stride = p.k32 ? TC_A_STAGE_BYTES / 2 : TC_A_STAGE_BYTES;
+  const int b_stride = p.k32 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+  uint8_t* smem_b = smem + STAGES * a_stride;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_hdr);   // header: barriers, TMEM address; bias tile after the ring
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -116,22 +120,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   if (warp == 0) {
     // ===================================================================== TMA producer
     int stage = 0; uint32_t phase = 0;
+    const int bk = p.k32 ? 32 : TC_BLOCK_K;
     for (int kb = 0; kb < num_kb; ++kb) {
       if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-        uint8_t* a_dst = smem_a + stage * TC_A_STAGE_BYTES;
-        uint8_t* b_dst = smem_b + stage * B_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], p.k32 ? STAGE_BYTES / 2 : STAGE_BYTES);
+        uint8_t* a_dst = smem_a + stage * a_stride;
+        uint8_t* b_dst = smem_b + stage * b_stride;
         int kcoord;
         if (kb < p.taps * p.kc1) {
           const int tap = kb / p.kc1, cc = kb - tap * p.kc1;
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
-          tma_load_4d(&tmA, &full_bar[stage], a_dst, cc * TC_BLOCK_K, x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, n0);
-          kcoord = tap * p.cin + cc * TC_BLOCK_K;
+          tma_load_4d(&tmA, &full_bar[stage], a_dst, cc * bk, x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, n0);
+          kcoord = tap * p.cin + cc * bk;
         } else {
           const int cc = kb - p.taps * p.kc1;
-          tma_load_4d(&tmA2, &full_bar[stage], a_dst, cc * TC_BLOCK_K, x0, y0, n0);
-          kcoord = p.taps * p.cin + cc * TC_BLOCK_K;
+          tma_load_4d(&tmA2, &full_bar[stage], a_dst, cc * bk, x0, y0, n0);
+          kcoord = p.taps * p.cin + cc * bk;
         }
         tma_load_2d(&tmB, &full_bar[stage], b_dst, kcoord, n_blk * BLOCK_N);
       }
@@ -146,13 +151,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       if (lane == 0) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + stage * TC_A_STAGE_BYTES);
-        const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+        const uint32_t a_addr = smem_u32(smem_a + stage * a_stride);
+        const uint32_t b_addr = smem_u32(smem_b + stage * b_stride);
+        if (p.k32) {
 #pragma unroll
-        for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * 32);
-          const uint64_t db = make_smem_desc(b_addr + k * 32);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 2; ++k)
+            umma_bf16(tmem_base, make_smem_desc_sw64(a_addr + k * 32), make_smem_desc_sw64(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32);
+            const uint64_t db = make_smem_desc(b_addr + k * 32);
+            umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);                     // smem slot free once these MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
@@ -394,32 +405,33 @@ static bool tile_geometry(int N, int H, int W, TileGeom* g) {
   return true;
 }
 
-static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g, int stride = 1) {
+static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g, int stride = 1, int block_k = TC_BLOCK_K) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
   cuuint64_t strides[3] = {(cuuint64_t)t->c * 2, (cuuint64_t)t->w * t->c * 2, (cuuint64_t)t->h * t->w * t->c * 2};
   // stride-2 convs: the box spans stride*bw x stride*bh input pixels and the TMA engine keeps every stride-th one
   // (ceil(box/elementStride) elements per dimension land in shared memory)
-  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(g.bw * stride), (cuuint32_t)(g.bh * stride), (cuuint32_t)g.bn};
+  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)(g.bw * stride), (cuuint32_t)(g.bh * stride), (cuuint32_t)g.bn};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d box=%d,%d,%d) failed: %d", t->n, t->h, t->w, t->c,
            g.bw, g.bh, g.bn, (int)r);
   return 0;
 }
 
-static int encode_weight_map(CUtensorMap* tm, const void* w, int cout, int ktot, int block_n) {
+static int encode_weight_map(CUtensorMap* tm, const void* w, int cout, int ktot, int block_n, int block_k = TC_BLOCK_K) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
   cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight cout=%d k=%d box_n=%d) failed: %d", cout, ktot, block_n, (int)r);
   return 0;
 }
@@ -453,7 +465,8 @@ static int launch_tc_(const CUtensorMap& a, const CUtensorMap& a2, const CUtenso
   }
   int staging = 0;
   if (p.tma_store) staging = ((p.out_bf16 ? 1 : 0) + (p.dact ? 1 : 0)) * ((BLOCK_N + 63) / 64) * 16384 + (p.out_f32 ? (BLOCK_N / 32) * 16384 : 0);
-  const int smem = 1024 + HDR_BYTES + (ring > staging ? ring : staging);
+  const int ring_rt = p.k32 ? ring / 2 : ring;
+  const int smem = 1024 + HDR_BYTES + (ring_rt > staging ? ring_rt : staging);
   GA_CHECK(smem <= 227 * 1024, "conv_tc: shared memory request %d too large", smem);
   conv_tc_kernel<BLOCK_N, STAGES, GENERAL_ACT><<<grid, TC_THREADS, smem, s>>>(a, a2, b, ob, of, od, p);
   GA_LAUNCH_OK();
@@ -518,15 +531,22 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   TileGeom g;
   tile_geometry(in->n, Ho, Wo, &g);
   const int block_n = pick_block_n(out->c);
+  // 32-channel K blocks when Cin is an odd multiple of 32 (32, 96, ...): a 64-channel box would be half empty (zero-filled) for the
+  // last block of every tap -- at Cin = 32 that is half of all operand traffic and half of all MMAs
+  static int k32_enabled = -1;
+  if (k32_enabled < 0) { const char* e = getenv("GA_TC_K32"); k32_enabled = e ? atoi(e) : 1; }
+  const int k32 = (k32_enabled && !in2 && (in->c % 64) == 32) ? 1 : 0;
+  const int bk = k32 ? 32 : TC_BLOCK_K;
   CUtensorMap tmA, tmA2, tmB;
-  if (encode_act_map(&tmA, in, g, d->stride)) return 1;
+  if (encode_act_map(&tmA, in, g, d->stride, bk)) return 1;
   if (in2) { if (encode_act_map(&tmA2, in2, g)) return 1; }
   else tmA2 = tmA;
-  if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n)) return 1;
+  if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n, bk)) return 1;
 
   TcParams p;
   p.taps = taps; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
-  p.cin = in->c; p.kc1 = (in->c + TC_BLOCK_K - 1) / TC_BLOCK_K; p.kc2 = in2 ? (in2->c + TC_BLOCK_K - 1) / TC_BLOCK_K : 0;
+  p.k32 = k32;
+  p.cin = in->c; p.kc1 = (in->c + bk - 1) / bk; p.kc2 = in2 ? (in2->c + TC_BLOCK_K - 1) / TC_BLOCK_K : 0;
   p.bw = g.bw; p.bh = g.bh; p.bn = g.bn; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
   p.H = Ho; p.W = Wo; p.M = (int64_t)in->n * Ho * Wo;
   p.cout = out->c; p.bias = d->bias; p.post_act = d->post_act;
@@ -557,7 +577,9 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.tma_store = tma_ok ? 1 : 0;
   p.partial = g.partial;
   const int num_kb = p.taps * p.kc1 + p.kc2;
-  const bool short_k = num_kb <= 2;             // 1x1 convs with K <= 128: 2-stage ring -> more CTAs per SM
+  static int short_kb = -1;                     // K loops up to this many blocks run on a 2-stage ring -> more co-resident CTAs per SM
+  if (short_kb < 0) { const char* e = getenv("GA_TC_SHORT_KB"); short_kb = e ? atoi(e) : 18; }   // measured: 3x3 C=64 @32x32 113 -> 82 us, C=128 @16x16 61 -> 59 us; 36 blocks prefer the deep ring
+  const bool short_k = num_kb <= short_kb;
   if (num_kb == 1) {                            // single K block: 1-stage ring, up to 4 CTAs per SM (TMEM-limited)
     switch (block_n) {
       case 32: return launch_tc<32, 1>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);

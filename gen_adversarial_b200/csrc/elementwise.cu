@@ -359,15 +359,17 @@ __global__ void __launch_bounds__(128) latent_mix_kernel(const void* __restrict_
   const float a = *alpha_dev;
   const float* e_base = eps != nullptr ? eps + n * Z * HW + hw : nullptr;
   const uint64_t stream = noise_stream(sample0 + n, level + 1);
+  const bool fast = false;     // (MUFU tanh / exp measured no faster once the loads were vectorised, and cost 5e-4 of the 1e-2 budget)
   for (int z0 = 0; z0 < Cz; z0 += 4) {             // 4 channels per trip: their loads are issued together
     float mq[4], mp[4], lp[4], ee[4];
+    if (e_base == nullptr && z0 < Z) latent_eps4(seed, stream, z0 >> 2, hw, HW, ee);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int zc = z0 + u;
-      mq[u] = mp[u] = lp[u] = ee[u] = 0.f;
+      mq[u] = mp[u] = lp[u] = 0.f;
       if (zc < Z) {
         mq[u] = ld1d(q, q_dtype, pix * Cq + zc);
-        ee[u] = e_base != nullptr ? __ldg(e_base + (int64_t)zc * HW) : philox_normal(seed, stream, (uint64_t)zc * HW + hw);
+        if (e_base != nullptr) ee[u] = __ldg(e_base + (int64_t)zc * HW);
         if (pp != nullptr) {
           mp[u] = ld1d(pp, p_dtype, pix * (2 * Z) + zc);
           lp[u] = ld1d(pp, p_dtype, pix * (2 * Z) + Z + zc);
@@ -380,12 +382,63 @@ __global__ void __launch_bounds__(128) latent_mix_kernel(const void* __restrict_
       if (zc >= Cz) continue;
       float out = 0.f;                             // channels >= Z: zero padding (tensor-core K padding)
       if (zc < Z) {
-        if (pp == nullptr) out = (1.f - a) * softclamp5_(mq[u]) + a * (ee[u] * temp);
-        else out = (1.f - a) * softclamp5_(mp[u] + mq[u]) + a * (softclamp5_(mp[u]) + ee[u] * (temp * expf(softclamp5_(lp[u]))));
+        if (fast) {
+          if (pp == nullptr) out = (1.f - a) * (5.f * tanh_approx(0.2f * mq[u])) + a * (ee[u] * temp);
+          else out = (1.f - a) * (5.f * tanh_approx(0.2f * (mp[u] + mq[u]))) +
+                     a * (5.f * tanh_approx(0.2f * mp[u]) + ee[u] * (temp * __expf(5.f * tanh_approx(0.2f * lp[u]))));
+        } else {
+          if (pp == nullptr) out = (1.f - a) * softclamp5_(mq[u]) + a * (ee[u] * temp);
+          else out = (1.f - a) * softclamp5_(mp[u] + mq[u]) + a * (softclamp5_(mp[u]) + ee[u] * (temp * expf(softclamp5_(lp[u]))));
+        }
       }
       st1d(zout, z_dtype, pix * Cz + zc, out);
     }
   }
+}
+
+// vectorised variant (Z, Cq, Cz multiples of 4): one thread per (pixel, 4-channel group), adjacent threads = adjacent 16-byte pieces of
+// the pixel rows, so every load / store instruction of a warp covers whole 128-byte lines (the per-pixel kernel above issues 60
+// scalar loads whose 32 lanes hit 32 different lines: L1 wavefront bound, 5x slower at 32x32)
+__global__ void __launch_bounds__(256) latent_mix_vec4_kernel(const void* __restrict__ q, int q_dtype, int Cq, const void* __restrict__ pp,
+                                                              int p_dtype, const float* __restrict__ eps, uint64_t seed, int level,
+                                                              int64_t sample0, const float* __restrict__ alpha_dev, float temp, int Z,
+                                                              int64_t total_pix, int HW, void* __restrict__ zout, int z_dtype, int Cz) {
+  const int groups = Cz >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_pix * groups) return;
+  const int j = (int)(idx % groups);
+  const int64_t pix = idx / groups;
+  float out[4] = {0.f, 0.f, 0.f, 0.f};               // channel groups >= Z: zero padding (tensor-core K padding)
+  if (4 * j < Z) {
+    const int64_t n = pix / HW;
+    const int hw = (int)(pix % HW);
+    const float a = *alpha_dev;
+    float mq[4], mp[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f}, ee[4];
+    ld4d(q, q_dtype, pix * Cq + 4 * j, mq);
+    if (pp != nullptr) {
+      ld4d(pp, p_dtype, pix * (2 * Z) + 4 * j, mp);
+      ld4d(pp, p_dtype, pix * (2 * Z) + Z + 4 * j, lp);
+    }
+    if (eps != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ee[u] = __ldg(eps + (n * Z + 4 * j + u) * HW + hw);
+    } else {
+      latent_eps4(seed, noise_stream(sample0 + n, level + 1), j, hw, HW, ee);
+    }
+    const bool fast = false;   // see latent_mix_kernel
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (fast) {
+        if (pp == nullptr) out[u] = (1.f - a) * (5.f * tanh_approx(0.2f * mq[u])) + a * (ee[u] * temp);
+        else out[u] = (1.f - a) * (5.f * tanh_approx(0.2f * (mp[u] + mq[u]))) +
+                      a * (5.f * tanh_approx(0.2f * mp[u]) + ee[u] * (temp * __expf(5.f * tanh_approx(0.2f * lp[u]))));
+      } else {
+        if (pp == nullptr) out[u] = (1.f - a) * softclamp5_(mq[u]) + a * (ee[u] * temp);
+        else out[u] = (1.f - a) * softclamp5_(mp[u] + mq[u]) + a * (softclamp5_(mp[u]) + ee[u] * (temp * expf(softclamp5_(lp[u]))));
+      }
+    }
+  }
+  st4d(zout, z_dtype, pix * Cz + 4 * j, out);
 }
 
 // ============================================================================ DiscMixLogistic mean
@@ -796,6 +849,13 @@ extern "C" int ga_latent_mix_fwd(const ga_tensor* q, const ga_tensor* p, const f
   GA_CHECK(!p || (p->c == 2 * zdim && p->n == q->n && p->h == q->h && p->w == q->w), "ga_latent_mix_fwd: prior tensor must have 2*zdim channels");
   const int64_t total_pix = (int64_t)z->n * z->h * z->w;
   if (total_pix == 0) return 0;
+  if ((zdim & 3) == 0 && (q->c & 3) == 0 && (z->c & 3) == 0) {
+    latent_mix_vec4_kernel<<<cdiv(total_pix * (z->c / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, seed, level, sample0, alpha_dev,
+        temperature, zdim, total_pix, z->h * z->w, z->data, z->dtype, z->c);
+    GA_LAUNCH_OK();
+    return 0;
+  }
   latent_mix_kernel<<<cdiv(total_pix, 128), 128, 0, (cudaStream_t)stream>>>(
       q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, seed, level, sample0, alpha_dev,
       temperature, zdim, total_pix, z->h * z->w, z->data, z->dtype, z->c);

@@ -263,6 +263,11 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, u
   __sincosf(6.283185307179586f * u3, &s1, &c1);
   z[0] = m0 * c0; z[1] = m0 * s0; z[2] = m1 * c1; z[3] = m1 * s1;
 }
+// per-level latent noise eps[zc][hw] of one sample (stream = (global sample, level)): the four channels 4j .. 4j+3 of pixel hw are
+// ONE Philox block (counter j * HW + hw), so a thread that owns a pixel draws 4 channels per block with no redundant rounds
+__device__ __forceinline__ void latent_eps4(uint64_t seed, uint64_t stream, int j, int hw, int HW, float (&z)[4]) {
+  philox_normal4(seed, stream, (uint64_t)j * (uint64_t)HW + (uint64_t)hw, z);
+}
 // scalar convenience: element `idx` of the stream
 __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t stream, uint64_t idx) {
   float z[4];

@@ -71,12 +71,13 @@ __global__ void __launch_bounds__(256) channel_scale_kernel(const void* x, int x
 // ---------------------------------------------------------------------------- fused demod + noise + bias + leaky-ReLU*sqrt(2)
 // out[n,y,x,c] = act( y_conv * demod[n,c] + noise_w * noise[y,x] + bias[c] ) (+ skip)    -- StyledConv.forward (generator.py:258-268)
 // and ToRGB (generator.py:283-292, act = none, demod = NULL, skip = up-sampled RGB).  This is the `fused_bias_act` equivalent.
-// phases = 1: y_conv holds the 4 sub-pixel phase planes [4][N][H/2][W/2][C] of an up-sampling conv (see stylegan_engine.py).
+// phases = 1: y_conv = [N][H/2][W/2][4*C], the 4 sub-pixel phases of an up-sampling conv as channel groups (see stylegan_engine.py).
 __global__ void __launch_bounds__(256) styled_bias_act_kernel(const void* y, int y_dtype, int phases, const float* __restrict__ demod,
                                                               const float* __restrict__ noise, float noise_w,
                                                               const float* __restrict__ bias, int act, const void* skip, int skip_dtype,
                                                               int N, int H, int W, int C, const float* __restrict__ scale_a, void* out,
-                                                              int out_dtype, const float* __restrict__ scale_b, void* out_b, int out_b_dtype) {
+                                                              int out_dtype, const float* __restrict__ scale_b, void* out_b, int out_b_dtype,
+                                                              const float* __restrict__ skip_up_kernel) {
   const int c4n = C >> 2;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * H * W * c4n) return;
@@ -87,9 +88,10 @@ __global__ void __launch_bounds__(256) styled_bias_act_kernel(const void* y, int
   const int64_t n = t / H;
   int64_t src;
   if (phases) {
+    // the four sub-pixel phases of the up-sampling conv are channel groups [ph*C, (ph+1)*C) of ONE half-resolution conv output
     const int ph = (yy & 1) * 2 + (x & 1);
     const int Hh = H >> 1, Wh = W >> 1;
-    src = ((((int64_t)ph * N + n) * Hh + (yy >> 1)) * Wh + (x >> 1)) * C + c;
+    src = (((n * Hh + (yy >> 1)) * Wh + (x >> 1)) * 4 + ph) * C + c;
   } else {
     src = ((n * H + yy) * W + x) * C + c;
   }
@@ -106,11 +108,30 @@ __global__ void __launch_bounds__(256) styled_bias_act_kernel(const void* y, int
 #pragma unroll
   for (int j = 0; j < 4; ++j) v[j] = v[j] + nz + b4[j];
   apply_act_n<4>(v, act);
-  if (skip != nullptr) {
+  if (skip != nullptr && skip_up_kernel == nullptr) {
     float s4[4];
     ld4s(skip, skip_dtype, o, s4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] += s4[j];
+  } else if (skip != nullptr) {
+    // `skip` is the HALF-resolution RGB image: its `Upsample` (upfirdn2d, up 2, 4x4 FIR, pad (2,1); generator.py:28-47) is evaluated
+    // here -- 4 of the 16 taps hit non-inserted samples -- instead of materialising the up-sampled image in HBM
+    const int Hs = H >> 1, Ws = W >> 1;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int uy = yy + ky - 2;
+      if (uy < 0 || uy >= H || (uy & 1)) continue;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ux = x + kx - 2;
+        if (ux < 0 || ux >= W || (ux & 1)) continue;
+        float s4[4];
+        ld4s(skip, skip_dtype, ((n * Hs + (uy >> 1)) * Ws + (ux >> 1)) * C + c, s4);
+        const float kw = __ldg(skip_up_kernel + (3 - ky) * 4 + (3 - kx));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaf(s4[j], kw, v[j]);
+      }
+    }
   }
   // the consumers are modulated convs: their per-sample input scaling (the "modulation", generator.py:164-167) is applied here on the
   // fp32 value, so no separate scaling pass (and no second bf16 rounding) exists -- one copy per consumer (next StyledConv / ToRGB)
@@ -210,14 +231,16 @@ extern "C" int ga_channel_scale(const ga_tensor* x, const float* s, const ga_ten
 }
 
 extern "C" int ga_styled_bias_act(const ga_tensor* y, int phases, const float* demod, const float* noise_hw, float noise_w,
-                                  const float* bias, int act, const ga_tensor* skip, const float* scale_a, const ga_tensor* out,
-                                  const float* scale_b, const ga_tensor* out_b, void* stream) {
+                                  const float* bias, int act, const ga_tensor* skip, const float* skip_up_kernel, const float* scale_a,
+                                  const ga_tensor* out, const float* scale_b, const ga_tensor* out_b, void* stream) {
   GA_CHECK(y && (out || out_b), "ga_styled_bias_act: null argument");
   const ga_tensor* o = out ? out : out_b;
   GA_CHECK((o->c % 4) == 0, "ga_styled_bias_act: channels must be a multiple of 4");
-  if (phases) GA_CHECK(y->n == 4 * o->n && y->h * 2 == o->h && y->w * 2 == o->w && y->c == o->c, "ga_styled_bias_act: phase planes must be [4*n][h/2][w/2][c]");
+  if (phases) GA_CHECK(y->n == o->n && y->h * 2 == o->h && y->w * 2 == o->w && y->c == 4 * o->c, "ga_styled_bias_act: phase tensor must be [n][h/2][w/2][4*c]");
   else GA_CHECK(same_shape(y, o), "ga_styled_bias_act: shape mismatch");
-  GA_CHECK(!skip || same_shape(skip, o), "ga_styled_bias_act: skip shape mismatch");
+  if (skip_up_kernel) GA_CHECK(skip && skip->n == o->n && skip->h * 2 == o->h && skip->w * 2 == o->w && skip->c == o->c,
+                               "ga_styled_bias_act: an up-sampled skip must have half the output resolution");
+  else GA_CHECK(!skip || same_shape(skip, o), "ga_styled_bias_act: skip shape mismatch");
   GA_CHECK(!out_b || (scale_b && (!out || same_shape(out, out_b))), "ga_styled_bias_act: out_b needs scale_b and out's shape");
   const int64_t total = numel(o) / 4;
   if (total == 0) return 0;
@@ -225,7 +248,7 @@ extern "C" int ga_styled_bias_act(const ga_tensor* y, int phases, const float* d
                                                                               skip ? skip->data : nullptr, skip ? skip->dtype : GA_F32, o->n,
                                                                               o->h, o->w, o->c, scale_a, out ? out->data : nullptr,
                                                                               out ? out->dtype : GA_F32, scale_b, out_b ? out_b->data : nullptr,
-                                                                              out_b ? out_b->dtype : GA_F32);
+                                                                              out_b ? out_b->dtype : GA_F32, skip_up_kernel);
   GA_LAUNCH_OK();
   return 0;
 }

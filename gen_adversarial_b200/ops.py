@@ -438,14 +438,15 @@ def channel_scale(x, s, out_dtype):
 
 @_timed("styled_bias_act")
 def styled_bias_act(y, phases: bool, demod, noise_hw, noise_w: float, bias, act: int, skip, out_dtype, scale_a=None, scale_b=None,
-                    want_out: bool = True):
-    """v = act(y * demod + noise + bias) (+ skip);  -> out = v * scale_a (or v), and with scale_b -> (out | None, v * scale_b)"""
-    n = y.shape[0] // 4 if phases else y.shape[0]
-    h, w = (y.shape[1] * 2, y.shape[2] * 2) if phases else (y.shape[1], y.shape[2])
-    out = torch.empty((n, h, w, y.shape[3]), device=y.device, dtype=out_dtype) if want_out else None
-    out_b = torch.empty((n, h, w, y.shape[3]), device=y.device, dtype=out_dtype) if scale_b is not None else None
+                    want_out: bool = True, skip_up_kernel=None):
+    """v = act(y * demod + noise + bias) (+ skip, up-sampled x2 on the fly through the 4x4 FIR `skip_up_kernel` when given);
+    -> out = v * scale_a (or v), and with scale_b -> (out | None, v * scale_b)"""
+    n = y.shape[0]
+    h, w, c = (y.shape[1] * 2, y.shape[2] * 2, y.shape[3] // 4) if phases else (y.shape[1], y.shape[2], y.shape[3])
+    out = torch.empty((n, h, w, c), device=y.device, dtype=out_dtype) if want_out else None
+    out_b = torch.empty((n, h, w, c), device=y.device, dtype=out_dtype) if scale_b is not None else None
     _lib.check(_lib.lib().ga_styled_bias_act(gt(y), int(phases), ptr(demod), ptr(noise_hw), float(noise_w), ptr(bias), act, gt(skip),
-                                             ptr(scale_a), gt(out), ptr(scale_b), gt(out_b), stream()), "styled_bias_act")
+                                             ptr(skip_up_kernel), ptr(scale_a), gt(out), ptr(scale_b), gt(out_b), stream()), "styled_bias_act")
     return (out, out_b) if scale_b is not None else out
 
 

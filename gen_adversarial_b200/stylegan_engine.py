@@ -11,8 +11,9 @@ Exact rewrites done at load (fp64):
   * up-sampling StyledConv = conv_transpose2d(stride 2) followed by the 4x4 FIR blur (generator.py:180-191): both are
     linear with zero boundaries, so their composition is a stride-2 transposed conv with a 6x6 kernel, i.e. FOUR
     ordinary 3x3 convolutions (one per output sub-pixel phase) at the INPUT resolution on composed weights
-    K_{py,px}[a,b] = G[py+2-2a, px+2-2b], G = W (*) blur.  They run on the tensor-core conv kernel and are interleaved by
-    the fused epilogue kernel -- no zero-insertion, no (2H+1)^2 intermediate, no separate blur pass;
+    K_{py,px}[a,b] = G[py+2-2a, px+2-2b], G = W (*) blur.  They share their input, so they run as ONE tensor-core conv with 4 x Cout
+    output channels (phase-major) and are interleaved by the fused epilogue kernel -- no zero-insertion, no (2H+1)^2 intermediate,
+    no separate blur pass;
   * `noise + bias + leaky_relu * sqrt(2)` (NoiseInjection + FusedLeakyReLU, generator.py:210-268) and the demodulation
     scale are one kernel (`ga_styled_bias_act`, the `fused_bias_act` equivalent);
   * the mapping MLP runs ONCE on all n_codes x B rows (the reference loops over codes in Python, models.py:120,335).
@@ -101,14 +102,16 @@ class StyleGan2Engine:
                             ky, kx = dy + ty - 1, dx + tx - 1
                             if 0 <= ky < 3 and 0 <= kx < 3:
                                 G[:, :, dy + 2, dx + 2] += kb[ty, tx] * w[:, :, ky, kx]
-            s.phase_convs = []
+            Ks = []
             for py in range(2):
                 for px in range(2):
                     K = torch.zeros((cout, cin, 3, 3), dtype=torch.float64)
                     for a in range(3):
                         for b in range(3):
                             K[:, :, a, b] = G[:, :, (py + 2 - 2 * a) + 2, (px + 2 - 2 * b) + 2]
-                    s.phase_convs.append(f.conv(K, None, pad=1, name=f"{prefix}.conv.phase{py}{px}"))
+                    Ks.append(K)
+            # the four phase convs share their input: ONE conv with 4 * cout output channels (phase-major) reads it once
+            s.phase_convs = f.conv(torch.cat(Ks, dim=0), None, pad=1, name=f"{prefix}.conv.phases")
         s.noise_w = float(f.f64(f"{prefix}.noise.weight")[0])
         s.bias = f.dev32(f.f64(f"{prefix}.activate.bias"))
         return s
@@ -176,9 +179,7 @@ class StyleGan2Engine:
             y = self._conv(xs, s.conv, want_f32=f32)
             phases = False
         else:
-            y = torch.empty((4 * b, h, w, s.cout), device=xs.device, dtype=torch.float32 if f32 else self.adt)
-            for ph, L in enumerate(s.phase_convs):
-                self._conv(xs, L, want_f32=f32, out=y[ph * b:(ph + 1) * b])
+            y = self._conv(xs, s.phase_convs, want_f32=f32)              # [b, h, w, 4 * cout]
             phases = True
         r = ops.styled_bias_act(y, phases, demod, noise, s.noise_w, s.bias, ACT_LRELU_SQRT2, None, self.adt, scale_a=scale_next,
                                 scale_b=scale_rgb, want_out=scale_next is not None)
@@ -186,9 +187,9 @@ class StyleGan2Engine:
 
     def _rgb(self, xs, r: _ToRGB, skip):
         y = self._conv(xs, r.conv, want_f32=True)                                                   # [B,H,W,4] fp32
-        if skip is not None:
-            skip = ops.upfirdn2d(skip, r.up_kernel, up=2, down=1, pad=(2, 1))                        # Upsample (generator.py:30-47)
-        return ops.styled_bias_act(y, False, None, None, 0.0, r.bias, ACT_NONE, skip, torch.float32)
+        # the half-resolution skip is up-sampled (Upsample, generator.py:30-47) inside the epilogue kernel
+        return ops.styled_bias_act(y, False, None, None, 0.0, r.bias, ACT_NONE, skip, torch.float32,
+                                   skip_up_kernel=r.up_kernel if skip is not None else None)
 
     def _cap(self, j: int) -> int:
         """largest batch slice block j (output resolution 8 * 2^j) runs on: keeps one activation tensor <= 2^29 elements (1 GB bf16)"""

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 6
+#define GA_ABI_VERSION 7
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3, GA_PRE_AFFINE = 4 };
@@ -172,11 +172,13 @@ int ga_pixelnorm(const float* x, int rows, int d, const ga_tensor* out, void* st
 int ga_style_demod(const float* s, const float* wsq, int n, int cin, int cout, float* demod, void* stream);
 int ga_channel_scale(const ga_tensor* x, const float* s /*[n][c]*/, const ga_tensor* out, void* stream); /* generator.py:164-167 */
 /* v = act(y * demod[n][c] + noise_w * noise[h][w] + bias[c]) (+ skip): StyledConv / ToRGB epilogue = fused_bias_act
- * (generator.py:258-268,283-292).  phases=1: y = the 4 sub-pixel planes [4*n][h/2][w/2][c] of an up-sampling conv.
+ * (generator.py:258-268,283-292).  phases=1: y = [n][h/2][w/2][4*c], the 4 sub-pixel phases of an up-sampling conv as channel groups.
  * out = v * scale_a[n][c], out_b = v * scale_b[n][c]: the consumers' modulation (their style vector) applied in the same pass */
 int ga_styled_bias_act(const ga_tensor* y, int phases, const float* demod, const float* noise_hw, float noise_w,
-                       const float* bias, int act, const ga_tensor* skip, const float* scale_a /*[n][c] nullable*/,
-                       const ga_tensor* out /*nullable*/, const float* scale_b, const ga_tensor* out_b /*nullable*/, void* stream);
+                       const float* bias, int act, const ga_tensor* skip,
+                       const float* skip_up_kernel /* nullable; 4x4 FIR: skip is HALF resolution and is up-sampled on the fly */,
+                       const float* scale_a /*[n][c] nullable*/, const ga_tensor* out /*nullable*/, const float* scale_b,
+                       const ga_tensor* out_b /*nullable*/, void* stream);
 /* zero-insert up-sample -> pad -> FIR (flipped kernel) -> decimate, NHWC                                 op/upfirdn2d_kernel.cu:52-137 */
 int ga_upfirdn2d(const ga_tensor* in, const float* kernel, int kh, int kw, int up, int down, int pad0, int pad1,
                  const ga_tensor* out, void* stream);

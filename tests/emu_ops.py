@@ -375,13 +375,17 @@ def channel_scale(x, s, out_dtype):
     return (x.float() * s[:, None, None, :]).to(out_dtype)
 
 
-def styled_bias_act(y, phases, demod, noise_hw, noise_w, bias, act, skip, out_dtype, scale_a=None, scale_b=None, want_out=True):
+def styled_bias_act(y, phases, demod, noise_hw, noise_w, bias, act, skip, out_dtype, scale_a=None, scale_b=None, want_out=True,
+                    skip_up_kernel=None):
     _launches[0] += 1
+    if skip is not None and skip_up_kernel is not None:
+        skip = upfirdn2d(skip, skip_up_kernel, up=2, down=1, pad=(2, 1), out_dtype=torch.float32)
+        _launches[0] -= 1
     v = y.float()
     if phases:
-        n = v.shape[0] // 4
-        ph = v.view(2, 2, n, v.shape[1], v.shape[2], v.shape[3])        # [py, px, n, h, w, c]
-        v = ph.permute(2, 3, 0, 4, 1, 5).reshape(n, v.shape[1] * 2, v.shape[2] * 2, v.shape[3])
+        n, hh, wh, c4 = v.shape
+        ph = v.view(n, hh, wh, 2, 2, c4 // 4)                           # [n, h, w, py, px, c]
+        v = ph.permute(0, 1, 3, 2, 4, 5).reshape(n, hh * 2, wh * 2, c4 // 4)
     if demod is not None:
         v = v * demod[:, None, None, :]
     if noise_hw is not None:

@@ -96,6 +96,8 @@ TC_CASES = [
     (2, 64, 64, 32, 32, 3, ACT_SILU, None, 0),            # Cin = 32 < 64: TMA zero fill in K
     (2, 64, 64, 96, 32, 1, ACT_NONE, None, 0),            # K = 96 (not a multiple of 64)
     (2, 64, 64, 32, 100, 3, ACT_NONE, None, 0),           # to_logits
+    (2, 32, 32, 96, 64, 3, ACT_SILU, "bf16", 0),          # Cin = 96: three 32-channel K blocks per tap (64-byte swizzle path)
+    (1, 128, 128, 32, 32, 3, ACT_NONE, None, 0),          # Cin = 32, W = 128 (one image row per tile)
     (3, 8, 8, 24, 256, 1, ACT_NONE, "f32", 0),            # level 0: z only + prior
     (5, 4, 4, 512, 512, 3, ACT_RELU, None, 0),            # VGG 4x4 (8 images per tile, ragged batch)
     (5, 2, 2, 512, 512, 3, ACT_RELU, None, 0),
@@ -188,6 +190,28 @@ def test_latent_mix_philox_statistics_and_shard_independence():
     assert abs(full.mean().item()) < 0.02 and abs(full.std().item() - 1.0) < 0.02
     half = ops.latent_mix(q[32:], None, None, 1234, 3, 32, alpha, 1.0, z, zc, torch.float32)[..., :z]
     assert torch.equal(half, full[32:])       # keyed by the GLOBAL sample index
+
+
+def test_latent_mix_philox_backward_regenerates_forward_noise():
+    """Philox mode: the backward kernel re-draws eps from (seed, level, global sample, channel, pixel); it must be the forward's draw.
+    eps is recovered from the forward output at alpha = 1 with the prior N(0,1) (z = eps * T) and fed explicitly to a second backward."""
+    n, h, z, zc, seed, lvl = 3, 8, 20, 24, 99, 5
+    g = torch.Generator().manual_seed(3)
+    q = (torch.randn(n, h, h, z, generator=g)).to(DEV)
+    p = (torch.randn(n, h, h, 2 * z, generator=g) * 0.5).to(DEV)
+    gz = torch.randn(n, h, h, zc, generator=g).to(DEV)
+    one, a = torch.ones(1, device=DEV), torch.full((1,), 0.4, device=DEV)
+    eps_nhwc = ops.latent_mix(torch.zeros_like(q), None, None, seed, lvl, 7, one, 1.0, z, zc, torch.float32)[..., :z]
+    eps = eps_nhwc.permute(0, 3, 1, 2).contiguous()
+    z_phi = ops.latent_mix(q, p, None, seed, lvl, 7, a, 0.6, z, zc, torch.float32)
+    z_exp = ops.latent_mix(q, p, eps, 0, lvl, 7, a, 0.6, z, zc, torch.float32)
+    assert (z_phi - z_exp).abs().max().item() <= 1e-5
+    gq1, gp1 = ops.latent_mix_bwd(gz, q, p, None, seed, lvl, 7, a, 0.6, z, zc)
+    gq2, gp2 = ops.latent_mix_bwd(gz, q, p, eps, 0, lvl, 7, a, 0.6, z, zc)
+    assert (gq1 - gq2).abs().max().item() <= 1e-6 and (gp1 - gp2).abs().max().item() <= 1e-5 * max(1.0, gp2.abs().max().item())
+    # bf16 output stays within bf16 rounding of the fp32 result
+    z_bf = ops.latent_mix(q, p, eps, 0, lvl, 7, a, 0.6, z, zc, torch.bfloat16)
+    assert (z_bf.float() - z_exp).abs().max().item() <= 2e-2 * max(1.0, z_exp.abs().max().item())
 
 
 def test_discmix_mean():

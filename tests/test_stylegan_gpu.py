@@ -32,13 +32,25 @@ def test_styled_bias_act(phases):
     """fused demod + noise + bias + leaky_relu*sqrt(2) (= fused_bias_act_kernel.cu + NoiseInjection)"""
     g = torch.Generator().manual_seed(1)
     n, h, w, c = 2, 16, 16, 32
-    y = torch.randn((4 * n, h // 2, w // 2, c) if phases else (n, h, w, c), generator=g)
+    y = torch.randn((n, h // 2, w // 2, 4 * c) if phases else (n, h, w, c), generator=g)
     demod, noise, bias = torch.rand(n, c, generator=g) + 0.5, torch.randn(h, w, generator=g), torch.randn(c, generator=g)
     skip = torch.randn(n, h, w, c, generator=g)
     for act, d, nz, sk in ((ACT_LRELU_SQRT2, demod, noise, None), (ACT_NONE, None, None, skip)):
         ref = emu_ops.styled_bias_act(y, phases, d, nz, 0.37, bias, act, sk, torch.float32)
         got = ops.styled_bias_act(y.to(DEV), phases, d.to(DEV) if d is not None else None, nz.to(DEV) if nz is not None else None,
                                   0.37, bias.to(DEV), act, sk.to(DEV) if sk is not None else None, torch.float32)
+        assert (got.cpu() - ref).abs().max().item() <= 1e-5
+    # consumers' modulation applied in the same pass (two scaled copies) and the half-resolution RGB skip up-sampled on the fly
+    sa, sb = torch.rand(n, c, generator=g) + 0.5, torch.rand(n, c, generator=g) + 0.5
+    ra, rb = emu_ops.styled_bias_act(y, phases, demod, noise, 0.37, bias, ACT_LRELU_SQRT2, None, torch.float32, scale_a=sa, scale_b=sb)
+    ga, gb = ops.styled_bias_act(y.to(DEV), phases, demod.to(DEV), noise.to(DEV), 0.37, bias.to(DEV), ACT_LRELU_SQRT2, None, torch.float32,
+                                 scale_a=sa.to(DEV), scale_b=sb.to(DEV))
+    assert (ga.cpu() - ra).abs().max().item() <= 1e-5 and (gb.cpu() - rb).abs().max().item() <= 1e-5
+    if not phases:
+        k = torch.tensor([1.0, 3.0, 3.0, 1.0]); k = k[None] * k[:, None]; k = k / k.sum() * 4
+        low = torch.randn(n, h // 2, w // 2, c, generator=g)
+        ref = emu_ops.styled_bias_act(y, False, None, None, 0.0, bias, ACT_NONE, low, torch.float32, skip_up_kernel=k)
+        got = ops.styled_bias_act(y.to(DEV), False, None, None, 0.0, bias.to(DEV), ACT_NONE, low.to(DEV), torch.float32, skip_up_kernel=k.to(DEV))
         assert (got.cpu() - ref).abs().max().item() <= 1e-5
 
 
