@@ -185,6 +185,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the ONE JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     from gen_adversarial_b200 import ops, synth
     from gen_adversarial_b200.nvae_spec import NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION
@@ -331,7 +332,12 @@ def run_ours(args):
         top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes, FLOP-weighted)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})", "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                # ncu --set full (profiles/r01_ncu_full_kernels_v7.md), per launch of the shape with the largest share of conv_tc time
+                # (3x3, 32x32, C 64 -> 64, batch 512): dram__bytes_read + dram__bytes_write = 67.2 + 28.7 MB; algorithmic bytes
+                # (x in + weights + y out, bf16) = 134.3 MB -- the output is still in the 126 MB L2 when the next kernel reads it
+                "traffic": 95.9e6 if (not pgd and not sg and B == 512) else None,
+                "traffic_note": "DRAM bytes per launch of 'k3 hw32 cin64 cout64' from ncu; algorithmic 134.3 MB",
                 "launches": n_l, "share_of_step": tot_ms / ms if ms > 0 else None,
                 "by_shape": [{"shape": k, "launches": a["launches"], "ms": round(a["ms"], 3),
                               "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 1) if a["ms"] > 0 else None,
