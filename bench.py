@@ -226,6 +226,9 @@ def run_ours(args):
                               cfg["gaussian_blur_input"], dev, mode=mode).eval()
         res, n_cls = NVAE_C32_RESOLUTION, 100
     dm.sample_offset = rank * B                      # Philox streams keyed by the GLOBAL sample index
+    use_graph = (args.cuda_graph == 1) or (args.cuda_graph < 0 and args.workload == "pgd")
+    if use_graph and not sg:
+        dm.enable_cuda_graph(True)                   # public API switch: whole call / PGD iteration replayed as a CUDA graph
     x_cpu, y_cpu = synth.synthetic_batch(B, res, n_cls, seed=42 + rank)
     x_host = x_cpu.pin_memory()
     x_dev = x_host.to(dev)
@@ -274,6 +277,8 @@ def run_ours(args):
         step_resident()
     barrier()
     ops.launch_count(reset=True)
+    from gen_adversarial_b200 import graphs as ga_graphs
+    replayed0 = ga_graphs.REPLAYED_LAUNCHES[0]
     timer = ops.KernelTimer() if rank == 0 else None
     ops.TIMER = timer
     ops.TIME_ALL = bool(args.breakdown)
@@ -288,7 +293,8 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = ops.launch_count(reset=True)
+    from gen_adversarial_b200 import graphs as ga_graphs
+    launches = ops.launch_count(reset=True) + ga_graphs.REPLAYED_LAUNCHES[0] - replayed0      # eager launches + graph-replayed kernel nodes
     ops.TIMER = None
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     counters[0] = B * args.steps
@@ -381,6 +387,7 @@ def run_ours(args):
                 "config": {"workload": workload,
                            "nvae": None if sg else NVAE_C32_CONFIG, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": "no explicit flush: each step streams > 10 GB of activations through the 126 MB L2",
+                           "cuda_graph": bool(use_graph and not sg),
                            "gflop_per_image_algorithmic": gflop},
                 "tflops_algorithmic": value * gflop / 1e3,
                 "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
@@ -404,6 +411,8 @@ def main():
     ap.add_argument("--workload", default="purify", choices=["purify", "pgd", "gender", "cars"])
     ap.add_argument("--chunk", type=int, default=0, help="generator batch chunk of the StyleGAN workloads (0: automatic)")
     ap.add_argument("--pgd-steps", type=int, default=50)
+    ap.add_argument("--cuda-graph", type=int, default=-1, help="1: replay the call / PGD iteration as a CUDA graph; 0: eager; default: pgd only "
+                    "(the purify roofline needs per-launch events, which only exist in eager mode)")
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded sample per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="CUDA-event time of EVERY op (written to stderr as a table)")

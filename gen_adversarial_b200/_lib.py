@@ -102,6 +102,8 @@ _PROTOS = {
     "ga_last_error": (c_char_p, []),
     "ga_abi_version": (c_int, []),
     "ga_launch_count": (c_int64, [c_int]),
+    "ga_seed_salt_set": (c_int, [c_void_p]),
+    "ga_seed_salt_bump": (c_int, [c_void_p]),
     "ga_noise_sumsq_parts": (c_int, [c_int]),
     "ga_channel_sum_parts": (c_int, [c_int, c_int]),
     "ga_noise_sumsq": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -173,7 +175,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 7:
+    if L.ga_abi_version() != 8:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -28,7 +28,18 @@ class PGDLinf:
         if self.random_start:
             x_adv = (x_adv + 0.001 * torch.randn_like(x_adv)).contiguous()
         fused = hasattr(net, "loss_input_grad")
-        for i in range(self.steps):
+        if fused and noise_schedule is None and getattr(net, "use_cuda_graph", False) and x.is_cuda:
+            # launch-rate bound at attack batch sizes (~1500 launches per iteration): replay one captured iteration `steps` times
+            from .graphs import GraphedPGD, GraphedForward
+            key = ("pgd", tuple(x.shape), self.step, self.eps)
+            g = net._graphs.get(key)
+            if g is None or g.key[3] != GraphedForward.make_key(net, x):
+                g = net._graphs[key] = GraphedPGD(net, x, labels, self.step, self.eps)
+            x_adv = g.run(net, x, labels, self.steps, x_adv if self.random_start else None).clone()
+            steps_left = 0
+        else:
+            steps_left = self.steps
+        for i in range(steps_left):
             if noise_schedule is not None:
                 net.set_explicit_noise(noise_schedule[i])
             if fused:

@@ -264,9 +264,10 @@ __global__ void maxpool2x2_bwd_kernel(const void* xin, int x_dtype, const void* 
 // ---------------------------------------------------------------------------- latent mix backward
 __global__ void __launch_bounds__(256) latent_mix_bwd_kernel(const void* gz, int gz_dtype, int Cz, const float* __restrict__ q, int Cq,
                                                              const float* __restrict__ pp, const float* __restrict__ eps,
-                                                             uint64_t seed, int level, int64_t sample0,
+                                                             SeedArg seed_arg, int level, int64_t sample0,
                                                              const float* __restrict__ alpha_dev, float temp, int Z, int N, int H,
                                                              int W, float* __restrict__ g_q, int Cgq, float* __restrict__ g_p) {
+  const uint64_t seed = seed_arg.get();
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * H * W * Cgq) return;
   const int zc = (int)(idx % Cgq);
@@ -471,7 +472,7 @@ extern "C" int ga_latent_mix_bwd(const ga_tensor* g_z, const ga_tensor* q, const
   const int64_t total = (int64_t)q->n * q->h * q->w * g_q->c;
   if (total == 0) return 0;
   latent_mix_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, seed, level, sample0,
+      g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, make_seed(seed), level, sample0,
       alpha_dev, temperature, zdim, q->n, q->h, q->w, (float*)g_q->data, g_q->c, g_p ? (float*)g_p->data : nullptr);
   GA_LAUNCH_OK();
   return 0;

@@ -59,7 +59,8 @@ __global__ void noise_sumsq_kernel(const float* __restrict__ noise, int chw, flo
   if (threadIdx.x == 0) sumsq[(int64_t)b * gridDim.x + blockIdx.x] = acc;
 }
 
-__global__ void noise_sumsq_philox_kernel(uint64_t seed, int64_t sample0, int chw, float* __restrict__ sumsq) {
+__global__ void noise_sumsq_philox_kernel(SeedArg seed_arg, int64_t sample0, int chw, float* __restrict__ sumsq) {
+  const uint64_t seed = seed_arg.get();
   const int b = blockIdx.y;
   const uint64_t stream = noise_stream(sample0 + b, 0);
   const int n4 = (chw + 3) >> 2;
@@ -89,9 +90,10 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 template <bool BLUR>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
-    const float* __restrict__ x, const float* __restrict__ noise, const float* __restrict__ sumsq, uint64_t seed,
+    const float* __restrict__ x, const float* __restrict__ noise, const float* __restrict__ sumsq, SeedArg seed_arg,
     int nparts, int64_t sample0, float eps, const float* __restrict__ taps, int R, int normalize, int C, int H, int W,
     void* out, int out_dtype, float* __restrict__ pre) {
+  const uint64_t seed = seed_arg.get();
   __shared__ float s_in[BLUR ? (PT + 2 * MAXR) : 1][BLUR ? (PT + 2 * MAXR + 1) : 1];
   __shared__ float s_h[BLUR ? (PT + 2 * MAXR) : 1][BLUR ? (PT + 1) : 1];
   __shared__ float s_taps[2 * MAXR + 1];
@@ -349,9 +351,10 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
 // NCHW eps reads are coalesced across the warp (adjacent threads = adjacent pixels)
 __global__ void __launch_bounds__(128) latent_mix_kernel(const void* __restrict__ q, int q_dtype, int Cq,
                                                          const void* __restrict__ pp, int p_dtype, const float* __restrict__ eps,
-                                                         uint64_t seed, int level, int64_t sample0,
+                                                         SeedArg seed_arg, int level, int64_t sample0,
                                                          const float* __restrict__ alpha_dev, float temp, int Z, int64_t total_pix,
                                                          int HW, void* __restrict__ zout, int z_dtype, int Cz) {
+  const uint64_t seed = seed_arg.get();
   const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total_pix) return;
   const int64_t n = pix / HW;
@@ -400,9 +403,10 @@ __global__ void __launch_bounds__(128) latent_mix_kernel(const void* __restrict_
 // the pixel rows, so every load / store instruction of a warp covers whole 128-byte lines (the per-pixel kernel above issues 60
 // scalar loads whose 32 lanes hit 32 different lines: L1 wavefront bound, 5x slower at 32x32)
 __global__ void __launch_bounds__(256) latent_mix_vec4_kernel(const void* __restrict__ q, int q_dtype, int Cq, const void* __restrict__ pp,
-                                                              int p_dtype, const float* __restrict__ eps, uint64_t seed, int level,
+                                                              int p_dtype, const float* __restrict__ eps, SeedArg seed_arg, int level,
                                                               int64_t sample0, const float* __restrict__ alpha_dev, float temp, int Z,
                                                               int64_t total_pix, int HW, void* __restrict__ zout, int z_dtype, int Cz) {
+  const uint64_t seed = seed_arg.get();
   const int groups = Cz >> 2;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_pix * groups) return;
@@ -746,7 +750,7 @@ extern "C" int ga_noise_sumsq(const float* noise, int n, int chw, float* sumsq, 
 extern "C" int ga_noise_sumsq_philox(uint64_t seed, int64_t sample0, int n, int chw, float* sumsq, void* stream) {
   GA_CHECK(sumsq && n >= 0 && chw > 0, "ga_noise_sumsq_philox: bad arguments");
   if (n == 0) return 0;
-  noise_sumsq_philox_kernel<<<dim3(ga_noise_sumsq_parts(chw), n), 256, 0, (cudaStream_t)stream>>>(seed, sample0, chw, sumsq);
+  noise_sumsq_philox_kernel<<<dim3(ga_noise_sumsq_parts(chw), n), 256, 0, (cudaStream_t)stream>>>(make_seed(seed), sample0, chw, sumsq);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -765,10 +769,10 @@ extern "C" int ga_preprocess_fwd(const float* x, const float* noise, const float
   dim3 grid(tiles, 1, out->n);
   cudaStream_t s = (cudaStream_t)stream;
   if (taps != nullptr)
-    preprocess_fwd_kernel<true><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, nparts, sample0, eps, taps, radius, normalize, out->c,
+    preprocess_fwd_kernel<true><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed), nparts, sample0, eps, taps, radius, normalize, out->c,
                                                     out->h, out->w, out->data, out->dtype, pre);
   else
-    preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, seed, nparts, sample0, eps, nullptr, 0, normalize, out->c,
+    preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed), nparts, sample0, eps, nullptr, 0, normalize, out->c,
                                                      out->h, out->w, out->data, out->dtype, pre);
   GA_LAUNCH_OK();
   return 0;
@@ -851,13 +855,13 @@ extern "C" int ga_latent_mix_fwd(const ga_tensor* q, const ga_tensor* p, const f
   if (total_pix == 0) return 0;
   if ((zdim & 3) == 0 && (q->c & 3) == 0 && (z->c & 3) == 0) {
     latent_mix_vec4_kernel<<<cdiv(total_pix * (z->c / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-        q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, seed, level, sample0, alpha_dev,
+        q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, make_seed(seed), level, sample0, alpha_dev,
         temperature, zdim, total_pix, z->h * z->w, z->data, z->dtype, z->c);
     GA_LAUNCH_OK();
     return 0;
   }
   latent_mix_kernel<<<cdiv(total_pix, 128), 128, 0, (cudaStream_t)stream>>>(
-      q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, seed, level, sample0, alpha_dev,
+      q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, make_seed(seed), level, sample0, alpha_dev,
       temperature, zdim, total_pix, z->h * z->w, z->data, z->dtype, z->c);
   GA_LAUNCH_OK();
   return 0;

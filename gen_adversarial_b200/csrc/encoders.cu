@@ -224,7 +224,8 @@ __global__ void image_pool_out_kernel(const float* __restrict__ in, int N, int S
 
 // ---------------------------------------------------------------------------- N(0, std) fill, keyed by (seed, code index, global sample index)
 // out[l][b][d] (the reference's torch.normal(0, std, (n_codes, b, d)) layout)
-__global__ void philox_codes_kernel(uint64_t seed, int64_t sample0, float std_, int L, int B, int D, float* __restrict__ out) {
+__global__ void philox_codes_kernel(SeedArg seed_arg, int64_t sample0, float std_, int L, int B, int D, float* __restrict__ out) {
+  const uint64_t seed = seed_arg.get();
   const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // D % 4 == 0
   const int d4n = D >> 2;
   if (i4 >= (int64_t)L * B * d4n) return;
@@ -325,7 +326,7 @@ extern "C" int ga_philox_codes(uint64_t seed, int64_t sample0, float std_, int l
   GA_CHECK(out && l > 0 && b >= 0 && d > 0 && d % 4 == 0, "ga_philox_codes: bad arguments");
   const int64_t total4 = (int64_t)l * b * (d / 4);
   if (total4 == 0) return 0;
-  philox_codes_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(seed, sample0, std_, l, b, d, out);
+  philox_codes_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(make_seed(seed), sample0, std_, l, b, d, out);
   GA_LAUNCH_OK();
   return 0;
 }

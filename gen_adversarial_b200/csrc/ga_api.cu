@@ -12,6 +12,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { ++g_launches; }
+static const uint64_t* g_seed_salt = nullptr;
+const uint64_t* seed_salt_ptr() { return g_seed_salt; }
+__global__ void seed_salt_bump_kernel(uint64_t* salt) { *salt += 0x9E3779B97F4A7C15ull; }
 }  // namespace ga
 
 extern "C" const char* ga_last_error(void) { return ga::g_err; }
@@ -20,4 +23,15 @@ extern "C" int64_t ga_launch_count(int reset) {
   int64_t v = ga::g_launches;
   if (reset) ga::g_launches = 0;
   return v;
+}
+
+extern "C" int ga_seed_salt_set(uint64_t* dev_salt) {
+  ga::g_seed_salt = dev_salt;
+  return 0;
+}
+extern "C" int ga_seed_salt_bump(void* stream) {
+  GA_CHECK(ga::g_seed_salt != nullptr, "ga_seed_salt_bump: no salt buffer registered (ga_seed_salt_set)");
+  ga::seed_salt_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(const_cast<uint64_t*>(ga::g_seed_salt));
+  GA_LAUNCH_OK();
+  return 0;
 }

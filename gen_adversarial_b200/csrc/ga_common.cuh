@@ -233,6 +233,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ----------------------------------------------------------------------------- seed with an optional device-side salt
+// Kernels take their Philox seed by value.  Under CUDA-graph replay a by-value seed is frozen into the graph, so every replay would
+// draw the same noise; when a salt buffer is registered (ga_seed_salt_set) the effective seed is seed + *salt, and ga_seed_salt_bump
+// -- a one-thread kernel captured as the first node of the graph -- advances the salt on every replay with no host involvement.
+const uint64_t* seed_salt_ptr();                       // host: the registered device buffer (nullptr = none)
+struct SeedArg {
+  uint64_t seed;
+  const uint64_t* salt;
+  __device__ __forceinline__ uint64_t get() const { return salt != nullptr ? seed + *salt : seed; }
+};
+static inline SeedArg make_seed(uint64_t seed) { return SeedArg{seed, seed_salt_ptr()}; }
+
 // ----------------------------------------------------------------------------- counter-based RNG (Philox4x32-10)
 // Stream is keyed by (seed, stream id, element counter) so results do not depend on launch geometry or on
 // how a batch is sharded over GPUs ("per-GPU seeded eps streams keyed by global sample index").

@@ -112,6 +112,8 @@ class MLVGMDefenseModel(ABC):
         self._alpha_pinned = None
         self._explicit_noise = None
         self._taps_cache = {}
+        self.use_cuda_graph = False     # enable_cuda_graph(): replay a captured graph of the whole call (no-grad calls, Philox noise)
+        self._graphs = {}
         self.noise_seed = None          # None: a fresh seed is drawn from torch's CPU generator on every call
         self.sample_offset = 0          # global index of sample 0 (data-parallel shards keep results G-independent)
 
@@ -128,6 +130,15 @@ class MLVGMDefenseModel(ABC):
         """Parity/test hook: the next call consumes these N(0,1) tensors (reference draw order)
         instead of the in-kernel Philox stream.  Pass None to go back to Philox."""
         self._explicit_noise = None if noises is None else [t.to(self.device, torch.float32).contiguous() for t in noises]
+
+    def enable_cuda_graph(self, on: bool = True):
+        """Replay the whole `__call__` (and, through `PGDLinf`, the attack iteration) as a CUDA graph: one graph per (batch shape, eps,
+        blur, sample_offset); alphas and noise stay run-time inputs (device memory / seed salt).  Outputs are static buffers that the
+        next call overwrites.  Calls that need gradients or explicit noise run eagerly."""
+        self.use_cuda_graph = bool(on)
+        if not on:
+            self._graphs.clear()
+        return self
 
     def _alphas_device(self) -> torch.Tensor:
         """`interpolation_alphas` is a plain list that callers reassign between calls (common_utils.py:88); the
@@ -175,6 +186,13 @@ class MLVGMDefenseModel(ABC):
         if batch.requires_grad and torch.is_grad_enabled():
             from ...autograd import defense_apply
             preds, purified = defense_apply(self, batch)
+        elif self.use_cuda_graph and self._explicit_noise is None and batch.is_cuda:
+            from ...graphs import GraphedForward
+            key = GraphedForward.make_key(self, batch)
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = GraphedForward(self, batch)
+            preds, purified = g(self, batch)
         else:
             preds, purified = self._forward_cuda(batch.detach())
         if preds_only:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 7
+#define GA_ABI_VERSION 8
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3, GA_PRE_AFFINE = 4 };
@@ -70,6 +70,11 @@ typedef struct ga_conv_desc {
 } ga_conv_desc;
 
 const char* ga_last_error(void);
+/* Device-side seed salt for CUDA-graph replay: every Philox kernel uses seed + *salt when a salt buffer is registered.
+ * ga_seed_salt_bump (a one-thread kernel, capturable as the first node of a graph) advances it, so each replay draws fresh noise
+ * although the by-value seeds are frozen into the graph.  Pass NULL to unregister. */
+int ga_seed_salt_set(uint64_t* dev_salt);
+int ga_seed_salt_bump(void* stream);
 int ga_abi_version(void);
 /* number of kernels launched by this library on the calling thread since the last reset (bench.py "gpu_launches") */
 int64_t ga_launch_count(int reset);

@@ -6,7 +6,7 @@ import torch
 from gen_adversarial_b200 import ops, synth
 from gen_adversarial_b200._lib import ACT_NONE, ACT_SILU, ACT_ELU, ACT_RELU
 from gen_adversarial_b200.attacks import PGDLinf
-from gen_adversarial_b200.nvae_spec import NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION
+from gen_adversarial_b200.nvae_spec import NvaeSpec, NVAE_C32_CONFIG, NVAE_C32_RESOLUTION, tiny_config
 from gen_adversarial_b200.defenses.ours.models import NVAEDefenseModel, CelebaIdentityClassifier
 from oracle import nvae_ref
 from tests import emu_ops
@@ -221,3 +221,48 @@ def test_purifier_gradient_bf16_is_accurate(c32_models):
     rel = ((gx - g_ref).norm() / g_ref.norm()).item()
     print(f"[bf16] purifier-only gradient: rel-L2 {rel:.3e}, cosine {cos:.6f}")
     assert cos >= 0.999 and rel <= 3e-2
+
+
+def test_cuda_graph_replay_matches_eager_and_draws_fresh_noise():
+    """CUDA-graph mode of the public API: same result as the eager call for the same seed salt state; every replay draws fresh
+    noise (device-side salt); alphas stay run-time inputs; the graphed PGD loop respects the eps ball and flips predictions like
+    the eager loop."""
+    from gen_adversarial_b200 import graphs
+    from gen_adversarial_b200.attacks import PGDLinf
+    from gen_adversarial_b200.defenses.ours.models import NVAEDefenseModel, CelebaIdentityClassifier
+    cfg, res = tiny_config(initial_channels=16, groups=2, scales=2, latent=4), (3, 32, 32)
+    spec = NvaeSpec(cfg, res)
+    clf = CelebaIdentityClassifier({"state_dict": synth.make_vgg11_state_dict(10, seed=3, device=DEV)}, DEV, mode="fp32", n_classes=10, image_size=32)
+    n = spec.n_latents
+    dm = NVAEDefenseModel(clf, synth.make_nvae_checkpoint(cfg, res, seed=3), [0.5] * n, 1.0, 1.0, True, DEV, mode="fp32")
+    dm.noise_seed = 5
+    x = synth.synthetic_batch(4, res, seed=2)[0].to(DEV)
+    graphs.enable_seed_salt(DEV).zero_()
+    eager = dm(x).clone()                                     # salt = 0: seed 5
+    dm.enable_cuda_graph(True)
+    graphs.enable_seed_salt(DEV).zero_()
+    g1 = dm(x).clone()                                        # capture (warm-up + capture bump the salt), then first replay
+    g2 = dm(x).clone()
+    assert (g1 - g2).abs().max().item() > 1e-6               # fresh noise per replay
+    salt = graphs.enable_seed_salt(DEV)
+    s_before = int(salt.item())
+    g3 = dm(x).clone()
+    dm.enable_cuda_graph(False)
+    v = (s_before + 0x9E3779B97F4A7C15) & ((1 << 64) - 1)     # the salt value the third replay ran with (uint64 add, stored as int64)
+    salt.copy_(torch.tensor([v - (1 << 64) if v >= (1 << 63) else v], dtype=torch.int64))
+    e3 = dm(x).clone()
+    assert (g3 - e3).abs().max().item() <= 1e-5 * max(1.0, e3.abs().max().item())
+    salt.zero_()
+    assert (dm(x) - eager).abs().max().item() <= 1e-5 * max(1.0, eager.abs().max().item())
+    # alphas are read from device memory at replay time
+    dm.enable_cuda_graph(True)
+    a = dm(x).clone()
+    dm.interpolation_alphas = [0.0] * n
+    b = dm(x).clone()
+    assert (a - b).abs().max().item() > 1e-4
+    # graphed PGD
+    y = dm(x).argmax(1)
+    succ, linf, x_adv = PGDLinf(8 / 255, 2 / 255, 5)(x, y, dm)
+    assert linf.max().item() <= 8 / 255 + 1e-6 and x_adv.min().item() >= 0 and x_adv.max().item() <= 1
+    assert (x_adv - x).abs().max().item() > 1e-3
+    graphs.enable_seed_salt(DEV).zero_()
