@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         float dv[16], pre16[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pre16[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-        act_grad_n<16>(pre16, dv, p.post_act);
+        act_grad_fast_n<16>(pre16, dv, p.post_act);          // dact is bf16
         if (p.tma_store) {
           uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
           const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);

@@ -185,6 +185,11 @@ static int launch_dw(const ga_tensor* in, const void* mul, const float* weight, 
                 : launch_dw2<TIn, TOut, GA_ACT_NONE, false>(in, mul, weight, bias, up, out, dact, s);
 }
 
+// persistent TMA-pipelined bf16 kernel (dwconv_tma.cu)
+bool dwconv_tma_supported(const ga_tensor* in, const ga_tensor* mul, const ga_tensor* out, const ga_tensor* dact);
+int dwconv_tma_launch(const ga_tensor* in, const ga_tensor* mul, const float* weight, const float* bias, int act, int up,
+                      const ga_tensor* out, const ga_tensor* dact, cudaStream_t s);
+
 }  // namespace ga
 
 using namespace ga;
@@ -205,6 +210,7 @@ static int dw_dispatch(const ga_tensor* in, const ga_tensor* mul, const float* w
   const void* m = mul ? mul->data : nullptr;
   void* da = dact ? dact->data : nullptr;
   if (in->dtype == GA_F32) return launch_dw<float, float>(in, m, weight, bias, act, up, out, da, s);
+  if (dwconv_tma_supported(in, mul, out, dact)) return dwconv_tma_launch(in, mul, weight, bias, act, up, out, dact, s);
   return launch_dw<__nv_bfloat16, __nv_bfloat16>(in, m, weight, bias, act, up, out, da, s);
 }
 

@@ -172,6 +172,26 @@ __device__ __forceinline__ void act_grad_n(const float (&pre)[N], float (&d)[N],
   }
 }
 
+// bf16-grade derivative (results rounded to bf16 by the caller): SiLU' from ONE MUFU.TANH -- with h = v/2, t = tanh(h):
+// silu'(v) = s (1 + v (1 - s)), s = (1 + t)/2  =  1/2 + (t + h (1 - t^2)) / 2.  The exact form costs an expf and a full-precision
+// division per element (~25 instructions), which made the taping epilogues of the attack path issue-bound.
+template <int N>
+__device__ __forceinline__ void act_grad_fast_n(const float (&pre)[N], float (&d)[N], int act) {
+  if (act == GA_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float h = 0.5f * pre[j];
+      const float t = tanh_approx(h);
+      d[j] = fmaf(0.5f, fmaf(h, fmaf(-t, t, 1.0f), t), 0.5f);
+    }
+  } else if (act == GA_ACT_ELU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) d[j] = pre[j] > 0.0f ? 1.0f : __expf(pre[j]);
+  } else {
+    act_grad_n<N>(pre, d, act);
+  }
+}
+
 // packed fp32 FMA (Blackwell FFMA2): two independent FMAs per issue slot -- d.xy = a.xy * b.xy + c.xy
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   uint64_t d;

@@ -144,6 +144,33 @@ def test_dwconv5x5():
         assert (gotb.float().cpu() - ref).abs().max().item() <= 3e-2
 
 
+@pytest.mark.parametrize("n,h,w,c,up", [(3, 16, 16, 128, False), (2, 32, 32, 64, False), (2, 12, 16, 96, False), (5, 8, 8, 192, False),
+                                        (2, 64, 64, 32, False), (2, 24, 40, 72, False), (3, 8, 8, 128, True), (2, 16, 16, 96, True),
+                                        (1, 4, 4, 64, True), (300, 8, 8, 64, False)])
+def test_dwconv5x5_bf16_tma_pipeline(n, h, w, c, up):
+    """persistent TMA-pipelined bf16 kernel (dwconv_tma.cu): plain forward, taping forward (dact) and backward (flipped taps x mul);
+    whole / partial tiles, partial channel blocks, nearest-x2 input, more tiles than resident CTAs"""
+    g = torch.Generator().manual_seed(n * 1000 + c)
+    x = torch.randn(n, h, w, c, generator=g).bfloat16()
+    wt = torch.randn(25, c, generator=g) * 0.2
+    b = torch.randn(c, generator=g) * 0.1
+    s = 2 if up else 1
+    m = torch.randn(n, h * s, w * s, c, generator=g).bfloat16()
+    xd, wd, bd, md = x.to(DEV), wt.to(DEV), b.to(DEV), m.to(DEV)
+    ref = emu_ops.dwconv5x5(x.float(), wt, b, ACT_SILU, up, torch.float32)
+    got = ops.dwconv5x5(xd, wd, bd, ACT_SILU, up, torch.bfloat16)
+    scale = max(1.0, ref.abs().max().item())
+    assert got.shape == ref.shape and (got.float().cpu() - ref).abs().max().item() <= 1e-2 * scale
+    ry, rd = emu_ops.dwconv5x5(x.float(), wt, b, ACT_SILU, up, torch.float32, want_dact=True)
+    gy, gd = ops.dwconv5x5(xd, wd, bd, ACT_SILU, up, torch.bfloat16, want_dact=True)
+    assert torch.equal(gy, got)                                              # the taping variant computes the same values
+    assert (gd.float().cpu() - rd).abs().max().item() <= 1e-2
+    rm = emu_ops.dwconv5x5(x.float(), wt, None, ACT_NONE, up, torch.float32, mul=m.float())
+    gm = ops.dwconv5x5(xd, wd, None, ACT_NONE, up, torch.bfloat16, mul=md)
+    assert (gm.float().cpu() - rm).abs().max().item() <= 1e-2 * max(1.0, rm.abs().max().item())
+    assert torch.equal(gm, ops.dwconv5x5(xd, wd, None, ACT_NONE, up, torch.bfloat16, mul=md))     # deterministic
+
+
 @pytest.mark.parametrize("c,hw", [(32, 64), (64, 32), (256, 8), (512, 4), (24, 8), (8, 16)])
 def test_channel_sum_and_se_residual(c, hw):
     g = torch.Generator().manual_seed(c)
