@@ -122,6 +122,7 @@ _PROTOS = {
     "ga_se_residual_bwd": (c_int, [T, T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, T, c_void_p]),
     "ga_sumpool2x2": (c_int, [T, T, T, c_void_p]),
     "ga_upsample_bilinear2x_bwd": (c_int, [T, T, c_void_p]),
+    "ga_depth_to_space2": (c_int, [T, T, c_void_p]),
     "ga_maxpool2x2_bwd": (c_int, [T, T, c_int, T, c_void_p]),
     "ga_latent_mix_bwd": (c_int, [T, T, T, c_void_p, c_uint64, c_int, c_int64, c_void_p, c_float, c_int, T, T, c_void_p]),
     "ga_discmix_mean_bwd": (c_int, [T, c_int, c_void_p, T, T, c_void_p]),
@@ -175,7 +176,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 8:
+    if L.ga_abi_version() != 9:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

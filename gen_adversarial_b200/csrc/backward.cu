@@ -84,7 +84,45 @@ __global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const void* __restri
   const int64_t base = ((int64_t)n * HW + p0) * C;
   const int cnt = (p1 - p0) * C;
   float* dst = partial + ((int64_t)n * gridDim.x + blockIdx.x) * C;
-  if (256 % C == 0) {
+  const int cg = C >> 2;                       // 4-channel groups
+  if ((C & 3) == 0 && cg <= 256 && 256 % cg == 0) {
+    // vector path: a thread owns 4 channels of every PL-th pixel (16-byte fp32 / 8-byte bf16 loads, 4 pixels in flight per thread);
+    // the pixel lanes are then added in fixed order (bit-reproducible)
+    __shared__ float s_vec[256][4];
+    const int PL = 256 / cg;
+    const int g4 = threadIdx.x % cg, pl = threadIdx.x / cg;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int npix = p1 - p0;
+    for (int q0 = pl; q0 < npix; q0 += 4 * PL) {
+      float gv[4][4], rv[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + u * PL;
+        if (q < npix) {
+          const int64_t off = base + (int64_t)q * C + 4 * g4;
+          if (g_dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(g) + off, gv[u]);
+          else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(g) + off, gv[u]);
+          if (r_dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(r) + off, rv[u]);
+          else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(r) + off, rv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (q0 + u * PL < npix) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(gv[u][j], rv[u][j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_vec[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t = 0.f;
+      for (int l = 0; l < PL; ++l) t += s_vec[l * cg + (c >> 2)][c & 3];
+      dst[c] = t;
+    }
+  } else if (256 % C == 0) {
     float acc = 0.f;
     for (int i = threadIdx.x; i < cnt; i += 256) acc = fmaf(ld1b(g, g_dtype, base + i), ld1b(r, r_dtype, base + i), acc);
     s_part[threadIdx.x] = acc;
@@ -171,6 +209,32 @@ __global__ void __launch_bounds__(256) se_bwd_apply_kernel(SeBwdParams p) {
   const int p1 = min(p0 + p.pix_per_block, p.HW);
   const int64_t base = ((int64_t)n * p.HW + p0) * p.C;
   const int cnt = (p1 - p0) * p.C;
+  if ((p.C & 3) == 0) {
+    const int c4n = p.C >> 2, cnt4 = cnt >> 2;
+    for (int i0 = tid; i0 < cnt4; i0 += 256 * 4) {       // 4 vectors per thread in flight
+      float gv[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < cnt4) {
+          if (p.g_dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(p.g) + base + (int64_t)i * 4, gv[u]);
+          else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.g) + base + (int64_t)i * 4, gv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i >= cnt4) continue;
+        const int c = (i % c4n) * 4;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf(p.res_scale * s_gate[c + j], gv[u][j], s_gmean[c + j]);
+        if (p.gr_dtype == GA_F32) st4<float>(reinterpret_cast<float*>(p.g_r) + base + (int64_t)i * 4, o);
+        else st4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.g_r) + base + (int64_t)i * 4, o);
+      }
+    }
+    return;
+  }
   for (int i = tid; i < cnt; i += 256) {
     const int c = i % p.C;
     st1b(p.g_r, p.gr_dtype, base + i, fmaf(p.res_scale * s_gate[c], ld1b(p.g, p.g_dtype, base + i), s_gmean[c]));
@@ -193,6 +257,22 @@ __global__ void sumpool2x2_kernel(const void* in, int in_dtype, const void* mul,
             ld1b(in, in_dtype, b + (int64_t)W * C + C);
   if (mul != nullptr) v *= ld1b(mul, mul_dtype, idx);
   st1b(out, out_dtype, idx, v);
+}
+
+// depth-to-space x2: out[n][2a+pi][2b+pj][c] = in[n][a][b][(2 pi + pj) C + c].  The input gradient of a stride-2 convolution is computed
+// as ONE stride-1 tensor-core conv over grad_out that emits the four output phases as 4C channels (nvae_engine._build_dgrad); this kernel
+// interleaves them.  4 channels per thread: reads and writes are 16-byte vectors on contiguous channel runs.
+__global__ void __launch_bounds__(256) depth_to_space2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t total4, int h,
+                                                              int w, int c4) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over the OUTPUT, channel-vector granularity
+  if (idx >= total4) return;
+  const int c = (int)(idx % c4);
+  int64_t t = idx / c4;
+  const int X = (int)(t % (2 * w)); t /= 2 * w;
+  const int Y = (int)(t % (2 * h));
+  const int64_t n = t / (2 * h);
+  const int ph = (Y & 1) * 2 + (X & 1);
+  out[idx] = __ldg(in + (((n * h + (Y >> 1)) * w + (X >> 1)) * 4 + ph) * c4 + c);
 }
 
 // transpose of the align_corners=True bilinear x2 up-sampling, as a deterministic gather
@@ -435,6 +515,18 @@ extern "C" int ga_sumpool2x2(const ga_tensor* in, const ga_tensor* mul, const ga
   sumpool2x2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, mul ? mul->data : nullptr,
                                                                         mul ? mul->dtype : GA_F32, out->data, out->dtype, out->n, out->h,
                                                                         out->w, out->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_depth_to_space2(const ga_tensor* in, const ga_tensor* out, void* stream) {
+  GA_CHECK(in && out && in->dtype == GA_F32 && out->dtype == GA_F32, "ga_depth_to_space2: fp32 tensors expected");
+  GA_CHECK(out->n == in->n && out->h == 2 * in->h && out->w == 2 * in->w && in->c == 4 * out->c && out->c % 4 == 0,
+           "ga_depth_to_space2: shape mismatch (in [n,h,w,4c] -> out [n,2h,2w,c], c % 4 == 0)");
+  const int64_t total4 = numel(out) / 4;
+  if (total4 == 0) return 0;
+  depth_to_space2_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)in->data, (float4*)out->data, total4, in->h,
+                                                                              in->w, out->c / 4);
   GA_LAUNCH_OK();
   return 0;
 }

@@ -13,6 +13,7 @@
 // scripts/ubench_pipes.cu: 0.5 inst/clk/SMSP -- so the floor is 128 FMA/clk/SM = 1600 cycles per 8x16x64 tile).
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "ga_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -57,8 +58,9 @@ __global__ void __launch_bounds__(TW * 16, TW == 16 ? 2 : 4) dwconv5x5_tma_kerne
 
   const int tid = threadIdx.x;
   const int cb = blockIdx.x % p.cblocks;                                   // this CTA's 64-channel block
-  const int64_t s0 = blockIdx.x / p.cblocks;
-  const int64_t sstep = gridDim.x / p.cblocks;
+  const int s0 = blockIdx.x / p.cblocks;
+  const int sstep = gridDim.x / p.cblocks;
+  const int tiles = (int)p.tiles;
   const int per_img = p.tiles_x * p.tiles_y;
   const bool use_mul = EXTRAS && p.has_mul != 0;
 
@@ -71,15 +73,15 @@ __global__ void __launch_bounds__(TW * 16, TW == 16 ? 2 : 4) dwconv5x5_tma_kerne
   }
   __syncthreads();
 
-  auto issue = [&](int64_t s, int b) {
-    const int n = (int)(s / per_img);
-    const int rem = (int)(s - (int64_t)n * per_img);
+  auto issue = [&](int s, int b) {
+    const int n = s / per_img;
+    const int rem = s - n * per_img;
     const int oy0 = (rem / p.tiles_x) * DT_TH, ox0 = (rem % p.tiles_x) * TW;
     mbar_expect_tx(&full[b], G::IN_BYTES + (use_mul ? G::MUL_BYTES : 0));
     tma_load_4d(&tmIn, &full[b], s_in + b * G::IN_BYTES, cb * DT_CH, UP ? ox0 / 2 - 1 : ox0 - 2, UP ? oy0 / 2 - 1 : oy0 - 2, n);
     if (use_mul) tma_load_4d(&tmMul, &full[b], s_mul + b * G::MUL_BYTES, cb * DT_CH, ox0, oy0, n);
   };
-  if (tid == 0 && s0 < p.tiles) issue(s0, 0);
+  if (tid == 0 && s0 < tiles) issue(s0, 0);
 
   // ---- per-thread taps (2 channels x 25) and bias: loaded once, the CTA stays on one channel block
   const int cp = tid & 31;                       // channel pair = lane: shared reads of a warp are 128 contiguous bytes
@@ -92,12 +94,12 @@ __global__ void __launch_bounds__(TW * 16, TW == 16 ? 2 : 4) dwconv5x5_tma_kerne
   const float2 b2 = (c_ok && p.bias != nullptr) ? __ldg(reinterpret_cast<const float2*>(p.bias + c0)) : make_float2(0.f, 0.f);
 
   int i = 0;
-  for (int64_t s = s0; s < p.tiles; s += sstep, ++i) {
+  for (int s = s0; s < tiles; s += sstep, ++i) {
     const int b = i & 1;
     // buffer b^1 was read in iteration i-1; every thread has passed that iteration's trailing barrier
-    if (tid == 0 && s + sstep < p.tiles) issue(s + sstep, b ^ 1);
-    const int n = (int)(s / per_img);
-    const int rem = (int)(s - (int64_t)n * per_img);
+    if (tid == 0 && s + sstep < tiles) issue(s + sstep, b ^ 1);
+    const int n = s / per_img;
+    const int rem = s - n * per_img;
     const int oy0 = (rem / p.tiles_x) * DT_TH, ox0 = (rem % p.tiles_x) * TW;
     mbar_wait(&full[b], (uint32_t)((i >> 1) & 1));
 
@@ -130,40 +132,51 @@ __global__ void __launch_bounds__(TW * 16, TW == 16 ? 2 : 4) dwconv5x5_tma_kerne
       }
     }
     if (c_ok) {
-      const uint32_t mul_a = smem_u32(s_mul + b * G::MUL_BYTES) + (uint32_t)cp * 4u;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int ox = ox0 + 2 * txp + j;
-        if (ox >= p.W) continue;
-        __nv_bfloat16* orow = p.out + (((int64_t)n * p.H + oy0) * p.W + ox) * p.C + c0;
-        __nv_bfloat16* drow = EXTRAS && p.dact != nullptr ? p.dact + (((int64_t)n * p.H + oy0) * p.W + ox) * p.C + c0 : nullptr;
-        const int64_t rstride = (int64_t)p.W * p.C;
+      const uint32_t mul_a = smem_u32(s_mul + b * G::MUL_BYTES) + (uint32_t)((2 * txp) * (DT_CH * 2) + cp * 4);
+      // one 64-bit address per tile; rows / the second column advance it by constant strides (the generic per-element index
+      // arithmetic was 600 of the 1500 instructions per tile)
+      const int64_t base_off = ((((int64_t)n * p.H + oy0) * p.W + ox0 + 2 * txp) * p.C + c0) * 2;
+      const int64_t rstride = (int64_t)p.W * p.C * 2;
+      const bool want_d = EXTRAS && p.dact != nullptr;
+      auto store_tile = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + base_off;
+        uint8_t* drow = reinterpret_cast<uint8_t*>(p.dact) + base_off;
+        const bool col1 = FULL || ox0 + 2 * txp + 1 < p.W;
+        const bool col0 = FULL || ox0 + 2 * txp < p.W;
 #pragma unroll
         for (int r = 0; r < DT_TH; ++r) {
-          if (oy0 + r >= p.H) break;
-          const float ax = acc[r][j].x, ay = acc[r][j].y;
-          float yx, yy;
-          if (act == GA_ACT_SILU) {
-            // one MUFU.TANH serves SiLU and its derivative: with h = v/2, t = tanh(h): silu = h + h t, silu' = 1/2 + (t + h (1 - t^2)) / 2
-            const float hx = 0.5f * ax, hy = 0.5f * ay;
-            const float tx = tanh_approx(hx), ty = tanh_approx(hy);
-            yx = fmaf(hx, tx, hx); yy = fmaf(hy, ty, hy);
-            if (EXTRAS && drow != nullptr) {
-              const float dx_ = fmaf(0.5f, fmaf(hx, fmaf(-tx, tx, 1.0f), tx), 0.5f);
-              const float dy_ = fmaf(0.5f, fmaf(hy, fmaf(-ty, ty, 1.0f), ty), 0.5f);
-              *reinterpret_cast<uint32_t*>(drow + r * rstride) = pack_bf16x2(dx_, dy_);
+          if (!FULL && oy0 + r >= p.H) break;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (!(j == 0 ? col0 : col1)) continue;
+            const float ax = acc[r][j].x, ay = acc[r][j].y;
+            float yx, yy;
+            if (act == GA_ACT_SILU) {
+              // one MUFU.TANH serves SiLU and its derivative: with h = v/2, t = tanh(h): silu = h + h t, silu' = 1/2 + (t + h (1 - t^2)) / 2
+              const float hx = 0.5f * ax, hy = 0.5f * ay;
+              const float tx = tanh_approx(hx), ty = tanh_approx(hy);
+              yx = fmaf(hx, tx, hx); yy = fmaf(hy, ty, hy);
+              if (want_d) {
+                const float dx_ = fmaf(0.5f, fmaf(hx, fmaf(-tx, tx, 1.0f), tx), 0.5f);
+                const float dy_ = fmaf(0.5f, fmaf(hy, fmaf(-ty, ty, 1.0f), ty), 0.5f);
+                *reinterpret_cast<uint32_t*>(drow + j * (p.C * 2)) = pack_bf16x2(dx_, dy_);
+              }
+            } else {
+              yx = ax; yy = ay;
+              if (want_d) *reinterpret_cast<uint32_t*>(drow + j * (p.C * 2)) = 0x3f803f80u;      // bf16 (1, 1)
             }
-          } else {
-            yx = ax; yy = ay;
-            if (EXTRAS && drow != nullptr) *reinterpret_cast<uint32_t*>(drow + r * rstride) = pack_bf16x2(1.0f, 1.0f);
+            if (use_mul) {
+              const float2 m = dt_bf2_to_f2(dt_lds_b32(mul_a + (uint32_t)((r * TW + j) * (DT_CH * 2))));
+              yx *= m.x; yy *= m.y;
+            }
+            *reinterpret_cast<uint32_t*>(orow + j * (p.C * 2)) = pack_bf16x2(yx, yy);
           }
-          if (use_mul) {
-            const float2 m = dt_bf2_to_f2(dt_lds_b32(mul_a + (uint32_t)((r * TW + 2 * txp + j) * (DT_CH * 2))));
-            yx *= m.x; yy *= m.y;
-          }
-          *reinterpret_cast<uint32_t*>(orow + r * rstride) = pack_bf16x2(yx, yy);
+          orow += rstride; drow += rstride;
         }
-      }
+      };
+      if (oy0 + DT_TH <= p.H && ox0 + TW <= p.W) store_tile(std::true_type{});
+      else store_tile(std::false_type{});
     }
     __syncthreads();                             // all reads of buffer b done before its next TMA (issued at the top of iteration i+1)
   }

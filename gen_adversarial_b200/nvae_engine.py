@@ -24,6 +24,28 @@ from .nvae_spec import NvaeSpec, EncCell, DecCell
 _PRE_TO_ACT = {PRE_ELU: ACT_ELU, PRE_SILU: ACT_SILU, PRE_AFFINE_SILU: ACT_SILU}
 
 
+def stride2_dgrad_phase_weights(w: torch.Tensor, pad: int) -> torch.Tensor:
+    """w [cout, cin, k, k] of a stride-2 conv (3x3 pad 1, or 1x1 pad 0) -> weights [4*cin, cout, k, k] of the stride-1 conv over grad_out
+    (same k and 'same' padding) whose output channels (2*pi + pj)*cin + c are the input gradient at pixels (2a + pi, 2b + pj).
+    Forward: out[y] = sum_ky W[ky] in[2y + ky - pad]  =>  gin[2a + pi] = sum over (y, ky) with 2y + ky - pad = 2a + pi:
+      3x3 pad 1: pi = 0 -> (y = a, ky = 1);  pi = 1 -> (y = a, ky = 2), (y = a + 1, ky = 0)        1x1 pad 0: pi = 0 -> (y = a, ky = 0)"""
+    cout, cin, k, _ = w.shape
+    if k == 3 and pad == 1:
+        taps = {0: [(0, 1)], 1: [(0, 2), (1, 0)]}          # phase -> [(dy, ky)]
+    elif k == 1 and pad == 0:
+        taps = {0: [(0, 0)], 1: []}
+    else:
+        raise NotImplementedError(f"stride-2 dgrad phases for k={k} pad={pad}")
+    wd = torch.zeros(4, cin, cout, k, k, dtype=w.dtype)
+    c = k // 2
+    for pi in (0, 1):
+        for pj in (0, 1):
+            for dy, ky in taps[pi]:
+                for dx, kx in taps[pj]:
+                    wd[2 * pi + pj, :, :, c + dy, c + dx] = w[:, :, ky, kx].t()
+    return wd.reshape(4 * cin, cout, k, k)
+
+
 class _Enc:
     __slots__ = ("c1", "c2", "se", "skip", "down", "pre_affine", "c1_d", "c2_d", "skip_d")
 
@@ -199,6 +221,12 @@ class NvaeEngine:
         if not self.bf16:
             out_hw = (g.shape[1] * L.up, g.shape[2] * L.up) if L.up > 1 else None
             return ops.conv2d_simt(g, L, torch.float32, add=add, out_hw=out_hw, mul=mul, mul_mode=mul_mode)
+        if L.phase is not None and f32 and mul is None:
+            # stride-2 conv: the four output phases as one stride-1 tensor-core conv over g, then interleaved (the zero-stuffed
+            # transposed conv ran on the SIMT kernel: 0.35-0.67 ms per launch at batch 128)
+            _, o4 = self._conv(g, L.phase, want_act=False, want_f32=True)
+            o = ops.depth_to_space2(o4)
+            return o if add is None else ops.add(o, add, torch.float32)
         ob, of = self._conv(g, L, add=add, want_act=not f32, want_f32=f32, mul=mul, mul_mode=mul_mode)
         return of if f32 else ob
 
@@ -380,7 +408,11 @@ class NvaeEngine:
             if pad_cin_to is not None and pad_cin_to > w.shape[0]:       # dgrad input channels = forward cout, zero padded
                 w = torch.cat([w, torch.zeros((pad_cin_to - w.shape[0],) + tuple(w.shape[1:]), dtype=w.dtype)], dim=0)
             wt = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()           # [cin, cout(_pad), kh, kw]
-            return f.conv(wt, None, stride=1, pad=L.kh - 1 - L.pad, name=L.name + ".dgrad", up=L.stride)
+            D = f.conv(wt, None, stride=1, pad=L.kh - 1 - L.pad, name=L.name + ".dgrad", up=L.stride)
+            if self.bf16 and L.stride == 2 and w.shape[0] % 8 == 0 and L.cin % 4 == 0:
+                P = f.conv(stride2_dgrad_phase_weights(w, L.pad), None, stride=1, pad=L.kh // 2, name=L.name + ".dgrad4", simt=False)
+                D.phase = P if P.w_tc is not None else None
+            return D
 
         for _, e, _ in self._enc_sequence():
             e.c1_d, e.c2_d = dg(e.c1), dg(e.c2)

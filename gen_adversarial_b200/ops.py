@@ -123,6 +123,7 @@ class ConvLayer:
     cin2: int = 0                              # channels of the second (1x1) K source folded into w_tc
     act_slope: Optional[torch.Tensor] = None   # fp32 [cout] negative slopes (ACT_PRELU)
     act_after_add: bool = False                # out = act(conv + bias + add)
+    phase: Optional["ConvLayer"] = None        # dgrad of a stride-2 conv as ONE stride-1 conv emitting the 4 output phases (4*cout channels)
     name: str = ""
 
     def desc(self, tc: bool, mul=None, mul_mode: int = 0, dact=None) -> GaConvDesc:
@@ -573,6 +574,15 @@ def upsample_bilinear2x_bwd(g_out, out_dtype):
     n, h, w, c = g_out.shape
     out = torch.empty((n, h // 2, w // 2, c), device=g_out.device, dtype=out_dtype)
     _lib.check(_lib.lib().ga_upsample_bilinear2x_bwd(gt(g_out), gt(out), stream()), "upsample_bilinear2x_bwd")
+    return out
+
+
+@_timed("depth_to_space2")
+def depth_to_space2(x: torch.Tensor) -> torch.Tensor:
+    """[n,h,w,4c] fp32 (phase-major channels) -> [n,2h,2w,c]"""
+    n, h, w, c4 = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c4 // 4), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ga_depth_to_space2(gt(x), gt(out), stream()), "depth_to_space2")
     return out
 
 

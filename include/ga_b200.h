@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 8
+#define GA_ABI_VERSION 9
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3, GA_PRE_AFFINE = 4 };
@@ -230,6 +230,10 @@ int ga_se_residual_bwd(const ga_tensor* g_out, const ga_tensor* r, const float* 
                        const ga_tensor* g_r, void* stream);
 int ga_sumpool2x2(const ga_tensor* in, const ga_tensor* mul /*nullable, out's shape*/, const ga_tensor* out, void* stream); /* nearest x2 backward (* mul) */
 int ga_upsample_bilinear2x_bwd(const ga_tensor* g_out, const ga_tensor* g_in, void* stream);
+/* depth-to-space x2 (fp32): out[n][2a+pi][2b+pj][c] = in[n][a][b][(2 pi + pj) C + c] -- interleaves the four output phases of a stride-2
+ * convolution's input gradient, computed as one stride-1 tensor-core conv over grad_out (replaces the zero-stuffed SIMT transposed conv;
+ * reference: autograd of the stride-2 convs of architecture.py:64-82,96-136) */
+int ga_depth_to_space2(const ga_tensor* in, const ga_tensor* out, void* stream);
 /* gradient to the first maximal element of each window (torch semantics); relu=1 also applies the mask x_in > 0 */
 int ga_maxpool2x2_bwd(const ga_tensor* x_in, const ga_tensor* g_out, int relu, const ga_tensor* g_in, void* stream);
 int ga_latent_mix_bwd(const ga_tensor* g_z, const ga_tensor* q, const ga_tensor* p /*nullable*/, const float* eps_nchw,

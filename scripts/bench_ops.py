@@ -1,0 +1,49 @@
+"""CUDA-event timing of single ops at the attack-path / purify-path shapes (isolated, L2-flushed between launches):
+python scripts/bench_ops.py [dwconv] [k1] [se]"""
+import sys
+import torch
+sys.path.insert(0, ".")
+from gen_adversarial_b200 import ops
+from gen_adversarial_b200._lib import ACT_NONE, ACT_SILU
+
+DEV = "cuda:0"
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def dwconv():
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for (n, h, c, up) in [(128, 32, 384, False), (128, 16, 768, False), (128, 8, 1536, False), (512, 64, 96, False),
+                          (512, 16, 768, True), (512, 32, 192, True), (512, 8, 1536, True)]:
+        x = torch.randn(n, h, h, c, device=DEV, generator=g).bfloat16()
+        w = torch.randn(25, c, device=DEV, generator=g) * 0.2
+        b = torch.randn(c, device=DEV, generator=g) * 0.1
+        s = 2 if up else 1
+        m = torch.randn(n, h * s, h * s, c, device=DEV, generator=g).bfloat16()
+        elems_out = n * h * s * h * s * c
+        elems_in = n * h * h * c
+        t_plain = timeit(lambda: ops.dwconv5x5(x, w, b, ACT_SILU, up, torch.bfloat16))
+        t_tape = timeit(lambda: ops.dwconv5x5(x, w, b, ACT_SILU, up, torch.bfloat16, want_dact=True))
+        t_bwd = timeit(lambda: ops.dwconv5x5(x, w, None, ACT_NONE, up, torch.bfloat16, mul=m)) if not up else float("nan")
+        gb = lambda k_out, t: (elems_in * 2 + k_out * elems_out * 2) / t / 1e3
+        print(f"dwconv n={n} hw={h} c={c} up={int(up)}: plain {t_plain:7.1f} us ({gb(1, t_plain):5.0f} GB/s)  taping {t_tape:7.1f} us "
+              f"({gb(2, t_tape):5.0f} GB/s)  backward {t_bwd:7.1f} us ({gb(2, t_bwd):5.0f} GB/s)   FMA floor {elems_out * 25 / (148 * 128 * 1.965e3):6.1f} us")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["dwconv"]
+    if "dwconv" in which:
+        dwconv()

@@ -459,6 +459,13 @@ def sumpool2x2(x, out_dtype, mul=None):
     return y.contiguous().to(out_dtype)
 
 
+def depth_to_space2(x):
+    _launches[0] += 1
+    n, h, w, c4 = x.shape
+    c = c4 // 4
+    return x.float().view(n, h, w, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * h, 2 * w, c).contiguous()
+
+
 def upsample_bilinear2x_bwd(g_out, out_dtype):
     _launches[0] += 1
     n, h, w, c = g_out.shape

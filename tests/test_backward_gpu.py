@@ -28,7 +28,7 @@ def test_affine_act_bwd_and_add():
     assert (ops.add(x.to(DEV), gr.to(DEV).bfloat16(), torch.float32).cpu() - (x + gr.bfloat16().float())).abs().max().item() <= 1e-6
 
 
-@pytest.mark.parametrize("c,hw", [(64, 32), (256, 8), (24, 8)])
+@pytest.mark.parametrize("c,hw", [(64, 32), (256, 8), (24, 8), (128, 16), (32, 64), (512, 4)])
 def test_se_residual_bwd(c, hw):
     g = torch.Generator().manual_seed(c)
     r, go = torch.randn(2, hw, hw, c, generator=g), torch.randn(2, hw, hw, c, generator=g)
@@ -39,6 +39,11 @@ def test_se_residual_bwd(c, hw):
     sums = ops.channel_sum(r.to(DEV))
     got = ops.se_residual_bwd(go.to(DEV), r.to(DEV), sums, tuple(t.to(DEV) for t in se), 0.1, torch.float32)
     assert (got.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    # the attack path's dtypes: fp32 stream gradient, bf16 branch output, bf16 result
+    rb = r.bfloat16()
+    refb = emu_ops.se_residual_bwd(go, rb.float(), None, se, 0.1, torch.float32)
+    gotb = ops.se_residual_bwd(go.to(DEV), rb.to(DEV), ops.channel_sum(rb.to(DEV)), tuple(t.to(DEV) for t in se), 0.1, torch.bfloat16)
+    assert gotb.dtype == torch.bfloat16 and (gotb.float().cpu() - refb).abs().max().item() <= 1e-2 * max(1.0, refb.abs().max().item())
 
 
 def test_resampling_backward_kernels():
@@ -52,6 +57,29 @@ def test_resampling_backward_kernels():
     for relu in (False, True):
         got = ops.maxpool2x2_bwd(xin.to(DEV), go.to(DEV), relu, torch.float32)
         assert (got.cpu() - emu_ops.maxpool2x2_bwd(xin, go, relu, torch.float32)).abs().max().item() <= 1e-6
+
+
+def test_depth_to_space2_and_stride2_phase_dgrad():
+    """depth-to-space kernel vs the torch restatement; stride-2 dgrad through the phase conv (tensor cores) vs autograd"""
+    import torch.nn.functional as F
+    from gen_adversarial_b200.nvae_engine import stride2_dgrad_phase_weights
+    from gen_adversarial_b200.fold import Folder
+    g = torch.Generator().manual_seed(0)
+    x4 = torch.randn(3, 5, 7, 4 * 12, generator=g)
+    assert torch.equal(ops.depth_to_space2(x4.to(DEV)).cpu(), emu_ops.depth_to_space2(x4))
+    for k, pad in ((3, 1), (1, 0)):
+        cin, cout, n, h = 32, 64, 4, 32
+        w = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64) / (k * cin ** 0.5)
+        x = torch.randn(n, cin, h, h, generator=g, dtype=torch.float64, requires_grad=True)
+        y = F.conv2d(x, w, None, stride=2, padding=pad)
+        go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        ref, = torch.autograd.grad(y, [x], go)
+        P = Folder({}, DEV, want_tc=True).conv(stride2_dgrad_phase_weights(w, pad), None, stride=1, pad=k // 2, simt=False)
+        gb = go.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+        assert ops.conv2d_tc_supported(gb, P)
+        _, o4 = ops.conv2d_tc(gb, P, want_bf16=False, want_f32=True)
+        got = ops.depth_to_space2(o4).permute(0, 3, 1, 2).cpu().double()
+        assert (got - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
 def test_dwconv_extras_and_conv_epilogue_extras():

@@ -116,3 +116,22 @@ def test_vgg_backward_host_logic_matches_torchvision_autograd(emu):
     # branch in two correct fp32 implementations, so the max-abs error is not a stable metric: use the relative L2 error
     rel_l2 = ((g - g_ref).norm() / g_ref.norm()).item()
     assert rel_l2 <= 5e-3, rel_l2
+
+
+@pytest.mark.parametrize("k,pad", [(3, 1), (1, 0)])
+def test_stride2_dgrad_phase_weights_match_autograd(k, pad):
+    """input gradient of a stride-2 conv = one stride-1 conv over grad_out emitting the 4 output phases + depth-to-space
+    (nvae_engine.stride2_dgrad_phase_weights) -- against torch autograd of F.conv2d."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(k)
+    cin, cout, n, h = 8, 16, 2, 12
+    w = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64)
+    x = torch.randn(n, cin, h, h, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, None, stride=2, padding=pad)
+    go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    ref, = torch.autograd.grad(y, [x], go)
+    wd = nvae_engine.stride2_dgrad_phase_weights(w, pad)
+    o4 = F.conv2d(go, wd, None, stride=1, padding=k // 2)                                  # [n, 4*cin, h/2, h/2]
+    got = emu_ops.depth_to_space2(o4.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
