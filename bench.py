@@ -193,7 +193,7 @@ def run_ours(args):
 
     mode = args.mode
     sg = args.workload in ("gender", "cars")
-    B = args.batch if args.batch is not None else {"purify": 512, "pgd": 128, "gender": 128, "cars": 256}[args.workload]
+    B = args.batch if args.batch is not None else {"purify": 512, "pgd": 512, "gender": 128, "cars": 256}[args.workload]
     if sg:
         # BASELINE configs[2] / [3]: StyleGAN-E4E @1024 + ResNet-50 (ours_linear_noise_gender.yaml) and
         # Style-Transformer @512 + ResNeXt-50 (ours_cosine_blur_cars.yaml); YAML values verbatim
@@ -407,7 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 512 purify / 128 pgd)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 512 purify / 512 pgd)")
     ap.add_argument("--workload", default="purify", choices=["purify", "pgd", "gender", "cars"])
     ap.add_argument("--chunk", type=int, default=0, help="generator batch chunk of the StyleGAN workloads (0: automatic)")
     ap.add_argument("--pgd-steps", type=int, default=50)

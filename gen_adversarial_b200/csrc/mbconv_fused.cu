@@ -38,6 +38,8 @@ struct MbParams {
   const float* dw_b;            // [hidden]
   const float* bp;              // [C] project bias
   __nv_bfloat16* out;           // [N][H][W][C]
+  int act_hi;                   // 1: activation warps are warps 9-12 (scheduler priority is highest-warp-id-first), depthwise warps 1-8
+  int sleep_ns;                 // back-off of the SIMT mbarrier polls
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -45,13 +47,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // mbarrier wait for the SIMT warps: back off between polls so that a waiting warp does not take issue slots from the warps of the
 // other role that share its scheduler (activation and depthwise warps wait for each other by design)
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 100) {
   uint32_t done;
   asm volatile(
       "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
       : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   while (!done) {
-    __nanosleep(100);
+    __nanosleep(ns);
     asm volatile(
         "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -141,7 +143,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) { s_be[i] = p.be[i]; s_dwb[i] = p.dw_b[i]; }
+    // expand bias pre-halved: SiLU(v) = h + h tanh(h) with h = v/2 = fma(acc, 0.5, be/2) -- exact (power-of-two scaling), one FMA-pipe op less
+    for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) { s_be[i] = 0.5f * p.be[i]; s_dwb[i] = p.dw_b[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -227,13 +230,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       }
     }
     __syncwarp();
-  } else if (warp <= 4) {
+  } else if (p.act_hi ? warp >= 9 : warp <= 4) {
     // ======================================================================= activation warps (1-4, one per TMEM lane quadrant):
     // expand accumulator -> + bias -> SiLU -> bf16 -> H[k & 1] (swizzled rows), one chunk ahead of the depthwise warps
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
     for (int k = 0; k < nch; ++k) {
-      mbar_wait_backoff(&exp_full[k & 1], (k >> 1) & 1);
-      if (k >= 2) mbar_wait_backoff(&h_empty[k & 1], ((k - 2) >> 1) & 1);          // depthwise(k-2) has read this H buffer
+      mbar_wait_backoff(&exp_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
+      if (k >= 2) mbar_wait_backoff(&h_empty[k & 1], ((k - 2) >> 1) & 1, (uint32_t)p.sleep_ns);          // depthwise(k-2) has read this H buffer
       tc_fence_after();
       const uint32_t hb = smem_u32(sH) + (k & 1) * H_BYTES;
       const uint32_t be_a = smem_u32(s_be) + k * 256;
@@ -259,7 +262,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 b = lds_f2(be_a + (c16 * 16 + 2 * j) * 4);
-            const float v0 = silu_fast(__uint_as_float(r[c16][2 * j]) + b.x), v1 = silu_fast(__uint_as_float(r[c16][2 * j + 1]) + b.y);
+            const float h0 = fmaf(__uint_as_float(r[c16][2 * j]), 0.5f, b.x), h1 = fmaf(__uint_as_float(r[c16][2 * j + 1]), 0.5f, b.y);
+            const float v0 = fmaf(h0, tanh_approx(h0), h0), v1 = fmaf(h1, tanh_approx(h1), h1);
             pk[j] = in_img ? pack_bf16x2(v0, v1) : 0u;
           }
           const uint32_t ch0 = (uint32_t)(c16 * 2);                       // 16-byte chunk index inside the 128-byte row
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       if (lane == 0) { mbar_arrive(&exp_empty[k & 1]); mbar_arrive(&h_full[k & 1]); }
     }
     // ---- project accumulator -> + bias -> r (bf16) -> HBM
-    mbar_wait_backoff(proj_full, 0);
+    mbar_wait_backoff(proj_full, 0, (uint32_t)p.sleep_ns);
     tc_fence_after();
     const int64_t pix0 = (W_IMG == 32) ? ((int64_t)n0 * p.H + y0) * W_IMG : (int64_t)n0 * p.H * W_IMG;
     const int64_t total_pix = (int64_t)p.N * p.H * W_IMG;
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     }
   } else {
     // ======================================================================= depthwise warps (5-12): 5x5 + bias + SiLU: H -> A2
-    const int sw = warp - 5;                 // 0..7
+    const int sw = p.act_hi ? warp - 1 : warp - 5;   // 0..7
     // strip of this warp
     const int img = (W_IMG == 8) ? (sw >> 2) : 0;
     const int cs = (W_IMG == 8) ? (sw & 3) * G::STRIP_W : sw * G::STRIP_W;
@@ -321,13 +325,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     for (int k = 0; k < nch; ++k) {
       float2 wt[25];
       {
-        mbar_wait_backoff(&dww_full[k & 1], (k >> 1) & 1);
+        mbar_wait_backoff(&dww_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
         const uint32_t wsrc = smem_u32(s_dww) + ((k & 1) * 25 * 64 + 2 * lane) * 4;
 #pragma unroll
         for (int t = 0; t < 25; ++t) wt[t] = lds_f2(wsrc + t * 256);
       }
       const float2 b2 = lds_f2(smem_u32(s_dwb) + (k * 64 + 2 * lane) * 4);
-      mbar_wait_backoff(&h_full[k & 1], (k >> 1) & 1);
+      mbar_wait_backoff(&h_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
       const uint32_t hb = smem_u32(sH) + (k & 1) * H_BYTES;
       // the strip's rows are produced in passes of RP rows (RP + 4 input rows each): RP x STRIP_W accumulators + 25 taps stay in
       // registers under the 128-register cap of a 13-warp CTA (16K registers per SM sub-partition, 4 warps on one of them)
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(&h_empty[k & 1]);                     // this warp is done reading H[k & 1]
         }
-        if (pass == 0 && k >= 1) mbar_wait_backoff(a2_empty, (k - 1) & 1); // project(k-1) has consumed A2
+        if (pass == 0 && k >= 1) mbar_wait_backoff(a2_empty, (k - 1) & 1, (uint32_t)p.sleep_ns); // project(k-1) has consumed A2
 #pragma unroll
         for (int oy = 0; oy < RP; ++oy)
 #pragma unroll
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       }
       fence_proxy_async_smem();                                            // generic-proxy writes -> visible to the MMA (async proxy)
       simt_bar();                                                          // A2 complete (all 8 depthwise warps)
-      if (threadIdx.x == 5 * 32) mbar_arrive(a2_full);
+      if (sw == 0 && lane == 0) mbar_arrive(a2_full);
     }
   }
   tc_fence_before();
@@ -470,6 +474,10 @@ extern "C" int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const floa
   MbParams p;
   p.N = x->n; p.H = x->h; p.hidden = hidden; p.be = be; p.dw_w = dw_w; p.dw_b = dw_b; p.bp = bp;
   p.out = (__nv_bfloat16*)out->data;
+  static int act_hi = -1, sleep_ns = -1;
+  if (act_hi < 0) { const char* e = getenv("GA_MB_ACT_HI"); act_hi = e ? atoi(e) : 0; }
+  if (sleep_ns < 0) { const char* e = getenv("GA_MB_SLEEP_NS"); sleep_ns = e ? atoi(e) : 100; }
+  p.act_hi = act_hi; p.sleep_ns = sleep_ns;
   cudaStream_t s = (cudaStream_t)stream;
   if (x->w == 8) return launch_mbconv<256, 8, 1>(x, we_tc, wp_tc, p, s);
   if (x->w == 16) return launch_mbconv<128, 16, 1>(x, we_tc, wp_tc, p, s);

@@ -43,7 +43,30 @@ def dwconv():
               f"({gb(2, t_tape):5.0f} GB/s)  backward {t_bwd:7.1f} us ({gb(2, t_bwd):5.0f} GB/s)   FMA floor {elems_out * 25 / (148 * 128 * 1.965e3):6.1f} us")
 
 
+def mbconv():
+    import math
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for (n, w, c) in [(512, 32, 64), (512, 16, 128), (512, 8, 256)]:
+        hidden = 6 * c
+        e = ops.ConvLayer(1, 1, 1, 0, c, hidden, post_act=ACT_SILU, name="expand")
+        e.w_tc = (torch.randn(hidden, c, device=DEV, generator=g) / math.sqrt(c)).bfloat16().contiguous()
+        e.bias = torch.randn(hidden, device=DEV, generator=g) * 0.3
+        p = ops.ConvLayer(1, 1, 1, 0, hidden, c, post_act=ACT_NONE, name="project")
+        p.w_tc = (torch.randn(c, hidden, device=DEV, generator=g) / math.sqrt(hidden)).bfloat16().contiguous()
+        p.bias = torch.randn(c, device=DEV, generator=g) * 0.3
+        dw = ops.dw_weights_chunked(torch.randn(25, hidden, device=DEV, generator=g) / 5.0)
+        db = torch.randn(hidden, device=DEV, generator=g) * 0.3
+        x = torch.randn(n, w, w, c, device=DEV, generator=g).bfloat16()
+        t = timeit(lambda: ops.mbconv_fused(x, e, dw, db, p))
+        m = n * w * w
+        fl = 2.0 * m * hidden * c * 2 + 2.0 * m * hidden * 25
+        print(f"mbconv n={n} hw={w} c={c} hidden={hidden}: {t:7.1f} us  {fl / t / 1e6:6.1f} TFLOP/s   fp32-pipe floor "
+              f"{m * hidden * (25 + 5) / (148 * 128 * 1.965e3):6.1f} us")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dwconv"]
     if "dwconv" in which:
         dwconv()
+    if "mbconv" in which:
+        mbconv()
