@@ -38,6 +38,7 @@ struct TcParams {
   int H, W;
   int64_t M;                  // total output pixels
   int cout;
+  int n_blocks;               // output-channel blocks (grid = m_tiles * n_blocks, N block fastest)
   const float* bias;
   int post_act;
   const void* add; int add_dtype;
@@ -82,12 +83,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.y;
+  // 1-D grid, N block fastest: the CTAs that share an A tile (same pixels, different output-channel blocks) are scheduled back to back, so
+  // the tile is fetched from HBM once and hits L2 afterwards (ncu, 1x1 expand 64 -> 384: the A tensor was read 3x from DRAM)
+  const int n_blk = blockIdx.x % p.n_blocks;
 
   // ---- tile -> pixel box
   int n0, y0, x0;
   {
-    const int t = blockIdx.x;
+    const int t = blockIdx.x / p.n_blocks;
     if (p.bn > 1) { n0 = t * p.bn; y0 = 0; x0 = 0; }
     else {
       const int per_img = p.tiles_x * p.tiles_y;
@@ -207,11 +210,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       float v[16];
       const int64_t off = pix * p.cout + nb;
       const bool full = vec_ok && nb + 16 <= p.cout;
+      bool have_v = false;
       if (p.dact != nullptr && (row_ok || p.tma_store)) {   // save act'(pre-activation) for the backward pass
         float dv[16], pre16[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pre16[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-        act_grad_fast_n<16>(pre16, dv, p.post_act);          // dact is bf16
+        if (!GENERAL_ACT && p.post_act == GA_ACT_SILU) { silu_with_grad_fast_n<16>(pre16, v, dv); have_v = true; }   // one tanh for both
+        else act_grad_fast_n<16>(pre16, dv, p.post_act);     // dact is bf16
         if (p.tma_store) {
           uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
           const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
@@ -229,9 +234,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             if (nb + j < p.cout) p.dact[off + j] = __float2bfloat16_rn(dv[j]);
         }
       }
+      if (!have_v) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-      if (!GENERAL_ACT) {
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+      }
+      if (have_v) {
+      } else if (!GENERAL_ACT) {
         apply_act_fast_n<16>(v, p.post_act);
       } else if (!p.act_after_add) {
 #pragma unroll
@@ -558,7 +566,9 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.dact = (__nv_bfloat16*)d->dact_out;
   p.act_slope = d->act_slope; p.act_after_add = d->act_after_add;
   GA_CHECK(d->post_act != GA_ACT_PRELU || d->act_slope != nullptr, "ga_conv2d_tc: PReLU needs act_slope");
-  dim3 grid((unsigned)g.m_tiles, (unsigned)((out->c + block_n - 1) / block_n));
+  p.n_blocks = (out->c + block_n - 1) / block_n;
+  GA_CHECK(g.m_tiles * p.n_blocks < (int64_t)1 << 31, "ga_conv2d_tc: grid too large");
+  dim3 grid((unsigned)(g.m_tiles * p.n_blocks));
   cudaStream_t s = (cudaStream_t)stream;
   // TMA-store epilogue needs 16-byte aligned row pitches and bases; tiny / odd Cout falls back to direct stores
   static int tma_store_enabled = -1;

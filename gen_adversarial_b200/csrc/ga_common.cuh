@@ -192,6 +192,19 @@ __device__ __forceinline__ void act_grad_fast_n(const float (&pre)[N], float (&d
   }
 }
 
+// SiLU and its derivative from the SAME MUFU.TANH (taping epilogues: the XU pipe does 16 lanes / clk / SM, a second tanh per element
+// would cost as much as the whole HBM time of a 6C-wide 1x1 conv)
+template <int N>
+__device__ __forceinline__ void silu_with_grad_fast_n(const float (&pre)[N], float (&y)[N], float (&d)[N]) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float h = 0.5f * pre[j];
+    const float t = tanh_approx(h);
+    y[j] = fmaf(h, t, h);
+    d[j] = fmaf(0.5f, fmaf(h, fmaf(-t, t, 1.0f), t), 0.5f);
+  }
+}
+
 // packed fp32 FMA (Blackwell FFMA2): two independent FMAs per issue slot -- d.xy = a.xy * b.xy + c.xy
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   uint64_t d;

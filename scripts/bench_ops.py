@@ -64,9 +64,46 @@ def mbconv():
               f"{m * hidden * (25 + 5) / (148 * 128 * 1.965e3):6.1f} us")
 
 
+def k1():
+    """the 1x1 convs of the attack path's decoder cells: expand with SiLU + saved derivative, dgrad of the project conv times a saved
+    derivative, project; plus the 3x3 tower conv for reference"""
+    import math
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for (n, w, c) in [(512, 32, 64), (512, 16, 128), (512, 8, 256)]:
+        hidden = 6 * c
+        m = n * w * w
+        x = torch.randn(n, w, w, c, device=DEV, generator=g).bfloat16()
+        hbig = torch.randn(n, w, w, hidden, device=DEV, generator=g).bfloat16()
+        e = ops.ConvLayer(1, 1, 1, 0, c, hidden, post_act=ACT_SILU, name="expand")
+        e.w_tc = (torch.randn(hidden, c, device=DEV, generator=g) / math.sqrt(c)).bfloat16().contiguous()
+        e.bias = torch.randn(hidden, device=DEV, generator=g) * 0.3
+        pd = ops.ConvLayer(1, 1, 1, 0, c, hidden, post_act=ACT_NONE, name="project.dgrad")
+        pd.w_tc = e.w_tc
+        pr = ops.ConvLayer(1, 1, 1, 0, hidden, c, post_act=ACT_NONE, name="project")
+        pr.w_tc = (torch.randn(c, hidden, device=DEV, generator=g) / math.sqrt(hidden)).bfloat16().contiguous()
+        pr.bias = torch.randn(c, device=DEV, generator=g) * 0.3
+        k3 = ops.ConvLayer(3, 3, 1, 1, c, c, post_act=ACT_SILU, name="k3")
+        k3.w_tc = (torch.randn(c, 9 * c, device=DEV, generator=g) / math.sqrt(9 * c)).bfloat16().contiguous()
+        k3.bias = torch.randn(c, device=DEV, generator=g) * 0.3
+        dact = torch.empty(n, w, w, hidden, device=DEV, dtype=torch.bfloat16)
+        ob = torch.empty(n, w, w, hidden, device=DEV, dtype=torch.bfloat16)
+        os_ = torch.empty(n, w, w, c, device=DEV, dtype=torch.bfloat16)
+        t_plain = timeit(lambda: ops.conv2d_tc(x, e, out_bf16=ob))
+        t_tape = timeit(lambda: ops.conv2d_tc(x, e, dact_out=dact, out_bf16=ob))
+        t_dg = timeit(lambda: ops.conv2d_tc(x, pd, mul=hbig, out_bf16=ob))
+        t_pr = timeit(lambda: ops.conv2d_tc(hbig, pr, out_bf16=os_))
+        t_k3 = timeit(lambda: ops.conv2d_tc(x, k3, out_bf16=os_))
+        big, small = m * hidden * 2, m * c * 2
+        print(f"k1 n={n} hw={w} c={c}: expand {t_plain:6.1f} us ({(small + big) / t_plain / 1e3:5.0f} GB/s)  expand+dact {t_tape:6.1f} us "
+              f"({(small + 2 * big) / t_tape / 1e3:5.0f} GB/s)  dgrad*mul {t_dg:6.1f} us ({(small + 2 * big) / t_dg / 1e3:5.0f} GB/s)  "
+              f"project {t_pr:6.1f} us ({(small + big) / t_pr / 1e3:5.0f} GB/s)  k3 {t_k3:6.1f} us ({2.0 * m * c * 9 * c / t_k3 / 1e6:5.0f} TFLOP/s)")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dwconv"]
     if "dwconv" in which:
         dwconv()
     if "mbconv" in which:
         mbconv()
+    if "k1" in which:
+        k1()

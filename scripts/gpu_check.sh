@@ -12,6 +12,7 @@ echo "== nvae parity" ; timeout -s KILL 900 python -m pytest tests/test_nvae_gpu
 echo "== backward / pgd" ; timeout -s KILL 900 python -m pytest tests/test_backward_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/backward.log 2>&1; grep -E "grad|PGD|passed|failed|FAILED|Error|error" gpurun_out/backward.log | tail -30
 echo "== stylegan" ; timeout -s KILL 600 python -m pytest tests/test_stylegan_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/stylegan.log 2>&1; grep -E "generator@|passed|failed|FAILED|Error|error" gpurun_out/stylegan.log | tail -12
 echo "== stylegan paths (configs 3/4)" ; timeout -s KILL 900 python -m pytest tests/test_stylegan_paths_gpu.py -q -m gpu -s -p no:cacheprovider > gpurun_out/stylegan_paths.log 2>&1; grep -E "purified max-abs|passed|failed|FAILED|Error|error|assert" gpurun_out/stylegan_paths.log | tail -25
+echo "== ablations / alpha search" ; timeout -s KILL 300 python -m pytest tests/test_ablations_gpu.py -q -m gpu -p no:cacheprovider 2>&1 | tail -3
 echo "== smoke" ; timeout -s KILL 300 python __graft_entry__.py smoke 2>&1 | tail -4 | tee gpurun_out/smoke.log
 echo "== bench" ; timeout -s KILL 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; rc=$?; python -c "
 import json;d=json.load(open('gpurun_out/bench.json'));r=d['roofline'];print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, 'e2e',d['e2e']['value'],'tc',r['achieved'],r['frac'],r['share_of_step']);[print(x) for x in r['by_shape']];print(d['cpu_baseline'])"; tail -5 gpurun_out/bench.err
