@@ -53,7 +53,7 @@ struct TcParams {
 };
 
 template <int BLOCK_N, int STAGES, bool GENERAL_ACT>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 128 ? 4 : 2)) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmA2,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmOutB,
@@ -211,12 +211,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       const int64_t off = pix * p.cout + nb;
       const bool full = vec_ok && nb + 16 <= p.cout;
       bool have_v = false;
-      if (p.dact != nullptr && (row_ok || p.tma_store)) {   // save act'(pre-activation) for the backward pass
-        float dv[16], pre16[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pre16[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-        if (!GENERAL_ACT && p.post_act == GA_ACT_SILU) { silu_with_grad_fast_n<16>(pre16, v, dv); have_v = true; }   // one tanh for both
-        else act_grad_fast_n<16>(pre16, dv, p.post_act);     // dact is bf16
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+      if (p.dact != nullptr && (row_ok || p.tma_store)) {   // save act'(pre-activation) for the backward pass
+        float dv[16];
+        if (!GENERAL_ACT && p.post_act == GA_ACT_SILU) { silu_with_grad_fast_n<16>(v, v, dv); have_v = true; }   // one tanh for both, in place
+        else act_grad_fast_n<16>(v, dv, p.post_act);         // dact is bf16
         if (p.tma_store) {
           uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
           const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
@@ -233,10 +233,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           for (int j = 0; j < 16; ++j)
             if (nb + j < p.cout) p.dact[off + j] = __float2bfloat16_rn(dv[j]);
         }
-      }
-      if (!have_v) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
       }
       if (have_v) {
       } else if (!GENERAL_ACT) {

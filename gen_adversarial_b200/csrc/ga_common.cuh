@@ -195,7 +195,7 @@ __device__ __forceinline__ void act_grad_fast_n(const float (&pre)[N], float (&d
 // SiLU and its derivative from the SAME MUFU.TANH (taping epilogues: the XU pipe does 16 lanes / clk / SM, a second tanh per element
 // would cost as much as the whole HBM time of a 6C-wide 1x1 conv)
 template <int N>
-__device__ __forceinline__ void silu_with_grad_fast_n(const float (&pre)[N], float (&y)[N], float (&d)[N]) {
+__device__ __forceinline__ void silu_with_grad_fast_n(const float (&pre)[N], float (&y)[N], float (&d)[N]) {   // y may alias pre
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     const float h = 0.5f * pre[j];
