@@ -150,7 +150,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} steps x batch {sample} of the same workload (oracle/nvae_ref.py, torch CPU fp32, {cores} threads)"},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- our arm (GPU)
@@ -395,12 +395,21 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_other_kernels": extra, "cpu_baseline": cpu,
                 "counters": {"n_total": int(counters[0].item()), "n_clean_correct": int(counters[1].item()),
                              "n_robust_correct": int(counters[2].item())}}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+JSON_OUT = None          # the process's original stdout; file descriptor 1 itself is pointed at stderr (see main)
+
+
 def main():
+    # stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner
+    # there even with NCCL_DEBUG_FILE set), so fd 1 is redirected to stderr for the whole run and the JSON goes to a dup of the original.
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -423,7 +432,7 @@ def main():
         run_reference(args)
     else:
         args.steps = args.steps if args.steps is not None else {"purify": 10, "pgd": 2}.get(args.workload, 3)
-        args.warmup = args.warmup if args.warmup is not None else {"purify": 3, "pgd": 1}.get(args.workload, 3)
+        args.warmup = args.warmup if args.warmup is not None else {"purify": 3, "pgd": 3}.get(args.workload, 3)
         run_ours(args)
 
 

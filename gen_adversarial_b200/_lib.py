@@ -37,7 +37,7 @@ class GaConvDesc(ctypes.Structure):
     _fields_ = [("kh", c_int32), ("kw", c_int32), ("stride", c_int32), ("pad", c_int32), ("up", c_int32),
                 ("pre_op", c_int32), ("post_act", c_int32),
                 ("pre_scale", c_void_p), ("pre_shift", c_void_p), ("weight", c_void_p), ("bias", c_void_p),
-                ("reserved0", c_int32), ("ktot", c_int32),
+                ("tf32", c_int32), ("ktot", c_int32),
                 ("mul", c_void_p), ("mul_dtype", c_int32), ("mul_mode", c_int32),
                 ("dact_out", c_void_p), ("dact_dtype", c_int32), ("act_after_add", c_int32), ("act_slope", c_void_p)]
 
@@ -101,6 +101,7 @@ D = POINTER(GaConvDesc)
 _PROTOS = {
     "ga_last_error": (c_char_p, []),
     "ga_abi_version": (c_int, []),
+    "ga_f32_round_tf32": (c_int, [c_int]),
     "ga_launch_count": (c_int64, [c_int]),
     "ga_seed_salt_set": (c_int, [c_void_p]),
     "ga_seed_salt_bump": (c_int, [c_void_p]),
@@ -176,7 +177,7 @@ def lib():
             raise RuntimeError(f"libga_b200.so does not export {name}")
         fn.restype = res
         fn.argtypes = args
-    if L.ga_abi_version() != 9:
+    if L.ga_abi_version() != 11:
         raise RuntimeError("libga_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -32,6 +32,7 @@ constexpr int TC_THREADS = 192;
 struct TcParams {
   int taps, kw, pad, stride;  // filter taps of source 1; stride 1 or 2 (TMA element strides do the decimation)
   int k32;                    // 1: 32-channel K blocks (64-byte swizzle) for Cin = 32, 96, ...: no half-empty 64-channel boxes
+  int tf32;                   // 1: fp32 activations and weights, kind::tf32 MMA, 32-channel K blocks (32 x 4 B = one 128-byte swizzle row)
   int cin, kc1, kc2;          // channels of source 1, its 64-blocks per tap, 64-blocks of source 2
   int bw, bh, bn;             // pixel box of one M tile (bw*bh*bn == 128)
   int tiles_x, tiles_y;       // tiles per image row / column (bn == 1) -- else whole images per tile
@@ -50,6 +51,7 @@ struct TcParams {
   __nv_bfloat16* dact;        // taping forward: derivative of post_act at the pre-activation (bf16)
   const float* act_slope;     // PReLU slopes [cout]
   int act_after_add;          // act(acc + bias + add)
+  int round_tf32;             // fp32 output rounded to TF32 (feeds a kind::tf32 conv)
 };
 
 template <int BLOCK_N, int STAGES, bool GENERAL_ACT>
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
   if (warp == 0) {
     // ===================================================================== TMA producer
     int stage = 0; uint32_t phase = 0;
-    const int bk = p.k32 ? 32 : TC_BLOCK_K;
+    const int bk = (p.k32 || p.tf32) ? 32 : TC_BLOCK_K;
     for (int kb = 0; kb < num_kb; ++kb) {
       if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -156,7 +158,12 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_a + stage * a_stride);
         const uint32_t b_addr = smem_u32(smem_b + stage * b_stride);
-        if (p.k32) {
+        if (p.tf32) {
+          constexpr uint32_t idesc32 = make_idesc_tf32(TC_BLOCK_M, BLOCK_N);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc32, (kb > 0 || k > 0) ? 1u : 0u);
+        } else if (p.k32) {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_bf16(tmem_base, make_smem_desc_sw64(a_addr + k * 32), make_smem_desc_sw64(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -307,6 +314,9 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
           }
         }
       }
+      float vf[16];                                            // fp32 output values (TF32-rounded on request)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) vf[j] = (p.round_tf32 && p.out_f32 != nullptr) ? round_tf32(v[j]) : v[j];
       if (p.tma_store) {
         if (p.out_bf16 != nullptr) {
           uint8_t* panel = stage_b + (c0 >> 6) * (128 * 128) + row * 128;
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
           const uint32_t k0 = (uint32_t)((c0 & 31) >> 2);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(vf[4 * j], vf[4 * j + 1], vf[4 * j + 2], vf[4 * j + 3]);
         }
       } else if (row_ok) {
         if (full) {
@@ -333,14 +343,14 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
           if (p.out_f32 != nullptr) {
             float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(vf[4 * j], vf[4 * j + 1], vf[4 * j + 2], vf[4 * j + 3]);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (nb + j >= p.cout) continue;
             if (p.out_bf16 != nullptr) p.out_bf16[off + j] = __float2bfloat16_rn(v[j]);
-            if (p.out_f32 != nullptr) p.out_f32[off + j] = v[j];
+            if (p.out_f32 != nullptr) p.out_f32[off + j] = vf[j];
           }
         }
       }
@@ -409,32 +419,32 @@ static bool tile_geometry(int N, int H, int W, TileGeom* g) {
   return true;
 }
 
-static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g, int stride = 1, int block_k = TC_BLOCK_K) {
+static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g, int stride = 1, int block_k = TC_BLOCK_K, int esize = 2) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
-  cuuint64_t strides[3] = {(cuuint64_t)t->c * 2, (cuuint64_t)t->w * t->c * 2, (cuuint64_t)t->h * t->w * t->c * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)t->c * esize, (cuuint64_t)t->w * t->c * esize, (cuuint64_t)t->h * t->w * t->c * esize};
   // stride-2 convs: the box spans stride*bw x stride*bh input pixels and the TMA engine keeps every stride-th one
   // (ceil(box/elementStride) elements per dimension land in shared memory)
   cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)(g.bw * stride), (cuuint32_t)(g.bh * stride), (cuuint32_t)g.bn};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, block_k * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d box=%d,%d,%d) failed: %d", t->n, t->h, t->w, t->c,
            g.bw, g.bh, g.bn, (int)r);
   return 0;
 }
 
-static int encode_weight_map(CUtensorMap* tm, const void* w, int cout, int ktot, int block_n, int block_k = TC_BLOCK_K) {
+static int encode_weight_map(CUtensorMap* tm, const void* w, int cout, int ktot, int block_n, int block_k = TC_BLOCK_K, int esize = 2) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
-  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * esize};
   cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, block_k * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight cout=%d k=%d box_n=%d) failed: %d", cout, ktot, block_n, (int)r);
   return 0;
@@ -502,7 +512,7 @@ using namespace ga;
 
 extern "C" int ga_conv2d_tc_supported(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, int cout) {
   if (!in || !d) return 0;
-  if (in->dtype != GA_BF16) return 0;
+  if (d->tf32 ? (in->dtype != GA_F32 || in2 != nullptr || in->c % 4 != 0) : (in->dtype != GA_BF16)) return 0;
   if ((d->stride != 1 && d->stride != 2) || d->up != 1 || d->pre_op != GA_PRE_NONE) return 0;
   if (!((d->kh == 1 && d->kw == 1 && d->pad == 0) || (d->kh == 3 && d->kw == 3 && d->pad == 1))) return 0;
   if (in->c % 8 != 0 || cout < 1) return 0;
@@ -539,17 +549,19 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   // last block of every tap -- at Cin = 32 that is half of all operand traffic and half of all MMAs
   static int k32_enabled = -1;
   if (k32_enabled < 0) { const char* e = getenv("GA_TC_K32"); k32_enabled = e ? atoi(e) : 1; }
-  const int k32 = (k32_enabled && !in2 && (in->c % 64) == 32) ? 1 : 0;
-  const int bk = k32 ? 32 : TC_BLOCK_K;
+  const int tf32 = d->tf32 ? 1 : 0;
+  const int k32 = (!tf32 && k32_enabled && !in2 && (in->c % 64) == 32) ? 1 : 0;
+  const int bk = (k32 || tf32) ? 32 : TC_BLOCK_K;
+  const int esize = tf32 ? 4 : 2;
   CUtensorMap tmA, tmA2, tmB;
-  if (encode_act_map(&tmA, in, g, d->stride, bk)) return 1;
+  if (encode_act_map(&tmA, in, g, d->stride, bk, esize)) return 1;
   if (in2) { if (encode_act_map(&tmA2, in2, g)) return 1; }
   else tmA2 = tmA;
-  if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n, bk)) return 1;
+  if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n, bk, esize)) return 1;
 
   TcParams p;
   p.taps = taps; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
-  p.k32 = k32;
+  p.k32 = k32; p.tf32 = tf32;
   p.cin = in->c; p.kc1 = (in->c + bk - 1) / bk; p.kc2 = in2 ? (in2->c + TC_BLOCK_K - 1) / TC_BLOCK_K : 0;
   p.bw = g.bw; p.bh = g.bh; p.bn = g.bn; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
   p.H = Ho; p.W = Wo; p.M = (int64_t)in->n * Ho * Wo;
@@ -561,6 +573,7 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   GA_CHECK(d->dact_out == nullptr || d->dact_dtype == GA_BF16, "ga_conv2d_tc: dact_out must be bf16");
   p.dact = (__nv_bfloat16*)d->dact_out;
   p.act_slope = d->act_slope; p.act_after_add = d->act_after_add;
+  p.round_tf32 = (out_f32 && round_tf32_enabled()) ? 1 : 0;
   GA_CHECK(d->post_act != GA_ACT_PRELU || d->act_slope != nullptr, "ga_conv2d_tc: PReLU needs act_slope");
   p.n_blocks = (out->c + block_n - 1) / block_n;
   GA_CHECK(g.m_tiles * p.n_blocks < (int64_t)1 << 31, "ga_conv2d_tc: grid too large");

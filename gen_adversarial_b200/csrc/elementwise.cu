@@ -273,6 +273,7 @@ struct SeParams {
   void* act; int act_dtype; const float* act_scale; const float* act_shift; int act_op;
   float* gate_out;
   int HW, C, pix_per_block, nparts;
+  int act_rtf;                 // round the fp32 `act` copy to TF32 (it feeds a kind::tf32 conv)
 };
 
 __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
@@ -339,6 +340,7 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
         for (int j = 0; j < 4; ++j) {
           const float t = fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]);
           a[j] = p.act_op == GA_ACT_SILU ? silu_fast(t) : t;
+          if (p.act_rtf) a[j] = round_tf32(a[j]);
         }
         st4d(p.act, p.act_dtype, off, a);
       }
@@ -623,19 +625,20 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(const void* in, int
 }
 
 __global__ void affine_act_kernel(const void* in, int in_dtype, const float* __restrict__ scale, const float* __restrict__ shift,
-                                  int act, void* out, int out_dtype, int C, int64_t total) {
+                                  int act, void* out, int out_dtype, int C, int64_t total, int rtf) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   float v = ld1d(in, in_dtype, idx);
   const int c = (int)(idx % C);
   if (scale != nullptr) v = fmaf(v, scale[c], shift[c]);
-  st1d(out, out_dtype, idx, apply_act(v, act));
+  v = apply_act(v, act);
+  st1d(out, out_dtype, idx, rtf ? round_tf32(v) : v);
 }
 
 // 8 elements per thread (C % 8 == 0): 16/32-byte vector accesses
 __global__ void __launch_bounds__(256) affine_act_vec8_kernel(const void* in, int in_dtype, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int act, void* out, int out_dtype,
-                                                              int C, int64_t total8) {
+                                                              int C, int64_t total8, int rtf) {
   int64_t i8 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i8 >= total8) return;
   const int64_t idx = i8 * 8;
@@ -651,6 +654,10 @@ __global__ void __launch_bounds__(256) affine_act_vec8_kernel(const void* in, in
   }
   apply_act_n<4>(a, act);
   apply_act_n<4>(b, act);
+  if (rtf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[j] = round_tf32(a[j]); b[j] = round_tf32(b[j]); }
+  }
   st4d(out, out_dtype, idx, a);
   st4d(out, out_dtype, idx + 4, b);
 }
@@ -835,6 +842,7 @@ extern "C" int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const f
   p.out2 = out2 ? out2->data : nullptr; p.out2_dtype = out2 ? out2->dtype : GA_F32;
   p.act = act ? act->data : nullptr; p.act_dtype = act ? act->dtype : GA_F32;
   p.act_scale = act_scale; p.act_shift = act_shift; p.act_op = act_op; p.gate_out = gate_out;
+  p.act_rtf = (act && act->dtype == GA_F32 && round_tf32_enabled()) ? 1 : 0;
   p.HW = r->h * r->w; p.C = r->c; p.pix_per_block = se_pix_per_block(p.HW, r->n);
   p.nparts = cdiv(p.HW, p.pix_per_block);
   const size_t smem = (2 * (size_t)p.C + hidden) * sizeof(float);
@@ -945,10 +953,11 @@ extern "C" int ga_affine_act(const ga_tensor* in, const float* scale, const floa
   GA_CHECK((scale == nullptr) == (shift == nullptr), "ga_affine_act: scale and shift go together");
   const int64_t total = numel(in);
   if (total == 0) return 0;
+  const int rtf = (out->dtype == GA_F32 && round_tf32_enabled()) ? 1 : 0;
   if ((in->c & 7) == 0)
-    affine_act_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total / 8);
+    affine_act_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total / 8, rtf);
   else
-    affine_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total);
+    affine_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, scale, shift, act, out->data, out->dtype, in->c, total, rtf);
   GA_LAUNCH_OK();
   return 0;
 }

@@ -266,6 +266,17 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ----------------------------------------------------------------------------- TF32 producers
+// tcgen05 kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits; truncation is biased (every operand shrinks), and the bias
+// compounds over a 50-layer backbone (measured: worse than bf16 operands).  While ga_f32_round_tf32(1) is in effect, kernels that
+// write fp32 activations consumed by a TF32 conv round them to nearest (cvt.rna.tf32.f32), so the MMA's truncation is exact.
+int round_tf32_enabled();                              // host: launch-time value of the switch
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 // ----------------------------------------------------------------------------- seed with an optional device-side salt
 // Kernels take their Philox seed by value.  Under CUDA-graph replay a by-value seed is frozen into the graph, so every replay would
 // draw the same noise; when a salt buffer is registered (ga_seed_salt_set) the effective seed is seed + *salt, and ga_seed_salt_bump

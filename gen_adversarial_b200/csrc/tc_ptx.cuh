@@ -62,6 +62,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with fp32 operands read as TF32 (10-bit mantissa, K = 8 per instruction = 32 bytes per row, like K = 16 bf16)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -101,6 +111,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
 // N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::tf32 instruction descriptor: c = f32, a = b = tf32 (format code 2), K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 }  // namespace ga

@@ -60,7 +60,8 @@ class Folder:
                      ("linear_1.weight", "linear_1.bias", "linear_2.weight", "linear_2.bias"))
 
     def conv(self, w: torch.Tensor, b: Optional[torch.Tensor], stride=1, pad=0, pre_op=PRE_NONE, pre_affine=None,
-             post_act=ACT_NONE, name="", w2: Optional[torch.Tensor] = None, simt: bool = True, up: int = 1) -> ConvLayer:
+             post_act=ACT_NONE, name="", w2: Optional[torch.Tensor] = None, simt: bool = True, up: int = 1,
+             tf32: bool = False) -> ConvLayer:
         """w: [cout, cin, kh, kw] fp64 (already folded). w2: optional [cout, cin2] weights of a second 1x1 source."""
         cout, cin, kh, kw = w.shape
         L = ConvLayer(kh, kw, stride, pad, cin, cout, pre_op=pre_op, post_act=post_act, name=name, up=up)
@@ -72,6 +73,10 @@ class Folder:
                 wk = torch.cat([wk, w2], dim=1)
                 L.cin2 = w2.shape[1]
             L.w_tc = wk.to(torch.bfloat16).contiguous().to(self.device)
+            if tf32 and w2 is None and cin % 4 == 0:
+                w32 = wk.to(torch.float32).contiguous()
+                bits = (w32.view(torch.int32) + 0x1000) & ~0x1FFF                # round to nearest TF32 (the MMA truncates: biased otherwise)
+                L.w_tf32 = bits.view(torch.float32).contiguous().to(self.device)
         L.bias = self.dev32(b)
         if pre_affine is not None:
             L.pre_scale, L.pre_shift = self.dev32(pre_affine[0]), self.dev32(pre_affine[1])

@@ -54,8 +54,13 @@ def conv1x1_any(engine, x, L, want_f32=False, add=None, out=None):
 class IrSe50Backbone:
     """input_layer + 24 `bottleneck_IR_SE` units; returns the taps c1 / c2 / c3 (after units 6, 20, 23)."""
 
-    def __init__(self, f: Folder, bf16: bool, in_channels: int = 3):
+    def __init__(self, f: Folder, bf16: bool, in_channels: int = 3, tf32: bool = False):
         self.bf16 = bf16
+        # tf32: in bf16 mode the 48 convs of the backbone keep fp32 activations / weights and multiply them as TF32 (kind::tf32: 10-bit
+        # mantissas, half the bf16 MMA rate).  The E4E path needs it: with a bf16 backbone its W+ codes are off by 0.35% of their range and
+        # the purified image lands AT the 1e-2 bf16 gate (DESIGN.md section 2); the taps handed to the heads stay bf16.
+        self.tf32 = bool(tf32 and bf16)
+        self.f32_taps = False                 # tf32 mode: hand the fp32 residual stream (not its bf16 copy) to the heads
         self.adt = torch.bfloat16 if bf16 else torch.float32
         w = f.f64("input_layer.0.weight")
         a, b = f.bn("input_layer.1")
@@ -69,14 +74,15 @@ class IrSe50Backbone:
             a0, b0 = f.bn(f"{p}.res_layer.0")
             u.pre = (f.dev32(a0), f.dev32(b0))
             u.c1 = f.conv(f.f64(f"{p}.res_layer.1.weight"), None, pad=1, pre_op=PRE_AFFINE, pre_affine=(a0, b0),
-                          post_act=ACT_PRELU, name=f"{p}.conv1")
+                          post_act=ACT_PRELU, name=f"{p}.conv1", tf32=self.tf32)
             u.c1.act_slope = f.dev32(f.f64(f"{p}.res_layer.2.weight"))
             a4, b4 = f.bn(f"{p}.res_layer.4")
-            u.c2 = f.conv(f.f64(f"{p}.res_layer.3.weight") * a4.view(-1, 1, 1, 1), b4, stride=stride, pad=1, name=f"{p}.conv2")
+            u.c2 = f.conv(f.f64(f"{p}.res_layer.3.weight") * a4.view(-1, 1, 1, 1), b4, stride=stride, pad=1, name=f"{p}.conv2",
+                          tf32=self.tf32)
             if cin != depth:
                 asc, bsc = f.bn(f"{p}.shortcut_layer.1")
                 u.sc = f.conv(f.f64(f"{p}.shortcut_layer.0.weight") * asc.view(-1, 1, 1, 1), bsc, stride=stride, pad=0,
-                              name=f"{p}.shortcut")
+                              name=f"{p}.shortcut", tf32=self.tf32)
             else:
                 u.sc = None
             w1 = f.f64(f"{p}.res_layer.5.fc1.weight").flatten(1)
@@ -85,6 +91,10 @@ class IrSe50Backbone:
             self.units.append(u)
 
     def _conv(self, x, L, want_f32=False, add=None, out=None):
+        if self.bf16 and x.dtype == torch.float32 and L.w_tf32 is not None and ops.conv2d_tc_supported(x, L, tf32=True):
+            ob, of = ops.conv2d_tc(x, L, want_bf16=not want_f32, want_f32=want_f32, add=add, tf32=True,
+                                   out_bf16=None if want_f32 else out, out_f32=out if want_f32 else None)
+            return of if want_f32 else ob
         if self.bf16 and L.w_tc is not None and x.dtype == torch.bfloat16 and ops.conv2d_tc_supported(x, L):
             ob, of = ops.conv2d_tc(x, L, want_bf16=not want_f32, want_f32=want_f32, add=add,
                                    out_bf16=None if want_f32 else out, out_f32=out if want_f32 else None)
@@ -95,6 +105,8 @@ class IrSe50Backbone:
         """x_nhwc (N,H,W,3) normalised input in the activation dtype -> (c1, c2, c3) in the activation dtype"""
         units = self.units
         x32 = ops.conv2d_simt(x_nhwc, self.stem, torch.float32)
+        if self.tf32:
+            return self._forward_tf32(x32)
         xa = ops.affine_act(x32, units[0].pre[0], units[0].pre[1], ACT_NONE, torch.bfloat16) if self.bf16 else None
         xb = ops.cast(x32, torch.bfloat16) if (self.bf16 and units[0].sc is not None) else None
         taps = {}
@@ -123,6 +135,58 @@ class IrSe50Backbone:
         return taps[6], taps[20], taps[23]
 
 
+    def _conv_tf32(self, x32, L, round_out: bool):
+        """fp32 activations x fp32 weights on the tensor cores as TF32 -> fp32 (rounded to TF32 when it feeds another TF32 conv);
+        shapes the TC kernel cannot tile return None (the caller falls back to the SIMT conv)"""
+        if L.w_tf32 is not None and ops.conv2d_tc_supported(x32, L, tf32=True):
+            ops.f32_round_tf32(round_out)
+            try:
+                return ops.conv2d_tc(x32, L, want_bf16=False, want_f32=True, tf32=True)[1]
+            finally:
+                ops.f32_round_tf32(False)
+        return None
+
+    @staticmethod
+    def _rounded(fn):
+        """run `fn` with fp32 activation outputs rounded to nearest TF32 (operands of kind::tf32 convs, which truncate)"""
+        ops.f32_round_tf32(True)
+        try:
+            return fn()
+        finally:
+            ops.f32_round_tf32(False)
+
+    def _forward_tf32(self, x32):
+        units = self.units
+        # BN of the first unit (the conv pads AFTER it), rounded to TF32
+        xa = self._rounded(lambda: ops.affine_act(x32, units[0].pre[0], units[0].pre[1], ACT_NONE, torch.float32))
+        taps = {}
+        for i, u in enumerate(units):
+            h = self._conv_tf32(xa, u.c1, True)
+            if h is None:
+                h = ops.conv2d_simt(x32, u.c1, torch.float32)                                   # SIMT applies the BN pre-op itself
+            r = self._conv_tf32(h, u.c2, False)                                                 # r feeds the SE mean and the fp32 stream: unrounded
+            if r is None:
+                r = ops.conv2d_simt(h, u.c2, torch.float32)
+            if u.sc is not None:
+                xs = self._rounded(lambda: ops.cast(x32, torch.float32))                        # TF32-rounded copy of the stream for the shortcut conv
+                skip = self._conv_tf32(xs, u.sc, False)
+                if skip is None:
+                    skip = ops.conv2d_simt(x32, u.sc, torch.float32)
+            else:
+                skip = x32 if u.stride == 1 else ops.subsample2x(x32)
+            sums = ops.channel_sum(r)
+            nxt = units[i + 1] if i + 1 < len(units) else None
+            is_tap = i in (6, 20, 23)
+            x32, xb, xa, _ = self._rounded(lambda: ops.se_residual(
+                r, sums, u.se, 1.0, skip, torch.float32, want_out2=is_tap, act_affine=nxt.pre if nxt is not None else None,
+                act_dtype=torch.float32, act_op=ACT_NONE))                                      # only the fp32 `act` copy is rounded
+            if is_tap:
+                # bf16 copies for the FPN / heads, or TF32-rounded copies of the fp32 stream
+                taps[i] = self._rounded(lambda: ops.cast(x32, torch.float32)) if self.f32_taps else xb
+        self.c3_f32 = x32
+        return taps[6], taps[20], taps[23]
+
+
 class _Head:
     __slots__ = ("convs", "linear")
 
@@ -138,7 +202,10 @@ class E4EEncoderEngine:
         self.bf16 = mode == "bf16"
         self.adt = torch.bfloat16 if self.bf16 else torch.float32
         f = Folder(state_dict, self.device, want_tc=self.bf16)
-        self.backbone = IrSe50Backbone(f, self.bf16)
+        env = __import__("os").environ
+        self.backbone = IrSe50Backbone(f, self.bf16, tf32=env.get("GA_E4E_TF32_BACKBONE", "1") != "0")
+        self.tf32_heads = self.bf16 and env.get("GA_E4E_TF32_HEADS", "0") != "0"      # FPN + map2style convs on fp32 operands (TF32 MMA)
+        self.backbone.f32_taps = self.tf32_heads and self.backbone.tf32
         self.style_count = 2 * int(math.log2(stylegan_size)) - 2
         self.coarse_ind, self.middle_ind = 3, 7
         self.slope = torch.full((512,), 0.01, dtype=torch.float32, device=self.device)        # nn.LeakyReLU() default
@@ -153,14 +220,14 @@ class E4EEncoderEngine:
             hd.convs = []
             for j in range(int(math.log2(spatial))):
                 L = f.conv(f.f64(f"styles.{i}.convs.{2 * j}.weight"), f.f64(f"styles.{i}.convs.{2 * j}.bias"), stride=2, pad=1,
-                           post_act=ACT_PRELU, name=f"styles.{i}.convs.{2 * j}")
+                           post_act=ACT_PRELU, name=f"styles.{i}.convs.{2 * j}", tf32=self.tf32_heads)
                 L.act_slope = self.slope
                 hd.convs.append(L)
             wl = f.f64(f"styles.{i}.linear.weight") * (1.0 / math.sqrt(512))                   # EqualLinear, lr_mul = 1
             hd.linear = f.conv(wl.view(512, 512, 1, 1), f.f64(f"styles.{i}.linear.bias"), name=f"styles.{i}.linear")
             self.heads.append(hd)
-        self.lat1 = f.conv(f.f64("latlayer1.weight"), f.f64("latlayer1.bias"), name="latlayer1")
-        self.lat2 = f.conv(f.f64("latlayer2.weight"), f.f64("latlayer2.bias"), name="latlayer2")
+        self.lat1 = f.conv(f.f64("latlayer1.weight"), f.f64("latlayer1.bias"), name="latlayer1", tf32=self.tf32_heads)
+        self.lat2 = f.conv(f.f64("latlayer2.weight"), f.f64("latlayer2.bias"), name="latlayer2", tf32=self.tf32_heads)
         self.latent_avg = None if latent_avg is None else latent_avg.to(torch.float32).reshape(-1, 512)[: self.style_count].contiguous().to(self.device)
 
     _conv = IrSe50Backbone._conv
@@ -169,7 +236,9 @@ class E4EEncoderEngine:
         """map2style head.  bf16 mode: the final EqualLinear (and, optionally, the convs on maps <= fp32_tail_hw) run in fp32"""
         x = feat
         for L in hd.convs:
-            if self.bf16 and (x.shape[1] <= self.fp32_tail_hw or x.dtype == torch.float32):
+            if self.tf32_heads and x.dtype == torch.float32 and L.w_tf32 is not None and ops.conv2d_tc_supported(x, L, tf32=True):
+                x = IrSe50Backbone._rounded(lambda: self._conv(x, L, want_f32=True))     # fp32 operands as TF32 on the tensor cores
+            elif self.bf16 and (x.shape[1] <= self.fp32_tail_hw or x.dtype == torch.float32):
                 x = ops.conv2d_simt(x, L, torch.float32)
             else:
                 x = self._conv(x, L)
@@ -179,15 +248,18 @@ class E4EEncoderEngine:
         """x_nhwc (B,256,256,3) normalised -> codes (B, n_styles, 512) fp32 (latent_avg already added, psp.py:92-99)"""
         b = x_nhwc.shape[0]
         c1, c2, c3 = self.backbone.forward(x_nhwc)
+        rnd = IrSe50Backbone._rounded if self.tf32_heads else (lambda fn: fn())
+        if self.tf32_heads and c3.dtype != torch.float32:
+            c1, c2, c3 = (ops.cast(t, torch.float32) for t in (c1, c2, c3))          # bf16 values are exact in TF32
         heads = torch.empty((self.style_count, b, 1, 1, 512), device=x_nhwc.device, dtype=torch.float32)
         feat = c3
         p2 = None
         for i, hd in enumerate(self.heads):
             if i == self.coarse_ind:
-                p2 = conv1x1_any(self, c2, self.lat1, add=ops.upsample_bilinear2x(c3))         # _upsample_add (helpers.py:122-139)
+                p2 = rnd(lambda: conv1x1_any(self, c2, self.lat1, add=ops.upsample_bilinear2x(c3), want_f32=self.tf32_heads))   # _upsample_add (helpers.py:122-139)
                 feat = p2
             elif i == self.middle_ind:
-                feat = conv1x1_any(self, c1, self.lat2, add=ops.upsample_bilinear2x(p2))
+                feat = rnd(lambda: conv1x1_any(self, c1, self.lat2, add=ops.upsample_bilinear2x(p2), want_f32=self.tf32_heads))
             # head 0 (w0, added to all 18 codes) runs in fp32 from the fp32 residual stream in both modes: 1% of the encoder's FLOPs
             self._head(self.backbone.c3_f32 if (i < self.fp32_heads and self.bf16) else feat, hd, heads[i])
         return ops.codes_assemble(heads, True, True, self.latent_avg, b, self.style_count, 512)

@@ -114,6 +114,7 @@ class ConvLayer:
     cout: int
     w_simt: Optional[torch.Tensor] = None      # fp32 [kh*kw*cin, cout]
     w_tc: Optional[torch.Tensor] = None        # bf16 [cout, ktot]  (ktot = kh*kw*cin + cin2)
+    w_tf32: Optional[torch.Tensor] = None      # fp32 [cout, ktot]: tensor-core path with fp32 activations, multiplied as TF32
     bias: Optional[torch.Tensor] = None        # fp32 [cout]
     pre_op: int = PRE_NONE
     pre_scale: Optional[torch.Tensor] = None   # fp32 [cin]
@@ -126,12 +127,12 @@ class ConvLayer:
     phase: Optional["ConvLayer"] = None        # dgrad of a stride-2 conv as ONE stride-1 conv emitting the 4 output phases (4*cout channels)
     name: str = ""
 
-    def desc(self, tc: bool, mul=None, mul_mode: int = 0, dact=None) -> GaConvDesc:
-        w = self.w_tc if tc else self.w_simt
+    def desc(self, tc: bool, mul=None, mul_mode: int = 0, dact=None, tf32: bool = False) -> GaConvDesc:
+        w = (self.w_tf32 if tf32 else self.w_tc) if tc else self.w_simt
         if w is None:
             raise RuntimeError(f"conv layer {self.name}: no {'tensor-core' if tc else 'SIMT'} weights prepared")
         return GaConvDesc(self.kh, self.kw, self.stride, self.pad, self.up, PRE_NONE if tc else self.pre_op, self.post_act,
-                          ptr(self.pre_scale), ptr(self.pre_shift), w.data_ptr(), ptr(self.bias), 0,
+                          ptr(self.pre_scale), ptr(self.pre_shift), w.data_ptr(), ptr(self.bias), int(bool(tf32 and tc)),
                           w.shape[1] if tc else 0,
                           ptr(mul), _dt(mul) if mul is not None else 0, mul_mode,
                           ptr(dact), _dt(dact) if dact is not None else 0, int(self.act_after_add), ptr(self.act_slope))
@@ -158,35 +159,39 @@ def conv2d_simt(x: torch.Tensor, L: ConvLayer, out_dtype: torch.dtype, add: Opti
     return (out, dact) if want_dact else out
 
 
-def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor] = None) -> bool:
-    if L.w_tc is None or x.dtype != torch.bfloat16:
+def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor] = None, tf32: bool = False) -> bool:
+    if tf32:
+        if L.w_tf32 is None or x.dtype != torch.float32:
+            return False
+    elif L.w_tc is None or x.dtype != torch.bfloat16:
         return False
-    d = L.desc(True)
+    d = L.desc(True, tf32=tf32)
     return bool(_lib.lib().ga_conv2d_tc_supported(gt(x), gt(x2), ctypes.byref(d), L.cout))
 
 
 def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
               add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None,
               mul: Optional[torch.Tensor] = None, mul_mode: int = 0, dact_out: Optional[torch.Tensor] = None,
-              out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
-    """-> (out_bf16 or None, out_f32 or None);  out = (act(conv + bias) + add) * f(mul); dact_out <- act'(conv + bias)"""
+              out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, tf32: bool = False):
+    """-> (out_bf16 or None, out_f32 or None);  out = (act(conv + bias) + add) * f(mul); dact_out <- act'(conv + bias).
+    tf32: x is fp32 and the layer's fp32 weights are used (kind::tf32 MMA: 10-bit mantissas, half the bf16 rate)"""
     n, h, w, c = x.shape
     assert c == L.cin, (L.name, c, L.cin)
     ho, wo = conv_out_hw(L, h, w)
     ob = (out_bf16 if out_bf16 is not None else torch.empty((n, ho, wo, L.cout), device=x.device, dtype=torch.bfloat16)) if want_bf16 else None
     of = (out_f32 if out_f32 is not None else torch.empty((n, ho, wo, L.cout), device=x.device, dtype=torch.float32)) if want_f32 else None
-    d = L.desc(True, mul, mul_mode, dact_out)
+    d = L.desc(True, mul, mul_mode, dact_out, tf32=tf32)
     e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_conv2d_tc(gt(x), gt(x2), ctypes.byref(d), gt(add), gt(ob), gt(of), stream()),
                f"conv2d_tc[{L.name}]")
     if e0 is not None:
         m = n * ho * wo
-        ktot = L.w_tc.shape[1]
+        ktot = (L.w_tf32 if tf32 else L.w_tc).shape[1]
         flops = 2.0 * m * L.cout * ktot
         # compulsory traffic: A once (not per tap), weights once, outputs (+ add) once
         bytes_ = 2.0 * n * h * w * c + 2.0 * m * (x2.shape[3] if x2 is not None else 0) + 2.0 * L.cout * ktot \
             + m * L.cout * ((2 if want_bf16 else 0) + (4 if want_f32 else 0) + (add.element_size() if add is not None else 0))
-        TIMER.stop(e0, f"k{L.kh}{'s2' if L.stride == 2 else ''} hw{h} cin{c} cout{L.cout}", flops, bytes_)
+        TIMER.stop(e0, f"k{L.kh}{'s2' if L.stride == 2 else ''}{' tf32' if tf32 else ''} hw{h} cin{c} cout{L.cout}", flops, bytes_)
     return ob, of
 
 
@@ -336,6 +341,11 @@ def affine_act(x, scale, shift, act: int, out_dtype):
 
 def cast(x, out_dtype):
     return affine_act(x, None, None, ACT_NONE, out_dtype)
+
+
+def f32_round_tf32(on: bool):
+    """while on, kernels writing fp32 activations round them to nearest TF32 (operands of the kind::tf32 convs, which truncate)"""
+    _lib.check(_lib.lib().ga_f32_round_tf32(int(bool(on))), "f32_round_tf32")
 
 
 @_timed("nchw_to_nhwc")

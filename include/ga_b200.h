@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 9
+#define GA_ABI_VERSION 11
 
 enum ga_dtype { GA_F32 = 0, GA_BF16 = 1 };
 enum ga_pre_op { GA_PRE_NONE = 0, GA_PRE_ELU = 1, GA_PRE_SILU = 2, GA_PRE_AFFINE_SILU = 3, GA_PRE_AFFINE = 4 };
@@ -57,7 +57,7 @@ typedef struct ga_conv_desc {
   const float* pre_shift;
   const void* weight;     /* SIMT: fp32 [kh*kw*cin][cout];  tensor-core: bf16 [cout][ktot] K-major */
   const float* bias;      /* [cout] or NULL */
-  int32_t reserved0;
+  int32_t tf32;            /* tensor-core path only: 1 = fp32 activations + fp32 weights multiplied as TF32 (kind::tf32), else bf16 operands */
   int32_t ktot;           /* tensor-core only: row length of `weight` = kh*kw*cin (+ cin2) */
   /* per-call epilogue extras.  out = (act(acc + bias) + add) * mul;  dact_out = act'(acc + bias) */
   const void* mul;        /* optional tensor of the output's shape (backward: derivative of the producer's activation) */
@@ -75,6 +75,10 @@ const char* ga_last_error(void);
  * although the by-value seeds are frozen into the graph.  Pass NULL to unregister. */
 int ga_seed_salt_set(uint64_t* dev_salt);
 int ga_seed_salt_bump(void* stream);
+/* TF32 producers: tcgen05 kind::tf32 truncates fp32 operands; while this switch is on, kernels that write fp32 ACTIVATIONS (conv_tc fp32
+ * output, ga_affine_act / ga_cast to fp32, the fp32 `act` copy of ga_se_residual_fwd) round them to nearest TF32 so the truncation is exact.
+ * Host-side, read at launch time on the calling thread. */
+int ga_f32_round_tf32(int on);
 int ga_abi_version(void);
 /* number of kernels launched by this library on the calling thread since the last reset (bench.py "gpu_launches") */
 int64_t ga_launch_count(int reset);

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider -k "tf32" 2>&1 | tail -6
+for cfg in "1 0" "1 1" "0 1"; do set -- $cfg
+echo "== GA_E4E_TF32_BACKBONE=$1 GA_E4E_TF32_HEADS=$2"
+GA_E4E_TF32_BACKBONE=$1 GA_E4E_TF32_HEADS=$2 timeout -s KILL 600 python scripts/diag_e4e_bf16.py 2>&1 | tail -5
+done
+GA_E4E_TF32_BACKBONE=1 GA_E4E_TF32_HEADS=1 timeout -s KILL 900 python bench.py --workload gender --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_gender_11.json 2> gpurun_out/bench_gender_11.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_gender_11.json'));print('gender 11', {k:d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'])"; tail -3 gpurun_out/bench_gender_11.err

@@ -112,8 +112,11 @@ def conv2d_simt(x, L, out_dtype, add=None, out_hw=None, mul=None, mul_mode=0, wa
     return y
 
 
-def conv2d_tc_supported(x, L, x2=None):
-    if L.w_tc is None or x.dtype != torch.bfloat16:
+def conv2d_tc_supported(x, L, x2=None, tf32=False):
+    if tf32:
+        if L.w_tf32 is None or x.dtype != torch.float32 or x2 is not None:
+            return False
+    elif L.w_tc is None or x.dtype != torch.bfloat16:
         return False
     if L.stride not in (1, 2) or L.up != 1 or (x2 is not None and L.stride != 1):
         return False
@@ -130,11 +133,11 @@ def conv2d_tc_supported(x, L, x2=None):
 
 
 def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None, mul_mode=0, dact_out=None, out_bf16=None,
-              out_f32=None):
+              out_f32=None, tf32=False):
     _launches[0] += 1
-    assert x.dtype == torch.bfloat16
+    assert x.dtype == (torch.float32 if tf32 else torch.bfloat16)
     k1 = L.kh * L.kw * L.cin
-    w = L.w_tc.float()
+    w = L.w_tf32.float() if tf32 else L.w_tc.float()
     w1 = w[:, :k1].view(L.cout, L.kh, L.kw, L.cin).permute(0, 3, 1, 2)
     y = F.conv2d(_nchw(x), w1, None, stride=L.stride, padding=L.pad)
     if x2 is not None:
@@ -457,6 +460,10 @@ def sumpool2x2(x, out_dtype, mul=None):
     if mul is not None:
         y = y * mul.float()
     return y.contiguous().to(out_dtype)
+
+
+def f32_round_tf32(on):
+    pass
 
 
 def depth_to_space2(x):

@@ -15,7 +15,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert set(_lib._PROTOS) == set(names), set(_lib._PROTOS) ^ set(names)
-    assert L.ga_abi_version() == 9
+    assert L.ga_abi_version() == 11
 
 
 def test_error_convention_without_gpu():

@@ -131,6 +131,43 @@ def test_conv_tc_bf16(case):
     assert e16 <= 1e-2 * scale, ("bf16 out", e16, scale)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k,stride,act", [(2, 32, 32, 64, 64, 3, 1, ACT_NONE), (3, 16, 16, 128, 256, 3, 2, ACT_NONE),
+                                                        (2, 64, 64, 64, 128, 1, 2, ACT_NONE), (4, 8, 8, 512, 512, 3, 1, ACT_SILU),
+                                                        (2, 128, 128, 64, 64, 3, 1, ACT_NONE), (1, 32, 32, 40, 72, 3, 1, ACT_RELU)])
+def test_conv_tc_tf32_operands(n, h, w, cin, cout, k, stride, act):
+    """kind::tf32 path of the tensor-core conv (fp32 activations / weights, 10-bit mantissas): against the fp32 torch convolution"""
+    import torch.nn.functional as F
+    from gen_adversarial_b200.fold import Folder
+    g = torch.Generator().manual_seed(cin + cout + k)
+    wt = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g, dtype=torch.float64) * 0.2
+    x = torch.randn(n, h, w, cin, generator=g)
+    L = Folder({}, DEV, want_tc=True).conv(wt, b, stride=stride, pad=k // 2, post_act=act, simt=False, tf32=True)
+    assert L.w_tf32 is not None and ops.conv2d_tc_supported(x.to(DEV), L, tf32=True)
+    ob, of = ops.conv2d_tc(x.to(DEV), L, want_bf16=True, want_f32=True, tf32=True)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), wt, b, stride=stride, padding=k // 2)
+    y = {ACT_NONE: y, ACT_SILU: F.silu(y), ACT_RELU: F.relu(y)}[act].permute(0, 2, 3, 1).float()
+    scale = max(1.0, y.abs().max().item())
+    e32 = (of.cpu() - y).abs().max().item()
+    assert of.shape == y.shape and e32 <= 2e-3 * scale, (e32, scale)          # TF32 rounding: 2^-11 per operand
+    assert (ob.float().cpu() - y).abs().max().item() <= 1e-2 * scale
+    # operands pre-rounded to nearest TF32 (what the engines do: the MMA itself truncates): the product is then exact up to fp32 accumulation
+    ops.f32_round_tf32(True)
+    xr = ops.cast(x.to(DEV), torch.float32)
+    ops.f32_round_tf32(False)
+    assert (xr.cpu() - x).abs().max().item() <= 2 ** -11 * x.abs().max().item() and not torch.equal(xr.cpu(), x)
+    assert torch.equal(ops.cast(x.to(DEV), torch.float32).cpu(), x)                 # switch off again: plain copy
+    _, ofr = ops.conv2d_tc(xr, L, want_bf16=False, want_f32=True, tf32=True)
+    wr = L.w_tf32.cpu().double().view(cout, k, k, cin).permute(0, 3, 1, 2)
+    yr = F.conv2d(xr.cpu().permute(0, 3, 1, 2).double(), wr, b, stride=stride, padding=k // 2)
+    yr = {ACT_NONE: yr, ACT_SILU: F.silu(yr), ACT_RELU: F.relu(yr)}[act].permute(0, 2, 3, 1).float()
+    assert (ofr.cpu() - yr).abs().max().item() <= (2e-5 if act != ACT_SILU else 2e-3) * scale     # SiLU epilogue uses tanh.approx
+    # and it is really more accurate than the bf16 operand path
+    Lb = Folder({}, DEV, want_tc=True).conv(wt, b, stride=stride, pad=k // 2, post_act=act, simt=False)
+    _, ofb = ops.conv2d_tc(x.to(DEV).bfloat16(), Lb, want_bf16=False, want_f32=True)
+    assert e32 < 0.5 * (ofb.cpu() - y).abs().max().item()
+
+
 def test_dwconv5x5():
     g = torch.Generator().manual_seed(0)
     for up in (False, True):
