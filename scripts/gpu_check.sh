@@ -2,7 +2,7 @@
 # One gpurun call: kernel unit tests (SIMT and tensor-core in separate processes), engine parity, smoke, short bench.
 # Optional extra stages (only if the plain bench exited 0):  ncu = launch list;  full = ncu --set full of the top kernels;
 # breakdown = per-op CUDA-event table.
-# Usage: gpurun --timeout 1800 -- bash scripts/gpu_check.sh [ncu] [full] [breakdown]
+# Usage: gpurun --timeout 1800 -- bash scripts/gpu_check.sh [pgd] [sg] [ncu] [full] [breakdown]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== kernels (non-TC)" ; timeout -s KILL 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "not conv_tc" -p no:cacheprovider > gpurun_out/kernels_simt.log 2>&1; tail -5 gpurun_out/kernels_simt.log
@@ -21,6 +21,13 @@ for stage in "$@"; do
     echo "== pgd bench"
     timeout -s KILL 900 python bench.py --workload pgd --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_pgd.json 2> gpurun_out/bench_pgd.err; python -c "
 import json;d=json.load(open('gpurun_out/bench_pgd.json'));print({k:d[k] for k in ('metric','value','ms_per_step','gpu_launches')}, d['e2e'], d['counters'], d['roofline']['achieved'])"; tail -5 gpurun_out/bench_pgd.err
+  fi
+  if [ "$stage" = "sg" ]; then
+    for wl in gender cars; do
+      echo "== $wl bench"
+      timeout -s KILL 900 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_$wl.json'));print({k:d[k] for k in ('metric','value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'])"; tail -3 gpurun_out/bench_$wl.err
+    done
   fi
   if [ $rc -ne 0 ]; then break; fi
   if [ "$stage" = "breakdown" ]; then
