@@ -352,10 +352,21 @@ def run_ours(args):
         extra = []
         if fused:
             f_ms = sum(a["ms"] for a in fused.values()); f_fl = sum(a["flops"] for a in fused.values())
+            # the stage that bounds this kernel runs on the fp32 pipe: per hidden element 25 depthwise FMAs + ~5 FMA-pipe ops of the two
+            # SiLUs; B200: 128 fp32 FMA lanes / clk / SM (scripts/ubench_pipes.cu: FFMA 1.0, FFMA2 0.5 warp-instructions / clk / SMSP)
+            import re as _re
+            simt_ops = 0.0
+            for k, a in fused.items():
+                m_ = _re.search(r"hw(\d+) c(\d+) hidden(\d+)", k)
+                simt_ops += a["launches"] * B * int(m_.group(1)) ** 2 * int(m_.group(3)) * 30.0
+            sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+            fp32_peak = 148 * 128 * sm_hz
             extra.append({"kernel": "mbconv_fused_kernel (decoder cell: expand 1x1 -> SiLU -> depthwise 5x5 -> SiLU -> project 1x1, hidden tensor on chip)",
                           "bound": "tensor", "achieved": f_fl / (f_ms * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                           "frac": f_fl / (f_ms * 1e-3) / 1e12 / pk["tf_sustained"], "launches": sum(a["launches"] for a in fused.values()),
                           "share_of_step": f_ms / ms,
+                          "fp32_pipe": {"achieved_tfma_s": simt_ops / (f_ms * 1e-3) / 1e12, "peak_tfma_s": fp32_peak / 1e12,
+                                        "frac": simt_ops / (f_ms * 1e-3) / fp32_peak},
                           "note": "issue/FMA-pipe bound by the SIMT depthwise stage (ncu: fp32 FMA pipe 25%, XU 24%, issue slots 48%, tensor pipe 6%); "
                                   "HBM traffic = x + r only (ncu dram 88 MB per 32x32 launch vs 1.6 GB for the three-kernel path)",
                           "by_shape": [{"shape": k[6:], "launches": a["launches"], "us_per_launch": round(1e3 * a["ms"] / a["launches"], 1),

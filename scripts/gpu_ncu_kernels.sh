@@ -12,3 +12,6 @@ timeout -s KILL 600 ncu --set full --clock-control none -k regex:"mbconv_fused" 
 timeout -s KILL 600 ncu --set full --clock-control none -k regex:"mbconv_fused" -s 30 -c 1 -o gpurun_out/prof_mbconv_b -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_d.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+timeout -s KILL 600 ncu --set full --clock-control none -k regex:"dwconv5x5_tma" -s 4 -c 3 -o gpurun_out/prof_dwconv_tma -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_e.log 2>&1
+ls -la gpurun_out/*.ncu-rep
