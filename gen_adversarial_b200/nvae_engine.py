@@ -476,5 +476,5 @@ class NvaeEngine:
                 g = self._enc_cell_bwd(g, rec)
             else:
                 raise RuntimeError(f"unknown tape record {kind}")
-        out_hw = None
-        return ops.conv2d_simt(g, self.init_conv_d, torch.float32, out_hw=out_hw)
+        # 32 -> 3 channels at full resolution: tensor cores in bf16 mode (the SIMT conv took 2 ms per iteration at batch 512), SIMT in fp32 mode
+        return self._dgrad(g, self.init_conv_d, f32=True)
