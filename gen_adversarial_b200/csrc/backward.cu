@@ -259,6 +259,39 @@ __global__ void sumpool2x2_kernel(const void* in, int in_dtype, const void* mul,
   st1b(out, out_dtype, idx, v);
 }
 
+// 4 channels per thread (C % 4 == 0): 16-byte fp32 / 8-byte bf16 accesses
+__global__ void __launch_bounds__(256) sumpool2x2_vec4_kernel(const void* __restrict__ in, int in_dtype, const void* __restrict__ mul,
+                                                              int mul_dtype, void* __restrict__ out, int out_dtype, int64_t total4, int Ho,
+                                                              int Wo, int C) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int c4n = C >> 2;
+  const int c = (int)(i4 % c4n) * 4;
+  int64_t t = i4 / c4n;
+  const int x = (int)(t % Wo); t /= Wo;
+  const int y = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  const int W = 2 * Wo;
+  const int64_t b = ((n * 2 * Ho + 2 * y) * W + 2 * x) * C + c;
+  float a0[4], a1[4], a2[4], a3[4], o[4];
+  auto ld = [&](const void* base, int dt, int64_t off, float (&v)[4]) {
+    if (dt == GA_F32) ld4<float>(reinterpret_cast<const float*>(base) + off, v);
+    else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(base) + off, v);
+  };
+  ld(in, in_dtype, b, a0); ld(in, in_dtype, b + C, a1); ld(in, in_dtype, b + (int64_t)W * C, a2); ld(in, in_dtype, b + (int64_t)W * C + C, a3);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = (a0[j] + a1[j]) + (a2[j] + a3[j]);
+  const int64_t oi = i4 * 4;
+  if (mul != nullptr) {
+    float m[4];
+    ld(mul, mul_dtype, oi, m);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] *= m[j];
+  }
+  if (out_dtype == GA_F32) st4<float>(reinterpret_cast<float*>(out) + oi, o);
+  else st4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(out) + oi, o);
+}
+
 // depth-to-space x2: out[n][2a+pi][2b+pj][c] = in[n][a][b][(2 pi + pj) C + c].  The input gradient of a stride-2 convolution is computed
 // as ONE stride-1 tensor-core conv over grad_out that emits the four output phases as 4C channels (nvae_engine._build_dgrad); this kernel
 // interleaves them.  4 channels per thread: reads and writes are 16-byte vectors on contiguous channel runs.
@@ -378,6 +411,55 @@ __global__ void __launch_bounds__(256) latent_mix_bwd_kernel(const void* gz, int
   g_p[pix * 2 * Z + Z + zc] = g * a * e * temp * expf(softclamp5_(ls_p)) * sc5_grad(ls_p);
 }
 
+// 4 channels per thread (all channel counts multiples of 4): one Philox call per 4 channels instead of four, 16-byte accesses
+__global__ void __launch_bounds__(256) latent_mix_bwd_vec4_kernel(const void* gz, int gz_dtype, int Cz, const float* __restrict__ q, int Cq,
+                                                                  const float* __restrict__ pp, const float* __restrict__ eps,
+                                                                  SeedArg seed_arg, int level, int64_t sample0,
+                                                                  const float* __restrict__ alpha_dev, float temp, int Z, int N, int H,
+                                                                  int W, float* __restrict__ g_q, int Cgq, float* __restrict__ g_p) {
+  const uint64_t seed = seed_arg.get();
+  const int groups = Cgq >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * H * W * groups) return;
+  const int zc = (int)(idx % groups) * 4;
+  const int64_t pix = idx / groups;
+  float4* gq4 = reinterpret_cast<float4*>(g_q + pix * Cgq + zc);
+  if (zc >= Z) { *gq4 = make_float4(0.f, 0.f, 0.f, 0.f); return; }       // zero padding channels (tensor-core K padding)
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int64_t n = pix / ((int64_t)W * H);
+  const float a = *alpha_dev;
+  float g[4], mq[4];
+  if (gz_dtype == GA_F32) ld4<float>(reinterpret_cast<const float*>(gz) + pix * Cz + zc, g);
+  else ld4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(gz) + pix * Cz + zc, g);
+  ld4<float>(q + pix * Cq + zc, mq);
+  if (pp == nullptr) {
+    *gq4 = make_float4(g[0] * (1.f - a) * sc5_grad(mq[0]), g[1] * (1.f - a) * sc5_grad(mq[1]), g[2] * (1.f - a) * sc5_grad(mq[2]),
+                       g[3] * (1.f - a) * sc5_grad(mq[3]));
+    return;
+  }
+  float e[4];
+  if (eps != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = eps[n * Z * H * W + (((int64_t)(zc + j)) * H + y) * W + x];
+  } else {
+    latent_eps4(seed, (uint64_t)(sample0 + n) * 64ull + (uint64_t)(level + 1), zc >> 2, y * W + x, H * W, e);
+  }
+  float mp[4], lp[4], o_q[4], o_m[4], o_l[4];
+  ld4<float>(pp + pix * 2 * Z + zc, mp);
+  ld4<float>(pp + pix * 2 * Z + Z + zc, lp);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float d_enc = (1.f - a) * sc5_grad(mp[j] + mq[j]);
+    o_q[j] = g[j] * d_enc;
+    o_m[j] = g[j] * (d_enc + a * sc5_grad(mp[j]));
+    o_l[j] = g[j] * a * e[j] * temp * expf(softclamp5_(lp[j])) * sc5_grad(lp[j]);
+  }
+  *gq4 = make_float4(o_q[0], o_q[1], o_q[2], o_q[3]);
+  st4<float>(g_p + pix * 2 * Z + zc, o_m);
+  st4<float>(g_p + pix * 2 * Z + Z + zc, o_l);
+}
+
 // ---------------------------------------------------------------------------- DiscMixLogistic mean backward
 __global__ void __launch_bounds__(128) discmix_mean_bwd_kernel(const float* __restrict__ logits, int n_mix, int HW, int64_t total_pix,
                                                                const float* __restrict__ g_pur, const void* g_cls, int gc_dtype,
@@ -450,6 +532,91 @@ __global__ void __launch_bounds__(128) discmix_mean_bwd_kernel(const float* __re
   }
 }
 
+// same arithmetic, but the 100 logits of a pixel (400-byte rows) go through shared memory: the per-pixel kernel above issues 100 scalar
+// loads / 104 scalar stores whose 32 lanes hit 32 different lines (L1-wavefront bound: 1.9 ms at batch 512, 7x the HBM time)
+__global__ void __launch_bounds__(128) discmix_mean_bwd_smem_kernel(const float* __restrict__ logits, int n_mix, int HW, int64_t total_pix,
+                                                                    const float* __restrict__ g_pur, const void* g_cls, int gc_dtype,
+                                                                    float* __restrict__ g_logits, int Cg, int stride) {
+  extern __shared__ float s_row[];                       // [128][stride], stride odd >= Cg: conflict-free rows, updated in place
+  const int CL = 10 * n_mix;
+  const int64_t pix0 = (int64_t)blockIdx.x * 128;
+  const int npix = (int)min((int64_t)128, total_pix - pix0);
+  for (int i = threadIdx.x; i < npix * CL; i += 128) {
+    const int p = i / CL;
+    s_row[p * stride + (i - p * CL)] = __ldg(logits + pix0 * CL + i);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < npix) {
+    const int64_t pix = pix0 + threadIdx.x;
+    float* l = s_row + threadIdx.x * stride;             // reads logits, ends up holding d loss / d logits
+    for (int c = CL; c < Cg; ++c) l[c] = 0.f;
+    const int64_t n = pix / HW, hw = pix % HW;
+    float gv[3] = {0.f, 0.f, 0.f};
+    if (g_pur != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gv[c] += 0.5f * g_pur[(n * 3 + c) * HW + hw];
+    }
+    if (g_cls != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gv[c] += ld1b(g_cls, gc_dtype, pix * 3 + c);
+    }
+    float mx = l[0];
+    for (int m = 1; m < n_mix; ++m) mx = fmaxf(mx, l[m]);
+    float den = 0.f, mu[3] = {0.f, 0.f, 0.f}, kk[3] = {0.f, 0.f, 0.f};
+    for (int m = 0; m < n_mix; ++m) {
+      const float e = expf(l[m] - mx);
+      const float* qd = l + n_mix + 9 * m;
+      den += e;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { mu[c] = fmaf(e, qd[c], mu[c]); kk[c] = fmaf(e, tanhf(qd[6 + c]), kk[c]); }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { mu[c] *= inv; kk[c] *= inv; }
+    const float r_pre = mu[0];
+    const float r = fminf(fmaxf(r_pre, -1.f), 1.f);
+    const float g_pre = fmaf(kk[0], r, mu[1]);
+    const float g = fminf(fmaxf(g_pre, -1.f), 1.f);
+    const float b_pre = mu[2] + kk[1] * r + kk[2] * g;
+    const float gb = (b_pre >= -1.f && b_pre <= 1.f) ? gv[2] : 0.f;
+    float g_mu[3], g_k[3];
+    g_mu[2] = gb; g_k[1] = gb * r; g_k[2] = gb * g;
+    float gr_acc = gv[0] + gb * kk[1];
+    const float gg_acc = gv[1] + gb * kk[2];
+    const float gg = (g_pre >= -1.f && g_pre <= 1.f) ? gg_acc : 0.f;
+    g_mu[1] = gg; g_k[0] = gg * r;
+    gr_acc += gg * kk[0];
+    g_mu[0] = (r_pre >= -1.f && r_pre <= 1.f) ? gr_acc : 0.f;
+    float dot = 0.f;
+    for (int m = 0; m < n_mix; ++m) {
+      const float pi = expf(l[m] - mx) * inv;
+      float* qd = l + n_mix + 9 * m;
+      float gpi = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float q = qd[c], th = tanhf(qd[6 + c]);
+        gpi += q * g_mu[c] + th * g_k[c];
+        qd[c] = pi * g_mu[c];
+        qd[6 + c] = pi * (1.f - th * th) * g_k[c];
+      }
+      qd[3] = pi;                                          // stash (the log-scale slots end up zero)
+      qd[4] = 0.f; qd[5] = 0.f;
+      l[m] = gpi;                                          // temporarily d / d pi_m
+      dot = fmaf(pi, gpi, dot);
+    }
+    for (int m = 0; m < n_mix; ++m) {
+      float* qd = l + n_mix + 9 * m;
+      l[m] = qd[3] * (l[m] - dot);
+      qd[3] = 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npix * Cg; i += 128) {
+    const int p = i / Cg;
+    g_logits[pix0 * Cg + i] = s_row[p * stride + (i - p * Cg)];
+  }
+}
+
 static int pix_per_block_se(int HW) { return HW < 128 ? HW : 128; }
 
 }  // namespace ga
@@ -512,6 +679,13 @@ extern "C" int ga_sumpool2x2(const ga_tensor* in, const ga_tensor* mul, const ga
   GA_CHECK(!mul || same_shape(mul, out), "ga_sumpool2x2: mul shape mismatch");
   const int64_t total = numel(out);
   if (total == 0) return 0;
+  if ((out->c & 3) == 0 && ((((uintptr_t)in->data) | ((uintptr_t)out->data) | (mul ? (uintptr_t)mul->data : 0)) & 15) == 0) {
+    sumpool2x2_vec4_kernel<<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, mul ? mul->data : nullptr,
+                                                                                  mul ? mul->dtype : GA_F32, out->data, out->dtype, total / 4,
+                                                                                  out->h, out->w, out->c);
+    GA_LAUNCH_OK();
+    return 0;
+  }
   sumpool2x2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in->data, in->dtype, mul ? mul->data : nullptr,
                                                                         mul ? mul->dtype : GA_F32, out->data, out->dtype, out->n, out->h,
                                                                         out->w, out->c);
@@ -563,6 +737,15 @@ extern "C" int ga_latent_mix_bwd(const ga_tensor* g_z, const ga_tensor* q, const
   GA_CHECK(!p || (p->dtype == GA_F32 && g_p->dtype == GA_F32 && p->c == 2 * zdim && g_p->c == 2 * zdim), "ga_latent_mix_bwd: p / g_p must be fp32 with 2*zdim channels");
   const int64_t total = (int64_t)q->n * q->h * q->w * g_q->c;
   if (total == 0) return 0;
+  if ((zdim & 3) == 0 && (g_z->c & 3) == 0 && (q->c & 3) == 0 && (g_q->c & 3) == 0 &&
+      ((((uintptr_t)g_z->data) | ((uintptr_t)q->data) | ((uintptr_t)g_q->data) | (p ? (uintptr_t)p->data : 0) | (g_p ? (uintptr_t)g_p->data : 0)) & 15) == 0) {
+    const int64_t total4 = (int64_t)q->n * q->h * q->w * (g_q->c / 4);
+    latent_mix_bwd_vec4_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, make_seed(seed), level, sample0,
+        alpha_dev, temperature, zdim, q->n, q->h, q->w, (float*)g_q->data, g_q->c, g_p ? (float*)g_p->data : nullptr);
+    GA_LAUNCH_OK();
+    return 0;
+  }
   latent_mix_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
       g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, make_seed(seed), level, sample0,
       alpha_dev, temperature, zdim, q->n, q->h, q->w, (float*)g_q->data, g_q->c, g_p ? (float*)g_p->data : nullptr);
@@ -579,6 +762,22 @@ extern "C" int ga_discmix_mean_bwd(const ga_tensor* logits, int n_mix, const flo
   GA_CHECK(g_purified_nchw || g_cls, "ga_discmix_mean_bwd: no incoming gradient");
   const int64_t total_pix = (int64_t)logits->n * logits->h * logits->w;
   if (total_pix == 0) return 0;
+  {
+    const int stride = g_logits->c | 1;
+    const int smem = 128 * stride * (int)sizeof(float);
+    static int configured = 0;
+    if (smem <= 200 * 1024) {
+      if (configured < smem) {
+        GA_CUDA(cudaFuncSetAttribute(discmix_mean_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+      }
+      discmix_mean_bwd_smem_kernel<<<cdiv(total_pix, 128), 128, smem, (cudaStream_t)stream>>>(
+          (const float*)logits->data, n_mix, logits->h * logits->w, total_pix, g_purified_nchw, g_cls ? g_cls->data : nullptr,
+          g_cls ? g_cls->dtype : GA_F32, (float*)g_logits->data, g_logits->c, stride);
+      GA_LAUNCH_OK();
+      return 0;
+    }
+  }
   discmix_mean_bwd_kernel<<<cdiv(total_pix, 128), 128, 0, (cudaStream_t)stream>>>(
       (const float*)logits->data, n_mix, logits->h * logits->w, total_pix, g_purified_nchw, g_cls ? g_cls->data : nullptr,
       g_cls ? g_cls->dtype : GA_F32, (float*)g_logits->data, g_logits->c);

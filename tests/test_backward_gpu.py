@@ -52,6 +52,12 @@ def test_resampling_backward_kernels():
     m = torch.randn(2, 8, 8, 8, generator=g)
     assert (ops.sumpool2x2(x.to(DEV), torch.float32, mul=m.to(DEV)).cpu() - emu_ops.sumpool2x2(x, torch.float32, mul=m)).abs().max().item() <= 1e-5
     assert (ops.upsample_bilinear2x_bwd(x.to(DEV), torch.float32).cpu() - emu_ops.upsample_bilinear2x_bwd(x, torch.float32)).abs().max().item() <= 1e-5
+    xb, mb = torch.randn(3, 12, 20, 24, generator=g).bfloat16(), torch.randn(3, 6, 10, 24, generator=g).bfloat16()      # attack-path dtypes
+    refb = emu_ops.sumpool2x2(xb.float(), torch.float32, mul=mb.float())
+    gotb = ops.sumpool2x2(xb.to(DEV), torch.bfloat16, mul=mb.to(DEV))
+    assert (gotb.float().cpu() - refb).abs().max().item() <= 2e-2 * max(1.0, refb.abs().max().item())
+    x3 = torch.randn(2, 4, 4, 6, generator=g)                                                                          # C % 4 != 0: scalar kernel
+    assert (ops.sumpool2x2(x3.to(DEV), torch.float32).cpu() - emu_ops.sumpool2x2(x3, torch.float32)).abs().max().item() <= 1e-5
     xin = torch.randn(2, 16, 16, 8, generator=g)
     go = torch.randn(2, 8, 8, 8, generator=g)
     for relu in (False, True):
@@ -128,6 +134,12 @@ def test_latent_mix_and_discmix_backward():
     ref = emu_ops.discmix_mean_bwd(logits, 10, gp_, gc_)
     got = ops.discmix_mean_bwd(logits.to(DEV), 10, gp_.to(DEV), gc_.to(DEV))
     assert (got.cpu() - ref).abs().max().item() <= 1e-5
+    # ragged pixel count (not a multiple of the 128-pixel block) + channel padding for the dgrad conv + one gradient source only
+    logits = torch.randn(3, 7, 9, 100, generator=g) * 1.5
+    gc_ = torch.randn(3, 7, 9, 3, generator=g)
+    ref = emu_ops.discmix_mean_bwd(logits, 10, None, gc_)
+    got = ops.discmix_mean_bwd(logits.to(DEV), 10, None, gc_.to(DEV), pad_to=104)
+    assert got.shape == (3, 7, 9, 104) and (got[..., :100].cpu() - ref).abs().max().item() <= 1e-5 and got[..., 100:].abs().max().item() == 0
 
 
 @pytest.mark.parametrize("blur,eps", [(True, 1.0), (False, 2.0)])
