@@ -433,7 +433,7 @@ def main():
     ap.add_argument("--pgd-steps", type=int, default=50)
     ap.add_argument("--cuda-graph", type=int, default=-1, help="1: replay the call / PGD iteration as a CUDA graph; 0: eager; default: pgd only "
                     "(the purify roofline needs per-launch events, which only exist in eager mode)")
-    ap.add_argument("--ref-batch", type=int, default=8, help="bounded sample per step of the CPU reference arm")
+    ap.add_argument("--ref-batch", type=int, default=16, help="bounded sample per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="CUDA-event time of EVERY op (written to stderr as a table)")
     args = ap.parse_args()
