@@ -135,3 +135,21 @@ def test_stride2_dgrad_phase_weights_match_autograd(k, pad):
     got = emu_ops.depth_to_space2(o4.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
     assert got.shape == ref.shape
     assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_alpha_schedules_match_reference_formulas():
+    """alpha_learning/common_utils.py:15-22 (the reference module itself does not import here: botorch / data deps)"""
+    import math
+    from gen_adversarial_b200.alpha_schedules import get_cosine_alphas, get_linear_alphas
+    for n in (16, 18, 24):
+        assert get_linear_alphas(n) == [i / n for i in range(1, n + 1)]
+        assert get_cosine_alphas(n) == [0.5 * (1 - math.cos(math.pi * (i / n))) for i in range(1, n + 1)]
+        assert get_linear_alphas(n)[-1] == 1.0 and abs(get_cosine_alphas(n)[-1] - 1.0) < 1e-15
+
+
+def test_ablation_models_refuse_cpu_tensors():
+    from gen_adversarial_b200.defenses.ablations.models import GaussianBlurDefenseModel, GaussianNoiseDefenseModel
+    x = torch.rand(2, 3, 64, 64)
+    for m in (GaussianBlurDefenseModel(torch.nn.Identity()), GaussianNoiseDefenseModel(torch.nn.Identity(), eps=0.5)):
+        with pytest.raises(RuntimeError):
+            m(x)
