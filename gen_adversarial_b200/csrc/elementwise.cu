@@ -209,6 +209,11 @@ __global__ void __launch_bounds__(256) preprocess_blur_fast_kernel(
   float tp[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) tp[t] = __ldg(taps + t);
+  // reflect-border source offsets of the staged rows / columns, computed once per CTA (the staging loop is then 2 LDS + 1 LDG per element)
+  __shared__ int s_gy[EXT], s_gx[EXT];
+  static_assert(EXT <= 64, "index tables are filled by threads 0..EXT-1 and 64..64+EXT-1");
+  if (tid < EXT) s_gy[tid] = min(max(reflect_idx(ty0 + tid - RT, H), 0), H - 1) * W;       // tiles hanging over the edge: clamped, masked later
+  else if (tid >= 64 && tid < 64 + EXT) s_gx[tid - 64] = min(max(reflect_idx(tx0 + tid - 64 - RT, W), 0), W - 1);
   float scale = 0.f;
   if (eps != 0.f) {
     float ss = 0.f;
@@ -223,9 +228,7 @@ __global__ void __launch_bounds__(256) preprocess_blur_fast_kernel(
     __syncthreads();
     for (int i = tid; i < EXT * EXT; i += 256) {
       const int yy = i / EXT, xx = i - yy * EXT;
-      int gy = reflect_idx(ty0 + yy - RT, H), gx = reflect_idx(tx0 + xx - RT, W);
-      gy = min(max(gy, 0), H - 1); gx = min(max(gx, 0), W - 1);              // tiles hanging over the edge: clamped, masked later
-      s_in[yy][xx] = __ldg(xp + (int64_t)gy * W + gx);
+      s_in[yy][xx] = __ldg(xp + s_gy[yy] + s_gx[xx]);
     }
     __syncthreads();
     // horizontal pass: one item = 4 consecutive outputs of one staged row (window of 4 + 2 RT inputs, 16-byte loads)
