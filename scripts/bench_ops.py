@@ -99,6 +99,56 @@ def k1():
               f"project {t_pr:6.1f} us ({(small + big) / t_pr / 1e3:5.0f} GB/s)  k3 {t_k3:6.1f} us ({2.0 * m * c * 9 * c / t_k3 / 1e6:5.0f} TFLOP/s)")
 
 
+def hbm():
+    """the HBM-bound fused elementwise / stencil kernels (north-star item 3) at the BASELINE batch and at a saturating batch:
+    achieved GB/s on the ALGORITHMIC bytes of SURVEY 8d against the measured copy peak"""
+    import json, os
+    peak = 6542.1
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    g = torch.Generator(device=DEV).manual_seed(0)
+
+    def report(name, us, nbytes):
+        gbs = nbytes / us / 1e3
+        print(f"{name:58s} {us:8.1f} us  {nbytes / 1e6:8.1f} MB  {gbs:7.0f} GB/s  {100 * gbs / peak:5.1f}% of {peak:.0f}")
+
+    for n in (512, 4096):
+        x = torch.rand(n, 3, 64, 64, device=DEV, generator=g)
+        by = 2 * x.numel() * 4
+        report(f"preprocess blur (R=7) batch {n}", timeit(lambda: ops.preprocess(x, None, 0.0, True, torch.bfloat16)), x.numel() * 4 + x.numel() * 2)
+        report(f"preprocess Philox noise batch {n}", timeit(lambda: ops.preprocess(x, None, 1.0, False, torch.bfloat16, seed=3)), x.numel() * 4 + x.numel() * 2)
+        adv, gr = x.clone(), torch.randn(x.shape, device=DEV, generator=g)
+        report(f"pgd_linf_step batch {n}", timeit(lambda: ops.pgd_linf_step_(adv, gr, x, 2 / 255, 8 / 255)), 4 * x.numel() * 4)
+        del adv, gr
+    alpha = torch.tensor([0.5], device=DEV)
+    for n in (512, 2048):
+        for hw in (32, 16, 8):
+            q = torch.randn(n, hw, hw, 24, device=DEV, generator=g)
+            pp = torch.randn(n, hw, hw, 40, device=DEV, generator=g)
+            t = timeit(lambda: ops.latent_mix(q, pp, None, 5, 3, 0, alpha, 0.6, 20, 24, torch.bfloat16))
+            report(f"latent_mix (Philox eps) n={n} hw={hw}", t, n * hw * hw * (20 * 4 + 40 * 4 + 20 * 2))
+        logits = torch.randn(n, 64, 64, 100, device=DEV, generator=g)
+        t = timeit(lambda: ops.discmix_mean(logits, 10, torch.bfloat16))
+        report(f"discmix_mean n={n} (100 fp32 logits -> NCHW fp32 + NHWC bf16)", t, n * 4096 * (100 * 4 + 3 * 4 + 3 * 2))
+        del logits
+    for (n, hw, c) in [(512, 32, 64), (512, 16, 128), (512, 8, 256), (2048, 32, 64)]:
+        r = torch.randn(n, hw, hw, c, device=DEV, generator=g).bfloat16()
+        skip = torch.randn(n, hw, hw, c, device=DEV, generator=g)
+        hid = max(c // 16, 4)
+        se = (torch.randn(hid, c, device=DEV, generator=g) * 0.3, torch.randn(hid, device=DEV, generator=g) * 0.1,
+              torch.randn(c, hid, device=DEV, generator=g) * 0.3, torch.randn(c, device=DEV, generator=g) * 0.1)
+        sums = ops.channel_sum(r)
+        e = r.numel()
+        report(f"channel_sum n={n} hw={hw} c={c}", timeit(lambda: ops.channel_sum(r)), e * 2)
+        report(f"se_residual (fp32 stream + bf16 copy) n={n} hw={hw} c={c}",
+               timeit(lambda: ops.se_residual(r, sums, se, 0.1, skip, torch.float32, want_out2=True)), e * (2 + 4 + 4 + 2))
+        go = torch.randn(n, hw, hw, c, device=DEV, generator=g)
+        report(f"se_residual_bwd n={n} hw={hw} c={c}", timeit(lambda: ops.se_residual_bwd(go, r, sums, se, 0.1, torch.bfloat16)), e * (2 * (4 + 2) + 2))
+        del r, skip, go
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dwconv"]
     if "dwconv" in which:
@@ -107,3 +157,5 @@ if __name__ == "__main__":
         mbconv()
     if "k1" in which:
         k1()
+    if "hbm" in which:
+        hbm()
