@@ -445,8 +445,8 @@ __global__ void __launch_bounds__(256) se_residual_kernel(SeParams p) {
         float a[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float t = fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]);
-          a[j] = p.act_op == GA_ACT_SILU ? silu_fast(t) : t;
+          const float t = p.act_scale != nullptr ? fmaf(o[j], p.act_scale[c + j], p.act_shift[c + j]) : o[j];
+          a[j] = p.act_op == GA_ACT_SILU ? silu_fast(t) : (p.act_op == GA_ACT_ELU ? (t > 0.f ? t : __expf(t) - 1.0f) : t);
           if (p.act_rtf) a[j] = round_tf32(a[j]);
         }
         st4d(p.act, p.act_dtype, off, a);
@@ -947,10 +947,11 @@ extern "C" int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const f
                                   const ga_tensor* out2, const ga_tensor* act, const float* act_scale, const float* act_shift,
                                   int act_op, float* gate_out, void* stream) {
   GA_CHECK(r && sums && w1 && w2 && skip && out, "ga_se_residual_fwd: null argument");
-  GA_CHECK(act_op == GA_ACT_SILU || act_op == GA_ACT_NONE, "ga_se_residual_fwd: act_op must be SILU or NONE");
+  GA_CHECK(act_op == GA_ACT_SILU || act_op == GA_ACT_NONE || act_op == GA_ACT_ELU, "ga_se_residual_fwd: act_op must be SILU, ELU or NONE");
   GA_CHECK(same_shape(r, skip) && same_shape(r, out), "ga_se_residual_fwd: shape mismatch");
   GA_CHECK((r->c % 4) == 0, "ga_se_residual_fwd: channels must be a multiple of 4");
-  GA_CHECK(!act || (act_scale && act_shift && same_shape(r, act)), "ga_se_residual_fwd: act output needs scale/shift");
+  GA_CHECK(!act || same_shape(r, act), "ga_se_residual_fwd: act output shape mismatch");
+  GA_CHECK((act_scale == nullptr) == (act_shift == nullptr), "ga_se_residual_fwd: act_scale and act_shift go together");
   GA_CHECK(!out2 || same_shape(r, out2), "ga_se_residual_fwd: out2 shape mismatch");
   if (numel(r) == 0) return 0;
   SeParams p;

@@ -216,6 +216,13 @@ class NvaeEngine:
                 of, dact = of
         return (ob, of, dact) if want_dact else (ob, of)
 
+    def _conv_preact(self, x32, x_pre, L: ops.ConvLayer):
+        """fp32 output of a layer with an ELU pre-op: from the pre-activated bf16 copy `x_pre` when one exists and the tensor-core kernel
+        takes the shape, else the generic path (which materialises ELU(x32) itself)"""
+        if x_pre is not None and L.w_tc is not None and L.pre_op == PRE_ELU and ops.conv2d_tc_supported(x_pre, L):
+            return ops.conv2d_tc(x_pre, L, want_bf16=False, want_f32=True)[1]
+        return self._conv(x32, L, want_act=False, want_f32=True)[1]
+
     def _dgrad(self, g, L: ops.ConvLayer, add=None, mul=None, mul_mode=0, f32=True):
         """input-gradient of the forward conv whose dgrad layer is L: -> fp32 (stream gradients) or activation dtype."""
         if not self.bf16:
@@ -266,13 +273,18 @@ class NvaeEngine:
             t = g_out
         return ops.affine_act_bwd(g_a, x32, e.pre_affine[0], e.pre_affine[1], ACT_SILU, torch.float32, add=t)
 
-    def _dec_cell(self, x32, xa, d: _Dec, rec):
-        """x32: fp32 residual stream; xa: same values in the activation dtype (GEMM operand)."""
+    def _dec_cell(self, x32, xa, d: _Dec, rec, want_elu: bool = False):
+        """x32: fp32 residual stream; xa: same values in the activation dtype (GEMM operand).
+        want_elu (bf16 mode): the SE kernel also writes ELU(out) in bf16 -- the pre-activated input of the decoder sampler / logits head that
+        follows this cell (NVAE/model.py:226-231,310-313) -- and it is left in `self._elu_copy` (saves a pass over the fp32 stream)."""
         taping = rec is not None
+        elu = bool(want_elu and self.bf16)
+        self._elu_copy = None
         if not taping and self.fuse_cells and self.bf16 and not d.up and d.dw_wc is not None and ops.mbconv_fused_supported(xa, d.e, d.p):
             r = ops.mbconv_fused(xa, d.e, d.dw_wc, d.dw_b, d.p)     # expand -> dw5x5 -> project in one kernel, hidden tensor on chip
             sums = ops.channel_sum(r)
-            out, out2, _, _ = ops.se_residual(r, sums, d.se, 0.1, x32, torch.float32, want_out2=True)
+            out, out2, self._elu_copy, _ = ops.se_residual(r, sums, d.se, 0.1, x32, torch.float32, want_out2=True, act_plain=elu,
+                                                           act_op=ACT_ELU if elu else ACT_SILU)
             return out, out2
         if taping:
             h1, _, dact_e = self._conv(xa, d.e, want_dact=True)
@@ -287,7 +299,8 @@ class NvaeEngine:
         else:
             skip = x32
         sums = ops.channel_sum(r)
-        out, out2, _, _ = ops.se_residual(r, sums, d.se, 0.1, skip, torch.float32, want_out2=self.bf16)
+        out, out2, self._elu_copy, _ = ops.se_residual(r, sums, d.se, 0.1, skip, torch.float32, want_out2=self.bf16, act_plain=elu,
+                                                       act_op=ACT_ELU if elu else ACT_SILU)
         if taping:
             rec.append(("dec", d, dact_e, dact_dw, r, sums))
         return out, (out2 if self.bf16 else out)
@@ -372,11 +385,13 @@ class NvaeEngine:
             for L in self.levels:
                 if L["s"] != s or (L["s"] == 0 and L["g"] == 0):
                     continue
-                for d in L["cells"]:
-                    x32, xa = self._dec_cell(x32, xa, d, rec)
+                x_elu = None
+                for ci, d in enumerate(L["cells"]):
+                    x32, xa = self._dec_cell(x32, xa, d, rec, want_elu=ci == len(L["cells"]) - 1)
+                    x_elu = self._elu_copy
                 comb, _ = self._conv(xa, L["enc_comb"], add=stash[(L["s"], L["g"])])
                 _, muq = self._conv(comb, L["enc_sampler"], want_act=False, want_f32=True)
-                _, pp = self._conv(x32, L["dec_sampler"], want_act=False, want_f32=True)
+                pp = self._conv_preact(x32, x_elu, L["dec_sampler"])
                 eps = eps_levels[idx] if eps_levels is not None else None
                 z = ops.latent_mix(muq, pp, eps, seed, idx, sample0, alphas_dev[idx:idx + 1], self.temperature, spec.z, self.zc,
                                    self.adt)
@@ -388,10 +403,12 @@ class NvaeEngine:
             if s in self.up_cells:
                 x32, xa = self._dec_cell(x32, xa, self.up_cells[s], rec)
         self._tap("dec_out", x32)
-        for d in self.post_cells:
-            x32, xa = self._dec_cell(x32, xa, d, rec)
+        x_elu = None
+        for ci, d in enumerate(self.post_cells):
+            x32, xa = self._dec_cell(x32, xa, d, rec, want_elu=ci == len(self.post_cells) - 1)
+            x_elu = self._elu_copy
         self._tap("post", x32)
-        _, logits = self._conv(x32, self.to_logits, want_act=False, want_f32=True)
+        logits = self._conv_preact(x32, x_elu, self.to_logits)
         self._tap("logits", logits)
         if rec is not None:
             rec.append(("head", x32, logits))

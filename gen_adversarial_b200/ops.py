@@ -246,13 +246,14 @@ def channel_sum(r: torch.Tensor) -> torch.Tensor:
 
 
 def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
-                act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op: int = ACT_SILU):
+                act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op: int = ACT_SILU, act_plain: bool = False):
     """se = (w1, b1, w2, b2) fp32 device tensors (biases may be None).  -> (out, out2|None, act|None, gate|None);
-    act = act_op(act_scale * out + act_shift), act_op SiLU (NVAE cells) or none (IR-SE50 BatchNorm)"""
+    act = act_op(act_scale * out + act_shift), act_op SiLU (NVAE cells) or none (IR-SE50 BatchNorm); act_plain: act = act_op(out)
+    without an affine (ELU copy for the decoder sampler / logits head)"""
     w1, b1, w2, b2 = se
     out = torch.empty(r.shape, device=r.device, dtype=out_dtype)
     out2 = torch.empty(r.shape, device=r.device, dtype=out2_dtype) if want_out2 else None
-    act = torch.empty(r.shape, device=r.device, dtype=act_dtype) if act_affine is not None else None
+    act = torch.empty(r.shape, device=r.device, dtype=act_dtype) if (act_affine is not None or act_plain) else None
     gate = torch.empty((r.shape[0], r.shape[3]), device=r.device, dtype=torch.float32) if want_gate else None
     a_s, a_b = act_affine if act_affine is not None else (None, None)
     e0 = TIMER.start() if TIMER is not None else None

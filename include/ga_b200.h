@@ -132,7 +132,8 @@ int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, cons
 int ga_channel_sum_parts(int n, int hw);
 int ga_channel_sum(const ga_tensor* r, float* sums, void* stream);
 /* gate = sigmoid(W2 relu(W1 mean + b1) + b2);  out = skip + res_scale * gate * r;
- * optional extra outputs: out_bf16 copy, act = SiLU(act_scale*out + act_shift) (next cell's BN+SiLU). */
+ * optional extra outputs: out_bf16 copy, act = act_op(act_scale*out + act_shift) -- the next cell's BN+SiLU, or (scale/shift NULL,
+ * act_op ELU) the pre-activated input of the decoder sampler / logits head (NVAE/model.py:226-231,310-313). */
 int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const float* w1, const float* b1, const float* w2,
                        const float* b2, int hidden, float res_scale, const ga_tensor* skip,
                        const ga_tensor* out, const ga_tensor* out2 /*nullable*/, const ga_tensor* act /*nullable*/,

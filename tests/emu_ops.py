@@ -202,7 +202,7 @@ def mbconv_fused(x, e, dw_w_chunked, dw_b, p):
 
 
 def se_residual(r, sums, se, res_scale, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
-                act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op=ACT_SILU):
+                act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op=ACT_SILU, act_plain=False):
     _launches[0] += 1
     w1, b1, w2, b2 = se
     mean = sums.sum(dim=1) / (r.shape[1] * r.shape[2])
@@ -210,9 +210,9 @@ def se_residual(r, sums, se, res_scale, skip, out_dtype=torch.float32, want_out2
     out = skip.float() + res_scale * gate[:, None, None, :] * r.float()
     out2 = out.to(out2_dtype) if want_out2 else None
     act = None
-    if act_affine is not None:
-        act = out * act_affine[0] + act_affine[1]
-        act = (F.silu(act) if act_op == ACT_SILU else act).to(act_dtype)
+    if act_affine is not None or act_plain:
+        act = out * act_affine[0] + act_affine[1] if act_affine is not None else out
+        act = (F.silu(act) if act_op == ACT_SILU else (F.elu(act) if act_op == ACT_ELU else act)).to(act_dtype)
     return out.to(out_dtype), out2, act, (gate if want_gate else None)
 
 
