@@ -229,6 +229,13 @@ def test_channel_sum_and_se_residual(c, hw):
     assert (got[1].float().cpu() - ref[0]).abs().max().item() <= 3e-2
     assert (got[2].float().cpu() - ref[2].float()).abs().max().item() <= 3e-2
     assert (got[3].cpu() - ref[3]).abs().max().item() <= 1e-5
+    # ELU copy without an affine (pre-activated input of the decoder sampler / logits head)
+    from gen_adversarial_b200._lib import ACT_ELU as _ELU
+    ref_e = emu_ops.se_residual(r, sums_ref, se, 0.1, skip, torch.float32, want_out2=True, act_plain=True, act_op=_ELU)
+    got_e = ops.se_residual(r.to(DEV), sums, tuple(t.to(DEV) for t in se), 0.1, skip.to(DEV), torch.float32, want_out2=True,
+                            act_plain=True, act_op=_ELU)
+    assert (got_e[0].cpu() - ref_e[0]).abs().max().item() <= 1e-5
+    assert got_e[2].dtype == torch.bfloat16 and (got_e[2].float().cpu() - ref_e[2].float()).abs().max().item() <= 3e-2
 
 
 def test_latent_mix_explicit_noise():
