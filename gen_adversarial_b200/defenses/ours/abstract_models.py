@@ -183,7 +183,11 @@ class MLVGMDefenseModel(ABC):
         :return if preds only: un-normalized predictions (B, N_CLASSES) computed on the purified images,
                 else: (predictions, purified images (B, C, H, W))
         """
-        if batch.requires_grad and torch.is_grad_enabled():
+        if batch.shape[0] == 0:
+            # empty batch: the reference's torch modules return empty tensors; the kernels are never launched on zero-sized buffers
+            preds = torch.zeros((0, self.classifier.classifier.n_classes), device=batch.device, dtype=torch.float32)
+            purified = torch.zeros((0,) + tuple(batch.shape[1:]), device=batch.device, dtype=torch.float32)
+        elif batch.requires_grad and torch.is_grad_enabled():
             from ...autograd import defense_apply
             preds, purified = defense_apply(self, batch)
         elif self.use_cuda_graph and self._explicit_noise is None and batch.is_cuda:
