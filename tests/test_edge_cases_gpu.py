@@ -65,3 +65,22 @@ def test_eot_wrapper_reference_semantics(dm):
             assert (batched[:1] - single).abs().max().item() <= 1e-3 * max(1.0, single.abs().max().item())
     finally:
         dm.interpolation_alphas, dm.eps, dm.blur_input = alphas, eps, blur
+
+
+@pytest.mark.parametrize("kind,res", [("trans", 128), ("e4e", 256)])
+def test_stylegan_defenses_batch_composition_independence(kind, res):
+    """configs 3 / 4 (bf16 product mode, Philox noise): a sample's purified image does not depend on the batch it sits in -- batch 1 and an
+    odd batch against the same samples inside a batch of 4 (generator batch slicing, tensor-core tiles spanning images at low resolution)"""
+    from tests.test_stylegan_paths_gpu import _defense
+    m = _defense(kind, "bf16")
+    m.interpolation_alphas = [0.3] * len(m.interpolation_alphas)
+    m.eps, m.blur_input, m.noise_seed = 1.0, kind == "trans", 23
+    x = torch.rand(4, 3, res, res, generator=torch.Generator().manual_seed(9)).to(DEV)
+    with torch.no_grad():
+        _, full = m(x, preds_only=False)
+        for b in (1, 3):
+            _, part = m(x[:b].contiguous(), preds_only=False)
+            assert part.shape == (b, 3, res, res)
+            assert (part - full[:b]).abs().max().item() <= 1e-5, (kind, b)
+        empty_logits, empty = m(x[:0], preds_only=False)
+        assert empty.shape == (0, 3, res, res) and empty_logits.shape[0] == 0
