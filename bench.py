@@ -193,7 +193,7 @@ def run_ours(args):
 
     mode = args.mode
     sg = args.workload in ("gender", "cars")
-    B = args.batch if args.batch is not None else {"purify": 512, "pgd": 512, "gender": 128, "cars": 256}[args.workload]
+    B = args.batch if args.batch is not None else {"purify": 512, "pgd": 1024, "gender": 128, "cars": 256}[args.workload]
     if sg:
         # BASELINE configs[2] / [3]: StyleGAN-E4E @1024 + ResNet-50 (ours_linear_noise_gender.yaml) and
         # Style-Transformer @512 + ResNeXt-50 (ours_cosine_blur_cars.yaml); YAML values verbatim
@@ -403,7 +403,7 @@ def run_ours(args):
                 "tflops_algorithmic": value * gflop / 1e3,
                 "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                         "d2h_bytes_per_step": (B if pgd else logits_host.numel() * 4) * world},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_other_kernels": extra, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2), "clocks": clocks, "roofline": roof, "roofline_other_kernels": extra, "cpu_baseline": cpu,
                 "counters": {"n_total": int(counters[0].item()), "n_clean_correct": int(counters[1].item()),
                              "n_robust_correct": int(counters[2].item())}}
         print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
@@ -427,7 +427,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 512 purify / 512 pgd)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 512 purify / 1024 pgd: 95 GB of tape + activations)")
     ap.add_argument("--workload", default="purify", choices=["purify", "pgd", "gender", "cars"])
     ap.add_argument("--chunk", type=int, default=0, help="generator batch chunk of the StyleGAN workloads (0: automatic)")
     ap.add_argument("--pgd-steps", type=int, default=50)
