@@ -82,3 +82,32 @@ class _ClassifierFn(torch.autograd.Function):
 def classifier_apply(wrapper, batch: torch.Tensor):
     """differentiable `BaseClassificationModel.__call__`"""
     return _ClassifierFn.apply(batch, wrapper)
+
+
+class _PreprocessFn(torch.autograd.Function):
+    """blur / L2-normalised noise / clamp used ALONE (ablation defenses, `add_gaussian_noise`, `apply_gaussian_blur`), differentiable
+    w.r.t. the batch like the reference's torch/kornia code (src/defenses/ablations/models.py:21-60, abstract_models.py:129-159):
+    the noise is a constant, so the input gradient is the clamp mask followed by the transposed (= same symmetric, reflect-scatter) blur."""
+
+    @staticmethod
+    def forward(ctx, x, noise, eps, blur, seed, sample0, taps_cache):
+        out, pre = ops.preprocess(x.detach().to(torch.float32), noise, float(eps), bool(blur), torch.float32, seed=seed, sample0=sample0,
+                                  normalize=False, save_pre=True, taps_cache=taps_cache)
+        ctx.pre, ctx.blur, ctx.taps_cache = pre, bool(blur), taps_cache
+        return out.permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g_nhwc = g.to(torch.float32).permute(0, 2, 3, 1).contiguous()
+        gx = ops.preprocess_bwd(g_nhwc, ctx.pre, ctx.blur, normalize=False, taps_cache=ctx.taps_cache)
+        return gx, None, None, None, None, None, None
+
+
+def preprocess_apply(x: torch.Tensor, noise, eps: float, blur: bool, seed: int, sample0: int, taps_cache=None) -> torch.Tensor:
+    """(B,C,H,W) in [0,1] -> blurred / noised / clamped (B,C,H,W) fp32; differentiable w.r.t. x when x requires grad"""
+    if x.requires_grad and torch.is_grad_enabled():
+        return _PreprocessFn.apply(x, noise, eps, blur, seed, sample0, taps_cache)
+    out, _ = ops.preprocess(x.detach().to(torch.float32), noise, float(eps), bool(blur), torch.float32, seed=seed, sample0=sample0,
+                            normalize=False, taps_cache=taps_cache)
+    return out.permute(0, 3, 1, 2).contiguous()

@@ -741,13 +741,13 @@ extern "C" int ga_latent_mix_bwd(const ga_tensor* g_z, const ga_tensor* q, const
       ((((uintptr_t)g_z->data) | ((uintptr_t)q->data) | ((uintptr_t)g_q->data) | (p ? (uintptr_t)p->data : 0) | (g_p ? (uintptr_t)g_p->data : 0)) & 15) == 0) {
     const int64_t total4 = (int64_t)q->n * q->h * q->w * (g_q->c / 4);
     latent_mix_bwd_vec4_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-        g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, make_seed(seed), level, sample0,
+        g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, make_seed(seed, (cudaStream_t)stream), level, sample0,
         alpha_dev, temperature, zdim, q->n, q->h, q->w, (float*)g_q->data, g_q->c, g_p ? (float*)g_p->data : nullptr);
     GA_LAUNCH_OK();
     return 0;
   }
   latent_mix_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, make_seed(seed), level, sample0,
+      g_z->data, g_z->dtype, g_z->c, (const float*)q->data, q->c, p ? (const float*)p->data : nullptr, eps, make_seed(seed, (cudaStream_t)stream), level, sample0,
       alpha_dev, temperature, zdim, q->n, q->h, q->w, (float*)g_q->data, g_q->c, g_p ? (float*)g_p->data : nullptr);
   GA_LAUNCH_OK();
   return 0;

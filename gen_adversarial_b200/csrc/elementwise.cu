@@ -845,7 +845,7 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits, const int6
     }
   }
   if (lane == 0) {
-    if (loss != nullptr && y >= 0) loss[warp] = logf(den) + mx - l[y];
+    if (loss != nullptr) loss[warp] = (y >= 0 && y < classes) ? logf(den) + mx - l[y] : 0.f;   // out-of-range label: no read past the row
     if (pred != nullptr) pred[warp] = arg;
     if (n_correct != nullptr && y >= 0 && arg == (int)y) atomicAdd(n_correct, 1ull);
   }
@@ -870,7 +870,7 @@ extern "C" int ga_noise_sumsq(const float* noise, int n, int chw, float* sumsq, 
 extern "C" int ga_noise_sumsq_philox(uint64_t seed, int64_t sample0, int n, int chw, float* sumsq, void* stream) {
   GA_CHECK(sumsq && n >= 0 && chw > 0, "ga_noise_sumsq_philox: bad arguments");
   if (n == 0) return 0;
-  noise_sumsq_philox_kernel<<<dim3(ga_noise_sumsq_parts(chw), n), 256, 0, (cudaStream_t)stream>>>(make_seed(seed), sample0, chw, sumsq);
+  noise_sumsq_philox_kernel<<<dim3(ga_noise_sumsq_parts(chw), n), 256, 0, (cudaStream_t)stream>>>(make_seed(seed, (cudaStream_t)stream), sample0, chw, sumsq);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -889,16 +889,16 @@ extern "C" int ga_preprocess_fwd(const float* x, const float* noise, const float
   dim3 grid(tiles, 1, out->n);
   cudaStream_t s = (cudaStream_t)stream;
   if (taps != nullptr && radius == 7)
-    preprocess_blur_fast_kernel<7><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed), nparts, sample0, eps, taps, normalize, out->c, out->h,
+    preprocess_blur_fast_kernel<7><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed, (cudaStream_t)stream), nparts, sample0, eps, taps, normalize, out->c, out->h,
                                                        out->w, out->data, out->dtype, pre);
   else if (taps != nullptr && radius == 12)
-    preprocess_blur_fast_kernel<12><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed), nparts, sample0, eps, taps, normalize, out->c, out->h,
+    preprocess_blur_fast_kernel<12><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed, (cudaStream_t)stream), nparts, sample0, eps, taps, normalize, out->c, out->h,
                                                         out->w, out->data, out->dtype, pre);
   else if (taps != nullptr)
-    preprocess_fwd_kernel<true><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed), nparts, sample0, eps, taps, radius, normalize, out->c,
+    preprocess_fwd_kernel<true><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed, (cudaStream_t)stream), nparts, sample0, eps, taps, radius, normalize, out->c,
                                                     out->h, out->w, out->data, out->dtype, pre);
   else
-    preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed), nparts, sample0, eps, nullptr, 0, normalize, out->c,
+    preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed, (cudaStream_t)stream), nparts, sample0, eps, nullptr, 0, normalize, out->c,
                                                      out->h, out->w, out->data, out->dtype, pre);
   GA_LAUNCH_OK();
   return 0;
@@ -983,13 +983,13 @@ extern "C" int ga_latent_mix_fwd(const ga_tensor* q, const ga_tensor* p, const f
   if (total_pix == 0) return 0;
   if ((zdim & 3) == 0 && (q->c & 3) == 0 && (z->c & 3) == 0) {
     latent_mix_vec4_kernel<<<cdiv(total_pix * (z->c / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-        q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, make_seed(seed), level, sample0, alpha_dev,
+        q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, make_seed(seed, (cudaStream_t)stream), level, sample0, alpha_dev,
         temperature, zdim, total_pix, z->h * z->w, z->data, z->dtype, z->c);
     GA_LAUNCH_OK();
     return 0;
   }
   latent_mix_kernel<<<cdiv(total_pix, 128), 128, 0, (cudaStream_t)stream>>>(
-      q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, make_seed(seed), level, sample0, alpha_dev,
+      q->data, q->dtype, q->c, p ? p->data : nullptr, p ? p->dtype : GA_F32, eps, make_seed(seed, (cudaStream_t)stream), level, sample0, alpha_dev,
       temperature, zdim, total_pix, z->h * z->w, z->data, z->dtype, z->c);
   GA_LAUNCH_OK();
   return 0;

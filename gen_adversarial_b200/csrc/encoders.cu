@@ -326,7 +326,7 @@ extern "C" int ga_philox_codes(uint64_t seed, int64_t sample0, float std_, int l
   GA_CHECK(out && l > 0 && b >= 0 && d > 0 && d % 4 == 0, "ga_philox_codes: bad arguments");
   const int64_t total4 = (int64_t)l * b * (d / 4);
   if (total4 == 0) return 0;
-  philox_codes_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(make_seed(seed), sample0, std_, l, b, d, out);
+  philox_codes_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(make_seed(seed, (cudaStream_t)stream), sample0, std_, l, b, d, out);
   GA_LAUNCH_OK();
   return 0;
 }

@@ -279,7 +279,7 @@ __device__ __forceinline__ float round_tf32(float v) {
 
 // ----------------------------------------------------------------------------- seed with an optional device-side salt
 // Kernels take their Philox seed by value.  Under CUDA-graph replay a by-value seed is frozen into the graph, so every replay would
-// draw the same noise; when a salt buffer is registered (ga_seed_salt_set) the effective seed is seed + *salt, and ga_seed_salt_bump
+// draw the same noise; when a salt buffer is registered (ga_seed_salt_set) the effective seed of CAPTURED launches is seed + *salt, and ga_seed_salt_bump
 // -- a one-thread kernel captured as the first node of the graph -- advances the salt on every replay with no host involvement.
 const uint64_t* seed_salt_ptr();                       // host: the registered device buffer (nullptr = none)
 struct SeedArg {
@@ -287,7 +287,17 @@ struct SeedArg {
   const uint64_t* salt;
   __device__ __forceinline__ uint64_t get() const { return salt != nullptr ? seed + *salt : seed; }
 };
-static inline SeedArg make_seed(uint64_t seed) { return SeedArg{seed, seed_salt_ptr()}; }
+// The salt applies ONLY to launches recorded into a CUDA graph: an eager launch keeps its by-value seed, so (a) a fixed seed reproduces the
+// same noise in eager mode whether or not a graph has run in the process, and (b) a taped eager forward and its later backward passes
+// regenerate the same eps even if a graph replay advanced the salt in between (the tape stores only the by-value seed).
+static inline SeedArg make_seed(uint64_t seed, cudaStream_t stream) {
+  const uint64_t* salt = seed_salt_ptr();
+  if (salt != nullptr) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusActive) salt = nullptr;
+  }
+  return SeedArg{seed, salt};
+}
 
 // ----------------------------------------------------------------------------- counter-based RNG (Philox4x32-10)
 // Stream is keyed by (seed, stream id, element counter) so results do not depend on launch geometry or on

@@ -3,14 +3,16 @@
 Both are the preprocessing stage of the purification call used alone: they run on the same fused kernel
 (`ga_preprocess_fwd`: separable reflect-border Gaussian blur / L2-normalised Gaussian noise / clamp, one pass over the image)
 and hand the result to the base classifier.  Same class names, constructor arguments and `purify` / `forward` methods as the
-reference; noise comes from the in-kernel Philox stream (or from `set_explicit_noise` for parity runs).
+reference; noise comes from the in-kernel Philox stream (or from `set_explicit_noise` for parity runs).  `purify` / `forward` are
+differentiable w.r.t. the input (white-box attacks on the ablation configs): autograd.py `_PreprocessFn`.
 """
 from __future__ import annotations
 
 import torch
 from torch import nn
 
-from ... import ops
+from ... import ops  # noqa: F401
+from ...autograd import preprocess_apply
 
 
 class _AblationBase(nn.Module):
@@ -44,9 +46,7 @@ class GaussianNoiseDefenseModel(_AblationBase):
         if not x.is_cuda:
             raise RuntimeError("GaussianNoiseDefenseModel.purify: CUDA tensor expected (there is no CPU path)")
         noise = self._explicit_noise.to(x.device) if self._explicit_noise is not None else None
-        out, _ = ops.preprocess(x.detach().to(torch.float32), noise, float(self.eps), False, torch.float32, seed=self._seed(),
-                                sample0=self.sample_offset, normalize=False)
-        return out.permute(0, 3, 1, 2).contiguous()
+        return preprocess_apply(x, noise, float(self.eps), False, self._seed(), self.sample_offset)
 
 
 class GaussianBlurDefenseModel(_AblationBase):
@@ -58,5 +58,4 @@ class GaussianBlurDefenseModel(_AblationBase):
         """Gaussian blur, sigma 1, kernel 2^(sqrt(h)//2) - 1, reflect border (ablations/models.py:48-60)"""
         if not x.is_cuda:
             raise RuntimeError("GaussianBlurDefenseModel.purify: CUDA tensor expected (there is no CPU path)")
-        out, _ = ops.preprocess(x.detach().to(torch.float32), None, 0.0, True, torch.float32, normalize=False, taps_cache=self._taps_cache)
-        return out.permute(0, 3, 1, 2).contiguous()
+        return preprocess_apply(x, None, 0.0, True, 0, 0, self._taps_cache)

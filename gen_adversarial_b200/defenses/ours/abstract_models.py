@@ -146,8 +146,16 @@ class MLVGMDefenseModel(ABC):
         key = tuple(float(a) for a in self.interpolation_alphas)
         if key != self._alpha_key:
             if self._alpha_pinned is None or self._alpha_pinned.numel() != len(key):
-                self._alpha_pinned = torch.empty(len(key), dtype=torch.float32).pin_memory()
-                self._alpha_dev = torch.empty(len(key), dtype=torch.float32, device=self.device)
+                # one (pinned, device) buffer pair PER LENGTH, never freed: captured graphs are keyed by the length and keep the device
+                # pointer of the buffer that existed at capture time
+                if not hasattr(self, "_alpha_bufs"):
+                    self._alpha_bufs = {}
+                if len(key) not in self._alpha_bufs:
+                    self._alpha_bufs[len(key)] = (torch.empty(len(key), dtype=torch.float32).pin_memory(),
+                                                  torch.empty(len(key), dtype=torch.float32, device=self.device))
+                elif torch.cuda.is_available():
+                    torch.cuda.current_stream().synchronize()
+                self._alpha_pinned, self._alpha_dev = self._alpha_bufs[len(key)]
             elif torch.cuda.is_available():
                 torch.cuda.current_stream().synchronize()      # the previous async copy must have read the pinned buffer
             self._alpha_pinned.copy_(torch.tensor(key, dtype=torch.float32))
@@ -163,18 +171,17 @@ class MLVGMDefenseModel(ABC):
     # ------------------------------------------------------------------ reference API
     def add_gaussian_noise(self, x: torch.Tensor) -> torch.Tensor:
         """abstract_models.py:129-143 (N(0,1) noise scaled to L2 norm eps per sample, clamp to [0,1])."""
+        from ...autograd import preprocess_apply
         noise = self._explicit_noise[0] if self._explicit_noise is not None else None
-        out, _ = ops.preprocess(x.to(torch.float32), noise, float(self.eps), False, torch.float32, seed=self._next_seed(),
-                                sample0=self.sample_offset, normalize=False)
-        return out.permute(0, 3, 1, 2).contiguous()
+        return preprocess_apply(x, noise, float(self.eps), False, self._next_seed(), self.sample_offset)
 
     def apply_gaussian_blur(self, x: torch.Tensor) -> torch.Tensor:
         """abstract_models.py:145-159."""
         if not self.blur_input:
             return x
-        out, _ = ops.preprocess(x.to(torch.float32), None, 0.0, True, torch.float32, normalize=False, taps_cache=self._taps_cache)
+        from ...autograd import preprocess_apply
         # NOTE: the fused kernel also clamps to [0,1]; a blur of values in [0,1] stays in [0,1]
-        return out.permute(0, 3, 1, 2).contiguous()
+        return preprocess_apply(x, None, 0.0, True, 0, 0, self._taps_cache)
 
     def __call__(self, batch: torch.Tensor, preds_only: bool = True) \
             -> Union[torch.Tensor, [torch.Tensor, torch.Tensor]]:

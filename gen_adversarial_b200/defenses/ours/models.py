@@ -271,7 +271,9 @@ class TransStyleGanDefenseModel(_StyleGanDefenseBase, torch.nn.Module):
         ae = self.autoencoder
         n, h, w, c = x_nhwc.shape
         # resize(x, 256) then rows 32:-32 (models.py:307-308): bilinear to (256 * h / w ...) short side 256, crop fused in the kernel
-        full_h, full_w = (256, int(round(w * 256 / h))) if h <= w else (int(round(h * 256 / w)), 256)
+        # kornia `_side_to_image_size(256, w / h, 'short')` truncates: (256, int(256 * w/h)) if w/h > 1 else (int(256 / (w/h)), 256)
+        ar = w / h
+        full_h, full_w = (256, int(256 * ar)) if ar > 1 else (int(256 / ar), 256)
         x = ops.resize_bilinear(x_nhwc, full_h, full_w, 32, full_h - 64)
         query = ae.encoder.query(ae.decoder.mapping)                                      # models.py:310-315
         return ae.encoder.encode(x, query)

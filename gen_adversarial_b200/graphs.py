@@ -65,7 +65,9 @@ class GraphedForward:
 
     @staticmethod
     def make_key(model, batch):
-        return (tuple(batch.shape), float(model.eps), bool(model.blur_input), int(model.sample_offset), len(model.interpolation_alphas))
+        # everything a captured launch takes BY VALUE is part of the key (eps, blur, sample offset, the seed, the generator chunking)
+        return (tuple(batch.shape), float(model.eps), bool(model.blur_input), int(model.sample_offset), len(model.interpolation_alphas),
+                model.noise_seed, getattr(model, "max_chunk", None))
 
     def __call__(self, model, batch: torch.Tensor):
         model._alphas_device()
@@ -84,7 +86,7 @@ class GraphedPGD:
         self.key = (tuple(images.shape), float(step), float(eps), GraphedForward.make_key(net, images))
         self.x = images.detach().to(torch.float32).clone()
         self.x_adv = self.x.clone()
-        self.labels = labels.clone()
+        self.labels = labels.to(torch.int64).clone()          # the loss kernel reads int64 labels
 
         def body():
             bump_seed_salt()

@@ -87,7 +87,19 @@ TIMER: Optional[KernelTimer] = None
 TIME_ALL = False      # bench.py --breakdown: also bracket every non-conv_tc op (keyed "op:<name> <shape>")
 
 
-def _timed(name):
+def _tensor_bytes(objs) -> float:
+    by = 0.0
+    for o in objs:
+        if torch.is_tensor(o):
+            by += o.numel() * o.element_size()
+        elif isinstance(o, (tuple, list)):
+            by += _tensor_bytes(o)
+    return by
+
+
+def _timed(name, hbm: bool = False):
+    """bench.py instrumented pass: bracket the op with CUDA events.  hbm=True marks a bandwidth-bound kernel: its algorithmic bytes are
+    every tensor operand and result counted exactly once (compulsory traffic), keyed "hbm:<name> <shape>"."""
     def deco(fn):
         def wrapper(*a, **k):
             if TIMER is None or not TIME_ALL:
@@ -95,7 +107,10 @@ def _timed(name):
             e0 = TIMER.start()
             out = fn(*a, **k)
             shp = tuple(a[0].shape) if len(a) and torch.is_tensor(a[0]) else ()
-            TIMER.stop(e0, f"op:{name} {shp}", 0.0, 0.0)
+            if hbm:
+                TIMER.stop(e0, f"hbm:{name} {shp}", 0.0, _tensor_bytes(a) + _tensor_bytes(list(k.values())) + _tensor_bytes([out]))
+            else:
+                TIMER.stop(e0, f"op:{name} {shp}", 0.0, 0.0)
             return out
         wrapper.__name__ = fn.__name__
         wrapper.__doc__ = fn.__doc__
@@ -237,7 +252,7 @@ def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b
     return out
 
 
-@_timed("channel_sum")
+@_timed("channel_sum", hbm=True)
 def channel_sum(r: torch.Tensor) -> torch.Tensor:
     parts = _lib.lib().ga_channel_sum_parts(r.shape[0], r.shape[1] * r.shape[2])
     sums = torch.empty((r.shape[0], parts, r.shape[3]), device=r.device, dtype=torch.float32)
@@ -266,7 +281,7 @@ def se_residual(r, sums, se, res_scale: float, skip, out_dtype=torch.float32, wa
     return out, out2, act, gate
 
 
-@_timed("latent_mix")
+@_timed("latent_mix", hbm=True)
 def latent_mix(q, p, eps_nchw, seed: int, level: int, sample0: int, alpha_dev, temperature: float, zdim: int,
                zc: int, out_dtype) -> torch.Tensor:
     n, h, w, _ = q.shape
@@ -276,7 +291,7 @@ def latent_mix(q, p, eps_nchw, seed: int, level: int, sample0: int, alpha_dev, t
     return z
 
 
-@_timed("discmix_mean")
+@_timed("discmix_mean", hbm=True)
 def discmix_mean(logits, n_mix: int, cls_dtype=None):
     n, h, w, _ = logits.shape
     purified = torch.empty((n, 3, h, w), device=logits.device, dtype=torch.float32)
@@ -293,7 +308,7 @@ def upsample_nearest2x(x, out_dtype=None):
     return out
 
 
-@_timed("upsample_bilinear2x")
+@_timed("upsample_bilinear2x", hbm=True)
 def upsample_bilinear2x(x, out_dtype=None):
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=out_dtype or x.dtype)
@@ -301,7 +316,7 @@ def upsample_bilinear2x(x, out_dtype=None):
     return out
 
 
-@_timed("maxpool2x2")
+@_timed("maxpool2x2", hbm=True)
 def maxpool2x2(x, out_dtype=None):
     n, h, w, c = x.shape
     out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=out_dtype or x.dtype)
@@ -333,7 +348,7 @@ def global_avgpool(x, out_dtype=None):
     return out
 
 
-@_timed("affine_act")
+@_timed("affine_act", hbm=True)
 def affine_act(x, scale, shift, act: int, out_dtype):
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
     _lib.check(_lib.lib().ga_affine_act(gt(x), ptr(scale), ptr(shift), act, gt(out), stream()), "affine_act")
@@ -372,7 +387,7 @@ def gaussian_taps(h: int, max_radius: int = 12):
     return g.to(torch.float32), r
 
 
-@_timed("preprocess")
+@_timed("preprocess", hbm=True)
 def preprocess(x_nchw, noise_nchw, eps: float, blur: bool, out_dtype, seed: int = 0, sample0: int = 0,
                normalize: bool = True, save_pre: bool = False, taps_cache=None):
     """blur -> noise -> clamp -> (x-.5)/.5 in one kernel (+ the L2-norm pre-pass).  -> (out NHWC, pre NCHW|None)"""
@@ -403,6 +418,7 @@ def preprocess(x_nchw, noise_nchw, eps: float, blur: bool, out_dtype, seed: int 
     return out, pre
 
 
+@_timed("pgd_linf_step", hbm=True)
 def pgd_linf_step_(x_adv, grad, x_nat, step: float, eps: float):
     assert x_adv.is_contiguous() and grad.is_contiguous() and x_nat.is_contiguous()
     _lib.check(_lib.lib().ga_pgd_linf_step(ptr(x_adv), ptr(grad), ptr(x_nat), step, eps, x_adv.numel(), stream()), "pgd_linf_step")
@@ -414,6 +430,13 @@ def softmax_xent(logits, labels, want_grad=True, counter=None):
     """-> (loss[n], dlogits|None, pred[n] int32); `counter` (uint64 device scalar) accumulates argmax==label."""
     n, k = logits.shape
     logits = logits.contiguous()
+    if not labels.is_cuda or labels.dim() != 1 or labels.shape[0] != n:
+        raise RuntimeError(f"softmax_xent: labels must be a CUDA tensor of shape ({n},), got {tuple(labels.shape)} on {labels.device}")
+    if labels.dtype != torch.int64:          # the kernel reads const int64_t*: any other integer width would be misread
+        if labels.dtype.is_floating_point or labels.dtype == torch.bool:
+            raise TypeError(f"softmax_xent: labels must be an integer tensor, got {labels.dtype}")
+        labels = labels.to(torch.int64)
+    labels = labels.contiguous()
     loss = torch.empty((n,), device=logits.device, dtype=torch.float32)
     dl = torch.empty_like(logits) if want_grad else None
     pred = torch.empty((n,), device=logits.device, dtype=torch.int32)
@@ -448,7 +471,7 @@ def channel_scale(x, s, out_dtype):
     return out
 
 
-@_timed("styled_bias_act")
+@_timed("styled_bias_act", hbm=True)
 def styled_bias_act(y, phases: bool, demod, noise_hw, noise_w: float, bias, act: int, skip, out_dtype, scale_a=None, scale_b=None,
                     want_out: bool = True, skip_up_kernel=None):
     """v = act(y * demod + noise + bias) (+ skip, up-sampled x2 on the fly through the 4x4 FIR `skip_up_kernel` when given);
@@ -462,7 +485,7 @@ def styled_bias_act(y, phases: bool, demod, noise_hw, noise_w: float, bias, act:
     return (out, out_b) if scale_b is not None else out
 
 
-@_timed("upfirdn2d")
+@_timed("upfirdn2d", hbm=True)
 def upfirdn2d(x, kernel, up: int = 1, down: int = 1, pad=(0, 0), out_dtype=None):
     """same semantics as the reference op (stylegan2/op/upfirdn2d.py:141-147) on NHWC tensors"""
     n, h, w, c = x.shape
@@ -528,7 +551,7 @@ def resize_bilinear(x, full_h: int, out_w: int, crop_y0: int, crop_h: int, out_d
     return out
 
 
-@_timed("image_pool_out")
+@_timed("image_pool_out", hbm=True)
 def image_pool_out(img, k1: int, k2: int = 1, mask_rows: int = 0, denorm=(0.5, 0.5), cls_dtype=None, want_purified: bool = True):
     """generator image NHWC fp32 -> (purified NCHW fp32 denormalised | None, classifier input NHWC | None)"""
     n, s = img.shape[0], img.shape[1]
@@ -548,21 +571,21 @@ def philox_codes(seed: int, sample0: int, std: float, l: int, b: int, d: int, de
 
 
 # ------------------------------------------------------------------------------------------------ backward ops
-@_timed("affine_act_bwd")
+@_timed("affine_act_bwd", hbm=True)
 def affine_act_bwd(g, x, scale, shift, act: int, out_dtype, add=None):
     out = torch.empty(g.shape, device=g.device, dtype=out_dtype)
     _lib.check(_lib.lib().ga_affine_act_bwd(gt(g), gt(x), ptr(scale), ptr(shift), act, gt(add), gt(out), stream()), "affine_act_bwd")
     return out
 
 
-@_timed("add")
+@_timed("add", hbm=True)
 def add(a, b, out_dtype):
     out = torch.empty(a.shape, device=a.device, dtype=out_dtype)
     _lib.check(_lib.lib().ga_add(gt(a), gt(b), gt(out), stream()), "add")
     return out
 
 
-@_timed("se_residual_bwd")
+@_timed("se_residual_bwd", hbm=True)
 def se_residual_bwd(g_out, r, sums, se, res_scale: float, out_dtype):
     w1, b1, w2, b2 = se
     g_r = torch.empty(r.shape, device=r.device, dtype=out_dtype)
@@ -572,7 +595,7 @@ def se_residual_bwd(g_out, r, sums, se, res_scale: float, out_dtype):
     return g_r
 
 
-@_timed("sumpool2x2")
+@_timed("sumpool2x2", hbm=True)
 def sumpool2x2(x, out_dtype, mul=None):
     n, h, w, c = x.shape
     out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=out_dtype)
@@ -588,7 +611,7 @@ def upsample_bilinear2x_bwd(g_out, out_dtype):
     return out
 
 
-@_timed("depth_to_space2")
+@_timed("depth_to_space2", hbm=True)
 def depth_to_space2(x: torch.Tensor) -> torch.Tensor:
     """[n,h,w,4c] fp32 (phase-major channels) -> [n,2h,2w,c]"""
     n, h, w, c4 = x.shape
@@ -597,14 +620,14 @@ def depth_to_space2(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-@_timed("maxpool2x2_bwd")
+@_timed("maxpool2x2_bwd", hbm=True)
 def maxpool2x2_bwd(x_in, g_out, relu: bool, out_dtype):
     out = torch.empty(x_in.shape, device=x_in.device, dtype=out_dtype)
     _lib.check(_lib.lib().ga_maxpool2x2_bwd(gt(x_in), gt(g_out), int(relu), gt(out), stream()), "maxpool2x2_bwd")
     return out
 
 
-@_timed("latent_mix_bwd")
+@_timed("latent_mix_bwd", hbm=True)
 def latent_mix_bwd(g_z, q, p, eps_nchw, seed: int, level: int, sample0: int, alpha_dev, temperature: float, zdim: int, zc: int):
     """-> (g_q fp32 [n,h,w,zc] zero-padded beyond zdim, g_p fp32 [n,h,w,2*zdim] | None)"""
     n, h, w, _ = q.shape
@@ -615,7 +638,7 @@ def latent_mix_bwd(g_z, q, p, eps_nchw, seed: int, level: int, sample0: int, alp
     return g_q, g_p
 
 
-@_timed("discmix_mean_bwd")
+@_timed("discmix_mean_bwd", hbm=True)
 def discmix_mean_bwd(logits, n_mix: int, g_purified_nchw, g_cls, pad_to: int = 0):
     """-> d loss / d logits, fp32, channel-padded with zeros to `pad_to` channels (tensor-core alignment of the dgrad conv)"""
     n, h, w, c = logits.shape
@@ -625,6 +648,7 @@ def discmix_mean_bwd(logits, n_mix: int, g_purified_nchw, g_cls, pad_to: int = 0
     return g_logits
 
 
+@_timed("preprocess_bwd", hbm=True)
 def preprocess_bwd(g_nhwc, pre_nchw, blur: bool, normalize: bool = True, taps_cache=None):
     """-> gradient w.r.t. the input batch (NCHW fp32)."""
     n, h, w, c = g_nhwc.shape

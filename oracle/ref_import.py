@@ -1,10 +1,14 @@
 """TEST INFRASTRUCTURE ONLY -- imports the *unmodified* reference from /root/reference.
 
 This module is the "real reference" leg of the oracle.
-It only works inside the build container (where /root/reference is mounted); nothing in the
-`-m gpu` tests, `smoke()` or `bench.py` imports it.  It is used by
-  * tests/test_oracle_vs_reference.py  (validates oracle/nvae_ref.py against the reference), and
-  * oracle/make_golden.py              (generates tests/golden/* fixtures).
+The tree is /root/reference in the build container, or its byte-identical copy under the git-ignored
+oracle/_ref/reference/ (oracle/build_ref.sh) on the GPU box.  It is used by
+  * tests/test_oracle_vs_reference.py  (validates oracle/nvae_ref.py against the reference),
+  * oracle/make_golden.py              (generates tests/golden/* fixtures), and
+  * bench.py: `--impl reference` (the reference's own modules on the host cores, kind "reference") and the
+    `incumbent_gpu` block (the same modules on cuda:0 -- `install(cpu_stylegan_ops=False)` lets the reference
+    JIT-build and use its own upfirdn2d / fused_bias_act CUDA kernels there).
+The product never imports it.
 
 No reference file is copied or modified: three import-time shims make the tree importable
 (the committed reference has import-time defects):
@@ -35,7 +39,22 @@ import typing
 import torch
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("GA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference_root() -> str:
+    """/root/reference in the build container; on the GPU box the byte-identical copy that oracle/build_ref.sh placed under the
+    git-ignored oracle/_ref/reference/ (it travels with the snapshot like a built .so)."""
+    env = os.environ.get("GA_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref", "reference")):
+        if os.path.isdir(os.path.join(cand, "src", "defenses", "ours")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -103,11 +122,17 @@ def k_gaussian_blur2d(x, kernel_size, sigma, border_type="reflect", separable=Tr
 
 def k_resize(x, size, interpolation="bilinear", align_corners=None, side="short", antialias=False):
     if isinstance(size, int):
+        # kornia.geometry.transform.affwarp._side_to_image_size: truncation, not rounding
         h, w = x.shape[-2:]
-        if (side == "short" and h <= w) or (side == "long" and h > w) or side == "vert":
-            size = (size, int(round(w * size / h)))
+        ar = w / h
+        if side == "vert":
+            size = (size, int(size * ar))
+        elif side == "horz":
+            size = (int(size / ar), size)
+        elif (side == "short") ^ (ar < 1.0):
+            size = (size, int(size * ar))
         else:
-            size = (int(round(h * size / w)), size)
+            size = (int(size / ar), size)
     return F.interpolate(x, size=size, mode=interpolation, align_corners=align_corners, antialias=antialias)
 
 
@@ -255,3 +280,65 @@ class ExplicitNoise:
         torch.Tensor.normal_ = self._orig_normal_
         torch.normal = self._orig_normal
         return False
+
+
+class InMemoryCheckpoints:
+    """Context manager: `torch.load(path)` returns a prepared object for the given pseudo-paths, so the reference's own loaders
+    (src/defenses/loading_utils.py:10-81, psp.py:39-45, style_transformer.py:30-36) ingest synthetic checkpoints without a multi-GB
+    round trip through the file system (the VGG11 head alone is 2.5 GB).  No reference code is changed."""
+
+    def __init__(self, table):
+        self.table = dict(table)
+        self._orig = None
+
+    def __enter__(self):
+        self._orig = torch.load
+        outer = self
+
+        def load(f, *a, **kw):
+            if isinstance(f, str) and f in outer.table:
+                return outer.table[f]
+            return outer._orig(f, *a, **kw)
+
+        torch.load = load
+        return self
+
+    def __exit__(self, *exc):
+        torch.load = self._orig
+        return False
+
+
+REFERENCE_YAMLS = {"purify": "ours_learned_blur_ids.yaml", "pgd": "ours_cosine_noise_ids.yaml",
+                   "gender": "ours_linear_noise_gender.yaml", "cars": "ours_cosine_blur_cars.yaml"}
+
+
+def build_reference_defense(workload: str, device: str = "cpu"):
+    """The reference's OWN defense model for one BASELINE workload -- classes of src/defenses/ours/models.py constructed exactly as
+    src/experiments/load_defense.py:134-140 does, from the YAML in the reference's configs/ and the seeded synthetic checkpoints of
+    gen_adversarial_b200/synth.py (the same weights the CUDA path loads).  device "cpu": the two StyleGAN CUDA ops are replaced by
+    their CPU restatement (they refuse CPU tensors); device "cuda:*": the reference JIT-builds and runs its own kernels.
+    -> (defense model, resolution (C,H,W), n_classes, yaml dict)"""
+    import yaml
+    from gen_adversarial_b200 import synth
+    on_gpu = str(device).startswith("cuda")
+    install(cpu_stylegan_ops=not on_gpu)
+    mm = importlib.import_module("src.defenses.ours.models")
+    with open(os.path.join(REFERENCE_ROOT, "configs", REFERENCE_YAMLS[workload])) as f:
+        p = yaml.safe_load(f)
+    if workload in ("purify", "pgd"):
+        from gen_adversarial_b200.nvae_spec import NVAE_C32_RESOLUTION
+        table = {"mem://ae": synth.make_nvae_checkpoint(seed=0), "mem://clf": synth.make_vgg11_checkpoint(100, seed=1)}
+        Clf, Def, res, n_cls = mm.CelebaIdentityClassifier, mm.NVAEDefenseModel, NVAE_C32_RESOLUTION, 100
+    elif workload == "gender":
+        table = {"mem://ae": synth.make_e4e_checkpoint(1024), "mem://clf": synth.make_resnet50_checkpoint()}
+        Clf, Def, res, n_cls = mm.CelebaGenderClassifier, mm.E4EStyleGanDefenseModel, (3, 256, 256), 2
+    elif workload == "cars":
+        table = {"mem://ae": synth.make_trans_checkpoint(512), "mem://clf": synth.make_resnext50_checkpoint()}
+        Clf, Def, res, n_cls = mm.CarsTypeClassifier, mm.TransStyleGanDefenseModel, (3, 128, 128), 4
+    else:
+        raise ValueError(workload)
+    with InMemoryCheckpoints(table):
+        clf = Clf("mem://clf", device)
+        dm = Def(clf, "mem://ae", p["interpolation_alphas"], p["alpha_attenuation"], p["initial_noise_eps"], p["gaussian_blur_input"],
+                 device)
+    return dm, res, n_cls, p

@@ -65,3 +65,40 @@ def test_alpha_schedules_and_objective():
     assert acc0 == 1.0                                                        # alpha 0: no resampling, EoT replicas agree
     acc1 = ev.objective_function(get_cosine_alphas(spec.n_latents))
     assert 0.0 <= acc1 <= 1.0 and dm.interpolation_alphas[-1] == pytest.approx(0.7)
+
+
+def test_ablation_models_are_differentiable_like_the_reference():
+    """white-box attacks on the ablation configs take autograd.grad(loss, [x]) through purify + classifier
+    (reference ablations/models.py:21-60 is plain torch/kornia and differentiable): gradient parity against torch autograd
+    through the same arithmetic."""
+    g = torch.Generator().manual_seed(3)
+    x = synth.synthetic_batch(3, (3, 64, 64), seed=9)[0]
+    w = torch.randn(3, 3, 64, 64, generator=g)
+    k = int(2 ** (math.sqrt(64) // 2) - 1)
+
+    class _Lin(torch.nn.Module):      # any differentiable torch classifier works behind the ablation purifiers
+        def forward(self, t):
+            return (t * w.to(t.device)).flatten(1).sum(1, keepdim=True)
+
+    # blur
+    xr = x.clone().requires_grad_(True)
+    g_ref, = torch.autograd.grad(_Lin()(_kornia_blur(xr, k)).sum(), [xr])
+    xd = x.to(DEV).requires_grad_(True)
+    out = GaussianBlurDefenseModel(_Lin())(xd)
+    assert out.requires_grad
+    g_got, = torch.autograd.grad(out.sum(), [xd])
+    assert (g_got.cpu() - g_ref).abs().max().item() <= 1e-5 * max(1.0, g_ref.abs().max().item())
+    # noise + clamp: the gradient is the clamp mask
+    noise = torch.randn(x.shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = (xr + noise * (3.0 / noise.flatten(1).norm(dim=1).view(-1, 1, 1, 1))).clamp(0.0, 1.0)
+    g_ref, = torch.autograd.grad(_Lin()(ref).sum(), [xr])
+    nd = GaussianNoiseDefenseModel(_Lin(), eps=3.0)
+    nd.set_explicit_noise(noise)
+    xd = x.to(DEV).requires_grad_(True)
+    g_got, = torch.autograd.grad(nd(xd).sum(), [xd])
+    assert 0.0 < (g_ref == 0).float().mean().item() < 1.0                     # some pixels clamp, most do not
+    assert (g_got.cpu() - g_ref).abs().max().item() <= 1e-6
+    # no-grad calls stay on the plain path
+    with torch.no_grad():
+        assert not nd(x.to(DEV)).requires_grad

@@ -202,8 +202,9 @@ def test_input_gradient_through_the_api_matches_oracle_autograd(c32_models, mode
         else:
             # bf16: the purifier's gradient is accurate (cos 0.99998, test below); the random-init, BN-calibrated VGG11 is a
             # ReLU/max-pool network whose unit on/off pattern flips under bf16 rounding (the CPU emulation of the same bf16
-            # arithmetic shows the same 0.94-0.96), so the end-to-end direction is only required to stay close
-            assert cos >= 0.9
+            # arithmetic shows the same 0.94-0.96), so the end-to-end direction is only required to stay close; what the attack
+            # needs -- the same robust-accuracy counts as the fp32 path -- is gated in test_pgd_50_steps_robust_counts below
+            assert cos >= 0.93
     assert torch.allclose(g1b, 2 * g1, rtol=1e-3, atol=1e-9)
     assert ((g1 - g2).norm() / g2.norm()).item() <= 1e-4
 
@@ -288,12 +289,23 @@ def test_cuda_graph_replay_matches_eager_and_draws_fresh_noise():
     s_before = int(salt.item())
     g3 = dm(x).clone()
     dm.enable_cuda_graph(False)
-    v = (s_before + 0x9E3779B97F4A7C15) & ((1 << 64) - 1)     # the salt value the third replay ran with (uint64 add, stored as int64)
-    salt.copy_(torch.tensor([v - (1 << 64) if v >= (1 << 63) else v], dtype=torch.int64))
+    v = (s_before + 0x9E3779B97F4A7C15) & ((1 << 64) - 1)     # the salt value the third replay ran with (uint64 add)
+    # the salt applies to captured launches only: an eager call reproduces the replay when it is given seed + salt by value ...
+    dm.noise_seed = (5 + v) & ((1 << 64) - 1)
     e3 = dm(x).clone()
     assert (g3 - e3).abs().max().item() <= 1e-5 * max(1.0, e3.abs().max().item())
-    salt.zero_()
+    # ... and a fixed seed reproduces the first eager result no matter what the graphs did to the salt in between
+    dm.noise_seed = 5
     assert (dm(x) - eager).abs().max().item() <= 1e-5 * max(1.0, eager.abs().max().item())
+    # a taped eager forward and its backward see the same eps even if a replay bumps the salt in between
+    xg = x.clone().requires_grad_(True)
+    loss = dm(xg).square().sum()
+    ga_, = torch.autograd.grad(loss, [xg], retain_graph=True)
+    dm.enable_cuda_graph(True)
+    dm(x)                                                      # graph replay between forward and the second backward
+    dm.enable_cuda_graph(False)
+    gb_, = torch.autograd.grad(loss, [xg])
+    assert torch.equal(ga_, gb_)
     # alphas are read from device memory at replay time
     dm.enable_cuda_graph(True)
     a = dm(x).clone()
@@ -306,3 +318,80 @@ def test_cuda_graph_replay_matches_eager_and_draws_fresh_noise():
     assert linf.max().item() <= 8 / 255 + 1e-6 and x_adv.min().item() >= 0 and x_adv.max().item() <= 1
     assert (x_adv - x).abs().max().item() > 1e-3
     graphs.enable_seed_salt(DEV).zero_()
+
+
+def _tiny_attack_setup(batch, steps, seed):
+    """tiny NVAE (2 scales x 2 groups, 32x32) + VGG11(10 classes): small enough that the oracle's 50-step PGD takes seconds on CPU"""
+    cfg, res = tiny_config(initial_channels=16, groups=2, scales=2, latent=4), (3, 32, 32)
+    spec = NvaeSpec(cfg, res)
+    nv = synth.make_nvae_checkpoint(cfg, res, seed=3)
+    vg = {"state_dict": synth.make_vgg11_state_dict(10, seed=3)}
+    n = spec.n_latents
+    alphas = [0.7 * 0.5 * (1 - __import__("math").cos(__import__("math").pi * i / n)) for i in range(1, n + 1)]
+    x, _ = synth.synthetic_batch(batch, res, 10, seed=seed)
+    sched = [synth.synthetic_noise(spec, batch, seed=1000 + 7 * i) for i in range(steps + 1)]
+    return cfg, res, spec, nv, vg, alphas, x, sched
+
+
+def test_pgd_50_steps_robust_counts_match_oracle():
+    """BASELINE configs[4] at full attack length (eps 8/255, step 2/255, 50 steps, batch 16, explicit noise per step): the fp32 path
+    must reproduce the oracle's PGD -- identical per-image success flags (robust-accuracy count) and >= 99% identical adversarial
+    pixels; the bf16 path (what bench.py times) is reported against the same oracle run and gated on the robust count."""
+    steps, batch = 50, 16
+    cfg, res, spec, nv, vg, alphas, x, sched = _tiny_attack_setup(batch, steps, seed=21)
+    vgg = nvae_ref.build_vgg11(vg["state_dict"], 10)
+    sd = nv["state_dict_temp=0.6"]
+    with torch.no_grad():
+        y = nvae_ref.defense_call(sd, spec, vgg, x, alphas, sched[0], 1.0, True)[0].argmax(1)
+
+    def logits_fn(xa, i):
+        return nvae_ref.defense_call(sd, spec, vgg, xa, alphas, sched[i], 1.0, True)[0]
+
+    adv_ref = nvae_ref.pgd_linf_attack(logits_fn, x, y, 8 / 255, 2 / 255, steps)
+    with torch.no_grad():
+        succ_ref = logits_fn(adv_ref, steps).argmax(1) != y
+    print(f"oracle: {int(succ_ref.sum())}/{batch} attacks succeed (robust count {batch - int(succ_ref.sum())})")
+    results = {}
+    for mode in ("fp32", "bf16"):
+        clf = CelebaIdentityClassifier({"state_dict": {k: v.to(DEV) for k, v in vg["state_dict"].items()}}, DEV, mode=mode, n_classes=10, image_size=32)
+        dm = NVAEDefenseModel(clf, nv, [a / 0.7 for a in alphas], 0.7, 1.0, True, DEV, mode=mode).eval()
+        succ, linf, adv = PGDLinf(8 / 255, 2 / 255, steps)(x.to(DEV), y.to(DEV), dm, noise_schedule=sched)
+        same = ((adv.cpu() - adv_ref).abs() <= 1e-6).float().mean().item()
+        flags = int((succ.cpu() == succ_ref).sum())
+        results[mode] = (same, flags, int(succ.sum()))
+        print(f"[{mode}] 50-step PGD: {100 * same:.2f}% adversarial pixels identical, success flags equal on {flags}/{batch} images, "
+              f"robust count {batch - int(succ.sum())} (oracle {batch - int(succ_ref.sum())})")
+        assert linf.max().item() <= 8 / 255 + 1e-6 and adv.min().item() >= 0 and adv.max().item() <= 1
+    assert results["fp32"][1] == batch, "fp32 path: per-image success flags must equal the oracle's"
+    assert results["fp32"][0] >= 0.99
+    # bf16: the robust COUNT may differ by at most one image of 16 from the fp32 / oracle count
+    assert abs(results["bf16"][2] - int(succ_ref.sum())) <= 1
+
+
+def test_clean_counts_identical_on_64_images(c32_models):
+    """north star: clean accuracy counts identical for the fp32 path -- C32 + VGG11, 64 images, explicit noise, every arg-max equal to
+    the oracle's; the bf16 path is reported (count of differing arg-maxes)."""
+    nv, vg = c32_models
+    spec = NvaeSpec(NVAE_C32_CONFIG, NVAE_C32_RESOLUTION)
+    import math
+    alphas = [0.7 * 0.5 * (1 - math.cos(math.pi * i / 24)) for i in range(1, 25)]
+    x, _ = synth.synthetic_batch(64, seed=31)
+    noises = synth.synthetic_noise(spec, 64, seed=32)
+    vgg = nvae_ref.build_vgg11(vg["state_dict"], 100)
+    with torch.no_grad():
+        ref = nvae_ref.defense_call(nv["state_dict_temp=0.6"], spec, vgg, x, alphas, noises, 2.0, True)[0]
+    y = ref.argmax(1)
+    assert y.unique().numel() > 4                                          # not a constant predictor
+    for mode in ("fp32", "bf16"):
+        clf = CelebaIdentityClassifier(vg, DEV, mode=mode)
+        dm = NVAEDefenseModel(clf, nv, [a / 0.7 for a in alphas], 0.7, 2.0, True, DEV, mode=mode).eval()
+        dm.set_explicit_noise(noises)
+        with torch.no_grad():
+            got = dm(x.to(DEV)).cpu()
+        diff = int((got.argmax(1) != y).sum())
+        rel = ((got - ref).abs().max() / ref.abs().max()).item()
+        print(f"[{mode}] 64 images: {diff} arg-max differences, logits rel err {rel:.2e}")
+        if mode == "fp32":
+            assert diff == 0 and rel <= 1e-3
+        else:
+            assert diff <= 3
