@@ -473,7 +473,7 @@ def instrumented_pass(ctx, dm, workload, x_dev, y_dev, steps, step_ms, breakdown
         extra.append({"kernel": "mbconv_fused_kernel (decoder cell: expand 1x1 -> SiLU -> depthwise 5x5 -> SiLU -> project 1x1, hidden tensor on chip)",
                       "bound": "tensor", "achieved": f_fl / (f_ms * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                       "frac": f_fl / (f_ms * 1e-3) / 1e12 / pk["tf_sustained"], "launches_per_step": round(sum(a["launches"] for a in fused.values())),
-                      "share_of_step": f_ms / step_ms,
+                      "share_of_step": f_ms / step_ms if step_ms > 0 else None,
                       "fp32_pipe": {"achieved_tfma_s": simt_ops / (f_ms * 1e-3) / 1e12, "peak_tfma_s": fp32_peak / 1e12,
                                     "frac": simt_ops / (f_ms * 1e-3) / fp32_peak},
                       "by_shape": [{"shape": k[6:], "launches": round(a["launches"]), "us_per_launch": round(1e3 * a["ms"] / a["launches"], 1),
@@ -488,7 +488,7 @@ def instrumented_pass(ctx, dm, workload, x_dev, y_dev, steps, step_ms, breakdown
             continue
         extra.append({"kernel": name, "bound": "hbm", "achieved": h_by / (h_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                       "frac": h_by / (h_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "launches_per_step": round(sum(a["launches"] for a in shapes.values())),
-                      "share_of_step": h_ms / step_ms,
+                      "share_of_step": h_ms / step_ms if step_ms > 0 else None,
                       "by_shape": [{"shape": k, "launches": round(a["launches"]), "us_per_launch": round(1e3 * a["ms"] / a["launches"], 1),
                                     "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1)} for k, a in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:4]]})
     return roof, extra

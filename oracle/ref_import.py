@@ -334,6 +334,7 @@ def build_reference_defense(workload: str, device: str = "cpu"):
         Clf, Def, res, n_cls = mm.CelebaGenderClassifier, mm.E4EStyleGanDefenseModel, (3, 256, 256), 2
     elif workload == "cars":
         table = {"mem://ae": synth.make_trans_checkpoint(512), "mem://clf": synth.make_resnext50_checkpoint()}
+        table["mem://ae"]["opts"]["device"] = str(device)      # style_transformer.py:30-36 reads the device from the checkpoint's opts
         Clf, Def, res, n_cls = mm.CarsTypeClassifier, mm.TransStyleGanDefenseModel, (3, 128, 128), 4
     else:
         raise ValueError(workload)

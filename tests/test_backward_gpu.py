@@ -334,9 +334,12 @@ def _tiny_attack_setup(batch, steps, seed):
 
 
 def test_pgd_50_steps_robust_counts_match_oracle():
-    """BASELINE configs[4] at full attack length (eps 8/255, step 2/255, 50 steps, batch 16, explicit noise per step): the fp32 path
-    must reproduce the oracle's PGD -- identical per-image success flags (robust-accuracy count) and >= 99% identical adversarial
-    pixels; the bf16 path (what bench.py times) is reported against the same oracle run and gated on the robust count."""
+    """BASELINE configs[4] at full attack length (eps 8/255, step 2/255, 50 steps, batch 16, explicit noise per step).
+    PGD is a sign iteration: one flipped sign of a near-zero gradient component moves that pixel by 4/255 and the two trajectories
+    then drift apart chaotically (measured: fp32 free-running 74% identical pixels after 50 steps although every success flag agrees),
+    so pixel identity is checked TEACHER-FORCED -- at every one of the 50 steps the CUDA path takes the oracle's iterate and must produce
+    the oracle's next iterate on >= 99% of the pixels (fp32) -- and the attack OUTCOME is checked free-running: identical per-image
+    success flags (= identical robust-accuracy count) for the fp32 path; the bf16 path (what bench.py times) is gated on the count."""
     steps, batch = 50, 16
     cfg, res, spec, nv, vg, alphas, x, sched = _tiny_attack_setup(batch, steps, seed=21)
     vgg = nvae_ref.build_vgg11(vg["state_dict"], 10)
@@ -347,7 +350,12 @@ def test_pgd_50_steps_robust_counts_match_oracle():
     def logits_fn(xa, i):
         return nvae_ref.defense_call(sd, spec, vgg, xa, alphas, sched[i], 1.0, True)[0]
 
-    adv_ref = nvae_ref.pgd_linf_attack(logits_fn, x, y, 8 / 255, 2 / 255, steps)
+    traj = [x.clone()]                                         # the oracle's iterates x_adv^0 .. x_adv^50
+    for i in range(steps):
+        xa = traj[-1].clone().requires_grad_(True)
+        g, = torch.autograd.grad(torch.nn.functional.cross_entropy(logits_fn(xa, i), y), [xa])
+        traj.append(nvae_ref.pgd_linf_step(traj[-1], g, x, 2 / 255, 8 / 255).detach())
+    adv_ref = traj[-1]
     with torch.no_grad():
         succ_ref = logits_fn(adv_ref, steps).argmax(1) != y
     print(f"oracle: {int(succ_ref.sum())}/{batch} attacks succeed (robust count {batch - int(succ_ref.sum())})")
@@ -355,17 +363,30 @@ def test_pgd_50_steps_robust_counts_match_oracle():
     for mode in ("fp32", "bf16"):
         clf = CelebaIdentityClassifier({"state_dict": {k: v.to(DEV) for k, v in vg["state_dict"].items()}}, DEV, mode=mode, n_classes=10, image_size=32)
         dm = NVAEDefenseModel(clf, nv, [a / 0.7 for a in alphas], 0.7, 1.0, True, DEV, mode=mode).eval()
+        # free-running attack: outcome
         succ, linf, adv = PGDLinf(8 / 255, 2 / 255, steps)(x.to(DEV), y.to(DEV), dm, noise_schedule=sched)
-        same = ((adv.cpu() - adv_ref).abs() <= 1e-6).float().mean().item()
+        same_free = ((adv.cpu() - adv_ref).abs() <= 1e-6).float().mean().item()
         flags = int((succ.cpu() == succ_ref).sum())
-        results[mode] = (same, flags, int(succ.sum()))
-        print(f"[{mode}] 50-step PGD: {100 * same:.2f}% adversarial pixels identical, success flags equal on {flags}/{batch} images, "
-              f"robust count {batch - int(succ.sum())} (oracle {batch - int(succ_ref.sum())})")
         assert linf.max().item() <= 8 / 255 + 1e-6 and adv.min().item() >= 0 and adv.max().item() <= 1
-    assert results["fp32"][1] == batch, "fp32 path: per-image success flags must equal the oracle's"
-    assert results["fp32"][0] >= 0.99
+        # teacher-forced: one CUDA step from each oracle iterate
+        worst, mean = 1.0, 0.0
+        xd, yd = x.to(DEV), y.to(DEV)
+        for i in range(steps):
+            dm.set_explicit_noise(sched[i])
+            xa = traj[i].to(DEV).contiguous().clone()
+            _, grad, _ = dm.loss_input_grad(xa, yd)
+            ops.pgd_linf_step_(xa, grad, xd, 2 / 255, 8 / 255)
+            same = ((xa.cpu() - traj[i + 1]).abs() <= 1e-6).float().mean().item()
+            worst, mean = min(worst, same), mean + same / steps
+        dm.set_explicit_noise(None)
+        results[mode] = (worst, mean, flags, int(succ.sum()))
+        print(f"[{mode}] 50-step PGD: teacher-forced identical pixels per step: worst {100 * worst:.2f}% mean {100 * mean:.2f}%; free-running: "
+              f"{100 * same_free:.2f}% identical after 50 steps, success flags equal on {flags}/{batch} images, "
+              f"robust count {batch - int(succ.sum())} (oracle {batch - int(succ_ref.sum())})")
+    assert results["fp32"][2] == batch, "fp32 path: per-image success flags must equal the oracle's"
+    assert results["fp32"][0] >= 0.99, "fp32 path: every single PGD step must reproduce the oracle's step on >= 99% of the pixels"
     # bf16: the robust COUNT may differ by at most one image of 16 from the fp32 / oracle count
-    assert abs(results["bf16"][2] - int(succ_ref.sum())) <= 1
+    assert abs(results["bf16"][3] - int(succ_ref.sum())) <= 1
 
 
 def test_clean_counts_identical_on_64_images(c32_models):
