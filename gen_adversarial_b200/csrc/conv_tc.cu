@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include "ga_common.cuh"
 #include "tc_ptx.cuh"
+#include "conv_tc_epilogue.cuh"
+#include "tc_host.cuh"
 
 namespace ga {
 
@@ -29,30 +31,6 @@ constexpr int TC_BLOCK_K = 64;                       // bf16 elements = 128 byte
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 constexpr int TC_THREADS = 192;
 
-struct TcParams {
-  int taps, kw, pad, stride;  // filter taps of source 1; stride 1 or 2 (TMA element strides do the decimation)
-  int k32;                    // 1: 32-channel K blocks (64-byte swizzle) for Cin = 32, 96, ...: no half-empty 64-channel boxes
-  int tf32;                   // 1: fp32 activations and weights, kind::tf32 MMA, 32-channel K blocks (32 x 4 B = one 128-byte swizzle row)
-  int cin, kc1, kc2;          // channels of source 1, its 64-blocks per tap, 64-blocks of source 2
-  int bw, bh, bn;             // pixel box of one M tile (bw*bh*bn == 128)
-  int tiles_x, tiles_y;       // tiles per image row / column (bn == 1) -- else whole images per tile
-  int H, W;
-  int64_t M;                  // total output pixels
-  int cout;
-  int n_blocks;               // output-channel blocks (grid = m_tiles * n_blocks, N block fastest)
-  const float* bias;
-  int post_act;
-  const void* add; int add_dtype;
-  __nv_bfloat16* out_bf16;
-  float* out_f32;
-  int tma_store;              // 1: epilogue stages the tile in (swizzled) shared memory and TMA-stores it
-  int partial;                // 1: the last tile row of an image hangs over its bottom edge (bn == 1, bw == W): mask rows, direct stores
-  const void* mul; int mul_dtype, mul_mode;   // backward: out = (act(acc+bias) + add) * f(mul)
-  __nv_bfloat16* dact;        // taping forward: derivative of post_act at the pre-activation (bf16)
-  const float* act_slope;     // PReLU slopes [cout]
-  int act_after_add;          // act(acc + bias + add)
-  int round_tf32;             // fp32 output rounded to TF32 (feeds a kind::tf32 conv)
-};
 
 template <int BLOCK_N, int STAGES, bool GENERAL_ACT>
 __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 128 ? 4 : 2)) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -127,7 +105,7 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
     int stage = 0; uint32_t phase = 0;
     const int bk = (p.k32 || p.tf32) ? 32 : TC_BLOCK_K;
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (lane == 0) {
+      if (elect_one_sync()) {      // (not `lane == 0`: see tc_ptx.cuh -- uniform-datapath instructions issue directly under an elected lane)
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], p.k32 ? STAGE_BYTES / 2 : STAGE_BYTES);
         uint8_t* a_dst = smem_a + stage * a_stride;
@@ -153,7 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
     constexpr uint32_t idesc = make_idesc(TC_BLOCK_M, BLOCK_N);
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_a + stage * a_stride);
@@ -169,11 +147,9 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
             umma_bf16(tmem_base, make_smem_desc_sw64(a_addr + k * 32), make_smem_desc_sw64(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
         } else {
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32);
-            const uint64_t db = make_smem_desc(b_addr + k * 32);
-            umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k)      // K advance inside the swizzle atom: + 32 bytes = + 2 in the descriptor's low word
+            umma_bf16(tmem_base, smem_desc_from_lo(smem_desc_lo(a_addr) + k * 2), smem_desc_from_lo(smem_desc_lo(b_addr) + k * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);                     // smem slot free once these MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
@@ -192,189 +168,13 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
     asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier
     // GENERAL_ACT (compile time): PReLU slopes and/or act(acc + bias + add); the hot NVAE path compiles without it
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;
-    const int64_t pix = pix0 + row;
-    // partial tiles (H not a multiple of the tile's row count): rows past the image's last row were zero-filled by TMA, never stored
-    const bool row_ok = pix < p.M && (p.partial == 0 || row < (p.H - y0) * p.W);
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
-    const bool vec_ok = (p.cout & 7) == 0;
-    // staging tiles for the TMA store re-use the (now idle) operand ring: every MMA has retired, so every TMA load
-    // has landed and every operand read is done.  Layout = the SWIZZLE_128B box layout of the output tensor maps:
-    // 128-byte row panels (64 bf16 / 32 fp32 columns), 16-byte chunk index XOR (row & 7).
-    uint8_t* stage_b = smem;                                   // bf16: BLOCK_N/64 panels x 128 rows x 128 B
-    uint8_t* stage_f = smem + (p.out_bf16 != nullptr ? ((BLOCK_N + 63) / 64) * 16384 : 0);   // fp32: BLOCK_N/32 panels of 16 KB
-    uint8_t* stage_d = stage_f + (p.out_f32 != nullptr ? (BLOCK_N / 32) * 16384 : 0);               // bf16 dact panels
-    const uint32_t sw = (uint32_t)(row & 7);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const int nb = n_blk * BLOCK_N + c0;
-      if (nb >= p.cout) continue;                              // whole chunk beyond Cout (warp-uniform)
-      float v[16];
-      const int64_t off = pix * p.cout + nb;
-      const bool full = vec_ok && nb + 16 <= p.cout;
-      bool have_v = false;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-      if (p.dact != nullptr && (row_ok || p.tma_store)) {   // save act'(pre-activation) for the backward pass
-        float dv[16];
-        if (!GENERAL_ACT && p.post_act == GA_ACT_SILU) { silu_with_grad_fast_n<16>(v, v, dv); have_v = true; }   // one tanh for both, in place
-        else act_grad_fast_n<16>(v, dv, p.post_act);         // dact is bf16
-        if (p.tma_store) {
-          uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
-          const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
-          *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
-          *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
-        } else if (full) {
-          uint4* o = reinterpret_cast<uint4*>(p.dact + off);
-          o[0] = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
-          o[1] = make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.cout) p.dact[off + j] = __float2bfloat16_rn(dv[j]);
-        }
-      }
-      if (have_v) {
-      } else if (!GENERAL_ACT) {
-        apply_act_fast_n<16>(v, p.post_act);
-      } else if (!p.act_after_add) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j];
-      }
-      if (p.add != nullptr && row_ok) {
-        if (full) {
-          if (p.add_dtype == GA_F32) {
-            const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add) + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { float4 t = __ldg(a4 + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
-          } else {
-            const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add) + off);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4 t = __ldg(a4 + j);
-              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-                v[8 * j + 2 * k] += __low2float(h); v[8 * j + 2 * k + 1] += __high2float(h);
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.cout)
-              v[j] += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
-                                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
-        }
-      }
-      if (GENERAL_ACT && p.act_after_add) {
-        if (p.post_act == GA_ACT_PRELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j];
-        } else {
-          apply_act_fast_n<16>(v, p.post_act);
-        }
-      }
-      if (p.mul != nullptr && row_ok && full) {
-        float mv[16];
-        if (p.mul_dtype == GA_F32) {
-          const float4* m4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mul) + off);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { float4 t = __ldg(m4 + j); mv[4 * j] = t.x; mv[4 * j + 1] = t.y; mv[4 * j + 2] = t.z; mv[4 * j + 3] = t.w; }
-        } else {
-          const uint4* m4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mul) + off);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 t = __ldg(m4 + j);
-            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-              mv[8 * j + 2 * k] = __low2float(h); mv[8 * j + 2 * k + 1] = __high2float(h);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= mul_factor(mv[j], p.mul_mode);
-      } else if (p.mul != nullptr && row_ok) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (nb + j < p.cout) {
-            const float mv = (p.mul_dtype == GA_F32) ? __ldg(reinterpret_cast<const float*>(p.mul) + off + j)
-                                                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mul)[off + j]);
-            v[j] *= mul_factor(mv, p.mul_mode);
-          }
-        }
-      }
-      float vf[16];                                            // fp32 output values (TF32-rounded on request)
-#pragma unroll
-      for (int j = 0; j < 16; ++j) vf[j] = (p.round_tf32 && p.out_f32 != nullptr) ? round_tf32(v[j]) : v[j];
-      if (p.tma_store) {
-        if (p.out_bf16 != nullptr) {
-          uint8_t* panel = stage_b + (c0 >> 6) * (128 * 128) + row * 128;
-          const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
-          *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-        }
-        if (p.out_f32 != nullptr) {
-          uint8_t* panel = stage_f + (c0 >> 5) * (128 * 128) + row * 128;
-          const uint32_t k0 = (uint32_t)((c0 & 31) >> 2);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(vf[4 * j], vf[4 * j + 1], vf[4 * j + 2], vf[4 * j + 3]);
-        }
-      } else if (row_ok) {
-        if (full) {
-          if (p.out_bf16 != nullptr) {
-            uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + off);
-            o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-          }
-          if (p.out_f32 != nullptr) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = make_float4(vf[4 * j], vf[4 * j + 1], vf[4 * j + 2], vf[4 * j + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (nb + j >= p.cout) continue;
-            if (p.out_bf16 != nullptr) p.out_bf16[off + j] = __float2bfloat16_rn(v[j]);
-            if (p.out_f32 != nullptr) p.out_f32[off + j] = vf[j];
-          }
-        }
-      }
-    }
-    if (p.tma_store) {
-      // each epilogue warp stores its own 32-row slab: no cross-warp barrier; TMA clips rows >= M and cols >= Cout
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const int row0 = (int)(pix0 + q * 32);
-        if (p.out_bf16 != nullptr)
-          for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
-            tma_store_2d(&tmOutB, stage_b + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
-        if (p.out_f32 != nullptr)
-          for (int pn = 0; pn * 32 < BLOCK_N && n_blk * BLOCK_N + pn * 32 < p.cout; ++pn)
-            tma_store_2d(&tmOutF, stage_f + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 32, row0);
-        if (p.dact != nullptr)
-          for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
-            tma_store_2d(&tmOutD, stage_d + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
-        tma_store_commit();
-        tma_store_wait_read();       // smem must stay valid until the bulk stores have read it
-      }
-      __syncwarp();
-    }
+    // staging tiles for the TMA store re-use the (now idle) operand ring: every MMA has retired, so every TMA load has landed and
+    // every operand read is done
+    tc_epilogue_tile<BLOCK_N, GENERAL_ACT>(p, &tmOutB, &tmOutF, &tmOutD, tmem_base, n_blk, pix0, p.partial ? (p.H - y0) * p.W : 128, smem,
+                                           s_bias, s_slope, q, lane);
   }
   // ---- teardown: every tcgen05 op of this CTA is complete (the epilogue waited for the last commit)
   tc_fence_before();
@@ -385,21 +185,6 @@ __global__ void __launch_bounds__(TC_THREADS, BLOCK_N <= 64 ? 5 : (BLOCK_N == 12
 }
 
 // ----------------------------------------------------------------------------- host side
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_tmapEncodeTiled get_encode_fn() {
-  static PFN_tmapEncodeTiled fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
-  }
-  return fn;
-}
-
 struct TileGeom { int bw, bh, bn, tiles_x, tiles_y, partial; int64_t m_tiles; };
 
 static bool tile_geometry(int N, int H, int W, TileGeom* g) {
@@ -420,48 +205,33 @@ static bool tile_geometry(int N, int H, int W, TileGeom* g) {
 }
 
 static int encode_act_map(CUtensorMap* tm, const ga_tensor* t, const TileGeom& g, int stride = 1, int block_k = TC_BLOCK_K, int esize = 2) {
-  PFN_tmapEncodeTiled enc = get_encode_fn();
-  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
   cuuint64_t strides[3] = {(cuuint64_t)t->c * esize, (cuuint64_t)t->w * t->c * esize, (cuuint64_t)t->h * t->w * t->c * esize};
   // stride-2 convs: the box spans stride*bw x stride*bh input pixels and the TMA engine keeps every stride-th one
   // (ceil(box/elementStride) elements per dimension land in shared memory)
   cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)(g.bw * stride), (cuuint32_t)(g.bh * stride), (cuuint32_t)g.bn};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, block_k * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d box=%d,%d,%d) failed: %d", t->n, t->h, t->w, t->c,
-           g.bw, g.bh, g.bn, (int)r);
-  return 0;
+  return encode_tiled_cached(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box,
+                             estr, block_k * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
 static int encode_weight_map(CUtensorMap* tm, const void* w, int cout, int ktot, int block_n, int block_k = TC_BLOCK_K, int esize = 2) {
-  PFN_tmapEncodeTiled enc = get_encode_fn();
-  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
   cuuint64_t strides[1] = {(cuuint64_t)ktot * esize};
   cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, block_k * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight cout=%d k=%d box_n=%d) failed: %d", cout, ktot, block_n, (int)r);
-  return 0;
+  return encode_tiled_cached(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, estr,
+                             block_k * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
 static int encode_out_map(CUtensorMap* tm, void* base, int cout, int64_t m, int esize) {
-  PFN_tmapEncodeTiled enc = get_encode_fn();
-  GA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)m};
   cuuint64_t strides[1] = {(cuuint64_t)cout * esize};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esize), 32u};      // one 128-byte panel x one warp's 32 rows
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  GA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output cout=%d m=%lld esize=%d) failed: %d", cout, (long long)m, esize, (int)r);
-  return 0;
+  return encode_tiled_cached(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE);
 }
 
 template <int BLOCK_N, int STAGES, bool GENERAL_ACT>
@@ -553,12 +323,6 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   const int k32 = (!tf32 && k32_enabled && !in2 && (in->c % 64) == 32) ? 1 : 0;
   const int bk = (k32 || tf32) ? 32 : TC_BLOCK_K;
   const int esize = tf32 ? 4 : 2;
-  CUtensorMap tmA, tmA2, tmB;
-  if (encode_act_map(&tmA, in, g, d->stride, bk, esize)) return 1;
-  if (in2) { if (encode_act_map(&tmA2, in2, g)) return 1; }
-  else tmA2 = tmA;
-  if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n, bk, esize)) return 1;
-
   TcParams p;
   p.taps = taps; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
   p.k32 = k32; p.tf32 = tf32;
@@ -575,6 +339,17 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.act_slope = d->act_slope; p.act_after_add = d->act_after_add;
   p.round_tf32 = (out_f32 && round_tf32_enabled()) ? 1 : 0;
   GA_CHECK(d->post_act != GA_ACT_PRELU || d->act_slope != nullptr, "ga_conv2d_tc: PReLU needs act_slope");
+  // 3x3 stride-1 convolutions on 64-channel blocks: persistent halo-reuse kernel (conv3x3_tc.cu); -1 = shape not covered there
+  if (d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && !in2 && !tf32 && !k32) {
+    const int rc = conv3x3_halo_launch(in, d->weight, ktot, out_bf16, out_f32, p, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
+  CUtensorMap tmA, tmA2, tmB;
+  if (encode_act_map(&tmA, in, g, d->stride, bk, esize)) return 1;
+  if (in2) { if (encode_act_map(&tmA2, in2, g)) return 1; }
+  else tmA2 = tmA;
+  if (encode_weight_map(&tmB, d->weight, out->c, ktot, block_n, bk, esize)) return 1;
+
   p.n_blocks = (out->c + block_n - 1) / block_n;
   GA_CHECK(g.m_tiles * p.n_blocks < (int64_t)1 << 31, "ga_conv2d_tc: grid too large");
   dim3 grid((unsigned)(g.m_tiles * p.n_blocks));

@@ -1,0 +1,353 @@
+// Epilogue of the tcgen05 convolution kernels (conv_tc.cu, conv3x3_tc.cu): one 128-row x BLOCK_N accumulator tile
+//   TMEM -> registers -> + bias -> activation (+ saved derivative) -> + add -> * f(mul) -> bf16 / fp32 (TF32-rounded on request)
+//   -> swizzled staging tile in shared memory -> TMA store   (or direct vector stores for odd shapes / partial tiles).
+// Called by the 4 epilogue warps of a CTA (warp quadrant q = warp & 3 owns TMEM lanes 32q..32q+31 = tile rows).
+#pragma once
+#include "ga_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ga {
+
+struct TcParams {
+  int taps, kw, pad, stride;  // filter taps of source 1; stride 1 or 2 (TMA element strides do the decimation)
+  int k32;                    // 1: 32-channel K blocks (64-byte swizzle) for Cin = 32, 96, ...: no half-empty 64-channel boxes
+  int tf32;                   // 1: fp32 activations and weights, kind::tf32 MMA, 32-channel K blocks (32 x 4 B = one 128-byte swizzle row)
+  int cin, kc1, kc2;          // channels of source 1, its 64-blocks per tap, 64-blocks of source 2
+  int bw, bh, bn;             // pixel box of one M tile (bw*bh*bn == 128)
+  int tiles_x, tiles_y;       // tiles per image row / column (bn == 1) -- else whole images per tile
+  int H, W;
+  int64_t M;                  // total output pixels
+  int cout;
+  int n_blocks;               // output-channel blocks (grid = m_tiles * n_blocks, N block fastest)
+  const float* bias;
+  int post_act;
+  const void* add; int add_dtype;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  int tma_store;              // 1: epilogue stages the tile in (swizzled) shared memory and TMA-stores it
+  int partial;                // 1: the last tile row of an image hangs over its bottom edge (bn == 1, bw == W): mask rows, direct stores
+  const void* mul; int mul_dtype, mul_mode;   // backward: out = (act(acc+bias) + add) * f(mul)
+  __nv_bfloat16* dact;        // taping forward: derivative of post_act at the pre-activation (bf16)
+  const float* act_slope;     // PReLU slopes [cout]
+  int act_after_add;          // act(acc + bias + add)
+  int round_tf32;             // fp32 output rounded to TF32 (feeds a kind::tf32 conv)
+};
+
+// conv3x3_tc.cu: persistent halo-reuse kernel for 3x3 / stride 1 / pad 1; -> 0 launched, 1 error, -1 shape not covered
+int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
+                        cudaStream_t s);
+
+// tmem_acc: TMEM address (lane 0) of column 0 of the accumulator; pix0: global index of the tile's first output pixel; row_limit: rows of
+// the tile that exist (128, or fewer for the partial last tile row of an image); stage: 1024-aligned staging memory (TMA-store mode);
+// s_bias / s_slope: BLOCK_N floats each in shared memory (bias and PReLU slopes of this N block).
+// DEFER_STORE_WAIT: return without waiting for the bulk stores to have read the staging tile (the caller waits before re-using it).
+// LD_COLS: accumulator columns fetched per tcgen05.ld round trip.  A round trip costs ~1k cycles while the tensor pipe is busy (measured: the
+// persistent 3x3 kernel spent 1000 clk per 16-column chunk); a kernel with few resident warps must put many columns in flight per wait.
+template <int BLOCK_N, bool GENERAL_ACT, bool DEFER_STORE_WAIT = false, int LD_COLS = 16>
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const CUtensorMap* tmOutB, const CUtensorMap* tmOutF,
+                                                 const CUtensorMap* tmOutD, uint32_t tmem_acc, int n_blk, int64_t pix0, int row_limit,
+                                                 uint8_t* stage, const float* s_bias, const float* s_slope, int q, int lane) {
+  const int row = q * 32 + lane;
+  const int64_t pix = pix0 + row;
+  // partial tiles (H not a multiple of the tile's row count): rows past the image's last row were zero-filled by TMA, never stored
+  const bool row_ok = pix < p.M && row < row_limit;
+  const bool vec_ok = (p.cout & 7) == 0;
+  // staging tiles for the TMA store re-use the (now idle) operand ring: every MMA has retired, so every TMA load
+  // has landed and every operand read is done.  Layout = the SWIZZLE_128B box layout of the output tensor maps:
+  // 128-byte row panels (64 bf16 / 32 fp32 columns), 16-byte chunk index XOR (row & 7).
+  uint8_t* stage_b = stage;                                  // bf16: BLOCK_N/64 panels x 128 rows x 128 B
+  uint8_t* stage_f = stage + (p.out_bf16 != nullptr ? ((BLOCK_N + 63) / 64) * 16384 : 0);   // fp32: BLOCK_N/32 panels of 16 KB
+  uint8_t* stage_d = stage_f + (p.out_f32 != nullptr ? (BLOCK_N / 32) * 16384 : 0);               // bf16 dact panels
+  const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll 1
+  for (int cg = 0; cg < BLOCK_N; cg += LD_COLS) {
+  uint32_t rr[LD_COLS / 16][16];
+#pragma unroll
+  for (int i = 0; i < LD_COLS / 16; ++i)
+    if (cg + i * 16 < BLOCK_N) tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg + i * 16), rr[i]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int ci = 0; ci < LD_COLS / 16; ++ci) {
+    const int c0 = cg + ci * 16;
+    if (c0 >= BLOCK_N) break;
+    uint32_t (&r)[16] = rr[ci];
+    const int nb = n_blk * BLOCK_N + c0;
+    if (nb >= p.cout) continue;                              // whole chunk beyond Cout (warp-uniform)
+    float v[16];
+    const int64_t off = pix * p.cout + nb;
+    const bool full = vec_ok && nb + 16 <= p.cout;
+    bool have_v = false;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+    if (p.dact != nullptr && (row_ok || p.tma_store)) {   // save act'(pre-activation) for the backward pass
+      float dv[16];
+      if (!GENERAL_ACT && p.post_act == GA_ACT_SILU) { silu_with_grad_fast_n<16>(v, v, dv); have_v = true; }   // one tanh for both, in place
+      else act_grad_fast_n<16>(v, dv, p.post_act);         // dact is bf16
+      if (p.tma_store) {
+        uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
+        const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
+        *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+        *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
+      } else if (full) {
+        uint4* o = reinterpret_cast<uint4*>(p.dact + off);
+        o[0] = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+        o[1] = make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.cout) p.dact[off + j] = __float2bfloat16_rn(dv[j]);
+      }
+    }
+    if (have_v) {
+    } else if (!GENERAL_ACT) {
+      apply_act_fast_n<16>(v, p.post_act);
+    } else if (!p.act_after_add) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j];
+    }
+    if (p.add != nullptr && row_ok) {
+      if (full) {
+        if (p.add_dtype == GA_F32) {
+          const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { float4 t = __ldg(a4 + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+        } else {
+          const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add) + off);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 t = __ldg(a4 + j);
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+              v[8 * j + 2 * k] += __low2float(h); v[8 * j + 2 * k + 1] += __high2float(h);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.cout)
+            v[j] += (p.add_dtype == GA_F32) ? reinterpret_cast<const float*>(p.add)[off + j]
+                                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[off + j]);
+      }
+    }
+    if (GENERAL_ACT && p.act_after_add) {
+      if (p.post_act == GA_ACT_PRELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : s_slope[c0 + j] * v[j];
+      } else {
+        apply_act_fast_n<16>(v, p.post_act);
+      }
+    }
+    if (p.mul != nullptr && row_ok && full) {
+      float mv[16];
+      if (p.mul_dtype == GA_F32) {
+        const float4* m4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mul) + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float4 t = __ldg(m4 + j); mv[4 * j] = t.x; mv[4 * j + 1] = t.y; mv[4 * j + 2] = t.z; mv[4 * j + 3] = t.w; }
+      } else {
+        const uint4* m4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mul) + off);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint4 t = __ldg(m4 + j);
+          const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+            mv[8 * j + 2 * k] = __low2float(h); mv[8 * j + 2 * k + 1] = __high2float(h);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= mul_factor(mv[j], p.mul_mode);
+    } else if (p.mul != nullptr && row_ok) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (nb + j < p.cout) {
+          const float mv = (p.mul_dtype == GA_F32) ? __ldg(reinterpret_cast<const float*>(p.mul) + off + j)
+                                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mul)[off + j]);
+          v[j] *= mul_factor(mv, p.mul_mode);
+        }
+      }
+    }
+    float vf[16];                                            // fp32 output values (TF32-rounded on request)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vf[j] = (p.round_tf32 && p.out_f32 != nullptr) ? round_tf32(v[j]) : v[j];
+    if (p.tma_store) {
+      if (p.out_bf16 != nullptr) {
+        uint8_t* panel = stage_b + (c0 >> 6) * (128 * 128) + row * 128;
+        const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
+        *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      }
+      if (p.out_f32 != nullptr) {
+        uint8_t* panel = stage_f + (c0 >> 5) * (128 * 128) + row * 128;
+        const uint32_t k0 = (uint32_t)((c0 & 31) >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(vf[4 * j], vf[4 * j + 1], vf[4 * j + 2], vf[4 * j + 3]);
+      }
+    } else if (row_ok) {
+      if (full) {
+        if (p.out_bf16 != nullptr) {
+          uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + off);
+          o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        }
+        if (p.out_f32 != nullptr) {
+          float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(vf[4 * j], vf[4 * j + 1], vf[4 * j + 2], vf[4 * j + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (nb + j >= p.cout) continue;
+          if (p.out_bf16 != nullptr) p.out_bf16[off + j] = __float2bfloat16_rn(v[j]);
+          if (p.out_f32 != nullptr) p.out_f32[off + j] = vf[j];
+        }
+      }
+    }
+  }
+  }
+  if (p.tma_store) {
+    // each epilogue warp stores its own 32-row slab: no cross-warp barrier; TMA clips rows >= M and cols >= Cout
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const int row0 = (int)(pix0 + q * 32);
+      if (p.out_bf16 != nullptr)
+        for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
+          tma_store_2d(tmOutB, stage_b + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
+      if (p.out_f32 != nullptr)
+        for (int pn = 0; pn * 32 < BLOCK_N && n_blk * BLOCK_N + pn * 32 < p.cout; ++pn)
+          tma_store_2d(tmOutF, stage_f + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 32, row0);
+      if (p.dact != nullptr)
+        for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
+          tma_store_2d(tmOutD, stage_d + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
+      tma_store_commit();
+      if (!DEFER_STORE_WAIT) tma_store_wait_read();       // smem must stay valid until the bulk stores have read it
+    }
+    __syncwarp();
+  }
+}
+
+// Lean epilogue for the persistent kernel's hot cases: out = act(acc + bias) with act in {none, SiLU, ReLU}, optional SiLU' tape, bf16 and / or
+// fp32 output through the TMA-store staging tile; no add / mul / PReLU.  Every uniform decision is taken ONCE per tile (the generic
+// epilogue re-decides per 16-column chunk: ~1000 clk per chunk when the warp has its scheduler to itself, and 140 KB of code), and all
+// accumulator columns of the tile (up to 64 at a time) are in flight before the single tcgen05.wait.
+__host__ __device__ __forceinline__ bool tc_epilogue_is_lean(const TcParams& p) {
+  return p.add == nullptr && p.mul == nullptr && p.act_after_add == 0 && p.tma_store != 0 && p.round_tf32 == 0 &&
+         (p.post_act == GA_ACT_NONE || p.post_act == GA_ACT_SILU || p.post_act == GA_ACT_RELU) &&
+         (p.dact == nullptr || p.post_act == GA_ACT_SILU);
+}
+
+template <int BLOCK_N, int ACT, bool DACT, bool OUT_B, bool OUT_F>
+__device__ __forceinline__ void tc_epilogue_lean_body(const TcParams& p, uint32_t tmem_acc, int n_blk, uint8_t* stage, const float* s_bias,
+                                                      int q, int lane) {
+  constexpr int LD = BLOCK_N < 64 ? BLOCK_N : 64;
+  const int row = q * 32 + lane;
+  uint8_t* stage_b = stage;
+  uint8_t* stage_f = stage + (OUT_B ? ((BLOCK_N + 63) / 64) * 16384 : 0);
+  uint8_t* stage_d = stage_f + (OUT_F ? (BLOCK_N / 32) * 16384 : 0);
+  const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+  for (int cg = 0; cg < BLOCK_N; cg += LD) {
+    uint32_t rr[LD / 16][16];
+#pragma unroll
+    for (int i = 0; i < LD / 16; ++i) tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg + i * 16), rr[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int ci = 0; ci < LD / 16; ++ci) {
+      const int c0 = cg + ci * 16;
+      if (n_blk * BLOCK_N + c0 >= p.cout) continue;             // whole chunk beyond Cout (warp-uniform)
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[ci][j]) + s_bias[c0 + j];
+      if (ACT == GA_ACT_SILU) {
+        if (DACT) {
+          float dv[16];
+          silu_with_grad_fast_n<16>(v, v, dv);
+          uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
+          const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
+          *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+          *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
+        }
+      } else if (ACT == GA_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+      if (OUT_B) {
+        uint8_t* panel = stage_b + (c0 >> 6) * (128 * 128) + row * 128;
+        const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
+        *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      }
+      if (OUT_F) {
+        uint8_t* panel = stage_f + (c0 >> 5) * (128 * 128) + row * 128;
+        const uint32_t k0 = (uint32_t)((c0 & 31) >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+}
+
+// -> issues the bulk stores of this warp's 32-row slab and commits them; the CALLER waits (cp.async.bulk.wait_group.read) before the slab is
+// written again.  Same staging layout and store boxes as tc_epilogue_tile.
+template <int BLOCK_N>
+__device__ __forceinline__ void tc_epilogue_lean(const TcParams& p, const CUtensorMap* tmOutB, const CUtensorMap* tmOutF,
+                                                 const CUtensorMap* tmOutD, uint32_t tmem_acc, int n_blk, int64_t pix0, uint8_t* stage,
+                                                 const float* s_bias, int q, int lane) {
+  const bool ob = p.out_bf16 != nullptr, of = p.out_f32 != nullptr;
+  if (p.post_act == GA_ACT_SILU) {
+    if (p.dact != nullptr) {
+      if (of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, true, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);   // (bf16 + fp32 + tape; the engines never ask for fp32 + tape alone)
+      else tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, true, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    } else if (ob && of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, false, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    else if (ob) tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, false, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    else tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, false, false, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+  } else if (p.post_act == GA_ACT_RELU) {
+    if (ob && of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_RELU, false, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    else if (ob) tc_epilogue_lean_body<BLOCK_N, GA_ACT_RELU, false, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    else tc_epilogue_lean_body<BLOCK_N, GA_ACT_RELU, false, false, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+  } else {
+    if (ob && of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_NONE, false, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    else if (ob) tc_epilogue_lean_body<BLOCK_N, GA_ACT_NONE, false, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    else tc_epilogue_lean_body<BLOCK_N, GA_ACT_NONE, false, false, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+  }
+  uint8_t* stage_b = stage;
+  uint8_t* stage_f = stage + (ob ? ((BLOCK_N + 63) / 64) * 16384 : 0);
+  uint8_t* stage_d = stage_f + (of ? (BLOCK_N / 32) * 16384 : 0);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    const int row0 = (int)(pix0 + q * 32);
+    if (ob)
+      for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
+        tma_store_2d(tmOutB, stage_b + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
+    if (of)
+      for (int pn = 0; pn * 32 < BLOCK_N && n_blk * BLOCK_N + pn * 32 < p.cout; ++pn)
+        tma_store_2d(tmOutF, stage_f + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 32, row0);
+    if (p.dact != nullptr)
+      for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
+        tma_store_2d(tmOutD, stage_d + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
+    tma_store_commit();
+  }
+  __syncwarp();
+}
+
+}  // namespace ga

@@ -8,6 +8,21 @@ namespace ga {
 // ----------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp (cute::elect_one_sync): the compiler knows that code guarded by this predicate runs in exactly one thread and
+// issues the uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) directly; guarding them with `lane == 0` instead wraps EVERY such
+// instruction in an elect / branch loop (~10 extra instructions per MMA: the single issuing thread became the bottleneck)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -95,6 +110,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// The same descriptor split into its two 32-bit words: the high word is a constant, the low word is (address >> 4) | LBO -- advancing the
+// operand by `bytes` is ONE 32-bit add of bytes >> 4 (shared addresses stay below 256 KB, so the 14-bit field cannot carry).  The MMA
+// issuer is a single thread: rebuilding the 64-bit descriptor with shifts and ORs for every instruction made it the bottleneck of the
+// persistent 3x3 kernel (measured 81 clk per N = 64 MMA instead of the ~48 the operand reads need).
+constexpr uint32_t SMEM_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint64_t smem_desc_from_lo(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(SMEM_DESC_HI_SW128));
   return d;
 }
 // 64-byte swizzle variant (32 bf16 per row): 8-row atoms of 512 B, layout type 4 (cute::UMMA::LayoutType::SWIZZLE_64B)

@@ -126,6 +126,10 @@ int ga_dwconv5x5_ex(const ga_tensor* in, const ga_tensor* mul, const float* weig
 int ga_mbconv_fused_supported(const ga_tensor* x, int hidden);
 int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
                     const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, void* stream);
+/* debug only: per-role clock64 timeline of the 32x32 fused decoder cell; buf = device uint64[8*13*24*8] or NULL (off) */
+int ga_debug_mbconv_trace(unsigned long long* buf);
+/* debug only: clock64 timeline of CTA 0 of the persistent 3x3 kernel; buf = device uint64[3*16*16] or NULL (off) */
+int ga_debug_c3_trace(unsigned long long* buf);
 
 /* ---- squeeze-excite + residual (architecture.py:37-61,128-136,178-186) */
 /* sums is [n][ga_channel_sum_parts(n, h*w)][c] partial sums (two-stage, no atomics: bit-reproducible) */

@@ -131,6 +131,48 @@ def test_conv_tc_bf16(case):
     assert e16 <= 1e-2 * scale, ("bf16 out", e16, scale)
 
 
+HALO_CASES = [
+    # persistent halo-reuse kernel (conv3x3_tc.cu): n, h, w, cin, cout, post, add, mul_mode (None = no mul), want (bf16, f32), dact
+    (40, 32, 32, 64, 64, ACT_SILU, None, None, (True, False), True),      # encoder conv1, taping: 160 tiles > 148 CTAs, resident weights
+    (150, 16, 16, 128, 128, ACT_NONE, None, None, (True, False), False),  # 150 tiles, streaming weights, two K blocks
+    (37, 32, 32, 64, 128, ACT_RELU, None, None, (True, True), False),     # VGG-like: both outputs
+    (20, 16, 16, 128, 256, ACT_RELU, None, None, (False, True), False),   # two N blocks
+    (9, 16, 16, 256, 256, ACT_NONE, "f32", None, (False, True), False),   # four K blocks, + add
+    (6, 64, 64, 64, 64, ACT_NONE, None, None, (True, False), False),      # W = 64: 4-row tiles
+    (3, 32, 32, 64, 20, ACT_NONE, None, None, (False, True), False),      # sampler: 20 output channels, fp32 only
+    (5, 32, 32, 128, 64, ACT_NONE, "f32", 0, (False, True), False),       # dgrad style: (conv + add) * mul, fp32 gradient out
+    (5, 16, 16, 128, 128, ACT_NONE, None, 1, (True, False), False),       # VGG backward: times ReLU mask of mul
+    (1, 32, 32, 64, 64, ACT_SILU, None, None, (True, False), False),      # fewer tiles than SMs
+    (300, 8, 32, 64, 64, ACT_NONE, None, None, (True, False), False),     # H = 8: one tile per image, 300 tiles
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3x3_halo_kernel(case):
+    n, h, w, cin, cout, post, addk, mul_mode, (wb, wf), want_dact = case
+    L = _layer(cin, cout, 3, 1, 1, PRE_NONE, post, tc=True, seed=cin + cout + n)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16)
+    add = torch.randn(n, h, w, cout, generator=g) if addk == "f32" else None
+    mul = torch.randn(n, h, w, cout, generator=g).to(torch.bfloat16) if mul_mode is not None else None
+    LD = _to_dev(L)
+    dref = torch.empty(n, h, w, cout) if want_dact else None
+    _, ref = emu_ops.conv2d_tc(x, L, want_bf16=False, want_f32=True, add=add, mul=mul, mul_mode=mul_mode or 0, dact_out=dref)
+    dgot = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16) if want_dact else None
+    ob, of = ops.conv2d_tc(x.to(DEV), LD, want_bf16=wb, want_f32=wf, add=add.to(DEV) if add is not None else None,
+                           mul=mul.to(DEV) if mul is not None else None, mul_mode=mul_mode or 0, dact_out=dgot)
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    if wf:
+        e32 = (of.cpu() - ref).abs().max().item()
+        assert e32 <= 2e-3 * scale, ("fp32 out", e32, scale)
+    if wb:
+        e16 = (ob.float().cpu() - ref).abs().max().item()
+        assert e16 <= 1e-2 * scale, ("bf16 out", e16, scale)
+    if want_dact:
+        assert (dgot.float().cpu() - dref).abs().max().item() <= 2e-2
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,k,stride,act", [(2, 32, 32, 64, 64, 3, 1, ACT_NONE), (3, 16, 16, 128, 256, 3, 2, ACT_NONE),
                                                         (2, 64, 64, 64, 128, 1, 2, ACT_NONE), (4, 8, 8, 512, 512, 3, 1, ACT_SILU),
                                                         (2, 128, 128, 64, 64, 3, 1, ACT_NONE), (1, 32, 32, 40, 72, 3, 1, ACT_RELU)])
