@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BLOCK_N, bool RESIDENT_W, int EPI>      // EPI 0: lean epilogue, 1: generic, 2: generic with PReLU / act-after-add
+template <int BLOCK_N, bool RESIDENT_W, int EPI>      // EPI 0: lean epilogue, 1: generic, 2: generic with PReLU / act-after-add, 3: lean + add / mul
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmOutB,
@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         if (EPI == 0)
           tc_epilogue_lean<BLOCK_N>(p, &tmOutB, &tmOutF, &tmOutD, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
                                     (int64_t)mt * 256 + s * 128, s_stage, s_bias + n_blk * BLOCK_N, q, lane);
+        else if (EPI == 3)
+          tc_epilogue_lean_am<BLOCK_N>(p, &tmOutB, &tmOutF, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
+                                       (int64_t)mt * 256 + s * 128, s_stage, s_bias + n_blk * BLOCK_N, q, lane);
         else
           tc_epilogue_tile<BLOCK_N, GENERAL_ACT, true>(p, &tmOutB, &tmOutF, &tmOutD, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
                                                        (int64_t)mt * 256 + s * 128, 128, s_stage, s_bias + n_blk * BLOCK_N,
@@ -246,22 +249,24 @@ static int launch_c3(bool resident, int epi, const CUtensorMap& a, const CUtenso
   if (resident) {
     if (epi == 0) return launch_c3_<BLOCK_N, true, 0>(a, b, ob, of, od, p, c, smem, grid, s);
     if (epi == 1) return launch_c3_<BLOCK_N, true, 1>(a, b, ob, of, od, p, c, smem, grid, s);
+    if (epi == 3) return launch_c3_<BLOCK_N, true, 3>(a, b, ob, of, od, p, c, smem, grid, s);
     return launch_c3_<BLOCK_N, true, 2>(a, b, ob, of, od, p, c, smem, grid, s);
   }
   if (epi == 0) return launch_c3_<BLOCK_N, false, 0>(a, b, ob, of, od, p, c, smem, grid, s);
   if (epi == 1) return launch_c3_<BLOCK_N, false, 1>(a, b, ob, of, od, p, c, smem, grid, s);
+  if (epi == 3) return launch_c3_<BLOCK_N, false, 3>(a, b, ob, of, od, p, c, smem, grid, s);
   return launch_c3_<BLOCK_N, false, 2>(a, b, ob, of, od, p, c, smem, grid, s);
 }
 
 static unsigned long long* g_c3_trace = nullptr;
+static int g_halo_enabled = -1;     // GA_TC_HALO / ga_tc_halo_enable: 0 routes every 3x3 conv through the per-tap kernel (A/B comparisons)
 
 // Called by ga_conv2d_tc (conv_tc.cu) with a fully prepared TcParams (epilogue fields, cout, n_blocks unset).
 // -> 0 launched, 1 error, -1 not applicable (the caller goes on with the per-tap kernel).
 int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
                         cudaStream_t s) {
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("GA_TC_HALO"); enabled = e ? atoi(e) : 1; }
-  if (!enabled) return -1;
+  if (g_halo_enabled < 0) { const char* e = getenv("GA_TC_HALO"); g_halo_enabled = e ? atoi(e) : 1; }
+  if (!g_halo_enabled) return -1;
   const ga_tensor* out = out_bf16 ? out_bf16 : out_f32;
   const int W = in->w, H = in->h, cin = in->c, cout = out->c;
   if (cin % 64 != 0 || W % 8 != 0 || W > 128 || 256 % W != 0) return -1;
@@ -333,7 +338,8 @@ int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const
   const bool general = p.act_after_add != 0 || p.post_act == GA_ACT_PRELU;
   static int lean_enabled = -1;
   if (lean_enabled < 0) { const char* e = getenv("GA_TC_LEAN"); lean_enabled = e ? atoi(e) : 1; }
-  const int epi = general ? 2 : ((lean_enabled && tc_epilogue_is_lean(p) && !(p.dact && out_f32 && !out_bf16)) ? 0 : 1);
+  const int epi = general ? 2 : ((lean_enabled && tc_epilogue_is_lean(p) && !(p.dact && out_f32 && !out_bf16)) ? 0 :
+                                 ((lean_enabled && tc_epilogue_is_lean_am(p)) ? 3 : 1));
   const int grid = c.n_tiles < sm_count() ? c.n_tiles : sm_count();
   switch (block_n) {
     case 32: return launch_c3<32>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);
@@ -347,5 +353,11 @@ int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const
 // debug: clock64 timeline of CTA 0 of the halo kernel (scripts/trace_conv3x3.py); buf = device uint64[3 * 16 * 16] or NULL (off)
 extern "C" int ga_debug_c3_trace(unsigned long long* buf) {
   ga::g_c3_trace = buf;
+  return 0;
+}
+
+// debug / A-B testing: 1 = persistent halo kernel for the shapes it covers (default), 0 = per-tap kernel everywhere
+extern "C" int ga_tc_halo_enable(int on) {
+  ga::g_halo_enabled = on ? 1 : 0;
   return 0;
 }

@@ -350,4 +350,143 @@ __device__ __forceinline__ void tc_epilogue_lean(const TcParams& p, const CUtens
   __syncwarp();
 }
 
+// Lean epilogue with the backward-pass extras: out = (act(acc + bias) + add) * f(mul), add / mul tensors of the output's shape in fp32 or
+// bf16.  Each thread owns one output row: its add / mul values of the whole 64-column group are fetched with 16-byte loads BEFORE the
+// tcgen05.wait, so the global-load latency overlaps the TMEM round trip (the generic epilogue loads them per 16-column chunk, after the math).
+__host__ __device__ __forceinline__ bool tc_epilogue_is_lean_am(const TcParams& p) {
+  return (p.add != nullptr || p.mul != nullptr) && p.act_after_add == 0 && p.tma_store != 0 && p.round_tf32 == 0 && p.dact == nullptr &&
+         p.post_act != GA_ACT_PRELU && (p.cout % 16) == 0;
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ void tc_epilogue_lean_am(const TcParams& p, const CUtensorMap* tmOutB, const CUtensorMap* tmOutF, uint32_t tmem_acc,
+                                                    int n_blk, int64_t pix0, uint8_t* stage, const float* s_bias, int q, int lane) {
+  constexpr int LD = BLOCK_N < 64 ? BLOCK_N : 64;
+  const int row = q * 32 + lane;
+  const int64_t pix = pix0 + row;
+  const bool ob = p.out_bf16 != nullptr, of = p.out_f32 != nullptr;
+  const bool has_add = p.add != nullptr, add_f32 = p.add_dtype == GA_F32;
+  const bool has_mul = p.mul != nullptr, mul_f32 = p.mul_dtype == GA_F32;
+  uint8_t* stage_b = stage;
+  uint8_t* stage_f = stage + (ob ? ((BLOCK_N + 63) / 64) * 16384 : 0);
+  const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll 1
+  for (int cg = 0; cg < BLOCK_N; cg += LD) {
+    const int nb0 = n_blk * BLOCK_N + cg;
+    if (nb0 >= p.cout) break;
+    uint32_t rr[LD / 16][16];
+#pragma unroll
+    for (int i = 0; i < LD / 16; ++i) tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg + i * 16), rr[i]);
+    // columns of this group that exist (cout is a multiple of 16): nv 16-column chunks
+    const int nv = (p.cout - nb0) >= LD ? LD / 16 : (p.cout - nb0) / 16;
+    uint4 abuf[LD / 4], mbuf[LD / 4];                         // raw add / mul values: fp32 fills LD/4 vectors, bf16 the first LD/8
+    const int64_t off = pix * p.cout + nb0;
+    if (has_add) {
+      if (add_f32) {
+        const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.add) + off);
+#pragma unroll
+        for (int i = 0; i < LD / 4; ++i) if (i < nv * 4) abuf[i] = __ldg(a4 + i);
+      } else {
+        const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add) + off);
+#pragma unroll
+        for (int i = 0; i < LD / 8; ++i) if (i < nv * 2) abuf[i] = __ldg(a4 + i);
+      }
+    }
+    if (has_mul) {
+      if (mul_f32) {
+        const uint4* m4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.mul) + off);
+#pragma unroll
+        for (int i = 0; i < LD / 4; ++i) if (i < nv * 4) mbuf[i] = __ldg(m4 + i);
+      } else {
+        const uint4* m4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mul) + off);
+#pragma unroll
+        for (int i = 0; i < LD / 8; ++i) if (i < nv * 2) mbuf[i] = __ldg(m4 + i);
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int ci = 0; ci < LD / 16; ++ci) {
+      if (ci >= nv) break;
+      const int c0 = cg + ci * 16;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[ci][j]) + s_bias[c0 + j];
+      apply_act_fast_n<16>(v, p.post_act);
+      if (has_add) {
+        if (add_f32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 t = abuf[ci * 4 + j];
+            v[4 * j] += __uint_as_float(t.x); v[4 * j + 1] += __uint_as_float(t.y); v[4 * j + 2] += __uint_as_float(t.z); v[4 * j + 3] += __uint_as_float(t.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 t = abuf[ci * 2 + j];
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[8 * j + 2 * k] += __uint_as_float(w[k] << 16); v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u); }
+          }
+        }
+      }
+      if (has_mul) {
+        float mv[16];
+        if (mul_f32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 t = mbuf[ci * 4 + j];
+            mv[4 * j] = __uint_as_float(t.x); mv[4 * j + 1] = __uint_as_float(t.y); mv[4 * j + 2] = __uint_as_float(t.z); mv[4 * j + 3] = __uint_as_float(t.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 t = mbuf[ci * 2 + j];
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { mv[8 * j + 2 * k] = __uint_as_float(w[k] << 16); mv[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+          }
+        }
+        if (p.mul_mode == GA_MUL_RELU_MASK) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = mv[j] > 0.0f ? v[j] : 0.0f;
+        } else if (p.mul_mode == GA_MUL_ELU_FROM_Y) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= (mv[j] > 0.0f ? 1.0f : mv[j] + 1.0f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= mv[j];
+        }
+      }
+      if (ob) {
+        uint8_t* panel = stage_b + (c0 >> 6) * (128 * 128) + row * 128;
+        const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
+        *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      }
+      if (of) {
+        uint8_t* panel = stage_f + (c0 >> 5) * (128 * 128) + row * 128;
+        const uint32_t k0 = (uint32_t)((c0 & 31) >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    const int row0 = (int)(pix0 + q * 32);
+    if (ob)
+      for (int pn = 0; pn * 64 < BLOCK_N && n_blk * BLOCK_N + pn * 64 < p.cout; ++pn)
+        tma_store_2d(tmOutB, stage_b + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 64, row0);
+    if (of)
+      for (int pn = 0; pn * 32 < BLOCK_N && n_blk * BLOCK_N + pn * 32 < p.cout; ++pn)
+        tma_store_2d(tmOutF, stage_f + pn * (128 * 128) + q * 32 * 128, n_blk * BLOCK_N + pn * 32, row0);
+    tma_store_commit();
+  }
+  __syncwarp();
+}
+
 }  // namespace ga

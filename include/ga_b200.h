@@ -130,6 +130,8 @@ int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, cons
 int ga_debug_mbconv_trace(unsigned long long* buf);
 /* debug only: clock64 timeline of CTA 0 of the persistent 3x3 kernel; buf = device uint64[3*16*16] or NULL (off) */
 int ga_debug_c3_trace(unsigned long long* buf);
+/* A/B testing: 1 = persistent halo-reuse 3x3 kernel where it applies (default), 0 = per-tap kernel everywhere */
+int ga_tc_halo_enable(int on);
 
 /* ---- squeeze-excite + residual (architecture.py:37-61,128-136,178-186) */
 /* sums is [n][ga_channel_sum_parts(n, h*w)][c] partial sums (two-stage, no atomics: bit-reproducible) */
