@@ -59,8 +59,6 @@ class NvaeEngine:
                  temperature: float = 0.6, _host_logic_test: bool = False):
         if mode not in ("fp32", "bf16"):
             raise ValueError(f"unknown mode {mode}")
-        if spec.use_nf:
-            raise NotImplementedError("normalizing-flow cells are not supported")
         self.spec = spec
         self.device = torch.device(device)
         if self.device.type != "cuda" and not _host_logic_test:   # (tests/emu_ops.py drives the host logic on CPU)
@@ -126,6 +124,16 @@ class NvaeEngine:
             d.skip = f.conv(ws, bs, name=p + ".skip")
         return d
 
+    @staticmethod
+    def _nf_shift(f: Folder, cells, z: int) -> torch.Tensor:
+        shift = torch.zeros(z, dtype=torch.float64)
+        for q, _ in cells:
+            w_last = f.f64(f"{q}.4.weight") * f.f64(f"{q}.4.mask")
+            if float(w_last.abs().max()) != 0.0:
+                raise NotImplementedError(f"NF cell {q}: the 1x1 conv has surviving taps (a mask the reference's MaskedConv2d cannot produce)")
+            shift += f.f64(f"{q}.4.bias")
+        return shift
+
     def _fold(self, f: Folder):
         spec = self.spec
         w, b = f.wn("preprocessing_block.init_conv")
@@ -149,6 +157,12 @@ class NvaeEngine:
             wx = w[:, :c]
             wz = torch.zeros((c, self.zc), dtype=torch.float64)
             wz[:, :z] = w[:, c:, 0, 0]
+            if spec.use_nf:
+                # normalizing-flow cells (architecture.py:221-253, applied at models.py:209-210,253-254): NFCell(z) = z - layers(z), and the
+                # LAST layer of every cell is a MaskedConv2d 1x1 whose mask keeps (1*1)//2 = 0 taps (architecture.py:17-24): its weight is
+                # all zero, layers(z) is that conv's bias, and a chain of cells subtracts a per-channel constant from z.  z only feeds
+                # the decoder combiner's 1x1 conv, so the shift folds exactly into that conv's bias: b' = b - Wz . sum(bias_last).
+                b = b - wz[:, :z] @ self._nf_shift(f, spec.nf_cells_of(lvl.s, lvl.g), z)
             L["dec_comb"] = f.conv(wx, b, name=f"dec_comb_{lvl.s}:{lvl.g}", w2=wz)
             L["dec_comb_z"] = f.conv(wz.view(c, self.zc, 1, 1), None, name=f"dec_comb_z_{lvl.s}:{lvl.g}")
             if not (lvl.s == 0 and lvl.g == 0):

@@ -249,8 +249,37 @@ class NvaeSpec:
             self._se(sd, f"{p}.residual.{9 + o}", cell.cout)
         self._wn_conv(sd, "to_logits.1", self.logit_channels, self.out_channels, 3)
         if self.use_nf:
-            raise NotImplementedError("normalizing-flow cells (num_nf_cells != None) are not supported yet")
+            # NVAE/model.py:216-221: one nn.Sequential of `num_nf_cells` NFBlocks per latent level; NFBlock = cell1 (mirror False) +
+            # cell2 (mirror True); NFCell.layers = [MaskedConv2d 3x3 z -> 6z, ELU, MaskedConv2d dw5x5, ELU, MaskedConv2d 1x1 6z -> z]
+            # (architecture.py:221-253); every MaskedConv2d registers its `mask` as a buffer (:9-28)
+            z, hz = self.z, 6 * self.z
+            for lvl in self.levels:
+                for n in range(self.num_nf_cells):
+                    for cell in ("cell1", "cell2"):
+                        q = f"nf_cells.nf_{lvl.s}:{lvl.g}.{n}.{cell}.layers"
+                        for idx, shape in ((0, (hz, z, 3, 3)), (2, (hz, 1, 5, 5)), (4, (z, hz, 1, 1))):
+                            sd[f"{q}.{idx}.weight"] = shape
+                            sd[f"{q}.{idx}.bias"] = (shape[0],)
+                            sd[f"{q}.{idx}.mask"] = shape
         return OrderedDict((k, v) for k, v in sd.items() if v is not None)
+
+    @staticmethod
+    def nf_mask(shape, mirror: bool, zero_diag: bool):
+        """MaskedConv2d mask, architecture.py:17-28: taps in row-major order, the first (h*w)//2 (+1 with zero_diag) stay, mirrored = flipped"""
+        import torch
+        co, ci, h, w = shape
+        m = torch.ones(co, ci, h * w)
+        half = (h * w) // 2 + int(zero_diag)
+        m[:, :, half:] = 0
+        if mirror:
+            m = torch.flip(m, dims=(2,))
+        return m.view(co, ci, h, w)
+
+    def nf_cells_of(self, s: int, g: int):
+        """[(layers-prefix, mirror)] of the NF cells applied to z of level (s, g), in execution order"""
+        if not self.use_nf:
+            return []
+        return [(f"nf_cells.nf_{s}:{g}.{n}.{cell}.layers", cell == "cell2") for n in range(self.num_nf_cells) for cell in ("cell1", "cell2")]
 
     def noise_shapes(self, batch: int) -> List[tuple]:
         """RNG draw order of one `__call__`: input noise, then one eps per latent level."""

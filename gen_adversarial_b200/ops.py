@@ -425,6 +425,35 @@ def pgd_linf_step_(x_adv, grad, x_nat, step: float, eps: float):
     return x_adv
 
 
+def apgd_l2_step_(x_adv, x_adv_old, grad, x_nat, step_size, a: float, bound: float):
+    """in place: the APGD update (untargeted.py:176-193) for a batch, per-image norms; step_size: device float32 [n]"""
+    n = x_adv.shape[0]
+    chw = x_adv.numel() // max(n, 1)
+    for t in (x_adv, x_adv_old, grad, x_nat, step_size):
+        assert t.is_contiguous() and t.dtype == torch.float32
+    _lib.check(_lib.lib().ga_apgd_l2_step(ptr(x_adv), ptr(x_adv_old), ptr(grad), ptr(x_nat), ptr(step_size), float(a), float(bound), n, chw,
+                                          stream()), "apgd_l2_step")
+    return x_adv
+
+
+def fgsm_l2_step(x_nat, grad, l2: float):
+    """x + l2 * sign(g) / ||sign(g)||, clamped (untargeted.py:736-745; g = gradient of +CE)"""
+    n = x_nat.shape[0]
+    out = torch.empty_like(x_nat)
+    _lib.check(_lib.lib().ga_fgsm_l2_step(ptr(x_nat.contiguous()), ptr(grad.contiguous()), float(l2), ptr(out), n, x_nat.numel() // max(n, 1),
+                                          stream()), "fgsm_l2_step")
+    return out
+
+
+def l2_ball_start(x_nat, noise, bound: float):
+    """clamp(x + bound * noise / ||noise||, 0, 1) per image (untargeted.py:129-131)"""
+    n = x_nat.shape[0]
+    out = torch.empty_like(x_nat)
+    _lib.check(_lib.lib().ga_l2_ball_start(ptr(x_nat.contiguous()), ptr(noise.contiguous()), float(bound), ptr(out), n,
+                                           x_nat.numel() // max(n, 1), stream()), "l2_ball_start")
+    return out
+
+
 @_timed("softmax_xent")
 def softmax_xent(logits, labels, want_grad=True, counter=None):
     """-> (loss[n], dlogits|None, pred[n] int32); `counter` (uint64 device scalar) accumulates argmax==label."""

@@ -63,6 +63,8 @@ def make_nvae_state_dict(cfg: dict = None, resolution: Tuple[int, int, int] = No
             t = _rand(shape, g, 0.0, 1.0)
         elif leaf == "num_batches_tracked":
             t = torch.tensor(100, dtype=torch.long)
+        elif leaf == "mask":                            # MaskedConv2d buffer: fixed by the module's (mirror, zero_diag), architecture.py:17-28
+            t = NvaeSpec.nf_mask(shape, mirror=".cell2." in key, zero_diag=key.endswith("layers.0.mask"))
         elif leaf == "running_mean":
             t = _randn(shape, g, 0.1)
         elif leaf == "running_var":

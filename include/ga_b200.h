@@ -176,6 +176,15 @@ int ga_nchw_to_nhwc(const float* in_nchw, const ga_tensor* out, float scale, flo
  *      x_adv <- clamp(min(max(x_adv + a*sign(g), x-eps), x+eps), 0, 1), in place, NCHW fp32 */
 int ga_pgd_linf_step(float* x_adv, const float* grad, const float* x_nat, float step, float eps, int64_t numel,
                      void* stream);
+/* ---- batched L2 attack steps, one CTA per image, per-image norms, NCHW fp32 [n][chw]:
+ *      APGD update of src/attacks/untargeted.py:176-193 (step along grad/||grad||, project on the L2 ball of radius `bound` around x,
+ *      clamp, momentum a, project, clamp; x_adv_old <- x_adv), in place; step_size: device float[n] (per-image step sizes);
+ *      FGSM update of untargeted.py:736-745 (x + l2 * sign(g)/||sign(g)||, clamp; g = gradient of +CE);
+ *      APGD starting point of untargeted.py:129-131 (x + bound * noise/||noise||, clamp) */
+int ga_apgd_l2_step(float* x_adv, float* x_adv_old, const float* grad, const float* x_nat, const float* step_size, float a,
+                    float bound, int n, int chw, void* stream);
+int ga_fgsm_l2_step(const float* x_nat, const float* grad, float l2, float* out, int n, int chw, void* stream);
+int ga_l2_ball_start(const float* x_nat, const float* noise, float bound, float* out, int n, int chw, void* stream);
 /* softmax cross-entropy: dlogits = (softmax - onehot)/n (mean reduction), loss[n], argmax==label counter */
 int ga_softmax_xent(const float* logits, const int64_t* labels, int n, int classes, float* loss, float* dlogits,
                     int32_t* pred, unsigned long long* n_correct /*device, accumulated*/, void* stream);

@@ -143,6 +143,21 @@ def disc_mix_logistic_mean(logits: torch.Tensor, n_mix: int) -> torch.Tensor:
     return torch.stack([r, g, bl], dim=1)
 
 
+def nf_cells(S: _SD, z, cells):
+    """NFBlock / NFCell.forward, architecture.py:221-253: z - conv1x1(ELU(dw5x5(ELU(conv3x3(z))))) with every weight multiplied by the
+    module's mask buffer (MaskedConv2d.forward :30-34), cell after cell.  (The mask of the 1x1 conv is all zero by construction --
+    (1*1)//2 = 0 taps survive -- so each cell only subtracts that conv's bias; the restatement keeps the full arithmetic.)"""
+    for q, _ in cells:
+        sd = S.sd
+        h = F.conv2d(z, sd[f"{q}.0.weight"] * sd[f"{q}.0.mask"], sd[f"{q}.0.bias"], padding=1)
+        h = F.elu(h)
+        h = F.conv2d(h, sd[f"{q}.2.weight"] * sd[f"{q}.2.mask"], sd[f"{q}.2.bias"], padding=2, groups=h.shape[1])
+        h = F.elu(h)
+        h = F.conv2d(h, sd[f"{q}.4.weight"] * sd[f"{q}.4.mask"], sd[f"{q}.4.bias"])
+        z = z - h
+    return z
+
+
 def nvae_purify(sd: Dict[str, torch.Tensor], spec: NvaeSpec, batch: torch.Tensor, alphas: Sequence[float],
                 eps_levels: List[torch.Tensor], temperature: float = 0.6, dtype=torch.float32,
                 taps: Optional[dict] = None) -> torch.Tensor:
@@ -183,6 +198,8 @@ def nvae_purify(sd: Dict[str, torch.Tensor], spec: NvaeSpec, batch: torch.Tensor
     z = (1 - a0) * soft_clamp5(mu_q) + a0 * (eps_levels[0].to(dtype) * temperature)   # prior N(0,1)*temp
     if taps is not None:
         taps["z0"] = z
+    if spec.use_nf:                                                       # models.py:209-210
+        z = nf_cells(S, z, spec.nf_cells_of(0, 0))
     x = S.sd["const_prior"].expand(b, -1, -1, -1)                         # models.py:215
     w, bias = S.wn("decoder_combiners.combiner_0:0.conv")
     x = F.conv2d(torch.cat([x, z], dim=1), w, bias)                       # architecture.py:215-218
@@ -206,6 +223,8 @@ def nvae_purify(sd: Dict[str, torch.Tensor], spec: NvaeSpec, batch: torch.Tensor
             z = (1 - a) * enc_mu + a * dec_sample                         # models.py:246-250
             if taps is not None:
                 taps[f"z{idx}"] = z
+            if spec.use_nf:                                               # models.py:253-254
+                z = nf_cells(S, z, spec.nf_cells_of(lvl.s, lvl.g))
             w, bias = S.wn(f"decoder_combiners.combiner_{lvl.s}:{lvl.g}.conv")
             x = F.conv2d(torch.cat([x, z], dim=1), w, bias)
             idx += 1

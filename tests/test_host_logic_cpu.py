@@ -49,6 +49,32 @@ def test_nvae_engine_host_logic_3scale(emu):
         assert (pur - ref).abs().max().item() <= tol, mode
 
 
+@pytest.mark.parametrize("nf", [1, 2])
+def test_nvae_engine_normalizing_flow_cells(emu, nf):
+    """A12: checkpoints built with num_nf_cells (NVAE/model.py:58-59,216-221; applied at src/defenses/ours/models.py:209-210,253-254):
+    the engine folds the flow cells into the decoder-combiner biases (exact: the last masked 1x1 conv of every NFCell has an all-zero
+    mask); compared with the oracle, which evaluates the masked convs in full."""
+    cfg, res = tiny_config(initial_channels=8, groups=2, scales=2, latent=4), (3, 32, 32)
+    cfg["num_nf_cells"] = nf
+    spec = NvaeSpec(cfg, res)
+    assert spec.use_nf
+    sd = synth.make_nvae_state_dict(cfg, res, seed=11)
+    assert any(k.endswith("cell2.layers.0.mask") for k in sd)
+    x, _ = synth.synthetic_batch(2, res, seed=1)
+    noises = synth.synthetic_noise(spec, 2, seed=2)
+    alphas = [0.7 * (i + 1) / spec.n_latents for i in range(spec.n_latents)]
+    with torch.no_grad():
+        _, ref = nvae_ref.defense_call(sd, spec, None, x, alphas, noises, 1.0, False)
+        cfg0 = dict(cfg); cfg0["num_nf_cells"] = None
+        sd0 = {k: v for k, v in sd.items() if not k.startswith("nf_cells.")}
+        _, ref0 = nvae_ref.defense_call(sd0, NvaeSpec(cfg0, res), None, x, alphas, noises, 1.0, False)
+    assert (ref - ref0).abs().max().item() > 1e-3                  # the flow cells do change the result
+    eng = nvae_engine.NvaeEngine(sd, spec, "cpu", "fp32", _host_logic_test=True)
+    xin, _ = emu.preprocess(x, noises[0], 1.0, False, eng.adt)
+    pur, _ = eng.purify(xin, torch.tensor(alphas), noises[1:])
+    assert (pur - ref).abs().max().item() <= 2e-5
+
+
 def test_vgg_engine_host_logic_matches_torchvision(emu):
     """pool-fold + BN-fold of the VGG11 head against torchvision's vgg11_bn (small head to keep the test light)."""
     torch.manual_seed(0)

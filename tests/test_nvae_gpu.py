@@ -149,3 +149,44 @@ def test_stochastic_by_default_and_seedable(c32_models):
     assert (a - b).abs().max().item() > 1e-3      # fresh noise per call (the defense is stochastic by design)
     assert torch.equal(c, d)
     assert a.min() >= 0 and a.max() <= 1
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_normalizing_flow_checkpoint(mode):
+    """A12: a checkpoint built with num_nf_cells = 1 (the real model's configuration is unknown): NF cells are applied after
+    every latent mix (src/defenses/ours/models.py:209-210,253-254); against the oracle, which itself matches the unmodified reference on
+    this configuration (tests/test_oracle_vs_reference.py::test_normalizing_flow_config_matches_reference)."""
+    cfg, res = tiny_config(initial_channels=16, groups=2, scales=2, latent=4), (3, 32, 32)
+    cfg["num_nf_cells"] = 1
+    spec = NvaeSpec(cfg, res)
+    sd = synth.make_nvae_state_dict(cfg, res, seed=13)
+    x, _ = synth.synthetic_batch(3, res, seed=1)
+    noises = synth.synthetic_noise(spec, 3, seed=2)
+    alphas = [0.7 * (i + 1) / spec.n_latents for i in range(spec.n_latents)]
+    with torch.no_grad():
+        _, ref = nvae_ref.defense_call(sd, spec, None, x, alphas, noises, 1.0, True)
+    eng = NvaeEngine(sd, spec, DEV, mode)
+    err = (_run_engine(eng, x, noises, alphas, 1.0, True) - ref).abs().max().item()
+    print(f"[{mode}] NF checkpoint (tiny): purified max-abs err {err:.3e}")
+    assert err <= (1e-4 if mode == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c64_configuration(mode):
+    """SURVEY 8d secondary point: initial_channels 64 (3 scales x 8 groups, 180 M parameters, 57.9 GFLOP / image; channels 128 / 256 / 512 at
+    32x32 / 16x16 / 8x8: none of the fused-cell shapes, every conv through the generic kernels), with NF cells on top."""
+    cfg = dict(NVAE_C32_CONFIG)
+    cfg["initial_channels"] = 64
+    cfg["num_nf_cells"] = 1
+    spec = NvaeSpec(cfg, NVAE_C32_RESOLUTION)
+    sd = synth.make_nvae_state_dict(cfg, NVAE_C32_RESOLUTION, seed=14)
+    x, _ = synth.synthetic_batch(2, seed=3)
+    noises = synth.synthetic_noise(spec, 2, seed=4)
+    import math
+    alphas = [0.7 * 0.5 * (1 - math.cos(math.pi * i / 24)) for i in range(1, 25)]
+    with torch.no_grad():
+        _, ref = nvae_ref.defense_call(sd, spec, None, x, alphas, noises, 2.0, True)
+    eng = NvaeEngine(sd, spec, DEV, mode)
+    err = (_run_engine(eng, x, noises, alphas, 2.0, True) - ref).abs().max().item()
+    print(f"[{mode}] C64 + NF configuration: purified max-abs err {err:.3e}")
+    assert err <= TOL[mode]

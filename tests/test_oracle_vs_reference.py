@@ -52,6 +52,36 @@ def test_restatement_matches_reference_call(tmp_path):
     assert (pur - pur_ref).abs().max().item() <= 1e-5
 
 
+def test_normalizing_flow_config_matches_reference(tmp_path):
+    """A12: a configuration with num_nf_cells = 1 -- state_dict layout (incl. the MaskedConv2d mask buffers, architecture.py:9-34) and
+    the whole defense call against the unmodified reference (src/defenses/ours/models.py:209-210,253-254)."""
+    cfg, res = tiny_config(initial_channels=8, groups=2, scales=2, latent=4), (3, 32, 32)
+    cfg["num_nf_cells"] = 1
+    spec = NvaeSpec(cfg, res)
+    ae = ref_import.ref_nvae_module().AutoEncoder(cfg, res)
+    ref_sd = ae.state_dict()
+    mine = synth.make_nvae_state_dict(cfg, res, seed=12)
+    assert set(ref_sd) == set(mine)
+    for k in ref_sd:
+        assert tuple(ref_sd[k].shape) == tuple(mine[k].shape), k
+        if k.endswith(".mask"):
+            assert torch.equal(ref_sd[k], mine[k]), k              # the masks are fixed by (mirror, zero_diag), not learned
+    ckpt = synth.make_nvae_checkpoint(cfg, res, seed=12)
+    path = os.path.join(tmp_path, "nvae_nf.pt")
+    torch.save(ckpt, path)
+    mm = ref_import.ref_models()
+    n = spec.n_latents
+    alphas = [i / n for i in range(1, n + 1)]
+    dm = mm.NVAEDefenseModel(_MeanClassifier(), path, alphas, 0.7, 1.0, True, "cpu")
+    x, _ = synth.synthetic_batch(2, res, seed=1)
+    noises = synth.synthetic_noise(spec, 2, seed=2)
+    with torch.no_grad(), ref_import.ExplicitNoise(noises):
+        _, pur_ref = dm(x, preds_only=False)
+    with torch.no_grad():
+        _, pur = nvae_ref.defense_call(ckpt["state_dict_temp=0.6"], spec, None, x, [a * 0.7 for a in alphas], noises, 1.0, True)
+    assert (pur - pur_ref).abs().max().item() <= 1e-5
+
+
 def test_restatement_gradient_matches_reference(tmp_path):
     """input-gradient of the oracle == autograd through the reference (attack path, untargeted.py:146)."""
     cfg, res = tiny_config(), (3, 32, 32)
