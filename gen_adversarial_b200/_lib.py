@@ -109,6 +109,8 @@ _PROTOS = {
     "ga_channel_sum_parts": (c_int, [c_int, c_int]),
     "ga_noise_sumsq": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ga_noise_sumsq_philox": (c_int, [c_uint64, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "ga_preprocess_image_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "ga_preprocess_image_fwd": (c_int, [c_void_p, c_void_p, c_uint64, c_int64, c_float, c_void_p, c_int, c_int, T, c_void_p, c_void_p]),
     "ga_preprocess_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_int64, c_float, c_void_p, c_int, c_int, T,
                                   c_void_p, c_void_p]),
     "ga_preprocess_bwd": (c_int, [T, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -124,6 +126,8 @@ _PROTOS = {
     "ga_sumpool2x2": (c_int, [T, T, T, c_void_p]),
     "ga_upsample_bilinear2x_bwd": (c_int, [T, T, c_void_p]),
     "ga_depth_to_space2": (c_int, [T, T, c_void_p]),
+    "ga_maxpool3x3s2_bwd": (c_int, [T, T, c_int, T, c_void_p]),
+    "ga_avgpool_bwd_relu": (c_int, [T, T, T, c_void_p]),
     "ga_maxpool2x2_bwd": (c_int, [T, T, c_int, T, c_void_p]),
     "ga_latent_mix_bwd": (c_int, [T, T, T, c_void_p, c_uint64, c_int, c_int64, c_void_p, c_float, c_int, T, T, c_void_p]),
     "ga_discmix_mean_bwd": (c_int, [T, c_int, c_void_p, T, T, c_void_p]),

@@ -52,7 +52,7 @@ class Tape:
 
     # the engines only `append` -- route by record kind
     def append(self, rec):
-        (self.vgg if rec[0].startswith("vgg_") else self.nvae).append(rec)
+        (self.vgg if rec[0].startswith(("vgg_", "resnet")) else self.nvae).append(rec)
 
 
 def defense_apply(model, batch: torch.Tensor):

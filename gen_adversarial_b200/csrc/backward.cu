@@ -374,6 +374,60 @@ __global__ void maxpool2x2_bwd_kernel(const void* xin, int x_dtype, const void* 
   for (int k = 0; k < 4; ++k) st1b(out, out_dtype, o[k], k == best ? gv : 0.f);
 }
 
+
+// max-pool 3x3 / stride 2 / pad 1 backward (torchvision ResNet stem), gather form without atomics: an input pixel belongs to up to four
+// windows; it receives a window's gradient iff it is that window's FIRST maximum in scan order (torch's max_pool2d_with_indices backward).
+// relu != 0: the pooled tensor is ReLU(conv): the gradient also passes the ReLU mask of the input value (stem conv -> ReLU -> pool).
+__global__ void maxpool3x3s2_bwd_kernel(const void* xin, int x_dtype, const void* g, int g_dtype, int relu, void* out, int out_dtype,
+                                        int N, int H, int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // over input elements
+  if (idx >= (int64_t)N * H * W * C) return;
+  const int c = (int)(idx % C);
+  int64_t t = idx / C;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H);
+  const int64_t n = t / H;
+  const float v = ld1b(xin, x_dtype, idx);
+  float acc = 0.f;
+  if (!(relu && !(v > 0.f))) {
+    // windows (oy, ox) with 2*oy - 1 <= y <= 2*oy + 1
+    for (int oy = (y) / 2; oy <= (y + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= Ho) continue;
+      for (int ox = (x) / 2; ox <= (x + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= Wo) continue;
+        // is (y, x) the first maximum of window (oy, ox)?
+        bool first = true;
+        for (int dy = -1; dy <= 1 && first; ++dy) {
+          const int iy = 2 * oy + dy;
+          if (iy < 0 || iy >= H) continue;
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int ix = 2 * ox + dx;
+            if (ix < 0 || ix >= W) continue;
+            if (iy == y && ix == x) continue;
+            const float u = ld1b(xin, x_dtype, ((n * H + iy) * W + ix) * C + c);
+            const bool before = (iy < y) || (iy == y && ix < x);
+            if (u > v || (before && u == v)) { first = false; break; }
+          }
+        }
+        if (first) acc += ld1b(g, g_dtype, ((n * Ho + oy) * Wo + ox) * C + c);
+      }
+    }
+  }
+  st1b(out, out_dtype, idx, acc);
+}
+
+// global average pool backward fused with the ReLU mask of the pooled tensor: out[n,h,w,c] = g[n,c] / HW * (y[n,h,w,c] > 0)
+__global__ void avgpool_bwd_relu_kernel(const void* g, int g_dtype, const void* y, int y_dtype, void* out, int out_dtype, int HW, int C,
+                                        int64_t total) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int64_t n = idx / ((int64_t)HW * C);
+  const float m = ld1b(y, y_dtype, idx) > 0.f ? 1.f / (float)HW : 0.f;
+  st1b(out, out_dtype, idx, ld1b(g, g_dtype, n * C + c) * m);
+}
+
 // ---------------------------------------------------------------------------- latent mix backward
 __global__ void __launch_bounds__(256) latent_mix_bwd_kernel(const void* gz, int gz_dtype, int Cz, const float* __restrict__ q, int Cq,
                                                              const float* __restrict__ pp, const float* __restrict__ eps,
@@ -724,6 +778,29 @@ extern "C" int ga_maxpool2x2_bwd(const ga_tensor* x_in, const ga_tensor* g_out, 
   if (total == 0) return 0;
   maxpool2x2_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x_in->data, x_in->dtype, g_out->data, g_out->dtype, relu,
                                                                             g_in->data, g_in->dtype, x_in->n, x_in->h, x_in->w, x_in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+
+extern "C" int ga_maxpool3x3s2_bwd(const ga_tensor* x_in, const ga_tensor* g_out, int relu, const ga_tensor* g_in, void* stream) {
+  GA_CHECK(x_in && g_out && g_in && same_shape(x_in, g_in) && g_out->h == (x_in->h - 1) / 2 + 1 && g_out->w == (x_in->w - 1) / 2 + 1 &&
+               g_out->c == x_in->c && g_out->n == x_in->n, "ga_maxpool3x3s2_bwd: shape mismatch");
+  const int64_t total = numel(x_in);
+  if (total == 0) return 0;
+  maxpool3x3s2_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x_in->data, x_in->dtype, g_out->data, g_out->dtype, relu,
+                                                                              g_in->data, g_in->dtype, x_in->n, x_in->h, x_in->w, x_in->c);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ga_avgpool_bwd_relu(const ga_tensor* g_feat, const ga_tensor* y, const ga_tensor* g_in, void* stream) {
+  GA_CHECK(g_feat && y && g_in && same_shape(y, g_in) && g_feat->n == y->n && g_feat->c == y->c && g_feat->h == 1 && g_feat->w == 1,
+           "ga_avgpool_bwd_relu: shape mismatch");
+  const int64_t total = numel(y);
+  if (total == 0) return 0;
+  avgpool_bwd_relu_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(g_feat->data, g_feat->dtype, y->data, y->dtype, g_in->data,
+                                                                              g_in->dtype, y->h * y->w, y->c, total);
   GA_LAUNCH_OK();
   return 0;
 }

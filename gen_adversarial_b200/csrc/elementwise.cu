@@ -292,6 +292,162 @@ __global__ void __launch_bounds__(256) preprocess_blur_fast_kernel(
   }
 }
 
+
+// ============================================================================ whole-image pre-processing (3 x 64 x 64: the `ids` configs)
+// One CTA per image: the image (48 KB) lives in shared memory for the whole kernel -- ONE read of x from HBM, ONE write of the result.
+// The N(0,1) noise is drawn once (Philox, same stream and counters as the tiled kernels above, or read from the explicit tensor), kept in
+// registers while its L2 norm is reduced inside the CTA (fixed order: bit-reproducible), and added after the blur: no separate
+// sum-of-squares kernel, no second Philox pass.  Blur = separable 15-tap Gaussian with reflect border (abstract_models.py:145-159):
+// horizontal pass from a row layout with the reflected halo materialised (16-byte window loads), vertical pass register-blocked over 8
+// output rows (22 row loads for 8 output quads instead of 15 per quad).  Replaces preprocess_blur_fast_kernel<7> / preprocess_fwd_kernel
+// + noise_sumsq_* at this size (they ran at 5-16% of the HBM roofline: two Philox passes, 4 re-staged tiles per image and channel).
+constexpr int PI_HW = 64, PI_C = 3, PI_PITCH = 80, PI_OFF = 8;      // row = [8 halo | 64 data | 8 halo] floats
+constexpr int PI_SMEM_BYTES = (PI_C * PI_HW * PI_PITCH + PI_C * PI_HW * PI_HW) * 4;
+
+template <int RT>
+__global__ void __launch_bounds__(256, 2) preprocess_image_kernel(const float* __restrict__ x, const float* __restrict__ noise, SeedArg seed_arg,
+                                                                   int64_t sample0, float eps, const float* __restrict__ taps, int normalize,
+                                                                   void* out, int out_dtype, float* __restrict__ pre) {
+  extern __shared__ __align__(16) float pi_smem[];
+  float* s_x = pi_smem;                                    // [3][64][80]; re-used as s_v [3][64][64] after the horizontal pass
+  float* s_h = pi_smem + PI_C * PI_HW * PI_PITCH;          // [3][64][64]
+  constexpr int HW = PI_HW * PI_HW, CHW = PI_C * HW;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* xb = x + (int64_t)b * CHW;
+  // ---- image -> shared memory (data columns at offset 8: 16-byte aligned)
+#pragma unroll
+  for (int k = 0; k < CHW / 4 / 256; ++k) {
+    const int q = tid + k * 256;
+    const int c = q / (HW / 4), r = q - c * (HW / 4), y = r >> 4, xq = r & 15;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb) + q);
+    *reinterpret_cast<float4*>(&s_x[(c * PI_HW + y) * PI_PITCH + PI_OFF + 4 * xq]) = v;
+  }
+  // ---- noise of this thread's output items (item = 4 pixels x 3 channels), norm reduced in the CTA
+  float z[4][PI_C][4];
+  float scale = 0.f;
+  if (eps != 0.f) {
+    const uint64_t seed = seed_arg.get();
+    const uint64_t stream = noise_stream(sample0 + b, 0);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int it = tid + k * 256, y = it >> 4, xq = it & 15;
+#pragma unroll
+      for (int c = 0; c < PI_C; ++c) {
+        const int e4 = ((c * PI_HW + y) * PI_HW + 4 * xq) >> 2;
+        if (noise != nullptr) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(noise + (int64_t)b * CHW) + e4);
+          z[k][c][0] = v.x; z[k][c][1] = v.y; z[k][c][2] = v.z; z[k][c][3] = v.w;
+        } else {
+          philox_normal4(seed, stream, (uint64_t)e4, z[k][c]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = fmaf(z[k][c][j], z[k][c][j], acc);
+      }
+    }
+    scale = eps / sqrtf(block_sum_256(acc));
+  }
+  __syncthreads();
+  const float* s_v = s_x + PI_OFF;                         // un-blurred: read the data columns in place (pitch 80)
+  int v_pitch = PI_PITCH;
+  if (RT > 0) {
+    float tp[2 * RT + 1];
+#pragma unroll
+    for (int t = 0; t < 2 * RT + 1; ++t) tp[t] = __ldg(taps + t);
+    // ---- reflected halo columns: x = -k -> k, x = 63 + k -> 63 - k
+    for (int i = tid; i < PI_C * PI_HW * 2 * RT; i += 256) {
+      const int row = i / (2 * RT), k = i - row * (2 * RT);
+      float* rp = s_x + row * PI_PITCH + PI_OFF;
+      if (k < RT) rp[-(k + 1)] = rp[k + 1];
+      else rp[PI_HW + (k - RT)] = rp[PI_HW - 2 - (k - RT)];
+    }
+    __syncthreads();
+    // ---- horizontal pass: item = 4 consecutive outputs of one row
+#pragma unroll 1
+    for (int k = 0; k < CHW / 4 / 256; ++k) {
+      const int q = tid + k * 256;
+      const int row = q >> 4, xq = q & 15;
+      const float* rp = s_x + row * PI_PITCH + 4 * xq;     // window: columns (4 xq + 8 - RT) .. (4 xq + 11 + RT) of the padded row
+      constexpr int W0 = PI_OFF - RT;                      // first needed column relative to rp
+      constexpr int NV = (W0 + 2 * RT + 4 + 3) / 4;
+      float wv[4 * NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float4 t4 = *reinterpret_cast<const float4*>(rp + 4 * v);
+        wv[4 * v] = t4.x; wv[4 * v + 1] = t4.y; wv[4 * v + 2] = t4.z; wv[4 * v + 3] = t4.w;
+      }
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 2 * RT + 1; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = fmaf(tp[t], wv[W0 + t + j], a[j]);
+      *reinterpret_cast<float4*>(&s_h[row * PI_HW + 4 * xq]) = make_float4(a[0], a[1], a[2], a[3]);
+    }
+    __syncthreads();
+    // ---- vertical pass: item = (channel, 4-pixel column, block of 8 rows); results over the (now free) s_x region, pitch 64
+    float* s_o = s_x;
+    for (int it = tid; it < PI_C * 16 * 8; it += 256) {
+      const int c = it >> 7, r = it & 127, yb = r >> 4, xq = r & 15;
+      const float* cp = s_h + c * HW + 4 * xq;
+      float a[8][4];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { a[o][0] = 0.f; a[o][1] = 0.f; a[o][2] = 0.f; a[o][3] = 0.f; }
+#pragma unroll
+      for (int i = 0; i < 8 + 2 * RT; ++i) {
+        const int yy = reflect_idx(yb * 8 + i - RT, PI_HW);
+        const float4 t4 = *reinterpret_cast<const float4*>(cp + yy * PI_HW);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const int t = i - o;                             // input row i feeds output row o through tap t
+          if (t < 0 || t > 2 * RT) continue;
+          a[o][0] = fmaf(tp[t], t4.x, a[o][0]); a[o][1] = fmaf(tp[t], t4.y, a[o][1]);
+          a[o][2] = fmaf(tp[t], t4.z, a[o][2]); a[o][3] = fmaf(tp[t], t4.w, a[o][3]);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        *reinterpret_cast<float4*>(&s_o[(c * PI_HW + yb * 8 + o) * PI_HW + 4 * xq]) = make_float4(a[o][0], a[o][1], a[o][2], a[o][3]);
+    }
+    __syncthreads();
+    s_v = s_x;
+    v_pitch = PI_HW;
+  }
+  // ---- + noise, clamp, normalise; NHWC out: the 12 values of an item are contiguous
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int it = tid + k * 256, y = it >> 4, xq = it & 15;
+    float res[PI_C][4];
+#pragma unroll
+    for (int c = 0; c < PI_C; ++c) {
+      const float4 t4 = *reinterpret_cast<const float4*>(s_v + (c * PI_HW + y) * v_pitch + 4 * xq);
+      float v[4] = {t4.x, t4.y, t4.z, t4.w};
+      if (eps != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaf(z[k][c][j], scale, v[j]);
+      }
+      if (pre != nullptr)    // saved UNCLAMPED (clamp backward mask)
+        *reinterpret_cast<float4*>(pre + (int64_t)b * CHW + (c * PI_HW + y) * PI_HW + 4 * xq) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float r = fminf(fmaxf(v[j], 0.f), 1.f);
+        res[c][j] = normalize ? (r - 0.5f) * 2.0f : r;
+      }
+    }
+    const int64_t o = ((int64_t)b * HW + y * PI_HW + 4 * xq) * PI_C;
+    if (out_dtype == GA_F32) {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
+      op[0] = make_float4(res[0][0], res[1][0], res[2][0], res[0][1]);
+      op[1] = make_float4(res[1][1], res[2][1], res[0][2], res[1][2]);
+      op[2] = make_float4(res[2][2], res[0][3], res[1][3], res[2][3]);
+    } else {
+      uint2* op = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o);
+      op[0] = make_uint2(pack_bf16x2(res[0][0], res[1][0]), pack_bf16x2(res[2][0], res[0][1]));
+      op[1] = make_uint2(pack_bf16x2(res[1][1], res[2][1]), pack_bf16x2(res[0][2], res[1][2]));
+      op[2] = make_uint2(pack_bf16x2(res[2][2], res[0][3]), pack_bf16x2(res[1][3], res[2][3]));
+    }
+  }
+}
+
 // backward helpers: g (NHWC) -> masked/scaled NCHW;  1-D transposed reflect-border blur along one axis
 __global__ void preprocess_bwd_mask_kernel(const void* __restrict__ g, int g_dtype, const float* __restrict__ pre,
                                            float gscale, int C, int H, int W, int64_t total, float* __restrict__ out) {
@@ -900,6 +1056,33 @@ extern "C" int ga_preprocess_fwd(const float* x, const float* noise, const float
   else
     preprocess_fwd_kernel<false><<<grid, 256, 0, s>>>(x, noise, sumsq, make_seed(seed, (cudaStream_t)stream), nparts, sample0, eps, nullptr, 0, normalize, out->c,
                                                      out->h, out->w, out->data, out->dtype, pre);
+  GA_LAUNCH_OK();
+  return 0;
+}
+
+
+extern "C" int ga_preprocess_image_supported(int c, int h, int w, int radius, int have_taps) {
+  return (c == PI_C && h == PI_HW && w == PI_HW && (!have_taps || radius == 7)) ? 1 : 0;
+}
+
+// blur -> noise -> clamp -> normalise for 3 x 64 x 64 images in ONE launch (the noise norm is reduced inside the kernel: no sumsq pre-pass)
+extern "C" int ga_preprocess_image_fwd(const float* x, const float* noise, uint64_t seed, int64_t sample0, float eps, const float* taps,
+                                       int radius, int normalize, const ga_tensor* out, float* pre, void* stream) {
+  GA_CHECK(x && out && out->data, "ga_preprocess_image_fwd: null argument");
+  GA_CHECK(ga_preprocess_image_supported(out->c, out->h, out->w, radius, taps != nullptr), "ga_preprocess_image_fwd: unsupported shape");
+  GA_CHECK(out->dtype == GA_F32 || out->dtype == GA_BF16, "ga_preprocess_image_fwd: out must be fp32 or bf16");
+  if (out->n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    GA_CUDA(cudaFuncSetAttribute(preprocess_image_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, PI_SMEM_BYTES));
+    GA_CUDA(cudaFuncSetAttribute(preprocess_image_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PI_SMEM_BYTES));
+    configured = true;
+  }
+  if (taps != nullptr)
+    preprocess_image_kernel<7><<<out->n, 256, PI_SMEM_BYTES, s>>>(x, noise, make_seed(seed, s), sample0, eps, taps, normalize, out->data, out->dtype, pre);
+  else
+    preprocess_image_kernel<0><<<out->n, 256, PI_SMEM_BYTES, s>>>(x, noise, make_seed(seed, s), sample0, eps, nullptr, normalize, out->data, out->dtype, pre);
   GA_LAUNCH_OK();
   return 0;
 }

@@ -46,6 +46,21 @@ def stride2_dgrad_phase_weights(w: torch.Tensor, pad: int) -> torch.Tensor:
     return wd.reshape(4 * cin, cout, k, k)
 
 
+def make_dgrad_layer(f: Folder, L: ops.ConvLayer, bf16: bool, pad_cin_to: Optional[int] = None) -> ops.ConvLayer:
+    """Input-gradient layer of the forward conv L (weights frozen: dgrad only): flipped taps, transposed channels; a stride-2 forward conv
+    becomes an input-dilated (`up`) conv for the SIMT kernel and, in bf16 mode, ONE stride-1 tensor-core conv emitting the four output
+    phases (`.phase`, see stride2_dgrad_phase_weights).  pad_cin_to: zero-pad the dgrad's input channels (= forward cout) to this many."""
+    w = L.w_simt.detach().to("cpu", torch.float64).view(L.kh, L.kw, L.cin, L.cout).permute(3, 2, 0, 1)   # [cout,cin,kh,kw]
+    if pad_cin_to is not None and pad_cin_to > w.shape[0]:
+        w = torch.cat([w, torch.zeros((pad_cin_to - w.shape[0],) + tuple(w.shape[1:]), dtype=w.dtype)], dim=0)
+    wt = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()           # [cin, cout(_pad), kh, kw]
+    D = f.conv(wt, None, stride=1, pad=L.kh - 1 - L.pad, name=L.name + ".dgrad", up=L.stride)
+    if bf16 and L.stride == 2 and w.shape[0] % 8 == 0 and L.cin % 4 == 0 and ((L.kh == 3 and L.pad == 1) or (L.kh == 1 and L.pad == 0)):
+        P = f.conv(stride2_dgrad_phase_weights(w, L.pad), None, stride=1, pad=L.kh // 2, name=L.name + ".dgrad4", simt=False)
+        D.phase = P if P.w_tc is not None else None
+    return D
+
+
 class _Enc:
     __slots__ = ("c1", "c2", "se", "skip", "down", "pre_affine", "c1_d", "c2_d", "skip_d")
 
@@ -435,15 +450,7 @@ class NvaeEngine:
         f = Folder({}, self.device, want_tc=self.bf16)
 
         def dg(L: ops.ConvLayer, pad_cin_to=None):
-            w = L.w_simt.detach().to("cpu", torch.float64).view(L.kh, L.kw, L.cin, L.cout).permute(3, 2, 0, 1)   # [cout,cin,kh,kw]
-            if pad_cin_to is not None and pad_cin_to > w.shape[0]:       # dgrad input channels = forward cout, zero padded
-                w = torch.cat([w, torch.zeros((pad_cin_to - w.shape[0],) + tuple(w.shape[1:]), dtype=w.dtype)], dim=0)
-            wt = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()           # [cin, cout(_pad), kh, kw]
-            D = f.conv(wt, None, stride=1, pad=L.kh - 1 - L.pad, name=L.name + ".dgrad", up=L.stride)
-            if self.bf16 and L.stride == 2 and w.shape[0] % 8 == 0 and L.cin % 4 == 0:
-                P = f.conv(stride2_dgrad_phase_weights(w, L.pad), None, stride=1, pad=L.kh // 2, name=L.name + ".dgrad4", simt=False)
-                D.phase = P if P.w_tc is not None else None
-            return D
+            return make_dgrad_layer(f, L, self.bf16, pad_cin_to)
 
         for _, e, _ in self._enc_sequence():
             e.c1_d, e.c2_d = dg(e.c1), dg(e.c2)

@@ -396,14 +396,6 @@ def preprocess(x_nchw, noise_nchw, eps: float, blur: bool, out_dtype, seed: int 
     x_nchw = x_nchw.contiguous()
     out = torch.empty((n, h, w, c), device=x_nchw.device, dtype=out_dtype)
     pre = torch.empty_like(x_nchw) if save_pre else None
-    sumsq = None
-    if eps != 0.0:
-        sumsq = torch.empty((n, L.ga_noise_sumsq_parts(c * h * w)), device=x_nchw.device, dtype=torch.float32)
-        if noise_nchw is not None:
-            noise_nchw = noise_nchw.contiguous()
-            _lib.check(L.ga_noise_sumsq(ptr(noise_nchw), n, c * h * w, ptr(sumsq), stream()), "noise_sumsq")
-        else:
-            _lib.check(L.ga_noise_sumsq_philox(seed, sample0, n, c * h * w, ptr(sumsq), stream()), "noise_sumsq_philox")
     taps, radius = None, 0
     if blur:
         if taps_cache is not None and taps_cache.get("h") == h and taps_cache["taps"].device == x_nchw.device:
@@ -413,6 +405,21 @@ def preprocess(x_nchw, noise_nchw, eps: float, blur: bool, out_dtype, seed: int 
             taps = t.to(x_nchw.device)
             if taps_cache is not None:
                 taps_cache.update({"h": h, "taps": taps, "radius": radius})
+    if L.ga_preprocess_image_supported(c, h, w, radius, int(blur)):
+        # 3 x 64 x 64: one launch, image resident in shared memory, noise norm reduced in the kernel
+        if eps != 0.0 and noise_nchw is not None:
+            noise_nchw = noise_nchw.contiguous()
+        _lib.check(L.ga_preprocess_image_fwd(ptr(x_nchw), ptr(noise_nchw) if eps != 0.0 else None, seed, sample0, eps, ptr(taps), radius,
+                                             int(normalize), gt(out), ptr(pre), stream()), "preprocess_image_fwd")
+        return out, pre
+    sumsq = None
+    if eps != 0.0:
+        sumsq = torch.empty((n, L.ga_noise_sumsq_parts(c * h * w)), device=x_nchw.device, dtype=torch.float32)
+        if noise_nchw is not None:
+            noise_nchw = noise_nchw.contiguous()
+            _lib.check(L.ga_noise_sumsq(ptr(noise_nchw), n, c * h * w, ptr(sumsq), stream()), "noise_sumsq")
+        else:
+            _lib.check(L.ga_noise_sumsq_philox(seed, sample0, n, c * h * w, ptr(sumsq), stream()), "noise_sumsq_philox")
     _lib.check(L.ga_preprocess_fwd(ptr(x_nchw), ptr(noise_nchw) if eps != 0.0 else None, ptr(sumsq), seed, sample0, eps,
                                    ptr(taps), radius, int(normalize), gt(out), ptr(pre), stream()), "preprocess_fwd")
     return out, pre
@@ -653,6 +660,21 @@ def depth_to_space2(x: torch.Tensor) -> torch.Tensor:
 def maxpool2x2_bwd(x_in, g_out, relu: bool, out_dtype):
     out = torch.empty(x_in.shape, device=x_in.device, dtype=out_dtype)
     _lib.check(_lib.lib().ga_maxpool2x2_bwd(gt(x_in), gt(g_out), int(relu), gt(out), stream()), "maxpool2x2_bwd")
+    return out
+
+
+@_timed("maxpool3x3s2_bwd", hbm=True)
+def maxpool3x3s2_bwd(x_in, g_out, relu: bool, out_dtype):
+    out = torch.empty(x_in.shape, device=x_in.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_maxpool3x3s2_bwd(gt(x_in), gt(g_out), int(relu), gt(out), stream()), "maxpool3x3s2_bwd")
+    return out
+
+
+@_timed("avgpool_bwd_relu", hbm=True)
+def avgpool_bwd_relu(g_feat, y, out_dtype):
+    """global-average-pool backward times the ReLU mask of the pooled map y: g_feat (N,1,1,C) -> (N,H,W,C)"""
+    out = torch.empty(y.shape, device=y.device, dtype=out_dtype)
+    _lib.check(_lib.lib().ga_avgpool_bwd_relu(gt(g_feat), gt(y), gt(out), stream()), "avgpool_bwd_relu")
     return out
 
 

@@ -15,14 +15,14 @@ from typing import Dict
 import torch
 
 from . import ops
-from ._lib import ACT_NONE, ACT_RELU
+from ._lib import ACT_NONE, ACT_RELU, MUL_RELU_MASK
 from .fold import Folder
 
 LAYERS = (3, 4, 6, 3)
 
 
 class _Block:
-    __slots__ = ("c1", "c2", "c3", "down")
+    __slots__ = ("c1", "c2", "c3", "down", "c1_d", "c2_d", "c3_d", "down_d")
 
 
 def densify_grouped(w: torch.Tensor, groups: int) -> torch.Tensor:
@@ -73,6 +73,7 @@ class ResNetEngine:
         w3 = f.f64("fc.3.weight")
         self.fc1 = f.conv(w3.view(w3.shape[0], w3.shape[1], 1, 1), f.f64("fc.3.bias"), name="fc.3")
         self.n_classes = w3.shape[0]
+        self._has_dgrad = False
 
     def _conv(self, x, L, want_f32=False, add=None):
         if self.bf16 and L.w_tc is not None and x.dtype == torch.bfloat16 and ops.conv2d_tc_supported(x, L):
@@ -81,18 +82,82 @@ class ResNetEngine:
         return ops.conv2d_simt(x, L, torch.float32 if (want_f32 or not self.bf16) else torch.bfloat16, add=add)
 
     def forward(self, x_nhwc: torch.Tensor, tape=None) -> torch.Tensor:
-        """x_nhwc (N,H,W,3) normalised with mean=std=0.5 (abstract_models.py:59-60) -> logits fp32 (N, classes)"""
-        if tape is not None:
-            raise NotImplementedError("input-gradient backward through the ResNet classifiers is not built (SURVEY 8f rank 3)")
-        x = ops.conv2d_simt(x_nhwc, self.stem, self.adt)
-        x = ops.maxpool3x3s2(x)
+        """x_nhwc (N,H,W,3) normalised with mean=std=0.5 (abstract_models.py:59-60) -> logits fp32 (N, classes).
+        tape: None or a list receiving the activations the input-gradient needs (every ReLU output is also the next op's input: nothing is
+        saved that the forward did not produce anyway)."""
+        if tape is not None and not self._has_dgrad:
+            self._build_dgrad()
+        x_stem = ops.conv2d_simt(x_nhwc, self.stem, self.adt)
+        x = ops.maxpool3x3s2(x_stem)
+        recs = []
         for blk in self.blocks:
             idt = x if blk.down is None else self._conv(x, blk.down)
-            h = self._conv(x, blk.c1)
-            h = self._conv(h, blk.c2)
-            x = self._conv(h, blk.c3, add=idt)
+            h1 = self._conv(x, blk.c1)
+            h2 = self._conv(h1, blk.c2)
+            out = self._conv(h2, blk.c3, add=idt)
+            if tape is not None:
+                recs.append((blk, x, h1, h2, out))
+            x = out
         n = x.shape[0]
         feat = ops.global_avgpool(x)
         h = self._conv(feat, self.fc0)
         logits = self._conv(h, self.fc1, want_f32=True)
+        if tape is not None:
+            tape.append(("resnet", x_nhwc.shape, x_stem, recs, h))
         return logits.reshape(n, self.n_classes)
+
+    # ------------------------------------------------------------------ backward (input gradient only; SURVEY 8f rank 3)
+    def _build_dgrad(self):
+        """flipped / transposed weights of every conv (built on first use: attacks only)"""
+        from .nvae_engine import make_dgrad_layer
+        f = Folder({}, self.device, want_tc=self.bf16)
+        dg = lambda L: make_dgrad_layer(f, L, self.bf16)
+        for blk in self.blocks:
+            blk.c1_d, blk.c2_d, blk.c3_d = dg(blk.c1), dg(blk.c2), dg(blk.c3)
+            blk.down_d = dg(blk.down) if blk.down is not None else None
+        self.stem_d = dg(self.stem)
+        self.fc0_d, self.fc1_d = dg(self.fc0), dg(self.fc1)
+        self._has_dgrad = True
+
+    def _dg(self, g, D, add=None, mul=None, f32=False):
+        """input gradient through one conv: (dgrad(g) + add) * [mul > 0]  (mul = the ReLU output that fed the forward conv)"""
+        mode = MUL_RELU_MASK
+        if not self.bf16:
+            out_hw = (g.shape[1] * D.up, g.shape[2] * D.up) if D.up > 1 else None
+            return ops.conv2d_simt(g, D, torch.float32, add=add, out_hw=out_hw, mul=mul, mul_mode=mode)
+        if g.dtype != torch.bfloat16:
+            g = ops.cast(g, torch.bfloat16)
+        if D.phase is not None:
+            # stride-2 forward conv: the four output phases as one stride-1 tensor-core conv over g, interleaved, then add / mask
+            _, o4 = ops.conv2d_tc(g, D.phase, want_bf16=False, want_f32=True)
+            o = ops.depth_to_space2(o4)
+            if add is not None:
+                o = ops.add(o, add, torch.float32)
+            if mul is not None:
+                o = ops.affine_act_bwd(o, mul, None, None, ACT_RELU, torch.float32 if f32 else torch.bfloat16)
+            return o
+        if D.w_tc is not None and ops.conv2d_tc_supported(g, D):
+            ob, of = ops.conv2d_tc(g, D, want_bf16=not f32, want_f32=f32, add=add, mul=mul, mul_mode=mode)
+            return of if f32 else ob
+        out_hw = (g.shape[1] * D.up, g.shape[2] * D.up) if D.up > 1 else None
+        return ops.conv2d_simt(g, D, torch.float32 if f32 else torch.bfloat16, add=add, out_hw=out_hw, mul=mul, mul_mode=mode)
+
+    def backward(self, tape, g_logits: torch.Tensor) -> torch.Tensor:
+        """g_logits (N, classes) fp32 -> d loss / d x_nhwc (N,H,W,3) fp32.  `tape` = the list filled by forward(tape=...)."""
+        (_, in_shape, x_stem, recs, h_fc), = [r for r in tape if r[0] == "resnet"]
+        n = g_logits.shape[0]
+        g = g_logits.contiguous().to(torch.float32).reshape(n, 1, 1, -1)
+        g = self._dg(g, self.fc1_d, mul=h_fc)                       # times the ReLU mask of the hidden layer
+        g = self._dg(g, self.fc0_d)                                  # w.r.t. the pooled features
+        last = recs[-1][4]
+        g = ops.avgpool_bwd_relu(g, last, self.adt)                  # average-pool backward x ReLU mask of the last block's output
+        for i in range(len(recs) - 1, -1, -1):
+            blk, x_in, h1, h2, _ = recs[i]
+            # g: gradient at the block's pre-ReLU sum (the output's ReLU mask is already applied)
+            g_h2 = self._dg(g, blk.c3_d, mul=h2)
+            g_h1 = self._dg(g_h2, blk.c2_d, mul=h1)
+            g_idt = g if blk.down is None else self._dg(g, blk.down_d, f32=True)
+            # the block input is the previous block's ReLU output (mask applied here) or, for the first block, the pooled stem
+            g = self._dg(g_h1, blk.c1_d, add=g_idt, mul=x_in if i > 0 else None)
+        g = ops.maxpool3x3s2_bwd(x_stem, g, True, torch.float32)     # first maximum of every 3x3 window, times the stem's ReLU mask
+        return ops.conv2d_simt(g, self.stem_d, torch.float32, out_hw=(in_shape[1], in_shape[2]))

@@ -95,6 +95,11 @@ int ga_preprocess_fwd(const float* x_nchw, const float* noise_nchw /*NULL => phi
                       int normalize, const ga_tensor* out_nhwc, float* pre_nchw /*optional: value before clamp, saved for bwd*/,
                       void* stream);
 /* backward of the above w.r.t. x: clamp mask, symmetric reflect-border blur transposed. g_nhwc is d/d(out). */
+/* whole-image variant for 3 x 64 x 64 inputs (radius 7 or no blur): one CTA per image, image resident in shared memory, noise norm
+ * reduced in-kernel -- one launch, one HBM read + one write (replaces ga_noise_sumsq* + ga_preprocess_fwd at this size) */
+int ga_preprocess_image_supported(int c, int h, int w, int radius, int have_taps);
+int ga_preprocess_image_fwd(const float* x_nchw, const float* noise_nchw, uint64_t seed, int64_t sample0, float eps, const float* taps,
+                            int radius, int normalize, const ga_tensor* out, float* pre_nchw, void* stream);
 int ga_preprocess_bwd(const ga_tensor* g_nhwc, const float* pre_nchw /*saved pre-clamp value (clamp mask)*/,
                       const float* taps, int radius, int normalize, float* tmp_nchw /*workspace, same size as gx (blur only)*/,
                       float* gx_nchw, void* stream);
@@ -256,6 +261,10 @@ int ga_upsample_bilinear2x_bwd(const ga_tensor* g_out, const ga_tensor* g_in, vo
 int ga_depth_to_space2(const ga_tensor* in, const ga_tensor* out, void* stream);
 /* gradient to the first maximal element of each window (torch semantics); relu=1 also applies the mask x_in > 0 */
 int ga_maxpool2x2_bwd(const ga_tensor* x_in, const ga_tensor* g_out, int relu, const ga_tensor* g_in, void* stream);
+/* ResNet / ResNeXt classifier backward: 3x3 stride-2 pad-1 max-pool backward (first maximum wins; relu: also the ReLU
+ * mask of the pooled tensor) and global-average-pool backward fused with the ReLU mask of the pooled feature map */
+int ga_maxpool3x3s2_bwd(const ga_tensor* x_in, const ga_tensor* g_out, int relu, const ga_tensor* g_in, void* stream);
+int ga_avgpool_bwd_relu(const ga_tensor* g_feat, const ga_tensor* y, const ga_tensor* g_in, void* stream);
 int ga_latent_mix_bwd(const ga_tensor* g_z, const ga_tensor* q, const ga_tensor* p /*nullable*/, const float* eps_nchw,
                       uint64_t seed, int level, int64_t sample0, const float* alpha_dev, float temperature, int zdim,
                       const ga_tensor* g_q, const ga_tensor* g_p /*nullable*/, void* stream);
