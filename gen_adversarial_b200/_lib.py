@@ -39,7 +39,8 @@ class GaConvDesc(ctypes.Structure):
                 ("pre_scale", c_void_p), ("pre_shift", c_void_p), ("weight", c_void_p), ("bias", c_void_p),
                 ("tf32", c_int32), ("ktot", c_int32),
                 ("mul", c_void_p), ("mul_dtype", c_int32), ("mul_mode", c_int32),
-                ("dact_out", c_void_p), ("dact_dtype", c_int32), ("act_after_add", c_int32), ("act_slope", c_void_p)]
+                ("dact_out", c_void_p), ("dact_dtype", c_int32), ("act_after_add", c_int32), ("act_slope", c_void_p),
+                ("csum_out", c_void_p)]
 
 
 def sources():
@@ -116,6 +117,7 @@ _PROTOS = {
     "ga_preprocess_bwd": (c_int, [T, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ga_conv2d_simt": (c_int, [T, D, T, T, c_void_p]),
     "ga_conv2d_tc": (c_int, [T, T, D, T, T, T, c_void_p]),
+    "ga_conv2d_tc_csum_supported": (c_int, [T, D, c_int]),
     "ga_conv2d_tc_supported": (c_int, [T, T, D, c_int]),
     "ga_dwconv5x5_fwd": (c_int, [T, c_void_p, c_void_p, c_int, c_int, T, c_void_p]),
     "ga_dwconv5x5_ex": (c_int, [T, T, c_void_p, c_void_p, c_int, c_int, T, T, c_void_p]),

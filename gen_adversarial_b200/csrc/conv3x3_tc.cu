@@ -24,7 +24,7 @@
 namespace ga {
 
 constexpr int C3_THREADS = 192;
-constexpr int C3_HDR_BYTES = 1024 + 2048 + 2048;   // barriers | bias[<=512] | PReLU slopes[<=512]
+constexpr int C3_HDR_BYTES = 1024 + 2048 + 2048 + 4096;   // barriers | bias[<=512] | PReLU slopes[<=512] | channel-sum slabs [2][4][<=128]
 
 struct C3Params {
   int kc;              // 64-channel blocks of Cin
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full + 1);
   float* s_bias = reinterpret_cast<float*>(hdr + 1024);
   float* s_slope = reinterpret_cast<float*>(hdr + 1024 + 2048);
+  float* s_csum = reinterpret_cast<float*>(hdr + 1024 + 2048 + 2048);   // double buffered by sub-tile parity
   uint8_t* s_w = hdr + C3_HDR_BYTES;                                           // resident weights: [tap][kc] tiles
   uint8_t* s_ring = s_w + (RESIDENT_W ? 9 * c.kc * B_TILE : 0);
   uint8_t* s_stage = s_ring + c.stages * c.stage_bytes;                        // epilogue staging (1024-aligned: all sizes are multiples)
@@ -200,12 +201,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
         // this warp's slab of the staging tile is free once its previous bulk stores have read it
-        if (lane == 0) tma_store_wait_read();
+        if (lane == 0) tma_store_wait_read();          // this warp's slab of the staging tile is free once its previous bulk stores have read it
         __syncwarp();
         if (warp == 2 && lane == 0) stamp(2, it, 6 + s);
         if (EPI == 0)
           tc_epilogue_lean<BLOCK_N>(p, &tmOutB, &tmOutF, &tmOutD, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
-                                    (int64_t)mt * 256 + s * 128, s_stage, s_bias + n_blk * BLOCK_N, q, lane);
+                                    (int64_t)mt * 256 + s * 128, s_stage, s_bias + n_blk * BLOCK_N, q, lane, s_csum + s * (4 * BLOCK_N));
         else if (EPI == 3)
           tc_epilogue_lean_am<BLOCK_N>(p, &tmOutB, &tmOutF, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
                                        (int64_t)mt * 256 + s * 128, s_stage, s_bias + n_blk * BLOCK_N, q, lane);
@@ -230,6 +231,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 }
 
 // ----------------------------------------------------------------------------- host side
+static unsigned long long* g_c3_trace = nullptr;
+static int g_halo_enabled = -1;     // GA_TC_HALO / ga_tc_halo_enable: 0 routes every 3x3 conv through the per-tap kernel (A/B comparisons)
+
 template <int BLOCK_N, bool RESIDENT_W, int EPI>
 static int launch_c3_(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of, const CUtensorMap& od,
                       const TcParams& p, const C3Params& c, int smem, int grid, cudaStream_t s) {
@@ -258,50 +262,79 @@ static int launch_c3(bool resident, int epi, const CUtensorMap& a, const CUtenso
   return launch_c3_<BLOCK_N, false, 2>(a, b, ob, of, od, p, c, smem, grid, s);
 }
 
-static unsigned long long* g_c3_trace = nullptr;
-static int g_halo_enabled = -1;     // GA_TC_HALO / ga_tc_halo_enable: 0 routes every 3x3 conv through the per-tap kernel (A/B comparisons)
 
 // Called by ga_conv2d_tc (conv_tc.cu) with a fully prepared TcParams (epilogue fields, cout, n_blocks unset).
 // -> 0 launched, 1 error, -1 not applicable (the caller goes on with the per-tap kernel).
-int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
-                        cudaStream_t s) {
+struct C3Plan { C3Params c; int block_n, n_blocks, smem; bool resident; };
+
+// geometry / shared-memory plan of the persistent kernel for one problem; false = shape not covered (the per-tap kernel runs it)
+static bool c3_plan(int n, int H, int W, int cin, int cout, bool out_b, bool out_f, bool dact, bool direct, C3Plan* pl) {
   if (g_halo_enabled < 0) { const char* e = getenv("GA_TC_HALO"); g_halo_enabled = e ? atoi(e) : 1; }
-  if (!g_halo_enabled) return -1;
-  const ga_tensor* out = out_bf16 ? out_bf16 : out_f32;
-  const int W = in->w, H = in->h, cin = in->c, cout = out->c;
-  if (cin % 64 != 0 || W % 8 != 0 || W > 128 || 256 % W != 0) return -1;
+  if (!g_halo_enabled) return false;
+  if (cin % 64 != 0 || W % 8 != 0 || W > 128 || 256 % W != 0) return false;
   const int TR = 256 / W;
-  if (TR < 2 || TR > H || H % TR != 0) return -1;
-  if (cout > 512) return -1;
+  if (TR < 2 || TR > H || H % TR != 0) return false;
+  if (cout > 512) return false;
   const int block_n = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
   const int n_blocks = (cout + block_n - 1) / block_n;
-  // TMA-store epilogue only (16-byte aligned row pitches and bases); anything else stays on the per-tap kernel
-  if (out_bf16 && ((cout * 2) % 16 != 0 || (((uintptr_t)out_bf16->data) & 15))) return -1;
-  if (out_f32 && ((cout * 4) % 16 != 0 || (((uintptr_t)out_f32->data) & 15))) return -1;
-  if (p.dact && ((((uintptr_t)p.dact) & 15) || (cout * 2) % 16 != 0)) return -1;
-  if (block_n == 32 && cout > 32) return -1;
-  if (block_n == 32 && (out_bf16 || p.dact) && cout < 32 && n_blocks > 1) return -1;
-
-  C3Params c;
+  // TMA-store epilogue only (16-byte aligned row pitches); anything else stays on the per-tap kernel
+  if ((out_b || dact) && (cout * 2) % 16 != 0) return false;
+  if (out_f && (cout * 4) % 16 != 0) return false;
+  C3Params& c = pl->c;
   c.kc = cin / 64; c.W = W; c.TR = TR; c.tiles_per_img = H / TR;
-  c.n_mtiles = in->n * c.tiles_per_img;
+  c.n_mtiles = n * c.tiles_per_img;
   c.n_tiles = c.n_mtiles * n_blocks;
   c.a_bytes = (TR + 2) * W * 128;
   const int b_tile = block_n * 128;
   const int w_bytes = 9 * c.kc * b_tile;
-  const int staging = ((out_bf16 ? 1 : 0) + (p.dact ? 1 : 0)) * ((block_n + 63) / 64) * 16384 + (out_f32 ? (block_n / 32) * 16384 : 0);
+  (void)direct;
+  const int staging = ((out_b ? 1 : 0) + (dact ? 1 : 0)) * ((block_n + 63) / 64) * 16384 + (out_f ? (block_n / 32) * 16384 : 0);
   c.staging_bytes = staging;
-  c.trace = g_c3_trace;
   const int budget = 227 * 1024 - 1024 - C3_HDR_BYTES - staging;
   // resident weights: one N block, and room for at least 2 ring stages of halo boxes next to them
-  bool resident = n_blocks == 1 && w_bytes + 2 * c.a_bytes <= budget;
+  const bool resident = n_blocks == 1 && w_bytes + 2 * c.a_bytes <= budget;
   c.stage_bytes = c.a_bytes + (resident ? 0 : 3 * b_tile);
   int stages = (budget - (resident ? w_bytes : 0)) / c.stage_bytes;
   if (stages > 4) stages = 4;
-  if (stages < 2) return -1;
+  if (stages < 2) return false;
   c.stages = stages;
-  const int smem = 1024 + C3_HDR_BYTES + (resident ? w_bytes : 0) + stages * c.stage_bytes + staging;
+  c.trace = g_c3_trace;
+  pl->block_n = block_n; pl->n_blocks = n_blocks; pl->resident = resident;
+  pl->smem = 1024 + C3_HDR_BYTES + (resident ? w_bytes : 0) + stages * c.stage_bytes + staging;
+  return true;
+}
 
+static int lean_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GA_TC_LEAN"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+// can this 3x3 convolution also emit the SE channel sums of its bf16 output (TcParams::csum)?  Needs the persistent kernel with the lean
+// epilogue, no activation / add / mul / tape, bf16 output only, and whole 128-pixel slices per image (the layout of ga_channel_sum)
+bool conv3x3_halo_csum_ok(const ga_tensor* in, int cout, const TcParams& p, bool out_b, bool out_f) {
+  C3Plan pl;
+  if (!lean_enabled() || !out_b || out_f || p.dact || p.add || p.mul || p.post_act != GA_ACT_NONE || p.act_after_add || p.round_tf32) return false;
+  if ((in->h * in->w) % 128 != 0) return false;
+  return c3_plan(in->n, in->h, in->w, in->c, cout, true, false, false, true, &pl);
+}
+
+int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
+                        cudaStream_t s) {
+  const ga_tensor* out = out_bf16 ? out_bf16 : out_f32;
+  const int W = in->w, H = in->h, cin = in->c, cout = out->c;
+  C3Plan pl;
+  p.cin = cin; p.cout = cout; p.tma_store = 1; p.partial = 0;
+  const bool general = p.act_after_add != 0 || p.post_act == GA_ACT_PRELU;
+  const int epi = general ? 2 : ((lean_enabled() && tc_epilogue_is_lean(p) && !(p.dact && out_f32 && !out_bf16)) ? 0 :
+                                 ((lean_enabled() && tc_epilogue_is_lean_am(p)) ? 3 : 1));
+  if (!c3_plan(in->n, H, W, cin, cout, out_bf16 != nullptr, out_f32 != nullptr, p.dact != nullptr, epi == 0, &pl)) return -1;
+  if (out_bf16 && (((uintptr_t)out_bf16->data) & 15)) return -1;
+  if (out_f32 && (((uintptr_t)out_f32->data) & 15)) return -1;
+  if (p.dact && (((uintptr_t)p.dact) & 15)) return -1;
+  const C3Params& c = pl.c;
+  const int block_n = pl.block_n, n_blocks = pl.n_blocks, smem = pl.smem, TR = c.TR;
+  const bool resident = pl.resident;
   p.cin = cin; p.cout = cout; p.n_blocks = n_blocks; p.M = (int64_t)in->n * H * W; p.H = H; p.W = W;
   p.tma_store = 1; p.partial = 0;
 
@@ -335,11 +368,8 @@ int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const
   if (out_f32 && out_map(&tmOF, out_f32->data, 4)) return 1;
   if (p.dact && out_map(&tmOD, p.dact, 2)) return 1;
 
-  const bool general = p.act_after_add != 0 || p.post_act == GA_ACT_PRELU;
-  static int lean_enabled = -1;
-  if (lean_enabled < 0) { const char* e = getenv("GA_TC_LEAN"); lean_enabled = e ? atoi(e) : 1; }
-  const int epi = general ? 2 : ((lean_enabled && tc_epilogue_is_lean(p) && !(p.dact && out_f32 && !out_bf16)) ? 0 :
-                                 ((lean_enabled && tc_epilogue_is_lean_am(p)) ? 3 : 1));
+  if (p.csum != nullptr) GA_CHECK(epi == 0 && conv3x3_halo_csum_ok(in, cout, p, out_bf16 != nullptr, out_f32 != nullptr),
+                                  "ga_conv2d_tc: csum_out requested for a convolution that cannot emit it (ask ga_conv2d_tc_csum_supported first)");
   const int grid = c.n_tiles < sm_count() ? c.n_tiles : sm_count();
   switch (block_n) {
     case 32: return launch_c3<32>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);

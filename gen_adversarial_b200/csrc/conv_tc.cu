@@ -19,6 +19,7 @@
 // epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "ga_common.cuh"
 #include "tc_ptx.cuh"
 #include "conv_tc_epilogue.cuh"
@@ -338,12 +339,14 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
   p.dact = (__nv_bfloat16*)d->dact_out;
   p.act_slope = d->act_slope; p.act_after_add = d->act_after_add;
   p.round_tf32 = (out_f32 && round_tf32_enabled()) ? 1 : 0;
+  p.csum = d->csum_out;
   GA_CHECK(d->post_act != GA_ACT_PRELU || d->act_slope != nullptr, "ga_conv2d_tc: PReLU needs act_slope");
   // 3x3 stride-1 convolutions on 64-channel blocks: persistent halo-reuse kernel (conv3x3_tc.cu); -1 = shape not covered there
   if (d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && !in2 && !tf32 && !k32) {
     const int rc = conv3x3_halo_launch(in, d->weight, ktot, out_bf16, out_f32, p, (cudaStream_t)stream);
     if (rc >= 0) return rc;
   }
+  GA_CHECK(p.csum == nullptr, "ga_conv2d_tc: csum_out requested for a convolution that cannot emit it (ask ga_conv2d_tc_csum_supported first)");
   CUtensorMap tmA, tmA2, tmB;
   if (encode_act_map(&tmA, in, g, d->stride, bk, esize)) return 1;
   if (in2) { if (encode_act_map(&tmA2, in2, g)) return 1; }
@@ -388,4 +391,14 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
     case 128: return short_k ? launch_tc<128, 2>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s) : launch_tc<128, 3>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
     default: return launch_tc<256, 3>(tmA, tmA2, tmB, tmOB, tmOF, tmOD, p, grid, s);
   }
+}
+
+// 1 if ga_conv2d_tc with this descriptor (bf16 output only, no add) can also write the SE channel sums of its output to desc->csum_out
+extern "C" int ga_conv2d_tc_csum_supported(const ga_tensor* in, const ga_conv_desc* d, int cout) {
+  if (!in || !d || !ga_conv2d_tc_supported(in, nullptr, d, cout)) return 0;
+  if (!(d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1) || d->tf32 || (in->c % 64) != 0) return 0;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.post_act = d->post_act; p.mul = d->mul; p.dact = (__nv_bfloat16*)d->dact_out; p.act_after_add = d->act_after_add;
+  return conv3x3_halo_csum_ok(in, cout, p, true, false) ? 1 : 0;
 }

@@ -31,11 +31,14 @@ struct TcParams {
   const float* act_slope;     // PReLU slopes [cout]
   int act_after_add;          // act(acc + bias + add)
   int round_tf32;             // fp32 output rounded to TF32 (feeds a kind::tf32 conv)
+  float* csum;                // optional (persistent 3x3 kernel, lean epilogue): per-image channel sums of the bf16 output in 128-pixel
+                              // slices, [n][HW / 128][cout] -- the layout ga_channel_sum writes (SE squeeze fused into the conv)
 };
 
 // conv3x3_tc.cu: persistent halo-reuse kernel for 3x3 / stride 1 / pad 1; -> 0 launched, 1 error, -1 shape not covered
 int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
                         cudaStream_t s);
+bool conv3x3_halo_csum_ok(const ga_tensor* in, int cout, const TcParams& p, bool out_b, bool out_f);
 
 // tmem_acc: TMEM address (lane 0) of column 0 of the accumulator; pix0: global index of the tile's first output pixel; row_limit: rows of
 // the tile that exist (128, or fewer for the partial last tile row of an image); stage: 1024-aligned staging memory (TMA-store mode);
@@ -237,6 +240,23 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const CUtens
   }
 }
 
+// A warp's 32-row slab of a swizzled staging tile (128-byte panels, 16-byte chunk index XOR (row & 7)) -> global memory with coalesced
+// 16-byte stores: consecutive lanes write consecutive chunks of a row (a 128-byte row = 8 lanes = one full line per 8 lanes).  Used instead
+// of a TMA store (experiment, off: SIMT_STORE): MEASURED SLOWER than the TMA store it replaces (C64 @32x32: 69.1 vs 53.4 us) although it needs
+// no wait for the TMA engine -- kept for the record, the lean epilogue uses staging + TMA store.
+template <int ESIZE>     // 2: bf16 panels of 64 columns, 4: fp32 panels of 32 columns
+__device__ __forceinline__ void tc_store_slab(const uint8_t* stage_x, void* out, int64_t pix0, int q, int lane, int cout, int col0, int ncols) {
+  const int row_chunks = (ncols * ESIZE) >> 4;                   // 16-byte chunks per row of this N block that exist in the tensor
+  const int total = 32 * row_chunks;
+  uint8_t* obase = reinterpret_cast<uint8_t*>(out) + ((pix0 + q * 32) * (int64_t)cout + col0) * ESIZE;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / row_chunks, cidx = idx - r * row_chunks;
+    const int panel = cidx >> 3, k = cidx & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage_x + panel * (128 * 128) + (q * 32 + r) * 128 + ((k ^ (r & 7)) << 4));
+    *reinterpret_cast<uint4*>(obase + (int64_t)r * cout * ESIZE + cidx * 16) = v;
+  }
+}
+
 // Lean epilogue for the persistent kernel's hot cases: out = act(acc + bias) with act in {none, SiLU, ReLU}, optional SiLU' tape, bf16 and / or
 // fp32 output through the TMA-store staging tile; no add / mul / PReLU.  Every uniform decision is taken ONCE per tile (the generic
 // epilogue re-decides per 16-column chunk: ~1000 clk per chunk when the warp has its scheduler to itself, and 140 KB of code), and all
@@ -247,9 +267,13 @@ __host__ __device__ __forceinline__ bool tc_epilogue_is_lean(const TcParams& p) 
          (p.dact == nullptr || p.post_act == GA_ACT_SILU);
 }
 
-template <int BLOCK_N, int ACT, bool DACT, bool OUT_B, bool OUT_F>
+// DIRECT (experiment, off): every thread stores its own output row (128 contiguous bytes for 64 bf16 channels) straight from registers --
+// no staging tile, no TMA store, no wait for the TMA engine.  MEASURED SLOWER than staging + TMA store (C64 @32x32, batch 512: 59.7 vs
+// 53.4 us): 32 lanes x 16 B to 32 different lines per STG keep the four epilogue warps in the LSU longer than the ~800 clk they wait for
+// the bulk store to have read the staging tile.
+template <int BLOCK_N, int ACT, bool DACT, bool OUT_B, bool OUT_F, bool CSUM = false, bool DIRECT = false>
 __device__ __forceinline__ void tc_epilogue_lean_body(const TcParams& p, uint32_t tmem_acc, int n_blk, uint8_t* stage, const float* s_bias,
-                                                      int q, int lane) {
+                                                      int q, int lane, float* s_csum = nullptr, int64_t pix0 = 0) {
   constexpr int LD = BLOCK_N < 64 ? BLOCK_N : 64;
   const int row = q * 32 + lane;
   uint8_t* stage_b = stage;
@@ -265,7 +289,9 @@ __device__ __forceinline__ void tc_epilogue_lean_body(const TcParams& p, uint32_
 #pragma unroll
     for (int ci = 0; ci < LD / 16; ++ci) {
       const int c0 = cg + ci * 16;
-      if (n_blk * BLOCK_N + c0 >= p.cout) continue;             // whole chunk beyond Cout (warp-uniform)
+      const int nb = n_blk * BLOCK_N + c0;
+      if (nb >= p.cout) continue;                               // whole chunk beyond Cout (warp-uniform)
+      const int64_t goff = (pix0 + row) * p.cout + nb;          // DIRECT: this thread's row, this chunk's first column
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[ci][j]) + s_bias[c0 + j];
@@ -273,12 +299,18 @@ __device__ __forceinline__ void tc_epilogue_lean_body(const TcParams& p, uint32_
         if (DACT) {
           float dv[16];
           silu_with_grad_fast_n<16>(v, v, dv);
+          if (DIRECT) {
+            uint4* o = reinterpret_cast<uint4*>(p.dact + goff);
+            if (nb + 8 <= p.cout) o[0] = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+            if (nb + 16 <= p.cout) o[1] = make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
+          } else {
           uint8_t* panel = stage_d + (c0 >> 6) * (128 * 128) + row * 128;
           const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
           *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
               make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
           *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
               make_uint4(pack_bf16x2(dv[8], dv[9]), pack_bf16x2(dv[10], dv[11]), pack_bf16x2(dv[12], dv[13]), pack_bf16x2(dv[14], dv[15]));
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
@@ -287,7 +319,11 @@ __device__ __forceinline__ void tc_epilogue_lean_body(const TcParams& p, uint32_
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
       }
-      if (OUT_B) {
+      if (OUT_B && DIRECT) {
+        uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + goff);
+        if (nb + 8 <= p.cout) o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        if (nb + 16 <= p.cout) o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      } else if (OUT_B) {
         uint8_t* panel = stage_b + (c0 >> 6) * (128 * 128) + row * 128;
         const uint32_t k0 = (uint32_t)((c0 & 63) >> 3);
         *reinterpret_cast<uint4*>(panel + (((k0) ^ sw) << 4)) =
@@ -295,12 +331,34 @@ __device__ __forceinline__ void tc_epilogue_lean_body(const TcParams& p, uint32_
         *reinterpret_cast<uint4*>(panel + (((k0 + 1) ^ sw) << 4)) =
             make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
       }
-      if (OUT_F) {
+      if (OUT_F && DIRECT) {
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + goff);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (nb + 4 * j + 4 <= p.cout) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else if (OUT_F) {
         uint8_t* panel = stage_f + (c0 >> 5) * (128 * 128) + row * 128;
         const uint32_t k0 = (uint32_t)((c0 & 31) >> 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<float4*>(panel + (((k0 + j) ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (CSUM) {
+        // column sums over this warp's 32 rows of the values AS STORED (bf16-rounded), by recursive halving: after the exchanges over lane
+        // bits 4, 3, 2, 1 every lane holds ONE column -- column (lane >> 1) & 15 -- summed over 16 lanes; the last exchange adds the other 16
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+        float w8[8], w4[4], w2[2];
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w8[j] = (b4 ? v[8 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, b4 ? v[j] : v[8 + j], 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w4[j] = (b3 ? w8[4 + j] : w8[j]) + __shfl_xor_sync(0xffffffffu, b3 ? w8[j] : w8[4 + j], 8);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) w2[j] = (b2 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, b2 ? w4[j] : w4[2 + j], 4);
+        float w1 = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+        if ((lane & 1) == 0) s_csum[q * BLOCK_N + c0 + ((lane >> 1) & 15)] = w1;
       }
     }
   }
@@ -308,30 +366,51 @@ __device__ __forceinline__ void tc_epilogue_lean_body(const TcParams& p, uint32_
 
 // -> issues the bulk stores of this warp's 32-row slab and commits them; the CALLER waits (cp.async.bulk.wait_group.read) before the slab is
 // written again.  Same staging layout and store boxes as tc_epilogue_tile.
-template <int BLOCK_N>
+template <int BLOCK_N, bool DIRECT = false, bool SIMT_STORE = false>
 __device__ __forceinline__ void tc_epilogue_lean(const TcParams& p, const CUtensorMap* tmOutB, const CUtensorMap* tmOutF,
                                                  const CUtensorMap* tmOutD, uint32_t tmem_acc, int n_blk, int64_t pix0, uint8_t* stage,
-                                                 const float* s_bias, int q, int lane) {
+                                                 const float* s_bias, int q, int lane, float* s_csum = nullptr) {
   const bool ob = p.out_bf16 != nullptr, of = p.out_f32 != nullptr;
-  if (p.post_act == GA_ACT_SILU) {
+#define GA_LEAN(ACT_, DACT_, OB_, OF_, CS_) tc_epilogue_lean_body<BLOCK_N, ACT_, DACT_, OB_, OF_, CS_, DIRECT>(p, tmem_acc, n_blk, stage, s_bias, q, lane, s_csum, pix0)
+  if (p.csum != nullptr) {
+    // SE squeeze fused into the conv (host guarantees: no activation, bf16 output only): per-warp column sums -> shared memory ->
+    // the 4 epilogue warps meet at a named barrier -> fixed-order sum of the 4 slabs -> [image][128-pixel slice][channel]
+    GA_LEAN(GA_ACT_NONE, false, true, false, true);
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    const int t = q * 32 + lane;
+    if (t < BLOCK_N && n_blk * BLOCK_N + t < p.cout)
+      p.csum[(pix0 >> 7) * p.cout + n_blk * BLOCK_N + t] = (s_csum[t] + s_csum[BLOCK_N + t]) + (s_csum[2 * BLOCK_N + t] + s_csum[3 * BLOCK_N + t]);
+  } else if (p.post_act == GA_ACT_SILU) {
     if (p.dact != nullptr) {
-      if (of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, true, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);   // (bf16 + fp32 + tape; the engines never ask for fp32 + tape alone)
-      else tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, true, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
-    } else if (ob && of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, false, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
-    else if (ob) tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, false, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
-    else tc_epilogue_lean_body<BLOCK_N, GA_ACT_SILU, false, false, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+      if (of) GA_LEAN(GA_ACT_SILU, true, true, true, false);      // (bf16 + fp32 + tape; the engines never ask for fp32 + tape alone)
+      else GA_LEAN(GA_ACT_SILU, true, true, false, false);
+    } else if (ob && of) GA_LEAN(GA_ACT_SILU, false, true, true, false);
+    else if (ob) GA_LEAN(GA_ACT_SILU, false, true, false, false);
+    else GA_LEAN(GA_ACT_SILU, false, false, true, false);
   } else if (p.post_act == GA_ACT_RELU) {
-    if (ob && of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_RELU, false, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
-    else if (ob) tc_epilogue_lean_body<BLOCK_N, GA_ACT_RELU, false, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
-    else tc_epilogue_lean_body<BLOCK_N, GA_ACT_RELU, false, false, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    if (ob && of) GA_LEAN(GA_ACT_RELU, false, true, true, false);
+    else if (ob) GA_LEAN(GA_ACT_RELU, false, true, false, false);
+    else GA_LEAN(GA_ACT_RELU, false, false, true, false);
   } else {
-    if (ob && of) tc_epilogue_lean_body<BLOCK_N, GA_ACT_NONE, false, true, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
-    else if (ob) tc_epilogue_lean_body<BLOCK_N, GA_ACT_NONE, false, true, false>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
-    else tc_epilogue_lean_body<BLOCK_N, GA_ACT_NONE, false, false, true>(p, tmem_acc, n_blk, stage, s_bias, q, lane);
+    if (ob && of) GA_LEAN(GA_ACT_NONE, false, true, true, false);
+    else if (ob) GA_LEAN(GA_ACT_NONE, false, true, false, false);
+    else GA_LEAN(GA_ACT_NONE, false, false, true, false);
   }
+#undef GA_LEAN
+  if (DIRECT) return;
   uint8_t* stage_b = stage;
   uint8_t* stage_f = stage + (ob ? ((BLOCK_N + 63) / 64) * 16384 : 0);
   uint8_t* stage_d = stage_f + (of ? (BLOCK_N / 32) * 16384 : 0);
+  if (SIMT_STORE) {
+    __syncwarp();
+    const int col0 = n_blk * BLOCK_N;
+    const int ncols = (p.cout - col0) < BLOCK_N ? (p.cout - col0) : BLOCK_N;
+    if (ob) tc_store_slab<2>(stage_b, p.out_bf16, pix0, q, lane, p.cout, col0, ncols);
+    if (of) tc_store_slab<4>(stage_f, p.out_f32, pix0, q, lane, p.cout, col0, ncols);
+    if (p.dact != nullptr) tc_store_slab<2>(stage_d, p.dact, pix0, q, lane, p.cout, col0, ncols);
+    __syncwarp();
+    return;
+  }
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {

@@ -86,6 +86,7 @@ class NvaeEngine:
         self.taps: Optional[dict] = None
         # fused decoder-cell kernel (expand -> dw5x5 -> project, hidden tensor on chip); GA_MBCONV_FUSED=0 selects the three-kernel path
         self.fuse_cells = __import__("os").environ.get("GA_MBCONV_FUSED", "1") != "0"
+        self.fuse_csum = __import__("os").environ.get("GA_FUSE_CSUM", "1") != "0"     # SE channel sums from the encoder conv2 epilogue
         f = Folder(state_dict, self.device, want_tc=self.bf16)
         self._fold(f)
         self._prior_cache = {}
@@ -278,12 +279,20 @@ class NvaeEngine:
         else:
             h, _ = self._conv(x32, e.c1)
             dact1 = None
-        r, _ = self._conv(h, e.c2)
+        sums = None
+        if self.bf16 and self.fuse_csum and ops.conv2d_tc_csum_supported(h, e.c2):
+            # SE squeeze fused into conv2's epilogue (persistent 3x3 kernel): per-image channel sums in the 128-pixel slices ga_channel_sum uses
+            sums = torch.empty((h.shape[0], ops.channel_sum_parts(h.shape[0], h.shape[1] * h.shape[2]), e.c2.cout), device=h.device,
+                               dtype=torch.float32)
+            r, _ = ops.conv2d_tc(h, e.c2, csum_out=sums)
+        else:
+            r, _ = self._conv(h, e.c2)
         if e.down:
             _, skip = self._conv(x32, e.skip, want_act=False, want_f32=True)
         else:
             skip = x32
-        sums = ops.channel_sum(r)
+        if sums is None:
+            sums = ops.channel_sum(r)
         out, _, act_next, _ = ops.se_residual(r, sums, e.se, 0.1, skip, torch.float32,
                                               act_affine=next_affine if self.bf16 else None)
         if taping:

@@ -142,7 +142,7 @@ class ConvLayer:
     phase: Optional["ConvLayer"] = None        # dgrad of a stride-2 conv as ONE stride-1 conv emitting the 4 output phases (4*cout channels)
     name: str = ""
 
-    def desc(self, tc: bool, mul=None, mul_mode: int = 0, dact=None, tf32: bool = False) -> GaConvDesc:
+    def desc(self, tc: bool, mul=None, mul_mode: int = 0, dact=None, tf32: bool = False, csum=None) -> GaConvDesc:
         w = (self.w_tf32 if tf32 else self.w_tc) if tc else self.w_simt
         if w is None:
             raise RuntimeError(f"conv layer {self.name}: no {'tensor-core' if tc else 'SIMT'} weights prepared")
@@ -150,7 +150,7 @@ class ConvLayer:
                           ptr(self.pre_scale), ptr(self.pre_shift), w.data_ptr(), ptr(self.bias), int(bool(tf32 and tc)),
                           w.shape[1] if tc else 0,
                           ptr(mul), _dt(mul) if mul is not None else 0, mul_mode,
-                          ptr(dact), _dt(dact) if dact is not None else 0, int(self.act_after_add), ptr(self.act_slope))
+                          ptr(dact), _dt(dact) if dact is not None else 0, int(self.act_after_add), ptr(self.act_slope), ptr(csum))
 
 
 def conv_out_hw(L: ConvLayer, h: int, w: int):
@@ -184,10 +184,19 @@ def conv2d_tc_supported(x: torch.Tensor, L: ConvLayer, x2: Optional[torch.Tensor
     return bool(_lib.lib().ga_conv2d_tc_supported(gt(x), gt(x2), ctypes.byref(d), L.cout))
 
 
+def conv2d_tc_csum_supported(x: torch.Tensor, L: ConvLayer) -> bool:
+    """can conv2d_tc(x, L) (bf16 output only, no add / mul / tape) also emit the SE channel sums of its output (`want_csum`)?"""
+    if L.w_tc is None or x.dtype != torch.bfloat16:
+        return False
+    d = L.desc(True)
+    return bool(_lib.lib().ga_conv2d_tc_csum_supported(gt(x), ctypes.byref(d), L.cout))
+
+
 def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: bool = False,
               add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None,
               mul: Optional[torch.Tensor] = None, mul_mode: int = 0, dact_out: Optional[torch.Tensor] = None,
-              out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, tf32: bool = False):
+              out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, tf32: bool = False,
+              csum_out: Optional[torch.Tensor] = None):
     """-> (out_bf16 or None, out_f32 or None);  out = (act(conv + bias) + add) * f(mul); dact_out <- act'(conv + bias).
     tf32: x is fp32 and the layer's fp32 weights are used (kind::tf32 MMA: 10-bit mantissas, half the bf16 rate)"""
     n, h, w, c = x.shape
@@ -195,7 +204,7 @@ def conv2d_tc(x: torch.Tensor, L: ConvLayer, want_bf16: bool = True, want_f32: b
     ho, wo = conv_out_hw(L, h, w)
     ob = (out_bf16 if out_bf16 is not None else torch.empty((n, ho, wo, L.cout), device=x.device, dtype=torch.bfloat16)) if want_bf16 else None
     of = (out_f32 if out_f32 is not None else torch.empty((n, ho, wo, L.cout), device=x.device, dtype=torch.float32)) if want_f32 else None
-    d = L.desc(True, mul, mul_mode, dact_out, tf32=tf32)
+    d = L.desc(True, mul, mul_mode, dact_out, tf32=tf32, csum=csum_out)
     e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_conv2d_tc(gt(x), gt(x2), ctypes.byref(d), gt(add), gt(ob), gt(of), stream()),
                f"conv2d_tc[{L.name}]")
@@ -250,6 +259,10 @@ def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b
         # algorithmic work: two 1x1 GEMMs on the tensor cores + 25 MAC per hidden element on the fp32 pipe; compulsory HBM traffic: x in, r out
         TIMER.stop(e0, f"fused:mbconv hw{h} c{c} hidden{hid}", 2.0 * m * hid * c * 2 + 2.0 * m * hid * 25, 2.0 * m * c * 2 + 2.0 * hid * c * 2)
     return out
+
+
+def channel_sum_parts(n: int, hw: int) -> int:
+    return int(_lib.lib().ga_channel_sum_parts(n, hw))
 
 
 @_timed("channel_sum", hbm=True)

@@ -67,6 +67,8 @@ typedef struct ga_conv_desc {
   int32_t dact_dtype;
   int32_t act_after_add;  /* 1: out = act(acc + bias + add) (ResNet bottleneck) instead of act(acc + bias) + add */
   const float* act_slope; /* [cout] negative slopes for GA_ACT_PRELU */
+  float* csum_out;        /* optional (ga_conv2d_tc only, when ga_conv2d_tc_csum_supported): per-image channel sums of the bf16 output in
+                             128-pixel slices, [n][h*w/128][cout] -- exactly what ga_channel_sum would compute from the output */
 } ga_conv_desc;
 
 const char* ga_last_error(void);
@@ -112,6 +114,8 @@ int ga_conv2d_simt(const ga_tensor* in, const ga_conv_desc* d, const ga_tensor* 
 int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, const ga_tensor* add,
                  const ga_tensor* out_bf16, const ga_tensor* out_f32, void* stream);
 int ga_conv2d_tc_supported(const ga_tensor* in, const ga_tensor* in2, const ga_conv_desc* d, int cout);
+/* SE squeeze fused into the producing conv: 1 if ga_conv2d_tc (bf16 output only, no add) can also fill desc->csum_out */
+int ga_conv2d_tc_csum_supported(const ga_tensor* in, const ga_conv_desc* desc, int cout);
 
 /* depthwise 5x5, pad 2, + bias + SiLU (decoder cell, architecture.py:168-170 with BN folded).  up=1: the
  * input is read through a nearest x2 up-sampling (architecture.py:162). weight fp32 [25][c]. */

@@ -132,8 +132,12 @@ def conv2d_tc_supported(x, L, x2=None, tf32=False):
     return True if h >= rows else (rows % h == 0)
 
 
+def conv2d_tc_csum_supported(x, L):
+    return False          # the emulation keeps the separate channel_sum op (the fused form is a kernel-level feature)
+
+
 def conv2d_tc(x, L, want_bf16=True, want_f32=False, add=None, x2=None, mul=None, mul_mode=0, dact_out=None, out_bf16=None,
-              out_f32=None, tf32=False):
+              out_f32=None, tf32=False, csum_out=None):
     _launches[0] += 1
     assert x.dtype == (torch.float32 if tf32 else torch.bfloat16)
     k1 = L.kh * L.kw * L.cin

@@ -173,6 +173,27 @@ def test_conv3x3_halo_kernel(case):
         assert (dgot.float().cpu() - dref).abs().max().item() <= 2e-2
 
 
+@pytest.mark.parametrize("n,h,w,c", [(37, 32, 32, 64), (150, 16, 16, 128), (3, 64, 64, 64), (5, 16, 16, 256)])
+def test_conv3x3_fused_channel_sums(n, h, w, c):
+    """SE squeeze fused into the conv epilogue: the sums written next to the bf16 output equal ga_channel_sum of that output (same
+    128-pixel slices; fp32 sums of the bf16-rounded values, only the order of the additions differs)"""
+    L = _layer(c, c, 3, 1, 1, PRE_NONE, ACT_NONE, tc=True, seed=c + n)
+    x = torch.randn(n, h, w, c, generator=torch.Generator().manual_seed(n)).to(torch.bfloat16).to(DEV)
+    LD = _to_dev(L)
+    assert ops.conv2d_tc_csum_supported(x, LD)
+    sums = torch.full((n, ops.channel_sum_parts(n, h * w), c), float("nan"), device=DEV)
+    r, _ = ops.conv2d_tc(x, LD, csum_out=sums)
+    r_plain, _ = ops.conv2d_tc(x, LD)
+    torch.cuda.synchronize()
+    assert torch.equal(r, r_plain)
+    ref = ops.channel_sum(r)
+    assert ref.shape == sums.shape and not torch.isnan(sums).any()
+    assert (sums - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+    # shapes the fused form does not cover say so instead of silently skipping the sums
+    x8 = torch.randn(4, 8, 8, 256).to(torch.bfloat16).to(DEV)
+    assert not ops.conv2d_tc_csum_supported(x8, _to_dev(_layer(256, 256, 3, 1, 1, PRE_NONE, ACT_NONE, tc=True)))
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,k,stride,act", [(2, 32, 32, 64, 64, 3, 1, ACT_NONE), (3, 16, 16, 128, 256, 3, 2, ACT_NONE),
                                                         (2, 64, 64, 64, 128, 1, 2, ACT_NONE), (4, 8, 8, 512, 512, 3, 1, ACT_SILU),
                                                         (2, 128, 128, 64, 64, 3, 1, ACT_NONE), (1, 32, 32, 40, 72, 3, 1, ACT_RELU)])
