@@ -103,6 +103,38 @@ def main_stylegan_paths():
     shutil.rmtree(SCRATCH, ignore_errors=True)
 
 
+def main_stylegan_counts(batch: int = 64, chunk: int = 8):
+    """north star: clean-accuracy COUNTS identical on the fp32 path -- logits of the reference's own E4E / Style-Transformer defense calls
+    (configs 3 / 4, full-size architectures, YAMLs verbatim) on 64 seeded images, explicit noise; only the logits are stored"""
+    import yaml
+    mm = ref_import.ref_models()
+    os.makedirs(SCRATCH, exist_ok=True)
+    for kind in ("e4e", "trans"):
+        if kind == "e4e":
+            ckpt, clf, yml, res, n_codes = synth.make_e4e_checkpoint(1024), synth.make_resnet50_checkpoint(), "ours_linear_noise_gender.yaml", 256, 18
+            Clf, Def = mm.CelebaGenderClassifier, mm.E4EStyleGanDefenseModel
+        else:
+            ckpt, clf, yml, res, n_codes = synth.make_trans_checkpoint(512), synth.make_resnext50_checkpoint(), "ours_cosine_blur_cars.yaml", 128, 16
+            Clf, Def = mm.CarsTypeClassifier, mm.TransStyleGanDefenseModel
+        with open(os.path.join(ref_import.REFERENCE_ROOT, "configs", yml)) as f:
+            p = yaml.safe_load(f)
+        with ref_import.InMemoryCheckpoints({"mem://ae": ckpt, "mem://clf": clf}):
+            dm = Def(Clf("mem://clf", "cpu"), "mem://ae", p["interpolation_alphas"], p["alpha_attenuation"], p["initial_noise_eps"],
+                     p["gaussian_blur_input"], "cpu")
+        x, noises = synth.synthetic_stylegan_inputs(batch, res, n_codes, seed=4242)
+        logits = []
+        for i in range(0, batch, chunk):
+            with torch.no_grad(), ref_import.ExplicitNoise([noises[0][i:i + chunk], noises[1][:, i:i + chunk]]):
+                logits.append(dm(x[i:i + chunk]))
+            print(kind, "chunk", i, flush=True)
+        logits = torch.cat(logits)
+        torch.save({"yaml": yml, "alphas": p["interpolation_alphas"], "attenuation": p["alpha_attenuation"], "eps": p["initial_noise_eps"],
+                    "blur": p["gaussian_blur_input"], "batch": batch, "x_seed": 4242, "logits": logits,
+                    "ae_digest": sd_digest(ckpt["state_dict"]), "clf_digest": sd_digest(clf["state_dict"])},
+                   os.path.join(GOLDEN, f"{kind}_counts_b{batch}.pt"))
+        print(kind, "argmax histogram", torch.bincount(logits.argmax(1)).tolist())
+
+
 def main_generator():
     import importlib
     ref_import.install()
@@ -176,4 +208,4 @@ def main():
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    {"all": main, "generator": main_generator, "stylegan_paths": main_stylegan_paths}[which]()
+    {"all": main, "generator": main_generator, "stylegan_paths": main_stylegan_paths, "stylegan_counts": main_stylegan_counts}[which]()

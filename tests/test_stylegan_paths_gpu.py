@@ -213,3 +213,34 @@ def test_defense_philox_mode_is_shard_independent():
     dm.sample_offset = 2
     _, tail = dm(x[2:], preds_only=False)
     assert (full[2:] - tail).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("kind,res,n_codes", [("e4e", 256, 18), ("trans", 128, 16)])
+def test_clean_counts_identical_on_64_images(kind, res, n_codes):
+    """north star: clean accuracy COUNTS identical on the fp32 path -- 64 seeded images per StyleGAN config, explicit noise, against the
+    logits of the reference's own defense call (tests/golden/*_counts_b64.pt, oracle/make_golden.py stylegan_counts); bf16 reported."""
+    path = os.path.join(GOLDEN, f"{kind}_counts_b64.pt")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = torch.load(path, weights_only=True)
+    x, noises = synth.synthetic_stylegan_inputs(g["batch"], res, n_codes, seed=g["x_seed"])
+    ref = g["logits"]
+    for mode in ("fp32", "bf16"):
+        dm = _defense(kind, mode)
+        dm.interpolation_alphas = [a * g["attenuation"] for a in g["alphas"]]
+        dm.eps, dm.blur_input = g["eps"], g["blur"]
+        got = []
+        for i in range(0, g["batch"], 16):
+            dm.set_explicit_noise([noises[0][i:i + 16], noises[1][:, i:i + 16]])
+            with torch.no_grad():
+                got.append(dm(x[i:i + 16].to(DEV)).cpu())
+        got = torch.cat(got)
+        diff = int((got.argmax(1) != ref.argmax(1)).sum())
+        rel = ((got - ref).abs().max() / ref.abs().max()).item()
+        print(f"[{mode}] {kind}: 64 images, {diff} arg-max differences, logits rel err {rel:.2e}, class histogram {torch.bincount(ref.argmax(1)).tolist()}")
+        if mode == "fp32":
+            assert diff == 0 and rel <= 1e-3
+        else:
+            assert diff <= 6
+        del dm
+        torch.cuda.empty_cache()
