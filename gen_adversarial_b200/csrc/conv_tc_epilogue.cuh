@@ -460,7 +460,10 @@ __device__ __forceinline__ void tc_epilogue_lean_am(const TcParams& p, const CUt
     const int nv = (p.cout - nb0) >= LD ? LD / 16 : (p.cout - nb0) / 16;
     uint4 abuf[LD / 4], mbuf[LD / 4];                         // raw add / mul values: fp32 fills LD/4 vectors, bf16 the first LD/8
     const int64_t off = pix * p.cout + nb0;
-    if (has_add) {
+    const bool row_ok = pix < p.M;                            // ragged last tile of the per-tap kernel: rows past M are never loaded (TMA clips their stores)
+#pragma unroll
+    for (int i = 0; i < LD / 4; ++i) { abuf[i] = make_uint4(0u, 0u, 0u, 0u); mbuf[i] = make_uint4(0u, 0u, 0u, 0u); }
+    if (has_add && row_ok) {
       if (add_f32) {
         const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.add) + off);
 #pragma unroll
@@ -471,7 +474,7 @@ __device__ __forceinline__ void tc_epilogue_lean_am(const TcParams& p, const CUt
         for (int i = 0; i < LD / 8; ++i) if (i < nv * 2) abuf[i] = __ldg(a4 + i);
       }
     }
-    if (has_mul) {
+    if (has_mul && row_ok) {
       if (mul_f32) {
         const uint4* m4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.mul) + off);
 #pragma unroll
