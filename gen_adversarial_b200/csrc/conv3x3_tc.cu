@@ -16,6 +16,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue (shared with conv_tc.cu).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "ga_common.cuh"
 #include "tc_ptx.cuh"
 #include "conv_tc_epilogue.cuh"
@@ -44,7 +45,10 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BLOCK_N, bool RESIDENT_W, int EPI>      // EPI 0: lean epilogue, 1: generic, 2: generic with PReLU / act-after-add, 3: lean + add / mul
+// TAPS 9: 3x3 convolution with halo reuse.  TAPS 1: 1x1 convolution / linear layer on the same persistent pipeline -- the activation tensor is a
+// plain [M][Cin] matrix, a stage is one 256-row x 64-channel box, tiles may span images (no geometry constraints); what the 1x1 convs gain is
+// the persistent structure: resident weights, double-buffered TMEM and the lean epilogues (their tiles are all epilogue).
+template <int BLOCK_N, bool RESIDENT_W, int EPI, int TAPS = 9>      // EPI 0: lean epilogue, 1: generic, 2: generic with PReLU / act-after-add, 3: lean + add / mul
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmOutB,
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   float* s_slope = reinterpret_cast<float*>(hdr + 1024 + 2048);
   float* s_csum = reinterpret_cast<float*>(hdr + 1024 + 2048 + 2048);   // double buffered by sub-tile parity
   uint8_t* s_w = hdr + C3_HDR_BYTES;                                           // resident weights: [tap][kc] tiles
-  uint8_t* s_ring = s_w + (RESIDENT_W ? 9 * c.kc * B_TILE : 0);
+  uint8_t* s_ring = s_w + (RESIDENT_W ? TAPS * c.kc * B_TILE : 0);
   uint8_t* s_stage = s_ring + c.stages * c.stage_bytes;                        // epilogue staging (1024-aligned: all sizes are multiples)
 
   const int warp = threadIdx.x >> 5;
@@ -107,8 +111,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     // ===================================================================== TMA producer
     if (elect_one_sync()) {
       if (RESIDENT_W) {
-        mbar_expect_tx(w_full, 9 * c.kc * B_TILE);
-        for (int tap = 0; tap < 9; ++tap)
+        mbar_expect_tx(w_full, TAPS * c.kc * B_TILE);
+        for (int tap = 0; tap < TAPS; ++tap)
           for (int kc = 0; kc < c.kc; ++kc)
             tma_load_2d(&tmB, w_full, s_w + (tap * c.kc + kc) * B_TILE, tap * p.cin + kc * 64, 0);
       }
@@ -116,6 +120,18 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       int pit = 0;
       for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++pit) {
         const int n_blk = t % n_blocks, mt = t / n_blocks;
+        if (TAPS == 1) {
+          for (int kc = 0; kc < c.kc; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            stamp(0, pit, kc);
+            mbar_expect_tx(&full_bar[stage], c.stage_bytes);
+            uint8_t* dst = s_ring + stage * c.stage_bytes;
+            tma_load_2d(&tmA, &full_bar[stage], dst, kc * 64, mt * 256);                    // box = 64 channels x 256 rows (rows past M: zero fill)
+            if (!RESIDENT_W) tma_load_2d(&tmB, &full_bar[stage], dst + c.a_bytes, kc * 64, n_blk * BLOCK_N);
+            if (++stage == c.stages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         const int img = mt / c.tiles_per_img, y0 = (mt - img * c.tiles_per_img) * c.TR;
         for (int kc = 0; kc < c.kc; ++kc)
           for (int kx = 0; kx < 3; ++kx) {
@@ -143,8 +159,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       uint32_t it = 0;
       // descriptor low words advance by (bytes >> 4): the second sub-tile sits TR/2 image rows further down the halo box, a vertical
       // tap shifts by one image row (W * 128 bytes, a multiple of the 1024-byte swizzle atom)
-      const uint32_t sub16 = ((uint32_t)(c.TR / 2) * c.W * 128) >> 4;
-      const uint32_t row16 = ((uint32_t)c.W * 128) >> 4;
+      const uint32_t sub16 = TAPS == 9 ? ((uint32_t)(c.TR / 2) * c.W * 128) >> 4 : (16384u >> 4);   // 1x1: the second 128 rows of the box
+      const uint32_t row16 = TAPS == 9 ? ((uint32_t)c.W * 128) >> 4 : 0u;
       const uint32_t w_lo = smem_desc_lo(smem_u32(s_w));
       for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
@@ -154,7 +170,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         const uint32_t d0 = tmem_base + buf * (2 * BLOCK_N);
         for (int kc = 0; kc < c.kc; ++kc) {
 #pragma unroll 1
-          for (int kx = 0; kx < 3; ++kx) {
+          for (int kx = 0; kx < (TAPS == 9 ? 3 : 1); ++kx) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (lane == 0) stamp(1, it, kc * 3 + kx);
@@ -164,7 +180,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             const uint32_t acc0 = (kc == 0 && kx == 0) ? 0u : 1u;
             if (elect_one_sync()) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
+            for (int ky = 0; ky < (TAPS == 9 ? 3 : 1); ++ky) {
               const uint32_t b_lo = b_lo0 + ky * b_step;
 #pragma unroll
               for (int s = 0; s < 2; ++s) {
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
               }
             }
             umma_commit(&empty_bar[stage]);
-            if (kc == c.kc - 1 && kx == 2) umma_commit(&tmem_full[buf]);
+            if (kc == c.kc - 1 && kx == (TAPS == 9 ? 2 : 0)) umma_commit(&tmem_full[buf]);
             }
             __syncwarp();
             if (++stage == c.stages) { stage = 0; phase ^= 1; }
@@ -234,15 +250,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 static unsigned long long* g_c3_trace = nullptr;
 static int g_halo_enabled = -1;     // GA_TC_HALO / ga_tc_halo_enable: 0 routes every 3x3 conv through the per-tap kernel (A/B comparisons)
 
-template <int BLOCK_N, bool RESIDENT_W, int EPI>
+template <int BLOCK_N, bool RESIDENT_W, int EPI, int TAPS = 9>
 static int launch_c3_(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of, const CUtensorMap& od,
                       const TcParams& p, const C3Params& c, int smem, int grid, cudaStream_t s) {
   static int configured = 0;
   if (configured < smem) {
-    GA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, RESIDENT_W, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, RESIDENT_W, EPI, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  conv3x3_tc_kernel<BLOCK_N, RESIDENT_W, EPI><<<grid, C3_THREADS, smem, s>>>(a, b, ob, of, od, p, c);
+  conv3x3_tc_kernel<BLOCK_N, RESIDENT_W, EPI, TAPS><<<grid, C3_THREADS, smem, s>>>(a, b, ob, of, od, p, c);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -265,6 +281,16 @@ static int launch_c3(bool resident, int epi, const CUtensorMap& a, const CUtenso
 
 // Called by ga_conv2d_tc (conv_tc.cu) with a fully prepared TcParams (epilogue fields, cout, n_blocks unset).
 // -> 0 launched, 1 error, -1 not applicable (the caller goes on with the per-tap kernel).
+// 1x1 convolutions: lean epilogues only (EPI 0 / 3); anything else stays on the per-tap kernel
+template <int BLOCK_N>
+static int launch_c1(bool resident, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& ob, const CUtensorMap& of,
+                     const CUtensorMap& od, const TcParams& p, const C3Params& c, int smem, int grid, cudaStream_t s) {
+  if (resident) return epi == 0 ? launch_c3_<BLOCK_N, true, 0, 1>(a, b, ob, of, od, p, c, smem, grid, s)
+                                : launch_c3_<BLOCK_N, true, 3, 1>(a, b, ob, of, od, p, c, smem, grid, s);
+  return epi == 0 ? launch_c3_<BLOCK_N, false, 0, 1>(a, b, ob, of, od, p, c, smem, grid, s)
+                  : launch_c3_<BLOCK_N, false, 3, 1>(a, b, ob, of, od, p, c, smem, grid, s);
+}
+
 struct C3Plan { C3Params c; int block_n, n_blocks, smem; bool resident; };
 
 // geometry / shared-memory plan of the persistent kernel for one problem; false = shape not covered (the per-tap kernel runs it)
@@ -375,6 +401,89 @@ int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const
     case 32: return launch_c3<32>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);
     case 64: return launch_c3<64>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);
     default: return launch_c3<128>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);
+  }
+}
+
+// 1x1 / stride 1 convolution (or linear layer) on the persistent pipeline.  -> 0 launched, 1 error, -1 not covered (per-tap kernel runs it).
+int conv1x1_persistent_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
+                              cudaStream_t s) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("GA_TC_P1X1"); enabled = e ? atoi(e) : 1; }
+  if (g_halo_enabled < 0) { const char* e = getenv("GA_TC_HALO"); g_halo_enabled = e ? atoi(e) : 1; }
+  if (!enabled || !g_halo_enabled || !lean_enabled()) return -1;
+  const ga_tensor* out = out_bf16 ? out_bf16 : out_f32;
+  const int cin = in->c, cout = out->c;
+  const int64_t M = (int64_t)in->n * in->h * in->w;
+  if (cin % 64 != 0 || ktot != cin || cout > 512 || M < 256 * 64) return -1;      // small problems: launch-bound either way, keep the per-tap kernel
+  if ((out_bf16 || p.dact) && (cout * 2) % 16 != 0) return -1;
+  if (out_f32 && (cout * 4) % 16 != 0) return -1;
+  if (out_bf16 && (((uintptr_t)out_bf16->data) & 15)) return -1;
+  if (out_f32 && (((uintptr_t)out_f32->data) & 15)) return -1;
+  if (p.dact && (((uintptr_t)p.dact) & 15)) return -1;
+  p.cin = cin; p.cout = cout; p.tma_store = 1; p.partial = 0; p.M = M; p.H = in->h; p.W = in->w;
+  if (p.act_after_add != 0 || p.post_act == GA_ACT_PRELU) return -1;
+  int epi;
+  if (tc_epilogue_is_lean(p) && !(p.dact && out_f32 && !out_bf16)) epi = 0;
+  // add/mul epilogues stream one more tensor per output row: with one CTA per SM and four epilogue warps too few of those loads are in flight
+  // (N=384 dgrad*mul at 32x32: 425 us here against 273 us on the per-tap kernel, which keeps several CTAs per SM) -- GA_TC_P1X1=2 opts them in.
+  else if (enabled >= 2 && tc_epilogue_is_lean_am(p)) epi = 3;
+  else return -1;
+  const int block_n = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+  const int n_blocks = (cout + block_n - 1) / block_n;
+  p.n_blocks = n_blocks;
+  C3Params c;
+  memset(&c, 0, sizeof(c));
+  c.kc = cin / 64; c.W = 0; c.TR = 0; c.tiles_per_img = 1;
+  c.n_mtiles = (int)((M + 255) / 256);
+  c.n_tiles = c.n_mtiles * n_blocks;
+  c.a_bytes = 256 * 128;
+  const int b_tile = block_n * 128;
+  const int w_bytes = c.kc * b_tile;
+  const int staging = ((out_bf16 ? 1 : 0) + (p.dact ? 1 : 0)) * ((block_n + 63) / 64) * 16384 + (out_f32 ? (block_n / 32) * 16384 : 0);
+  c.staging_bytes = staging;
+  const int budget = 227 * 1024 - 1024 - C3_HDR_BYTES - staging;
+  const bool resident = n_blocks == 1 && w_bytes + 2 * c.a_bytes <= budget;
+  c.stage_bytes = c.a_bytes + (resident ? 0 : b_tile);
+  int stages = (budget - (resident ? w_bytes : 0)) / c.stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) return -1;
+  c.stages = stages;
+  c.trace = nullptr;
+  const int smem = 1024 + C3_HDR_BYTES + (resident ? w_bytes : 0) + stages * c.stage_bytes + staging;
+  CUtensorMap tmA, tmB, tmOB, tmOF, tmOD;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
+    cuuint32_t box[2] = {64u, 256u};
+    cuuint32_t estr[2] = {1, 1};
+    if (encode_tiled_cached(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, in->data, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return 1;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    if (encode_tiled_cached(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, weight, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return 1;
+  }
+  auto out_map = [&](CUtensorMap* tm, void* base, int esize) {
+    cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)cout * esize};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esize), 32u};
+    cuuint32_t estr[2] = {1, 1};
+    return encode_tiled_cached(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
+                               estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+  };
+  tmOB = tmA; tmOF = tmA; tmOD = tmA;
+  if (out_bf16 && out_map(&tmOB, out_bf16->data, 2)) return 1;
+  if (out_f32 && out_map(&tmOF, out_f32->data, 4)) return 1;
+  if (p.dact && out_map(&tmOD, p.dact, 2)) return 1;
+  const int grid = c.n_tiles < sm_count() ? c.n_tiles : sm_count();
+  switch (block_n) {
+    case 32: return launch_c1<32>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);
+    case 64: return launch_c1<64>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);
+    default: return launch_c1<128>(resident, epi, tmA, tmB, tmOB, tmOF, tmOD, p, c, smem, grid, s);
   }
 }
 

@@ -346,6 +346,11 @@ extern "C" int ga_conv2d_tc(const ga_tensor* in, const ga_tensor* in2, const ga_
     const int rc = conv3x3_halo_launch(in, d->weight, ktot, out_bf16, out_f32, p, (cudaStream_t)stream);
     if (rc >= 0) return rc;
   }
+  // 1x1 stride-1 convolutions / linear layers with a lean epilogue: the same persistent pipeline (resident weights, double-buffered TMEM)
+  if (d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0 && !in2 && !tf32 && !k32 && p.csum == nullptr) {
+    const int rc = conv1x1_persistent_launch(in, d->weight, ktot, out_bf16, out_f32, p, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   GA_CHECK(p.csum == nullptr, "ga_conv2d_tc: csum_out requested for a convolution that cannot emit it (ask ga_conv2d_tc_csum_supported first)");
   CUtensorMap tmA, tmA2, tmB;
   if (encode_act_map(&tmA, in, g, d->stride, bk, esize)) return 1;

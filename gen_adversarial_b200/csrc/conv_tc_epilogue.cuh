@@ -38,6 +38,8 @@ struct TcParams {
 // conv3x3_tc.cu: persistent halo-reuse kernel for 3x3 / stride 1 / pad 1; -> 0 launched, 1 error, -1 shape not covered
 int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
                         cudaStream_t s);
+int conv1x1_persistent_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
+                              cudaStream_t s);
 bool conv3x3_halo_csum_ok(const ga_tensor* in, int cout, const TcParams& p, bool out_b, bool out_f);
 
 // tmem_acc: TMEM address (lane 0) of column 0 of the accumulator; pix0: global index of the tile's first output pixel; row_limit: rows of

@@ -173,6 +173,45 @@ def test_conv3x3_halo_kernel(case):
         assert (dgot.float().cpu() - dref).abs().max().item() <= 2e-2
 
 
+P1X1_CASES = [
+    # 1x1 convolutions at M >= 16384 rows, where the persistent pipeline takes the plain epilogues (and, with GA_TC_P1X1=2, the add/mul ones):
+    # n, h, w, cin, cout, post, add, mul_mode, want (bf16, f32), dact
+    (64, 32, 32, 64, 64, ACT_NONE, "f32", None, (True, False), False),      # encoder combiner: + stash (lean add epilogue), resident weights
+    (64, 32, 32, 64, 384, ACT_SILU, None, None, (True, False), True),       # decoder expand, taping: three N blocks, streaming weights
+    (64, 32, 32, 384, 64, ACT_NONE, None, None, (True, False), False),      # decoder project: six K blocks, resident weights
+    (64, 32, 32, 384, 64, ACT_NONE, "f32", None, (False, True), False),     # expand dgrad: fp32 stream gradient + add
+    (64, 32, 32, 64, 384, ACT_NONE, None, 0, (True, False), False),         # project dgrad times SiLU' tape (bf16 mul)
+    (100, 16, 16, 128, 40, ACT_NONE, None, None, (False, True), False),     # decoder sampler: 40 fp32 channels
+    (257, 8, 8, 64, 128, ACT_RELU, None, None, (True, False), False),       # ragged: M = 16448 = 64 tiles of 256 + 64 rows
+    (75, 16, 16, 128, 64, ACT_NONE, "f32", 1, (True, False), False),        # M = 19200 = 75 tiles of 256 with add and ReLU-mask mul
+    (4, 64, 64, 1536, 256, ACT_NONE, None, None, (True, False), False),     # K = 1536 (24 blocks), two N blocks
+]
+
+
+@pytest.mark.parametrize("case", P1X1_CASES)
+def test_conv1x1_persistent_kernel(case):
+    n, h, w, cin, cout, post, addk, mul_mode, (wb, wf), want_dact = case
+    L = _layer(cin, cout, 1, 1, 0, PRE_NONE, post, tc=True, seed=cin + cout + n)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16)
+    add = torch.randn(n, h, w, cout, generator=g) if addk == "f32" else None
+    mul = torch.randn(n, h, w, cout, generator=g).to(torch.bfloat16) if mul_mode is not None else None
+    LD = _to_dev(L)
+    dref = torch.empty(n, h, w, cout) if want_dact else None
+    _, ref = emu_ops.conv2d_tc(x, L, want_bf16=False, want_f32=True, add=add, mul=mul, mul_mode=mul_mode or 0, dact_out=dref)
+    dgot = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16) if want_dact else None
+    ob, of = ops.conv2d_tc(x.to(DEV), LD, want_bf16=wb, want_f32=wf, add=add.to(DEV) if add is not None else None,
+                           mul=mul.to(DEV) if mul is not None else None, mul_mode=mul_mode or 0, dact_out=dgot)
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    if wf:
+        assert (of.cpu() - ref).abs().max().item() <= 2e-3 * scale
+    if wb:
+        assert (ob.float().cpu() - ref).abs().max().item() <= 1e-2 * scale
+    if want_dact:
+        assert (dgot.float().cpu() - dref).abs().max().item() <= 2e-2
+
+
 @pytest.mark.parametrize("n,h,w,c", [(37, 32, 32, 64), (150, 16, 16, 128), (3, 64, 64, 64), (5, 16, 16, 256)])
 def test_conv3x3_fused_channel_sums(n, h, w, c):
     """SE squeeze fused into the conv epilogue: the sums written next to the bf16 output equal ga_channel_sum of that output (same
