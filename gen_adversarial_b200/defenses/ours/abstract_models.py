@@ -116,6 +116,9 @@ class MLVGMDefenseModel(ABC):
         self._graphs = {}
         self.noise_seed = None          # None: a fresh seed is drawn from torch's CPU generator on every call
         self.sample_offset = 0          # global index of sample 0 (data-parallel shards keep results G-independent)
+        self.streams = 1                # set_streams(k): no-grad calls split the batch over k CUDA streams
+        self._side_streams = []
+        self._stream_warm = set()
 
     @abstractmethod
     def load_autoencoder(self, model_path: str, device: str):
@@ -139,6 +142,54 @@ class MLVGMDefenseModel(ABC):
         if not on:
             self._graphs.clear()
         return self
+
+    def set_streams(self, k: int = 2):
+        """Run no-grad calls as k part-batches on k CUDA streams: the HBM-bound kernels of one part (SE / residual, channel sums, latent
+        mixing) fill the SMs' idle memory pipes while the tensor-core / FMA-bound kernels of another part run, and kernel tails overlap.
+        Results do not change: every kernel keys its Philox stream on the GLOBAL sample index (`sample_offset` + index inside the part)
+        and no kernel reduces across images.  Measured on B200, NVAE ids batch 512: +5% img/s at k = 2."""
+        self.streams = max(1, int(k))
+        self._graphs.clear()
+        return self
+
+    def _forward_parts(self, batch: torch.Tensor):
+        """`_forward_cuda` of the whole batch, or of `streams` contiguous parts on side streams joined back into the caller's stream."""
+        k, n = self.streams, batch.shape[0]
+        if k <= 1 or n < 2 * k or not batch.is_cuda or self._explicit_noise is not None:
+            return self._forward_cuda(batch)
+        bounds = [(n * i) // k for i in range(k + 1)]
+        sizes = tuple(bounds[i + 1] - bounds[i] for i in range(k))
+        cur = torch.cuda.current_stream()
+        self._alphas_device()                                   # host -> device refresh on the caller's stream, before the fork
+        seed_was, off_was = self.noise_seed, self.sample_offset
+        if seed_was is None:
+            self.noise_seed = self._next_seed()                 # one draw per call, as `_forward_cuda` makes for the whole batch
+        # the first call with these part sizes runs the parts back to back on the caller's stream: lazily built state (prepared weights,
+        # blur taps, the broadcast prior) is then created in stream order and only read afterwards
+        warm = sizes in self._stream_warm
+        self._stream_warm.add(sizes)
+        while len(self._side_streams) < k:
+            self._side_streams.append(torch.cuda.Stream(device=batch.device))
+        outs = []
+        try:
+            for i in range(k):
+                part = batch[bounds[i]:bounds[i + 1]]
+                self.sample_offset = off_was + bounds[i]
+                if not warm:
+                    outs.append(self._forward_cuda(part))
+                    continue
+                s = self._side_streams[i]
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    outs.append(self._forward_cuda(part))
+            if warm:
+                for s in self._side_streams[:k]:
+                    cur.wait_stream(s)
+        finally:
+            self.noise_seed, self.sample_offset = seed_was, off_was
+        preds = torch.cat([o[0] for o in outs], dim=0)
+        purified = torch.cat([o[1] for o in outs], dim=0)
+        return preds, purified
 
     def _alphas_device(self) -> torch.Tensor:
         """`interpolation_alphas` is a plain list that callers reassign between calls (common_utils.py:88); the
@@ -205,7 +256,7 @@ class MLVGMDefenseModel(ABC):
                 g = self._graphs[key] = GraphedForward(self, batch)
             preds, purified = g(self, batch)
         else:
-            preds, purified = self._forward_cuda(batch.detach())
+            preds, purified = self._forward_parts(batch.detach())
         if preds_only:
             return preds
         return preds, purified

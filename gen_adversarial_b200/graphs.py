@@ -59,7 +59,7 @@ class GraphedForward:
         def body():
             bump_seed_salt()
             with torch.no_grad():
-                return model._forward_cuda(self.x)
+                return model._forward_parts(self.x)
 
         self.graph, (self.preds, self.purified), self.nodes = _capture(body)
 
@@ -67,7 +67,7 @@ class GraphedForward:
     def make_key(model, batch):
         # everything a captured launch takes BY VALUE is part of the key (eps, blur, sample offset, the seed, the generator chunking)
         return (tuple(batch.shape), float(model.eps), bool(model.blur_input), int(model.sample_offset), len(model.interpolation_alphas),
-                model.noise_seed, getattr(model, "max_chunk", None))
+                model.noise_seed, getattr(model, "max_chunk", None), int(getattr(model, "streams", 1)))
 
     def __call__(self, model, batch: torch.Tensor):
         model._alphas_device()

@@ -29,6 +29,10 @@ __global__ void k(float* out, const float* in, long long* cycles) {
   const float w0 = in[threadIdx.x & 127], w1 = in[(threadIdx.x + 7) & 127];
   const float2 w2 = make_float2(w0, w1), v2 = make_float2(w1, w0);
   uint32_t saddr = (threadIdx.x & 31) * 4;
+  uint32_t h[NACC], g[NACC];
+  const uint32_t hw = 0x3c003800u ^ (threadIdx.x & 1), hv = 0x38003c00u ^ (threadIdx.x & 2);      // fp16 (1.0, 0.5) / (0.5, 1.0)
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) { h[i] = 0x3c003c00u + i; g[i] = threadIdx.x + i; }
   long long t0 = clock64();
   for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
@@ -46,12 +50,23 @@ __global__ void k(float* out, const float* in, long long* cycles) {
       if (MODE == 7) {                                                          // FFMA2 with per-iteration distinct operands (window)
         a2[i] = ffma2(a2[(i + 1) & (NACC - 1)], w2, a2[i]);
       }
+      if (MODE == 8) asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(hw), "r"(hv));                   // HFMA2 (fp16 pair)
+      if (MODE == 9) asm volatile("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(hw), "r"(hv));                  // HFMA2.BF16
+      if (MODE == 10) asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(h[(i + 1) & (NACC - 1)]), "r"(hv));   // HFMA2, rotating operands
+      if (MODE == 11) {                                                         // FFMA2 + one ALU op each: does the ALU op issue in FFMA2's 2nd cycle?
+        a2[i] = ffma2(w2, v2, a2[i]);
+        h[i] = (h[i] << 3) ^ hw;
+      }
+      if (MODE == 12) {                                                         // HFMA2 + one ALU op each
+        asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(hw), "r"(hv));
+        g[i] = (g[i] << 3) ^ hw;
+      }
     }
   }
   long long t1 = clock64();
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) s += a[i] + a2[i].x + a2[i].y;
+  for (int i = 0; i < NACC; ++i) s += a[i] + a2[i].x + a2[i].y + __uint_as_float(h[i] ^ g[i]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -94,6 +109,11 @@ int main() {
   run<3>("MUFU.TANH", out, in, cyc);
   run<4>("LDS.32 + FADD", out, in, cyc);
   run<5>("SHL + LOP3 + FADD", out, in, cyc);
+  run<8>("HFMA2 (f16x2)", out, in, cyc);
+  run<9>("HFMA2.BF16 (bf16x2)", out, in, cyc);
+  run<10>("HFMA2 (rotating operands)", out, in, cyc);
+  run<11>("FFMA2 + SHL/LOP3 pair", out, in, cyc);
+  run<12>("HFMA2 + SHL/LOP3 pair", out, in, cyc);
   cudaError_t e = cudaGetLastError();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;

@@ -151,6 +151,53 @@ def test_stochastic_by_default_and_seedable(c32_models):
     assert a.min() >= 0 and a.max() <= 1
 
 
+@pytest.mark.parametrize("n,k", [(8, 2), (7, 2), (9, 3), (3, 2)])
+def test_part_batches_on_streams_change_nothing(c32_models, n, k):
+    """`set_streams(k)`: k contiguous part-batches on k CUDA streams.  Philox streams are keyed by the global sample index and no kernel
+    reduces across images, so logits and purified images are bit-identical to the single-stream call (noise eps and sampling both on);
+    the same holds under CUDA-graph replay of the forked call."""
+    nv, vg = c32_models
+    clf = CelebaIdentityClassifier(vg, DEV, mode="bf16")
+    dm = NVAEDefenseModel(clf, nv, [0.5] * 24, 1.0, 2.0, True, DEV, mode="bf16")
+    dm.noise_seed = 23
+    x, _ = synth.synthetic_batch(n, seed=5)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        l1, p1 = dm(xd, preds_only=False)
+        dm.set_streams(k)
+        l2, p2 = dm(xd, preds_only=False)          # first call with these part sizes: parts run back to back on the caller's stream
+        l3, p3 = dm(xd, preds_only=False)          # forked
+        l4, p4 = dm(xd, preds_only=False)
+    torch.cuda.synchronize()
+    if n >= 2 * k:
+        assert len(dm._side_streams) == k
+    for l, p in ((l2, p2), (l3, p3), (l4, p4)):
+        assert torch.equal(l1, l) and torch.equal(p1, p)
+    # stochastic per call when no seed is pinned, also when forked
+    dm.noise_seed = None
+    with torch.no_grad():
+        _, a = dm(xd, preds_only=False)
+        _, b = dm(xd, preds_only=False)
+    assert (a - b).abs().max().item() > 1e-3
+
+
+def test_part_batches_under_graph_replay(c32_models):
+    nv, vg = c32_models
+    clf = CelebaIdentityClassifier(vg, DEV, mode="bf16")
+    dm = NVAEDefenseModel(clf, nv, [0.5] * 24, 1.0, 0.0, True, DEV, mode="bf16")
+    x, _ = synth.synthetic_batch(8, seed=6)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        dm.set_streams(2).enable_cuda_graph(True)
+        l_a, p_a = [t.clone() for t in dm(xd, preds_only=False)]
+        l_b, p_b = [t.clone() for t in dm(xd, preds_only=False)]
+        dm.enable_cuda_graph(False)
+    torch.cuda.synchronize()
+    assert p_a.shape == (8, 3, 64, 64) and torch.isfinite(p_a).all() and torch.isfinite(l_a).all()
+    assert p_a.min() >= 0 and p_a.max() <= 1
+    assert (p_a - p_b).abs().max().item() > 1e-4     # the salt advances between replays: fresh noise on both streams' kernels
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_normalizing_flow_checkpoint(mode):
     """A12: a checkpoint built with num_nf_cells = 1 (the real model's configuration is unknown): NF cells are applied after
