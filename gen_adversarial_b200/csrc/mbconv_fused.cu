@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
   float* s_dww = reinterpret_cast<float*>(sA2 + A2_BYTES);          // [2][25][64] depthwise taps of the current / next chunk
   float* s_be = s_dww + 2 * 25 * 64;
   float* s_dwb = s_be + p.hidden;
+  float* s_bp = s_dwb + p.hidden;                                   // [C] project bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.hidden / 64;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
   } else {
     // expand bias pre-halved: SiLU(v) = h + h tanh(h) with h = v/2 = fma(acc, 0.5, be/2) -- exact (power-of-two scaling), one FMA-pipe op less
     for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) { s_be[i] = 0.5f * p.be[i]; s_dwb[i] = p.dw_b[i]; }
+    for (int i = threadIdx.x - 32; i < C; i += MB_THREADS - 32) s_bp[i] = p.bp[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -311,21 +313,28 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
 #pragma unroll 1
     for (int m = 0; m < G::MT_OUT; ++m) {
       const int64_t pix = pix0 + m * 128 + q * 32 + lane;
+      // 64 accumulator columns in flight per tcgen05.wait (the round trip is ~1k clk for a lone warp; C / 16 of them in a row were 10% of
+      // the CTA's lifetime), then one full 128-byte line per thread
 #pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + PROJ_OFF + m * C + c0, r);
+      for (int c0 = 0; c0 < C; c0 += 64) {
+        uint32_t r[4][16];
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + PROJ_OFF + m * C + c0 + c16 * 16, r[c16]);
         tmem_ld_wait();
         if (pix < total_pix) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 b = __ldg(reinterpret_cast<const float2*>(p.bp + c0 + 2 * j));
-            pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + b.x, __uint_as_float(r[2 * j + 1]) + b.y);
-          }
           uint4* o = reinterpret_cast<uint4*>(p.out + pix * C + c0);
-          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          const uint32_t bp_a = smem_u32(s_bp) + c0 * 4;
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 b = lds_f2(bp_a + (c16 * 16 + 2 * j) * 4);
+              pk[j] = pack_bf16x2(__uint_as_float(r[c16][2 * j]) + b.x, __uint_as_float(r[c16][2 * j + 1]) + b.y);
+            }
+            o[2 * c16] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[2 * c16 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
         }
       }
     }
@@ -534,7 +543,7 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   using G = MbGeom<W_IMG>;
   constexpr int KB = C / 64;
   const int smem = 1024 /*align*/ + 1024 /*header*/ + G::MT_IN * KB * 16384 + NBUF * (KB * 8192 + C * 128) + 2 * G::MT_IN * 16384 +
-                   G::MT_OUT * 16384 + 2 * DWW_BYTES + 2 * p.hidden * 4;
+                   G::MT_OUT * 16384 + 2 * DWW_BYTES + 2 * p.hidden * 4 + C * 4;
   GA_CHECK(smem <= 227 * 1024, "ga_mbconv_fused: shared memory request %d too large", smem);
   static int configured = 0;
   if (configured < smem) {

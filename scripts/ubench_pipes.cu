@@ -57,6 +57,16 @@ __global__ void k(float* out, const float* in, long long* cycles) {
         a2[i] = ffma2(w2, v2, a2[i]);
         h[i] = (h[i] << 3) ^ hw;
       }
+      if (MODE == 13) { a2[i] = ffma2(w2, v2, a2[i]); a[i] = fmaf(a[i], w0, w1); }                  // FFMA2 + FFMA: does the scalar FMA ride a second pipe?
+      if (MODE == 14) {                                                                             // HFMA2 + FFMA
+        asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(hw), "r"(hv));
+        a[i] = fmaf(a[i], w0, w1);
+      }
+      if (MODE == 15) {                                                                             // HFMA2 + LDS.32 (the depthwise loop's pair)
+        asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(hw), "r"(__float_as_uint(sm[(saddr >> 2) + i * 32 + (it & 1) * 512])));
+      }
+      if (MODE == 16) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));      // MUFU.EX2
+      if (MODE == 17) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));      // MUFU.RCP
       if (MODE == 12) {                                                         // HFMA2 + one ALU op each
         asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(hw), "r"(hv));
         g[i] = (g[i] << 3) ^ hw;
@@ -114,6 +124,11 @@ int main() {
   run<10>("HFMA2 (rotating operands)", out, in, cyc);
   run<11>("FFMA2 + SHL/LOP3 pair", out, in, cyc);
   run<12>("HFMA2 + SHL/LOP3 pair", out, in, cyc);
+  run<16>("MUFU.EX2", out, in, cyc);
+  run<17>("MUFU.RCP", out, in, cyc);
+  run<13>("FFMA2 + FFMA (pairs/clk)", out, in, cyc);
+  run<14>("HFMA2 + FFMA (pairs/clk)", out, in, cyc);
+  run<15>("HFMA2 fed by LDS.32", out, in, cyc);
   cudaError_t e = cudaGetLastError();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
