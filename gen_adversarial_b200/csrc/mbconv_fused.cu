@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include "ga_common.cuh"
 #include "tc_ptx.cuh"
+#include "tc_host.cuh"
 
 namespace ga {
 
@@ -32,6 +33,7 @@ template <> struct MbGeom<32> { static constexpr int IMGS = 1, R_OUT = 8,  HALO 
 
 struct MbParams {
   int N, H;                     // images, image height (= width = W_IMG)
+  int n_tiles;                  // spatial tiles of the batch; CTA b walks tiles b, b + gridDim.x, ... (persistent, one CTA per SM)
   int hidden;                   // 6C (multiple of 64)
   const float* be;              // [hidden] expand bias
   const float* dw_w;            // [hidden/64][25][64] depthwise taps, chunk-major (one 6400-byte bulk copy per chunk)
@@ -118,7 +120,9 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
   uint64_t* dww_full = bars + 16;        // [2]
   uint64_t* h_full = bars + 18;          // [2]
   uint64_t* h_empty = bars + 20;         // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* x_free = bars + 22;          // all expand MMAs of a tile have read X: the next tile may be loaded
+  uint64_t* proj_empty = bars + 23;      // the epilogue has drained the project accumulator
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 24);
   uint8_t* sX = hdr + 1024;
   uint8_t* sWe = sX + X_BYTES;
   uint8_t* sWp = sWe + NBUF * WE_BYTES;
@@ -131,6 +135,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.hidden / 64;
+  // persistent: this CTA's tiles, and ONE chunk counter g over all of them (chunk k of local tile i is g = i * nch + k).  Every ring
+  // (weights, expand accumulator, H, A2, taps) is indexed by g, so the next tile's first chunks are loaded / expanded / activated while
+  // the depthwise warps finish this tile and the activation warps drain its project accumulator: no per-tile head or tail.
+  const int my_tiles = ((int)p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int g_total = my_tiles * nch;
   // debug timeline: lane 0 of every warp stamps clock64 at the role's synchronisation points (traced CTAs: the first 4 and 4 of a later wave)
   const int tr_cta = TRACE ? (blockIdx.x < 4 ? (int)blockIdx.x : ((blockIdx.x >= 1184 && blockIdx.x < 1188) ? (int)blockIdx.x - 1180 : -1)) : -1;
   auto stamp = [&](int k, int ev) {
@@ -139,11 +148,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
   };
   stamp(0, 7);
 
-  // ---- tile -> (first image, first output row)
-  int n0, y0;
-  if (W_IMG == 8) { n0 = blockIdx.x * 2; y0 = 0; }
-  else if (W_IMG == 16) { n0 = blockIdx.x; y0 = 0; }
-  else { n0 = blockIdx.x / (W_IMG / G::R_OUT); y0 = (blockIdx.x % (W_IMG / G::R_OUT)) * G::R_OUT; }
+  // ---- local tile i -> (first image, first output row)
+  auto tile_origin = [&](int i, int& n0, int& y0) {
+    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    if (W_IMG == 8) { n0 = t * 2; y0 = 0; }
+    else if (W_IMG == 16) { n0 = t; y0 = 0; }
+    else { n0 = t / (W_IMG / G::R_OUT); y0 = (t % (W_IMG / G::R_OUT)) * G::R_OUT; }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmWe); tma_prefetch_desc(&tmWp);
@@ -154,6 +165,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       mbar_init(&h_full[i], 4); mbar_init(&h_empty[i], 8);
     }
     mbar_init(a2_full, 8); mbar_init(a2_empty, 1); mbar_init(proj_full, 1);      // a2_full: one arrival per depthwise warp
+    mbar_init(x_free, 1); mbar_init(proj_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -174,31 +186,44 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     if (elect_one_sync()) {      // (elected lane, not `lane == 0`: uniform-datapath instructions then issue without an elect / branch loop each)
       constexpr uint32_t idesc_e = make_idesc(128, 64);
       constexpr uint32_t idesc_p = make_idesc(128, C);
-      auto load_we = [&](int j) {
-        const int b = j % NBUF;
+      auto load_we = [&](int gj) {
+        const int b = gj % NBUF, j = gj % nch;
         mbar_expect_tx(&we_full[b], WE_BYTES);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmWe, &we_full[b], sWe + b * WE_BYTES + kb * 8192, kb * 64, j * 64);
       };
-      auto load_dww = [&](int j) {
-        mbar_expect_tx(&dww_full[j & 1], DWW_BYTES);
-        bulk_load_1d(s_dww + (j & 1) * 25 * 64, p.dw_w + (size_t)j * 25 * 64, DWW_BYTES, &dww_full[j & 1]);
+      auto load_dww = [&](int gj) {
+        mbar_expect_tx(&dww_full[gj & 1], DWW_BYTES);
+        bulk_load_1d(s_dww + (gj & 1) * 25 * 64, p.dw_w + (size_t)(gj % nch) * 25 * 64, DWW_BYTES, &dww_full[gj & 1]);
       };
-      auto load_wp = [&](int j) {
-        const int b = j % NBUF;
+      auto load_wp = [&](int gj) {
+        const int b = gj % NBUF, j = gj % nch;
         mbar_expect_tx(&wp_full[b], WP_BYTES);
         tma_load_2d(&tmWp, &wp_full[b], sWp + b * WP_BYTES, j * 64, 0);
       };
-      auto expand = [&](int k) {
-        if (k >= 1) {                                     // lazy refill of the buffer expand(k-1) has finished with
-          const int j = k - 1 + NBUF;
-          if (j < nch) { mbar_wait(&we_empty[(k - 1) % NBUF], ((k - 1) / NBUF) & 1); load_we(j); }
+      auto load_x = [&](int i) {
+        int n0, y0;
+        tile_origin(i, n0, y0);
+        mbar_expect_tx(x_full, X_BYTES);
+        for (int m = 0; m < G::MT_IN; ++m)
+          for (int kb = 0; kb < KB; ++kb) {
+            uint8_t* dst = sX + (m * KB + kb) * 16384;
+            if (W_IMG == 8) tma_load_4d(&tmX, x_full, dst, kb * 64, 0, 0, n0);
+            else tma_load_4d(&tmX, x_full, dst, kb * 64, 0, y0 - G::HALO + m * (128 / W_IMG), n0);
+          }
+      };
+      auto expand = [&](int g) {
+        if (g >= 1) {                                     // lazy refill of the buffer expand(g-1) has finished with
+          const int gj = g - 1 + NBUF;
+          if (gj < g_total) { mbar_wait(&we_empty[(g - 1) % NBUF], ((g - 1) / NBUF) & 1); load_we(gj); }
         }
-        mbar_wait(&we_full[k % NBUF], (k / NBUF) & 1);
-        if (k >= 2) mbar_wait(&exp_empty[k & 1], ((k - 2) >> 1) & 1);
+        const int i = g / nch, k = g - i * nch;
+        if (k == 0) { mbar_wait(x_full, i & 1); if (i == 0) stamp(0, 6); }
+        mbar_wait(&we_full[g % NBUF], (g / NBUF) & 1);
+        if (g >= 2) mbar_wait(&exp_empty[g & 1], ((g - 2) >> 1) & 1);
         tc_fence_after();
-        const uint32_t we_addr = smem_u32(sWe + (k % NBUF) * WE_BYTES);
+        const uint32_t we_addr = smem_u32(sWe + (g % NBUF) * WE_BYTES);
         for (int m = 0; m < G::MT_IN; ++m) {
-          const uint32_t d = tmem_base + (k & 1) * EXP_COLS + m * 64;
+          const uint32_t d = tmem_base + (g & 1) * EXP_COLS + m * 64;
           for (int kb = 0; kb < KB; ++kb) {
             const uint32_t a_addr = smem_u32(sX + (m * KB + kb) * 16384);
 #pragma unroll
@@ -206,22 +231,29 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
               umma_bf16(d, make_smem_desc(a_addr + kk * 32), make_smem_desc(we_addr + kb * 8192 + kk * 32), idesc_e, (kb > 0 || kk > 0) ? 1u : 0u);
           }
         }
-        umma_commit(&exp_full[k & 1]);
-        umma_commit(&we_empty[k % NBUF]);
-        stamp(k, 0);
-      };
-      auto project = [&](int k) {
-        if (k >= 1) {
-          const int j = k - 1 + NBUF;
-          if (j < nch) { mbar_wait(&wp_empty[(k - 1) % NBUF], ((k - 1) / NBUF) & 1); load_wp(j); }
+        umma_commit(&exp_full[g & 1]);
+        umma_commit(&we_empty[g % NBUF]);
+        stamp(g, 0);
+        if (k == nch - 1 && i + 1 < my_tiles) {           // the tile's last expand: X is free once these MMAs have run -> prefetch the next tile
+          umma_commit(x_free);
+          mbar_wait(x_free, i & 1);
+          load_x(i + 1);
         }
-        stamp(k, 1);
-        mbar_wait(a2_full, k & 1);
-        stamp(k, 2);
-        if (k + 2 < nch) load_dww(k + 2);                 // every SIMT thread has taken chunk k's taps into registers
-        mbar_wait(&wp_full[k % NBUF], (k / NBUF) & 1);
+      };
+      auto project = [&](int g) {
+        if (g >= 1) {
+          const int gj = g - 1 + NBUF;
+          if (gj < g_total) { mbar_wait(&wp_empty[(g - 1) % NBUF], ((g - 1) / NBUF) & 1); load_wp(gj); }
+        }
+        stamp(g, 1);
+        mbar_wait(a2_full, g & 1);
+        stamp(g, 2);
+        if (g + 2 < g_total) load_dww(g + 2);             // every SIMT thread has taken chunk g's taps into registers
+        mbar_wait(&wp_full[g % NBUF], (g / NBUF) & 1);
+        const int i = g / nch, k = g - i * nch;
+        if (k == 0 && i >= 1) mbar_wait(proj_empty, (i - 1) & 1);      // the previous tile's accumulator has been read out
         tc_fence_after();
-        const uint32_t wp_addr = smem_u32(sWp + (k % NBUF) * WP_BYTES);
+        const uint32_t wp_addr = smem_u32(sWp + (g % NBUF) * WP_BYTES);
         for (int m = 0; m < G::MT_OUT; ++m) {
           const uint32_t a_addr = smem_u32(sA2 + m * 16384);
 #pragma unroll
@@ -230,26 +262,18 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
                       (k > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(a2_empty);
-        umma_commit(&wp_empty[k % NBUF]);
-        stamp(k, 3);
+        umma_commit(&wp_empty[g % NBUF]);
+        stamp(g, 3);
         if (k == nch - 1) umma_commit(proj_full);
       };
-      // ---- prologue: the activation tile (stays resident) and the first weight chunks
-      mbar_expect_tx(x_full, X_BYTES);
-      for (int m = 0; m < G::MT_IN; ++m)
-        for (int kb = 0; kb < KB; ++kb) {
-          uint8_t* dst = sX + (m * KB + kb) * 16384;
-          if (W_IMG == 8) tma_load_4d(&tmX, x_full, dst, kb * 64, 0, 0, n0);
-          else tma_load_4d(&tmX, x_full, dst, kb * 64, 0, y0 - G::HALO + m * (128 / W_IMG), n0);
-        }
-      for (int j = 0; j < NBUF && j < nch; ++j) { load_we(j); load_wp(j); }
-      for (int j = 0; j < 2 && j < nch; ++j) load_dww(j);
-      mbar_wait(x_full, 0);
-      stamp(0, 6);
+      // ---- prologue: the first activation tile and the first weight chunks
+      load_x(0);
+      for (int j = 0; j < NBUF && j < g_total; ++j) { load_we(j); load_wp(j); }
+      for (int j = 0; j < 2 && j < g_total; ++j) load_dww(j);
       expand(0);
-      for (int k = 0; k < nch; ++k) {
-        if (k + 1 < nch) expand(k + 1);
-        project(k);
+      for (int g = 0; g < g_total; ++g) {
+        if (g + 1 < g_total) expand(g + 1);
+        project(g);
       }
     }
     __syncwarp();
@@ -257,14 +281,61 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     // ======================================================================= activation warps (1-4, one per TMEM lane quadrant):
     // expand accumulator -> + bias -> SiLU -> bf16 -> H[k & 1] (swizzled rows), one chunk ahead of the depthwise warps
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-    for (int k = 0; k < nch; ++k) {
-      stamp(k, 0);
-      mbar_wait_backoff(&exp_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
-      stamp(k, 1);
-      if (k >= 2) mbar_wait_backoff(&h_empty[k & 1], ((k - 2) >> 1) & 1, (uint32_t)p.sleep_ns);          // depthwise(k-2) has read this H buffer
-      stamp(k, 2);
+    // ---- project accumulator of local tile j -> + bias -> r (bf16) -> HBM
+    auto epilogue = [&](int j) {
+      int n0, y0;
+      tile_origin(j, n0, y0);
+      stamp(j, 4);
+      mbar_wait_backoff(proj_full, j & 1, (uint32_t)p.sleep_ns);
+      stamp(j, 5);
       tc_fence_after();
-      const uint32_t hb = smem_u32(sH) + (k & 1) * H_BYTES;
+      const int64_t pix0 = (W_IMG == 32) ? ((int64_t)n0 * p.H + y0) * W_IMG : (int64_t)n0 * p.H * W_IMG;
+      const int64_t total_pix = (int64_t)p.N * p.H * W_IMG;
+#pragma unroll 1
+      for (int m = 0; m < G::MT_OUT; ++m) {
+        const int64_t pix = pix0 + m * 128 + q * 32 + lane;
+        // 64 accumulator columns in flight per tcgen05.wait (the round trip is ~1k clk for a lone warp; C / 16 of them in a row were 10% of
+        // the CTA's lifetime), then one full 128-byte line per thread
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 64) {
+          uint32_t r[4][16];
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + PROJ_OFF + m * C + c0 + c16 * 16, r[c16]);
+          tmem_ld_wait();
+          if (m == G::MT_OUT - 1 && c0 + 64 >= C) {       // last read of the accumulator: hand it back before the stores go out
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(proj_empty);
+          }
+          if (pix < total_pix) {
+            uint4* o = reinterpret_cast<uint4*>(p.out + pix * C + c0);
+            const uint32_t bp_a = smem_u32(s_bp) + c0 * 4;
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float2 b = lds_f2(bp_a + (c16 * 16 + 2 * jj) * 4);
+                pk[jj] = pack_bf16x2(__uint_as_float(r[c16][2 * jj]) + b.x, __uint_as_float(r[c16][2 * jj + 1]) + b.y);
+              }
+              o[2 * c16] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              o[2 * c16 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+      }
+    };
+    int ti = 0, k = 0, n0, y0;
+    tile_origin(0, n0, y0);
+    const int epi_after = nch > 1 ? 1 : 0;   // the previous tile is drained after this tile's second chunk has been activated (see below)
+    for (int g = 0; g < g_total; ++g) {
+      stamp(g, 0);
+      mbar_wait_backoff(&exp_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
+      stamp(g, 1);
+      if (g >= 2) mbar_wait_backoff(&h_empty[g & 1], ((g - 2) >> 1) & 1, (uint32_t)p.sleep_ns);          // depthwise(g-2) has read this H buffer
+      stamp(g, 2);
+      tc_fence_after();
+      const uint32_t hb = smem_u32(sH) + (g & 1) * H_BYTES;
       const uint32_t be_a = smem_u32(s_be) + k * 256;
 #pragma unroll
       for (int m = 0; m < G::MT_IN; ++m) {
@@ -280,7 +351,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
         uint32_t r[4][16];
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16)
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (k & 1) * EXP_COLS + m * 64 + c16 * 16, r[c16]);
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * EXP_COLS + m * 64 + c16 * 16, r[c16]);
         tmem_ld_wait();
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
@@ -300,44 +371,14 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&exp_empty[k & 1]); mbar_arrive(&h_full[k & 1]); }
-      stamp(k, 3);
+      if (lane == 0) { mbar_arrive(&exp_empty[g & 1]); mbar_arrive(&h_full[g & 1]); }
+      stamp(g, 3);
+      // the previous tile's accumulator completes about when the depthwise warps start on this tile's first chunk; by then this warp has
+      // produced the chunk after it, so draining now keeps the depthwise warps fed (activation first, epilogue second)
+      if (ti >= 1 && k == epi_after) epilogue(ti - 1);
+      if (++k == nch) { k = 0; ++ti; tile_origin(ti, n0, y0); }
     }
-    // ---- project accumulator -> + bias -> r (bf16) -> HBM
-    stamp(0, 4);
-    mbar_wait_backoff(proj_full, 0, (uint32_t)p.sleep_ns);
-    stamp(0, 5);
-    tc_fence_after();
-    const int64_t pix0 = (W_IMG == 32) ? ((int64_t)n0 * p.H + y0) * W_IMG : (int64_t)n0 * p.H * W_IMG;
-    const int64_t total_pix = (int64_t)p.N * p.H * W_IMG;
-#pragma unroll 1
-    for (int m = 0; m < G::MT_OUT; ++m) {
-      const int64_t pix = pix0 + m * 128 + q * 32 + lane;
-      // 64 accumulator columns in flight per tcgen05.wait (the round trip is ~1k clk for a lone warp; C / 16 of them in a row were 10% of
-      // the CTA's lifetime), then one full 128-byte line per thread
-#pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 64) {
-        uint32_t r[4][16];
-#pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + PROJ_OFF + m * C + c0 + c16 * 16, r[c16]);
-        tmem_ld_wait();
-        if (pix < total_pix) {
-          uint4* o = reinterpret_cast<uint4*>(p.out + pix * C + c0);
-          const uint32_t bp_a = smem_u32(s_bp) + c0 * 4;
-#pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 b = lds_f2(bp_a + (c16 * 16 + 2 * j) * 4);
-              pk[j] = pack_bf16x2(__uint_as_float(r[c16][2 * j]) + b.x, __uint_as_float(r[c16][2 * j + 1]) + b.y);
-            }
-            o[2 * c16] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            o[2 * c16 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
-      }
-    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
   } else {
     // ======================================================================= depthwise warps (5-12): 5x5 + bias + SiLU: H -> A2
     const int sw = p.act_hi ? warp - 1 : warp - 5;   // 0..7
@@ -364,20 +405,20 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       // accumulates in ONE pass -- no input row is read twice -- and the 25 multiply-adds per output pair are 25 HFMA2 instead of 25 FFMA2
       // (half the fp32-pipe cycles) with no unpack.  The 25-term fp16 accumulation adds ~1e-3 relative rounding noise, about half of what the
       // bf16 rounding of the result adds anyway; the bias, SiLU and the bf16 rounding stay fp32.
-      for (int k = 0; k < nch; ++k) {
+      for (int g = 0, kc = 0; g < g_total; ++g, kc = (kc + 1 == nch) ? 0 : kc + 1) {
         uint32_t wt[25];
-        stamp(k, 0);
-        mbar_wait_backoff(&dww_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
+        stamp(g, 0);
+        mbar_wait_backoff(&dww_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
         {
-          const uint32_t wsrc = smem_u32(s_dww) + ((k & 1) * 25 * 64 + 2 * lane) * 4;
+          const uint32_t wsrc = smem_u32(s_dww) + ((g & 1) * 25 * 64 + 2 * lane) * 4;
 #pragma unroll
           for (int t = 0; t < 25; ++t) { const float2 w = lds_f2(wsrc + t * 256); wt[t] = pack_f16x2(w.x, w.y); }
         }
-        const float2 b2 = lds_f2(smem_u32(s_dwb) + (k * 64 + 2 * lane) * 4);
-        stamp(k, 1);
-        mbar_wait_backoff(&h_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
-        stamp(k, 2);
-        const uint32_t hb = smem_u32(sH) + (k & 1) * H_BYTES;
+        const float2 b2 = lds_f2(smem_u32(s_dwb) + (kc * 64 + 2 * lane) * 4);
+        stamp(g, 1);
+        mbar_wait_backoff(&h_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
+        stamp(g, 2);
+        const uint32_t hb = smem_u32(sH) + (g & 1) * H_BYTES;
         constexpr int RP = G::R_OUT;
         uint32_t acc[RP][G::STRIP_W];
 #pragma unroll
@@ -405,10 +446,10 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&h_empty[k & 1]);
-        stamp(k, 3);
-        if (k >= 1) mbar_wait_backoff(a2_empty, (k - 1) & 1, (uint32_t)p.sleep_ns);
-        stamp(k, 4);
+        if (lane == 0) mbar_arrive(&h_empty[g & 1]);
+        stamp(g, 3);
+        if (g >= 1) mbar_wait_backoff(a2_empty, (g - 1) & 1, (uint32_t)p.sleep_ns);
+        stamp(g, 4);
 #pragma unroll
         for (int oy = 0; oy < RP; ++oy)
 #pragma unroll
@@ -419,23 +460,23 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a2_full);
-        stamp(k, 5);
+        stamp(g, 5);
       }
     } else
-    for (int k = 0; k < nch; ++k) {
+    for (int g = 0, kc = 0; g < g_total; ++g, kc = (kc + 1 == nch) ? 0 : kc + 1) {
       float2 wt[25];
       {
-        stamp(k, 0);
-        mbar_wait_backoff(&dww_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
-        const uint32_t wsrc = smem_u32(s_dww) + ((k & 1) * 25 * 64 + 2 * lane) * 4;
+        stamp(g, 0);
+        mbar_wait_backoff(&dww_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
+        const uint32_t wsrc = smem_u32(s_dww) + ((g & 1) * 25 * 64 + 2 * lane) * 4;
 #pragma unroll
         for (int t = 0; t < 25; ++t) wt[t] = lds_f2(wsrc + t * 256);
       }
-      const float2 b2 = lds_f2(smem_u32(s_dwb) + (k * 64 + 2 * lane) * 4);
-      stamp(k, 1);
-      mbar_wait_backoff(&h_full[k & 1], (k >> 1) & 1, (uint32_t)p.sleep_ns);
-      stamp(k, 2);
-      const uint32_t hb = smem_u32(sH) + (k & 1) * H_BYTES;
+      const float2 b2 = lds_f2(smem_u32(s_dwb) + (kc * 64 + 2 * lane) * 4);
+      stamp(g, 1);
+      mbar_wait_backoff(&h_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
+      stamp(g, 2);
+      const uint32_t hb = smem_u32(sH) + (g & 1) * H_BYTES;
       // the strip's rows are produced in passes of RP rows (RP + 4 input rows each): RP x STRIP_W accumulators + 25 taps stay in
       // registers under the 128-register cap of a 13-warp CTA (16K registers per SM sub-partition, 4 warps on one of them)
       constexpr int RP = (G::R_OUT * G::STRIP_W > 16) ? G::R_OUT / 2 : G::R_OUT;
@@ -469,11 +510,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
         }
         if (pass == G::R_OUT / RP - 1) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&h_empty[k & 1]);                     // this warp is done reading H[k & 1]
+          if (lane == 0) mbar_arrive(&h_empty[g & 1]);                     // this warp is done reading H[g & 1]
         }
-        if (pass == 0) stamp(k, 3);
-        if (pass == 0 && k >= 1) mbar_wait_backoff(a2_empty, (k - 1) & 1, (uint32_t)p.sleep_ns); // project(k-1) has consumed A2
-        if (pass == 0) stamp(k, 4);
+        if (pass == 0) stamp(g, 3);
+        if (pass == 0 && g >= 1) mbar_wait_backoff(a2_empty, (g - 1) & 1, (uint32_t)p.sleep_ns); // project(k-1) has consumed A2
+        if (pass == 0) stamp(g, 4);
 #pragma unroll
         for (int oy = 0; oy < RP; ++oy)
 #pragma unroll
@@ -485,7 +526,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
       // every depthwise warp arrives on its own (count 8): no warp waits for the slowest one at a CTA barrier, it goes on to the next
       // chunk's taps / H tile and only meets the others again at a2_empty, after its next pass-0 accumulation (ncu: 13% barrier stalls)
       if (lane == 0) mbar_arrive(a2_full);
-      stamp(k, 5);
+      stamp(g, 5);
     }
   }
   stamp(1, 7);
@@ -559,7 +600,10 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   if (W_IMG == 8) tiles = (x->n + 1) / 2;
   else if (W_IMG == 16) tiles = x->n;
   else tiles = x->n * (W_IMG / G::R_OUT);
-  mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16><<<tiles, MB_THREADS, smem, s>>>(tmX, tmWe, tmWp, p);
+  MbParams q = p;
+  q.n_tiles = tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16><<<grid, MB_THREADS, smem, s>>>(tmX, tmWe, tmWp, q);
   GA_LAUNCH_OK();
   return 0;
 }

@@ -36,7 +36,10 @@ def _dev(L):
 
 
 @pytest.mark.parametrize("n,w,c,hidden", [(3, 8, 256, 1536), (2, 8, 256, 64), (2, 16, 128, 768), (1, 16, 128, 128),
-                                          (2, 32, 64, 384), (1, 32, 64, 192), (5, 32, 64, 64)])
+                                          (2, 32, 64, 384), (1, 32, 64, 192), (5, 32, 64, 64),
+                                          # more tiles than SMs: the persistent CTAs walk 2-3 tiles each (cross-tile pipelining of the rings)
+                                          (75, 32, 64, 128), (40, 32, 64, 64), (301, 8, 256, 128), (297, 8, 256, 64), (150, 16, 128, 192),
+                                          (149, 16, 128, 64)])
 def test_mbconv_fused_matches_three_kernels(n, w, c, hidden):
     e, dw_w, dw_b, p = _cell(c, hidden, seed=n + w + hidden)
     x = torch.randn(n, w, w, c, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
