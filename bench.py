@@ -60,7 +60,7 @@ YAML = {   # /root/reference/configs/*.yaml, verbatim
              "alpha_attenuation": 0.7, "initial_noise_eps": 0.0, "gaussian_blur_input": True},
 }
 LEARNED_BLUR_IDS, COSINE_NOISE_IDS = YAML["purify"], YAML["pgd"]
-DEFAULT_BATCH = {"purify": 512, "pgd": 1024, "gender": 128, "cars": 256}
+DEFAULT_BATCH = {"purify": 1024, "pgd": 1024, "gender": 128, "cars": 256}
 RESOLUTION = {"purify": (3, 64, 64), "pgd": (3, 64, 64), "gender": (3, 256, 256), "cars": (3, 128, 128)}
 N_CLASSES = {"purify": 100, "pgd": 100, "gender": 2, "cars": 4}
 WORKLOAD_TEXT = {
