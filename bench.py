@@ -520,7 +520,7 @@ def run_ours(args):
     use_graph = (args.cuda_graph == 1) or (args.cuda_graph < 0 and (pgd or wl == "purify"))
     t_start = time.perf_counter()
     dm = make_ours(wl, mode, dev, args.chunk)
-    n_streams = args.streams if args.streams > 0 else (2 if wl == "purify" else 1)
+    n_streams = args.streams if args.streams > 0 else (2 if wl in ("purify", "pgd") else 1)
     dm.set_streams(n_streams)              # public API: no-grad calls run as part-batches on CUDA streams (results unchanged)
     main = measure(ctx, dm, wl, B, args.steps, args.warmup, mode, use_graph and not sg, args.pgd_steps, sample_clocks=True)
     log(f"[bench] {wl}: {main['value']:.1f} img/s resident, {main['e2e']['value']:.1f} e2e ({time.perf_counter() - t_start:.0f} s)")
@@ -553,6 +553,7 @@ def run_ours(args):
         # ---- configs[4]: PGD-Linf, short run (1 attack of 50 iterations per rank), CUDA-graph replay of one iteration
         try:
             dmp = make_ours("pgd", mode, dev)
+            dmp.set_streams(n_streams)
             m = measure(ctx, dmp, "pgd", args.pgd_batch, 1, 1, mode, True, args.pgd_steps)
             r_pgd, _ = instrumented_pass(ctx, dmp, "pgd", m["_x_dev"][:min(args.pgd_batch, 512)], m["_y_dev"][:min(args.pgd_batch, 512)], 1, 0.0)
             r_pgd["share_of_step"] = None
@@ -618,7 +619,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--streams", type=int, default=0, help="part-batches / CUDA streams per call (0: 2 for purify, 1 otherwise)")
+    ap.add_argument("--streams", type=int, default=0, help="part-batches / CUDA streams per call (0: 2 for purify and pgd, 1 otherwise)")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 512 purify / 1024 pgd: 95 GB of tape + activations)")
     ap.add_argument("--workload", default="purify", choices=["purify", "pgd", "gender", "cars"])
     ap.add_argument("--chunk", type=int, default=0, help="generator batch chunk of the StyleGAN workloads (0: automatic)")

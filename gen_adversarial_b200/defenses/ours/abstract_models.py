@@ -152,20 +152,21 @@ class MLVGMDefenseModel(ABC):
         self._graphs.clear()
         return self
 
-    def _forward_parts(self, batch: torch.Tensor):
-        """`_forward_cuda` of the whole batch, or of `streams` contiguous parts on side streams joined back into the caller's stream."""
+    def _run_parts(self, tag: str, fn, batch: torch.Tensor):
+        """fn(part, lo, hi) for `streams` contiguous parts [lo, hi) of the batch, each on its own side stream, joined back into the caller's
+        stream -> list of fn's results, or None when the call should not be split (one stream, tiny batch, explicit noise)."""
         k, n = self.streams, batch.shape[0]
         if k <= 1 or n < 2 * k or not batch.is_cuda or self._explicit_noise is not None:
-            return self._forward_cuda(batch)
+            return None
         bounds = [(n * i) // k for i in range(k + 1)]
-        sizes = tuple(bounds[i + 1] - bounds[i] for i in range(k))
+        sizes = (tag,) + tuple(bounds[i + 1] - bounds[i] for i in range(k))
         cur = torch.cuda.current_stream()
         self._alphas_device()                                   # host -> device refresh on the caller's stream, before the fork
         seed_was, off_was = self.noise_seed, self.sample_offset
         if seed_was is None:
-            self.noise_seed = self._next_seed()                 # one draw per call, as `_forward_cuda` makes for the whole batch
+            self.noise_seed = self._next_seed()                 # one draw per call, as the unsplit call makes for the whole batch
         # the first call with these part sizes runs the parts back to back on the caller's stream: lazily built state (prepared weights,
-        # blur taps, the broadcast prior) is then created in stream order and only read afterwards
+        # dgrad layers, blur taps, the broadcast prior) is then created in stream order and only read afterwards
         warm = sizes in self._stream_warm
         self._stream_warm.add(sizes)
         while len(self._side_streams) < k:
@@ -176,20 +177,25 @@ class MLVGMDefenseModel(ABC):
                 part = batch[bounds[i]:bounds[i + 1]]
                 self.sample_offset = off_was + bounds[i]
                 if not warm:
-                    outs.append(self._forward_cuda(part))
+                    outs.append(fn(part, bounds[i], bounds[i + 1]))
                     continue
                 s = self._side_streams[i]
                 s.wait_stream(cur)
                 with torch.cuda.stream(s):
-                    outs.append(self._forward_cuda(part))
+                    outs.append(fn(part, bounds[i], bounds[i + 1]))
             if warm:
                 for s in self._side_streams[:k]:
                     cur.wait_stream(s)
         finally:
             self.noise_seed, self.sample_offset = seed_was, off_was
-        preds = torch.cat([o[0] for o in outs], dim=0)
-        purified = torch.cat([o[1] for o in outs], dim=0)
-        return preds, purified
+        return outs
+
+    def _forward_parts(self, batch: torch.Tensor):
+        """`_forward_cuda` of the whole batch, or of `streams` contiguous parts on side streams."""
+        outs = self._run_parts("fwd", lambda part, lo, hi: self._forward_cuda(part), batch)
+        if outs is None:
+            return self._forward_cuda(batch)
+        return torch.cat([o[0] for o in outs], dim=0), torch.cat([o[1] for o in outs], dim=0)
 
     def _alphas_device(self) -> torch.Tensor:
         """`interpolation_alphas` is a plain list that callers reassign between calls (common_utils.py:88); the
@@ -270,10 +276,21 @@ class MLVGMDefenseModel(ABC):
         (what `torch.autograd.grad(F.cross_entropy(net(x), y), [x])` returns, untargeted.py:146,201) without going through
         torch's autograd engine.  -> (loss[n], grad (n,C,H,W) fp32, pred[n] int32).  `counter`: optional uint64 device
         scalar accumulating argmax == label."""
+        n = batch.shape[0]
+        outs = self._run_parts("grad", lambda part, lo, hi: self._loss_input_grad_one(part, labels[lo:hi], counter, (hi - lo) / n), batch.detach())
+        if outs is None:
+            return self._loss_input_grad_one(batch, labels, counter, 1.0)
+        return tuple(torch.cat([o[j] for o in outs], dim=0) for j in range(3))
+
+    def _loss_input_grad_one(self, batch, labels, counter, weight: float):
+        """`weight` = this part's share of the batch: the loss kernel differentiates the mean over ITS rows, the caller wants the mean over
+        the whole batch (exact for the power-of-two shares of an even split)"""
         from ...autograd import Tape
         tape = Tape()
         preds, _ = self._forward_cuda(batch.detach(), tape=tape)
         loss, dlogits, pred = ops.softmax_xent(preds, labels, want_grad=True, counter=counter)
+        if weight != 1.0:
+            dlogits.mul_(weight)
         g_cls = self.classifier.classifier.backward(tape.vgg, dlogits)
         g_x = self.autoencoder.backward(tape.nvae, None, g_cls)
         gx = ops.preprocess_bwd(g_x, tape.pre, bool(self.blur_input), normalize=True, taps_cache=self._taps_cache)

@@ -421,3 +421,34 @@ def test_clean_counts_identical_on_64_images(c32_models):
             # bf16 path: not a north-star gate (counts must be identical for the fp32 path only); measured 4 of 64 arg-maxes differ on
             # this random-init, near-tied 100-class head (logits rel err 2.3e-2) -- gated so that a regression shows
             assert diff <= 6
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_loss_input_grad_on_part_batches_changes_nothing(mode):
+    """`set_streams(2)`: the fused attack primitive runs two half batches on two streams (taping forward + dgrad sweep each) with the
+    loss gradient weighted by the part's share of the batch: loss, gradient and predictions are bit-identical to the unsplit call, and
+    the graphed PGD loop built on it stays inside the eps ball."""
+    from gen_adversarial_b200.attacks import PGDLinf
+    from gen_adversarial_b200.defenses.ours.models import NVAEDefenseModel, CelebaIdentityClassifier
+    cfg, res = tiny_config(initial_channels=16, groups=2, scales=2, latent=4), (3, 32, 32)
+    spec = NvaeSpec(cfg, res)
+    clf = CelebaIdentityClassifier({"state_dict": synth.make_vgg11_state_dict(10, seed=3, device=DEV)}, DEV, mode=mode, n_classes=10, image_size=32)
+    dm = NVAEDefenseModel(clf, synth.make_nvae_checkpoint(cfg, res, seed=3), [0.5] * spec.n_latents, 1.0, 1.0, True, DEV, mode=mode)
+    dm.noise_seed = 11
+    x, y = synth.synthetic_batch(8, res, 10, seed=2)
+    x, y = x.to(DEV), y.to(DEV)
+    cnt = torch.zeros(1, dtype=torch.int64, device=DEV)
+    l1, g1, p1 = dm.loss_input_grad(x, y, counter=cnt)
+    c1 = int(cnt.item())
+    dm.set_streams(2)
+    outs = [dm.loss_input_grad(x, y, counter=cnt) for _ in range(3)]      # first: parts back to back; then forked
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == 4 * c1
+    for l, g, p in outs:
+        assert torch.equal(l1, l) and torch.equal(p1, p) and torch.equal(g1, g)
+    dm.noise_seed = None
+    dm.enable_cuda_graph(True)
+    succ, linf, x_adv = PGDLinf(8 / 255, 2 / 255, 5)(x, y, dm)
+    dm.enable_cuda_graph(False)
+    assert linf.max().item() <= 8 / 255 + 1e-6 and x_adv.min() >= 0 and x_adv.max() <= 1
+    assert (x_adv - x).abs().max().item() > 1e-3
