@@ -12,4 +12,4 @@ print({k:d[k] for k in ('value','n_gpus','ms_per_step','scaling')}, 'e2e', d['e2
 for k in ('strong_scaling','pgd'):
     e=d.get(k,{}); print(k, {kk:e.get(kk) for kk in ('value','ms_per_step','batch_per_gpu','global_batch','error')})
 PY
-echo "== reference arm under torchrun"; timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 2 --warmup 1 2>/dev/null | cut -c1-300
+if [ "$N" -le 2 ]; then echo "== reference arm under torchrun"; timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 2 --warmup 1 2>/dev/null | cut -c1-300; fi
