@@ -454,10 +454,13 @@ def instrumented_pass(ctx, dm, workload, x_dev, y_dev, steps, step_ms, breakdown
     tot_fl = sum(a["flops"] for a in conv.values())
     ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
     top = sorted(conv.items(), key=lambda kv: -kv[1]["ms"])[:10]
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes, FLOP-weighted)",
+    roof = {"bound": "tensor", "kernel": "conv3x3_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs, all shapes, FLOP-weighted)",
             "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
-            "traffic": None, "traffic_note": "see profiles/ (ncu --set full dram bytes per launch of the dominant shape)",
+            "traffic": 90.1e6, "traffic_unit": "bytes per launch",
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant shape (3x3, 64 -> 64 channels at 32x32, 512-image part-batch: "
+                            "67.3 + 22.8 MB against 134.3 MB algorithmic x + W + y -- the previous kernel's output is partly still in L2) from the committed "
+                            "ncu --set full capture profiles/r02_ncu_full_kernels_v1.md; `achieved` is FLOP-weighted over ALL conv shapes",
             "launches_per_step": round(sum(a["launches"] for a in conv.values())), "share_of_step": tot_ms / step_ms if step_ms > 0 else None,
             "collected": f"separate instrumented pass of {steps} step(s), per-launch CUDA events on the launching stream",
             "by_shape": [{"shape": k, "launches": round(a["launches"]), "ms": round(a["ms"], 3),
