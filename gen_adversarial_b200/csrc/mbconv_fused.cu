@@ -25,6 +25,9 @@
 namespace ga {
 
 constexpr int MB_THREADS = 416;      // control warp + 4 activation warps + 8 depthwise warps
+#ifndef MB_MAXNREG
+#define MB_MAXNREG 112
+#endif
 
 template <int W_IMG> struct MbGeom;
 template <> struct MbGeom<8>  { static constexpr int IMGS = 2, R_OUT = 8,  HALO = 0, MT_IN = 1, MT_OUT = 1, STRIP_W = 2; };
@@ -87,8 +90,10 @@ __device__ __forceinline__ float2 h2_to_f2(uint32_t v) {
 }
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 
+// 416 threads x 112 registers = 46.6K of the SM's 64K: a 256-thread elementwise CTA (<= 64 registers: SE / residual, channel sums, latent mixing) of
+// ANOTHER stream fits beside this CTA and streams through the HBM pipes the cell leaves idle (MLVGMDefenseModel.set_streams)
 template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false>
-__global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                      const __grid_constant__ CUtensorMap tmWe,
                                                                      const __grid_constant__ CUtensorMap tmWp, const MbParams p) {
   using G = MbGeom<W_IMG>;
@@ -130,8 +135,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
   uint8_t* sA2 = sH + 2 * H_BYTES;                                   // H is double buffered (activation warps run one chunk ahead)
   float* s_dww = reinterpret_cast<float*>(sA2 + A2_BYTES);          // [2][25][64] depthwise taps of the current / next chunk
   float* s_be = s_dww + 2 * 25 * 64;
-  float* s_dwb = s_be + p.hidden;
-  float* s_bp = s_dwb + p.hidden;                                   // [C] project bias
+  float* s_bp = s_be + p.hidden;                                    // [C] project bias (the depthwise bias is read through L1: 2 floats per lane and chunk)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.hidden / 64;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
     // expand bias pre-halved: SiLU(v) = h + h tanh(h) with h = v/2 = fma(acc, 0.5, be/2) -- exact (power-of-two scaling), one FMA-pipe op less
-    for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) { s_be[i] = 0.5f * p.be[i]; s_dwb[i] = p.dw_b[i]; }
+    for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) s_be[i] = 0.5f * p.be[i];
     for (int i = threadIdx.x - 32; i < C; i += MB_THREADS - 32) s_bp[i] = p.bp[i];
   }
   tc_fence_before();
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
 #pragma unroll
           for (int t = 0; t < 25; ++t) { const float2 w = lds_f2(wsrc + t * 256); wt[t] = pack_f16x2(w.x, w.y); }
         }
-        const float2 b2 = lds_f2(smem_u32(s_dwb) + (kc * 64 + 2 * lane) * 4);
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.dw_b + kc * 64 + 2 * lane));
         stamp(g, 1);
         mbar_wait_backoff(&h_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
         stamp(g, 2);
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_fused_kernel(const __gri
 #pragma unroll
         for (int t = 0; t < 25; ++t) wt[t] = lds_f2(wsrc + t * 256);
       }
-      const float2 b2 = lds_f2(smem_u32(s_dwb) + (kc * 64 + 2 * lane) * 4);
+      const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.dw_b + kc * 64 + 2 * lane));
       stamp(g, 1);
       mbar_wait_backoff(&h_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
       stamp(g, 2);
@@ -584,7 +588,7 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   using G = MbGeom<W_IMG>;
   constexpr int KB = C / 64;
   const int smem = 1024 /*align*/ + 1024 /*header*/ + G::MT_IN * KB * 16384 + NBUF * (KB * 8192 + C * 128) + 2 * G::MT_IN * 16384 +
-                   G::MT_OUT * 16384 + 2 * DWW_BYTES + 2 * p.hidden * 4 + C * 4;
+                   G::MT_OUT * 16384 + 2 * DWW_BYTES + p.hidden * 4 + C * 4;
   GA_CHECK(smem <= 227 * 1024, "ga_mbconv_fused: shared memory request %d too large", smem);
   static int configured = 0;
   if (configured < smem) {
@@ -643,6 +647,9 @@ extern "C" int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const floa
     if (x->w == 8) return launch_mbconv<256, 8, 1, false, true>(x, we_tc, wp_tc, p, s);
     if (x->w == 16) return launch_mbconv<128, 16, 1, false, true>(x, we_tc, wp_tc, p, s);
     if (p.trace != nullptr) return launch_mbconv<64, 32, 2, true, true>(x, we_tc, wp_tc, p, s);
+    static int nbuf32 = -1;
+    if (nbuf32 < 0) { const char* e = getenv("GA_MB_NBUF32"); nbuf32 = e ? atoi(e) : 2; }
+    if (nbuf32 == 1) return launch_mbconv<64, 32, 1, false, true>(x, we_tc, wp_tc, p, s);
     return launch_mbconv<64, 32, 2, false, true>(x, we_tc, wp_tc, p, s);
   }
   if (x->w == 8) return launch_mbconv<256, 8, 1>(x, we_tc, wp_tc, p, s);
