@@ -43,6 +43,7 @@ struct MbParams {
   const float* dw_b;            // [hidden]
   const float* bp;              // [C] project bias
   __nv_bfloat16* out;           // [N][H][W][C]
+  float* csum;                  // optional: SE squeeze of `out` -- per-image channel sums in the 128-pixel slices of ga_channel_sum, [N][HW/128 or 1][C]
   int act_hi;                   // 1: activation warps are warps 9-12 (scheduler priority is highest-warp-id-first), depthwise warps 1-8
   int sleep_ns;                 // back-off of the SIMT mbarrier polls
   unsigned long long* trace;    // debug (ga_debug_mbconv_trace): clock64 stamps [cta < 8][warp 13][chunk 24][event 8]
@@ -136,6 +137,7 @@ __global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __
   float* s_dww = reinterpret_cast<float*>(sA2 + A2_BYTES);          // [2][25][64] depthwise taps of the current / next chunk
   float* s_be = s_dww + 2 * 25 * 64;
   float* s_bp = s_be + p.hidden;                                    // [C] project bias (the depthwise bias is read through L1: 2 floats per lane and chunk)
+  float* s_cs = s_bp + C;                                           // [2][4][64] per-warp column sums of the epilogue (double buffered)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.hidden / 64;
@@ -285,6 +287,7 @@ __global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __
     // ======================================================================= activation warps (1-4, one per TMEM lane quadrant):
     // expand accumulator -> + bias -> SiLU -> bf16 -> H[k & 1] (swizzled rows), one chunk ahead of the depthwise warps
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    int cs_batch = 0;                        // channel-sum batches done (selects the shared-memory buffer)
     // ---- project accumulator of local tile j -> + bias -> r (bf16) -> HBM
     auto epilogue = [&](int j) {
       int n0, y0;
@@ -311,20 +314,57 @@ __global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __
             __syncwarp();
             if (lane == 0) mbar_arrive(proj_empty);
           }
-          if (pix < total_pix) {
-            uint4* o = reinterpret_cast<uint4*>(p.out + pix * C + c0);
-            const uint32_t bp_a = smem_u32(s_bp) + c0 * 4;
+          const bool row_ok = pix < total_pix;
+          uint4* o = reinterpret_cast<uint4*>(p.out + pix * C + c0);
+          const uint32_t bp_a = smem_u32(s_bp) + c0 * 4;
+          float* cs = s_cs + (cs_batch & 1) * 256 + q * 64;
 #pragma unroll
-            for (int c16 = 0; c16 < 4; ++c16) {
-              uint32_t pk[8];
+          for (int c16 = 0; c16 < 4; ++c16) {
+            uint32_t pk[8];
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float2 b = lds_f2(bp_a + (c16 * 16 + 2 * jj) * 4);
-                pk[jj] = pack_bf16x2(__uint_as_float(r[c16][2 * jj]) + b.x, __uint_as_float(r[c16][2 * jj + 1]) + b.y);
-              }
+            for (int jj = 0; jj < 8; ++jj) {
+              const float2 b = lds_f2(bp_a + (c16 * 16 + 2 * jj) * 4);
+              pk[jj] = pack_bf16x2(__uint_as_float(r[c16][2 * jj]) + b.x, __uint_as_float(r[c16][2 * jj + 1]) + b.y);
+            }
+            if (row_ok) {
               o[2 * c16] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               o[2 * c16 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
+            if (p.csum != nullptr) {
+              // column sums over this warp's 32 pixels of the values AS STORED (bf16), by recursive halving (the scheme of the persistent 3x3
+              // kernel's epilogue, conv_tc_epilogue.cuh): after the exchanges over lane bits 4..1 a lane holds one column, summed over 16 lanes
+              float v[16];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                v[2 * jj] = row_ok ? __uint_as_float(pk[jj] << 16) : 0.f;
+                v[2 * jj + 1] = row_ok ? __uint_as_float(pk[jj] & 0xffff0000u) : 0.f;
+              }
+              float w8[8], w4[4], w2[2];
+              const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w8[j] = (b4 ? v[8 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, b4 ? v[j] : v[8 + j], 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) w4[j] = (b3 ? w8[4 + j] : w8[j]) + __shfl_xor_sync(0xffffffffu, b3 ? w8[j] : w8[4 + j], 8);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) w2[j] = (b2 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, b2 ? w4[j] : w4[2 + j], 4);
+              float w1 = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2);
+              w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+              if ((lane & 1) == 0) cs[c16 * 16 + ((lane >> 1) & 15)] = w1;
+            }
+          }
+          if (p.csum != nullptr) {
+            // the four activation warps meet (named barrier 2; the buffers alternate, so one barrier per batch is enough), then a fixed-order
+            // sum of the four 32-pixel slabs -> [image][128-pixel slice][channel]; 8x8 maps: two images of 64 pixels per accumulator tile
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const float* cb = s_cs + (cs_batch & 1) * 256;
+            const int t = q * 32 + lane;
+            if (W_IMG == 8) {
+              const int img = t >> 6, ch = t & 63;
+              if (n0 + img < p.N) p.csum[(int64_t)(n0 + img) * C + c0 + ch] = cb[(2 * img) * 64 + ch] + cb[(2 * img + 1) * 64 + ch];
+            } else if (t < 64) {
+              p.csum[(((pix0 + m * 128) >> 7)) * C + c0 + t] = (cb[t] + cb[64 + t]) + (cb[128 + t] + cb[192 + t]);
+            }
+            ++cs_batch;
           }
         }
       }
@@ -588,7 +628,7 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   using G = MbGeom<W_IMG>;
   constexpr int KB = C / 64;
   const int smem = 1024 /*align*/ + 1024 /*header*/ + G::MT_IN * KB * 16384 + NBUF * (KB * 8192 + C * 128) + 2 * G::MT_IN * 16384 +
-                   G::MT_OUT * 16384 + 2 * DWW_BYTES + p.hidden * 4 + C * 4;
+                   G::MT_OUT * 16384 + 2 * DWW_BYTES + p.hidden * 4 + C * 4 + 2 * 4 * 64 * 4;
   GA_CHECK(smem <= 227 * 1024, "ga_mbconv_fused: shared memory request %d too large", smem);
   static int configured = 0;
   if (configured < smem) {
@@ -622,8 +662,16 @@ extern "C" int ga_mbconv_fused_supported(const ga_tensor* x, int hidden) {
   return (x->w == 8 && x->c == 256) || (x->w == 16 && x->c == 128) || (x->w == 32 && x->c == 64);
 }
 
+extern "C" int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
+                                  const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out, void* stream);
+
 extern "C" int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
                                const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, void* stream) {
+  return ga_mbconv_fused_ex(x, we_tc, be, dw_w, dw_b, wp_tc, bp, hidden, out, nullptr, stream);
+}
+
+extern "C" int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
+                                  const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out, void* stream) {
   GA_CHECK(x && we_tc && be && dw_w && dw_b && wp_tc && bp && out, "ga_mbconv_fused: null argument");
   GA_CHECK(ga_mbconv_fused_supported(x, hidden), "ga_mbconv_fused: unsupported problem (n=%d h=%d w=%d c=%d hidden=%d)", x->n, x->h, x->w,
            x->c, hidden);
@@ -633,6 +681,7 @@ extern "C" int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const floa
   MbParams p;
   p.N = x->n; p.H = x->h; p.hidden = hidden; p.be = be; p.dw_w = dw_w; p.dw_b = dw_b; p.bp = bp;
   p.out = (__nv_bfloat16*)out->data;
+  p.csum = csum_out;
   static int act_hi = -1, sleep_ns = -1;
   if (act_hi < 0) { const char* e = getenv("GA_MB_ACT_HI"); act_hi = e ? atoi(e) : 0; }
   if (sleep_ns < 0) { const char* e = getenv("GA_MB_SLEEP_NS"); sleep_ns = e ? atoi(e) : 100; }

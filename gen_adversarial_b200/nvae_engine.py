@@ -319,8 +319,12 @@ class NvaeEngine:
         elu = bool(want_elu and self.bf16)
         self._elu_copy = None
         if not taping and self.fuse_cells and self.bf16 and not d.up and d.dw_wc is not None and ops.mbconv_fused_supported(xa, d.e, d.p):
-            r = ops.mbconv_fused(xa, d.e, d.dw_wc, d.dw_b, d.p)     # expand -> dw5x5 -> project in one kernel, hidden tensor on chip
-            sums = ops.channel_sum(r)
+            # expand -> dw5x5 -> project in one kernel, hidden tensor on chip; the SE squeeze comes out of its epilogue (GA_FUSE_CSUM)
+            if self.fuse_csum:
+                r, sums = ops.mbconv_fused(xa, d.e, d.dw_wc, d.dw_b, d.p, want_sums=True)
+            else:
+                r = ops.mbconv_fused(xa, d.e, d.dw_wc, d.dw_b, d.p)
+                sums = ops.channel_sum(r)
             out, out2, self._elu_copy, _ = ops.se_residual(r, sums, d.se, 0.1, x32, torch.float32, want_out2=True, act_plain=elu,
                                                            act_op=ACT_ELU if elu else ACT_SILU)
             return out, out2

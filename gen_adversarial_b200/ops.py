@@ -247,18 +247,21 @@ def dw_weights_chunked(dw_w: torch.Tensor) -> torch.Tensor:
     return dw_w.reshape(t, hidden // 64, 64).permute(1, 0, 2).contiguous()
 
 
-def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer) -> torch.Tensor:
-    """decoder-cell body in ONE kernel: project(SiLU(dw5x5(SiLU(expand(x)))))  -> r (bf16); dw_w_chunked = dw_weights_chunked(dw_w)"""
+def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer, want_sums: bool = False):
+    """decoder-cell body in ONE kernel: project(SiLU(dw5x5(SiLU(expand(x)))))  -> r (bf16); dw_w_chunked = dw_weights_chunked(dw_w).
+    want_sums: -> (r, sums): the SE channel sums of r ([n][parts][c] fp32, what `channel_sum(r)` returns) from the cell's epilogue"""
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    sums = torch.empty((x.shape[0], channel_sum_parts(x.shape[0], x.shape[1] * x.shape[2]), x.shape[3]), device=x.device,
+                       dtype=torch.float32) if want_sums else None
     e0 = TIMER.start() if TIMER is not None else None
-    _lib.check(_lib.lib().ga_mbconv_fused(gt(x), e.w_tc.data_ptr(), ptr(e.bias), ptr(dw_w_chunked), ptr(dw_b), p.w_tc.data_ptr(), ptr(p.bias),
-                                          e.cout, gt(out), stream()), "mbconv_fused")
+    _lib.check(_lib.lib().ga_mbconv_fused_ex(gt(x), e.w_tc.data_ptr(), ptr(e.bias), ptr(dw_w_chunked), ptr(dw_b), p.w_tc.data_ptr(), ptr(p.bias),
+                                             e.cout, gt(out), ptr(sums), stream()), "mbconv_fused")
     if e0 is not None:
         n, h, w, c = x.shape
         m, hid = n * h * w, e.cout
         # algorithmic work: two 1x1 GEMMs on the tensor cores + 25 MAC per hidden element on the fp32 pipe; compulsory HBM traffic: x in, r out
         TIMER.stop(e0, f"fused:mbconv hw{h} c{c} hidden{hid}", 2.0 * m * hid * c * 2 + 2.0 * m * hid * 25, 2.0 * m * c * 2 + 2.0 * hid * c * 2)
-    return out
+    return (out, sums) if want_sums else out
 
 
 def channel_sum_parts(n: int, hw: int) -> int:

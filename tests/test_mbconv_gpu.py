@@ -58,3 +58,22 @@ def test_mbconv_fused_matches_three_kernels(n, w, c, hidden):
     print(f"mbconv n={n} w={w} c={c} hidden={hidden}: vs torch {err:.3e}, vs 3 kernels {err3:.3e} (scale {scale:.2f})")
     assert err <= 2e-2 * scale, (err, scale)
     assert err3 <= 2e-2 * scale, (err3, scale)
+
+
+@pytest.mark.parametrize("n,w,c,hidden", [(3, 8, 256, 128), (301, 8, 256, 64), (2, 16, 128, 128), (150, 16, 128, 64), (3, 32, 64, 128), (40, 32, 64, 64)])
+def test_mbconv_fused_channel_sums(n, w, c, hidden):
+    """SE squeeze from the fused cell's epilogue: the sums of r AS STORED (bf16), per image and 128-pixel slice, in the layout `channel_sum`
+    writes; r itself is unchanged by asking for them."""
+    e, dw_w, dw_b, p = _cell(c, hidden, seed=n + w + hidden)
+    x = torch.randn(n, w, w, c, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+    ed, pd, xd, wd, bd = _dev(e), _dev(p), x.to(DEV), dw_w.to(DEV), dw_b.to(DEV)
+    wc = ops.dw_weights_chunked(wd)
+    r0 = ops.mbconv_fused(xd, ed, wc, bd, pd)
+    r, sums = ops.mbconv_fused(xd, ed, wc, bd, pd, want_sums=True)
+    ref = ops.channel_sum(r)
+    torch.cuda.synchronize()
+    assert torch.equal(r0, r)
+    assert sums.shape == ref.shape
+    # same addends, different association: fp32 rounding only
+    scale = max(1.0, ref.abs().max().item())
+    assert (sums - ref).abs().max().item() <= 2e-5 * scale * (min(w * w, 128) ** 0.5)
