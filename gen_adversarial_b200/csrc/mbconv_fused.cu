@@ -43,6 +43,8 @@ struct MbParams {
   const float* dw_b;            // [hidden]
   const float* bp;              // [C] project bias
   __nv_bfloat16* out;           // [N][H][W][C]
+  __nv_bfloat16* dact_e;        // TAPE: SiLU'(expand pre-activation), [N][H][W][hidden] (what the attack path's backward multiplies by)
+  __nv_bfloat16* dact_dw;       // TAPE: SiLU'(depthwise pre-activation), [N][H][W][hidden]
   float* csum;                  // optional: SE squeeze of `out` -- per-image channel sums in the 128-pixel slices of ga_channel_sum, [N][HW/128 or 1][C]
   int act_hi;                   // 1: activation warps are warps 9-12 (scheduler priority is highest-warp-id-first), depthwise warps 1-8
   int sleep_ns;                 // back-off of the SIMT mbarrier polls
@@ -93,8 +95,8 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) { return make_float2(__u
 
 // 416 threads x 112 registers = 46.6K of the SM's 64K: a 256-thread elementwise CTA (<= 64 registers: SE / residual, channel sums, latent mixing) of
 // ANOTHER stream fits beside this CTA and streams through the HBM pipes the cell leaves idle (MLVGMDefenseModel.set_streams)
-template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false>
-__global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
+template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false, bool TAPE = false>
+__global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                      const __grid_constant__ CUtensorMap tmWe,
                                                                      const __grid_constant__ CUtensorMap tmWp, const MbParams p) {
   using G = MbGeom<W_IMG>;
@@ -390,6 +392,19 @@ __global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __
           in_img = y >= 0 && y < p.H;                     // halo rows outside the image are the conv's zero padding
         }
         const uint32_t row = hb + pin * 128;
+        // TAPE: the global pixel this thread's row belongs to (halo rows of a 32x32 tile belong to the neighbouring tiles)
+        bool own = false;
+        int64_t gpix = 0;
+        if (TAPE) {
+          if (W_IMG == 32) {
+            const int rt = (pin >> 5) - G::HALO;
+            own = rt >= 0 && rt < G::R_OUT;
+            gpix = (((int64_t)n0 * p.H + y0 + rt) << 5) + (pin & 31);
+          } else {
+            gpix = (int64_t)n0 * p.H * W_IMG + pin;
+            own = gpix < (int64_t)p.N * p.H * W_IMG;
+          }
+        }
         // all 64 columns of this lane's pixel in flight before ONE wait: a tcgen05.ld round trip costs ~1k cycles, and one warp per
         // scheduler cannot hide it behind anything else
         uint32_t r[4][16];
@@ -399,18 +414,26 @@ __global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __
         tmem_ld_wait();
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
-          uint32_t pk[8];
+          uint32_t pk[8], dk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 b = lds_f2(be_a + (c16 * 16 + 2 * j) * 4);
             const float h0 = fmaf(__uint_as_float(r[c16][2 * j]), 0.5f, b.x), h1 = fmaf(__uint_as_float(r[c16][2 * j + 1]), 0.5f, b.y);
-            const float v0 = fmaf(h0, tanh_approx(h0), h0), v1 = fmaf(h1, tanh_approx(h1), h1);
+            const float t0 = tanh_approx(h0), t1 = tanh_approx(h1);
+            const float v0 = fmaf(h0, t0, h0), v1 = fmaf(h1, t1, h1);
+            // TAPE: SiLU' from the same tanh (act_grad_fast_n's form: 1/2 + (t + h (1 - t^2)) / 2)
+            if (TAPE) dk[j] = pack_bf16x2(fmaf(0.5f, fmaf(h0, fmaf(-t0, t0, 1.0f), t0), 0.5f), fmaf(0.5f, fmaf(h1, fmaf(-t1, t1, 1.0f), t1), 0.5f));
             // fp16 H: SiLU(h) >= -0.28, so only the upper end can leave the fp16 range -- clamp instead of producing inf
             pk[j] = in_img ? (F16 ? pack_f16x2(fminf(v0, 60000.f), fminf(v1, 60000.f)) : pack_bf16x2(v0, v1)) : 0u;
           }
           const uint32_t ch0 = (uint32_t)(c16 * 2);                       // 16-byte chunk index inside the 128-byte row
           sts_v4(row + (((ch0) ^ (pin & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           sts_v4(row + (((ch0 + 1) ^ (pin & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+          if (TAPE && own) {
+            uint4* o = reinterpret_cast<uint4*>(p.dact_e + gpix * p.hidden + k * 64 + c16 * 16);
+            o[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+            o[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+          }
         }
       }
       tc_fence_before();
@@ -449,6 +472,8 @@ __global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __
       // accumulates in ONE pass -- no input row is read twice -- and the 25 multiply-adds per output pair are 25 HFMA2 instead of 25 FFMA2
       // (half the fp32-pipe cycles) with no unpack.  The 25-term fp16 accumulation adds ~1e-3 relative rounding noise, about half of what the
       // bf16 rounding of the result adds anyway; the bias, SiLU and the bf16 rounding stay fp32.
+      int ti_d = 0, n0d = 0, y0d = 0;
+      if (TAPE) tile_origin(0, n0d, y0d);
       for (int g = 0, kc = 0; g < g_total; ++g, kc = (kc + 1 == nch) ? 0 : kc + 1) {
         uint32_t wt[25];
         stamp(g, 0);
@@ -499,12 +524,29 @@ __global__ void __maxnreg__(F16 ? MB_MAXNREG : 128) mbconv_fused_kernel(const __
 #pragma unroll
           for (int c = 0; c < G::STRIP_W; ++c) {
             const float2 a = h2_to_f2(acc[oy][c]);
-            sts_b32(a2_col[c] + oy * (W_IMG * 128), pack_bf16x2(silu_fast(a.x + b2.x), silu_fast(a.y + b2.y)));
+            if (TAPE) {
+              // SiLU and SiLU' from one tanh each; the derivative goes to the tape of the attack path's backward (coalesced: a warp's 32
+              // channel pairs are 128 contiguous bytes of the pixel's hidden row)
+              const float h0 = 0.5f * (a.x + b2.x), h1 = 0.5f * (a.y + b2.y);
+              const float t0 = tanh_approx(h0), t1 = tanh_approx(h1);
+              sts_b32(a2_col[c] + oy * (W_IMG * 128), pack_bf16x2(fmaf(h0, t0, h0), fmaf(h1, t1, h1)));
+              int64_t gpix;
+              bool ok = true;
+              if (W_IMG == 32) gpix = (((int64_t)n0d * p.H + y0d + oy) << 5) + cs + c;
+              else if (W_IMG == 16) gpix = (int64_t)n0d * 256 + oy * 16 + cs + c;
+              else { gpix = (int64_t)(n0d + img) * 64 + oy * 8 + cs + c; ok = n0d + img < p.N; }
+              if (ok)
+                *reinterpret_cast<uint32_t*>(p.dact_dw + gpix * p.hidden + kc * 64 + 2 * lane) =
+                    pack_bf16x2(fmaf(0.5f, fmaf(h0, fmaf(-t0, t0, 1.0f), t0), 0.5f), fmaf(0.5f, fmaf(h1, fmaf(-t1, t1, 1.0f), t1), 0.5f));
+            } else {
+              sts_b32(a2_col[c] + oy * (W_IMG * 128), pack_bf16x2(silu_fast(a.x + b2.x), silu_fast(a.y + b2.y)));
+            }
           }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a2_full);
         stamp(g, 5);
+        if (TAPE && kc + 1 == nch) { ++ti_d; tile_origin(ti_d, n0d, y0d); }
       }
     } else
     for (int g = 0, kc = 0; g < g_total; ++g, kc = (kc + 1 == nch) ? 0 : kc + 1) {
@@ -623,7 +665,7 @@ static int mb_encode_x(CUtensorMap* tm, const ga_tensor* t, int bw, int bh, int 
 
 static unsigned long long* g_mb_trace = nullptr;
 
-template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false>
+template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false, bool TAPE = false>
 static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, const MbParams& p, cudaStream_t s) {
   using G = MbGeom<W_IMG>;
   constexpr int KB = C / 64;
@@ -632,7 +674,7 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   GA_CHECK(smem <= 227 * 1024, "ga_mbconv_fused: shared memory request %d too large", smem);
   static int configured = 0;
   if (configured < smem) {
-    GA_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GA_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   CUtensorMap tmX, tmWe, tmWp;
@@ -647,7 +689,7 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   MbParams q = p;
   q.n_tiles = tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16><<<grid, MB_THREADS, smem, s>>>(tmX, tmWe, tmWp, q);
+  mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16, TAPE><<<grid, MB_THREADS, smem, s>>>(tmX, tmWe, tmWp, q);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -663,15 +705,17 @@ extern "C" int ga_mbconv_fused_supported(const ga_tensor* x, int hidden) {
 }
 
 extern "C" int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
-                                  const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out, void* stream);
+                                  const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out,
+                                  const ga_tensor* dact_e, const ga_tensor* dact_dw, void* stream);
 
 extern "C" int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
                                const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, void* stream) {
-  return ga_mbconv_fused_ex(x, we_tc, be, dw_w, dw_b, wp_tc, bp, hidden, out, nullptr, stream);
+  return ga_mbconv_fused_ex(x, we_tc, be, dw_w, dw_b, wp_tc, bp, hidden, out, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
-                                  const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out, void* stream) {
+                                  const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out,
+                                  const ga_tensor* dact_e, const ga_tensor* dact_dw, void* stream) {
   GA_CHECK(x && we_tc && be && dw_w && dw_b && wp_tc && bp && out, "ga_mbconv_fused: null argument");
   GA_CHECK(ga_mbconv_fused_supported(x, hidden), "ga_mbconv_fused: unsupported problem (n=%d h=%d w=%d c=%d hidden=%d)", x->n, x->h, x->w,
            x->c, hidden);
@@ -682,6 +726,15 @@ extern "C" int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const f
   p.N = x->n; p.H = x->h; p.hidden = hidden; p.be = be; p.dw_w = dw_w; p.dw_b = dw_b; p.bp = bp;
   p.out = (__nv_bfloat16*)out->data;
   p.csum = csum_out;
+  GA_CHECK((dact_e == nullptr) == (dact_dw == nullptr), "ga_mbconv_fused: the two tape tensors go together");
+  const bool tape = dact_e != nullptr;
+  if (tape) {
+    GA_CHECK(dact_e->dtype == GA_BF16 && dact_dw->dtype == GA_BF16 && dact_e->n == x->n && dact_e->h == x->h && dact_e->w == x->w && dact_e->c == hidden &&
+                 same_shape(dact_e, dact_dw), "ga_mbconv_fused: tape tensors must be bf16 [n][h][w][hidden]");
+    GA_CHECK(((((uintptr_t)dact_e->data) | ((uintptr_t)dact_dw->data)) & 15) == 0, "ga_mbconv_fused: tape pointers must be 16-byte aligned");
+  }
+  p.dact_e = tape ? (__nv_bfloat16*)dact_e->data : nullptr;
+  p.dact_dw = tape ? (__nv_bfloat16*)dact_dw->data : nullptr;
   static int act_hi = -1, sleep_ns = -1;
   if (act_hi < 0) { const char* e = getenv("GA_MB_ACT_HI"); act_hi = e ? atoi(e) : 0; }
   if (sleep_ns < 0) { const char* e = getenv("GA_MB_SLEEP_NS"); sleep_ns = e ? atoi(e) : 100; }
@@ -692,6 +745,11 @@ extern "C" int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const f
   // 0: bf16 hidden tile, fp32 FFMA2 accumulation (bit-identical to the three separate kernels)
   static int f16 = -1;
   if (f16 < 0) { const char* e = getenv("GA_MB_F16"); f16 = e ? atoi(e) : 1; }
+  if (tape) {          // the taping variant exists for the fp16 hidden tile only
+    if (x->w == 8) return launch_mbconv<256, 8, 1, false, true, true>(x, we_tc, wp_tc, p, s);
+    if (x->w == 16) return launch_mbconv<128, 16, 1, false, true, true>(x, we_tc, wp_tc, p, s);
+    return launch_mbconv<64, 32, 2, false, true, true>(x, we_tc, wp_tc, p, s);
+  }
   if (f16) {
     if (x->w == 8) return launch_mbconv<256, 8, 1, false, true>(x, we_tc, wp_tc, p, s);
     if (x->w == 16) return launch_mbconv<128, 16, 1, false, true>(x, we_tc, wp_tc, p, s);

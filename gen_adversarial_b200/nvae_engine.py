@@ -87,6 +87,7 @@ class NvaeEngine:
         # fused decoder-cell kernel (expand -> dw5x5 -> project, hidden tensor on chip); GA_MBCONV_FUSED=0 selects the three-kernel path
         self.fuse_cells = __import__("os").environ.get("GA_MBCONV_FUSED", "1") != "0"
         self.fuse_csum = __import__("os").environ.get("GA_FUSE_CSUM", "1") != "0"     # SE channel sums from the encoder conv2 epilogue
+        self.fuse_tape = __import__("os").environ.get("GA_FUSE_TAPE", "1") != "0"     # attack path: taping forward of the decoder cells in the fused kernel
         f = Folder(state_dict, self.device, want_tc=self.bf16)
         self._fold(f)
         self._prior_cache = {}
@@ -318,7 +319,15 @@ class NvaeEngine:
         taping = rec is not None
         elu = bool(want_elu and self.bf16)
         self._elu_copy = None
-        if not taping and self.fuse_cells and self.bf16 and not d.up and d.dw_wc is not None and ops.mbconv_fused_supported(xa, d.e, d.p):
+        fused_ok = self.fuse_cells and self.bf16 and not d.up and d.dw_wc is not None and ops.mbconv_fused_supported(xa, d.e, d.p)
+        if taping and fused_ok and self.fuse_tape:
+            # attack path: the same fused kernel also writes the two SiLU' tapes (hidden-sized, write-only) that `_dec_cell_bwd` multiplies by
+            r, sums, dact_e, dact_dw = ops.mbconv_fused(xa, d.e, d.dw_wc, d.dw_b, d.p, want_sums=True, want_tape=True)
+            out, out2, self._elu_copy, _ = ops.se_residual(r, sums, d.se, 0.1, x32, torch.float32, want_out2=True, act_plain=elu,
+                                                           act_op=ACT_ELU if elu else ACT_SILU)
+            rec.append(("dec", d, dact_e, dact_dw, r, sums))
+            return out, out2
+        if not taping and fused_ok:
             # expand -> dw5x5 -> project in one kernel, hidden tensor on chip; the SE squeeze comes out of its epilogue (GA_FUSE_CSUM)
             if self.fuse_csum:
                 r, sums = ops.mbconv_fused(xa, d.e, d.dw_wc, d.dw_b, d.p, want_sums=True)

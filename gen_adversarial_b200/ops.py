@@ -247,20 +247,28 @@ def dw_weights_chunked(dw_w: torch.Tensor) -> torch.Tensor:
     return dw_w.reshape(t, hidden // 64, 64).permute(1, 0, 2).contiguous()
 
 
-def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer, want_sums: bool = False):
+def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b: torch.Tensor, p: ConvLayer, want_sums: bool = False,
+                 want_tape: bool = False):
     """decoder-cell body in ONE kernel: project(SiLU(dw5x5(SiLU(expand(x)))))  -> r (bf16); dw_w_chunked = dw_weights_chunked(dw_w).
-    want_sums: -> (r, sums): the SE channel sums of r ([n][parts][c] fp32, what `channel_sum(r)` returns) from the cell's epilogue"""
+    want_sums: also the SE channel sums of r ([n][parts][c] fp32, what `channel_sum(r)` returns) from the cell's epilogue;
+    want_tape: also SiLU'(expand pre-activation) and SiLU'(depthwise pre-activation), bf16 [n][h][w][hidden] (attack path).
+    -> r | (r, sums) | (r, sums | None, dact_e, dact_dw)"""
+    n, h, w, c = x.shape
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    sums = torch.empty((x.shape[0], channel_sum_parts(x.shape[0], x.shape[1] * x.shape[2]), x.shape[3]), device=x.device,
-                       dtype=torch.float32) if want_sums else None
+    sums = torch.empty((n, channel_sum_parts(n, h * w), c), device=x.device, dtype=torch.float32) if want_sums else None
+    dact_e = torch.empty((n, h, w, e.cout), device=x.device, dtype=torch.bfloat16) if want_tape else None
+    dact_dw = torch.empty((n, h, w, e.cout), device=x.device, dtype=torch.bfloat16) if want_tape else None
     e0 = TIMER.start() if TIMER is not None else None
     _lib.check(_lib.lib().ga_mbconv_fused_ex(gt(x), e.w_tc.data_ptr(), ptr(e.bias), ptr(dw_w_chunked), ptr(dw_b), p.w_tc.data_ptr(), ptr(p.bias),
-                                             e.cout, gt(out), ptr(sums), stream()), "mbconv_fused")
+                                             e.cout, gt(out), ptr(sums), gt(dact_e), gt(dact_dw), stream()), "mbconv_fused")
     if e0 is not None:
-        n, h, w, c = x.shape
         m, hid = n * h * w, e.cout
         # algorithmic work: two 1x1 GEMMs on the tensor cores + 25 MAC per hidden element on the fp32 pipe; compulsory HBM traffic: x in, r out
-        TIMER.stop(e0, f"fused:mbconv hw{h} c{c} hidden{hid}", 2.0 * m * hid * c * 2 + 2.0 * m * hid * 25, 2.0 * m * c * 2 + 2.0 * hid * c * 2)
+        # (+ the two hidden-sized tapes when taping)
+        TIMER.stop(e0, f"fused:mbconv{'_tape' if want_tape else ''} hw{h} c{c} hidden{hid}", 2.0 * m * hid * c * 2 + 2.0 * m * hid * 25,
+                   2.0 * m * c * 2 + 2.0 * hid * c * 2 + (4.0 * m * hid if want_tape else 0.0))
+    if want_tape:
+        return out, sums, dact_e, dact_dw
     return (out, sums) if want_sums else out
 
 

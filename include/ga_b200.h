@@ -135,10 +135,15 @@ int ga_dwconv5x5_ex(const ga_tensor* in, const ga_tensor* mul, const float* weig
 int ga_mbconv_fused_supported(const ga_tensor* x, int hidden);
 int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
                     const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, void* stream);
-/* same, and the SE squeeze of the result (architecture.py:37-61, `x.mean(dim=[2,3])` numerator) from the cell's epilogue: csum_out (or NULL) receives the
- * per-image channel sums of `out` as stored (bf16) in the slices ga_channel_sum uses, [N][ga_channel_sum_parts(N, H*W)][C] fp32 */
+/* same, with two optional extras from the same pass:
+ *   csum_out (or NULL): the SE squeeze of the result (architecture.py:37-61, the numerator of `x.mean(dim=[2,3])`) -- per-image channel sums of `out`
+ *     as stored (bf16) in the slices ga_channel_sum uses, [N][ga_channel_sum_parts(N, H*W)][C] fp32;
+ *   dact_e, dact_dw (both or neither): the tape of the attack path -- SiLU'(expand pre-activation) and SiLU'(depthwise pre-activation), bf16
+ *     [N][H][W][hidden], the factors ga_conv2d_tc(mul=) / ga_dwconv5x5_ex(mul=) apply in the backward sweep (what autograd saves for
+ *     architecture.py:164-173 under untargeted.py:146,201). */
 int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
-                       const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out, void* stream);
+                       const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out,
+                       const ga_tensor* dact_e, const ga_tensor* dact_dw, void* stream);
 /* debug only: per-role clock64 timeline of the 32x32 fused decoder cell; buf = device uint64[8*13*24*8] or NULL (off) */
 int ga_debug_mbconv_trace(unsigned long long* buf);
 /* debug only: clock64 timeline of CTA 0 of the persistent 3x3 kernel; buf = device uint64[3*16*16] or NULL (off) */

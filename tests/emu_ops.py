@@ -193,7 +193,18 @@ def dw_weights_chunked(dw_w):
     return real_ops.dw_weights_chunked(dw_w)
 
 
-def mbconv_fused(x, e, dw_w_chunked, dw_b, p, want_sums=False):
+def mbconv_fused(x, e, dw_w_chunked, dw_b, p, want_sums=False, want_tape=False):
+    if want_tape:          # the three kernels the fused taping cell replaces, with their tapes
+        dw_w = dw_w_chunked.permute(1, 0, 2).reshape(25, -1)
+        dact_e = torch.empty(x.shape[:3] + (e.cout,), dtype=torch.bfloat16)
+        h1, _ = conv2d_tc(x, e, dact_out=dact_e)
+        h2, dact_dw = dwconv5x5(h1, dw_w, dw_b, ACT_SILU, False, torch.bfloat16, want_dact=True)
+        r, _ = conv2d_tc(h2, p)
+        _launches[0] -= 2
+        s_ = channel_sum(r) if want_sums else None
+        if want_sums:
+            _launches[0] -= 1
+        return r, s_, dact_e, dact_dw
     if want_sums:
         r = mbconv_fused(x, e, dw_w_chunked, dw_b, p)
         s = channel_sum(r)

@@ -77,3 +77,25 @@ def test_mbconv_fused_channel_sums(n, w, c, hidden):
     # same addends, different association: fp32 rounding only
     scale = max(1.0, ref.abs().max().item())
     assert (sums - ref).abs().max().item() <= 2e-5 * scale * (min(w * w, 128) ** 0.5)
+
+
+@pytest.mark.parametrize("n,w,c,hidden", [(3, 8, 256, 128), (301, 8, 256, 64), (2, 16, 128, 192), (150, 16, 128, 64), (3, 32, 64, 128), (40, 32, 64, 64)])
+def test_mbconv_fused_tape(n, w, c, hidden):
+    """Taping variant (attack path): r and the channel sums are those of the plain fused cell, and the two tapes are SiLU' of the expand /
+    depthwise pre-activations -- compared with the three taping kernels it replaces (bf16 tapes of O(1) values: a few bf16 ulps; the fused cell
+    keeps the hidden tile in fp16 where the three kernels round it to bf16)."""
+    e, dw_w, dw_b, p = _cell(c, hidden, seed=n + w + hidden)
+    x = torch.randn(n, w, w, c, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    ed, pd, xd, wd, bd = _dev(e), _dev(p), x.to(DEV), dw_w.to(DEV), dw_b.to(DEV)
+    wc = ops.dw_weights_chunked(wd)
+    r0, s0 = ops.mbconv_fused(xd, ed, wc, bd, pd, want_sums=True)
+    r, s, de, dd = ops.mbconv_fused(xd, ed, wc, bd, pd, want_sums=True, want_tape=True)
+    de3 = torch.empty(n, w, w, hidden, device=DEV, dtype=torch.bfloat16)
+    h1, _ = ops.conv2d_tc(xd, ed, dact_out=de3)
+    h2, dd3 = ops.dwconv5x5(h1, wd, bd, ACT_SILU, False, torch.bfloat16, want_dact=True)
+    torch.cuda.synchronize()
+    assert torch.equal(r0, r) and torch.equal(s0, s)
+    assert de.shape == (n, w, w, hidden) and dd.shape == (n, w, w, hidden)
+    assert (de.float() - de3.float()).abs().max().item() <= 1.6e-2          # same accumulator, same formula: at most one bf16 ulp of ~1
+    err_dd = (dd.float() - dd3.float()).abs()
+    assert err_dd.max().item() <= 6e-2 and err_dd.mean().item() <= 4e-3, (err_dd.max().item(), err_dd.mean().item())
