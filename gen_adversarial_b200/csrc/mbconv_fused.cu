@@ -26,7 +26,7 @@ namespace ga {
 
 constexpr int MB_THREADS = 416;      // control warp + 4 activation warps + 8 depthwise warps
 #ifndef MB_MAXNREG
-#define MB_MAXNREG 112
+#define MB_MAXNREG 128
 #endif
 
 template <int W_IMG> struct MbGeom;
@@ -45,6 +45,12 @@ struct MbParams {
   __nv_bfloat16* out;           // [N][H][W][C]
   __nv_bfloat16* dact_e;        // TAPE: SiLU'(expand pre-activation), [N][H][W][hidden] (what the attack path's backward multiplies by)
   __nv_bfloat16* dact_dw;       // TAPE: SiLU'(depthwise pre-activation), [N][H][W][hidden]
+  // BWD (input gradient of the cell, same pipeline with transposed weights and flipped taps): the two stages multiply by the tapes instead of
+  // applying bias + SiLU, and the epilogue is  out_f32 = acc + add_f32
+  const __nv_bfloat16* mul_act; // [N][H][W][hidden] factor of the first stage (dact_dw: the gradient enters through the project conv)
+  const __nv_bfloat16* mul_dw;  // [N][H][W][hidden] factor of the depthwise stage (dact_e)
+  const float* add_f32;         // [N][H][W][C] or NULL: gradient arriving through the skip connection
+  float* out_f32;               // [N][H][W][C]
   float* csum;                  // optional: SE squeeze of `out` -- per-image channel sums in the 128-pixel slices of ga_channel_sum, [N][HW/128 or 1][C]
   int act_hi;                   // 1: activation warps are warps 9-12 (scheduler priority is highest-warp-id-first), depthwise warps 1-8
   int sleep_ns;                 // back-off of the SIMT mbarrier polls
@@ -93,10 +99,10 @@ __device__ __forceinline__ float2 h2_to_f2(uint32_t v) {
 }
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 
-// 416 threads x 112 registers = 46.6K of the SM's 64K: a 256-thread elementwise CTA (<= 64 registers: SE / residual, channel sums, latent mixing) of
-// ANOTHER stream fits beside this CTA and streams through the HBM pipes the cell leaves idle (MLVGMDefenseModel.set_streams)
-template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false, bool TAPE = false>
-__global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
+// (a 112-register build -- room for a 256-thread elementwise CTA of another stream beside this CTA -- was tried: registers are per SM sub-partition
+// and 4 of this CTA's 13 warps share one, so the second CTA does not fit anyway)
+template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false, bool TAPE = false, bool BWD = false>
+__global__ void __maxnreg__(MB_MAXNREG) mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                      const __grid_constant__ CUtensorMap tmWe,
                                                                      const __grid_constant__ CUtensorMap tmWp, const MbParams p) {
   using G = MbGeom<W_IMG>;
@@ -181,8 +187,10 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
     // expand bias pre-halved: SiLU(v) = h + h tanh(h) with h = v/2 = fma(acc, 0.5, be/2) -- exact (power-of-two scaling), one FMA-pipe op less
-    for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) s_be[i] = 0.5f * p.be[i];
-    for (int i = threadIdx.x - 32; i < C; i += MB_THREADS - 32) s_bp[i] = p.bp[i];
+    if (!BWD) {
+      for (int i = threadIdx.x - 32; i < p.hidden; i += MB_THREADS - 32) s_be[i] = 0.5f * p.be[i];
+      for (int i = threadIdx.x - 32; i < C; i += MB_THREADS - 32) s_bp[i] = p.bp[i];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -305,6 +313,41 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
         const int64_t pix = pix0 + m * 128 + q * 32 + lane;
         // 64 accumulator columns in flight per tcgen05.wait (the round trip is ~1k clk for a lone warp; C / 16 of them in a row were 10% of
         // the CTA's lifetime), then one full 128-byte line per thread
+        if (BWD) {
+          // out_f32 = acc + add_f32: 32 columns per step (the skip gradient's 128 bytes are in flight while the accumulator is read)
+          const bool row_ok = pix < total_pix;
+#pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            float4 av[8];
+            if (p.add_f32 != nullptr && row_ok) {
+              const float4* ap = reinterpret_cast<const float4*>(p.add_f32 + pix * C + c0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) av[i] = __ldg(ap + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint32_t r[2][16];
+#pragma unroll
+            for (int c16 = 0; c16 < 2; ++c16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + PROJ_OFF + m * C + c0 + c16 * 16, r[c16]);
+            tmem_ld_wait();
+            if (m == G::MT_OUT - 1 && c0 + 32 >= C) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(proj_empty);
+            }
+            if (row_ok) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * C + c0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t* rr = &r[i >> 2][(i & 3) * 4];
+                o[i] = make_float4(__uint_as_float(rr[0]) + av[i].x, __uint_as_float(rr[1]) + av[i].y, __uint_as_float(rr[2]) + av[i].z,
+                                   __uint_as_float(rr[3]) + av[i].w);
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < C; c0 += 64) {
           uint32_t r[4][16];
@@ -395,6 +438,19 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
         // TAPE: the global pixel this thread's row belongs to (halo rows of a 32x32 tile belong to the neighbouring tiles)
         bool own = false;
         int64_t gpix = 0;
+        uint4 mv[8];                 // BWD: this pixel's 64 tape factors of the chunk (in flight while the accumulator is read)
+        if (BWD) {
+          if (W_IMG == 32) {
+            own = in_img;            // every row of the tile inside the image, halo rows included
+            gpix = (((int64_t)n0 * p.H + y0 - G::HALO + (pin >> 5)) << 5) + (pin & 31);
+          } else {
+            gpix = (int64_t)n0 * p.H * W_IMG + pin;
+            own = gpix < (int64_t)p.N * p.H * W_IMG;
+          }
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mul_act + gpix * p.hidden + k * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mv[i] = own ? __ldg(mp + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
         if (TAPE) {
           if (W_IMG == 32) {
             const int rt = (pin >> 5) - G::HALO;
@@ -417,6 +473,13 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
           uint32_t pk[8], dk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            if (BWD) {               // gradient through the first GEMM times the tape; rows outside the image are the conv's zero padding
+              const uint4 mq = mv[c16 * 2 + (j >> 2)];
+              const uint32_t mw = (j & 3) == 0 ? mq.x : ((j & 3) == 1 ? mq.y : ((j & 3) == 2 ? mq.z : mq.w));
+              const float2 f = bf2_to_f2(mw);
+              pk[j] = own ? pack_bf16x2(__uint_as_float(r[c16][2 * j]) * f.x, __uint_as_float(r[c16][2 * j + 1]) * f.y) : 0u;
+              continue;
+            }
             const float2 b = lds_f2(be_a + (c16 * 16 + 2 * j) * 4);
             const float h0 = fmaf(__uint_as_float(r[c16][2 * j]), 0.5f, b.x), h1 = fmaf(__uint_as_float(r[c16][2 * j + 1]), 0.5f, b.y);
             const float t0 = tanh_approx(h0), t1 = tanh_approx(h1);
@@ -548,7 +611,9 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
         stamp(g, 5);
         if (TAPE && kc + 1 == nch) { ++ti_d; tile_origin(ti_d, n0d, y0d); }
       }
-    } else
+    } else {
+    int ti_b = 0, n0b = 0, y0b = 0;
+    if (BWD) tile_origin(0, n0b, y0b);
     for (int g = 0, kc = 0; g < g_total; ++g, kc = (kc + 1 == nch) ? 0 : kc + 1) {
       float2 wt[25];
       {
@@ -558,7 +623,25 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
 #pragma unroll
         for (int t = 0; t < 25; ++t) wt[t] = lds_f2(wsrc + t * 256);
       }
-      const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.dw_b + kc * 64 + 2 * lane));
+      const float2 b2 = BWD ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(p.dw_b + kc * 64 + 2 * lane));
+      // BWD: global pixel of output (oy, c) of this warp's strip, and an L2 prefetch of the tape lines the store phases will read
+      auto gpix_of = [&](int oy, int c, bool& ok) -> int64_t {
+        ok = true;
+        if (W_IMG == 32) return (((int64_t)n0b * p.H + y0b + oy) << 5) + cs + c;
+        if (W_IMG == 16) return (int64_t)n0b * 256 + oy * 16 + cs + c;
+        ok = n0b + img < p.N;
+        return (int64_t)(n0b + img) * 64 + oy * 8 + cs + c;
+      };
+      if (BWD) {
+#pragma unroll
+        for (int oy = 0; oy < G::R_OUT; ++oy)
+#pragma unroll
+          for (int c = 0; c < G::STRIP_W; ++c) {
+            bool ok;
+            const int64_t gp = gpix_of(oy, c, ok);
+            if (ok && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mul_dw + gp * p.hidden + kc * 64));
+          }
+      }
       stamp(g, 1);
       mbar_wait_backoff(&h_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
       stamp(g, 2);
@@ -601,11 +684,30 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
         if (pass == 0) stamp(g, 3);
         if (pass == 0 && g >= 1) mbar_wait_backoff(a2_empty, (g - 1) & 1, (uint32_t)p.sleep_ns); // project(k-1) has consumed A2
         if (pass == 0) stamp(g, 4);
+        if (BWD) {
+          uint32_t dv[RP][G::STRIP_W];
+#pragma unroll
+          for (int oy = 0; oy < RP; ++oy)
+#pragma unroll
+            for (int c = 0; c < G::STRIP_W; ++c) {
+              bool ok;
+              const int64_t gp = gpix_of(pass * RP + oy, c, ok);
+              dv[oy][c] = ok ? __ldg(reinterpret_cast<const uint32_t*>(p.mul_dw + gp * p.hidden + kc * 64 + 2 * lane)) : 0u;
+            }
+#pragma unroll
+          for (int oy = 0; oy < RP; ++oy)
+#pragma unroll
+            for (int c = 0; c < G::STRIP_W; ++c) {
+              const float2 f = bf2_to_f2(dv[oy][c]);
+              sts_b32(a2_col[c] + (pass * RP + oy) * (W_IMG * 128), pack_bf16x2(acc[oy][c].x * f.x, acc[oy][c].y * f.y));
+            }
+        } else {
 #pragma unroll
         for (int oy = 0; oy < RP; ++oy)
 #pragma unroll
           for (int c = 0; c < G::STRIP_W; ++c)
             sts_b32(a2_col[c] + (pass * RP + oy) * (W_IMG * 128), pack_bf16x2(silu_fast(acc[oy][c].x), silu_fast(acc[oy][c].y)));
+        }
       }
       fence_proxy_async_smem();                                            // generic-proxy writes -> visible to the MMA (async proxy)
       __syncwarp();
@@ -613,6 +715,8 @@ __global__ void __maxnreg__((F16 && !TAPE) ? MB_MAXNREG : 128) mbconv_fused_kern
       // chunk's taps / H tile and only meets the others again at a2_empty, after its next pass-0 accumulation (ncu: 13% barrier stalls)
       if (lane == 0) mbar_arrive(a2_full);
       stamp(g, 5);
+      if (BWD && kc + 1 == nch) { ++ti_b; tile_origin(ti_b, n0b, y0b); }
+    }
     }
   }
   stamp(1, 7);
@@ -665,7 +769,7 @@ static int mb_encode_x(CUtensorMap* tm, const ga_tensor* t, int bw, int bh, int 
 
 static unsigned long long* g_mb_trace = nullptr;
 
-template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false, bool TAPE = false>
+template <int C, int W_IMG, int NBUF, bool TRACE = false, bool F16 = false, bool TAPE = false, bool BWD = false>
 static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, const MbParams& p, cudaStream_t s) {
   using G = MbGeom<W_IMG>;
   constexpr int KB = C / 64;
@@ -674,7 +778,7 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   GA_CHECK(smem <= 227 * 1024, "ga_mbconv_fused: shared memory request %d too large", smem);
   static int configured = 0;
   if (configured < smem) {
-    GA_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GA_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16, TAPE, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   CUtensorMap tmX, tmWe, tmWp;
@@ -689,7 +793,7 @@ static int launch_mbconv(const ga_tensor* x, const void* we, const void* wp, con
   MbParams q = p;
   q.n_tiles = tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16, TAPE><<<grid, MB_THREADS, smem, s>>>(tmX, tmWe, tmWp, q);
+  mbconv_fused_kernel<C, W_IMG, NBUF, TRACE, F16, TAPE, BWD><<<grid, MB_THREADS, smem, s>>>(tmX, tmWe, tmWp, q);
   GA_LAUNCH_OK();
   return 0;
 }
@@ -763,6 +867,34 @@ extern "C" int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const f
   if (x->w == 16) return launch_mbconv<128, 16, 1>(x, we_tc, wp_tc, p, s);
   if (p.trace != nullptr) return launch_mbconv<64, 32, 2, true>(x, we_tc, wp_tc, p, s);
   return launch_mbconv<64, 32, 2>(x, we_tc, wp_tc, p, s);
+}
+
+// Input gradient of the decoder cell in one kernel (the attack path's backward; architecture.py:164-173 under torch.autograd.grad, untargeted.py:146,201):
+//   out = add + expand^T( dact_e * dw5x5^T( dact_dw * project^T(g) ) )
+// = the forward pipeline with the two 1x1 convs swapped and transposed (wpT_tc [hidden][C] feeds the first GEMM, weT_tc [C][hidden] the second), the taps
+// flipped (dw_wT, chunk-major), the tapes of ga_mbconv_fused_ex as stage factors, no biases, bf16 hidden tile with fp32 accumulation (gradients need the
+// bf16 exponent range), fp32 result.
+extern "C" int ga_mbconv_fused_bwd(const ga_tensor* g, const void* wpT_tc, const float* dw_wT, const ga_tensor* dact_dw, const ga_tensor* dact_e,
+                                   const void* weT_tc, const ga_tensor* add, int hidden, const ga_tensor* out, void* stream) {
+  GA_CHECK(g && wpT_tc && dw_wT && dact_dw && dact_e && weT_tc && out, "ga_mbconv_fused_bwd: null argument");
+  GA_CHECK(ga_mbconv_fused_supported(g, hidden), "ga_mbconv_fused_bwd: unsupported problem (n=%d h=%d w=%d c=%d hidden=%d)", g->n, g->h, g->w, g->c, hidden);
+  GA_CHECK(out->dtype == GA_F32 && same_shape(g, out) && (!add || (add->dtype == GA_F32 && same_shape(g, add))),
+           "ga_mbconv_fused_bwd: out (and add) must be fp32 with the gradient's shape");
+  GA_CHECK(dact_e->dtype == GA_BF16 && dact_dw->dtype == GA_BF16 && dact_e->n == g->n && dact_e->h == g->h && dact_e->w == g->w && dact_e->c == hidden &&
+               same_shape(dact_e, dact_dw), "ga_mbconv_fused_bwd: tape tensors must be bf16 [n][h][w][hidden]");
+  GA_CHECK(((((uintptr_t)wpT_tc) | ((uintptr_t)weT_tc) | ((uintptr_t)out->data) | ((uintptr_t)dact_e->data) | ((uintptr_t)dact_dw->data) |
+             (add ? (uintptr_t)add->data : 0)) & 15) == 0, "ga_mbconv_fused_bwd: pointers must be 16-byte aligned");
+  if (numel(g) == 0) return 0;
+  MbParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = g->n; p.H = g->h; p.hidden = hidden; p.dw_w = dw_wT;
+  p.mul_act = (const __nv_bfloat16*)dact_dw->data; p.mul_dw = (const __nv_bfloat16*)dact_e->data;
+  p.add_f32 = add ? (const float*)add->data : nullptr; p.out_f32 = (float*)out->data;
+  p.sleep_ns = 100;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g->w == 8) return launch_mbconv<256, 8, 1, false, false, false, true>(g, wpT_tc, weT_tc, p, s);
+  if (g->w == 16) return launch_mbconv<128, 16, 1, false, false, false, true>(g, wpT_tc, weT_tc, p, s);
+  return launch_mbconv<64, 32, 2, false, false, false, true>(g, wpT_tc, weT_tc, p, s);
 }
 
 // debug: per-role clock64 timeline of the 32x32 fused cell (scripts/trace_mbconv.py); buf = device uint64[8 * 13 * 24 * 8] or NULL (off)

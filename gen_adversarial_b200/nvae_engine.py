@@ -66,7 +66,7 @@ class _Enc:
 
 
 class _Dec:
-    __slots__ = ("e", "dw_w", "dw_wc", "dw_b", "p", "se", "skip", "up", "e_d", "p_d", "skip_d", "dw_wT")
+    __slots__ = ("e", "dw_w", "dw_wc", "dw_b", "p", "se", "skip", "up", "e_d", "p_d", "skip_d", "dw_wT", "dw_wTc")
 
 
 class NvaeEngine:
@@ -88,6 +88,7 @@ class NvaeEngine:
         self.fuse_cells = __import__("os").environ.get("GA_MBCONV_FUSED", "1") != "0"
         self.fuse_csum = __import__("os").environ.get("GA_FUSE_CSUM", "1") != "0"     # SE channel sums from the encoder conv2 epilogue
         self.fuse_tape = __import__("os").environ.get("GA_FUSE_TAPE", "1") != "0"     # attack path: taping forward of the decoder cells in the fused kernel
+        self.fuse_bwd = __import__("os").environ.get("GA_FUSE_BWD", "1") != "0"       # attack path: backward of the decoder cells in the fused kernel
         f = Folder(state_dict, self.device, want_tc=self.bf16)
         self._fold(f)
         self._prior_cache = {}
@@ -359,6 +360,10 @@ class NvaeEngine:
     def _dec_cell_bwd(self, g_out, rec):
         _, d, dact_e, dact_dw, r, sums = rec
         g_r = ops.se_residual_bwd(g_out, r, sums, d.se, 0.1, self.adt)
+        if (self.fuse_bwd and self.bf16 and not d.up and d.dw_wTc is not None and g_r.dtype == torch.bfloat16
+                and ops.mbconv_fused_supported(g_r, d.e, d.p)):
+            # project^T -> x SiLU'(dw out) -> transposed depthwise -> x SiLU'(expand out) -> expand^T (+ skip gradient) in one kernel
+            return ops.mbconv_fused_bwd(g_r, d.p_d, d.dw_wTc, dact_dw, dact_e, d.e_d, add=g_out)
         g_v2 = self._dgrad(g_r, d.p_d, mul=dact_dw, f32=False)                      # through project, times SiLU'(dw out)
         if d.up:
             g_h1 = ops.dwconv5x5(g_v2, d.dw_wT, None, ACT_NONE, False, self.adt)    # transposed depthwise (flipped taps)
@@ -482,6 +487,7 @@ class NvaeEngine:
             d.e_d, d.p_d = dg(d.e), dg(d.p)
             d.skip_d = dg(d.skip) if d.skip is not None else None
             d.dw_wT = d.dw_w.flip(0).contiguous()                        # 5x5 taps reversed = spatial flip
+            d.dw_wTc = ops.dw_weights_chunked(d.dw_wT) if (self.bf16 and d.dw_wc is not None) else None
         self.init_conv_d = dg(self.init_conv)
         self.enc0_d = dg(self.enc0)
         self.to_logits_d = dg(self.to_logits, pad_cin_to=round_up(self.to_logits.cout, 8))

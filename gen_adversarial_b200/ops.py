@@ -272,6 +272,22 @@ def mbconv_fused(x: torch.Tensor, e: ConvLayer, dw_w_chunked: torch.Tensor, dw_b
     return (out, sums) if want_sums else out
 
 
+def mbconv_fused_bwd(g: torch.Tensor, p_d: ConvLayer, dw_wT_chunked: torch.Tensor, dact_dw: torch.Tensor, dact_e: torch.Tensor, e_d: ConvLayer,
+                     add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """input gradient of the decoder-cell body in ONE kernel: add + e_d(dact_e * dw5x5^T(dact_dw * p_d(g)))  -> fp32 NHWC.
+    p_d / e_d: the dgrad layers of project / expand (transposed bf16 weights), dw_wT_chunked = dw_weights_chunked(flipped taps)"""
+    out = torch.empty(g.shape, device=g.device, dtype=torch.float32)
+    e0 = TIMER.start() if TIMER is not None else None
+    _lib.check(_lib.lib().ga_mbconv_fused_bwd(gt(g), p_d.w_tc.data_ptr(), ptr(dw_wT_chunked), gt(dact_dw), gt(dact_e), e_d.w_tc.data_ptr(),
+                                              gt(add), p_d.cout, gt(out), stream()), "mbconv_fused_bwd")
+    if e0 is not None:
+        n, h, w, c = g.shape
+        m, hid = n * h * w, p_d.cout
+        TIMER.stop(e0, f"fused:mbconv_bwd hw{h} c{c} hidden{hid}", 2.0 * m * hid * c * 2 + 2.0 * m * hid * 25,
+                   2.0 * m * c + 4.0 * m * c * (2 if add is not None else 1) + 4.0 * m * hid)
+    return out
+
+
 def channel_sum_parts(n: int, hw: int) -> int:
     return int(_lib.lib().ga_channel_sum_parts(n, hw))
 

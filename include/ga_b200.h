@@ -144,6 +144,13 @@ int ga_mbconv_fused(const ga_tensor* x, const void* we_tc, const float* be, cons
 int ga_mbconv_fused_ex(const ga_tensor* x, const void* we_tc, const float* be, const float* dw_w, const float* dw_b,
                        const void* wp_tc, const float* bp, int hidden, const ga_tensor* out, float* csum_out,
                        const ga_tensor* dact_e, const ga_tensor* dact_dw, void* stream);
+/* input gradient of the decoder cell in ONE kernel (the attack path's backward sweep; what torch.autograd.grad computes for
+ * architecture.py:164-173 under untargeted.py:146,201):   out = add + expand^T( dact_e * dw5x5^T( dact_dw * project^T(g) ) ).
+ * g: bf16 NHWC gradient w.r.t. the cell body's output; wpT_tc [hidden][C], weT_tc [C][hidden]: the transposed 1x1 weights (bf16 K-major, the
+ * dgrad layers' weights); dw_wT: flipped taps, chunk-major [hidden/64][25][64] fp32; dact_dw / dact_e: the tapes of ga_mbconv_fused_ex;
+ * add: fp32 NHWC gradient arriving through the skip connection, or NULL; out: fp32 NHWC.  Same shapes as ga_mbconv_fused_supported. */
+int ga_mbconv_fused_bwd(const ga_tensor* g, const void* wpT_tc, const float* dw_wT, const ga_tensor* dact_dw, const ga_tensor* dact_e,
+                        const void* weT_tc, const ga_tensor* add, int hidden, const ga_tensor* out, void* stream);
 /* debug only: per-role clock64 timeline of the 32x32 fused decoder cell; buf = device uint64[8*13*24*8] or NULL (off) */
 int ga_debug_mbconv_trace(unsigned long long* buf);
 /* debug only: clock64 timeline of CTA 0 of the persistent 3x3 kernel; buf = device uint64[3*16*16] or NULL (off) */

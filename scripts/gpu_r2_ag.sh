@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== mbconv tests"; timeout -s KILL 600 python -m pytest tests/test_mbconv_gpu.py -q -m gpu -x -p no:cacheprovider -s 2>&1 | grep -E "mbconv bwd|passed|failed|Error|error" | tail -20
+echo "== backward tests"; timeout -s KILL 1200 python -m pytest tests/test_backward_gpu.py tests/test_attacks_gpu.py -q -m gpu -x -p no:cacheprovider 2>&1 | tail -5
+for fb in 1 0; do echo "== pgd GA_FUSE_BWD=$fb"; GA_FUSE_BWD=$fb timeout -s KILL 900 python bench.py --workload pgd --steps 1 --warmup 1 --no-cpu-baseline 2>&1 >gpurun_out/r2ag_pgd_fb$fb.json | tail -1; done

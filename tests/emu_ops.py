@@ -221,6 +221,16 @@ def mbconv_fused(x, e, dw_w_chunked, dw_b, p, want_sums=False, want_tape=False):
     return r
 
 
+def mbconv_fused_bwd(g, p_d, dw_wT_chunked, dact_dw, dact_e, e_d, add=None):
+    """the three kernels the fused backward cell replaces"""
+    dw_wT = dw_wT_chunked.permute(1, 0, 2).reshape(25, -1)
+    g_v2, _ = conv2d_tc(g, p_d, mul=dact_dw)
+    g_v1 = dwconv5x5(g_v2, dw_wT, None, ACT_NONE, False, torch.bfloat16, mul=dact_e)
+    _, o = conv2d_tc(g_v1, e_d, want_bf16=False, want_f32=True, add=add)
+    _launches[0] -= 2
+    return o
+
+
 def se_residual(r, sums, se, res_scale, skip, out_dtype=torch.float32, want_out2=False, out2_dtype=torch.bfloat16,
                 act_affine=None, act_dtype=torch.bfloat16, want_gate=False, act_op=ACT_SILU, act_plain=False):
     _launches[0] += 1

@@ -99,3 +99,32 @@ def test_mbconv_fused_tape(n, w, c, hidden):
     assert (de.float() - de3.float()).abs().max().item() <= 1.6e-2          # same accumulator, same formula: at most one bf16 ulp of ~1
     err_dd = (dd.float() - dd3.float()).abs()
     assert err_dd.max().item() <= 6e-2 and err_dd.mean().item() <= 4e-3, (err_dd.max().item(), err_dd.mean().item())
+
+
+@pytest.mark.parametrize("with_add", [True, False])
+@pytest.mark.parametrize("n,w,c,hidden", [(3, 8, 256, 128), (301, 8, 256, 64), (2, 16, 128, 192), (150, 16, 128, 64), (3, 32, 64, 128), (40, 32, 64, 64)])
+def test_mbconv_fused_backward_matches_three_kernels(n, w, c, hidden, with_add):
+    """Input gradient of the cell in one kernel against the three kernels of the backward sweep it replaces (project dgrad x tape, transposed
+    depthwise x tape, expand dgrad + skip gradient): same bf16 intermediates, fp32 accumulation, fp32 result."""
+    e, dw_w, dw_b, p = _cell(c, hidden, seed=n + w + hidden)
+    gen = torch.Generator().manual_seed(7)
+    g = (torch.randn(n, w, w, c, generator=gen) * 1e-3).to(torch.bfloat16).to(DEV)
+    dact_dw = (torch.rand(n, w, w, hidden, generator=gen) * 1.2 - 0.1).to(torch.bfloat16).to(DEV)
+    dact_e = (torch.rand(n, w, w, hidden, generator=gen) * 1.2 - 0.1).to(torch.bfloat16).to(DEV)
+    add = (torch.randn(n, w, w, c, generator=gen) * 1e-3).to(DEV) if with_add else None
+    p_d = ops.ConvLayer(1, 1, 1, 0, c, hidden, post_act=ACT_NONE, name="project_dgrad")
+    p_d.w_tc = p.w_tc.t().contiguous().to(DEV)           # [hidden][C]
+    e_d = ops.ConvLayer(1, 1, 1, 0, hidden, c, post_act=ACT_NONE, name="expand_dgrad")
+    e_d.w_tc = e.w_tc.t().contiguous().to(DEV)           # [C][hidden]
+    dw_wT = dw_w.flip(0).contiguous().to(DEV)
+    g_v2, _ = ops.conv2d_tc(g, p_d, mul=dact_dw)
+    g_v1 = ops.dwconv5x5(g_v2, dw_wT, None, ACT_NONE, False, torch.bfloat16, mul=dact_e)
+    _, ref = ops.conv2d_tc(g_v1, e_d, want_bf16=False, want_f32=True, add=add)
+    got = ops.mbconv_fused_bwd(g, p_d, ops.dw_weights_chunked(dw_wT), dact_dw, dact_e, e_d, add=add)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    rel = ((got - ref).norm() / ref.norm()).item()
+    print(f"mbconv bwd n={n} w={w} c={c} hidden={hidden} add={with_add}: max err {err:.3e} (scale {scale:.3e}), rel-L2 {rel:.3e}")
+    assert torch.isfinite(got).all()
+    assert rel <= 1e-2 and err <= 3e-2 * scale
