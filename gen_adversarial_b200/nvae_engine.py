@@ -88,7 +88,7 @@ class NvaeEngine:
         self.fuse_cells = __import__("os").environ.get("GA_MBCONV_FUSED", "1") != "0"
         self.fuse_csum = __import__("os").environ.get("GA_FUSE_CSUM", "1") != "0"     # SE channel sums from the encoder conv2 epilogue
         self.fuse_tape = __import__("os").environ.get("GA_FUSE_TAPE", "1") != "0"     # attack path: taping forward of the decoder cells in the fused kernel
-        self.fuse_bwd = __import__("os").environ.get("GA_FUSE_BWD", "1") != "0"       # attack path: backward of the decoder cells in the fused kernel
+        self.fuse_bwd = int(__import__("os").environ.get("GA_FUSE_BWD", "2"))         # attack path: backward of the decoder cells in the fused kernel
         f = Folder(state_dict, self.device, want_tc=self.bf16)
         self._fold(f)
         self._prior_cache = {}
@@ -360,8 +360,11 @@ class NvaeEngine:
     def _dec_cell_bwd(self, g_out, rec):
         _, d, dact_e, dact_dw, r, sums = rec
         g_r = ops.se_residual_bwd(g_out, r, sums, d.se, 0.1, self.adt)
+        # (isolated: 332 vs 431 us at 16x16, 197 vs 249 us at 8x8, but 779 vs 707 us at 32x32 -- the 4 halo rows make the first stage read 1.5x the
+        #  tape, one 128-byte row load per thread; inside the attack iteration the fused kernel is no slower there either (118.2 vs 117.9 img/s) and
+        #  saves two hidden-sized intermediates.  GA_FUSE_BWD=1 keeps the 32x32 cells on the three kernels, 0 all cells.)
         if (self.fuse_bwd and self.bf16 and not d.up and d.dw_wTc is not None and g_r.dtype == torch.bfloat16
-                and ops.mbconv_fused_supported(g_r, d.e, d.p)):
+                and (g_r.shape[2] <= 16 or self.fuse_bwd >= 2) and ops.mbconv_fused_supported(g_r, d.e, d.p)):
             # project^T -> x SiLU'(dw out) -> transposed depthwise -> x SiLU'(expand out) -> expand^T (+ skip gradient) in one kernel
             return ops.mbconv_fused_bwd(g_r, d.p_d, d.dw_wTc, dact_dw, dact_e, d.e_d, add=g_out)
         g_v2 = self._dgrad(g_r, d.p_d, mul=dact_dw, f32=False)                      # through project, times SiLU'(dw out)

@@ -62,6 +62,36 @@ def mbconv():
         fl = 2.0 * m * hidden * c * 2 + 2.0 * m * hidden * 25
         print(f"mbconv n={n} hw={w} c={c} hidden={hidden}: {t:7.1f} us  {fl / t / 1e6:6.1f} TFLOP/s   fp32-pipe floor "
               f"{m * hidden * (25 + 5) / (148 * 128 * 1.965e3):6.1f} us")
+        # attack path: taping forward and backward of the cell, fused against the three kernels each replaces
+        t_tape = timeit(lambda: ops.mbconv_fused(x, e, dw, db, p, want_sums=True, want_tape=True))
+        dw_w = dw.permute(1, 0, 2).reshape(25, hidden).contiguous()
+
+        def tape3():
+            de = torch.empty(n, w, w, hidden, device=DEV, dtype=torch.bfloat16)
+            h1, _ = ops.conv2d_tc(x, e, dact_out=de)
+            h2, dd = ops.dwconv5x5(h1, dw_w, db, ACT_SILU, False, torch.bfloat16, want_dact=True)
+            r, _ = ops.conv2d_tc(h2, p)
+            return ops.channel_sum(r)
+        t_tape3 = timeit(tape3)
+        _, _, de, dd = ops.mbconv_fused(x, e, dw, db, p, want_sums=True, want_tape=True)
+        p_d = ops.ConvLayer(1, 1, 1, 0, c, hidden, post_act=ACT_NONE, name="project_dgrad")
+        p_d.w_tc = p.w_tc.t().contiguous()
+        e_d = ops.ConvLayer(1, 1, 1, 0, hidden, c, post_act=ACT_NONE, name="expand_dgrad")
+        e_d.w_tc = e.w_tc.t().contiguous()
+        dw_wT = dw_w.flip(0).contiguous()
+        dwTc = ops.dw_weights_chunked(dw_wT)
+        gr = (torch.randn(n, w, w, c, device=DEV, generator=g) * 1e-3).bfloat16()
+        add = torch.randn(n, w, w, c, device=DEV, generator=g) * 1e-3
+        t_bwd = timeit(lambda: ops.mbconv_fused_bwd(gr, p_d, dwTc, dd, de, e_d, add=add))
+
+        def bwd3():
+            g2, _ = ops.conv2d_tc(gr, p_d, mul=dd)
+            g1 = ops.dwconv5x5(g2, dw_wT, None, ACT_NONE, False, torch.bfloat16, mul=de)
+            return ops.conv2d_tc(g1, e_d, want_bf16=False, want_f32=True, add=add)
+        t_bwd3 = timeit(bwd3)
+        print(f"   attack path: taping fwd fused {t_tape:7.1f} us (three kernels + channel_sum {t_tape3:7.1f} us)   backward fused {t_bwd:7.1f} us "
+              f"(three kernels {t_bwd3:7.1f} us)")
+        del de, dd
 
 
 def k1():
