@@ -624,23 +624,23 @@ __global__ void __maxnreg__(MB_MAXNREG) mbconv_fused_kernel(const __grid_constan
         for (int t = 0; t < 25; ++t) wt[t] = lds_f2(wsrc + t * 256);
       }
       const float2 b2 = BWD ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(p.dw_b + kc * 64 + 2 * lane));
-      // BWD: global pixel of output (oy, c) of this warp's strip, and an L2 prefetch of the tape lines the store phases will read
-      auto gpix_of = [&](int oy, int c, bool& ok) -> int64_t {
-        ok = true;
-        if (W_IMG == 32) return (((int64_t)n0b * p.H + y0b + oy) << 5) + cs + c;
-        if (W_IMG == 16) return (int64_t)n0b * 256 + oy * 16 + cs + c;
-        ok = n0b + img < p.N;
-        return (int64_t)(n0b + img) * 64 + oy * 8 + cs + c;
-      };
+      // BWD: this lane's tape word of output (0, 0) of the warp's strip; output (oy, c) is (oy * W + c) pixels further.  The lines the store
+      // phases will read are pulled into L2 now.
+      const char* tape0 = nullptr;
+      bool tape_ok = true;
+      const uint32_t pstride = (uint32_t)p.hidden * 2u;
       if (BWD) {
+        int64_t gp0;
+        if (W_IMG == 32) gp0 = (((int64_t)n0b * p.H + y0b) << 5) + cs;
+        else if (W_IMG == 16) gp0 = (int64_t)n0b * 256 + cs;
+        else { gp0 = (int64_t)(n0b + img) * 64 + cs; tape_ok = n0b + img < p.N; }
+        tape0 = reinterpret_cast<const char*>(p.mul_dw + gp0 * p.hidden + kc * 64 + 2 * lane);
+        if (tape_ok) {
 #pragma unroll
-        for (int oy = 0; oy < G::R_OUT; ++oy)
+          for (int oy = 0; oy < G::R_OUT; ++oy)
 #pragma unroll
-          for (int c = 0; c < G::STRIP_W; ++c) {
-            bool ok;
-            const int64_t gp = gpix_of(oy, c, ok);
-            if (ok && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mul_dw + gp * p.hidden + kc * 64));
-          }
+            for (int c = 0; c < G::STRIP_W; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(tape0 + (uint32_t)(oy * W_IMG + c) * pstride));
+        }
       }
       stamp(g, 1);
       mbar_wait_backoff(&h_full[g & 1], (g >> 1) & 1, (uint32_t)p.sleep_ns);
@@ -651,6 +651,13 @@ __global__ void __maxnreg__(MB_MAXNREG) mbconv_fused_kernel(const __grid_constan
       constexpr int RP = (G::R_OUT * G::STRIP_W > 16) ? G::R_OUT / 2 : G::R_OUT;
 #pragma unroll
       for (int pass = 0; pass < G::R_OUT / RP; ++pass) {
+        if (BWD && pass > 0) {
+          // BWD: the taps are re-read from shared memory for every pass, so their 50 registers are free while the previous pass' store phase
+          // keeps all its tape loads in flight (with the taps live the compiler serialised them: 2.8k clk per store phase)
+          const uint32_t wsrc = smem_u32(s_dww) + ((g & 1) * 25 * 64 + 2 * lane) * 4;
+#pragma unroll
+          for (int t = 0; t < 25; ++t) wt[t] = lds_f2(wsrc + t * 256);
+        }
         float2 acc[RP][G::STRIP_W];
 #pragma unroll
         for (int oy = 0; oy < RP; ++oy)
@@ -689,11 +696,8 @@ __global__ void __maxnreg__(MB_MAXNREG) mbconv_fused_kernel(const __grid_constan
 #pragma unroll
           for (int oy = 0; oy < RP; ++oy)
 #pragma unroll
-            for (int c = 0; c < G::STRIP_W; ++c) {
-              bool ok;
-              const int64_t gp = gpix_of(pass * RP + oy, c, ok);
-              dv[oy][c] = ok ? __ldg(reinterpret_cast<const uint32_t*>(p.mul_dw + gp * p.hidden + kc * 64 + 2 * lane)) : 0u;
-            }
+            for (int c = 0; c < G::STRIP_W; ++c)
+              dv[oy][c] = tape_ok ? __ldg(reinterpret_cast<const uint32_t*>(tape0 + (uint32_t)((pass * RP + oy) * W_IMG + c) * pstride)) : 0u;
 #pragma unroll
           for (int oy = 0; oy < RP; ++oy)
 #pragma unroll
@@ -894,6 +898,8 @@ extern "C" int ga_mbconv_fused_bwd(const ga_tensor* g, const void* wpT_tc, const
   cudaStream_t s = (cudaStream_t)stream;
   if (g->w == 8) return launch_mbconv<256, 8, 1, false, false, false, true>(g, wpT_tc, weT_tc, p, s);
   if (g->w == 16) return launch_mbconv<128, 16, 1, false, false, false, true>(g, wpT_tc, weT_tc, p, s);
+  p.trace = g_mb_trace;
+  if (p.trace != nullptr) return launch_mbconv<64, 32, 2, true, false, false, true>(g, wpT_tc, weT_tc, p, s);
   return launch_mbconv<64, 32, 2, false, false, false, true>(g, wpT_tc, weT_tc, p, s);
 }
 
