@@ -651,7 +651,7 @@ __global__ void __maxnreg__(MB_MAXNREG) mbconv_fused_kernel(const __grid_constan
       constexpr int RP = (G::R_OUT * G::STRIP_W > 16) ? G::R_OUT / 2 : G::R_OUT;
 #pragma unroll
       for (int pass = 0; pass < G::R_OUT / RP; ++pass) {
-        if (BWD && pass > 0) {
+        if (BWD && pass > 0 && W_IMG != 16) {         // (measured per shape: 32x32 769 -> 663 us, 8x8 195 -> 178 us; 16x16 is faster without: 331 vs 354 us)
           // BWD: the taps are re-read from shared memory for every pass, so their 50 registers are free while the previous pass' store phase
           // keeps all its tape loads in flight (with the taps live the compiler serialised them: 2.8k clk per store phase)
           const uint32_t wsrc = smem_u32(s_dww) + ((g & 1) * 25 * 64 + 2 * lane) * 4;
