@@ -4,6 +4,7 @@
 // anywhere here (the reference computes them and throws them away).
 // Convolution dgrads re-use the forward conv kernels on flipped/transposed weights; this file holds the
 // bandwidth-bound pieces.  Reductions are two-stage without atomics (bit-reproducible).
+#include <stdlib.h>
 #include "ga_common.cuh"
 
 namespace ga {
@@ -720,10 +721,15 @@ extern "C" int ga_se_residual_bwd(const ga_tensor* g_out, const ga_tensor* r, co
   SeBwdParams p;
   p.g = g_out->data; p.g_dtype = g_out->dtype; p.sums = sums; p.dots = dots_ws;
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.hidden = hidden; p.res_scale = res_scale;
-  p.g_r = g_r->data; p.gr_dtype = g_r->dtype; p.HW = HW; p.C = C; p.pix_per_block = ppb; p.nparts = nparts;
+  // the apply stage recomputes the gate MLP and its backward per CTA (five block-wide phases): give a CTA up to 512 pixels of an image so that
+  // the preamble is paid 4x less often at 32x32 (the slicing of the SUMS stays 128 pixels: nparts)
+  static int apply_ppb_max = -1;
+  if (apply_ppb_max < 0) { const char* e = getenv("GA_SE_BWD_APPLY_PPB"); apply_ppb_max = e ? atoi(e) : 512; }
+  const int appb = HW < apply_ppb_max ? HW : apply_ppb_max;
+  p.g_r = g_r->data; p.gr_dtype = g_r->dtype; p.HW = HW; p.C = C; p.pix_per_block = appb; p.nparts = nparts;
   const size_t smem = (4 * (size_t)C + 2 * hidden) * sizeof(float);
   GA_CHECK(smem <= 48 * 1024, "ga_se_residual_bwd: too many channels");
-  se_bwd_apply_kernel<<<dim3(nparts, r->n), 256, smem, s>>>(p);
+  se_bwd_apply_kernel<<<dim3(cdiv(HW, appb), r->n), 256, smem, s>>>(p);
   GA_LAUNCH_OK();
   return 0;
 }

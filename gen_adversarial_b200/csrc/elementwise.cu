@@ -1146,8 +1146,13 @@ extern "C" int ga_se_residual_fwd(const ga_tensor* r, const float* sums, const f
   p.act = act ? act->data : nullptr; p.act_dtype = act ? act->dtype : GA_F32;
   p.act_scale = act_scale; p.act_shift = act_shift; p.act_op = act_op; p.gate_out = gate_out;
   p.act_rtf = (act && act->dtype == GA_F32 && round_tf32_enabled()) ? 1 : 0;
-  p.HW = r->h * r->w; p.C = r->c; p.pix_per_block = se_pix_per_block(p.HW, r->n);
-  p.nparts = cdiv(p.HW, p.pix_per_block);
+  p.HW = r->h * r->w; p.C = r->c;
+  p.nparts = cdiv(p.HW, se_pix_per_block(p.HW, r->n));          // slicing of the channel sums: fixed 128 pixels
+  // a CTA recomputes the gate MLP (three block-wide phases of dependent loads) before it streams: up to 512 pixels of an image per CTA so that
+  // the preamble is paid 4x less often at 32x32
+  static int apply_ppb_max = -1;
+  if (apply_ppb_max < 0) { const char* e = getenv("GA_SE_APPLY_PPB"); apply_ppb_max = e ? atoi(e) : 512; }
+  p.pix_per_block = p.HW < apply_ppb_max ? p.HW : apply_ppb_max;
   const size_t smem = (2 * (size_t)p.C + hidden) * sizeof(float);
   GA_CHECK(smem <= 48 * 1024, "ga_se_residual_fwd: too many channels");
   se_residual_kernel<<<dim3(cdiv(p.HW, p.pix_per_block), r->n), 256, smem, (cudaStream_t)stream>>>(p);
