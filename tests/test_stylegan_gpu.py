@@ -54,6 +54,33 @@ def test_styled_bias_act(phases):
         assert (got.cpu() - ref).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("ydt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("phases", [False, True])
+@pytest.mark.parametrize("n,h,w,c", [(3, 16, 16, 32), (2, 32, 64, 8), (5, 8, 8, 256), (1, 64, 32, 64)])
+def test_styled_bias_act_vector_path(phases, ydt, n, h, w, c):
+    """the generator's big layers take the 8-channel / 4-items-per-thread kernel (bf16 outputs, lrelu * sqrt(2), power-of-two H, W, C / 8):
+    same arithmetic in the same order as the general kernel -- compared with the torch restatement at one bf16 ulp of the rounded outputs --
+    for plain and phase-interleaved inputs (bf16 / fp32 conv outputs), one or two modulated copies, ragged grid tails"""
+    g = torch.Generator().manual_seed(n + h + c)
+    y = torch.randn((n, h // 2, w // 2, 4 * c) if phases else (n, h, w, c), generator=g).to(ydt)
+    demod, noise, bias = torch.rand(n, c, generator=g) + 0.5, torch.randn(h, w, generator=g), torch.randn(c, generator=g)
+    sa, sb = torch.rand(n, c, generator=g) + 0.5, torch.rand(n, c, generator=g) + 0.5
+    yd, dd, nd, bd, sad, sbd = (t.to(DEV) for t in (y, demod, noise, bias, sa, sb))
+    for kw_ref, kw_got in (({}, {}), ({"scale_a": sa}, {"scale_a": sad}), ({"scale_a": sa, "scale_b": sb}, {"scale_a": sad, "scale_b": sbd}),
+                           ({"scale_b": sb, "want_out": False}, {"scale_b": sbd, "want_out": False})):
+        ref = emu_ops.styled_bias_act(y.float(), phases, demod, noise, 0.37, bias, ACT_LRELU_SQRT2, None, torch.float32, **kw_ref)
+        got = ops.styled_bias_act(yd, phases, dd, nd, 0.37, bd, ACT_LRELU_SQRT2, None, torch.bfloat16, **kw_got)
+        ref = ref if isinstance(ref, tuple) else (ref,)
+        got = got if isinstance(got, tuple) else (got,)
+        for r_, g_ in zip(ref, got):
+            if r_ is None:
+                assert g_ is None
+                continue
+            assert g_.dtype == torch.bfloat16 and g_.shape == (n, h, w, c)
+            err = (g_.float().cpu() - r_).abs()
+            assert (err <= 8e-3 * r_.abs().clamp_min(1.0)).all(), err.max().item()
+
+
 @pytest.mark.parametrize("up,down,pad", [(1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (2, 2)), (1, 1, (2, 1))])
 def test_upfirdn2d_matches_reference_semantics(up, down, pad):
     g = torch.Generator().manual_seed(2)
