@@ -140,6 +140,7 @@ _PROTOS = {
     "ga_debug_c3_trace": (c_int, [c_void_p]),
     "ga_tc_halo_enable": (c_int, [c_int]),
     "ga_mbconv_fused": (c_int, [T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, T, c_void_p]),
+    "ga_torgb_fused": (c_int, [T, c_void_p, c_void_p, T, c_void_p, T, c_void_p]),
     "ga_mbconv_fused_bwd": (c_int, [T, c_void_p, c_void_p, T, T, c_void_p, T, c_int, T, c_void_p]),
     "ga_mbconv_fused_ex": (c_int, [T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, T, c_void_p, T, T, c_void_p]),
     "ga_add_layernorm": (c_int, [T, T, c_void_p, c_void_p, c_float, T, T, c_void_p]),

@@ -561,6 +561,15 @@ def styled_bias_act(y, phases: bool, demod, noise_hw, noise_w: float, bias, act:
     return (out, out_b) if scale_b is not None else out
 
 
+@_timed("torgb_fused", hbm=True)
+def torgb_fused(x: torch.Tensor, L: ConvLayer, bias, skip=None, skip_up_kernel=None) -> torch.Tensor:
+    """ToRGB in one pass: conv1x1(x, L.w_tc [4][cin]) + bias + Upsample(skip)  -> fp32 (n, h, w, 4)"""
+    n, h, w, _ = x.shape
+    out = torch.empty((n, h, w, 4), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ga_torgb_fused(gt(x), L.w_tc.data_ptr(), ptr(bias), gt(skip), ptr(skip_up_kernel), gt(out), stream()), "torgb_fused")
+    return out
+
+
 @_timed("upfirdn2d", hbm=True)
 def upfirdn2d(x, kernel, up: int = 1, down: int = 1, pad=(0, 0), out_dtype=None):
     """same semantics as the reference op (stylegan2/op/upfirdn2d.py:141-147) on NHWC tensors"""

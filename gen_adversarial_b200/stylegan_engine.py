@@ -185,7 +185,13 @@ class StyleGan2Engine:
                                 scale_b=scale_rgb, want_out=scale_next is not None)
         return r if scale_rgb is not None else (r, None)
 
+    fuse_rgb = __import__("os").environ.get("GA_SG_FUSE_RGB", "1") != "0"
+
     def _rgb(self, xs, r: _ToRGB, skip):
+        if (self.fuse_rgb and self.bf16 and xs.dtype == torch.bfloat16 and r.conv.w_tc is not None and r.conv.w_tc.shape[0] == 4
+                and xs.shape[3] % 8 == 0 and r.conv.w_tc.shape[1] == xs.shape[3]):
+            # 1x1 conv to RGB + bias + up-sampled skip in one memory-bound pass (the tensor-core kernel ran this 4-column GEMM at 1.25 TB/s)
+            return ops.torgb_fused(xs, r.conv, r.bias, skip, r.up_kernel if skip is not None else None)
         y = self._conv(xs, r.conv, want_f32=True)                                                   # [B,H,W,4] fp32
         # the half-resolution skip is up-sampled (Upsample, generator.py:30-47) inside the epilogue kernel
         return ops.styled_bias_act(y, False, None, None, 0.0, r.bias, ACT_NONE, skip, torch.float32,

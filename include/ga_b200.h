@@ -230,6 +230,11 @@ int ga_styled_bias_act(const ga_tensor* y, int phases, const float* demod, const
                        const float* scale_a /*[n][c] nullable*/, const ga_tensor* out /*nullable*/, const float* scale_b,
                        const ga_tensor* out_b /*nullable*/, void* stream);
 /* zero-insert up-sample -> pad -> FIR (flipped kernel) -> decimate, NHWC                                 op/upfirdn2d_kernel.cu:52-137 */
+/* ToRGB in one pass (generator.py:271-292): out = conv1x1(x, w) + bias + Upsample(skip).  x: bf16 NHWC, already modulated by the layer's style;
+ * w_bf16 [4][cin] (RGB padded to 4 rows); bias fp32 [4] or NULL; skip: fp32 [n][h/2][w/2][4] with its 4x4 FIR `skip_up_kernel` (upfirdn2d up 2,
+ * pad (2,1)), or both NULL; out: fp32 [n][h][w][4]. */
+int ga_torgb_fused(const ga_tensor* x, const void* w_bf16, const float* bias, const ga_tensor* skip, const float* skip_up_kernel,
+                   const ga_tensor* out, void* stream);
 int ga_upfirdn2d(const ga_tensor* in, const float* kernel, int kh, int kw, int up, int down, int pad0, int pad1,
                  const ga_tensor* out, void* stream);
 int ga_avgpool_to_nchw(const ga_tensor* in, int k, int out_c, float* out_nchw, void* stream);           /* face_pool, psp.py:26,114 */

@@ -436,6 +436,17 @@ def styled_bias_act(y, phases, demod, noise_hw, noise_w, bias, act, skip, out_dt
     return out
 
 
+def torgb_fused(x, L, bias, skip=None, skip_up_kernel=None):
+    _launches[0] += 1
+    y = torch.einsum("nhwc,jc->nhwj", x.float(), L.w_tc.float())
+    if bias is not None:
+        y = y + bias
+    if skip is not None:
+        y = y + upfirdn2d(skip, skip_up_kernel, up=2, down=1, pad=(2, 1), out_dtype=torch.float32)
+        _launches[0] -= 1
+    return y.contiguous()
+
+
 def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0), out_dtype=None):
     _launches[0] += 1
     from oracle.ref_import import upfirdn2d_cpu

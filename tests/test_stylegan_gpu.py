@@ -81,6 +81,31 @@ def test_styled_bias_act_vector_path(phases, ydt, n, h, w, c):
             assert (err <= 8e-3 * r_.abs().clamp_min(1.0)).all(), err.max().item()
 
 
+@pytest.mark.parametrize("with_skip", [False, True])
+@pytest.mark.parametrize("n,h,w,cin", [(3, 16, 16, 32), (2, 8, 32, 64), (1, 4, 4, 512), (5, 32, 16, 8), (2, 64, 64, 40)])
+def test_torgb_fused(n, h, w, cin, with_skip):
+    """ToRGB (generator.py:271-292) in one pass: 1x1 conv to the padded RGB channels + bias + Upsample(skip), against the torch restatement
+    (bf16 inputs and weights, fp32 accumulation: only the summation order differs)"""
+    from gen_adversarial_b200 import ops as _ops
+    g = torch.Generator().manual_seed(n + h + cin)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16)
+    L = _ops.ConvLayer(1, 1, 1, 0, cin, 4, name="to_rgb")
+    w4 = torch.zeros(4, cin)
+    w4[:3] = torch.randn(3, cin, generator=g) / cin ** 0.5
+    L.w_tc = w4.to(torch.bfloat16)
+    bias = torch.tensor([0.1, -0.2, 0.3, 0.0])
+    k = torch.tensor([1.0, 3.0, 3.0, 1.0]); k = k[None] * k[:, None]; k = k / k.sum() * 4
+    skip = torch.randn(n, h // 2, w // 2, 4, generator=g) if with_skip else None
+    ref = emu_ops.torgb_fused(x, L, bias, skip, k if with_skip else None)
+    LD = _ops.ConvLayer(1, 1, 1, 0, cin, 4, name="to_rgb")
+    LD.w_tc = L.w_tc.to(DEV)
+    got = _ops.torgb_fused(x.to(DEV), LD, bias.to(DEV), skip.to(DEV) if with_skip else None, k.to(DEV) if with_skip else None)
+    torch.cuda.synchronize()
+    assert got.shape == (n, h, w, 4) and got.dtype == torch.float32
+    assert (got.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    assert (got[..., 3].cpu() - (ref[..., 3])).abs().max().item() <= 1e-6          # the padding channel stays bias + skip
+
+
 @pytest.mark.parametrize("up,down,pad", [(1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (2, 2)), (1, 1, (2, 1))])
 def test_upfirdn2d_matches_reference_semantics(up, down, pad):
     g = torch.Generator().manual_seed(2)
