@@ -29,8 +29,10 @@ constexpr int C3_HDR_BYTES = 1024 + 2048 + 2048 + 4096;   // barriers | bias[<=5
 
 struct C3Params {
   int kc;              // 64-channel blocks of Cin
-  int W, TR;           // image width, rows per tile (TR * W == 256)
-  int tiles_per_img;   // H / TR
+  int W, TR;           // tile width and rows (TR * W == 256): the image width when it is <= 128, 32 x 8 windows of wider images
+  int imgW, imgH;      // image size (global pixel indexing)
+  int xblocks;         // imgW / W
+  int tiles_per_img;   // (H / TR) * xblocks
   int n_mtiles;        // images * tiles_per_img
   int n_tiles;         // n_mtiles * n_blocks
   int stages;          // ring depth
@@ -132,14 +134,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
           }
           continue;
         }
-        const int img = mt / c.tiles_per_img, y0 = (mt - img * c.tiles_per_img) * c.TR;
+        const int img = mt / c.tiles_per_img, rem = mt - img * c.tiles_per_img;
+        const int yb = rem / c.xblocks, y0 = yb * c.TR, x0 = (rem - yb * c.xblocks) * c.W;
         for (int kc = 0; kc < c.kc; ++kc)
           for (int kx = 0; kx < 3; ++kx) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             stamp(0, pit, kc * 3 + kx);
             mbar_expect_tx(&full_bar[stage], c.stage_bytes);
             uint8_t* dst = s_ring + stage * c.stage_bytes;
-            tma_load_4d(&tmA, &full_bar[stage], dst, kc * 64, kx - 1, y0 - 1, img);       // halo box, columns shifted by kx - 1
+            tma_load_4d(&tmA, &full_bar[stage], dst, kc * 64, x0 + kx - 1, y0 - 1, img);  // halo box, columns shifted by kx - 1
             if (!RESIDENT_W) {
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky)
@@ -214,6 +217,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       __syncwarp();
       tc_fence_after();
       if (warp == 2 && lane == 0) stamp(2, it, 1);
+      // global pixel of the first row of this WARP's 32-row slab, minus q * 32 (the epilogues address pix0 + q * 32 + lane): a slab is 32
+      // consecutive pixels of one image row; full-width tiles reduce to mt * 256 + s * 128
+      int64_t pixw0 = (int64_t)mt * 256, pixw_s = 128;
+      if (TAPS == 9) {
+        const int img = mt / c.tiles_per_img, rem = mt - img * c.tiles_per_img;
+        const int yb = rem / c.xblocks, y0 = yb * c.TR, x0 = (rem - yb * c.xblocks) * c.W;
+        const int rpa = 128 / c.W, r = (q * 32) / c.W, col = (q * 32) - r * c.W;
+        pixw0 = ((int64_t)(img * c.imgH + y0 + r) * c.imgW + x0 + col) - q * 32;
+        pixw_s = (int64_t)rpa * c.imgW;
+      }
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
         // this warp's slab of the staging tile is free once its previous bulk stores have read it
@@ -222,13 +235,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         if (warp == 2 && lane == 0) stamp(2, it, 6 + s);
         if (EPI == 0)
           tc_epilogue_lean<BLOCK_N>(p, &tmOutB, &tmOutF, &tmOutD, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
-                                    (int64_t)mt * 256 + s * 128, s_stage, s_bias + n_blk * BLOCK_N, q, lane, s_csum + s * (4 * BLOCK_N));
+                                    pixw0 + s * pixw_s, s_stage, s_bias + n_blk * BLOCK_N, q, lane, s_csum + s * (4 * BLOCK_N));
         else if (EPI == 3)
           tc_epilogue_lean_am<BLOCK_N>(p, &tmOutB, &tmOutF, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
-                                       (int64_t)mt * 256 + s * 128, s_stage, s_bias + n_blk * BLOCK_N, q, lane);
+                                       pixw0 + s * pixw_s, s_stage, s_bias + n_blk * BLOCK_N, q, lane);
         else
           tc_epilogue_tile<BLOCK_N, GENERAL_ACT, true>(p, &tmOutB, &tmOutF, &tmOutD, tmem_base + buf * (2 * BLOCK_N) + s * BLOCK_N, n_blk,
-                                                       (int64_t)mt * 256 + s * 128, 128, s_stage, s_bias + n_blk * BLOCK_N,
+                                                       pixw0 + s * pixw_s, 128, s_stage, s_bias + n_blk * BLOCK_N,
                                                        s_slope + n_blk * BLOCK_N, q, lane);
         if (warp == 2 && lane == 0) stamp(2, it, 2 + s);
       }
@@ -294,11 +307,22 @@ static int launch_c1(bool resident, int epi, const CUtensorMap& a, const CUtenso
 struct C3Plan { C3Params c; int block_n, n_blocks, smem; bool resident; };
 
 // geometry / shared-memory plan of the persistent kernel for one problem; false = shape not covered (the per-tap kernel runs it)
+static int wide_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GA_TC_HALO_WIDE"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 static bool c3_plan(int n, int H, int W, int cin, int cout, bool out_b, bool out_f, bool dact, bool direct, C3Plan* pl) {
   if (g_halo_enabled < 0) { const char* e = getenv("GA_TC_HALO"); g_halo_enabled = e ? atoi(e) : 1; }
   if (!g_halo_enabled) return false;
-  if (cin % 64 != 0 || W % 8 != 0 || W > 128 || 256 % W != 0) return false;
-  const int TR = 256 / W;
+  if (cin % 64 != 0 || W % 8 != 0) return false;
+  // tile = 256 pixels: TR full rows of an image up to 128 wide, or an 8 x 32 window of a wider one (StyleGAN layers at 256^2 .. 1024^2: the same
+  // 40 KB halo boxes and vertical-tap views as a 32 x 32 image, only the box origin and the rows of the output slabs move)
+  int TW, TR;
+  if (W <= 128 && 256 % W == 0) { TW = W; TR = 256 / W; }
+  else if (W % 32 == 0 && wide_enabled()) { TW = 32; TR = 8; }
+  else return false;
   if (TR < 2 || TR > H || H % TR != 0) return false;
   if (cout > 512) return false;
   const int block_n = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
@@ -307,10 +331,10 @@ static bool c3_plan(int n, int H, int W, int cin, int cout, bool out_b, bool out
   if ((out_b || dact) && (cout * 2) % 16 != 0) return false;
   if (out_f && (cout * 4) % 16 != 0) return false;
   C3Params& c = pl->c;
-  c.kc = cin / 64; c.W = W; c.TR = TR; c.tiles_per_img = H / TR;
+  c.kc = cin / 64; c.W = TW; c.TR = TR; c.imgW = W; c.imgH = H; c.xblocks = W / TW; c.tiles_per_img = (H / TR) * c.xblocks;
   c.n_mtiles = n * c.tiles_per_img;
   c.n_tiles = c.n_mtiles * n_blocks;
-  c.a_bytes = (TR + 2) * W * 128;
+  c.a_bytes = (TR + 2) * TW * 128;
   const int b_tile = block_n * 128;
   const int w_bytes = 9 * c.kc * b_tile;
   (void)direct;
@@ -342,7 +366,7 @@ bool conv3x3_halo_csum_ok(const ga_tensor* in, int cout, const TcParams& p, bool
   C3Plan pl;
   if (!lean_enabled() || !out_b || out_f || p.dact || p.add || p.mul || p.post_act != GA_ACT_NONE || p.act_after_add || p.round_tf32) return false;
   if ((in->h * in->w) % 128 != 0) return false;
-  return c3_plan(in->n, in->h, in->w, in->c, cout, true, false, false, true, &pl);
+  return c3_plan(in->n, in->h, in->w, in->c, cout, true, false, false, true, &pl) && pl.c.xblocks == 1;     // (the 128-pixel slices are full-width rows)
 }
 
 int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const ga_tensor* out_bf16, const ga_tensor* out_f32, TcParams p,
@@ -368,7 +392,7 @@ int conv3x3_halo_launch(const ga_tensor* in, const void* weight, int ktot, const
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)in->n};
     cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
-    cuuint32_t box[4] = {64u, (cuuint32_t)W, (cuuint32_t)(TR + 2), 1u};
+    cuuint32_t box[4] = {64u, (cuuint32_t)c.W, (cuuint32_t)(TR + 2), 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (encode_tiled_cached(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->data, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return 1;
@@ -433,7 +457,7 @@ int conv1x1_persistent_launch(const ga_tensor* in, const void* weight, int ktot,
   p.n_blocks = n_blocks;
   C3Params c;
   memset(&c, 0, sizeof(c));
-  c.kc = cin / 64; c.W = 0; c.TR = 0; c.tiles_per_img = 1;
+  c.kc = cin / 64; c.W = 0; c.TR = 0; c.tiles_per_img = 1; c.imgW = 0; c.imgH = 0; c.xblocks = 1;
   c.n_mtiles = (int)((M + 255) / 256);
   c.n_tiles = c.n_mtiles * n_blocks;
   c.a_bytes = 256 * 128;

@@ -144,6 +144,14 @@ HALO_CASES = [
     (5, 16, 16, 128, 128, ACT_NONE, None, 1, (True, False), False),       # VGG backward: times ReLU mask of mul
     (1, 32, 32, 64, 64, ACT_SILU, None, None, (True, False), False),      # fewer tiles than SMs
     (300, 8, 32, 64, 64, ACT_NONE, None, None, (True, False), False),     # H = 8: one tile per image, 300 tiles
+    # images wider than 128 pixels (StyleGAN layers): 8 x 32 windows, the output slabs are row segments of the image
+    (2, 16, 256, 64, 64, ACT_NONE, None, None, (True, False), False),     # 32 windows, resident weights
+    (1, 8, 512, 64, 128, ACT_NONE, None, None, (False, True), False),     # phase conv of an up layer: fp32 conv output, streaming weights
+    (3, 24, 128, 128, 64, ACT_SILU, None, None, (True, True), True),      # W = 128: full-width 2-row tiles, both outputs + tape
+    (2, 24, 384, 128, 64, ACT_SILU, None, None, (True, True), True),      # W = 384: 12 windows per row, both outputs + tape
+    (2, 32, 256, 64, 256, ACT_RELU, "f32", None, (True, False), False),   # two N blocks, + add
+    (1, 64, 256, 128, 128, ACT_NONE, None, 0, (True, False), False),      # times mul
+    (37, 8, 256, 64, 32, ACT_NONE, None, None, (True, False), False),     # 296 windows > 148 CTAs, 32 output channels
 ]
 
 
