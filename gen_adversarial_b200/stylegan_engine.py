@@ -31,8 +31,23 @@ from .fold import Folder
 from .synth import STYLEGAN_CHANNELS
 
 
+def superpixel_weights(w: torch.Tensor) -> torch.Tensor:
+    """3x3 / pad 1 conv weights [cout, cin, 3, 3] -> the weights [2 cout, 2 cin, 3, 3] of the SAME conv evaluated on pairs of horizontally
+    adjacent pixels: an NHWC tensor [h][w][cin] is [h][w/2][2 cin] in memory (channel index = parity * cin + ci), output likewise.
+    W'[(q,co)][ky][dX + 1][(p,ci)] = W[co][ky][2 dX + p - q + 1][ci], zero where the tap index leaves 0..2."""
+    cout, cin = w.shape[0], w.shape[1]
+    w2 = torch.zeros((2 * cout, 2 * cin, 3, 3), dtype=w.dtype)
+    for q in range(2):
+        for p_ in range(2):
+            for dX in (-1, 0, 1):
+                kx = 2 * dX + p_ - q + 1
+                if 0 <= kx < 3:
+                    w2[q * cout:(q + 1) * cout, p_ * cin:(p_ + 1) * cin, :, dX + 1] = w[:, :, :, kx]
+    return w2
+
+
 class _Styled:
-    __slots__ = ("mod", "conv", "phase_convs", "wsq", "noise", "noise_w", "bias", "up", "cin", "cout")
+    __slots__ = ("mod", "conv", "conv_sp", "phase_convs", "wsq", "noise", "noise_w", "bias", "up", "cin", "cout")
 
 
 class _ToRGB:
@@ -90,8 +105,15 @@ class StyleGan2Engine:
         s.mod = self._fold_mod(f, prefix)
         s.wsq = f.dev32((w ** 2).sum(dim=(2, 3)))                                                   # [cout, cin]
         s.conv, s.phase_convs = None, None
+        s.conv_sp = None
         if not up:
             s.conv = f.conv(w, None, pad=1, name=prefix + ".conv")
+            if self.bf16 and cin == 32 and cout % 4 == 0 and self.superpixel:
+                # 32-channel layers (1024^2): the same conv on PAIRS of horizontally adjacent pixels -- [h][w][32] is [h][w/2][64] in memory --
+                # with 64 -> 2*cout channels and block-sparse weights W'[(q,co)][ky][dX][(p,ci)] = W[co][ky][2 dX + p - q + 1][ci]
+                # (zero outside 0..2).  Twice the multiply-adds, but 64-channel K blocks take the layer from the per-tap kernel
+                # (1.3 TB/s, 186 TFLOP/s: bound by neither) to the persistent halo kernel.
+                s.conv_sp = f.conv(superpixel_weights(w), None, pad=1, name=prefix + ".conv.superpixel", simt=False)
         else:
             kb = f.f64(f"{prefix}.conv.blur.kernel")                                                # 4x4, already x4
             G = torch.zeros((cout, cin, 6, 6), dtype=torch.float64)                                 # index d+2, d in [-2, 3]
@@ -176,7 +198,10 @@ class StyleGan2Engine:
         b, h, w, _ = xs.shape
         f32 = self.bf16 and h * (2 if s.up else 1) <= self.f32_conv_out_res
         if not s.up:
-            y = self._conv(xs, s.conv, want_f32=f32)
+            if s.conv_sp is not None and not f32 and xs.dtype == torch.bfloat16 and w % 2 == 0 and xs.is_contiguous():
+                y = self._conv(xs.view(b, h, w // 2, 2 * s.cin), s.conv_sp).view(b, h, w, s.cout)
+            else:
+                y = self._conv(xs, s.conv, want_f32=f32)
             phases = False
         else:
             y = self._conv(xs, s.phase_convs, want_f32=f32)              # [b, h, w, 4 * cout]
@@ -225,6 +250,7 @@ class StyleGan2Engine:
         self._run_blocks(j + 1, x, skip, st, lo, sink, outs)
 
     max_chunk = None
+    superpixel = __import__("os").environ.get("GA_SG_SUPERPIXEL", "1") != "0"
     f32_conv_out_res = int(__import__("os").environ.get("GA_SG_F32_RES", "128"))
 
     def synthesis(self, latent: torch.Tensor, sink=None):

@@ -61,3 +61,18 @@ def test_generator_matches_reference_fixture(emu):
     img = eng.decode(g["latent"], pool=2)
     scale = g["image_pool2"].abs().max().item()
     assert (img - g["image_pool2"]).abs().max().item() <= 2e-4 * scale
+
+
+def test_superpixel_weights_are_the_same_convolution():
+    """stylegan_engine.superpixel_weights: a 3x3 conv on [h][w][c] equals the transformed conv on the [h][w/2][2c] view (exact in fp64)"""
+    import torch
+    import torch.nn.functional as F
+    from gen_adversarial_b200.stylegan_engine import superpixel_weights
+    g = torch.Generator().manual_seed(0)
+    for cin, cout, h, w in ((4, 6, 5, 8), (32, 32, 6, 12), (3, 2, 4, 2)):
+        wt = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64)
+        x = torch.randn(2, h, w, cin, generator=g, dtype=torch.float64)                      # NHWC
+        ref = F.conv2d(x.permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)              # [n, h, w, cout]
+        xs = x.reshape(2, h, w // 2, 2 * cin)
+        got = F.conv2d(xs.permute(0, 3, 1, 2), superpixel_weights(wt), padding=1).permute(0, 2, 3, 1).reshape(2, h, w, cout)
+        assert (got - ref).abs().max().item() <= 1e-12
