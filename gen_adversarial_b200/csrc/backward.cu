@@ -72,6 +72,22 @@ __global__ void add_kernel(const void* a, int a_dtype, const void* b, int b_dtyp
   st1b(out, out_dtype, i, ld1b(a, a_dtype, i) + ld1b(b, b_dtype, i));
 }
 
+// fp32 + fp32 -> fp32 with 16-byte vectors, 4 per thread (the gradient accumulations of the attack path: stash / skip joins)
+__global__ void __launch_bounds__(256) add_f32x4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, int64_t total4) {
+  const int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  float4 va[4], vb[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = i0 + u * 256;
+    if (i < total4) { va[u] = __ldg(a + i); vb[u] = __ldg(b + i); }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = i0 + u * 256;
+    if (i < total4) out[i] = make_float4(va[u].x + vb[u].x, va[u].y + vb[u].y, va[u].z + vb[u].z, va[u].w + vb[u].w);
+  }
+}
+
 // ---------------------------------------------------------------------------- SE + residual backward
 // forward: out = skip + s * gate[n,c] * r ;  gate = sigmoid(W2 relu(W1 mean(r) + b1) + b2)
 // stage 1: dots[n][blk][c] = sum over the block's pixel slice of g_out * r
@@ -701,6 +717,13 @@ extern "C" int ga_add(const ga_tensor* a, const ga_tensor* b, const ga_tensor* o
   GA_CHECK(a && b && out && same_shape(a, b) && same_shape(a, out), "ga_add: shape mismatch");
   const int64_t total = numel(a);
   if (total == 0) return 0;
+  if (a->dtype == GA_F32 && b->dtype == GA_F32 && out->dtype == GA_F32 && (total & 3) == 0 &&
+      ((((uintptr_t)a->data) | ((uintptr_t)b->data) | ((uintptr_t)out->data)) & 15) == 0) {
+    add_f32x4_kernel<<<(unsigned)cdiv(total / 4, 1024), 256, 0, (cudaStream_t)stream>>>((const float4*)a->data, (const float4*)b->data,
+                                                                                         (float4*)out->data, total / 4);
+    GA_LAUNCH_OK();
+    return 0;
+  }
   add_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(a->data, a->dtype, b->data, b->dtype, out->data, out->dtype, total);
   GA_LAUNCH_OK();
   return 0;
